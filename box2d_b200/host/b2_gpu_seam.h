@@ -1,0 +1,51 @@
+/*
+ * b2_gpu_seam.h -- host side of the drop-in boundary (C17, compiled INTO the reference's library).
+ *
+ * The reference has no plugin API for its solver; the boundary is the internal seam inside b2Solve
+ * between "Solver Setup" and "Update Transforms" (reference src/solver.c:1560-1616).  The generated
+ * solver.c (tools/patch_solver.py --mode gpu) calls b2GpuSeam_SolveConstraints where the reference
+ * enqueues its b2SolverTask workers (src/solver.c:1563-1605).  Everything else in b2Solve -- setup,
+ * island split, finalize, events, refit, bullets, sleep -- is the reference's own code, unchanged.
+ */
+#pragma once
+
+#include "b2_gpu_solver.h"
+
+typedef struct b2World b2World;
+typedef struct b2StepContext b2StepContext;
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+/* Fill the C-ABI step descriptor from the reference's world + step context.  Joint sims must already be
+ * prepared (b2PrepareJoint, src/joint.c:1406).  Shared by the product seam and the oracle's capture hook. */
+void b2GpuSeam_BuildDesc( b2World* world, b2StepContext* stepContext, b2GpuStepDesc* desc );
+
+/* Prepare every awake joint on the host (b2ParallelFor over the flat joint range + the overflow colour),
+ * i.e. the b2_stagePrepareJoints stage and b2PrepareJoints_Overflow (src/solver.c:1060-1077). */
+void b2GpuSeam_PrepareJoints( b2World* world, b2StepContext* stepContext );
+
+/* The seam itself: host joint prepare -> b2GpuSolverStep -> event bits + b2Profile.  Aborts (B2_ASSERT-style)
+ * if the device solver fails: there is no CPU fallback. */
+void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* stepContext );
+
+/* Route the reference's allocations through page-locked memory (b2SetAllocator, include/box2d/base.h:86).
+ * Call before creating any world. */
+void b2GpuSeam_InstallPinnedAllocator( void );
+
+/* Last step's device-side result for a world id slot (for benchmarks / tests). */
+const b2GpuStepResult* b2GpuSeam_GetLastResult( int worldIndex );
+const b2GpuStepDesc* b2GpuSeam_GetLastDesc( int worldIndex );
+
+/* 0 = persistent cooperative kernel, 1 = one launch per stage.  Applies to solvers created afterwards and
+ * to existing ones. */
+void b2GpuSeam_SetMode( int mode );
+
+/* Destroy all device solvers created by the seam. */
+void b2GpuSeam_Shutdown( void );
+
+#ifdef __cplusplus
+}
+#endif

@@ -1,0 +1,191 @@
+/*
+ * b2_gpu_solver.h -- C-ABI of the B200-native Soft Step constraint solver.
+ *
+ * This is the drop-in boundary for ONE hot path of Box2D v3.2: the region of b2Solve between
+ * "Solver Setup" and "Update Transforms" (reference src/solver.c:1560-1616), i.e. everything
+ * b2SolverTask (src/solver.c:1010-1198) runs over the constraint-graph colours.  The reference has
+ * no FFI for this path (it is an internal seam); the entry points below are what
+ * a maintainer's solver.c would call instead of enqueueing b2SolverTask workers.  INTEGRATION.md
+ * shows the reference-side patch.
+ *
+ * Conventions
+ *  - plain C, plain pointers and sizes; all pointers in b2GpuStepDesc are HOST pointers that are only
+ *    valid for the duration of the call (the reference may reallocate/reorder its arrays between
+ *    steps: src/constraint_graph.c:198-211).
+ *  - the arrays are the reference's own structures, bit for bit (release build, float precision):
+ *        b2BodyState  32 B  src/body.h:153-168
+ *        b2BodySim    96 B  src/body.h:175-208
+ *        b2ContactSim 200 B src/contact.h:103-142  (b2Manifold include/box2d/collision.h:572-586)
+ *        b2JointSim   252 B src/joint.h:267-301    (already prepared on the host by b2PrepareJoint,
+ *                                                   src/joint.c:1406)
+ *    The byte offsets this library relies on are listed in b2gpu_layout.h and static-asserted against
+ *    the reference headers when the host seam is compiled (box2d_b200/host/b2_gpu_seam.c).
+ *  - every function returns 0 on success, non-zero on failure; b2GpuGetLastError() gives the text.
+ *    There is NO CPU fallback: if CUDA is unavailable the create call fails.
+ */
+#ifndef B2_GPU_SOLVER_H
+#define B2_GPU_SOLVER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#if defined( _WIN32 )
+#define B2GPU_API __declspec( dllexport )
+#else
+#define B2GPU_API __attribute__( ( visibility( "default" ) ) )
+#endif
+
+#define B2GPU_GRAPH_COLOR_COUNT 24 /* include/box2d/constants.h:29 B2_GRAPH_COLOR_COUNT */
+#define B2GPU_MAX_ACTIVE_COLORS ( B2GPU_GRAPH_COLOR_COUNT - 1 )
+
+/* b2Softness, src/solver.h:127-132 */
+typedef struct b2GpuSoftness
+{
+	float biasRate;
+	float massScale;
+	float impulseScale;
+} b2GpuSoftness;
+
+/* One graph colour as the solver sees it: colors[i].contactSims / colors[i].jointSims
+ * (src/constraint_graph.h:26-48). */
+typedef struct b2GpuColorDesc
+{
+	void* contactSims; /* b2ContactSim[contactCount], in: manifold+material, out: manifold impulses */
+	void* jointSims;   /* b2JointSim[jointCount], prepared; in/out (accumulated impulses live in place) */
+	int contactCount;
+	int jointCount;
+	int colorIndex; /* index into b2ConstraintGraph::colors, informational */
+	int reserved;
+} b2GpuColorDesc;
+
+/* Everything b2SolverTask reads from b2StepContext (src/solver.h:155-237) and b2World
+ * (src/physics_world.h:162-216). */
+typedef struct b2GpuStepDesc
+{
+	/* b2StepContext scalars, filled by b2World_Step (src/physics_world.c:907-935) */
+	float dt;
+	float inv_dt;
+	float h;
+	float inv_h;
+	int subStepCount;
+	b2GpuSoftness contactSoftness;
+	b2GpuSoftness staticSoftness;
+	float restitutionThreshold;
+	float maxLinearVelocity;
+
+	/* b2World fields read inside the stages */
+	float gravity[2];
+	float contactSpeed;
+	float contactHertz;
+	float contactDampingRatio;
+	float hitEventThreshold;
+	float lengthUnitsPerMeter; /* b2GetLengthUnitsPerMeter(), read by src/prismatic_joint.c:513,560 */
+	int enableWarmStarting;
+	int enableContactSoftening;
+
+	/* awake solver set (src/solver.c:1300-1301) */
+	void* states;     /* b2BodyState[awakeBodyCount], in/out */
+	const void* sims; /* b2BodySim[awakeBodyCount], in */
+	int awakeBodyCount;
+
+	/* active colours in ascending colour index (src/solver.c:1341-1367), then the overflow colour
+	 * colors[B2_OVERFLOW_INDEX] (src/constraint_graph.h:20) */
+	int activeColorCount;
+	b2GpuColorDesc colors[B2GPU_MAX_ACTIVE_COLORS];
+	b2GpuColorDesc overflow;
+
+	/* bit-set sizing (src/solver.c:1563-1564) */
+	int contactIdCapacity;
+	int jointIdCapacity;
+} b2GpuStepDesc;
+
+/* Index of each per-stage timer, same split as b2Profile (include/box2d/types.h:526-551) filled by the
+ * orchestrator at src/solver.c:1080,1097,1112,1132,1141,1159,1182,1191. */
+enum
+{
+	b2GpuStage_prepareConstraints = 0,
+	b2GpuStage_integrateVelocities = 1,
+	b2GpuStage_warmStart = 2,
+	b2GpuStage_solveImpulses = 3,
+	b2GpuStage_integratePositions = 4,
+	b2GpuStage_relaxImpulses = 5,
+	b2GpuStage_applyRestitution = 6,
+	b2GpuStage_storeImpulses = 7,
+	b2GpuStage_count = 8
+};
+
+typedef struct b2GpuStepResult
+{
+	/* Caller-provided bit sets, b2BitSet::bits layout (src/bitset.h): bit i of word i/64.  Sized for
+	 * contactIdCapacity / jointIdCapacity bits rounded up to 64.  The library ORs into them.  May be
+	 * NULL when the corresponding capacity is 0. */
+	uint64_t* hitEventBits;   /* src/contact_solver.c:2305-2320 */
+	uint64_t* jointEventBits; /* src/joint.c:1663-1675 */
+	int hasHitEvents;
+
+	/* device time per stage group in milliseconds (CUDA globaltimer inside the step kernel) */
+	float stageMs[b2GpuStage_count];
+	float kernelMs;     /* CUDA-event time of all kernels of the step */
+	float totalMs;      /* host wall time of the whole call, copies included */
+	uint64_t h2dBytes;  /* bytes copied host -> device during the call */
+	uint64_t d2hBytes;  /* bytes copied device -> host during the call */
+	int kernelLaunches; /* kernels launched by the call */
+	int gridBarriers;   /* grid-wide barriers executed inside the step kernel */
+} b2GpuStepResult;
+
+typedef struct b2GpuSolver b2GpuSolver;
+
+/* Create a solver bound to one CUDA device; owns a stream and geometrically grown device buffers.  One
+ * solver per world (different worlds may step concurrently, include/box2d/box2d.h:31-32).  Returns NULL on
+ * failure (no device, no driver): there is no CPU fallback. */
+B2GPU_API b2GpuSolver* b2GpuSolverCreate( int device );
+B2GPU_API void b2GpuSolverDestroy( b2GpuSolver* solver );
+
+/* The whole hot path for one world step: upload, all stages of src/solver.c:1055-1197 on the device,
+ * download.  Replaces the worker enqueue + b2SolverTask at src/solver.c:1563-1605.  Synchronous. */
+B2GPU_API int b2GpuSolverStep( b2GpuSolver* solver, const b2GpuStepDesc* desc, b2GpuStepResult* result );
+
+/* The same step split in three so a benchmark can time the device part with inputs resident in HBM:
+ * Upload copies the inputs, Run executes all stages from the resident inputs (it does not modify them, so
+ * it can be repeated), Download copies the outputs of the last Run back into the desc's host arrays. */
+B2GPU_API int b2GpuSolverUpload( b2GpuSolver* solver, const b2GpuStepDesc* desc );
+B2GPU_API int b2GpuSolverRun( b2GpuSolver* solver, b2GpuStepResult* result );
+B2GPU_API int b2GpuSolverDownload( b2GpuSolver* solver, const b2GpuStepDesc* desc, b2GpuStepResult* result );
+
+/* Batch of independent worlds (the RL-style workload): one launch solves all of them, one thread block
+ * per world with the world's bodies and constraints resident in shared memory for all sub-steps.  Each
+ * desc is a complete, independent world step.  Worlds that do not fit the per-block budget are solved
+ * one after the other with the single-world kernel. */
+B2GPU_API int b2GpuSolverUploadBatch( b2GpuSolver* solver, const b2GpuStepDesc* descs, int worldCount );
+B2GPU_API int b2GpuSolverRunBatch( b2GpuSolver* solver, b2GpuStepResult* result );
+B2GPU_API int b2GpuSolverDownloadBatch( b2GpuSolver* solver, const b2GpuStepDesc* descs, int worldCount,
+										 b2GpuStepResult* results );
+B2GPU_API int b2GpuSolverStepBatch( b2GpuSolver* solver, const b2GpuStepDesc* descs, int worldCount,
+									 b2GpuStepResult* results );
+
+/* Execution mode knobs (for tests and profiling).  mode 0 = one persistent cooperative kernel per step
+ * (default), mode 1 = one kernel launch per stage (same device functions, stream ordered). */
+B2GPU_API int b2GpuSolverSetMode( b2GpuSolver* solver, int mode );
+
+/* Page-locked host memory for the reference's own arrays, to be installed with b2SetAllocator
+ * (include/box2d/base.h:86) so uploads are true DMA.  Signatures match b2AllocFcn / b2FreeFcn. */
+B2GPU_API void* b2GpuHostAlloc( size_t size, int alignment );
+B2GPU_API void b2GpuHostFree( void* mem, size_t size );
+
+/* Diagnostics */
+B2GPU_API const char* b2GpuGetLastError( void );
+B2GPU_API int b2GpuGetDeviceCount( void );
+B2GPU_API int b2GpuGetVersion( void );
+/* Totals since creation */
+B2GPU_API uint64_t b2GpuSolverGetLaunchCount( const b2GpuSolver* solver );
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* B2_GPU_SOLVER_H */

@@ -1,0 +1,22 @@
+#!/usr/bin/env python3
+"""Recipe for oracle/_ref/: compile the UNTOUCHED reference (where it lies under /root/reference) with gcc into
+shared libraries the tests and bench.py's cpu_baseline / --impl reference arm load.  Test infrastructure only.
+
+    python oracle/build_ref.py            # libbox2d_ref.so, libbox2d_refcap.so (+ liboracle.so, the C restatement)
+"""
+import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from tools import buildlib  # noqa: E402
+
+
+def main() -> int:
+	libs = buildlib.build_reference_libs(verbose=True)
+	for name, path in libs.items():
+		print(name, path)
+	return 0
+
+
+if __name__ == "__main__":
+	sys.exit(main())
