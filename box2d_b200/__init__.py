@@ -1,0 +1,399 @@
+"""box2d_b200 -- a B200-native Soft Step constraint solver behind Box2D's own host code.
+
+The product is native: ``libb2gpusolver.so`` (hand-written sm_100a CUDA kernels + the C-ABI declared in
+``include/b2_gpu_solver.h``) and ``libbox2d_b200.so`` (the reference's C17 host with the solve region of
+``b2Solve`` replaced by the seam in ``box2d_b200/host``).  This package is only the thin Python mirror of
+that C-ABI used by the tests and ``bench.py``: ctypes structures with the header's exact layout, loaders that
+fail loudly when a library is missing (there is NO CPU fallback), and a reader for the oracle's capture files.
+"""
+from __future__ import annotations
+
+import ctypes
+import gzip
+import os
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+ROOT = PKG_DIR.parent
+
+GRAPH_COLOR_COUNT = 24
+MAX_ACTIVE_COLORS = GRAPH_COLOR_COUNT - 1
+STAGE_NAMES = (
+	"prepareConstraints", "integrateVelocities", "warmStart", "solveImpulses",
+	"integratePositions", "relaxImpulses", "applyRestitution", "storeImpulses",
+)
+
+STATE_SIZE = 32
+SIM_SIZE = 96
+CONTACT_SIZE = 200
+JOINT_SIZE = 252
+
+
+# ---- include/b2_gpu_solver.h ---------------------------------------------------------------------------------
+class Softness(ctypes.Structure):
+	_fields_ = [("biasRate", ctypes.c_float), ("massScale", ctypes.c_float), ("impulseScale", ctypes.c_float)]
+
+
+class ColorDesc(ctypes.Structure):
+	_fields_ = [
+		("contactSims", ctypes.c_void_p),
+		("jointSims", ctypes.c_void_p),
+		("contactCount", ctypes.c_int),
+		("jointCount", ctypes.c_int),
+		("colorIndex", ctypes.c_int),
+		("reserved", ctypes.c_int),
+	]
+
+
+class StepDesc(ctypes.Structure):
+	_fields_ = [
+		("dt", ctypes.c_float), ("inv_dt", ctypes.c_float), ("h", ctypes.c_float), ("inv_h", ctypes.c_float),
+		("subStepCount", ctypes.c_int),
+		("contactSoftness", Softness), ("staticSoftness", Softness),
+		("restitutionThreshold", ctypes.c_float), ("maxLinearVelocity", ctypes.c_float),
+		("gravity", ctypes.c_float * 2),
+		("contactSpeed", ctypes.c_float), ("contactHertz", ctypes.c_float), ("contactDampingRatio", ctypes.c_float),
+		("hitEventThreshold", ctypes.c_float), ("lengthUnitsPerMeter", ctypes.c_float),
+		("enableWarmStarting", ctypes.c_int), ("enableContactSoftening", ctypes.c_int),
+		("states", ctypes.c_void_p), ("sims", ctypes.c_void_p), ("awakeBodyCount", ctypes.c_int),
+		("activeColorCount", ctypes.c_int),
+		("colors", ColorDesc * MAX_ACTIVE_COLORS),
+		("overflow", ColorDesc),
+		("contactIdCapacity", ctypes.c_int), ("jointIdCapacity", ctypes.c_int),
+	]
+
+
+class StepResult(ctypes.Structure):
+	_fields_ = [
+		("hitEventBits", ctypes.c_void_p),
+		("jointEventBits", ctypes.c_void_p),
+		("hasHitEvents", ctypes.c_int),
+		("stageMs", ctypes.c_float * 8),
+		("kernelMs", ctypes.c_float),
+		("totalMs", ctypes.c_float),
+		("h2dBytes", ctypes.c_uint64),
+		("d2hBytes", ctypes.c_uint64),
+		("kernelLaunches", ctypes.c_int),
+		("gridBarriers", ctypes.c_int),
+	]
+
+
+class NativeLibraryMissing(RuntimeError):
+	pass
+
+
+def _load(path: Path, what: str) -> ctypes.CDLL:
+	if not path.is_file():
+		raise NativeLibraryMissing(
+			f"{what} not found at {path}: run `python -c 'import __graft_entry__ as g; g.build()'` "
+			"(the solver is native CUDA; there is no Python or CPU fallback)"
+		)
+	return ctypes.CDLL(str(path), mode=os.RTLD_LOCAL | os.RTLD_NOW)
+
+
+_solver_lib = None
+_host_lib = None
+
+
+def solver_lib() -> ctypes.CDLL:
+	"""libb2gpusolver.so with the C-ABI prototypes of include/b2_gpu_solver.h bound."""
+	global _solver_lib
+	if _solver_lib is not None:
+		return _solver_lib
+	lib = _load(PKG_DIR / "libb2gpusolver.so", "CUDA solver library")
+	P = ctypes.POINTER
+	lib.b2GpuSolverCreate.restype = ctypes.c_void_p
+	lib.b2GpuSolverCreate.argtypes = [ctypes.c_int]
+	lib.b2GpuSolverDestroy.restype = None
+	lib.b2GpuSolverDestroy.argtypes = [ctypes.c_void_p]
+	for name in ("b2GpuSolverStep", "b2GpuSolverDownload"):
+		fn = getattr(lib, name)
+		fn.restype = ctypes.c_int
+		fn.argtypes = [ctypes.c_void_p, P(StepDesc), P(StepResult)]
+	lib.b2GpuSolverUpload.restype = ctypes.c_int
+	lib.b2GpuSolverUpload.argtypes = [ctypes.c_void_p, P(StepDesc)]
+	lib.b2GpuSolverRun.restype = ctypes.c_int
+	lib.b2GpuSolverRun.argtypes = [ctypes.c_void_p, P(StepResult)]
+	lib.b2GpuSolverUploadBatch.restype = ctypes.c_int
+	lib.b2GpuSolverUploadBatch.argtypes = [ctypes.c_void_p, P(StepDesc), ctypes.c_int]
+	lib.b2GpuSolverRunBatch.restype = ctypes.c_int
+	lib.b2GpuSolverRunBatch.argtypes = [ctypes.c_void_p, P(StepResult)]
+	for name in ("b2GpuSolverDownloadBatch", "b2GpuSolverStepBatch"):
+		fn = getattr(lib, name)
+		fn.restype = ctypes.c_int
+		fn.argtypes = [ctypes.c_void_p, P(StepDesc), ctypes.c_int, P(StepResult)]
+	lib.b2GpuSolverSetMode.restype = ctypes.c_int
+	lib.b2GpuSolverSetMode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+	lib.b2GpuHostAlloc.restype = ctypes.c_void_p
+	lib.b2GpuHostAlloc.argtypes = [ctypes.c_size_t, ctypes.c_int]
+	lib.b2GpuHostFree.restype = None
+	lib.b2GpuHostFree.argtypes = [ctypes.c_void_p, ctypes.c_size_t]
+	lib.b2GpuGetLastError.restype = ctypes.c_char_p
+	lib.b2GpuGetDeviceCount.restype = ctypes.c_int
+	lib.b2GpuGetVersion.restype = ctypes.c_int
+	lib.b2GpuSolverGetLaunchCount.restype = ctypes.c_uint64
+	lib.b2GpuSolverGetLaunchCount.argtypes = [ctypes.c_void_p]
+	_solver_lib = lib
+	return lib
+
+
+def _bind_harness(lib: ctypes.CDLL) -> ctypes.CDLL:
+	"""Prototypes of oracle/harness/b2h_harness.c (linked into every host library variant)."""
+	lib.b2h_create.restype = ctypes.c_int
+	lib.b2h_create.argtypes = [ctypes.c_char_p, ctypes.c_int]
+	lib.b2h_destroy.argtypes = [ctypes.c_int]
+	lib.b2h_step.argtypes = [ctypes.c_int, ctypes.c_int]
+	lib.b2h_set_substeps.argtypes = [ctypes.c_int, ctypes.c_int]
+	lib.b2h_hash.restype = ctypes.c_uint64
+	lib.b2h_hash.argtypes = [ctypes.c_int]
+	lib.b2h_world_index.restype = ctypes.c_int
+	lib.b2h_world_index.argtypes = [ctypes.c_int]
+	lib.b2h_hinges_result.restype = ctypes.c_int
+	lib.b2h_hinges_result.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_uint32)]
+	lib.b2h_profile.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float)]
+	lib.b2h_profile_float_count.restype = ctypes.c_int
+	lib.b2h_counters.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+	lib.b2h_event_counts.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+	lib.b2h_move_transforms.restype = ctypes.c_int
+	lib.b2h_move_transforms.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+	lib.b2h_move_velocities.restype = ctypes.c_int
+	lib.b2h_move_velocities.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
+	lib.b2h_bench.restype = ctypes.c_float
+	lib.b2h_bench.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
+							  ctypes.POINTER(ctypes.c_float)]
+	lib.b2h_version.restype = ctypes.c_int
+	return lib
+
+
+def host_lib() -> ctypes.CDLL:
+	"""libbox2d_b200.so: the reference's host code + seam; b2World_Step solves on the GPU (no CPU solver path)."""
+	global _host_lib
+	if _host_lib is not None:
+		return _host_lib
+	solver_lib()  # dependency, resolved through $ORIGIN rpath as well
+	lib = _bind_harness(_load(PKG_DIR / "libbox2d_b200.so", "GPU host library"))
+	lib.b2GpuSeam_SetMode.argtypes = [ctypes.c_int]
+	lib.b2GpuSeam_GetLastResult.restype = ctypes.POINTER(StepResult)
+	lib.b2GpuSeam_GetLastResult.argtypes = [ctypes.c_int]
+	lib.b2GpuSeam_GetLastDesc.restype = ctypes.POINTER(StepDesc)
+	lib.b2GpuSeam_GetLastDesc.argtypes = [ctypes.c_int]
+	lib.b2GpuSeam_InstallPinnedAllocator.restype = None
+	lib.b2GpuSeam_Shutdown.restype = None
+	_host_lib = lib
+	return lib
+
+
+class World:
+	"""A scene in one of the host libraries (reference or GPU), driven through the b2h_* harness."""
+
+	def __init__(self, lib: ctypes.CDLL, scene: str, workers: int = 1):
+		self.lib = lib
+		self.handle = lib.b2h_create(scene.encode(), workers)
+		if self.handle < 0:
+			raise ValueError(f"unknown scene {scene!r} or no free world slot ({self.handle})")
+
+	def step(self, n: int = 1) -> None:
+		self.lib.b2h_step(self.handle, n)
+
+	def hash(self) -> int:
+		return int(self.lib.b2h_hash(self.handle))
+
+	def counters(self) -> dict:
+		out = (ctypes.c_int * 30)()
+		self.lib.b2h_counters(self.handle, out)
+		keys = ("bodyCount", "shapeCount", "contactCount", "jointCount", "islandCount", "awakeBodyCount")
+		d = dict(zip(keys, out[:6]))
+		d["colorCounts"] = list(out[6:30])
+		return d
+
+	def events(self) -> dict:
+		out = (ctypes.c_int * 5)()
+		self.lib.b2h_event_counts(self.handle, out)
+		return dict(zip(("move", "begin", "end", "hit", "joint"), out))
+
+	def profile(self) -> dict:
+		n = self.lib.b2h_profile_float_count()
+		out = (ctypes.c_float * n)()
+		self.lib.b2h_profile(self.handle, out)
+		names = ("step", "pairs", "collide", "solve", "solverSetup", "constraints", "prepareConstraints",
+				 "integrateVelocities", "warmStart", "solveImpulses", "integratePositions", "relaxImpulses",
+				 "applyRestitution", "storeImpulses", "splitIslands", "transforms", "sensorHits", "jointEvents",
+				 "hitEvents", "refit", "bullets", "sleepIslands", "sensors")
+		return dict(zip(names, out))
+
+	def transforms(self, max_bodies: int = 1 << 20) -> np.ndarray:
+		buf = np.zeros((max_bodies, 4), dtype=np.float32)
+		n = self.lib.b2h_move_transforms(self.handle, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), max_bodies)
+		return buf[:n].copy()
+
+	def velocities(self, max_bodies: int = 1 << 20) -> np.ndarray:
+		buf = np.zeros((max_bodies, 3), dtype=np.float32)
+		n = self.lib.b2h_move_velocities(self.handle, buf.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), max_bodies)
+		return buf[:n].copy()
+
+	def bench(self, steps: int) -> dict:
+		c = ctypes.c_float()
+		s = ctypes.c_float()
+		stages = (ctypes.c_float * 8)()
+		total = self.lib.b2h_bench(self.handle, steps, ctypes.byref(c), ctypes.byref(s), stages)
+		return {"wall_ms": float(total), "constraints_ms": float(c.value), "step_ms": float(s.value),
+				"stages_ms": dict(zip(STAGE_NAMES, stages))}
+
+	def hinges_result(self):
+		sleep_step = ctypes.c_int()
+		h = ctypes.c_uint32()
+		done = self.lib.b2h_hinges_result(self.handle, ctypes.byref(sleep_step), ctypes.byref(h))
+		return done, sleep_step.value, h.value
+
+	def world_index(self) -> int:
+		return self.lib.b2h_world_index(self.handle)
+
+	def destroy(self) -> None:
+		if self.handle >= 0:
+			self.lib.b2h_destroy(self.handle)
+			self.handle = -1
+
+	def __enter__(self):
+		return self
+
+	def __exit__(self, *exc):
+		self.destroy()
+
+
+# ---- capture files (oracle/harness/b2h_capture.c, format B2CAP002) ----------------------------------------------
+class Capture:
+	"""One captured solver step: the C-ABI inputs and the reference CPU solver's outputs."""
+
+	def __init__(self, path):
+		path = Path(path)
+		raw = gzip.open(path, "rb").read() if path.suffix == ".gz" else path.read_bytes()
+		if raw[:8] != b"B2CAP002":
+			raise ValueError(f"{path}: not a B2CAP002 capture")
+		desc_bytes = int.from_bytes(raw[8:12], "little")
+		if desc_bytes != ctypes.sizeof(StepDesc):
+			raise ValueError(f"{path}: descriptor size {desc_bytes} != {ctypes.sizeof(StepDesc)}")
+		self.desc = StepDesc.from_buffer_copy(raw[12:12 + desc_bytes])
+		self._pos = 12 + desc_bytes
+		self._raw = raw
+		d = self.desc
+		n = d.awakeBodyCount
+		colors = [d.colors[c] for c in range(d.activeColorCount)] + [d.overflow]
+		self.color_counts = [(c.contactCount, c.jointCount) for c in colors]
+
+		self.states_in = self._take(n * STATE_SIZE)
+		self.sims = self._take(n * SIM_SIZE)
+		self.contacts_in, self.joints_in = [], []
+		for cc, jc in self.color_counts:
+			self.contacts_in.append(self._take(cc * CONTACT_SIZE))
+			self.joints_in.append(self._take(jc * JOINT_SIZE))
+		self.states_out = self._take(n * STATE_SIZE)
+		self.contacts_out, self.joints_out = [], []
+		for cc, jc in self.color_counts:
+			self.contacts_out.append(self._take(cc * CONTACT_SIZE))
+			self.joints_out.append(self._take(jc * JOINT_SIZE))
+		hit_words = int.from_bytes(self._take(4).tobytes(), "little")
+		self.hit_bits = self._take(hit_words * 8).view(np.uint64).copy()
+		joint_words = int.from_bytes(self._take(4).tobytes(), "little")
+		self.joint_bits = self._take(joint_words * 8).view(np.uint64).copy()
+		self.has_hit_events = int.from_bytes(self._take(4).tobytes(), "little")
+		del self._raw
+
+	def _take(self, nbytes: int) -> np.ndarray:
+		a = np.frombuffer(self._raw, dtype=np.uint8, count=nbytes, offset=self._pos).copy()
+		self._pos += nbytes
+		return a
+
+	@property
+	def body_count(self) -> int:
+		return self.desc.awakeBodyCount
+
+	@property
+	def contact_count(self) -> int:
+		return sum(c for c, _ in self.color_counts)
+
+	@property
+	def joint_count(self) -> int:
+		return sum(j for _, j in self.color_counts)
+
+	def make_call(self):
+		"""Fresh, writable copies of the inputs wired into a StepDesc + StepResult (the arrays must outlive the call)."""
+		d = StepDesc.from_buffer_copy(bytes(self.desc))
+		bufs = {
+			"states": self.states_in.copy(),
+			"sims": self.sims.copy(),
+			"contacts": [a.copy() for a in self.contacts_in],
+			"joints": [a.copy() for a in self.joints_in],
+			"hit": np.zeros(max(1, (d.contactIdCapacity + 63) // 64), dtype=np.uint64),
+			"joint": np.zeros(max(1, (d.jointIdCapacity + 63) // 64), dtype=np.uint64),
+		}
+		d.states = bufs["states"].ctypes.data
+		d.sims = bufs["sims"].ctypes.data
+		for i in range(d.activeColorCount + 1):
+			cd = d.colors[i] if i < d.activeColorCount else d.overflow
+			cd.contactSims = bufs["contacts"][i].ctypes.data if bufs["contacts"][i].size else None
+			cd.jointSims = bufs["joints"][i].ctypes.data if bufs["joints"][i].size else None
+		r = StepResult()
+		r.hitEventBits = bufs["hit"].ctypes.data
+		r.jointEventBits = bufs["joint"].ctypes.data
+		return d, r, bufs
+
+
+# byte ranges of b2ContactSim that the solver writes (include/b2gpu_layout.h): manifold.rollingImpulse and, per
+# point, normalImpulse, tangentImpulse, totalNormalImpulse, normalVelocity
+def contact_output_view(contacts: np.ndarray) -> np.ndarray:
+	"""[n, 9] float32 view of the solver-written fields of a b2ContactSim byte array."""
+	n = contacts.size // CONTACT_SIZE
+	c = contacts.reshape(n, CONTACT_SIZE)
+	man = 68
+	cols = [c[:, man + 8:man + 12]]
+	for j in range(2):
+		p = man + 12 + 44 * j
+		cols.append(c[:, p + 24:p + 40])
+	return np.ascontiguousarray(np.concatenate(cols, axis=1)).view(np.float32)
+
+
+class GpuSolver:
+	"""RAII wrapper over b2GpuSolverCreate / Destroy."""
+
+	def __init__(self, device: int = 0, mode: int = 0):
+		self.lib = solver_lib()
+		self.handle = self.lib.b2GpuSolverCreate(device)
+		if not self.handle:
+			raise RuntimeError("b2GpuSolverCreate failed: " + self.lib.b2GpuGetLastError().decode())
+		self.lib.b2GpuSolverSetMode(self.handle, mode)
+
+	def _check(self, rc: int, what: str) -> None:
+		if rc != 0:
+			raise RuntimeError(f"{what} failed: " + self.lib.b2GpuGetLastError().decode())
+
+	def set_mode(self, mode: int) -> None:
+		self._check(self.lib.b2GpuSolverSetMode(self.handle, mode), "b2GpuSolverSetMode")
+
+	def step(self, desc: StepDesc, result: StepResult) -> None:
+		self._check(self.lib.b2GpuSolverStep(self.handle, ctypes.byref(desc), ctypes.byref(result)), "b2GpuSolverStep")
+
+	def upload(self, desc: StepDesc) -> None:
+		self._check(self.lib.b2GpuSolverUpload(self.handle, ctypes.byref(desc)), "b2GpuSolverUpload")
+
+	def run(self, result: StepResult) -> None:
+		self._check(self.lib.b2GpuSolverRun(self.handle, ctypes.byref(result)), "b2GpuSolverRun")
+
+	def download(self, desc: StepDesc, result: StepResult) -> None:
+		self._check(self.lib.b2GpuSolverDownload(self.handle, ctypes.byref(desc), ctypes.byref(result)),
+					"b2GpuSolverDownload")
+
+	def launch_count(self) -> int:
+		return int(self.lib.b2GpuSolverGetLaunchCount(self.handle))
+
+	def close(self) -> None:
+		if self.handle:
+			self.lib.b2GpuSolverDestroy(self.handle)
+			self.handle = None
+
+	def __enter__(self):
+		return self
+
+	def __exit__(self, *exc):
+		self.close()

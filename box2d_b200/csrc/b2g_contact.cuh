@@ -405,7 +405,9 @@ B2G_DEV void solveContact( const StepParams& P, int slot, bool active, bool useB
 			float deltaLambda = roll.z * ( bA.z - bB.z );
 			float lambda = imp1.w;
 			float maxLambda = roll.x * totalNormalImpulse;
-			float nb = 0.0f - maxLambda;
+			// b2SymClampW of the default SSE2 build flips the sign bit (src/contact_solver.c:869-878), so the lower
+			// bound is -maxLambda (-0 for +0), unlike the AVX2 wrapper's 0 - maxLambda (:641-645)
+			float nb = -maxLambda;
 			imp1.w = maxf_( nb, minf_( lambda + deltaLambda, maxLambda ) );
 			deltaLambda = imp1.w - lambda;
 

@@ -1,0 +1,81 @@
+"""CPU-side checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/*.h declares,
+its Python mirror has the header's layout, and it refuses to run without a device (no CPU fallback)."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+import box2d_b200 as b2
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared_symbols():
+	text = (ROOT / "include" / "b2_gpu_solver.h").read_text()
+	return sorted(set(re.findall(r"B2GPU_API\s+[\w\s\*]+?\b(b2Gpu\w+)\s*\(", text)))
+
+
+def test_header_declares_entry_points():
+	names = _declared_symbols()
+	for required in ("b2GpuSolverCreate", "b2GpuSolverDestroy", "b2GpuSolverStep", "b2GpuSolverUpload", "b2GpuSolverRun",
+					 "b2GpuSolverDownload", "b2GpuSolverStepBatch", "b2GpuHostAlloc", "b2GpuHostFree"):
+		assert required in names
+
+
+def test_library_exports_every_declared_symbol():
+	lib = b2.solver_lib()
+	for name in _declared_symbols():
+		assert hasattr(lib, name), f"{name} declared in include/b2_gpu_solver.h but not exported"
+
+
+def test_python_mirror_matches_header_layout(tmp_path):
+	src = tmp_path / "sz.c"
+	src.write_text(
+		'#include "b2_gpu_solver.h"\n#include "b2gpu_layout.h"\n#include <stdio.h>\n#include <stddef.h>\n'
+		'int main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(b2GpuStepDesc), sizeof(b2GpuStepResult),'
+		' offsetof(b2GpuStepDesc,states), offsetof(b2GpuStepDesc,colors), offsetof(b2GpuStepDesc,overflow),'
+		' sizeof(b2lJointSim));return 0;}\n')
+	exe = tmp_path / "sz"
+	subprocess.check_call(["gcc", f"-I{ROOT / 'include'}", str(src), "-o", str(exe)])
+	got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+	assert got == [ctypes.sizeof(b2.StepDesc), ctypes.sizeof(b2.StepResult), b2.StepDesc.states.offset,
+				   b2.StepDesc.colors.offset, b2.StepDesc.overflow.offset, b2.JOINT_SIZE]
+
+
+def test_no_cpu_fallback_without_device():
+	lib = b2.solver_lib()
+	if lib.b2GpuGetDeviceCount() > 0:
+		pytest.skip("a device is present")
+	assert lib.b2GpuSolverCreate(0) is None
+	assert b"no CPU fallback" in lib.b2GpuGetLastError()
+	with pytest.raises(RuntimeError):
+		b2.GpuSolver()
+
+
+def test_host_library_has_no_cpu_solver_entry():
+	"""The product host library is the reference with the b2SolverTask fan-out replaced by the seam call."""
+	path = b2.PKG_DIR / "libbox2d_b200.so"
+	if not path.is_file():
+		pytest.skip("host library not built")
+	symbols = subprocess.check_output(["nm", "-D", "--defined-only", str(path)], text=True)
+	assert "b2GpuSeam_SolveConstraints" in symbols
+	assert "b2World_Step" in symbols
+	full = subprocess.check_output(["nm", str(path)], text=True)
+	assert "b2SolverTask" not in full, "the CPU solver driver must not be linked into the GPU host library"
+
+
+def test_pinned_allocator_round_trip():
+	lib = b2.solver_lib()
+	blocks = []
+	for size in (1, 63, 64, 200, 4096, 100000, 5 << 20):
+		p = lib.b2GpuHostAlloc(size, 32)
+		assert p and p % 64 == 0
+		ctypes.memset(p, 0xAB, size)
+		blocks.append((p, size))
+	for p, size in blocks:
+		lib.b2GpuHostFree(p, size)
+	again = lib.b2GpuHostAlloc(200, 32)
+	assert again in [p for p, _ in blocks]  # recycled from the free list
+	lib.b2GpuHostFree(again, 200)
