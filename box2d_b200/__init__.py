@@ -77,6 +77,10 @@ class StepResult(ctypes.Structure):
 		("d2hBytes", ctypes.c_uint64),
 		("kernelLaunches", ctypes.c_int),
 		("gridBarriers", ctypes.c_int),
+		("uploadMs", ctypes.c_float),
+		("waitMs", ctypes.c_float),
+		("scatterMs", ctypes.c_float),
+		("h2dMs", ctypes.c_float),
 	]
 
 

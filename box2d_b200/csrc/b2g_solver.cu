@@ -314,7 +314,7 @@ struct b2GpuSolver
 	int mode = 0;
 	bool cooperative = false;
 	cudaStream_t stream = nullptr;
-	cudaEvent_t evStart = nullptr, evStop = nullptr;
+	cudaEvent_t evStart = nullptr, evStop = nullptr, evUpload = nullptr;
 
 	DeviceBuffer<uint8_t> rawStates, rawSims, rawContacts, rawJoints, joints, outStates;
 	DeviceBuffer<float4> vel, pos, bodyK, cf;
@@ -414,6 +414,7 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 	bool ok = cudaStreamCreateWithFlags( &s->stream, cudaStreamNonBlocking ) == cudaSuccess;
 	ok = ok && cudaEventCreate( &s->evStart ) == cudaSuccess;
 	ok = ok && cudaEventCreate( &s->evStop ) == cudaSuccess;
+	ok = ok && cudaEventCreate( &s->evUpload ) == cudaSuccess;
 	ok = ok && cudaMalloc( &s->control, sizeof( ControlBlock ) ) == cudaSuccess;
 	ok = ok && cudaHostAlloc( &s->hControl, sizeof( ControlBlock ), cudaHostAllocDefault ) == cudaSuccess;
 	if ( !ok )
@@ -470,6 +471,10 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	if ( s->evStop != nullptr )
 	{
 		cudaEventDestroy( s->evStop );
+	}
+	if ( s->evUpload != nullptr )
+	{
+		cudaEventDestroy( s->evUpload );
 	}
 	if ( s->stream != nullptr )
 	{
@@ -605,6 +610,7 @@ extern "C" int b2GpuSolverUpload( b2GpuSolver* s, const b2GpuStepDesc* d )
 	// host -> device: the reference's own arrays, no host-side repacking
 	uint64_t bytes = 0;
 	cudaStream_t st = s->stream;
+	B2G_CUDA( cudaEventRecord( s->evUpload, st ) );
 	if ( bodies > 0 )
 	{
 		B2G_CUDA( cudaMemcpyAsync( s->rawStates.ptr, d->states, bodies * B2L_STATE_SIZE, cudaMemcpyHostToDevice, st ) );
@@ -913,11 +919,14 @@ extern "C" int b2GpuSolverDownload( b2GpuSolver* s, const b2GpuStepDesc* d, b2Gp
 // ---- the whole step --------------------------------------------------------------------------------------------
 extern "C" int b2GpuSolverStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuStepResult* r )
 {
-	auto t0 = std::chrono::steady_clock::now();
+	using clock = std::chrono::steady_clock;
+	auto ms = []( clock::time_point a, clock::time_point b ) { return std::chrono::duration<float, std::milli>( b - a ).count(); };
+	auto t0 = clock::now();
 	if ( b2GpuSolverUpload( s, d ) != 0 )
 	{
 		return 1;
 	}
+	auto t1 = clock::now();
 	if ( b2gEnqueueRun( s ) != 0 )
 	{
 		return 1;
@@ -928,8 +937,10 @@ extern "C" int b2GpuSolverStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuSte
 		return 1;
 	}
 	B2G_CUDA( cudaStreamSynchronize( s->stream ) );
+	auto t2 = clock::now();
 	B2G_CUDA( cudaEventElapsedTime( &s->lastKernelMs, s->evStart, s->evStop ) );
 	b2gFinishDownload( s, d, r );
+	auto t3 = clock::now();
 	if ( r != nullptr )
 	{
 		r->kernelMs = s->lastKernelMs;
@@ -937,7 +948,12 @@ extern "C" int b2GpuSolverStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuSte
 		r->h2dBytes = s->lastH2D;
 		r->d2hBytes = d2h;
 		b2gFillTimers( s, r );
-		r->totalMs = std::chrono::duration<float, std::milli>( std::chrono::steady_clock::now() - t0 ).count();
+		r->uploadMs = ms( t0, t1 );
+		r->waitMs = ms( t1, t2 );
+		r->scatterMs = ms( t2, t3 );
+		r->h2dMs = 0.0f;
+		cudaEventElapsedTime( &r->h2dMs, s->evUpload, s->evStart );
+		r->totalMs = ms( t0, clock::now() );
 	}
 	return 0;
 }

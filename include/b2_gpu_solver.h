@@ -136,6 +136,11 @@ typedef struct b2GpuStepResult
 	uint64_t d2hBytes;  /* bytes copied device -> host during the call */
 	int kernelLaunches; /* kernels launched by the call */
 	int gridBarriers;   /* grid-wide barriers executed inside the step kernel */
+	/* host wall-clock split of b2GpuSolverStep, milliseconds */
+	float uploadMs;   /* descriptor -> params, buffer growth, enqueue of the H2D copies */
+	float waitMs;     /* launch + waiting for H2D, kernels and D2H to drain */
+	float scatterMs;  /* writing the impulses back into the reference's manifolds + event bits */
+	float h2dMs;      /* CUDA-event time of the H2D copies */
 } b2GpuStepResult;
 
 typedef struct b2GpuSolver b2GpuSolver;
