@@ -12,6 +12,7 @@ from tools import buildlib  # noqa: E402
 
 
 def main() -> int:
+	print(buildlib.build_oracle_lib(verbose=True))
 	libs = buildlib.build_reference_libs(verbose=True)
 	for name, path in libs.items():
 		print(name, path)

@@ -178,6 +178,20 @@ def build_host_lib(verbose: bool = False) -> Path:
 	return target
 
 
+def build_oracle_lib(verbose: bool = False) -> Path:
+	"""oracle/liboracle.so: the plain-C restatement of the solver (checker only, needs nothing from the reference)."""
+	odir = ROOT / "oracle"
+	sources = [odir / "b2o_solver.c", odir / "b2o_joints.c"]
+	headers = [odir / "b2o_solver.h", odir / "b2o_math.h", *sorted((ROOT / "include").glob("*.h"))]
+	target = odir / "liboracle.so"
+	if _stale(target, [*sources, *headers]):
+		_run([CC, "-O2", "-std=gnu17", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wextra", "-Wno-comment",
+			  f"-I{ROOT / 'include'}", f"-I{odir}", *[str(s) for s in sources], "-lm", "-o", str(target)])
+	if verbose:
+		print(f"built {target}")
+	return target
+
+
 def clean() -> None:
 	for d in (REF_OUT, GEN_DIR):
 		shutil.rmtree(d, ignore_errors=True)
