@@ -128,6 +128,18 @@ def solver_lib() -> ctypes.CDLL:
 		fn = getattr(lib, name)
 		fn.restype = ctypes.c_int
 		fn.argtypes = [ctypes.c_void_p, P(StepDesc), ctypes.c_int, P(StepResult)]
+	lib.b2GpuSolverBeginStep.restype = ctypes.c_int
+	lib.b2GpuSolverBeginStep.argtypes = [ctypes.c_void_p, P(StepDesc), P(StepResult)]
+	for name in ("b2GpuSolverGetPackItemCount", "b2GpuSolverGetUnpackItemCount", "b2GpuSolverSubmit", "b2GpuSolverWait"):
+		fn = getattr(lib, name)
+		fn.restype = ctypes.c_int
+		fn.argtypes = [ctypes.c_void_p]
+	for name in ("b2GpuSolverPackRange", "b2GpuSolverUnpackRange"):
+		fn = getattr(lib, name)
+		fn.restype = None
+		fn.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+	lib.b2GpuSolverEndStep.restype = ctypes.c_int
+	lib.b2GpuSolverEndStep.argtypes = [ctypes.c_void_p, P(StepResult)]
 	lib.b2GpuSolverSetMode.restype = ctypes.c_int
 	lib.b2GpuSolverSetMode.argtypes = [ctypes.c_void_p, ctypes.c_int]
 	lib.b2GpuHostAlloc.restype = ctypes.c_void_p

@@ -27,66 +27,60 @@ B2G_DEV int rawI( const uint8_t* base, int offset )
 // ---- body gather / scatter (replaces b2GatherBodies / b2ScatterBodies, src/contact_solver.c:1121-1562) -----
 // Index 0 is the static dummy body: vel = 0, flags = 0, pos = identity; it is never written because the
 // scatter is guarded by b2_dynamicFlag exactly like the reference (contact_solver.c:1531).
-B2G_DEV float4 gatherVel( const StepParams& P, int index )
+// Plain generic loads/stores: the view may live in shared memory (island-local kernel) or in global memory
+// (grid-barrier kernel, where the barrier's release/acquire pair orders them across blocks).
+B2G_DEV float4 gatherVel( const SolveView& V, int index )
 {
-	return __ldcg( P.vel + index );
+	return V.vel[index];
 }
 
-B2G_DEV float4 gatherPos( const StepParams& P, int index )
+B2G_DEV float4 gatherPos( const SolveView& V, int index )
 {
-	return __ldcg( P.pos + index );
+	return V.pos[index];
 }
 
-B2G_DEV void scatterVel( const StepParams& P, int index, float4 v )
+B2G_DEV void scatterVel( const SolveView& V, int index, float4 v )
 {
 	if ( ( __float_as_uint( v.w ) & B2L_FLAG_DYNAMIC ) != 0 )
 	{
-		__stcg( P.vel + index, v );
+		V.vel[index] = v;
 	}
 }
 
-B2G_DEV float4 loadField( const StepParams& P, int field, int slot )
+B2G_DEV float4 loadField( const SolveView& V, int field, int slot )
 {
-	return P.cf[(size_t)field * P.slotCapacity + slot];
+	return V.cf[(size_t)field * V.cfStride + slot];
 }
 
-B2G_DEV void storeField( const StepParams& P, int field, int slot, float4 value )
+B2G_DEV void storeField( const SolveView& V, int field, int slot, float4 value )
 {
-	P.cf[(size_t)field * P.slotCapacity + slot] = value;
+	V.cf[(size_t)field * V.cfStride + slot] = value;
 }
 
 // ---- prepare ---------------------------------------------------------------------------------------------
 // b2PrepareContactsTask (src/contact_solver.c:1573-1809) per lane; with wide == false it is
 // b2PrepareContacts_Overflow (src/contact_solver.c:24-160): no contact-softening branch.
-B2G_DEV void prepareContact( const StepParams& P, int slot, bool wide )
+// Reads the wire record `wireSlot`, takes the bodies' current {v, w} (sA, sB; zero for a static body, like the
+// reference's vA = 0 for B2_NULL_INDEX) and writes constraint slot `slot` of the view; localA/localB are the body
+// indices in the view's numbering (0 = static).
+B2G_DEV void prepareContact( const StepParams& P, const SolveView& V, int wireSlot, int slot, int localA, int localB, float4 sA,
+							 float4 sB, bool wide, int groupBits )
 {
-	const uint8_t* sim = P.rawContacts + (size_t)slot * B2L_CONTACT_SIZE;
-	const uint8_t* manifold = sim + B2L_CONTACT_MANIFOLD;
+	const float4* w = P.wire + (size_t)wireSlot * WR_COUNT;
+	float4 head = w[WR_HEAD];
+	float4 mass = w[WR_MASS];
+	float4 nrm = w[WR_NORMAL];
+	float4 mat = w[WR_MATERIAL];
+	float4 imp = w[WR_IMPULSE];
+	int meta = __float_as_int( head.z );
+	int pointCount = meta & kMetaPointMask;
 
-	int indexA = rawI( sim, B2L_CONTACT_INDEX_A );
-	int indexB = rawI( sim, B2L_CONTACT_INDEX_B );
+	float mA = mass.x, iA = mass.y, mB = mass.z, iB = mass.w;
 
-	float mA = rawF( sim, B2L_CONTACT_INV_MASS_A );
-	float iA = rawF( sim, B2L_CONTACT_INV_I_A );
-	float mB = rawF( sim, B2L_CONTACT_INV_MASS_B );
-	float iB = rawF( sim, B2L_CONTACT_INV_I_B );
-
-	V2 vA = v2( 0.0f, 0.0f );
-	float wA = 0.0f;
-	if ( indexA != -1 )
-	{
-		const uint8_t* s = P.rawStates + (size_t)indexA * B2L_STATE_SIZE;
-		vA = v2( rawF( s, 0 ), rawF( s, 4 ) );
-		wA = rawF( s, 8 );
-	}
-	V2 vB = v2( 0.0f, 0.0f );
-	float wB = 0.0f;
-	if ( indexB != -1 )
-	{
-		const uint8_t* s = P.rawStates + (size_t)indexB * B2L_STATE_SIZE;
-		vB = v2( rawF( s, 0 ), rawF( s, 4 ) );
-		wB = rawF( s, 8 );
-	}
+	V2 vA = v2( sA.x, sA.y );
+	float wA = sA.z;
+	V2 vB = v2( sB.x, sB.y );
+	float wB = sB.z;
 
 	float rollingMass;
 	{
@@ -95,7 +89,7 @@ B2G_DEV void prepareContact( const StepParams& P, int slot, bool wide )
 	}
 
 	Soft soft = P.contactSoft;
-	if ( indexA == -1 || indexB == -1 )
+	if ( localA == 0 || localB == 0 )
 	{
 		soft = P.staticSoft;
 	}
@@ -117,16 +111,19 @@ B2G_DEV void prepareContact( const StepParams& P, int slot, bool wide )
 
 	float warmStartScale = P.enableWarmStarting != 0 ? 1.0f : 0.0f;
 
-	V2 normal = v2( rawF( manifold, B2L_MANIFOLD_NORMAL ), rawF( manifold, B2L_MANIFOLD_NORMAL + 4 ) );
+	V2 normal = v2( nrm.x, nrm.y );
 	V2 tangent = rightPerp( normal );
-	float friction = rawF( sim, B2L_CONTACT_FRICTION );
-	float restitution = rawF( sim, B2L_CONTACT_RESTITUTION );
-	float rollingResistance = rawF( sim, B2L_CONTACT_ROLLING_RESISTANCE );
-	float tangentSpeed = rawF( sim, B2L_CONTACT_TANGENT_SPEED );
-	float rollingImpulse = warmStartScale * rawF( manifold, B2L_MANIFOLD_ROLLING_IMPULSE );
-	int pointCount = rawI( manifold, B2L_MANIFOLD_POINT_COUNT );
+	float friction = nrm.z;
+	float tangentSpeed = nrm.w;
+	float rollingResistance = mat.x;
+	float restitution = mat.y;
+	float rollingImpulse = warmStartScale * head.w;
 
-	float4 anchors[2], impulses[2];
+	float4 anchors[2] = { w[WR_ANCHOR1], w[WR_ANCHOR2] };
+	float separation[2] = { mat.z, mat.w };
+	float wireNormalImpulse[2] = { imp.x, imp.z };
+	float wireTangentImpulse[2] = { imp.y, imp.w };
+	float4 impulses[2];
 	float normalMass[2], tangentMass[2], baseSeparation[2], relativeVelocity[2];
 
 #pragma unroll
@@ -134,15 +131,13 @@ B2G_DEV void prepareContact( const StepParams& P, int slot, bool wide )
 	{
 		if ( j < pointCount )
 		{
-			const uint8_t* mp = manifold + B2L_MANIFOLD_POINTS + j * B2L_MP_SIZE;
-			V2 rA = v2( rawF( mp, B2L_MP_ANCHOR_A ), rawF( mp, B2L_MP_ANCHOR_A + 4 ) );
-			V2 rB = v2( rawF( mp, B2L_MP_ANCHOR_B ), rawF( mp, B2L_MP_ANCHOR_B + 4 ) );
-			anchors[j] = make_float4( rA.x, rA.y, rB.x, rB.y );
+			V2 rA = v2( anchors[j].x, anchors[j].y );
+			V2 rB = v2( anchors[j].z, anchors[j].w );
 
-			baseSeparation[j] = rawF( mp, B2L_MP_SEPARATION ) - dot( sub( rB, rA ), normal );
+			baseSeparation[j] = separation[j] - dot( sub( rB, rA ), normal );
 
-			impulses[j].x = warmStartScale * rawF( mp, B2L_MP_NORMAL_IMPULSE );
-			impulses[j].y = warmStartScale * rawF( mp, B2L_MP_TANGENT_IMPULSE );
+			impulses[j].x = warmStartScale * wireNormalImpulse[j];
+			impulses[j].y = warmStartScale * wireTangentImpulse[j];
 			impulses[j].z = 0.0f;
 
 			float rnA = cross( rA, normal );
@@ -174,17 +169,17 @@ B2G_DEV void prepareContact( const StepParams& P, int slot, bool wide )
 	impulses[0].w = rollingImpulse;
 	impulses[1].w = 0.0f;
 
-	storeField( P, CF_MASS, slot, make_float4( mA, iA, mB, iB ) );
-	storeField( P, CF_NORMAL, slot, make_float4( normal.x, normal.y, friction, tangentSpeed ) );
-	storeField( P, CF_ROLL, slot, make_float4( rollingResistance, restitution, rollingMass, 0.0f ) );
-	storeField( P, CF_SOFT, slot, make_float4( soft.biasRate, soft.massScale, soft.impulseScale, 0.0f ) );
-	storeField( P, CF_ANCHOR1, slot, anchors[0] );
-	storeField( P, CF_ANCHOR2, slot, anchors[1] );
-	storeField( P, CF_PMASS, slot, make_float4( normalMass[0], tangentMass[0], normalMass[1], tangentMass[1] ) );
-	storeField( P, CF_BASE, slot,
+	storeField( V, CF_MASS, slot, make_float4( mA, iA, mB, iB ) );
+	storeField( V, CF_NORMAL, slot, make_float4( normal.x, normal.y, friction, tangentSpeed ) );
+	storeField( V, CF_ROLL, slot, make_float4( rollingResistance, restitution, rollingMass, 0.0f ) );
+	storeField( V, CF_SOFT, slot, make_float4( soft.biasRate, soft.massScale, soft.impulseScale, 0.0f ) );
+	storeField( V, CF_ANCHOR1, slot, anchors[0] );
+	storeField( V, CF_ANCHOR2, slot, anchors[1] );
+	storeField( V, CF_PMASS, slot, make_float4( normalMass[0], tangentMass[0], normalMass[1], tangentMass[1] ) );
+	storeField( V, CF_BASE, slot,
 				make_float4( baseSeparation[0], baseSeparation[1], relativeVelocity[0], relativeVelocity[1] ) );
-	storeField( P, CF_IMP1, slot, impulses[0] );
-	storeField( P, CF_IMP2, slot, impulses[1] );
+	storeField( V, CF_IMP1, slot, impulses[0] );
+	storeField( V, CF_IMP2, slot, impulses[1] );
 
 	if ( !( restitution == 0.0f ) )
 	{
@@ -192,9 +187,37 @@ B2G_DEV void prepareContact( const StepParams& P, int slot, bool wide )
 	}
 
 	// 0 for null (contact_solver.c:1644-1646)
-	P.cidx[slot] = make_int2( indexA + 1, indexB + 1 );
-	int simFlags = rawI( sim, B2L_CONTACT_SIM_FLAGS );
-	P.cmeta[slot] = make_int2( rawI( sim, B2L_CONTACT_ID ), ( simFlags & (int)B2L_SIM_ENABLE_HIT_EVENT ) | pointCount );
+	V.cidx[slot] = make_int2( localA, localB );
+	V.cmeta[slot] = ( meta & ( kMetaPointMask | kMetaHitEnable ) ) | groupBits;
+}
+
+// The reference skips rolling resistance / restitution for a whole SIMD register when all its lanes have none
+// (src/contact_solver.c:2021, :2131).  The default build is SSE2 with 4 lanes, so the test is over aligned groups of
+// 4 consecutive constraints of the colour's array.  Evaluated once per step from the wire order by a full warp
+// (lane == colour-local index modulo 32); the result travels with the constraint in cmeta.
+B2G_DEV int simdGroupBits( const StepParams& P, int wireSlot, bool active, unsigned lane )
+{
+	float rollingResistance = 0.0f, restitution = 0.0f;
+	if ( active )
+	{
+		float4 mat = P.wire[(size_t)wireSlot * WR_COUNT + WR_MATERIAL];
+		rollingResistance = mat.x;
+		restitution = mat.y;
+	}
+	// x == 0 is false for NaN, like _mm_cmpeq_ps (ordered)
+	unsigned rolling = __ballot_sync( 0xffffffffu, !( rollingResistance == 0.0f ) );
+	unsigned bouncy = __ballot_sync( 0xffffffffu, !( restitution == 0.0f ) );
+	unsigned shift = lane & ~3u;
+	int bits = 0;
+	if ( ( ( rolling >> shift ) & 0xFu ) != 0 )
+	{
+		bits |= kMetaGroupRolling;
+	}
+	if ( ( ( bouncy >> shift ) & 0xFu ) != 0 )
+	{
+		bits |= kMetaGroupRestitution;
+	}
+	return bits;
 }
 
 // ===========================================================================================================
@@ -202,24 +225,24 @@ B2G_DEV void prepareContact( const StepParams& P, int slot, bool wide )
 // ===========================================================================================================
 
 // b2WarmStartContactsTask, src/contact_solver.c:1811-1871
-B2G_DEV void warmStartContact( const StepParams& P, int slot )
+B2G_DEV void warmStartContact( const SolveView& V, int slot )
 {
-	int2 idx = P.cidx[slot];
-	float4 bA = gatherVel( P, idx.x );
-	float4 bB = gatherVel( P, idx.y );
+	int2 idx = V.cidx[slot];
+	float4 bA = gatherVel( V, idx.x );
+	float4 bB = gatherVel( V, idx.y );
 
-	float4 mass = loadField( P, CF_MASS, slot );
+	float4 mass = loadField( V, CF_MASS, slot );
 	float invMassA = mass.x, invIA = mass.y, invMassB = mass.z, invIB = mass.w;
-	float4 nrm = loadField( P, CF_NORMAL, slot );
+	float4 nrm = loadField( V, CF_NORMAL, slot );
 	float nx = nrm.x, ny = nrm.y;
 	float tangentX = ny;
 	float tangentY = 0.0f - nx;
 
-	float4 imp1 = loadField( P, CF_IMP1, slot );
-	float4 imp2 = loadField( P, CF_IMP2, slot );
+	float4 imp1 = loadField( V, CF_IMP1, slot );
+	float4 imp2 = loadField( V, CF_IMP2, slot );
 
 	{
-		float4 a = loadField( P, CF_ANCHOR1, slot );
+		float4 a = loadField( V, CF_ANCHOR1, slot );
 		float Px = imp1.x * nx + imp1.y * tangentX;
 		float Py = imp1.x * ny + imp1.y * tangentY;
 		bA.z = bA.z - invIA * ( a.x * Py - a.y * Px );
@@ -231,7 +254,7 @@ B2G_DEV void warmStartContact( const StepParams& P, int slot )
 		imp1.z = imp1.z + imp1.x;
 	}
 	{
-		float4 a = loadField( P, CF_ANCHOR2, slot );
+		float4 a = loadField( V, CF_ANCHOR2, slot );
 		float Px = imp2.x * nx + imp2.y * tangentX;
 		float Py = imp2.x * ny + imp2.y * tangentY;
 		bA.z = bA.z - invIA * ( a.x * Py - a.y * Px );
@@ -246,10 +269,10 @@ B2G_DEV void warmStartContact( const StepParams& P, int slot )
 	bA.z = bA.z - invIA * imp1.w;
 	bB.z = invIB * imp1.w + bB.z;
 
-	storeField( P, CF_IMP1, slot, imp1 );
-	storeField( P, CF_IMP2, slot, imp2 );
-	scatterVel( P, idx.x, bA );
-	scatterVel( P, idx.y, bB );
+	storeField( V, CF_IMP1, slot, imp1 );
+	storeField( V, CF_IMP2, slot, imp2 );
+	scatterVel( V, idx.x, bA );
+	scatterVel( V, idx.y, bB );
 }
 
 // One non-penetration row of b2SolveContactsTask (src/contact_solver.c:1909-1964 / 1966-2016)
@@ -330,48 +353,37 @@ B2G_DEV void solveFrictionRow( float4& bA, float4& bB, float4 a, float tangentX,
 	bB.z = invIB * ( a.z * Py - a.w * Px ) + bB.z;
 }
 
-// b2SolveContactsTask, src/contact_solver.c:1873-2116.  `active` is false for the padding lanes of the last
-// warp of a colour: they take part in the warp votes only.  The reference skips rolling resistance for a
-// whole SIMD register when all its lanes have none (contact_solver.c:2021); the default build is SSE2 with
-// 4 lanes, so the vote is taken over aligned groups of 4 consecutive constraints of the colour.
-B2G_DEV void solveContact( const StepParams& P, int slot, bool active, bool useBias, unsigned lane )
+// b2SolveContactsTask, src/contact_solver.c:1873-2116.
+B2G_DEV void solveContact( const StepParams& P, const SolveView& V, int slot, bool useBias )
 {
 	float4 roll = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
-	if ( active && useBias == false )
-	{
-		roll = loadField( P, CF_ROLL, slot );
-	}
-
 	bool groupHasRolling = false;
 	if ( useBias == false )
 	{
-		// x == 0 is false for NaN, like _mm_cmpeq_ps (ordered)
-		unsigned nonZero = __ballot_sync( 0xffffffffu, !( roll.x == 0.0f ) );
-		groupHasRolling = ( ( nonZero >> ( lane & ~3u ) ) & 0xFu ) != 0;
+		groupHasRolling = ( V.cmeta[slot] & kMetaGroupRolling ) != 0;
+		if ( groupHasRolling )
+		{
+			roll = loadField( V, CF_ROLL, slot );
+		}
 	}
 
-	if ( active == false )
-	{
-		return;
-	}
+	int2 idx = V.cidx[slot];
+	float4 bA = gatherVel( V, idx.x );
+	float4 bB = gatherVel( V, idx.y );
+	float4 pA = gatherPos( V, idx.x );
+	float4 pB = gatherPos( V, idx.y );
 
-	int2 idx = P.cidx[slot];
-	float4 bA = gatherVel( P, idx.x );
-	float4 bB = gatherVel( P, idx.y );
-	float4 pA = gatherPos( P, idx.x );
-	float4 pB = gatherPos( P, idx.y );
-
-	float4 mass = loadField( P, CF_MASS, slot );
+	float4 mass = loadField( V, CF_MASS, slot );
 	float invMassA = mass.x, invIA = mass.y, invMassB = mass.z, invIB = mass.w;
-	float4 nrm = loadField( P, CF_NORMAL, slot );
+	float4 nrm = loadField( V, CF_NORMAL, slot );
 	float nx = nrm.x, ny = nrm.y;
-	float4 soft = loadField( P, CF_SOFT, slot );
-	float4 pmass = loadField( P, CF_PMASS, slot );
-	float4 base = loadField( P, CF_BASE, slot );
-	float4 a1 = loadField( P, CF_ANCHOR1, slot );
-	float4 a2 = loadField( P, CF_ANCHOR2, slot );
-	float4 imp1 = loadField( P, CF_IMP1, slot );
-	float4 imp2 = loadField( P, CF_IMP2, slot );
+	float4 soft = loadField( V, CF_SOFT, slot );
+	float4 pmass = loadField( V, CF_PMASS, slot );
+	float4 base = loadField( V, CF_BASE, slot );
+	float4 a1 = loadField( V, CF_ANCHOR1, slot );
+	float4 a2 = loadField( V, CF_ANCHOR2, slot );
+	float4 imp1 = loadField( V, CF_IMP1, slot );
+	float4 imp2 = loadField( V, CF_IMP2, slot );
 
 	float biasRate, massScale, impulseScale;
 	if ( useBias )
@@ -423,10 +435,10 @@ B2G_DEV void solveContact( const StepParams& P, int slot, bool active, bool useB
 						  imp2.y );
 	}
 
-	storeField( P, CF_IMP1, slot, imp1 );
-	storeField( P, CF_IMP2, slot, imp2 );
-	scatterVel( P, idx.x, bA );
-	scatterVel( P, idx.y, bB );
+	storeField( V, CF_IMP1, slot, imp1 );
+	storeField( V, CF_IMP2, slot, imp2 );
+	scatterVel( V, idx.x, bA );
+	scatterVel( V, idx.y, bB );
 }
 
 // One row of b2ApplyRestitutionTask (src/contact_solver.c:2144-2181 / 2183-2221)
@@ -463,73 +475,58 @@ B2G_DEV void restitutionRow( float4& bA, float4& bB, float4 a, float nx, float n
 }
 
 // b2ApplyRestitutionTask, src/contact_solver.c:2118-2228 (group-of-4 early out at :2131)
-B2G_DEV void restitutionContact( const StepParams& P, int slot, bool active, unsigned lane )
+B2G_DEV void restitutionContact( const StepParams& P, const SolveView& V, int slot )
 {
-	float4 roll = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
-	if ( active )
-	{
-		roll = loadField( P, CF_ROLL, slot );
-	}
-	float restitution = roll.y;
-	unsigned nonZero = __ballot_sync( 0xffffffffu, !( restitution == 0.0f ) );
-	bool groupHasRestitution = ( ( nonZero >> ( lane & ~3u ) ) & 0xFu ) != 0;
-	if ( active == false || groupHasRestitution == false )
+	if ( ( V.cmeta[slot] & kMetaGroupRestitution ) == 0 )
 	{
 		return;
 	}
+	float4 roll = loadField( V, CF_ROLL, slot );
+	float restitution = roll.y;
 
 	bool restitutionIsZero = restitution == 0.0f;
 
-	int2 idx = P.cidx[slot];
-	float4 bA = gatherVel( P, idx.x );
-	float4 bB = gatherVel( P, idx.y );
+	int2 idx = V.cidx[slot];
+	float4 bA = gatherVel( V, idx.x );
+	float4 bB = gatherVel( V, idx.y );
 
-	float4 mass = loadField( P, CF_MASS, slot );
-	float4 nrm = loadField( P, CF_NORMAL, slot );
-	float4 pmass = loadField( P, CF_PMASS, slot );
-	float4 base = loadField( P, CF_BASE, slot );
-	float4 a1 = loadField( P, CF_ANCHOR1, slot );
-	float4 a2 = loadField( P, CF_ANCHOR2, slot );
-	float4 imp1 = loadField( P, CF_IMP1, slot );
-	float4 imp2 = loadField( P, CF_IMP2, slot );
+	float4 mass = loadField( V, CF_MASS, slot );
+	float4 nrm = loadField( V, CF_NORMAL, slot );
+	float4 pmass = loadField( V, CF_PMASS, slot );
+	float4 base = loadField( V, CF_BASE, slot );
+	float4 a1 = loadField( V, CF_ANCHOR1, slot );
+	float4 a2 = loadField( V, CF_ANCHOR2, slot );
+	float4 imp1 = loadField( V, CF_IMP1, slot );
+	float4 imp2 = loadField( V, CF_IMP2, slot );
 
 	restitutionRow( bA, bB, a1, nrm.x, nrm.y, restitution, restitutionIsZero, P.restitutionThreshold, base.z, pmass.x, mass.x,
 					mass.y, mass.z, mass.w, imp1.x, imp1.z );
 	restitutionRow( bA, bB, a2, nrm.x, nrm.y, restitution, restitutionIsZero, P.restitutionThreshold, base.w, pmass.z, mass.x,
 					mass.y, mass.z, mass.w, imp2.x, imp2.z );
 
-	storeField( P, CF_IMP1, slot, imp1 );
-	storeField( P, CF_IMP2, slot, imp2 );
-	scatterVel( P, idx.x, bA );
-	scatterVel( P, idx.y, bB );
+	storeField( V, CF_IMP1, slot, imp1 );
+	storeField( V, CF_IMP2, slot, imp2 );
+	scatterVel( V, idx.x, bA );
+	scatterVel( V, idx.y, bB );
 }
 
 // b2StoreImpulsesTask, src/contact_solver.c:2238-2331 (wide == true) and b2StoreImpulses_Overflow :516-545
-// (wide == false: no hit-event test).  The 9 floats go to a packed record; the host scatters them into
-// b2Manifold (the overflow path only writes the first pointCount points, the host honours that).
-B2G_DEV void storeContact( const StepParams& P, int slot, bool wide )
+// (wide == false: no hit-event test).  The 9 floats + hit flag go to the packed record of the constraint's wire slot;
+// the host scatters them into b2Manifold and sets the hit bit by contactId (the overflow path only writes the first
+// pointCount points, the host honours that).
+B2G_DEV void storeContact( const StepParams& P, const SolveView& V, int slot, int wireSlot, bool wide )
 {
-	float4 imp1 = loadField( P, CF_IMP1, slot );
-	float4 imp2 = loadField( P, CF_IMP2, slot );
-	float4 base = loadField( P, CF_BASE, slot );
+	float4 imp1 = loadField( V, CF_IMP1, slot );
+	float4 imp2 = loadField( V, CF_IMP2, slot );
+	float4 base = loadField( V, CF_BASE, slot );
 
-	float* out = P.outImpulses + (size_t)slot * kImpulseFloats;
-	out[0] = imp1.w; // rollingImpulse
-	out[1] = imp1.x; // normalImpulse
-	out[2] = imp1.y; // tangentImpulse
-	out[3] = imp1.z; // totalNormalImpulse
-	out[4] = base.z; // normalVelocity
-	out[5] = imp2.x;
-	out[6] = imp2.y;
-	out[7] = imp2.z;
-	out[8] = base.w;
-
+	float hitFlag = 0.0f;
 	if ( wide )
 	{
-		int2 meta = P.cmeta[slot];
-		if ( ( meta.y & (int)B2L_SIM_ENABLE_HIT_EVENT ) != 0 )
+		int meta = V.cmeta[slot];
+		if ( ( meta & kMetaHitEnable ) != 0 )
 		{
-			int pointCount = meta.y & 3;
+			int pointCount = meta & kMetaPointMask;
 			float negHitThreshold = -P.hitEventThreshold;
 			bool hit = ( base.z < negHitThreshold && imp1.z > 0.0f );
 			if ( pointCount > 1 )
@@ -538,12 +535,18 @@ B2G_DEV void storeContact( const StepParams& P, int slot, bool wide )
 			}
 			if ( hit )
 			{
-				unsigned id = (unsigned)meta.x;
-				atomicOr( P.hitBits + ( id >> 5 ), 1u << ( id & 31u ) );
+				hitFlag = 1.0f;
 				*P.hasHitEvents = 1;
 			}
 		}
 	}
+
+	float2* out = reinterpret_cast<float2*>( P.outImpulses + (size_t)wireSlot * kImpulseFloats );
+	out[0] = make_float2( imp1.w, imp1.x ); // rollingImpulse, normalImpulse1
+	out[1] = make_float2( imp1.y, imp1.z ); // tangentImpulse1, totalNormalImpulse1
+	out[2] = make_float2( base.z, imp2.x ); // normalVelocity1, normalImpulse2
+	out[3] = make_float2( imp2.y, imp2.z ); // tangentImpulse2, totalNormalImpulse2
+	out[4] = make_float2( base.w, hitFlag ); // normalVelocity2, hit event
 }
 
 // ===========================================================================================================
@@ -551,25 +554,25 @@ B2G_DEV void storeContact( const StepParams& P, int slot, bool wide )
 // ===========================================================================================================
 
 // b2WarmStartContacts_Overflow, src/contact_solver.c:162-237
-B2G_DEV void warmStartContactOverflow( const StepParams& P, int slot )
+B2G_DEV void warmStartContactOverflow( const SolveView& V, int slot )
 {
-	int2 idx = P.cidx[slot];
-	int pointCount = P.cmeta[slot].y & 3;
-	float4 sA = gatherVel( P, idx.x );
-	float4 sB = gatherVel( P, idx.y );
+	int2 idx = V.cidx[slot];
+	int pointCount = V.cmeta[slot] & kMetaPointMask;
+	float4 sA = gatherVel( V, idx.x );
+	float4 sB = gatherVel( V, idx.y );
 	V2 vA = v2( sA.x, sA.y );
 	float wA = sA.z;
 	V2 vB = v2( sB.x, sB.y );
 	float wB = sB.z;
 
-	float4 mass = loadField( P, CF_MASS, slot );
+	float4 mass = loadField( V, CF_MASS, slot );
 	float mA = mass.x, iA = mass.y, mB = mass.z, iB = mass.w;
-	float4 nrm = loadField( P, CF_NORMAL, slot );
+	float4 nrm = loadField( V, CF_NORMAL, slot );
 	V2 normal = v2( nrm.x, nrm.y );
 	V2 tangent = rightPerp( normal );
 
-	float4 imp[2] = { loadField( P, CF_IMP1, slot ), loadField( P, CF_IMP2, slot ) };
-	float4 anc[2] = { loadField( P, CF_ANCHOR1, slot ), loadField( P, CF_ANCHOR2, slot ) };
+	float4 imp[2] = { loadField( V, CF_IMP1, slot ), loadField( V, CF_IMP2, slot ) };
+	float4 anc[2] = { loadField( V, CF_ANCHOR1, slot ), loadField( V, CF_ANCHOR2, slot ) };
 
 	for ( int j = 0; j < pointCount; ++j )
 	{
@@ -588,31 +591,31 @@ B2G_DEV void warmStartContactOverflow( const StepParams& P, int slot )
 	wA -= iA * imp[0].w;
 	wB += iB * imp[0].w;
 
-	storeField( P, CF_IMP1, slot, imp[0] );
-	storeField( P, CF_IMP2, slot, imp[1] );
-	scatterVel( P, idx.x, make_float4( vA.x, vA.y, wA, sA.w ) );
-	scatterVel( P, idx.y, make_float4( vB.x, vB.y, wB, sB.w ) );
+	storeField( V, CF_IMP1, slot, imp[0] );
+	storeField( V, CF_IMP2, slot, imp[1] );
+	scatterVel( V, idx.x, make_float4( vA.x, vA.y, wA, sA.w ) );
+	scatterVel( V, idx.y, make_float4( vB.x, vB.y, wB, sB.w ) );
 }
 
 // b2SolveContacts_Overflow, src/contact_solver.c:239-408 (friction BEFORE rolling resistance)
-B2G_DEV void solveContactOverflow( const StepParams& P, int slot, bool useBias )
+B2G_DEV void solveContactOverflow( const StepParams& P, const SolveView& V, int slot, bool useBias )
 {
-	int2 idx = P.cidx[slot];
-	int pointCount = P.cmeta[slot].y & 3;
+	int2 idx = V.cidx[slot];
+	int pointCount = V.cmeta[slot] & kMetaPointMask;
 
-	float4 mass = loadField( P, CF_MASS, slot );
+	float4 mass = loadField( V, CF_MASS, slot );
 	float mA = mass.x, iA = mass.y, mB = mass.z, iB = mass.w;
 
-	float4 sA = gatherVel( P, idx.x );
-	float4 qA = gatherPos( P, idx.x );
+	float4 sA = gatherVel( V, idx.x );
+	float4 qA = gatherPos( V, idx.x );
 	V2 vA = v2( sA.x, sA.y );
 	float wA = sA.z;
 	Rot dqA;
 	dqA.c = qA.z;
 	dqA.s = qA.w;
 
-	float4 sB = gatherVel( P, idx.y );
-	float4 qB = gatherPos( P, idx.y );
+	float4 sB = gatherVel( V, idx.y );
+	float4 qB = gatherPos( V, idx.y );
 	V2 vB = v2( sB.x, sB.y );
 	float wB = sB.z;
 	Rot dqB;
@@ -621,21 +624,21 @@ B2G_DEV void solveContactOverflow( const StepParams& P, int slot, bool useBias )
 
 	V2 dp = sub( v2( qB.x, qB.y ), v2( qA.x, qA.y ) );
 
-	float4 nrm = loadField( P, CF_NORMAL, slot );
+	float4 nrm = loadField( V, CF_NORMAL, slot );
 	V2 normal = v2( nrm.x, nrm.y );
 	V2 tangent = rightPerp( normal );
 	float friction = nrm.z;
 	float tangentSpeed = nrm.w;
-	float4 soft = loadField( P, CF_SOFT, slot );
-	float4 roll = loadField( P, CF_ROLL, slot );
-	float4 pmass = loadField( P, CF_PMASS, slot );
-	float4 base = loadField( P, CF_BASE, slot );
+	float4 soft = loadField( V, CF_SOFT, slot );
+	float4 roll = loadField( V, CF_ROLL, slot );
+	float4 pmass = loadField( V, CF_PMASS, slot );
+	float4 base = loadField( V, CF_BASE, slot );
 	float normalMass[2] = { pmass.x, pmass.z };
 	float tangentMass[2] = { pmass.y, pmass.w };
 	float baseSeparation[2] = { base.x, base.y };
 
-	float4 imp[2] = { loadField( P, CF_IMP1, slot ), loadField( P, CF_IMP2, slot ) };
-	float4 anc[2] = { loadField( P, CF_ANCHOR1, slot ), loadField( P, CF_ANCHOR2, slot ) };
+	float4 imp[2] = { loadField( V, CF_IMP1, slot ), loadField( V, CF_IMP2, slot ) };
+	float4 anc[2] = { loadField( V, CF_ANCHOR1, slot ), loadField( V, CF_ANCHOR2, slot ) };
 
 	float totalNormalImpulse = 0.0f;
 
@@ -722,42 +725,42 @@ B2G_DEV void solveContactOverflow( const StepParams& P, int slot, bool useBias )
 		}
 	}
 
-	storeField( P, CF_IMP1, slot, imp[0] );
-	storeField( P, CF_IMP2, slot, imp[1] );
-	scatterVel( P, idx.x, make_float4( vA.x, vA.y, wA, sA.w ) );
-	scatterVel( P, idx.y, make_float4( vB.x, vB.y, wB, sB.w ) );
+	storeField( V, CF_IMP1, slot, imp[0] );
+	storeField( V, CF_IMP2, slot, imp[1] );
+	scatterVel( V, idx.x, make_float4( vA.x, vA.y, wA, sA.w ) );
+	scatterVel( V, idx.y, make_float4( vB.x, vB.y, wB, sB.w ) );
 }
 
 // b2ApplyRestitution_Overflow, src/contact_solver.c:410-514
-B2G_DEV void restitutionContactOverflow( const StepParams& P, int slot )
+B2G_DEV void restitutionContactOverflow( const StepParams& P, const SolveView& V, int slot )
 {
-	float4 roll = loadField( P, CF_ROLL, slot );
+	float4 roll = loadField( V, CF_ROLL, slot );
 	float restitution = roll.y;
 	if ( restitution == 0.0f )
 	{
 		return;
 	}
 
-	int2 idx = P.cidx[slot];
-	int pointCount = P.cmeta[slot].y & 3;
-	float4 mass = loadField( P, CF_MASS, slot );
+	int2 idx = V.cidx[slot];
+	int pointCount = V.cmeta[slot] & kMetaPointMask;
+	float4 mass = loadField( V, CF_MASS, slot );
 	float mA = mass.x, iA = mass.y, mB = mass.z, iB = mass.w;
 
-	float4 sA = gatherVel( P, idx.x );
-	float4 sB = gatherVel( P, idx.y );
+	float4 sA = gatherVel( V, idx.x );
+	float4 sB = gatherVel( V, idx.y );
 	V2 vA = v2( sA.x, sA.y );
 	float wA = sA.z;
 	V2 vB = v2( sB.x, sB.y );
 	float wB = sB.z;
 
-	float4 nrm = loadField( P, CF_NORMAL, slot );
+	float4 nrm = loadField( V, CF_NORMAL, slot );
 	V2 normal = v2( nrm.x, nrm.y );
-	float4 pmass = loadField( P, CF_PMASS, slot );
-	float4 base = loadField( P, CF_BASE, slot );
+	float4 pmass = loadField( V, CF_PMASS, slot );
+	float4 base = loadField( V, CF_BASE, slot );
 	float normalMass[2] = { pmass.x, pmass.z };
 	float relativeVelocity[2] = { base.z, base.w };
-	float4 imp[2] = { loadField( P, CF_IMP1, slot ), loadField( P, CF_IMP2, slot ) };
-	float4 anc[2] = { loadField( P, CF_ANCHOR1, slot ), loadField( P, CF_ANCHOR2, slot ) };
+	float4 imp[2] = { loadField( V, CF_IMP1, slot ), loadField( V, CF_IMP2, slot ) };
+	float4 anc[2] = { loadField( V, CF_ANCHOR1, slot ), loadField( V, CF_ANCHOR2, slot ) };
 	float threshold = P.restitutionThreshold;
 
 	for ( int j = 0; j < pointCount; ++j )
@@ -788,10 +791,10 @@ B2G_DEV void restitutionContactOverflow( const StepParams& P, int slot )
 		wB += iB * cross( rB, Pv );
 	}
 
-	storeField( P, CF_IMP1, slot, imp[0] );
-	storeField( P, CF_IMP2, slot, imp[1] );
-	scatterVel( P, idx.x, make_float4( vA.x, vA.y, wA, sA.w ) );
-	scatterVel( P, idx.y, make_float4( vB.x, vB.y, wB, sB.w ) );
+	storeField( V, CF_IMP1, slot, imp[0] );
+	storeField( V, CF_IMP2, slot, imp[1] );
+	scatterVel( V, idx.x, make_float4( vA.x, vA.y, wA, sA.w ) );
+	scatterVel( V, idx.y, make_float4( vB.x, vB.y, wB, sB.w ) );
 }
 
 } // namespace b2g

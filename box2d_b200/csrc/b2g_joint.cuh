@@ -40,55 +40,55 @@ B2G_DEV Rot deltaRot( float4 p )
 	return r;
 }
 
-B2G_DEV JointBodies gatherJointBodies( const StepParams& P, int indexA, int indexB )
+B2G_DEV JointBodies gatherJointBodies( const SolveView& V, int indexA, int indexB )
 {
 	JointBodies jb;
 	jb.a = indexA + 1; // B2_NULL_INDEX (-1) -> dummy
 	jb.b = indexB + 1;
-	jb.vA = gatherVel( P, jb.a );
-	jb.vB = gatherVel( P, jb.b );
-	jb.pA = gatherPos( P, jb.a );
-	jb.pB = gatherPos( P, jb.b );
+	jb.vA = gatherVel( V, jb.a );
+	jb.vB = gatherVel( V, jb.b );
+	jb.pA = gatherPos( V, jb.a );
+	jb.pB = gatherPos( V, jb.b );
 	return jb;
 }
 
-B2G_DEV void scatterJointBodies( const StepParams& P, const JointBodies& jb, V2 vA, float wA, V2 vB, float wB )
+B2G_DEV void scatterJointBodies( const SolveView& V, const JointBodies& jb, V2 vA, float wA, V2 vB, float wB )
 {
-	scatterVel( P, jb.a, make_float4( vA.x, vA.y, wA, jb.vA.w ) );
-	scatterVel( P, jb.b, make_float4( vB.x, vB.y, wB, jb.vB.w ) );
+	scatterVel( V, jb.a, make_float4( vA.x, vA.y, wA, jb.vA.w ) );
+	scatterVel( V, jb.b, make_float4( vB.x, vB.y, wB, jb.vB.w ) );
 }
 
 // Warm start helper shared by the types whose warm start is "apply linear impulse L at anchors + angular
 // impulse" written against the state directly (reference writes state->x -= ... under the dynamic flag).
-B2G_DEV void applyWarmStart( const StepParams& P, const JointBodies& jb, float mA, float iA, float mB, float iB, V2 linear, float LA,
+B2G_DEV void applyWarmStart( const SolveView& V, const JointBodies& jb, float mA, float iA, float mB, float iB, V2 linear, float LA,
 							 float LB )
 {
 	V2 vA = mulSub( v2( jb.vA.x, jb.vA.y ), mA, linear );
 	float wA = jb.vA.z - iA * LA;
 	V2 vB = mulAdd( v2( jb.vB.x, jb.vB.y ), mB, linear );
 	float wB = jb.vB.z + iB * LB;
-	scatterJointBodies( P, jb, vA, wA, vB, wB );
+	scatterJointBodies( V, jb, vA, wA, vB, wB );
 }
 
 // ---- revolute (src/revolute_joint.c:283-500) ----------------------------------------------------------------
-B2G_DEV void warmStartRevolute( const StepParams& P, b2lJointSim* base )
+B2G_DEV void warmStartRevolute( const StepParams& P, const SolveView& V, b2lJointSim* base )
 {
 	b2lRevolute* j = &base->u.revolute;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 	V2 rA = rotate( deltaRot( jb.pA ), toV2( j->frameA.p ) );
 	V2 rB = rotate( deltaRot( jb.pB ), toV2( j->frameB.p ) );
 	float axialImpulse = j->springImpulse + j->motorImpulse + j->lowerImpulse - j->upperImpulse;
 	V2 L = toV2( j->linearImpulse );
-	applyWarmStart( P, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, L, cross( rA, L ) + axialImpulse,
+	applyWarmStart( V, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, L, cross( rA, L ) + axialImpulse,
 					cross( rB, L ) + axialImpulse );
 }
 
-B2G_DEV void solveRevolute( const StepParams& P, b2lJointSim* base, bool useBias )
+B2G_DEV void solveRevolute( const StepParams& P, const SolveView& V, b2lJointSim* base, bool useBias )
 {
 	float mA = base->invMassA, mB = base->invMassB;
 	float iA = base->invIA, iB = base->invIB;
 	b2lRevolute* j = &base->u.revolute;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 
 	V2 vA = v2( jb.vA.x, jb.vA.y );
 	float wA = jb.vA.z;
@@ -239,27 +239,27 @@ B2G_DEV void solveRevolute( const StepParams& P, b2lJointSim* base, bool useBias
 		wB += iB * cross( rB, impulse );
 	}
 
-	scatterJointBodies( P, jb, vA, wA, vB, wB );
+	scatterJointBodies( V, jb, vA, wA, vB, wB );
 }
 
 // ---- weld (src/weld_joint.c:222-453, non-block path: B2_WELD_BLOCK_SOLVE 0) ------------------------------------
-B2G_DEV void warmStartWeld( const StepParams& P, b2lJointSim* base )
+B2G_DEV void warmStartWeld( const StepParams& P, const SolveView& V, b2lJointSim* base )
 {
 	b2lWeld* j = &base->u.weld;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 	V2 rA = rotate( deltaRot( jb.pA ), toV2( j->frameA.p ) );
 	V2 rB = rotate( deltaRot( jb.pB ), toV2( j->frameB.p ) );
 	V2 L = toV2( j->linearImpulse );
-	applyWarmStart( P, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, L, cross( rA, L ) + j->angularImpulse,
+	applyWarmStart( V, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, L, cross( rA, L ) + j->angularImpulse,
 					cross( rB, L ) + j->angularImpulse );
 }
 
-B2G_DEV void solveWeld( const StepParams& P, b2lJointSim* base, bool useBias )
+B2G_DEV void solveWeld( const StepParams& P, const SolveView& V, b2lJointSim* base, bool useBias )
 {
 	float mA = base->invMassA, mB = base->invMassB;
 	float iA = base->invIA, iB = base->invIB;
 	b2lWeld* j = &base->u.weld;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 
 	V2 vA = v2( jb.vA.x, jb.vA.y );
 	float wA = jb.vA.z;
@@ -333,14 +333,14 @@ B2G_DEV void solveWeld( const StepParams& P, b2lJointSim* base, bool useBias )
 		wB += iB * cross( rB, impulse );
 	}
 
-	scatterJointBodies( P, jb, vA, wA, vB, wB );
+	scatterJointBodies( V, jb, vA, wA, vB, wB );
 }
 
 // ---- prismatic (src/prismatic_joint.c:353-666) -----------------------------------------------------------------
-B2G_DEV void warmStartPrismatic( const StepParams& P, b2lJointSim* base )
+B2G_DEV void warmStartPrismatic( const StepParams& P, const SolveView& V, b2lJointSim* base )
 {
 	b2lPrismatic* j = &base->u.prismatic;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 	Rot dqA = deltaRot( jb.pA ), dqB = deltaRot( jb.pB );
 
 	V2 rA = rotate( dqA, toV2( j->frameA.p ) );
@@ -365,15 +365,15 @@ B2G_DEV void warmStartPrismatic( const StepParams& P, b2lJointSim* base )
 	float LA = axialImpulse * a1 + perpImpulse * s1 + angleImpulse;
 	float LB = axialImpulse * a2 + perpImpulse * s2 + angleImpulse;
 
-	applyWarmStart( P, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, Pv, LA, LB );
+	applyWarmStart( V, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, Pv, LA, LB );
 }
 
-B2G_DEV void solvePrismatic( const StepParams& P, b2lJointSim* base, bool useBias )
+B2G_DEV void solvePrismatic( const StepParams& P, const SolveView& V, b2lJointSim* base, bool useBias )
 {
 	float mA = base->invMassA, mB = base->invMassB;
 	float iA = base->invIA, iB = base->invIB;
 	b2lPrismatic* j = &base->u.prismatic;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 
 	V2 vA = v2( jb.vA.x, jb.vA.y );
 	float wA = jb.vA.z;
@@ -592,14 +592,14 @@ B2G_DEV void solvePrismatic( const StepParams& P, b2lJointSim* base, bool useBia
 		wB += iB * LB;
 	}
 
-	scatterJointBodies( P, jb, vA, wA, vB, wB );
+	scatterJointBodies( V, jb, vA, wA, vB, wB );
 }
 
 // ---- wheel (src/wheel_joint.c:280-523) -------------------------------------------------------------------------
-B2G_DEV void warmStartWheel( const StepParams& P, b2lJointSim* base )
+B2G_DEV void warmStartWheel( const StepParams& P, const SolveView& V, b2lJointSim* base )
 {
 	b2lWheel* j = &base->u.wheel;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 	Rot dqA = deltaRot( jb.pA ), dqB = deltaRot( jb.pB );
 
 	V2 rA = rotate( dqA, toV2( j->frameA.p ) );
@@ -621,15 +621,15 @@ B2G_DEV void warmStartWheel( const StepParams& P, b2lJointSim* base )
 	float LA = axialImpulse * a1 + j->perpImpulse * s1 + j->motorImpulse;
 	float LB = axialImpulse * a2 + j->perpImpulse * s2 + j->motorImpulse;
 
-	applyWarmStart( P, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, Pv, LA, LB );
+	applyWarmStart( V, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, Pv, LA, LB );
 }
 
-B2G_DEV void solveWheel( const StepParams& P, b2lJointSim* base, bool useBias )
+B2G_DEV void solveWheel( const StepParams& P, const SolveView& V, b2lJointSim* base, bool useBias )
 {
 	float mA = base->invMassA, mB = base->invMassB;
 	float iA = base->invIA, iB = base->invIB;
 	b2lWheel* j = &base->u.wheel;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 
 	V2 vA = v2( jb.vA.x, jb.vA.y );
 	float wA = jb.vA.z;
@@ -797,14 +797,14 @@ B2G_DEV void solveWheel( const StepParams& P, b2lJointSim* base, bool useBias )
 		wB += iB * LB;
 	}
 
-	scatterJointBodies( P, jb, vA, wA, vB, wB );
+	scatterJointBodies( V, jb, vA, wA, vB, wB );
 }
 
 // ---- distance (src/distance_joint.c:315-542) -------------------------------------------------------------------
-B2G_DEV void warmStartDistance( const StepParams& P, b2lJointSim* base )
+B2G_DEV void warmStartDistance( const StepParams& P, const SolveView& V, b2lJointSim* base )
 {
 	b2lDistance* j = &base->u.distance;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 
 	V2 rA = rotate( deltaRot( jb.pA ), toV2( j->anchorA ) );
 	V2 rB = rotate( deltaRot( jb.pB ), toV2( j->anchorB ) );
@@ -816,15 +816,15 @@ B2G_DEV void warmStartDistance( const StepParams& P, b2lJointSim* base )
 	float axialImpulse = j->impulse + j->lowerImpulse - j->upperImpulse + j->motorImpulse;
 	V2 Pv = mulSV( axialImpulse, axis );
 
-	applyWarmStart( P, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, Pv, cross( rA, Pv ), cross( rB, Pv ) );
+	applyWarmStart( V, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, Pv, cross( rA, Pv ), cross( rB, Pv ) );
 }
 
-B2G_DEV void solveDistance( const StepParams& P, b2lJointSim* base, bool useBias )
+B2G_DEV void solveDistance( const StepParams& P, const SolveView& V, b2lJointSim* base, bool useBias )
 {
 	float mA = base->invMassA, mB = base->invMassB;
 	float iA = base->invIA, iB = base->invIB;
 	b2lDistance* j = &base->u.distance;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 
 	V2 vA = v2( jb.vA.x, jb.vA.y );
 	float wA = jb.vA.z;
@@ -986,14 +986,14 @@ B2G_DEV void solveDistance( const StepParams& P, b2lJointSim* base, bool useBias
 		wB += iB * cross( rB, Pv );
 	}
 
-	scatterJointBodies( P, jb, vA, wA, vB, wB );
+	scatterJointBodies( V, jb, vA, wA, vB, wB );
 }
 
 // ---- motor (src/motor_joint.c:251-436) -------------------------------------------------------------------------
-B2G_DEV void warmStartMotor( const StepParams& P, b2lJointSim* base )
+B2G_DEV void warmStartMotor( const StepParams& P, const SolveView& V, b2lJointSim* base )
 {
 	b2lMotor* j = &base->u.motor;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 
 	V2 rA = rotate( deltaRot( jb.pA ), toV2( j->frameA.p ) );
 	V2 rB = rotate( deltaRot( jb.pB ), toV2( j->frameB.p ) );
@@ -1001,16 +1001,16 @@ B2G_DEV void warmStartMotor( const StepParams& P, b2lJointSim* base )
 	V2 linearImpulse = add( toV2( j->linearVelocityImpulse ), toV2( j->linearSpringImpulse ) );
 	float angularImpulse = j->angularVelocityImpulse + j->angularSpringImpulse;
 
-	applyWarmStart( P, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, linearImpulse,
+	applyWarmStart( V, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, linearImpulse,
 					cross( rA, linearImpulse ) + angularImpulse, cross( rB, linearImpulse ) + angularImpulse );
 }
 
-B2G_DEV void solveMotor( const StepParams& P, b2lJointSim* base )
+B2G_DEV void solveMotor( const StepParams& P, const SolveView& V, b2lJointSim* base )
 {
 	float mA = base->invMassA, mB = base->invMassB;
 	float iA = base->invIA, iB = base->invIB;
 	b2lMotor* j = &base->u.motor;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 
 	V2 vA = v2( jb.vA.x, jb.vA.y );
 	float wA = jb.vA.z;
@@ -1157,25 +1157,25 @@ B2G_DEV void solveMotor( const StepParams& P, b2lJointSim* base )
 		wB += iB * cross( rB, impulse );
 	}
 
-	scatterJointBodies( P, jb, vA, wA, vB, wB );
+	scatterJointBodies( V, jb, vA, wA, vB, wB );
 }
 
 // ---- mover (src/mover_joint.c:94-170) --------------------------------------------------------------------------
-B2G_DEV void warmStartMover( const StepParams& P, b2lJointSim* base )
+B2G_DEV void warmStartMover( const StepParams& P, const SolveView& V, b2lJointSim* base )
 {
 	b2lMover* j = &base->u.mover;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 	V2 L = toV2( j->linearVelocityImpulse );
 	V2 vA = mulSub( v2( jb.vA.x, jb.vA.y ), base->invMassA, L );
 	V2 vB = mulAdd( v2( jb.vB.x, jb.vB.y ), base->invMassB, L );
-	scatterJointBodies( P, jb, vA, jb.vA.z, vB, jb.vB.z );
+	scatterJointBodies( V, jb, vA, jb.vA.z, vB, jb.vB.z );
 }
 
-B2G_DEV void solveMover( const StepParams& P, b2lJointSim* base )
+B2G_DEV void solveMover( const StepParams& P, const SolveView& V, b2lJointSim* base )
 {
 	float mA = base->invMassA, mB = base->invMassB;
 	b2lMover* j = &base->u.mover;
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 
 	V2 vA = v2( jb.vA.x, jb.vA.y );
 	V2 vB = v2( jb.vB.x, jb.vB.y );
@@ -1207,11 +1207,11 @@ B2G_DEV void solveMover( const StepParams& P, b2lJointSim* base )
 		j->linearVelocityImpulse.y = 0.0f;
 	}
 
-	scatterJointBodies( P, jb, vA, jb.vA.z, vB, jb.vB.z );
+	scatterJointBodies( V, jb, vA, jb.vA.z, vB, jb.vB.z );
 }
 
 // ---- pogo (src/pogo_joint.c:160-281) ---------------------------------------------------------------------------
-B2G_DEV void warmStartPogo( const StepParams& P, b2lJointSim* base )
+B2G_DEV void warmStartPogo( const StepParams& P, const SolveView& V, b2lJointSim* base )
 {
 	b2lPogo* j = &base->u.pogo;
 	if ( j->hertz == 0.0f )
@@ -1220,16 +1220,16 @@ B2G_DEV void warmStartPogo( const StepParams& P, b2lJointSim* base )
 		return;
 	}
 
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 	V2 rA = rotate( deltaRot( jb.pA ), toV2( j->frameA.p ) );
 	V2 rB = rotate( deltaRot( jb.pB ), toV2( j->frameB.p ) );
 
 	V2 linearImpulse = mulSV( j->impulse, toV2( j->normal ) );
-	applyWarmStart( P, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, linearImpulse, cross( rA, linearImpulse ),
+	applyWarmStart( V, jb, base->invMassA, base->invIA, base->invMassB, base->invIB, linearImpulse, cross( rA, linearImpulse ),
 					cross( rB, linearImpulse ) );
 }
 
-B2G_DEV void solvePogo( const StepParams& P, b2lJointSim* base, bool useBias )
+B2G_DEV void solvePogo( const StepParams& P, const SolveView& V, b2lJointSim* base, bool useBias )
 {
 	float mA = base->invMassA, mB = base->invMassB;
 	float iA = base->invIA, iB = base->invIB;
@@ -1240,7 +1240,7 @@ B2G_DEV void solvePogo( const StepParams& P, b2lJointSim* base, bool useBias )
 		return;
 	}
 
-	JointBodies jb = gatherJointBodies( P, j->indexA, j->indexB );
+	JointBodies jb = gatherJointBodies( V, j->indexA, j->indexB );
 	V2 vA = v2( jb.vA.x, jb.vA.y );
 	float wA = jb.vA.z;
 	V2 vB = v2( jb.vB.x, jb.vB.y );
@@ -1281,70 +1281,96 @@ B2G_DEV void solvePogo( const StepParams& P, b2lJointSim* base, bool useBias )
 	vB = mulAdd( vB, mB, Pv );
 	wB += iB * cross( rB, Pv );
 
-	scatterJointBodies( P, jb, vA, wA, vB, wB );
+	scatterJointBodies( V, jb, vA, wA, vB, wB );
 }
 
-// ---- dispatch (src/joint.c:1454-1540) ----------------------------------------------------------------------------
-B2G_DEV void warmStartJoint( const StepParams& P, b2lJointSim* joint )
+// indexA (indexB follows it) of the per-type block: rewritten to the island-local numbering by the island kernel
+B2G_DEV int* jointIndexPair( b2lJointSim* joint )
 {
 	switch ( joint->type )
 	{
 		case b2l_distanceJoint:
-			warmStartDistance( P, joint );
+			return &joint->u.distance.indexA;
+		case b2l_motorJoint:
+			return &joint->u.motor.indexA;
+		case b2l_moverJoint:
+			return &joint->u.mover.indexA;
+		case b2l_pogoJoint:
+			return &joint->u.pogo.indexA;
+		case b2l_prismaticJoint:
+			return &joint->u.prismatic.indexA;
+		case b2l_revoluteJoint:
+			return &joint->u.revolute.indexA;
+		case b2l_weldJoint:
+			return &joint->u.weld.indexA;
+		case b2l_wheelJoint:
+			return &joint->u.wheel.indexA;
+		default:
+			return nullptr; // filter joint: no solver data
+	}
+}
+
+// ---- dispatch (src/joint.c:1454-1540) ----------------------------------------------------------------------------
+B2G_DEV void warmStartJoint( const StepParams& P, const SolveView& V, b2lJointSim* joint )
+{
+	switch ( joint->type )
+	{
+		case b2l_distanceJoint:
+			warmStartDistance( P, V, joint );
 			break;
 		case b2l_motorJoint:
-			warmStartMotor( P, joint );
+			warmStartMotor( P, V, joint );
 			break;
 		case b2l_moverJoint:
-			warmStartMover( P, joint );
+			warmStartMover( P, V, joint );
 			break;
 		case b2l_pogoJoint:
-			warmStartPogo( P, joint );
+			warmStartPogo( P, V, joint );
 			break;
 		case b2l_prismaticJoint:
-			warmStartPrismatic( P, joint );
+			warmStartPrismatic( P, V, joint );
 			break;
 		case b2l_revoluteJoint:
-			warmStartRevolute( P, joint );
+			warmStartRevolute( P, V, joint );
 			break;
 		case b2l_weldJoint:
-			warmStartWeld( P, joint );
+			warmStartWeld( P, V, joint );
 			break;
 		case b2l_wheelJoint:
-			warmStartWheel( P, joint );
+			warmStartWheel( P, V, joint );
 			break;
 		default: // filter joint: nothing to solve
 			break;
 	}
 }
 
-B2G_DEV void solveJoint( const StepParams& P, b2lJointSim* joint, bool useBias )
+B2G_DEV void solveJoint( const StepParams& P, const SolveView& V, b2lJointSim* joint, bool useBias )
 {
 	switch ( joint->type )
 	{
 		case b2l_distanceJoint:
-			solveDistance( P, joint, useBias );
+			solveDistance( P, V, joint, useBias );
 			break;
 		case b2l_motorJoint:
-			solveMotor( P, joint );
+			solveMotor( P, V, joint );
 			break;
 		case b2l_moverJoint:
-			solveMover( P, joint );
+			solveMover( P, V, joint );
 			break;
 		case b2l_pogoJoint:
-			solvePogo( P, joint, useBias );
+			solvePogo( P, V, joint, useBias );
 			break;
 		case b2l_prismaticJoint:
-			solvePrismatic( P, joint, useBias );
+			solvePrismatic( P, V, joint, useBias );
 			break;
 		case b2l_revoluteJoint:
-			solveRevolute( P, joint, useBias );
+			solveRevolute( P, V, joint, useBias );
 			break;
 		case b2l_weldJoint:
-			solveWeld( P, joint, useBias );
+			solveWeld( P, V, joint, useBias );
 			break;
 		case b2l_wheelJoint:
-			solveWheel( P, joint, useBias );
+			solveWheel( P, V, joint, useBias );
 			break;
 		default:
 			break;

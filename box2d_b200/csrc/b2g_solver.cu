@@ -13,6 +13,8 @@
 
 #include <cuda_runtime.h>
 
+#include <immintrin.h>
+
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -306,6 +308,8 @@ struct ControlBlock
 	unsigned long long stageCycles[10];
 };
 
+constexpr int kMaxColorSlots = b2g::kMaxColors + 1; // active colours + overflow
+
 struct b2GpuSolver
 {
 	int device = 0;
@@ -316,24 +320,44 @@ struct b2GpuSolver
 	cudaStream_t stream = nullptr;
 	cudaEvent_t evStart = nullptr, evStop = nullptr, evUpload = nullptr;
 
-	DeviceBuffer<uint8_t> rawStates, rawSims, rawContacts, rawJoints, joints, outStates;
-	DeviceBuffer<float4> vel, pos, bodyK, cf;
-	DeviceBuffer<float> angDamp, outImpulses;
-	DeviceBuffer<int2> cidx, cmeta;
-	DeviceBuffer<uint32_t> hitBits, jointBits;
+	// device: one input arena (mirror of the host wire staging), one output arena, the SoA solver state
+	DeviceBuffer<float4> wireAll, outAll, vel, pos, bodyK, cf;
+	DeviceBuffer<float> angDamp;
+	DeviceBuffer<int2> cidx;
+	DeviceBuffer<int> cmeta;
 	ControlBlock* control = nullptr;
 
-	PinnedBuffer<float> hImpulses;
-	PinnedBuffer<uint32_t> hBits;
+	// page-locked staging owned by the library.  The input staging is written with non-temporal stores: on the
+	// target hosts a DMA read of lines that sit dirty in several cores' caches runs at ~6 GB/s instead of ~53 GB/s
+	// (tools/microbench/h2d_bench.cu, profiles/).
+	PinnedBuffer<float4> hWire;
+	PinnedBuffer<float4> hOut;
 	ControlBlock* hControl = nullptr;
 
+	// arena layouts, in float4 units
+	size_t inStates = 0, inBody = 0, inWire = 0, inJoints = 0, inTotal = 0;
+	size_t outStates = 0, outImpulses = 0, outJoints = 0, outBits = 0, outTotal = 0;
+
+	// the step in flight
+	b2GpuStepDesc desc;
+	b2GpuStepResult* result = nullptr;
 	b2g::StepParams params;
+	int flatStart[kMaxColorSlots + 1];	// flat contact index of each colour slot's first contact (overflow last)
+	int slotStart[kMaxColorSlots];		// wire slot of each colour slot's first contact
+	int jointFlatStart[kMaxColorSlots + 1]; // flat joint index of each colour slot's first joint
+	int jointTotal = 0;
+	int colorSlotCount = 0;
+	int contactTotal = 0;
+	bool begun = false;
 	bool uploaded = false;
 	bool ran = false;
+
 	uint64_t launchCount = 0;
 	uint64_t lastH2D = 0;
+	uint64_t lastD2H = 0;
 	int lastLaunches = 0;
 	float lastKernelMs = 0.0f;
+	std::chrono::steady_clock::time_point tBegin, tSubmit, tWaited;
 };
 
 static int b2gRoundUp32( int n )
@@ -343,7 +367,7 @@ static int b2gRoundUp32( int n )
 
 extern "C" int b2GpuGetVersion( void )
 {
-	return 100;
+	return 101;
 }
 
 extern "C" const char* b2GpuGetLastError( void )
@@ -424,6 +448,7 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		return nullptr;
 	}
 	memset( &s->params, 0, sizeof( s->params ) );
+	memset( &s->desc, 0, sizeof( s->desc ) );
 	return s;
 }
 
@@ -438,24 +463,17 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	{
 		cudaStreamSynchronize( s->stream );
 	}
-	s->rawStates.release();
-	s->rawSims.release();
-	s->rawContacts.release();
-	s->rawJoints.release();
-	s->joints.release();
-	s->outStates.release();
+	s->wireAll.release();
+	s->outAll.release();
 	s->vel.release();
 	s->pos.release();
 	s->bodyK.release();
 	s->cf.release();
 	s->angDamp.release();
-	s->outImpulses.release();
 	s->cidx.release();
 	s->cmeta.release();
-	s->hitBits.release();
-	s->jointBits.release();
-	s->hImpulses.release();
-	s->hBits.release();
+	s->hWire.release();
+	s->hOut.release();
 	if ( s->control != nullptr )
 	{
 		cudaFree( s->control );
@@ -464,17 +482,12 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	{
 		cudaFreeHost( s->hControl );
 	}
-	if ( s->evStart != nullptr )
+	for ( cudaEvent_t ev : { s->evStart, s->evStop, s->evUpload } )
 	{
-		cudaEventDestroy( s->evStart );
-	}
-	if ( s->evStop != nullptr )
-	{
-		cudaEventDestroy( s->evStop );
-	}
-	if ( s->evUpload != nullptr )
-	{
-		cudaEventDestroy( s->evUpload );
+		if ( ev != nullptr )
+		{
+			cudaEventDestroy( ev );
+		}
 	}
 	if ( s->stream != nullptr )
 	{
@@ -498,20 +511,29 @@ extern "C" uint64_t b2GpuSolverGetLaunchCount( const b2GpuSolver* s )
 	return s != nullptr ? s->launchCount : 0;
 }
 
-// ---- upload ---------------------------------------------------------------------------------------------------
-extern "C" int b2GpuSolverUpload( b2GpuSolver* s, const b2GpuStepDesc* d )
+// ---- phase 1: layout --------------------------------------------------------------------------------------------
+static const b2GpuColorDesc& b2gColorSlot( const b2GpuStepDesc& d, int slot )
+{
+	return slot < d.activeColorCount ? d.colors[slot] : d.overflow;
+}
+
+extern "C" int b2GpuSolverBeginStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuStepResult* r )
 {
 	if ( s == nullptr || d == nullptr )
 	{
-		return b2gFailMsg( "b2GpuSolverUpload: null argument" );
+		return b2gFailMsg( "b2GpuSolverBeginStep: null argument" );
 	}
 	if ( d->activeColorCount < 0 || d->activeColorCount > b2g::kMaxColors || d->awakeBodyCount < 0 || d->subStepCount < 0 )
 	{
-		return b2gFailMsg( "b2GpuSolverUpload: bad descriptor" );
+		return b2gFailMsg( "b2GpuSolverBeginStep: bad descriptor" );
 	}
 	B2G_CUDA( cudaSetDevice( s->device ) );
+	s->tBegin = std::chrono::steady_clock::now();
+	s->begun = false;
 	s->uploaded = false;
 	s->ran = false;
+	s->desc = *d;
+	s->result = r;
 
 	b2g::StepParams& P = s->params;
 	memset( &P, 0, sizeof( P ) );
@@ -537,111 +559,270 @@ extern "C" int b2GpuSolverUpload( b2GpuSolver* s, const b2GpuStepDesc* d )
 	P.colorCount = d->activeColorCount;
 
 	// slot layout: every colour starts on a multiple of 32, overflow last
-	int slot = 0, joint = 0;
-	for ( int c = 0; c < d->activeColorCount; ++c )
+	s->colorSlotCount = d->activeColorCount + 1;
+	int slot = 0, joint = 0, flat = 0;
+	for ( int c = 0; c < s->colorSlotCount; ++c )
 	{
-		const b2GpuColorDesc& color = d->colors[c];
+		const b2GpuColorDesc& color = b2gColorSlot( *d, c );
 		if ( color.contactCount < 0 || color.jointCount < 0 )
 		{
-			return b2gFailMsg( "b2GpuSolverUpload: negative count" );
+			return b2gFailMsg( "b2GpuSolverBeginStep: negative count" );
 		}
-		P.colors[c].contactStart = slot;
-		P.colors[c].contactCount = color.contactCount;
-		P.colors[c].jointStart = joint;
-		P.colors[c].jointCount = color.jointCount;
+		b2g::ColorRange& range = c < d->activeColorCount ? P.colors[c] : P.overflow;
+		range.contactStart = slot;
+		range.contactCount = color.contactCount;
+		range.jointStart = joint;
+		range.jointCount = color.jointCount;
+		s->flatStart[c] = flat;
+		s->slotStart[c] = slot;
 		slot += b2gRoundUp32( color.contactCount );
 		joint += color.jointCount;
+		flat += color.contactCount;
 	}
-	P.overflow.contactStart = slot;
-	P.overflow.contactCount = d->overflow.contactCount;
-	P.overflow.jointStart = joint;
-	P.overflow.jointCount = d->overflow.jointCount;
-	slot += b2gRoundUp32( d->overflow.contactCount );
-	joint += d->overflow.jointCount;
+	s->flatStart[s->colorSlotCount] = flat;
+	s->contactTotal = flat;
+	for ( int c = 0; c < s->colorSlotCount; ++c )
+	{
+		const b2g::ColorRange& range = c < d->activeColorCount ? P.colors[c] : P.overflow;
+		s->jointFlatStart[c] = range.jointStart;
+	}
+	s->jointFlatStart[s->colorSlotCount] = joint;
+	s->jointTotal = joint;
 	P.contactSlots = slot;
 	P.jointCount = joint;
-	P.hitWords = 2 * ( ( d->contactIdCapacity + 63 ) / 64 );
 	P.jointWords = 2 * ( ( d->jointIdCapacity + 63 ) / 64 );
 
 	size_t bodies = (size_t)P.bodyCount;
-	B2G_CUDA( s->rawStates.reserve( bodies * B2L_STATE_SIZE + 16 ) );
-	B2G_CUDA( s->rawSims.reserve( bodies * B2L_SIM_SIZE + 16 ) );
-	B2G_CUDA( s->outStates.reserve( bodies * B2L_STATE_SIZE + 16 ) );
+	const size_t jointQuads = b2g::kJointStride / 16;
+	// input arena: [states 2/body][packed sims 2/body][contacts 7/slot][joints 16/joint]
+	s->inStates = 0;
+	s->inBody = s->inStates + 2 * bodies;
+	s->inWire = s->inBody + 2 * bodies;
+	s->inJoints = s->inWire + (size_t)b2g::WR_COUNT * slot;
+	s->inTotal = s->inJoints + jointQuads * joint;
+	// output arena: [states 2/body][impulse records][joints 16/joint][joint event bits]
+	size_t impulseQuads = ( (size_t)slot * b2g::kImpulseFloats + 3 ) / 4;
+	s->outStates = 0;
+	s->outImpulses = s->outStates + 2 * bodies;
+	s->outJoints = s->outImpulses + impulseQuads;
+	s->outBits = s->outJoints + jointQuads * joint;
+	s->outTotal = s->outBits + ( (size_t)P.jointWords + 3 ) / 4;
+
+	B2G_CUDA( s->wireAll.reserve( s->inTotal + 1 ) );
+	B2G_CUDA( s->hWire.reserve( s->inTotal + 1 ) );
+	B2G_CUDA( s->outAll.reserve( s->outTotal + 1 ) );
+	B2G_CUDA( s->hOut.reserve( s->outTotal + 1 ) );
 	B2G_CUDA( s->vel.reserve( bodies + 1 ) );
 	B2G_CUDA( s->pos.reserve( bodies + 1 ) );
 	B2G_CUDA( s->bodyK.reserve( bodies + 1 ) );
 	B2G_CUDA( s->angDamp.reserve( bodies + 1 ) );
-	B2G_CUDA( s->rawContacts.reserve( (size_t)slot * B2L_CONTACT_SIZE + 16 ) );
 	B2G_CUDA( s->cidx.reserve( (size_t)slot + 1 ) );
 	B2G_CUDA( s->cmeta.reserve( (size_t)slot + 1 ) );
 	// the SoA field stride follows cidx's capacity so that all per-slot arrays grow together
 	size_t slotCapacity = s->cidx.capacity;
 	B2G_CUDA( s->cf.reserve( slotCapacity * b2g::CF_COUNT ) );
-	B2G_CUDA( s->outImpulses.reserve( slotCapacity * b2g::kImpulseFloats ) );
-	B2G_CUDA( s->rawJoints.reserve( (size_t)joint * B2L_JOINT_SIZE + 16 ) );
-	B2G_CUDA( s->joints.reserve( (size_t)joint * B2L_JOINT_SIZE + 16 ) );
-	B2G_CUDA( s->hitBits.reserve( (size_t)P.hitWords + 2 ) );
-	B2G_CUDA( s->jointBits.reserve( (size_t)P.jointWords + 2 ) );
-	B2G_CUDA( s->hImpulses.reserve( (size_t)slot * b2g::kImpulseFloats + 16 ) );
-	B2G_CUDA( s->hBits.reserve( (size_t)P.hitWords + (size_t)P.jointWords + 4 ) );
-	P.slotCapacity = (int)slotCapacity;
 
-	P.rawStates = s->rawStates.ptr;
-	P.rawSims = s->rawSims.ptr;
-	P.rawContacts = s->rawContacts.ptr;
-	P.rawJoints = s->rawJoints.ptr;
-	P.vel = s->vel.ptr;
-	P.pos = s->pos.ptr;
-	P.bodyK = s->bodyK.ptr;
-	P.angDamp = s->angDamp.ptr;
-	P.cf = s->cf.ptr;
-	P.cidx = s->cidx.ptr;
-	P.cmeta = s->cmeta.ptr;
-	P.joints = s->joints.ptr;
-	P.outStates = s->outStates.ptr;
-	P.outImpulses = s->outImpulses.ptr;
-	P.hitBits = s->hitBits.ptr;
-	P.jointBits = s->jointBits.ptr;
+	P.rawStates = reinterpret_cast<const uint8_t*>( s->wireAll.ptr + s->inStates );
+	P.wireBody = s->wireAll.ptr + s->inBody;
+	P.wire = s->wireAll.ptr + s->inWire;
+	P.rawJoints = reinterpret_cast<const uint8_t*>( s->wireAll.ptr + s->inJoints );
+	P.g.vel = s->vel.ptr;
+	P.g.pos = s->pos.ptr;
+	P.g.bodyK = s->bodyK.ptr;
+	P.g.angDamp = s->angDamp.ptr;
+	P.g.cf = s->cf.ptr;
+	P.g.cfStride = (int)slotCapacity;
+	P.g.cidx = s->cidx.ptr;
+	P.g.cmeta = s->cmeta.ptr;
+	P.g.joints = reinterpret_cast<uint8_t*>( s->outAll.ptr + s->outJoints ); // the working copy IS the output
+	P.outStates = reinterpret_cast<uint8_t*>( s->outAll.ptr + s->outStates );
+	P.outImpulses = reinterpret_cast<float*>( s->outAll.ptr + s->outImpulses );
+	P.jointBits = reinterpret_cast<uint32_t*>( s->outAll.ptr + s->outBits );
 	P.hasHitEvents = &s->control->hasHitEvents;
 	P.anyRestitution = &s->control->anyRestitution;
 	P.barrier = s->control->barrier;
 	P.stageCycles = s->control->stageCycles;
 
-	// host -> device: the reference's own arrays, no host-side repacking
-	uint64_t bytes = 0;
+	s->begun = true;
+	return 0;
+}
+
+// pack items: [bodies][contacts, colour order, overflow last][joints, same order]
+extern "C" int b2GpuSolverGetPackItemCount( const b2GpuSolver* s )
+{
+	return s != nullptr && s->begun ? s->params.bodyCount + s->contactTotal + s->jointTotal : 0;
+}
+
+// unpack items: the same index space
+extern "C" int b2GpuSolverGetUnpackItemCount( const b2GpuSolver* s )
+{
+	return b2GpuSolverGetPackItemCount( s );
+}
+
+// ---- phase 2: pack the reference's arrays into the wire format (callable concurrently on disjoint ranges) ---------
+static inline float b2gRdF( const uint8_t* p, int offset )
+{
+	float v;
+	memcpy( &v, p + offset, 4 );
+	return v;
+}
+
+static inline float b2gIntBits( int v )
+{
+	float f;
+	memcpy( &f, &v, 4 );
+	return f;
+}
+
+static inline int b2gRdI( const uint8_t* p, int offset )
+{
+	int v;
+	memcpy( &v, p + offset, 4 );
+	return v;
+}
+
+static inline int b2gColorSlotOfFlat( const b2GpuSolver* s, int flat )
+{
+	int c = 0;
+	while ( s->flatStart[c + 1] <= flat )
+	{
+		c += 1;
+	}
+	return c;
+}
+
+static inline int b2gSlotOfFlat( const int* starts, int flat )
+{
+	int c = 0;
+	while ( starts[c + 1] <= flat )
+	{
+		c += 1;
+	}
+	return c;
+}
+
+// non-temporal 16-byte stores: the staging buffer must not stay dirty in the CPU caches (see b2GpuSolver::hWire)
+static inline void b2gStream4( float4* dst, float a, float b, float c, float d )
+{
+	_mm_stream_ps( reinterpret_cast<float*>( dst ), _mm_set_ps( d, c, b, a ) );
+}
+
+static inline void b2gStreamCopy( float4* dst, const uint8_t* src, int quads )
+{
+	for ( int q = 0; q < quads; ++q )
+	{
+		_mm_stream_si128( reinterpret_cast<__m128i*>( dst + q ), _mm_loadu_si128( reinterpret_cast<const __m128i*>( src + 16 * q ) ) );
+	}
+}
+
+extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
+{
+	const b2GpuStepDesc& d = s->desc;
+	int bodyCount = s->params.bodyCount;
+	float4* base = s->hWire.ptr;
+
+	// ---- bodies: the state as is + the 32 of b2BodySim's 96 bytes that integrate-velocities reads (src/solver.c:94-102)
+	{
+		const uint8_t* states = static_cast<const uint8_t*>( d.states );
+		const uint8_t* sims = static_cast<const uint8_t*>( d.sims );
+		float4* wireStates = base + s->inStates;
+		float4* wireBody = base + s->inBody;
+		int bodyEnd = end < bodyCount ? end : bodyCount;
+		for ( int i = begin; i < bodyEnd; ++i )
+		{
+			b2gStreamCopy( wireStates + 2 * (size_t)i, states + (size_t)i * B2L_STATE_SIZE, 2 );
+			const uint8_t* sim = sims + (size_t)i * B2L_SIM_SIZE;
+			b2gStream4( wireBody + 2 * (size_t)i + 0, b2gRdF( sim, B2L_SIM_INV_MASS ), b2gRdF( sim, B2L_SIM_INV_INERTIA ),
+						b2gRdF( sim, B2L_SIM_FORCE ), b2gRdF( sim, B2L_SIM_FORCE + 4 ) );
+			b2gStream4( wireBody + 2 * (size_t)i + 1, b2gRdF( sim, B2L_SIM_TORQUE ), b2gRdF( sim, B2L_SIM_LINEAR_DAMPING ),
+						b2gRdF( sim, B2L_SIM_ANGULAR_DAMPING ), b2gRdF( sim, B2L_SIM_GRAVITY_SCALE ) );
+		}
+	}
+
+	// ---- contacts: the 112 of b2ContactSim's 200 bytes that prepare reads (src/contact_solver.c:1629-1785)
+	{
+		float4* wire = base + s->inWire;
+		int flat = ( begin > bodyCount ? begin : bodyCount ) - bodyCount;
+		int flatEnd = ( end - bodyCount < s->contactTotal ? end - bodyCount : s->contactTotal );
+		int c = flat < flatEnd ? b2gSlotOfFlat( s->flatStart, flat ) : 0;
+		while ( flat < flatEnd )
+		{
+			const b2GpuColorDesc& color = b2gColorSlot( d, c );
+			int local = flat - s->flatStart[c];
+			int localEnd = ( flatEnd < s->flatStart[c + 1] ? flatEnd : s->flatStart[c + 1] ) - s->flatStart[c];
+			const uint8_t* sims = static_cast<const uint8_t*>( color.contactSims );
+			int colorIndex = color.colorIndex;
+			for ( int i = local; i < localEnd; ++i )
+			{
+				const uint8_t* sim = sims + (size_t)i * B2L_CONTACT_SIZE;
+				const uint8_t* m = sim + B2L_CONTACT_MANIFOLD;
+				const uint8_t* p0 = m + B2L_MANIFOLD_POINTS;
+				const uint8_t* p1 = p0 + B2L_MP_SIZE;
+				int pointCount = b2gRdI( m, B2L_MANIFOLD_POINT_COUNT );
+				int hitEnable = ( (uint32_t)b2gRdI( sim, B2L_CONTACT_SIM_FLAGS ) & B2L_SIM_ENABLE_HIT_EVENT ) != 0 ? b2g::kMetaHitEnable : 0;
+				int meta = ( colorIndex << b2g::kMetaColorShift ) | hitEnable | ( pointCount & b2g::kMetaPointMask );
+				float4* w = wire + (size_t)( s->slotStart[c] + i ) * b2g::WR_COUNT;
+				b2gStream4( w + b2g::WR_HEAD, b2gIntBits( b2gRdI( sim, B2L_CONTACT_INDEX_A ) ), b2gIntBits( b2gRdI( sim, B2L_CONTACT_INDEX_B ) ),
+							b2gIntBits( meta ), b2gRdF( m, B2L_MANIFOLD_ROLLING_IMPULSE ) );
+				b2gStream4( w + b2g::WR_MASS, b2gRdF( sim, B2L_CONTACT_INV_MASS_A ), b2gRdF( sim, B2L_CONTACT_INV_I_A ),
+							b2gRdF( sim, B2L_CONTACT_INV_MASS_B ), b2gRdF( sim, B2L_CONTACT_INV_I_B ) );
+				b2gStream4( w + b2g::WR_NORMAL, b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ),
+							b2gRdF( sim, B2L_CONTACT_FRICTION ), b2gRdF( sim, B2L_CONTACT_TANGENT_SPEED ) );
+				b2gStream4( w + b2g::WR_MATERIAL, b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ), b2gRdF( sim, B2L_CONTACT_RESTITUTION ),
+							b2gRdF( p0, B2L_MP_SEPARATION ), b2gRdF( p1, B2L_MP_SEPARATION ) );
+				b2gStream4( w + b2g::WR_ANCHOR1, b2gRdF( p0, B2L_MP_ANCHOR_A ), b2gRdF( p0, B2L_MP_ANCHOR_A + 4 ),
+							b2gRdF( p0, B2L_MP_ANCHOR_B ), b2gRdF( p0, B2L_MP_ANCHOR_B + 4 ) );
+				b2gStream4( w + b2g::WR_ANCHOR2, b2gRdF( p1, B2L_MP_ANCHOR_A ), b2gRdF( p1, B2L_MP_ANCHOR_A + 4 ),
+							b2gRdF( p1, B2L_MP_ANCHOR_B ), b2gRdF( p1, B2L_MP_ANCHOR_B + 4 ) );
+				b2gStream4( w + b2g::WR_IMPULSE, b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ),
+							b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ) );
+			}
+			flat = s->flatStart[c + 1];
+			c += 1;
+		}
+	}
+
+	// ---- joints: the prepared b2JointSim as is, padded to 256 bytes
+	{
+		float4* wireJoints = base + s->inJoints;
+		int first = bodyCount + s->contactTotal;
+		int flat = ( begin > first ? begin : first ) - first;
+		int flatEnd = end - first;
+		int c = flat < flatEnd ? b2gSlotOfFlat( s->jointFlatStart, flat ) : 0;
+		while ( flat < flatEnd )
+		{
+			const b2GpuColorDesc& color = b2gColorSlot( d, c );
+			int local = flat - s->jointFlatStart[c];
+			int localEnd = ( flatEnd < s->jointFlatStart[c + 1] ? flatEnd : s->jointFlatStart[c + 1] ) - s->jointFlatStart[c];
+			const uint8_t* sims = static_cast<const uint8_t*>( color.jointSims );
+			for ( int i = local; i < localEnd; ++i )
+			{
+				uint8_t padded[b2g::kJointStride] = { 0 };
+				memcpy( padded, sims + (size_t)i * B2L_JOINT_SIZE, B2L_JOINT_SIZE );
+				b2gStreamCopy( wireJoints + (size_t)( s->jointFlatStart[c] + i ) * ( b2g::kJointStride / 16 ), padded, b2g::kJointStride / 16 );
+			}
+			flat = s->jointFlatStart[c + 1];
+			c += 1;
+		}
+	}
+	_mm_sfence();
+}
+
+// ---- phase 3: H2D + kernels + D2H, all asynchronous on the solver's stream -------------------------------------------
+static int b2gEnqueueUpload( b2GpuSolver* s )
+{
 	cudaStream_t st = s->stream;
 	B2G_CUDA( cudaEventRecord( s->evUpload, st ) );
-	if ( bodies > 0 )
+	size_t bytes = s->inTotal * sizeof( float4 );
+	if ( bytes > 0 )
 	{
-		B2G_CUDA( cudaMemcpyAsync( s->rawStates.ptr, d->states, bodies * B2L_STATE_SIZE, cudaMemcpyHostToDevice, st ) );
-		B2G_CUDA( cudaMemcpyAsync( s->rawSims.ptr, d->sims, bodies * B2L_SIM_SIZE, cudaMemcpyHostToDevice, st ) );
-		bytes += bodies * ( B2L_STATE_SIZE + B2L_SIM_SIZE );
-	}
-	for ( int c = 0; c <= d->activeColorCount; ++c )
-	{
-		const b2GpuColorDesc& color = c < d->activeColorCount ? d->colors[c] : d->overflow;
-		const b2g::ColorRange& range = c < d->activeColorCount ? P.colors[c] : P.overflow;
-		if ( color.contactCount > 0 )
-		{
-			size_t n = (size_t)color.contactCount * B2L_CONTACT_SIZE;
-			B2G_CUDA( cudaMemcpyAsync( s->rawContacts.ptr + (size_t)range.contactStart * B2L_CONTACT_SIZE, color.contactSims, n,
-									   cudaMemcpyHostToDevice, st ) );
-			bytes += n;
-		}
-		if ( color.jointCount > 0 )
-		{
-			size_t n = (size_t)color.jointCount * B2L_JOINT_SIZE;
-			B2G_CUDA( cudaMemcpyAsync( s->rawJoints.ptr + (size_t)range.jointStart * B2L_JOINT_SIZE, color.jointSims, n,
-									   cudaMemcpyHostToDevice, st ) );
-			bytes += n;
-		}
+		B2G_CUDA( cudaMemcpyAsync( s->wireAll.ptr, s->hWire.ptr, bytes, cudaMemcpyHostToDevice, st ) );
 	}
 	s->lastH2D = bytes;
 	s->uploaded = true;
 	return 0;
 }
 
-// ---- run -----------------------------------------------------------------------------------------------------
 static int b2gLaunchStage( b2GpuSolver* s, int op, int color, int blocks )
 {
 	b2g::b2gStageKernel<<<blocks, b2g::kBlockThreads, 0, s->stream>>>( s->params, op, color );
@@ -748,6 +929,135 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 	return 0;
 }
 
+static int b2gEnqueueDownload( b2GpuSolver* s )
+{
+	cudaStream_t st = s->stream;
+	size_t bytes = s->outTotal * sizeof( float4 );
+	if ( bytes > 0 )
+	{
+		B2G_CUDA( cudaMemcpyAsync( s->hOut.ptr, s->outAll.ptr, bytes, cudaMemcpyDeviceToHost, st ) );
+	}
+	B2G_CUDA( cudaMemcpyAsync( s->hControl, s->control, sizeof( ControlBlock ), cudaMemcpyDeviceToHost, st ) );
+	s->lastD2H = bytes + sizeof( ControlBlock );
+	return 0;
+}
+
+extern "C" int b2GpuSolverSubmit( b2GpuSolver* s )
+{
+	if ( s == nullptr || !s->begun )
+	{
+		return b2gFailMsg( "b2GpuSolverSubmit: no step begun" );
+	}
+	s->tSubmit = std::chrono::steady_clock::now();
+	if ( b2gEnqueueUpload( s ) != 0 || b2gEnqueueRun( s ) != 0 || b2gEnqueueDownload( s ) != 0 )
+	{
+		return 1;
+	}
+	return 0;
+}
+
+extern "C" int b2GpuSolverWait( b2GpuSolver* s )
+{
+	if ( s == nullptr )
+	{
+		return b2gFailMsg( "b2GpuSolverWait: null solver" );
+	}
+	B2G_CUDA( cudaStreamSynchronize( s->stream ) );
+	s->tWaited = std::chrono::steady_clock::now();
+	if ( s->ran )
+	{
+		B2G_CUDA( cudaEventElapsedTime( &s->lastKernelMs, s->evStart, s->evStop ) );
+	}
+	return 0;
+}
+
+// ---- phase 4: unpack (callable concurrently on disjoint ranges) ---------------------------------------------------------
+// Scatter the packed impulse records into the reference's manifolds: what b2StoreImpulsesTask
+// (src/contact_solver.c:2293-2320) and b2StoreImpulses_Overflow (:526-542) write.
+extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
+{
+	const b2GpuStepDesc& d = s->desc;
+	if ( begin >= end )
+	{
+		return;
+	}
+	int bodyCount = s->params.bodyCount;
+	const float4* base = s->hOut.ptr;
+
+	// ---- body states
+	{
+		uint8_t* states = static_cast<uint8_t*>( d.states );
+		const float4* outStates = base + s->outStates;
+		int bodyEnd = end < bodyCount ? end : bodyCount;
+		if ( begin < bodyEnd )
+		{
+			memcpy( states + (size_t)begin * B2L_STATE_SIZE, outStates + 2 * (size_t)begin, (size_t)( bodyEnd - begin ) * B2L_STATE_SIZE );
+		}
+	}
+
+	// ---- contact impulses
+	{
+		uint64_t* hitBits = s->result != nullptr ? s->result->hitEventBits : nullptr;
+		const float* allRecords = reinterpret_cast<const float*>( base + s->outImpulses );
+		int flat = ( begin > bodyCount ? begin : bodyCount ) - bodyCount;
+		int flatEnd = ( end - bodyCount < s->contactTotal ? end - bodyCount : s->contactTotal );
+		int c = flat < flatEnd ? b2gSlotOfFlat( s->flatStart, flat ) : 0;
+		while ( flat < flatEnd )
+		{
+			bool wide = c < d.activeColorCount;
+			const b2GpuColorDesc& color = b2gColorSlot( d, c );
+			int local = flat - s->flatStart[c];
+			int localEnd = ( flatEnd < s->flatStart[c + 1] ? flatEnd : s->flatStart[c + 1] ) - s->flatStart[c];
+			uint8_t* sims = static_cast<uint8_t*>( color.contactSims );
+			const float* records = allRecords + (size_t)s->slotStart[c] * b2g::kImpulseFloats;
+			for ( int i = local; i < localEnd; ++i )
+			{
+				uint8_t* sim = sims + (size_t)i * B2L_CONTACT_SIZE;
+				uint8_t* manifold = sim + B2L_CONTACT_MANIFOLD;
+				const float* rec = records + (size_t)i * b2g::kImpulseFloats;
+				int pointCount = wide ? 2 : b2gRdI( manifold, B2L_MANIFOLD_POINT_COUNT );
+				memcpy( manifold + B2L_MANIFOLD_ROLLING_IMPULSE, rec + 0, 4 );
+				for ( int j = 0; j < pointCount; ++j )
+				{
+					uint8_t* mp = manifold + B2L_MANIFOLD_POINTS + j * B2L_MP_SIZE;
+					// normalImpulse, tangentImpulse, totalNormalImpulse, normalVelocity are contiguous (collision.h:549-561)
+					memcpy( mp + B2L_MP_NORMAL_IMPULSE, rec + 1 + 4 * j, 16 );
+				}
+				if ( rec[9] != 0.0f && hitBits != nullptr )
+				{
+					uint32_t id = (uint32_t)b2gRdI( sim, B2L_CONTACT_ID );
+					__atomic_fetch_or( hitBits + ( id >> 6 ), (uint64_t)1 << ( id & 63u ), __ATOMIC_RELAXED );
+				}
+			}
+			flat = s->flatStart[c + 1];
+			c += 1;
+		}
+	}
+
+	// ---- joints (accumulated impulses live in the record itself)
+	{
+		const uint8_t* outJoints = reinterpret_cast<const uint8_t*>( base + s->outJoints );
+		int first = bodyCount + s->contactTotal;
+		int flat = ( begin > first ? begin : first ) - first;
+		int flatEnd = end - first;
+		int c = flat < flatEnd ? b2gSlotOfFlat( s->jointFlatStart, flat ) : 0;
+		while ( flat < flatEnd )
+		{
+			const b2GpuColorDesc& color = b2gColorSlot( d, c );
+			int local = flat - s->jointFlatStart[c];
+			int localEnd = ( flatEnd < s->jointFlatStart[c + 1] ? flatEnd : s->jointFlatStart[c + 1] ) - s->jointFlatStart[c];
+			uint8_t* sims = static_cast<uint8_t*>( color.jointSims );
+			for ( int i = local; i < localEnd; ++i )
+			{
+				memcpy( sims + (size_t)i * B2L_JOINT_SIZE, outJoints + (size_t)( s->jointFlatStart[c] + i ) * b2g::kJointStride,
+						B2L_JOINT_SIZE );
+			}
+			flat = s->jointFlatStart[c + 1];
+			c += 1;
+		}
+	}
+}
+
 static void b2gFillTimers( b2GpuSolver* s, b2GpuStepResult* r )
 {
 	// stage split from the in-kernel cycle counters, scaled to the CUDA-event kernel time
@@ -762,6 +1072,79 @@ static void b2gFillTimers( b2GpuSolver* s, b2GpuStepResult* r )
 		r->stageMs[i] = total > 0 ? s->lastKernelMs * (float)( (double)c->stageCycles[i] / (double)total ) : 0.0f;
 	}
 	r->gridBarriers = (int)c->stageCycles[8];
+}
+
+extern "C" int b2GpuSolverEndStep( b2GpuSolver* s, b2GpuStepResult* r )
+{
+	if ( s == nullptr || !s->begun )
+	{
+		return b2gFailMsg( "b2GpuSolverEndStep: no step begun" );
+	}
+	const b2g::StepParams& P = s->params;
+	auto ms = []( std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b ) {
+		return std::chrono::duration<float, std::milli>( b - a ).count();
+	};
+	if ( r != nullptr )
+	{
+		// uint32 pairs are the little-endian halves of the reference's uint64 blocks (src/bitset.h)
+		if ( r->jointEventBits != nullptr )
+		{
+			const uint32_t* bits = reinterpret_cast<const uint32_t*>( s->hOut.ptr + s->outBits );
+			for ( int i = 0; i < P.jointWords / 2; ++i )
+			{
+				uint64_t word = (uint64_t)bits[2 * i] | ( (uint64_t)bits[2 * i + 1] << 32 );
+				r->jointEventBits[i] |= word;
+			}
+		}
+		r->hasHitEvents = s->hControl->hasHitEvents;
+		r->kernelMs = s->lastKernelMs;
+		r->kernelLaunches = s->lastLaunches;
+		r->h2dBytes = s->lastH2D;
+		r->d2hBytes = s->lastD2H;
+		b2gFillTimers( s, r );
+		auto now = std::chrono::steady_clock::now();
+		r->uploadMs = ms( s->tBegin, s->tSubmit );	 // layout + packing
+		r->waitMs = ms( s->tSubmit, s->tWaited );	 // H2D + kernels + D2H
+		r->scatterMs = ms( s->tWaited, now );		 // unpack + event bits
+		r->h2dMs = 0.0f;
+		cudaEventElapsedTime( &r->h2dMs, s->evUpload, s->evStart );
+		r->totalMs = ms( s->tBegin, now );
+	}
+	s->begun = false;
+	return 0;
+}
+
+// ---- the whole step, single host thread ----------------------------------------------------------------------------------
+extern "C" int b2GpuSolverStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuStepResult* r )
+{
+	if ( b2GpuSolverBeginStep( s, d, r ) != 0 )
+	{
+		return 1;
+	}
+	b2GpuSolverPackRange( s, 0, b2GpuSolverGetPackItemCount( s ) );
+	if ( b2GpuSolverSubmit( s ) != 0 || b2GpuSolverWait( s ) != 0 )
+	{
+		return 1;
+	}
+	b2GpuSolverUnpackRange( s, 0, b2GpuSolverGetUnpackItemCount( s ) );
+	return b2GpuSolverEndStep( s, r );
+}
+
+// ---- split for benchmarks: Upload (pack + H2D), Run (kernels only, repeatable), Download (D2H + unpack) -------------------
+extern "C" int b2GpuSolverUpload( b2GpuSolver* s, const b2GpuStepDesc* d )
+{
+	if ( b2GpuSolverBeginStep( s, d, nullptr ) != 0 )
+	{
+		return 1;
+	}
+	b2GpuSolverPackRange( s, 0, b2GpuSolverGetPackItemCount( s ) );
+	s->tSubmit = std::chrono::steady_clock::now();
+	if ( b2gEnqueueUpload( s ) != 0 )
+	{
+		return 1;
+	}
+	B2G_CUDA( cudaStreamSynchronize( s->stream ) );
+	return 0;
 }
 
 extern "C" int b2GpuSolverRun( b2GpuSolver* s, b2GpuStepResult* r )
@@ -787,179 +1170,25 @@ extern "C" int b2GpuSolverRun( b2GpuSolver* s, b2GpuStepResult* r )
 	return 0;
 }
 
-// ---- download --------------------------------------------------------------------------------------------------
-static int b2gEnqueueDownload( b2GpuSolver* s, const b2GpuStepDesc* d, uint64_t* bytesOut )
-{
-	const b2g::StepParams& P = s->params;
-	cudaStream_t st = s->stream;
-	uint64_t bytes = 0;
-	size_t bodies = (size_t)P.bodyCount;
-	if ( bodies > 0 )
-	{
-		B2G_CUDA( cudaMemcpyAsync( d->states, s->outStates.ptr, bodies * B2L_STATE_SIZE, cudaMemcpyDeviceToHost, st ) );
-		bytes += bodies * B2L_STATE_SIZE;
-	}
-	if ( P.contactSlots > 0 )
-	{
-		size_t n = (size_t)P.contactSlots * b2g::kImpulseFloats * sizeof( float );
-		B2G_CUDA( cudaMemcpyAsync( s->hImpulses.ptr, s->outImpulses.ptr, n, cudaMemcpyDeviceToHost, st ) );
-		bytes += n;
-	}
-	for ( int c = 0; c <= d->activeColorCount; ++c )
-	{
-		const b2GpuColorDesc& color = c < d->activeColorCount ? d->colors[c] : d->overflow;
-		const b2g::ColorRange& range = c < d->activeColorCount ? P.colors[c] : P.overflow;
-		if ( color.jointCount > 0 )
-		{
-			size_t n = (size_t)color.jointCount * B2L_JOINT_SIZE;
-			B2G_CUDA( cudaMemcpyAsync( color.jointSims, s->joints.ptr + (size_t)range.jointStart * B2L_JOINT_SIZE, n,
-									   cudaMemcpyDeviceToHost, st ) );
-			bytes += n;
-		}
-	}
-	if ( P.hitWords > 0 )
-	{
-		B2G_CUDA( cudaMemcpyAsync( s->hBits.ptr, s->hitBits.ptr, (size_t)P.hitWords * 4, cudaMemcpyDeviceToHost, st ) );
-		bytes += (uint64_t)P.hitWords * 4;
-	}
-	if ( P.jointWords > 0 )
-	{
-		B2G_CUDA( cudaMemcpyAsync( s->hBits.ptr + P.hitWords, s->jointBits.ptr, (size_t)P.jointWords * 4, cudaMemcpyDeviceToHost, st ) );
-		bytes += (uint64_t)P.jointWords * 4;
-	}
-	B2G_CUDA( cudaMemcpyAsync( s->hControl, s->control, sizeof( ControlBlock ), cudaMemcpyDeviceToHost, st ) );
-	bytes += sizeof( ControlBlock );
-	*bytesOut = bytes;
-	return 0;
-}
-
-// Scatter the packed impulse records into the reference's manifolds: what b2StoreImpulsesTask
-// (src/contact_solver.c:2293-2303) and b2StoreImpulses_Overflow (:526-542) write.
-static void b2gScatterImpulses( const b2GpuSolver* s, const b2GpuStepDesc* d )
-{
-	const b2g::StepParams& P = s->params;
-	for ( int c = 0; c <= d->activeColorCount; ++c )
-	{
-		bool wide = c < d->activeColorCount;
-		const b2GpuColorDesc& color = wide ? d->colors[c] : d->overflow;
-		const b2g::ColorRange& range = wide ? P.colors[c] : P.overflow;
-		uint8_t* sims = static_cast<uint8_t*>( color.contactSims );
-		const float* records = s->hImpulses.ptr + (size_t)range.contactStart * b2g::kImpulseFloats;
-		for ( int i = 0; i < color.contactCount; ++i )
-		{
-			uint8_t* manifold = sims + (size_t)i * B2L_CONTACT_SIZE + B2L_CONTACT_MANIFOLD;
-			const float* rec = records + (size_t)i * b2g::kImpulseFloats;
-			int pointCount = wide ? 2 : *reinterpret_cast<const int*>( manifold + B2L_MANIFOLD_POINT_COUNT );
-			*reinterpret_cast<float*>( manifold + B2L_MANIFOLD_ROLLING_IMPULSE ) = rec[0];
-			for ( int j = 0; j < pointCount; ++j )
-			{
-				uint8_t* mp = manifold + B2L_MANIFOLD_POINTS + j * B2L_MP_SIZE;
-				const float* pr = rec + 1 + 4 * j;
-				*reinterpret_cast<float*>( mp + B2L_MP_NORMAL_IMPULSE ) = pr[0];
-				*reinterpret_cast<float*>( mp + B2L_MP_TANGENT_IMPULSE ) = pr[1];
-				*reinterpret_cast<float*>( mp + B2L_MP_TOTAL_NORMAL_IMPULSE ) = pr[2];
-				*reinterpret_cast<float*>( mp + B2L_MP_NORMAL_VELOCITY ) = pr[3];
-			}
-		}
-	}
-}
-
-static void b2gFinishDownload( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuStepResult* r )
-{
-	const b2g::StepParams& P = s->params;
-	b2gScatterImpulses( s, d );
-	if ( r != nullptr )
-	{
-		// uint32 pairs are the little-endian halves of the reference's uint64 blocks (src/bitset.h)
-		if ( r->hitEventBits != nullptr )
-		{
-			const uint64_t* src = reinterpret_cast<const uint64_t*>( s->hBits.ptr );
-			for ( int i = 0; i < P.hitWords / 2; ++i )
-			{
-				r->hitEventBits[i] |= src[i];
-			}
-		}
-		if ( r->jointEventBits != nullptr )
-		{
-			for ( int i = 0; i < P.jointWords / 2; ++i )
-			{
-				uint64_t word = (uint64_t)s->hBits.ptr[P.hitWords + 2 * i] | ( (uint64_t)s->hBits.ptr[P.hitWords + 2 * i + 1] << 32 );
-				r->jointEventBits[i] |= word;
-			}
-		}
-		r->hasHitEvents = s->hControl->hasHitEvents;
-	}
-}
-
 extern "C" int b2GpuSolverDownload( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuStepResult* r )
 {
 	if ( s == nullptr || d == nullptr )
 	{
 		return b2gFailMsg( "b2GpuSolverDownload: null argument" );
 	}
-	if ( !s->ran )
+	if ( !s->ran || !s->begun )
 	{
 		return b2gFailMsg( "b2GpuSolverDownload: nothing has run" );
 	}
-	B2G_CUDA( cudaSetDevice( s->device ) );
-	uint64_t bytes = 0;
-	if ( b2gEnqueueDownload( s, d, &bytes ) != 0 )
+	s->desc = *d;
+	s->result = r;
+	if ( b2gEnqueueDownload( s ) != 0 || b2GpuSolverWait( s ) != 0 )
 	{
 		return 1;
 	}
-	B2G_CUDA( cudaStreamSynchronize( s->stream ) );
-	b2gFinishDownload( s, d, r );
-	if ( r != nullptr )
-	{
-		r->d2hBytes = bytes;
-	}
-	return 0;
+	b2GpuSolverUnpackRange( s, 0, b2GpuSolverGetUnpackItemCount( s ) );
+	return b2GpuSolverEndStep( s, r );
 }
-
-// ---- the whole step --------------------------------------------------------------------------------------------
-extern "C" int b2GpuSolverStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuStepResult* r )
-{
-	using clock = std::chrono::steady_clock;
-	auto ms = []( clock::time_point a, clock::time_point b ) { return std::chrono::duration<float, std::milli>( b - a ).count(); };
-	auto t0 = clock::now();
-	if ( b2GpuSolverUpload( s, d ) != 0 )
-	{
-		return 1;
-	}
-	auto t1 = clock::now();
-	if ( b2gEnqueueRun( s ) != 0 )
-	{
-		return 1;
-	}
-	uint64_t d2h = 0;
-	if ( b2gEnqueueDownload( s, d, &d2h ) != 0 )
-	{
-		return 1;
-	}
-	B2G_CUDA( cudaStreamSynchronize( s->stream ) );
-	auto t2 = clock::now();
-	B2G_CUDA( cudaEventElapsedTime( &s->lastKernelMs, s->evStart, s->evStop ) );
-	b2gFinishDownload( s, d, r );
-	auto t3 = clock::now();
-	if ( r != nullptr )
-	{
-		r->kernelMs = s->lastKernelMs;
-		r->kernelLaunches = s->lastLaunches;
-		r->h2dBytes = s->lastH2D;
-		r->d2hBytes = d2h;
-		b2gFillTimers( s, r );
-		r->uploadMs = ms( t0, t1 );
-		r->waitMs = ms( t1, t2 );
-		r->scatterMs = ms( t2, t3 );
-		r->h2dMs = 0.0f;
-		cudaEventElapsedTime( &r->h2dMs, s->evUpload, s->evStart );
-		r->totalMs = ms( t0, clock::now() );
-	}
-	return 0;
-}
-
-// ---- batch of independent worlds (implemented in b2g_batch.cu) ----------------------------------------------------
-// see b2g_batch.cu
 
 // =================================================================================================================
 // Page-locked host allocator for b2SetAllocator (include/box2d/base.h:86)

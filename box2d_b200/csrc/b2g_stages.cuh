@@ -17,56 +17,54 @@ constexpr float kMaxRotation = 0.25f * kPi; // B2_MAX_ROTATION, include/box2d/co
 
 // ---- body stages --------------------------------------------------------------------------------------------
 
-// AoS -> SoA + per-step body constants.  The velocity increment of b2IntegrateVelocitiesTask
-// (src/solver.c:94-102) depends only on per-step constants, so it is evaluated once here with the same
-// operations and reused by every sub-step.
-B2G_DEV void loadBody( const StepParams& P, int i )
+// Per-step body constants.  The velocity increment of b2IntegrateVelocitiesTask (src/solver.c:94-102) depends only
+// on per-step constants, so it is evaluated once here with the same operations and reused by every sub-step.
+// `body` is the global body index (wire order), `local` the 1-based index in the view.
+B2G_DEV void loadBody( const StepParams& P, const SolveView& V, int body, int local )
 {
-	const uint8_t* s = P.rawStates + (size_t)i * B2L_STATE_SIZE;
-	const float4* s4 = reinterpret_cast<const float4*>( s );
-	float4 v = s4[0];
-	float4 p = s4[1];
-	__stcg( P.vel + i + 1, v );
-	__stcg( P.pos + i + 1, p );
+	const float4* s4 = reinterpret_cast<const float4*>( P.rawStates + (size_t)body * B2L_STATE_SIZE );
+	V.vel[local] = s4[0];
+	V.pos[local] = s4[1];
 
-	const uint8_t* sim = P.rawSims + (size_t)i * B2L_SIM_SIZE;
-	float invMass = rawF( sim, B2L_SIM_INV_MASS );
-	float invInertia = rawF( sim, B2L_SIM_INV_INERTIA );
-	V2 force = v2( rawF( sim, B2L_SIM_FORCE ), rawF( sim, B2L_SIM_FORCE + 4 ) );
-	float torque = rawF( sim, B2L_SIM_TORQUE );
+	float4 a = P.wireBody[2 * (size_t)body + 0]; // invMass, invInertia, force.x, force.y
+	float4 b = P.wireBody[2 * (size_t)body + 1]; // torque, linearDamping, angularDamping, gravityScale
+	float invMass = a.x;
+	float invInertia = a.y;
+	V2 force = v2( a.z, a.w );
+	float torque = b.x;
 	float h = P.h;
 
-	float linearDamping = 1.0f / ( 1.0f + h * rawF( sim, B2L_SIM_LINEAR_DAMPING ) );
-	float angularDamping = 1.0f / ( 1.0f + h * rawF( sim, B2L_SIM_ANGULAR_DAMPING ) );
+	float linearDamping = 1.0f / ( 1.0f + h * b.y );
+	float angularDamping = 1.0f / ( 1.0f + h * b.z );
 
 	// gravity scale will be zero for kinematic bodies
-	float gravityScale = invMass > 0.0f ? rawF( sim, B2L_SIM_GRAVITY_SCALE ) : 0.0f;
+	float gravityScale = invMass > 0.0f ? b.w : 0.0f;
 
 	V2 linearVelocityDelta = add( mulSV( h * invMass, force ), mulSV( h * gravityScale, v2( P.gravityX, P.gravityY ) ) );
 	float angularVelocityDelta = h * invInertia * torque;
 
-	P.bodyK[i] = make_float4( linearVelocityDelta.x, linearVelocityDelta.y, angularVelocityDelta, linearDamping );
-	P.angDamp[i] = angularDamping;
+	V.bodyK[local - 1] = make_float4( linearVelocityDelta.x, linearVelocityDelta.y, angularVelocityDelta, linearDamping );
+	V.angDamp[local - 1] = angularDamping;
 }
 
-// b2IntegrateVelocitiesTask, src/solver.c:66-112
-B2G_DEV void integrateVelocities( const StepParams& P, int i )
+// b2IntegrateVelocitiesTask, src/solver.c:66-112 (i is 0-based in the view)
+B2G_DEV void integrateVelocities( const SolveView& V, int i )
 {
-	float4 v = __ldcg( P.vel + i + 1 );
-	float4 k = P.bodyK[i];
-	float angularDamping = P.angDamp[i];
+	float4 v = V.vel[i + 1];
+	float4 k = V.bodyK[i];
+	float angularDamping = V.angDamp[i];
 
 	v.x = k.x + k.w * v.x;
 	v.y = k.y + k.w * v.y;
 	v.z = k.z + angularDamping * v.z;
-	__stcg( P.vel + i + 1, v );
+	V.vel[i + 1] = v;
 }
 
 // b2IntegratePositionsTask, src/solver.c:114-162
-B2G_DEV void integratePositions( const StepParams& P, int i )
+B2G_DEV void integratePositions( const StepParams& P, const SolveView& V, int i )
 {
-	float4 s = __ldcg( P.vel + i + 1 );
-	float4 p = __ldcg( P.pos + i + 1 );
+	float4 s = V.vel[i + 1];
+	float4 p = V.pos[i + 1];
 	uint32_t flags = __float_as_uint( s.w );
 
 	float h = P.h;
@@ -103,16 +101,26 @@ B2G_DEV void integratePositions( const StepParams& P, int i )
 	dq.s = p.w;
 	dq = integrateRotation( dq, h * w );
 
-	__stcg( P.vel + i + 1, make_float4( v.x, v.y, w, __uint_as_float( flags ) ) );
-	__stcg( P.pos + i + 1, make_float4( dp.x, dp.y, dq.c, dq.s ) );
+	V.vel[i + 1] = make_float4( v.x, v.y, w, __uint_as_float( flags ) );
+	V.pos[i + 1] = make_float4( dp.x, dp.y, dq.c, dq.s );
 }
 
-// SoA -> the reference's AoS b2BodyState for the download
-B2G_DEV void storeBody( const StepParams& P, int i )
+// view -> the reference's AoS b2BodyState for the download
+B2G_DEV void storeBody( const StepParams& P, const SolveView& V, int body, int local )
 {
-	float4* out = reinterpret_cast<float4*>( P.outStates + (size_t)i * B2L_STATE_SIZE );
-	out[0] = __ldcg( P.vel + i + 1 );
-	out[1] = __ldcg( P.pos + i + 1 );
+	float4* out = reinterpret_cast<float4*>( P.outStates + (size_t)body * B2L_STATE_SIZE );
+	out[0] = V.vel[local];
+	out[1] = V.pos[local];
+}
+
+// {v, w} of a body as the prepare stage needs it, straight from the wire states (0 for the static dummy)
+B2G_DEV float4 wireVelocity( const StepParams& P, int index )
+{
+	if ( index < 0 )
+	{
+		return make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+	}
+	return *reinterpret_cast<const float4*>( P.rawStates + (size_t)index * B2L_STATE_SIZE );
 }
 
 // ---- distribution -------------------------------------------------------------------------------------------
@@ -160,9 +168,9 @@ template <typename FJ, typename FC> B2G_DEV void forEachInColor( const ColorRang
 	} );
 }
 
-B2G_DEV b2lJointSim* jointAt( const StepParams& P, int index )
+B2G_DEV b2lJointSim* jointAt( const SolveView& V, int index )
 {
-	return reinterpret_cast<b2lJointSim*>( P.joints + (size_t)index * B2L_JOINT_SIZE );
+	return reinterpret_cast<b2lJointSim*>( V.joints + (size_t)index * kJointStride );
 }
 
 B2G_DEV bool isLeadThread()
@@ -170,57 +178,60 @@ B2G_DEV bool isLeadThread()
 	return blockIdx.x == 0 && threadIdx.x == 0;
 }
 
-// ---- one stage ----------------------------------------------------------------------------------------------
+// ---- one stage of the grid-barrier path (view = global memory, wire slot == constraint slot) -----------------------
+B2G_DEV void prepareContactGlobal( const StepParams& P, int slot, bool active, bool wide, unsigned lane )
+{
+	int groupBits = wide ? simdGroupBits( P, slot, active, lane ) : 0;
+	if ( active )
+	{
+		float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+		int indexA = __float_as_int( head.x );
+		int indexB = __float_as_int( head.y );
+		prepareContact( P, P.g, slot, slot, indexA + 1, indexB + 1, wireVelocity( P, indexA ), wireVelocity( P, indexB ), wide,
+						groupBits );
+	}
+}
+
 B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 {
+	const SolveView& V = P.g;
 	switch ( op )
 	{
 		case OP_PREPARE:
 		{
 			if ( isLeadThread() )
 			{
-				__stcg( P.vel, make_float4( 0.0f, 0.0f, 0.0f, __uint_as_float( 0u ) ) );
-				__stcg( P.pos, make_float4( 0.0f, 0.0f, 1.0f, 0.0f ) );
+				V.vel[0] = make_float4( 0.0f, 0.0f, 0.0f, __uint_as_float( 0u ) );
+				V.pos[0] = make_float4( 0.0f, 0.0f, 1.0f, 0.0f );
 			}
 			forEachItem( P.bodyCount, [&]( int i ) {
 				if ( i < P.bodyCount )
 				{
-					loadBody( P, i );
+					loadBody( P, V, i, i + 1 );
 				}
 			} );
 			// coloured contacts, flat over all colours (b2_stagePrepareContacts, src/solver.c:1068-1074)
+			unsigned lane = threadIdx.x & 31u;
 			for ( int c = 0; c < P.colorCount; ++c )
 			{
 				ColorRange color = P.colors[c];
 				forEachItem( color.contactCount, [&]( int i ) {
-					if ( i < color.contactCount )
-					{
-						prepareContact( P, color.contactStart + i, true );
-					}
+					prepareContactGlobal( P, color.contactStart + i, i < color.contactCount, true, lane );
 				} );
 			}
 			// overflow contacts (b2PrepareContacts_Overflow, src/solver.c:1078): order free, they only read
 			forEachItem( P.overflow.contactCount, [&]( int i ) {
-				if ( i < P.overflow.contactCount )
-				{
-					prepareContact( P, P.overflow.contactStart + i, false );
-				}
+				prepareContactGlobal( P, P.overflow.contactStart + i, i < P.overflow.contactCount, false, lane );
 			} );
-			// stage the host-prepared joints into the working copy + clear the event bit sets
+			// stage the host-prepared joints into the working copy + clear the joint event bit set
 			{
-				int words = P.jointCount * ( B2L_JOINT_SIZE / 4 );
+				int words = P.jointCount * ( kJointStride / 4 );
 				const uint32_t* src = reinterpret_cast<const uint32_t*>( P.rawJoints );
-				uint32_t* dst = reinterpret_cast<uint32_t*>( P.joints );
+				uint32_t* dst = reinterpret_cast<uint32_t*>( V.joints );
 				forEachItem( words, [&]( int i ) {
 					if ( i < words )
 					{
 						dst[i] = src[i];
-					}
-				} );
-				forEachItem( P.hitWords, [&]( int i ) {
-					if ( i < P.hitWords )
-					{
-						P.hitBits[i] = 0u;
 					}
 				} );
 				forEachItem( P.jointWords, [&]( int i ) {
@@ -237,7 +248,7 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 			forEachItem( P.bodyCount, [&]( int i ) {
 				if ( i < P.bodyCount )
 				{
-					integrateVelocities( P, i );
+					integrateVelocities( V, i );
 				}
 			} );
 			break;
@@ -246,18 +257,18 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 			forEachItem( P.bodyCount, [&]( int i ) {
 				if ( i < P.bodyCount )
 				{
-					integratePositions( P, i );
+					integratePositions( P, V, i );
 				}
 			} );
 			break;
 
 		case OP_WARM:
 			forEachInColor(
-				P.colors[colorIndex], [&]( int j ) { warmStartJoint( P, jointAt( P, j ) ); },
+				P.colors[colorIndex], [&]( int j ) { warmStartJoint( P, V, jointAt( V, j ) ); },
 				[&]( int slot, bool active, unsigned ) {
 					if ( active )
 					{
-						warmStartContact( P, slot );
+						warmStartContact( V, slot );
 					}
 				} );
 			break;
@@ -266,23 +277,38 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 			forEachInColor(
 				P.colors[colorIndex],
 				[&]( int j ) {
-					b2lJointSim* joint = jointAt( P, j );
-					solveJoint( P, joint, true );
+					b2lJointSim* joint = jointAt( V, j );
+					solveJoint( P, V, joint, true );
 					jointEventTest( P, joint );
 				},
-				[&]( int slot, bool active, unsigned lane ) { solveContact( P, slot, active, true, lane ); } );
+				[&]( int slot, bool active, unsigned ) {
+					if ( active )
+					{
+						solveContact( P, V, slot, true );
+					}
+				} );
 			break;
 
 		case OP_RELAX:
 			forEachInColor(
-				P.colors[colorIndex], [&]( int j ) { solveJoint( P, jointAt( P, j ), false ); },
-				[&]( int slot, bool active, unsigned lane ) { solveContact( P, slot, active, false, lane ); } );
+				P.colors[colorIndex], [&]( int j ) { solveJoint( P, V, jointAt( V, j ), false ); },
+				[&]( int slot, bool active, unsigned ) {
+					if ( active )
+					{
+						solveContact( P, V, slot, false );
+					}
+				} );
 			break;
 
 		case OP_RESTITUTION:
 			forEachInColor(
 				P.colors[colorIndex], [&]( int ) {},
-				[&]( int slot, bool active, unsigned lane ) { restitutionContact( P, slot, active, lane ); } );
+				[&]( int slot, bool active, unsigned ) {
+					if ( active )
+					{
+						restitutionContact( P, V, slot );
+					}
+				} );
 			break;
 
 		// The overflow colour is solved by ONE thread, strictly in array order, joints before contacts
@@ -292,11 +318,11 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 			{
 				for ( int i = 0; i < P.overflow.jointCount; ++i )
 				{
-					warmStartJoint( P, jointAt( P, P.overflow.jointStart + i ) );
+					warmStartJoint( P, V, jointAt( V, P.overflow.jointStart + i ) );
 				}
 				for ( int i = 0; i < P.overflow.contactCount; ++i )
 				{
-					warmStartContactOverflow( P, P.overflow.contactStart + i );
+					warmStartContactOverflow( V, P.overflow.contactStart + i );
 				}
 			}
 			break;
@@ -308,11 +334,11 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 				bool useBias = op == OP_OVERFLOW_SOLVE;
 				for ( int i = 0; i < P.overflow.jointCount; ++i )
 				{
-					solveJoint( P, jointAt( P, P.overflow.jointStart + i ), useBias );
+					solveJoint( P, V, jointAt( V, P.overflow.jointStart + i ), useBias );
 				}
 				for ( int i = 0; i < P.overflow.contactCount; ++i )
 				{
-					solveContactOverflow( P, P.overflow.contactStart + i, useBias );
+					solveContactOverflow( P, V, P.overflow.contactStart + i, useBias );
 				}
 			}
 			break;
@@ -322,7 +348,7 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 			{
 				for ( int i = 0; i < P.overflow.contactCount; ++i )
 				{
-					restitutionContactOverflow( P, P.overflow.contactStart + i );
+					restitutionContactOverflow( P, V, P.overflow.contactStart + i );
 				}
 			}
 			break;
@@ -335,20 +361,20 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 				forEachItem( color.contactCount, [&]( int i ) {
 					if ( i < color.contactCount )
 					{
-						storeContact( P, color.contactStart + i, true );
+						storeContact( P, V, color.contactStart + i, color.contactStart + i, true );
 					}
 				} );
 			}
 			forEachItem( P.overflow.contactCount, [&]( int i ) {
 				if ( i < P.overflow.contactCount )
 				{
-					storeContact( P, P.overflow.contactStart + i, false );
+					storeContact( P, V, P.overflow.contactStart + i, P.overflow.contactStart + i, false );
 				}
 			} );
 			forEachItem( P.bodyCount, [&]( int i ) {
 				if ( i < P.bodyCount )
 				{
-					storeBody( P, i );
+					storeBody( P, V, i, i + 1 );
 				}
 			} );
 		}

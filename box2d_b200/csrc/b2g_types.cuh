@@ -1,22 +1,22 @@
 // b2g_types.cuh -- device-side data layout of one solver step.
 //
-// Data layout in HBM (all buffers owned by b2GpuSolver, resident for the whole step):
+// Wire format (what crosses PCIe, packed by the host side of the C-ABI from the reference's own arrays):
+//     states   b2BodyState[bodyCount]      32 B each, copied as is
+//     wireBody 2 float4 per body           {invMass, invInertia, force.x, force.y} {torque, linDamping, angDamping, gravityScale}
+//     wire     7 float4 per contact slot   the 112 of b2ContactSim's 200 bytes the solver reads (see WireRow); colour c
+//                                          occupies slots [colors[c].contactStart, +contactCount), starts are multiples of 32
+//     joints   b2JointSim[jointCount]      252 B each padded to 256, prepared on the host; solved in place in a working copy
 //
-//   raw inputs (uploaded as the reference's own AoS, read once by the prepare stage)
-//     rawStates   b2BodyState[bodyCount]            32 B each
-//     rawSims     b2BodySim[bodyCount]              96 B each
-//     rawContacts b2ContactSim[contactSlots]       200 B each, colour c at slot colors[c].contactStart
-//     joints      b2JointSim[jointSlots]           252 B each (working copy, solved in place)
+// Solver state, reached through a SolveView (generic pointers: global memory for the grid-barrier kernel, shared
+// memory for the island-local kernel -- the stage code is the same):
+//     vel[1+n]  float4 {v.x, v.y, w, flags-bits}        index 0 = static dummy (identity)
+//     pos[1+n]  float4 {dp.x, dp.y, dq.c, dq.s}         index 0 = {0,0,1,0}
+//     bodyK[n]  float4 {lvd.x, lvd.y, avd, linDamp} + angDamp[n]   (per-step body constants)
+//     contact constraint = 10 float4 + int2 + int per slot, field-major: field f of slot s at f*cfStride+s, so a warp
+//       reads 512 contiguous bytes per field (one thread per constraint).
 //
-//   solver state (SoA, what the 3*subSteps*colours hot stages touch)
-//     vel[1+bodyCount]  float4 {v.x, v.y, w, flags-bits}        index 0 = static dummy (identity)
-//     pos[1+bodyCount]  float4 {dp.x, dp.y, dq.c, dq.s}         index 0 = {0,0,1,0}
-//     bodyK[bodyCount]  float4 {lvd.x, lvd.y, avd, linDamp} + angDamp[bodyCount]   (per-step body constants)
-//     contact constraint = 10 float4 + 2 int2 per slot, field-major: field f of slot s at f*slotCapacity+s
-//       so a warp reads 512 contiguous bytes per field (one thread per constraint).
-//
-// Splitting b2BodyState's two 16-byte halves into two arrays keeps the float4 gathers the north_star
-// asks for and lets warm-start / restitution skip the position half.
+// Splitting b2BodyState's two 16-byte halves into two arrays keeps the float4 gathers the north_star asks for and
+// lets warm-start / restitution skip the position half.
 #pragma once
 
 #include "b2g_math.cuh"
@@ -41,6 +41,25 @@ enum ContactField
 	CF_COUNT = 10
 };
 
+// rows of a wire contact record (float4 each)
+enum WireRow
+{
+	WR_HEAD = 0,	// indexA (int), indexB (int), meta (int: colour<<8 | hitEnable<<2 | pointCount), rollingImpulse
+	WR_MASS = 1,	// invMassA, invIA, invMassB, invIB
+	WR_NORMAL = 2,	// normal.x, normal.y, friction, tangentSpeed
+	WR_MATERIAL = 3, // rollingResistance, restitution, separation1, separation2
+	WR_ANCHOR1 = 4, // anchorA1.xy, anchorB1.xy
+	WR_ANCHOR2 = 5, // anchorA2.xy, anchorB2.xy
+	WR_IMPULSE = 6, // normalImpulse1, tangentImpulse1, normalImpulse2, tangentImpulse2
+	WR_COUNT = 7
+};
+
+constexpr int kMetaPointMask = 3;
+constexpr int kMetaHitEnable = 4;
+constexpr int kMetaGroupRolling = 8;	   // some lane of this constraint's SIMD group of 4 has rolling resistance
+constexpr int kMetaGroupRestitution = 16; // ... has restitution
+constexpr int kMetaColorShift = 8;
+
 struct ColorRange
 {
 	int contactStart; // slot of the colour's first contact (multiple of 32)
@@ -50,11 +69,26 @@ struct ColorRange
 };
 
 constexpr int kMaxColors = 23;
+constexpr int kJointStride = 256; // b2JointSim (252 B) padded to 16-byte multiples on the wire and in the working copy
 constexpr int kStageTimerCount = 8;
 
 // Per-contact output record copied back to the host and scattered into b2Manifold
-// (what b2StoreImpulsesTask writes, src/contact_solver.c:2293-2303): 9 floats.
-constexpr int kImpulseFloats = 9;
+// (what b2StoreImpulsesTask writes, src/contact_solver.c:2293-2303): 9 floats + the hit-event flag (:2305-2320).
+constexpr int kImpulseFloats = 10;
+
+// The arrays the stage functions work on.  Generic pointers: global memory or shared memory.
+struct SolveView
+{
+	float4* vel;
+	float4* pos;
+	float4* bodyK;
+	float* angDamp;
+	float4* cf;	   // CF_COUNT field groups, field f of slot s at f*cfStride + s
+	int cfStride;
+	int2* cidx;	   // indexA+1, indexB+1 (0 = static dummy) in the view's own body numbering
+	int* cmeta;	   // kMeta* bits
+	uint8_t* joints; // b2JointSim working copy (indexA/indexB in the view's numbering, 0-based, -1 = static)
+};
 
 struct StepParams
 {
@@ -80,30 +114,20 @@ struct StepParams
 	ColorRange overflow;
 	int contactSlots; // slots in use, colours + overflow, padded
 	int jointCount;	  // joints in use, colours + overflow
-	int slotCapacity; // field stride of the contact SoA
-	int hitWords;	  // uint32 words in hitBits
 	int jointWords;	  // uint32 words in jointBits
 
-	// raw inputs
+	// wire inputs (global memory)
 	const uint8_t* rawStates;
-	const uint8_t* rawSims;
-	const uint8_t* rawContacts;
+	const float4* wireBody;
+	const float4* wire;		  // WR_COUNT float4 per slot, AoS
 	const uint8_t* rawJoints; // pristine prepared joints as uploaded
 
-	// solver state
-	float4* vel;
-	float4* pos;
-	float4* bodyK;
-	float* angDamp;
-	float4* cf; // CF_COUNT * slotCapacity
-	int2* cidx; // indexA+1, indexB+1 (0 = static)
-	int2* cmeta; // contactId, (simFlags & hitEvent) | pointCount
-	uint8_t* joints; // b2JointSim working copy
+	// solver state in global memory (the grid-barrier kernel's view)
+	SolveView g;
 
 	// outputs
 	uint8_t* outStates; // b2BodyState[bodyCount]
 	float* outImpulses; // kImpulseFloats per slot
-	uint32_t* hitBits;
 	uint32_t* jointBits;
 	int* hasHitEvents;
 	int* anyRestitution; // set by prepare when some contact has restitution != 0 (else the restitution stages are skipped)

@@ -11,6 +11,7 @@
 #include "bitset.h"
 #include "core.h"
 #include "id_pool.h"
+#include "parallel_for.h"
 #include "physics_world.h"
 #include "solver.h"
 
@@ -103,6 +104,18 @@ void b2GpuSeam_InstallPinnedAllocator( void )
 	b2SetAllocator( b2GpuHostAlloc, b2GpuHostFree );
 }
 
+static void b2SeamPackTask( int startIndex, int endIndex, int workerIndex, void* taskContext )
+{
+	(void)workerIndex;
+	b2GpuSolverPackRange( taskContext, startIndex, endIndex );
+}
+
+static void b2SeamUnpackTask( int startIndex, int endIndex, int workerIndex, void* taskContext )
+{
+	(void)workerIndex;
+	b2GpuSolverUnpackRange( taskContext, startIndex, endIndex );
+}
+
 /* ---- the seam ------------------------------------------------------------------------------------------- */
 
 void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
@@ -133,10 +146,20 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 	result->hitEventBits = taskContext0->hitEventBitSet.bits;
 	result->jointEventBits = taskContext0->jointStateBitSet.bits;
 
-	int status = b2GpuSolverStep( slot->solver, desc, result );
-	if ( status != 0 )
+	// The two memory-bound host passes (wire packing, impulse write-back) run on the world's own workers.
+	if ( b2GpuSolverBeginStep( slot->solver, desc, result ) != 0 )
 	{
-		b2SeamFatal( "b2GpuSolverStep failed" );
+		b2SeamFatal( "b2GpuSolverBeginStep failed" );
+	}
+	b2ParallelFor( world, b2SeamPackTask, b2GpuSolverGetPackItemCount( slot->solver ), 512, slot->solver );
+	if ( b2GpuSolverSubmit( slot->solver ) != 0 || b2GpuSolverWait( slot->solver ) != 0 )
+	{
+		b2SeamFatal( "device solve failed" );
+	}
+	b2ParallelFor( world, b2SeamUnpackTask, b2GpuSolverGetUnpackItemCount( slot->solver ), 512, slot->solver );
+	if ( b2GpuSolverEndStep( slot->solver, result ) != 0 )
+	{
+		b2SeamFatal( "b2GpuSolverEndStep failed" );
 	}
 
 	// The event consumers at src/solver.c:1648-1820 read worker 0's sets after OR-ing the others in.

@@ -162,6 +162,22 @@ B2GPU_API int b2GpuSolverUpload( b2GpuSolver* solver, const b2GpuStepDesc* desc 
 B2GPU_API int b2GpuSolverRun( b2GpuSolver* solver, b2GpuStepResult* result );
 B2GPU_API int b2GpuSolverDownload( b2GpuSolver* solver, const b2GpuStepDesc* desc, b2GpuStepResult* result );
 
+/* The same step in phases, so the host side can use ITS OWN worker threads for the two memory-bound host passes
+ * (the seam runs them through the reference's b2ParallelFor): Begin fixes the layout; PackRange converts a range of
+ * items (first the awake bodies, then all contacts in colour order, overflow last) from the reference's arrays into
+ * the page-locked wire buffer and may be called concurrently on disjoint ranges; Submit enqueues H2D + kernels + D2H
+ * and returns immediately; Wait blocks; UnpackRange writes the impulses of a range of contacts back into the
+ * reference's manifolds (+ hit-event bits) and may be called concurrently on disjoint ranges; End fills the result.
+ * The desc's arrays must stay valid and unchanged from Begin to End. */
+B2GPU_API int b2GpuSolverBeginStep( b2GpuSolver* solver, const b2GpuStepDesc* desc, b2GpuStepResult* result );
+B2GPU_API int b2GpuSolverGetPackItemCount( const b2GpuSolver* solver );
+B2GPU_API void b2GpuSolverPackRange( b2GpuSolver* solver, int begin, int end );
+B2GPU_API int b2GpuSolverSubmit( b2GpuSolver* solver );
+B2GPU_API int b2GpuSolverWait( b2GpuSolver* solver );
+B2GPU_API int b2GpuSolverGetUnpackItemCount( const b2GpuSolver* solver );
+B2GPU_API void b2GpuSolverUnpackRange( b2GpuSolver* solver, int begin, int end );
+B2GPU_API int b2GpuSolverEndStep( b2GpuSolver* solver, b2GpuStepResult* result );
+
 /* Batch of independent worlds (the RL-style workload): one launch solves all of them, one thread block
  * per world with the world's bodies and constraints resident in shared memory for all sub-steps.  Each
  * desc is a complete, independent world step.  Worlds that do not fit the per-block budget are solved
