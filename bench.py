@@ -192,7 +192,7 @@ def run_gpu_arm(args) -> int:
 		torch.cuda.synchronize()
 
 	sampler = ClockSampler(local_rank)
-	workers = min(os.cpu_count() or 1, 8)  # host phases (collide, finalize) of the GPU arm
+	workers = min(os.cpu_count() or 1, 16)  # host phases of the GPU arm (collide, pack/unpack, finalize)
 	with b2.World(host, args.scene, workers) as world:
 		world.step(args.warmup)
 		widx = world.world_index()

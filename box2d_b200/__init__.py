@@ -62,6 +62,7 @@ class StepDesc(ctypes.Structure):
 		("colors", ColorDesc * MAX_ACTIVE_COLORS),
 		("overflow", ColorDesc),
 		("contactIdCapacity", ctypes.c_int), ("jointIdCapacity", ctypes.c_int),
+		("bodyIsland", ctypes.c_void_p), ("islandCount", ctypes.c_int), ("reserved0", ctypes.c_int),
 	]
 
 
@@ -278,15 +279,15 @@ class World:
 		self.destroy()
 
 
-# ---- capture files (oracle/harness/b2h_capture.c, format B2CAP002) ----------------------------------------------
+# ---- capture files (oracle/harness/b2h_capture.c, format B2CAP003) ----------------------------------------------
 class Capture:
 	"""One captured solver step: the C-ABI inputs and the reference CPU solver's outputs."""
 
 	def __init__(self, path):
 		path = Path(path)
 		raw = gzip.open(path, "rb").read() if path.suffix == ".gz" else path.read_bytes()
-		if raw[:8] != b"B2CAP002":
-			raise ValueError(f"{path}: not a B2CAP002 capture")
+		if raw[:8] != b"B2CAP003":
+			raise ValueError(f"{path}: not a B2CAP003 capture")
 		desc_bytes = int.from_bytes(raw[8:12], "little")
 		if desc_bytes != ctypes.sizeof(StepDesc):
 			raise ValueError(f"{path}: descriptor size {desc_bytes} != {ctypes.sizeof(StepDesc)}")
@@ -300,6 +301,7 @@ class Capture:
 
 		self.states_in = self._take(n * STATE_SIZE)
 		self.sims = self._take(n * SIM_SIZE)
+		self.island_labels = self._take(n * 4).view(np.int32).copy()
 		self.contacts_in, self.joints_in = [], []
 		for cc, jc in self.color_counts:
 			self.contacts_in.append(self._take(cc * CONTACT_SIZE))
@@ -333,8 +335,9 @@ class Capture:
 	def joint_count(self) -> int:
 		return sum(j for _, j in self.color_counts)
 
-	def make_call(self):
-		"""Fresh, writable copies of the inputs wired into a StepDesc + StepResult (the arrays must outlive the call)."""
+	def make_call(self, islands: bool = True):
+		"""Fresh, writable copies of the inputs wired into a StepDesc + StepResult (the arrays must outlive the call).
+		islands=False drops the island hint: the step is then solved by the grid-barrier kernel."""
 		d = StepDesc.from_buffer_copy(bytes(self.desc))
 		bufs = {
 			"states": self.states_in.copy(),
@@ -346,6 +349,12 @@ class Capture:
 		}
 		d.states = bufs["states"].ctypes.data
 		d.sims = bufs["sims"].ctypes.data
+		bufs["islands"] = self.island_labels.copy()
+		if islands and self.island_labels.size:
+			d.bodyIsland = bufs["islands"].ctypes.data
+		else:
+			d.bodyIsland = None
+			d.islandCount = 0
 		for i in range(d.activeColorCount + 1):
 			cd = d.colors[i] if i < d.activeColorCount else d.overflow
 			cd.contactSims = bufs["contacts"][i].ctypes.data if bufs["contacts"][i].size else None

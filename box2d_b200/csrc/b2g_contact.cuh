@@ -183,7 +183,7 @@ B2G_DEV void prepareContact( const StepParams& P, const SolveView& V, int wireSl
 
 	if ( !( restitution == 0.0f ) )
 	{
-		*P.anyRestitution = 1;
+		*V.anyRestitution = 1;
 	}
 
 	// 0 for null (contact_solver.c:1644-1646)

@@ -9,7 +9,7 @@
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
 #include "b2_gpu_solver.h"
 
-#include "b2g_stages.cuh"
+#include "b2g_island.cuh"
 
 #include <cuda_runtime.h>
 
@@ -26,61 +26,15 @@
 namespace b2g
 {
 
-constexpr int kBlockThreads = 256;
-
-// ---- grid barrier ---------------------------------------------------------------------------------------------
-// Arrive = release-add at gpu scope by one thread after the block has synchronised; wait = acquire-load spin.
-// The acquire makes the other blocks' body/constraint writes visible to every thread of this block after the
-// trailing __syncthreads (PTX memory model: bar.sync and release/acquire chains compose by causality order).
-B2G_DEV void gridBarrier( unsigned int* counter, unsigned int target )
-{
-	__syncthreads();
-	if ( threadIdx.x == 0 )
-	{
-		asm volatile( "red.release.gpu.global.add.u32 [%0], 1;" ::"l"( counter ) : "memory" );
-		unsigned int seen;
-		do
-		{
-			asm volatile( "ld.acquire.gpu.global.u32 %0, [%1];" : "=r"( seen ) : "l"( counter ) : "memory" );
-		}
-		while ( seen < target );
-	}
-	__syncthreads();
-}
-
-struct StageClock
-{
-	long long last;
-	long long acc[b2GpuStage_count];
-	bool lead;
-
-	B2G_DEV void start()
-	{
-		lead = isLeadThread();
-		last = lead ? clock64() : 0;
-#pragma unroll
-		for ( int i = 0; i < b2GpuStage_count; ++i )
-		{
-			acc[i] = 0;
-		}
-	}
-
-	// timers are compile-time constants, so acc[] stays in registers
-	B2G_DEV void lap( int timer )
-	{
-		if ( lead )
-		{
-			long long now = clock64();
-			acc[timer] += now - last;
-			last = now;
-		}
-	}
-};
-
 // The whole step.  Stage order and barrier placement = b2SolverTask (src/solver.c:1055-1197); the stage timers
 // are the reference's b2Profile split (src/solver.c:1080,1097,1112,1132,1141,1159,1182,1191).
 __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gStepKernel( const __grid_constant__ StepParams P )
 {
+	if ( P.binCount > 0 && __ldcg( P.binFail ) == 0 )
+	{
+		return; // the island kernel solved this step
+	}
+
 	unsigned int epoch = 0;
 	const unsigned int blocks = gridDim.x;
 	auto sync = [&]() {
@@ -149,7 +103,7 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gStepKernel( const __gri
 	// Restitution: the reference skips every SIMD group whose lanes all have restitution 0
 	// (src/contact_solver.c:2131, :432); when NO contact of the step has any, all groups skip, so the colour
 	// stages and their barriers are skipped as a whole.
-	if ( __ldcg( P.anyRestitution ) != 0 )
+	if ( __ldcg( P.g.anyRestitution ) != 0 )
 	{
 		if ( hasOverflow )
 		{
@@ -327,6 +281,18 @@ struct b2GpuSolver
 	DeviceBuffer<int> cmeta;
 	ControlBlock* control = nullptr;
 
+	// island mode scratch (b2g_island.cuh)
+	DeviceBuffer<int> binCounters; // [binBodyCount | binColorStart | binJointStart | binFail], zeroed every run
+	DeviceBuffer<int> bodyLocal, binBodyList, slotGroupBits, binContactList, binJointList;
+	DeviceBuffer<int2> contactBinRank, jointBinRank;
+	std::vector<int> islandBin;	 // host: bin of every awake island
+	std::vector<int> islandBodies; // host: bodies per island, then per bin
+	size_t binCounterCount = 0;
+	size_t islandSmemBytes = 0;
+	bool islandMode = false;
+	int islandsEnabled = 1;
+	int maxSharedOptin = 0;
+
 	// page-locked staging owned by the library.  The input staging is written with non-temporal stores: on the
 	// target hosts a DMA read of lines that sit dirty in several cores' caches runs at ~6 GB/s instead of ~53 GB/s
 	// (tools/microbench/h2d_bench.cu, profiles/).
@@ -335,7 +301,7 @@ struct b2GpuSolver
 	ControlBlock* hControl = nullptr;
 
 	// arena layouts, in float4 units
-	size_t inStates = 0, inBody = 0, inWire = 0, inJoints = 0, inTotal = 0;
+	size_t inStates = 0, inBody = 0, inWire = 0, inJoints = 0, inBins = 0, inTotal = 0;
 	size_t outStates = 0, outImpulses = 0, outJoints = 0, outBits = 0, outTotal = 0;
 
 	// the step in flight
@@ -435,6 +401,15 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		s->gridBlocks = atoi( gridEnv );
 	}
 
+	s->maxSharedOptin = (int)prop.sharedMemPerBlockOptin;
+	const char* islandEnv = getenv( "B2GPU_ISLANDS" );
+	s->islandsEnabled = islandEnv != nullptr ? atoi( islandEnv ) : 1;
+	if ( cudaFuncSetAttribute( b2g::b2gIslandKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->maxSharedOptin - 1024 ) != cudaSuccess )
+	{
+		cudaGetLastError();
+		s->islandsEnabled = 0;
+	}
+
 	bool ok = cudaStreamCreateWithFlags( &s->stream, cudaStreamNonBlocking ) == cudaSuccess;
 	ok = ok && cudaEventCreate( &s->evStart ) == cudaSuccess;
 	ok = ok && cudaEventCreate( &s->evStop ) == cudaSuccess;
@@ -474,6 +449,14 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	s->cmeta.release();
 	s->hWire.release();
 	s->hOut.release();
+	s->binCounters.release();
+	s->bodyLocal.release();
+	s->binBodyList.release();
+	s->slotGroupBits.release();
+	s->binContactList.release();
+	s->binJointList.release();
+	s->contactBinRank.release();
+	s->jointBinRank.release();
 	if ( s->control != nullptr )
 	{
 		cudaFree( s->control );
@@ -509,6 +492,117 @@ extern "C" int b2GpuSolverSetMode( b2GpuSolver* s, int mode )
 extern "C" uint64_t b2GpuSolverGetLaunchCount( const b2GpuSolver* s )
 {
 	return s != nullptr ? s->launchCount : 0;
+}
+
+// ---- island mode planning (host) --------------------------------------------------------------------------------
+// Pack the awake islands into at most one bin per SM, balanced by body count, and size the island kernel's shared
+// memory carve-up.  Island mode is used when the hint is present, the overflow colour is empty (it is strictly
+// sequential, src/solver.c:1100-1101) and the estimated bins fit; the device double-checks the exact sizes.
+static int b2gPlanIslands( b2GpuSolver* s )
+{
+	const b2GpuStepDesc& d = s->desc;
+	b2g::StepParams& P = s->params;
+	s->islandMode = false;
+	P.binCount = 0;
+	int bodies = P.bodyCount;
+	if ( s->islandsEnabled == 0 || s->mode != 0 || d.bodyIsland == nullptr || d.islandCount <= 0 || bodies == 0 ||
+		 d.overflow.contactCount + d.overflow.jointCount > 0 )
+	{
+		return 0;
+	}
+
+	int islandCount = d.islandCount;
+	s->islandBodies.assign( (size_t)islandCount, 0 );
+	for ( int i = 0; i < bodies; ++i )
+	{
+		int island = d.bodyIsland[i];
+		if ( island < 0 || island >= islandCount )
+		{
+			return 0; // a body without an island: no partition guarantee, use the grid-barrier kernel
+		}
+		s->islandBodies[island] += 1;
+	}
+
+	int binLimit = s->smCount < islandCount ? s->smCount : islandCount;
+	int target = ( bodies + binLimit - 1 ) / binLimit;
+	s->islandBin.assign( (size_t)islandCount, 0 );
+	// island i goes to the bin its first body falls in when the islands are laid end to end and cut every `target`
+	// bodies: every bin gets between target - (largest island) and target + (largest island) bodies
+	s->islandBodies.push_back( 0 ); // scratch: per-bin totals are accumulated below
+	std::vector<int> binBodies( (size_t)binLimit, 0 );
+	int bin = 0, maxBin = 0;
+	long long before = 0;
+	for ( int i = 0; i < islandCount; ++i )
+	{
+		int n = s->islandBodies[i];
+		int b = (int)( before / target );
+		b = b < binLimit ? b : binLimit - 1;
+		s->islandBin[i] = b;
+		binBodies[b] += n;
+		maxBin = binBodies[b] > maxBin ? binBodies[b] : maxBin;
+		bin = b > bin ? b : bin;
+		before += n;
+	}
+	int binCount = bin + 1;
+
+	// capacities: exact for bodies, proportional estimate with slack for constraints
+	auto roundUp4 = []( double v ) { return ( (int)v + 3 ) & ~3; };
+	int capB = roundUp4( maxBin );
+	double share = (double)maxBin / (double)bodies;
+	double needC = share * s->contactTotal, needJ = share * s->jointTotal;
+	size_t budget = (size_t)s->maxSharedOptin - 2048;
+	// The proportional need is only an estimate (constraint density differs between islands): hand the whole
+	// shared-memory budget to the bin -- bodies exactly, the rest split between contacts and joints in
+	// proportion to their estimated bytes -- so a bin may hold several times its fair share before binFail trips.
+	const double bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0, bytesPerJoint = b2g::kJointStride + 8.0;
+	size_t fixed = b2g::islandSharedBytes( capB, 0, 0 );
+	if ( fixed + (size_t)( needC * 1.1 * bytesPerContact + needJ * 1.1 * bytesPerJoint ) + 4096 > budget )
+	{
+		return 0;
+	}
+	double weightC = needC * bytesPerContact + 2048.0, weightJ = s->jointTotal > 0 ? needJ * bytesPerJoint + 2048.0 : 0.0;
+	double spare = (double)( budget - fixed ) - 64.0;
+	int capC = ( (int)( spare * weightC / ( weightC + weightJ ) / bytesPerContact ) ) & ~3;
+	int capJ = s->jointTotal > 0 ? ( (int)( spare * weightJ / ( weightC + weightJ ) / bytesPerJoint ) ) & ~3 : 0;
+	// no point in exceeding what exists
+	capC = capC > ( ( s->contactTotal + 3 ) & ~3 ) ? ( ( s->contactTotal + 3 ) & ~3 ) : capC;
+	capJ = capJ > ( ( s->jointTotal + 3 ) & ~3 ) ? ( ( s->jointTotal + 3 ) & ~3 ) : capJ;
+	capC = capC < 4 ? 4 : capC;
+	if ( b2g::islandSharedBytes( capB, capC, capJ ) > budget )
+	{
+		return 0;
+	}
+
+	size_t slots = (size_t)P.contactSlots;
+	s->binCounterCount = (size_t)binCount * ( 1 + 2 * b2g::kColorSlots ) + 1;
+	B2G_CUDA( s->binCounters.reserve( s->binCounterCount ) );
+	B2G_CUDA( s->bodyLocal.reserve( (size_t)bodies + 1 ) );
+	B2G_CUDA( s->binBodyList.reserve( (size_t)binCount * capB + 1 ) );
+	B2G_CUDA( s->slotGroupBits.reserve( slots + 1 ) );
+	B2G_CUDA( s->contactBinRank.reserve( slots + 1 ) );
+	B2G_CUDA( s->binContactList.reserve( (size_t)binCount * capC + 1 ) );
+	B2G_CUDA( s->jointBinRank.reserve( (size_t)s->jointTotal + 1 ) );
+	B2G_CUDA( s->binJointList.reserve( (size_t)binCount * capJ + 1 ) );
+
+	P.binCount = binCount;
+	P.capBodies = capB;
+	P.capContacts = capC;
+	P.capJoints = capJ;
+	P.bodyBin = reinterpret_cast<const int*>( s->wireAll.ptr + s->inBins );
+	P.bodyLocal = s->bodyLocal.ptr;
+	P.binBodyCount = s->binCounters.ptr;
+	P.binColorStart = s->binCounters.ptr + binCount;
+	P.binJointStart = P.binColorStart + (size_t)binCount * b2g::kColorSlots;
+	P.binFail = P.binJointStart + (size_t)binCount * b2g::kColorSlots;
+	P.binBodyList = s->binBodyList.ptr;
+	P.contactBinRank = s->contactBinRank.ptr;
+	P.slotGroupBits = s->slotGroupBits.ptr;
+	P.binContactList = s->binContactList.ptr;
+	P.jointBinRank = s->jointBinRank.ptr;
+	P.binJointList = s->binJointList.ptr;
+	s->islandSmemBytes = b2g::islandSharedBytes( capB, capC, capJ );
+	s->islandMode = true;
+	return 0;
 }
 
 // ---- phase 1: layout --------------------------------------------------------------------------------------------
@@ -599,7 +693,8 @@ extern "C" int b2GpuSolverBeginStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2G
 	s->inBody = s->inStates + 2 * bodies;
 	s->inWire = s->inBody + 2 * bodies;
 	s->inJoints = s->inWire + (size_t)b2g::WR_COUNT * slot;
-	s->inTotal = s->inJoints + jointQuads * joint;
+	s->inBins = s->inJoints + jointQuads * joint;
+	s->inTotal = s->inBins + ( bodies + 3 ) / 4;
 	// output arena: [states 2/body][impulse records][joints 16/joint][joint event bits]
 	size_t impulseQuads = ( (size_t)slot * b2g::kImpulseFloats + 3 ) / 4;
 	s->outStates = 0;
@@ -639,9 +734,14 @@ extern "C" int b2GpuSolverBeginStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2G
 	P.outImpulses = reinterpret_cast<float*>( s->outAll.ptr + s->outImpulses );
 	P.jointBits = reinterpret_cast<uint32_t*>( s->outAll.ptr + s->outBits );
 	P.hasHitEvents = &s->control->hasHitEvents;
-	P.anyRestitution = &s->control->anyRestitution;
+	P.g.anyRestitution = &s->control->anyRestitution;
 	P.barrier = s->control->barrier;
 	P.stageCycles = s->control->stageCycles;
+
+	if ( b2gPlanIslands( s ) != 0 )
+	{
+		return 1;
+	}
 
 	s->begun = true;
 	return 0;
@@ -727,9 +827,14 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		const uint8_t* sims = static_cast<const uint8_t*>( d.sims );
 		float4* wireStates = base + s->inStates;
 		float4* wireBody = base + s->inBody;
+		int* wireBins = reinterpret_cast<int*>( base + s->inBins );
 		int bodyEnd = end < bodyCount ? end : bodyCount;
 		for ( int i = begin; i < bodyEnd; ++i )
 		{
+			if ( s->islandMode )
+			{
+				_mm_stream_si32( wireBins + i, s->islandBin[d.bodyIsland[i]] );
+			}
 			b2gStreamCopy( wireStates + 2 * (size_t)i, states + (size_t)i * B2L_STATE_SIZE, 2 );
 			const uint8_t* sim = sims + (size_t)i * B2L_SIM_SIZE;
 			b2gStream4( wireBody + 2 * (size_t)i + 0, b2gRdF( sim, B2L_SIM_INV_MASS ), b2gRdF( sim, B2L_SIM_INV_INERTIA ),
@@ -900,6 +1005,32 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 	{
 		void* args[] = { (void*)&s->params };
 		cudaError_t err;
+		if ( s->islandMode )
+		{
+			// partition -> island kernel; the grid-barrier kernel below only runs if a bin did not fit (binFail)
+			B2G_CUDA( cudaMemsetAsync( s->binCounters.ptr, 0, s->binCounterCount * sizeof( int ), s->stream ) );
+			if ( s->cooperative )
+			{
+				err = cudaLaunchCooperativeKernel( (const void*)b2g::b2gPartitionKernel, dim3( s->gridBlocks ),
+												   dim3( b2g::kBlockThreads ), args, 0, s->stream );
+			}
+			else
+			{
+				err = cudaLaunchKernel( (const void*)b2g::b2gPartitionKernel, dim3( s->gridBlocks ), dim3( b2g::kBlockThreads ), args, 0,
+										s->stream );
+			}
+			if ( err != cudaSuccess )
+			{
+				return b2gFail( "b2gPartitionKernel launch", err );
+			}
+			err = cudaLaunchKernel( (const void*)b2g::b2gIslandKernel, dim3( s->params.binCount ), dim3( b2g::kIslandThreads ), args,
+									s->islandSmemBytes, s->stream );
+			if ( err != cudaSuccess )
+			{
+				return b2gFail( "b2gIslandKernel launch", err );
+			}
+			s->lastLaunches += 2;
+		}
 		if ( s->cooperative )
 		{
 			err = cudaLaunchCooperativeKernel( (const void*)b2g::b2gStepKernel, dim3( s->gridBlocks ), dim3( b2g::kBlockThreads ),
@@ -914,7 +1045,7 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 		{
 			return b2gFail( "b2gStepKernel launch", err );
 		}
-		s->lastLaunches = 1;
+		s->lastLaunches += 1;
 	}
 	else
 	{

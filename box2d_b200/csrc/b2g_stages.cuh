@@ -14,6 +14,62 @@ namespace b2g
 {
 
 constexpr float kMaxRotation = 0.25f * kPi; // B2_MAX_ROTATION, include/box2d/constants.h:50
+constexpr int kBlockThreads = 256;
+
+B2G_DEV bool isLeadThread()
+{
+	return blockIdx.x == 0 && threadIdx.x == 0;
+}
+
+// ---- grid barrier ---------------------------------------------------------------------------------------------
+// Arrive = release-add at gpu scope by one thread after the block has synchronised; wait = acquire-load spin.
+// The acquire makes the other blocks' body/constraint writes visible to every thread of this block after the
+// trailing __syncthreads (PTX memory model: bar.sync and release/acquire chains compose by causality order).
+B2G_DEV void gridBarrier( unsigned int* counter, unsigned int target )
+{
+	__syncthreads();
+	if ( threadIdx.x == 0 )
+	{
+		asm volatile( "red.release.gpu.global.add.u32 [%0], 1;" ::"l"( counter ) : "memory" );
+		unsigned int seen;
+		do
+		{
+			asm volatile( "ld.acquire.gpu.global.u32 %0, [%1];" : "=r"( seen ) : "l"( counter ) : "memory" );
+		}
+		while ( seen < target );
+	}
+	__syncthreads();
+}
+
+struct StageClock
+{
+	long long last;
+	long long acc[b2GpuStage_count];
+	bool lead;
+
+	B2G_DEV void start()
+	{
+		lead = isLeadThread();
+		last = lead ? clock64() : 0;
+#pragma unroll
+		for ( int i = 0; i < b2GpuStage_count; ++i )
+		{
+			acc[i] = 0;
+		}
+	}
+
+	// timers are compile-time constants, so acc[] stays in registers
+	B2G_DEV void lap( int timer )
+	{
+		if ( lead )
+		{
+			long long now = clock64();
+			acc[timer] += now - last;
+			last = now;
+		}
+	}
+};
+
 
 // ---- body stages --------------------------------------------------------------------------------------------
 
@@ -171,11 +227,6 @@ template <typename FJ, typename FC> B2G_DEV void forEachInColor( const ColorRang
 B2G_DEV b2lJointSim* jointAt( const SolveView& V, int index )
 {
 	return reinterpret_cast<b2lJointSim*>( V.joints + (size_t)index * kJointStride );
-}
-
-B2G_DEV bool isLeadThread()
-{
-	return blockIdx.x == 0 && threadIdx.x == 0;
 }
 
 // ---- one stage of the grid-barrier path (view = global memory, wire slot == constraint slot) -----------------------

@@ -21,6 +21,8 @@
 
 #include "b2g_math.cuh"
 
+#include "b2_gpu_solver.h"
+
 namespace b2g
 {
 
@@ -88,6 +90,7 @@ struct SolveView
 	int2* cidx;	   // indexA+1, indexB+1 (0 = static dummy) in the view's own body numbering
 	int* cmeta;	   // kMeta* bits
 	uint8_t* joints; // b2JointSim working copy (indexA/indexB in the view's numbering, 0-based, -1 = static)
+	int* anyRestitution; // set by prepare when a contact of the view has restitution != 0
 };
 
 struct StepParams
@@ -130,7 +133,25 @@ struct StepParams
 	float* outImpulses; // kImpulseFloats per slot
 	uint32_t* jointBits;
 	int* hasHitEvents;
-	int* anyRestitution; // set by prepare when some contact has restitution != 0 (else the restitution stages are skipped)
+
+	// island-local mode (b2g_island.cuh): islands are packed into bins, one thread block solves one bin entirely in
+	// shared memory.  Scratch written by the partition kernel, read by the island kernel.
+	int binCount;	   // 0 = island mode off for this step
+	int capBodies;	   // per-bin capacities the shared memory carve-up was sized for
+	int capContacts;
+	int capJoints;
+	const int* bodyBin;	 // [bodyCount] bin of each body (wire arena)
+	int* bodyLocal;		 // [bodyCount] 1-based index of the body inside its bin
+	int* binBodyCount;	 // [binCount]
+	int* binBodyList;	 // [binCount * capBodies] global body index
+	int* binColorStart;	 // [binCount * (kMaxColors + 1)] contact counts per colour, then exclusive offsets (+ total)
+	int* binJointStart;	 // same for joints
+	int2* contactBinRank; // [contactSlots] bin, rank within (bin, colour)
+	int* slotGroupBits;	 // [contactSlots] kMetaGroup* bits in wire order
+	int* binContactList; // [binCount * capContacts] wire slots, colour-major
+	int2* jointBinRank;	 // [jointCount]
+	int* binJointList;	 // [binCount * capJoints] joint index, colour-major
+	int* binFail;		 // set when some bin does not fit its capacities: the grid-barrier kernel takes the step
 
 	// sync + profiling
 	unsigned int* barrier;			 // [0] arrival counter, [1] exit counter

@@ -27,6 +27,8 @@
 typedef struct b2SeamSlot
 {
 	b2GpuSolver* solver;
+	int* islandLabels;
+	int islandLabelCapacity;
 	b2GpuStepResult lastResult;
 	b2GpuStepDesc lastDesc;
 } b2SeamSlot;
@@ -85,6 +87,9 @@ void b2GpuSeam_Shutdown( void )
 		{
 			b2GpuSolverDestroy( s_slots[i].solver );
 			s_slots[i].solver = NULL;
+			free( s_slots[i].islandLabels );
+			s_slots[i].islandLabels = NULL;
+			s_slots[i].islandLabelCapacity = 0;
 		}
 	}
 }
@@ -139,6 +144,15 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 
 	b2GpuStepDesc* desc = &slot->lastDesc;
 	b2GpuSeam_BuildDesc( world, context, desc );
+
+	// island hint: lets the device solve islands independently in shared memory (no grid barriers)
+	if ( slot->islandLabelCapacity < desc->awakeBodyCount )
+	{
+		free( slot->islandLabels );
+		slot->islandLabelCapacity = desc->awakeBodyCount + desc->awakeBodyCount / 2 + 64;
+		slot->islandLabels = malloc( (size_t)slot->islandLabelCapacity * sizeof( int ) );
+	}
+	b2GpuSeam_FillIslands( world, desc, slot->islandLabels, true );
 
 	b2GpuStepResult* result = &slot->lastResult;
 	memset( result, 0, sizeof( *result ) );

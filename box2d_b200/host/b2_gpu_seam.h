@@ -11,6 +11,8 @@
 
 #include "b2_gpu_solver.h"
 
+#include <stdbool.h>
+
 typedef struct b2World b2World;
 typedef struct b2StepContext b2StepContext;
 
@@ -22,6 +24,10 @@ extern "C"
 /* Fill the C-ABI step descriptor from the reference's world + step context.  Joint sims must already be
  * prepared (b2PrepareJoint, src/joint.c:1406).  Shared by the product seam and the oracle's capture hook. */
 void b2GpuSeam_BuildDesc( b2World* world, b2StepContext* stepContext, b2GpuStepDesc* desc );
+
+/* Fill the optional island hint of the descriptor: labels[i] = index of awake body i's island among the awake islands.
+ * `labels` must hold awakeBodyCount ints and stay valid for the duration of the solver call. */
+void b2GpuSeam_FillIslands( b2World* world, b2GpuStepDesc* desc, int* labels, bool parallel );
 
 /* Prepare every awake joint on the host (b2ParallelFor over the flat joint range + the overflow colour),
  * i.e. the b2_stagePrepareJoints stage and b2PrepareJoints_Overflow (src/solver.c:1060-1077). */

@@ -16,6 +16,7 @@
 #include "contact.h"
 #include "core.h"
 #include "id_pool.h"
+#include "island.h"
 #include "joint.h"
 #include "parallel_for.h"
 #include "physics_world.h"
@@ -281,6 +282,46 @@ void b2GpuSeam_BuildDesc( b2World* world, b2StepContext* context, b2GpuStepDesc*
 
 	desc->contactIdCapacity = b2GetIdCapacity( &world->contactIdPool );
 	desc->jointIdCapacity = b2GetIdCapacity( &world->jointIdPool );
+}
+
+/* ---- island hint ------------------------------------------------------------------------------------------- */
+
+typedef struct b2SeamIslandTask
+{
+	b2World* world;
+	const b2BodySim* sims;
+	int* labels;
+} b2SeamIslandTask;
+
+// label = index of the body's island among the awake islands (b2Island::localIndex, src/island.h:49-74)
+static void b2SeamIslandLabelsTask( int startIndex, int endIndex, int workerIndex, void* taskContext )
+{
+	(void)workerIndex;
+	b2SeamIslandTask* task = taskContext;
+	const b2Body* bodies = task->world->bodies.data;
+	const b2Island* islands = task->world->islands.data;
+	for ( int i = startIndex; i < endIndex; ++i )
+	{
+		int islandId = bodies[task->sims[i].bodyId].islandId;
+		task->labels[i] = islandId == B2_NULL_INDEX ? -1 : islands[islandId].localIndex;
+	}
+}
+
+void b2GpuSeam_FillIslands( b2World* world, b2GpuStepDesc* desc, int* labels, bool parallel )
+{
+	b2SolverSet* awakeSet = world->solverSets.data + b2_awakeSet;
+	b2SeamIslandTask task = { world, awakeSet->bodySims.data, labels };
+	int count = awakeSet->bodySims.count;
+	if ( parallel )
+	{
+		b2ParallelFor( world, b2SeamIslandLabelsTask, count, 512, &task );
+	}
+	else
+	{
+		b2SeamIslandLabelsTask( 0, count, 0, &task );
+	}
+	desc->bodyIsland = labels;
+	desc->islandCount = awakeSet->islandSims.count;
 }
 
 /* ---- host joint prepare --------------------------------------------------------------------------------- */

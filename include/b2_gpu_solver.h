@@ -102,6 +102,15 @@ typedef struct b2GpuStepDesc
 	/* bit-set sizing (src/solver.c:1563-1564) */
 	int contactIdCapacity;
 	int jointIdCapacity;
+
+	/* Optional partition hint: for every awake body the index of its simulation island among the awake islands
+	 * (b2Island::localIndex of world->islands[b2Body::islandId], src/island.h:49-74), -1 if the body has none.
+	 * Constraints never couple dynamic bodies of different islands (src/island.c:194-330), which lets the device
+	 * solve islands independently in shared memory with no grid-wide barriers.  NULL = no hint: the whole step is
+	 * solved by the grid-barrier kernel.  The result does not depend on the hint (bit-identical either way). */
+	const int* bodyIsland;
+	int islandCount;
+	int reserved0;
 } b2GpuStepDesc;
 
 /* Index of each per-stage timer, same split as b2Profile (include/box2d/types.h:526-551) filled by the

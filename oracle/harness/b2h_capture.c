@@ -6,9 +6,9 @@
  * inputs the C-ABI of include/b2_gpu_solver.h would receive for this step and the outputs the reference's CPU
  * solver produced from them.  The dumps are the kernel-level golden vectors under tests/golden/.
  *
- * File format "B2CAP002" (little endian):
+ * File format "B2CAP003" (little endian):
  *   char[8] magic | u32 descBytes | b2GpuStepDesc (raw, pointers meaningless)
- *   inputs : states[n*32] sims[n*96] { contacts[c*200] joints[j*252] } per active colour, then overflow
+ *   inputs : states[n*32] sims[n*96] islandLabels[n*4] { contacts[c*200] joints[j*252] } per active colour, then overflow
  *            (joints are PREPARED copies: b2PrepareJoint applied to a copy, src/joint.c:1406)
  *   outputs: states[n*32] { contacts[c*200] joints[j*252] } per active colour, then overflow
  *            u32 hitWords | u64[hitWords] | u32 jointWords | u64[jointWords] | i32 hasHitEvents
@@ -70,13 +70,18 @@ void b2OracleHook_BeforeSolve( b2World* world, b2StepContext* context )
 
 	b2GpuStepDesc* desc = &s_capture.desc;
 	b2GpuSeam_BuildDesc( world, context, desc );
+	int* labels = malloc( (size_t)( desc->awakeBodyCount + 1 ) * sizeof( int ) );
+	b2GpuSeam_FillIslands( world, desc, labels, false );
 
 	uint32_t descBytes = (uint32_t)sizeof( b2GpuStepDesc );
-	b2hWrite( "B2CAP002", 8 );
+	b2hWrite( "B2CAP003", 8 );
 	b2hWrite( &descBytes, 4 );
 	b2hWrite( desc, sizeof( *desc ) );
 	b2hWrite( desc->states, (size_t)desc->awakeBodyCount * sizeof( b2BodyState ) );
 	b2hWrite( desc->sims, (size_t)desc->awakeBodyCount * sizeof( b2BodySim ) );
+	b2hWrite( labels, (size_t)desc->awakeBodyCount * sizeof( int ) );
+	free( labels );
+	desc->bodyIsland = NULL;
 
 	for ( int c = 0; c <= desc->activeColorCount; ++c )
 	{
