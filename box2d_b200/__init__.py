@@ -135,6 +135,8 @@ def solver_lib() -> ctypes.CDLL:
 		fn = getattr(lib, name)
 		fn.restype = ctypes.c_int
 		fn.argtypes = [ctypes.c_void_p]
+	lib.b2GpuSolverFlushPacked.restype = ctypes.c_int
+	lib.b2GpuSolverFlushPacked.argtypes = [ctypes.c_void_p, ctypes.c_int]
 	for name in ("b2GpuSolverPackRange", "b2GpuSolverUnpackRange"):
 		fn = getattr(lib, name)
 		fn.restype = None

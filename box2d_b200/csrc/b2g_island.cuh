@@ -23,7 +23,8 @@ namespace b2g
 {
 
 constexpr int kIslandThreads = 512;
-constexpr int kColorSlots = kMaxColors + 1; // per-bin offsets: colours + total
+constexpr int kColorSlots = kMaxColors + 2; // per-bin offsets: active colours, then the overflow bucket, then the total
+constexpr int kMaxBinOverflow = 256;		   // overflow constraints (contacts or joints) one bin can order
 
 B2G_DEV int jointBodyForBin( const uint8_t* record )
 {
@@ -37,6 +38,27 @@ B2G_DEV int jointBodyForBin( const uint8_t* record )
 	return pair[0] >= 0 ? pair[0] : pair[1];
 }
 
+// Warp-aggregated counter increment: lanes with the same key elect a leader that does ONE atomicAdd for the group and
+// hands out consecutive values.  Must be called by all 32 lanes; inactive lanes pass active == false.
+B2G_DEV int aggregatedAdd( int* counters, int key, bool active )
+{
+	unsigned peers = __match_any_sync( 0xffffffffu, active ? key : -1 - (int)( threadIdx.x & 31u ) );
+	int result = 0;
+	if ( active )
+	{
+		unsigned lane = threadIdx.x & 31u;
+		int leader = __ffs( peers ) - 1;
+		int base = 0;
+		if ( (int)lane == leader )
+		{
+			base = atomicAdd( counters + key, __popc( peers ) );
+		}
+		base = __shfl_sync( peers, base, leader );
+		result = base + __popc( peers & ( ( 1u << lane ) - 1u ) );
+	}
+	return result;
+}
+
 // ---- partition ---------------------------------------------------------------------------------------------------------
 // counters (binBodyCount, binColorStart, binJointStart, binFail) are zeroed by the host before the launch
 __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const __grid_constant__ StepParams P )
@@ -44,7 +66,9 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned blocks = gridDim.x;
 
-	// phase 1: local index of every body in its bin, (bin, rank) of every constraint, SIMD-group bits in wire order
+	// phase 1: local index of every body in its bin, (bin, rank) of every constraint, SIMD-group bits in wire order.
+	// Every pass is flat over all items (no per-colour loop: each pass is a chain of dependent L2 round trips, so the
+	// passes must not be serialised), and lanes that hit the same counter are aggregated into one atomic.
 	forEachItem( P.jointWords, [&]( int i ) {
 		if ( i < P.jointWords )
 		{
@@ -52,10 +76,11 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 		}
 	} );
 	forEachItem( P.bodyCount, [&]( int b ) {
-		if ( b < P.bodyCount )
+		bool active = b < P.bodyCount;
+		int bin = active ? P.bodyBin[b] : -1;
+		int local = aggregatedAdd( P.binBodyCount, bin, active );
+		if ( active )
 		{
-			int bin = P.bodyBin[b];
-			int local = atomicAdd( P.binBodyCount + bin, 1 );
 			if ( local < P.capBodies )
 			{
 				P.binBodyList[(size_t)bin * P.capBodies + local] = b;
@@ -67,36 +92,56 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 			P.bodyLocal[b] = local + 1;
 		}
 	} );
-	for ( int c = 0; c < P.colorCount; ++c )
-	{
-		ColorRange color = P.colors[c];
-		forEachItem( color.contactCount, [&]( int i ) {
-			bool active = i < color.contactCount;
-			int slot = color.contactStart + i;
-			int bits = simdGroupBits( P, slot, active, lane );
-			if ( active )
+	// contacts: colour slots are 32-aligned, so a chunk of 32 slots belongs to exactly one colour (or to the overflow
+	// colour, bucket index colorCount, whose constraints keep their array order: see the island kernel)
+	forEachItem( P.contactSlots, [&]( int slot ) {
+		int c = 0;
+		while ( c < P.colorCount && ( c + 1 < P.colorCount ? P.colors[c + 1].contactStart : P.overflow.contactStart ) <= slot )
+		{
+			c += 1;
+		}
+		bool isOverflow = c == P.colorCount;
+		ColorRange color = isOverflow ? P.overflow : P.colors[c];
+		bool active = slot < color.contactStart + color.contactCount;
+		int bits = simdGroupBits( P, slot, active && !isOverflow, lane );
+		int key = -1;
+		int bin = 0;
+		if ( active )
+		{
+			float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+			int indexA = __float_as_int( head.x );
+			int indexB = __float_as_int( head.y );
+			bin = P.bodyBin[indexA >= 0 ? indexA : indexB];
+			key = bin * kColorSlots + c;
+		}
+		int rank = aggregatedAdd( P.binColorStart, key, active );
+		if ( active )
+		{
+			P.contactBinRank[slot] = make_int2( bin, rank );
+			P.slotGroupBits[slot] = bits;
+		}
+	} );
+	forEachItem( P.jointCount, [&]( int j ) {
+		bool active = j < P.jointCount;
+		int key = -1, bin = 0;
+		if ( active )
+		{
+			int c = 0;
+			while ( c < P.colorCount && ( c + 1 < P.colorCount ? P.colors[c + 1].jointStart : P.overflow.jointStart ) <= j )
 			{
-				float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
-				int indexA = __float_as_int( head.x );
-				int indexB = __float_as_int( head.y );
-				int bin = P.bodyBin[indexA >= 0 ? indexA : indexB];
-				int rank = atomicAdd( P.binColorStart + (size_t)bin * kColorSlots + c, 1 );
-				P.contactBinRank[slot] = make_int2( bin, rank );
-				P.slotGroupBits[slot] = bits;
+				c += 1;
 			}
-		} );
-		forEachItem( color.jointCount, [&]( int i ) {
-			if ( i < color.jointCount )
-			{
-				int j = color.jointStart + i;
-				int body = jointBodyForBin( P.rawJoints + (size_t)j * kJointStride );
-				// a filter joint has no solver data: park it in bin 0, it is a no-op in every stage
-				int bin = body >= 0 ? P.bodyBin[body] : 0;
-				int rank = atomicAdd( P.binJointStart + (size_t)bin * kColorSlots + c, 1 );
-				P.jointBinRank[j] = make_int2( bin, rank );
-			}
-		} );
-	}
+			int body = jointBodyForBin( P.rawJoints + (size_t)j * kJointStride );
+			// a filter joint has no solver data: park it in bin 0, it is a no-op in every stage
+			bin = body >= 0 ? P.bodyBin[body] : 0;
+			key = bin * kColorSlots + c;
+		}
+		int rank = aggregatedAdd( P.binJointStart, key, active );
+		if ( active )
+		{
+			P.jointBinRank[j] = make_int2( bin, rank );
+		}
+	} );
 	gridBarrier( P.barrier + 1, blocks );
 
 	// phase 2: per bin, counts -> exclusive offsets (colour-major layout of the bin's lists), capacity check
@@ -106,7 +151,7 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 			int* contactStart = P.binColorStart + (size_t)bin * kColorSlots;
 			int* jointStart = P.binJointStart + (size_t)bin * kColorSlots;
 			int contacts = 0, joints = 0;
-			for ( int c = 0; c < P.colorCount; ++c )
+			for ( int c = 0; c <= P.colorCount; ++c ) // the bucket after the last colour is the overflow colour
 			{
 				int n = contactStart[c];
 				contactStart[c] = contacts;
@@ -114,8 +159,12 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 				int m = jointStart[c];
 				jointStart[c] = joints;
 				joints += m;
+				if ( c == P.colorCount && ( n > kMaxBinOverflow || m > kMaxBinOverflow ) )
+				{
+					*P.binFail = 1;
+				}
 			}
-			for ( int c = P.colorCount; c < kColorSlots; ++c )
+			for ( int c = P.colorCount + 1; c < kColorSlots; ++c )
 			{
 				contactStart[c] = contacts;
 				jointStart[c] = joints;
@@ -132,29 +181,34 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 		return;
 	}
 
-	// phase 3: place every constraint in its bin's list
-	for ( int c = 0; c < P.colorCount; ++c )
-	{
-		ColorRange color = P.colors[c];
-		forEachItem( color.contactCount, [&]( int i ) {
-			if ( i < color.contactCount )
+	// phase 3: place every constraint in its bin's list (flat passes again)
+	forEachItem( P.contactSlots, [&]( int slot ) {
+		int c = 0;
+		while ( c < P.colorCount && ( c + 1 < P.colorCount ? P.colors[c + 1].contactStart : P.overflow.contactStart ) <= slot )
+		{
+			c += 1;
+		}
+		ColorRange color = c == P.colorCount ? P.overflow : P.colors[c];
+		if ( slot < color.contactStart + color.contactCount )
+		{
+			int2 br = P.contactBinRank[slot];
+			int dest = P.binColorStart[(size_t)br.x * kColorSlots + c] + br.y;
+			P.binContactList[(size_t)br.x * P.capContacts + dest] = slot;
+		}
+	} );
+	forEachItem( P.jointCount, [&]( int j ) {
+		if ( j < P.jointCount )
+		{
+			int c = 0;
+			while ( c < P.colorCount && ( c + 1 < P.colorCount ? P.colors[c + 1].jointStart : P.overflow.jointStart ) <= j )
 			{
-				int slot = color.contactStart + i;
-				int2 br = P.contactBinRank[slot];
-				int dest = P.binColorStart[(size_t)br.x * kColorSlots + c] + br.y;
-				P.binContactList[(size_t)br.x * P.capContacts + dest] = slot;
+				c += 1;
 			}
-		} );
-		forEachItem( color.jointCount, [&]( int i ) {
-			if ( i < color.jointCount )
-			{
-				int j = color.jointStart + i;
-				int2 br = P.jointBinRank[j];
-				int dest = P.binJointStart[(size_t)br.x * kColorSlots + c] + br.y;
-				P.binJointList[(size_t)br.x * P.capJoints + dest] = j;
-			}
-		} );
-	}
+			int2 br = P.jointBinRank[j];
+			int dest = P.binJointStart[(size_t)br.x * kColorSlots + c] + br.y;
+			P.binJointList[(size_t)br.x * P.capJoints + dest] = j;
+		}
+	} );
 }
 
 // ---- island kernel -------------------------------------------------------------------------------------------------------
@@ -200,6 +254,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	__shared__ int colorStartC[kColorSlots];
 	__shared__ int colorStartJ[kColorSlots];
 	__shared__ int anyRestitution;
+	__shared__ int overflowOrder[kMaxBinOverflow]; // scratch for ordering the bin's overflow constraints
 
 	const int bin = (int)blockIdx.x;
 	const int capB = P.capBodies, capC = P.capContacts, capJ = P.capJoints;
@@ -221,7 +276,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	V.cidx = reinterpret_cast<int2*>( cursor );
 	cursor += (size_t)capC * sizeof( int2 );
 	int2* jointGlobal = reinterpret_cast<int2*>( cursor ); // the joints' global body indices, restored at the end
-	cursor += (size_t)capJ * sizeof( int2 );
+	cursor += (size_t)capJ * ( sizeof( int2 ) + sizeof( int ) ); // + jointIndexOf
 	V.angDamp = reinterpret_cast<float*>( cursor );
 	cursor += (size_t)capB * sizeof( float );
 	V.cmeta = reinterpret_cast<int*>( cursor );
@@ -252,28 +307,70 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	forEachLocal( bodyCount, [&]( int i ) { loadBody( P, V, bodyList[i], i + 1 ); } );
 	__syncthreads();
 
-	const int contactCount = colorStartC[kMaxColors];
-	const int jointCount = colorStartJ[kMaxColors];
+	const int contactCount = colorStartC[kColorSlots - 1];
+	const int jointCount = colorStartJ[kColorSlots - 1];
 	const int colorCount = P.colorCount;
+	// the overflow colour's constraints of this bin, solved by one thread in array order
+	const int ovCb = colorStartC[colorCount], ovCe = colorStartC[colorCount + 1];
+	const int ovJb = colorStartJ[colorCount], ovJe = colorStartJ[colorCount + 1];
+	const bool hasOverflow = ( ovCe - ovCb ) + ( ovJe - ovJb ) > 0;
+
+	// The atomics of the partition kernel scrambled the order inside a bucket.  That is harmless for a colour, but the
+	// overflow colour is solved sequentially in ARRAY order (src/solver.c:1100-1101): rank-sort its part of the lists.
+	auto orderedIndex = [&]( const int* list, int begin, int end, int k ) -> int {
+		// returns the element of list[begin, end) whose rank is (k - begin) in ascending order
+		return k < begin || k >= end ? list[k] : overflowOrder[k - begin];
+	};
+	if ( ovCe > ovCb )
+	{
+		for ( int k = ovCb + (int)threadIdx.x; k < ovCe; k += (int)blockDim.x )
+		{
+			int mine = contactList[k], rank = 0;
+			for ( int m = ovCb; m < ovCe; ++m )
+			{
+				rank += contactList[m] < mine ? 1 : 0;
+			}
+			overflowOrder[rank] = mine;
+		}
+	}
+	__syncthreads();
 
 	// prepare: contacts read the bodies' initial velocities from the view (identical to the wire states here)
 	forEachLocal( contactCount, [&]( int k ) {
-		int slot = contactList[k];
+		int slot = orderedIndex( contactList, ovCb, ovCe, k );
 		float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
 		int indexA = __float_as_int( head.x );
 		int indexB = __float_as_int( head.y );
 		int localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;
 		int localB = indexB >= 0 ? P.bodyLocal[indexB] : 0;
 		wireSlot[k] = slot;
-		prepareContact( P, V, slot, k, localA, localB, V.vel[localA], V.vel[localB], true, P.slotGroupBits[slot] );
+		bool wide = k < ovCb || k >= ovCe;
+		prepareContact( P, V, slot, k, localA, localB, V.vel[localA], V.vel[localB], wide, wide ? P.slotGroupBits[slot] : 0 );
 	} );
+	__syncthreads();
 	// joints: copy the prepared record into shared memory, renumber its bodies to the bin
+	if ( ovJe > ovJb )
+	{
+		for ( int k = ovJb + (int)threadIdx.x; k < ovJe; k += (int)blockDim.x )
+		{
+			int mine = jointList[k], rank = 0;
+			for ( int m = ovJb; m < ovJe; ++m )
+			{
+				rank += jointList[m] < mine ? 1 : 0;
+			}
+			overflowOrder[rank] = mine;
+		}
+	}
+	__syncthreads();
+	int* jointIndexOf = reinterpret_cast<int*>( jointGlobal + capJ ); // [capJ] global joint index of every local joint
+	forEachLocal( jointCount, [&]( int k ) { jointIndexOf[k] = orderedIndex( jointList, ovJb, ovJe, k ); } );
+	__syncthreads();
 	{
 		const int quads = kJointStride / 16;
 		for ( int t = (int)threadIdx.x; t < jointCount * quads; t += (int)blockDim.x )
 		{
 			int k = t / quads, q = t - k * quads;
-			const float4* src = reinterpret_cast<const float4*>( P.rawJoints + (size_t)jointList[k] * kJointStride );
+			const float4* src = reinterpret_cast<const float4*>( P.rawJoints + (size_t)jointIndexOf[k] * kJointStride );
 			reinterpret_cast<float4*>( V.joints + (size_t)k * kJointStride )[q] = src[q];
 		}
 	}
@@ -297,6 +394,21 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		__syncthreads();
 		clk.lap( b2GpuStage_integrateVelocities );
 
+		if ( hasOverflow )
+		{
+			if ( threadIdx.x == 0 )
+			{
+				for ( int k = ovJb; k < ovJe; ++k )
+				{
+					warmStartJoint( P, V, jointAt( V, k ) );
+				}
+				for ( int k = ovCb; k < ovCe; ++k )
+				{
+					warmStartContactOverflow( V, k );
+				}
+			}
+			__syncthreads();
+		}
 		for ( int c = 0; c < colorCount; ++c )
 		{
 			int jb = colorStartJ[c], je = colorStartJ[c + 1], cb = colorStartC[c], ce = colorStartC[c + 1];
@@ -310,6 +422,21 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		}
 		clk.lap( b2GpuStage_warmStart );
 
+		if ( hasOverflow )
+		{
+			if ( threadIdx.x == 0 )
+			{
+				for ( int k = ovJb; k < ovJe; ++k )
+				{
+					solveJoint( P, V, jointAt( V, k ), true );
+				}
+				for ( int k = ovCb; k < ovCe; ++k )
+				{
+					solveContactOverflow( P, V, k, true );
+				}
+			}
+			__syncthreads();
+		}
 		for ( int c = 0; c < colorCount; ++c )
 		{
 			int jb = colorStartJ[c], je = colorStartJ[c + 1], cb = colorStartC[c], ce = colorStartC[c + 1];
@@ -333,6 +460,21 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		__syncthreads();
 		clk.lap( b2GpuStage_integratePositions );
 
+		if ( hasOverflow )
+		{
+			if ( threadIdx.x == 0 )
+			{
+				for ( int k = ovJb; k < ovJe; ++k )
+				{
+					solveJoint( P, V, jointAt( V, k ), false );
+				}
+				for ( int k = ovCb; k < ovCe; ++k )
+				{
+					solveContactOverflow( P, V, k, false );
+				}
+			}
+			__syncthreads();
+		}
 		for ( int c = 0; c < colorCount; ++c )
 		{
 			int jb = colorStartJ[c], je = colorStartJ[c + 1], cb = colorStartC[c], ce = colorStartC[c + 1];
@@ -350,6 +492,17 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 
 	if ( anyRestitution != 0 )
 	{
+		if ( ovCe > ovCb )
+		{
+			if ( threadIdx.x == 0 )
+			{
+				for ( int k = ovCb; k < ovCe; ++k )
+				{
+					restitutionContactOverflow( P, V, k );
+				}
+			}
+			__syncthreads();
+		}
 		for ( int c = 0; c < colorCount; ++c )
 		{
 			int cb = colorStartC[c], ce = colorStartC[c + 1];
@@ -367,7 +520,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	clk.lap( b2GpuStage_applyRestitution );
 
 	// store: impulses by wire slot, states by global body index, joints with their global body indices restored
-	forEachLocal( contactCount, [&]( int k ) { storeContact( P, V, k, wireSlot[k], true ); } );
+	forEachLocal( contactCount, [&]( int k ) { storeContact( P, V, k, wireSlot[k], k < ovCb || k >= ovCe ); } );
 	forEachLocal( bodyCount, [&]( int i ) { storeBody( P, V, bodyList[i], i + 1 ); } );
 	forEachLocal( jointCount, [&]( int k ) {
 		int* pair = jointIndexPair( jointAt( V, k ) );
@@ -383,7 +536,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		for ( int t = (int)threadIdx.x; t < jointCount * quads; t += (int)blockDim.x )
 		{
 			int k = t / quads, q = t - k * quads;
-			float4* dst = reinterpret_cast<float4*>( P.g.joints + (size_t)jointList[k] * kJointStride );
+			float4* dst = reinterpret_cast<float4*>( P.g.joints + (size_t)jointIndexOf[k] * kJointStride );
 			dst[q] = reinterpret_cast<const float4*>( V.joints + (size_t)k * kJointStride )[q];
 		}
 	}
@@ -410,7 +563,7 @@ inline size_t islandSharedBytes( int capB, int capC, int capJ )
 	bytes += (size_t)CF_COUNT * capC * sizeof( float4 );  // contact fields
 	bytes += (size_t)capJ * kJointStride;				  // joints
 	bytes += (size_t)capC * sizeof( int2 );				  // cidx
-	bytes += (size_t)capJ * sizeof( int2 );				  // jointGlobal
+	bytes += (size_t)capJ * ( sizeof( int2 ) + sizeof( int ) ); // jointGlobal, jointIndexOf
 	bytes += (size_t)capB * sizeof( float );			  // angDamp
 	bytes += 2 * (size_t)capC * sizeof( int );			  // cmeta, wireSlot
 	return bytes;

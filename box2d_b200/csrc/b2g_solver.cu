@@ -289,6 +289,7 @@ struct b2GpuSolver
 	std::vector<int> islandBodies; // host: bodies per island, then per bin
 	size_t binCounterCount = 0;
 	size_t islandSmemBytes = 0;
+	size_t islandSmemBudget = 0;
 	bool islandMode = false;
 	int islandsEnabled = 1;
 	int maxSharedOptin = 0;
@@ -302,6 +303,7 @@ struct b2GpuSolver
 
 	// arena layouts, in float4 units
 	size_t inStates = 0, inBody = 0, inWire = 0, inJoints = 0, inBins = 0, inTotal = 0;
+	size_t sentQuads = 0; // prefix of the input arena already enqueued for upload (b2GpuSolverFlushPacked)
 	size_t outStates = 0, outImpulses = 0, outJoints = 0, outBits = 0, outTotal = 0;
 
 	// the step in flight
@@ -404,10 +406,21 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 	s->maxSharedOptin = (int)prop.sharedMemPerBlockOptin;
 	const char* islandEnv = getenv( "B2GPU_ISLANDS" );
 	s->islandsEnabled = islandEnv != nullptr ? atoi( islandEnv ) : 1;
-	if ( cudaFuncSetAttribute( b2g::b2gIslandKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, s->maxSharedOptin - 1024 ) != cudaSuccess )
 	{
-		cudaGetLastError();
-		s->islandsEnabled = 0;
+		cudaFuncAttributes attr;
+		int dynamicMax = 0;
+		if ( cudaFuncGetAttributes( &attr, b2g::b2gIslandKernel ) == cudaSuccess )
+		{
+			dynamicMax = s->maxSharedOptin - (int)attr.sharedSizeBytes - 256;
+		}
+		if ( dynamicMax <= 0 ||
+			 cudaFuncSetAttribute( b2g::b2gIslandKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dynamicMax ) != cudaSuccess )
+		{
+			cudaGetLastError();
+			s->islandsEnabled = 0;
+			dynamicMax = 0;
+		}
+		s->islandSmemBudget = (size_t)dynamicMax;
 	}
 
 	bool ok = cudaStreamCreateWithFlags( &s->stream, cudaStreamNonBlocking ) == cudaSuccess;
@@ -496,8 +509,8 @@ extern "C" uint64_t b2GpuSolverGetLaunchCount( const b2GpuSolver* s )
 
 // ---- island mode planning (host) --------------------------------------------------------------------------------
 // Pack the awake islands into at most one bin per SM, balanced by body count, and size the island kernel's shared
-// memory carve-up.  Island mode is used when the hint is present, the overflow colour is empty (it is strictly
-// sequential, src/solver.c:1100-1101) and the estimated bins fit; the device double-checks the exact sizes.
+// memory carve-up.  Island mode is used when the hint is present and the estimated bins fit; the device double-checks
+// the exact sizes (binFail -> the grid-barrier kernel takes the step).
 static int b2gPlanIslands( b2GpuSolver* s )
 {
 	const b2GpuStepDesc& d = s->desc;
@@ -505,8 +518,7 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	s->islandMode = false;
 	P.binCount = 0;
 	int bodies = P.bodyCount;
-	if ( s->islandsEnabled == 0 || s->mode != 0 || d.bodyIsland == nullptr || d.islandCount <= 0 || bodies == 0 ||
-		 d.overflow.contactCount + d.overflow.jointCount > 0 )
+	if ( s->islandsEnabled == 0 || s->mode != 0 || d.bodyIsland == nullptr || d.islandCount <= 0 || bodies == 0 )
 	{
 		return 0;
 	}
@@ -550,11 +562,11 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	int capB = roundUp4( maxBin );
 	double share = (double)maxBin / (double)bodies;
 	double needC = share * s->contactTotal, needJ = share * s->jointTotal;
-	size_t budget = (size_t)s->maxSharedOptin - 2048;
+	size_t budget = s->islandSmemBudget;
 	// The proportional need is only an estimate (constraint density differs between islands): hand the whole
 	// shared-memory budget to the bin -- bodies exactly, the rest split between contacts and joints in
 	// proportion to their estimated bytes -- so a bin may hold several times its fair share before binFail trips.
-	const double bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0, bytesPerJoint = b2g::kJointStride + 8.0;
+	const double bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0, bytesPerJoint = b2g::kJointStride + 12.0;
 	size_t fixed = b2g::islandSharedBytes( capB, 0, 0 );
 	if ( fixed + (size_t)( needC * 1.1 * bytesPerContact + needJ * 1.1 * bytesPerJoint ) + 4096 > budget )
 	{
@@ -568,7 +580,14 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	capC = capC > ( ( s->contactTotal + 3 ) & ~3 ) ? ( ( s->contactTotal + 3 ) & ~3 ) : capC;
 	capJ = capJ > ( ( s->jointTotal + 3 ) & ~3 ) ? ( ( s->jointTotal + 3 ) & ~3 ) : capJ;
 	capC = capC < 4 ? 4 : capC;
-	if ( b2g::islandSharedBytes( capB, capC, capJ ) > budget )
+	for ( int guard = 0; guard < 64 && b2g::islandSharedBytes( capB, capC, capJ ) > budget; ++guard )
+	{
+		capC = ( capC - capC / 32 - 4 ) & ~3; // rounding slack: shave ~3 % until it fits
+		capJ = capJ > 0 ? ( capJ - capJ / 32 - 4 ) & ~3 : 0;
+		capC = capC < 4 ? 4 : capC;
+		capJ = capJ < 0 ? 0 : capJ;
+	}
+	if ( b2g::islandSharedBytes( capB, capC, capJ ) > budget || capC < needC || capJ < needJ )
 	{
 		return 0;
 	}
@@ -688,13 +707,15 @@ extern "C" int b2GpuSolverBeginStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2G
 
 	size_t bodies = (size_t)P.bodyCount;
 	const size_t jointQuads = b2g::kJointStride / 16;
-	// input arena: [states 2/body][packed sims 2/body][contacts 7/slot][joints 16/joint]
+	// input arena: [states 2/body][packed sims 2/body][bins 1/4 body][contacts 7/slot][joints 16/joint]; item order
+	// (bodies, contacts, joints) is address order, so a prefix of packed items is a prefix of the arena
 	s->inStates = 0;
 	s->inBody = s->inStates + 2 * bodies;
-	s->inWire = s->inBody + 2 * bodies;
+	s->inBins = s->inBody + 2 * bodies;
+	s->inWire = s->inBins + ( bodies + 3 ) / 4;
 	s->inJoints = s->inWire + (size_t)b2g::WR_COUNT * slot;
-	s->inBins = s->inJoints + jointQuads * joint;
-	s->inTotal = s->inBins + ( bodies + 3 ) / 4;
+	s->inTotal = s->inJoints + jointQuads * joint;
+	s->sentQuads = 0;
 	// output arena: [states 2/body][impulse records][joints 16/joint][joint event bits]
 	size_t impulseQuads = ( (size_t)slot * b2g::kImpulseFloats + 3 ) / 4;
 	s->outStates = 0;
@@ -914,16 +935,67 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 }
 
 // ---- phase 3: H2D + kernels + D2H, all asynchronous on the solver's stream -------------------------------------------
+// quads of the input arena that hold items [0, itemEnd) (bodies, then contacts in slot order, then joints)
+static size_t b2gArenaPrefix( const b2GpuSolver* s, int itemEnd )
+{
+	int bodyCount = s->params.bodyCount;
+	if ( itemEnd < bodyCount )
+	{
+		return 0; // the three body regions are interleaved by region, not by body: wait for all bodies
+	}
+	int flat = itemEnd - bodyCount;
+	if ( flat <= 0 )
+	{
+		return s->inWire;
+	}
+	if ( flat < s->contactTotal )
+	{
+		int c = 0;
+		while ( s->flatStart[c + 1] <= flat )
+		{
+			c += 1;
+		}
+		int slot = s->slotStart[c] + ( flat - s->flatStart[c] );
+		return s->inWire + (size_t)slot * b2g::WR_COUNT;
+	}
+	int joints = flat - s->contactTotal;
+	joints = joints < s->jointTotal ? joints : s->jointTotal;
+	return s->inJoints + (size_t)joints * ( b2g::kJointStride / 16 );
+}
+
+static int b2gSendArena( b2GpuSolver* s, size_t uptoQuads )
+{
+	if ( s->sentQuads == 0 )
+	{
+		B2G_CUDA( cudaEventRecord( s->evUpload, s->stream ) );
+	}
+	if ( uptoQuads > s->sentQuads )
+	{
+		B2G_CUDA( cudaMemcpyAsync( s->wireAll.ptr + s->sentQuads, s->hWire.ptr + s->sentQuads,
+								   ( uptoQuads - s->sentQuads ) * sizeof( float4 ), cudaMemcpyHostToDevice, s->stream ) );
+		s->sentQuads = uptoQuads;
+	}
+	return 0;
+}
+
+// Start uploading what has been packed so far (items [0, itemEnd) must be complete): overlaps the PCIe transfer with
+// the packing of the remaining items.
+extern "C" int b2GpuSolverFlushPacked( b2GpuSolver* s, int itemEnd )
+{
+	if ( s == nullptr || !s->begun )
+	{
+		return b2gFailMsg( "b2GpuSolverFlushPacked: no step begun" );
+	}
+	return b2gSendArena( s, b2gArenaPrefix( s, itemEnd ) );
+}
+
 static int b2gEnqueueUpload( b2GpuSolver* s )
 {
-	cudaStream_t st = s->stream;
-	B2G_CUDA( cudaEventRecord( s->evUpload, st ) );
-	size_t bytes = s->inTotal * sizeof( float4 );
-	if ( bytes > 0 )
+	if ( b2gSendArena( s, s->inTotal ) != 0 )
 	{
-		B2G_CUDA( cudaMemcpyAsync( s->wireAll.ptr, s->hWire.ptr, bytes, cudaMemcpyHostToDevice, st ) );
+		return 1;
 	}
-	s->lastH2D = bytes;
+	s->lastH2D = s->inTotal * sizeof( float4 );
 	s->uploaded = true;
 	return 0;
 }
@@ -1105,6 +1177,56 @@ extern "C" int b2GpuSolverWait( b2GpuSolver* s )
 // ---- phase 4: unpack (callable concurrently on disjoint ranges) ---------------------------------------------------------
 // Scatter the packed impulse records into the reference's manifolds: what b2StoreImpulsesTask
 // (src/contact_solver.c:2293-2320) and b2StoreImpulses_Overflow (:526-542) write.
+// Evict a consumed part of the D2H staging buffer from the CPU caches.  On the target hosts a DMA write into lines
+// that are still cached by several cores runs at ~7 GB/s instead of ~54 GB/s (tools/microbench/d2h_bench.cu); flushing
+// right after the unpack pass keeps the next step's download at full speed for ~0.03 ms of host work.
+#if defined( __x86_64__ )
+#include <cpuid.h>
+static bool b2gHasClflushopt()
+{
+	static int cached = -1;
+	if ( cached < 0 )
+	{
+		unsigned a = 0, b = 0, c = 0, d = 0;
+		cached = ( __get_cpuid_count( 7, 0, &a, &b, &c, &d ) != 0 && ( b & ( 1u << 23 ) ) != 0 ) ? 1 : 0;
+	}
+	return cached == 1;
+}
+
+__attribute__( ( target( "clflushopt" ) ) ) static void b2gFlushOpt( const char* p, const char* end )
+{
+	for ( ; p < end; p += 64 )
+	{
+		_mm_clflushopt( const_cast<char*>( p ) );
+	}
+}
+
+static void b2gFlushLines( const void* ptr, size_t bytes )
+{
+	if ( bytes == 0 )
+	{
+		return;
+	}
+	const char* p = reinterpret_cast<const char*>( reinterpret_cast<uintptr_t>( ptr ) & ~uintptr_t( 63 ) );
+	const char* end = static_cast<const char*>( ptr ) + bytes;
+	if ( b2gHasClflushopt() )
+	{
+		b2gFlushOpt( p, end );
+	}
+	else
+	{
+		for ( ; p < end; p += 64 )
+		{
+			_mm_clflush( p );
+		}
+	}
+}
+#else
+static void b2gFlushLines( const void*, size_t )
+{
+}
+#endif
+
 extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 {
 	const b2GpuStepDesc& d = s->desc;
@@ -1123,6 +1245,7 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 		if ( begin < bodyEnd )
 		{
 			memcpy( states + (size_t)begin * B2L_STATE_SIZE, outStates + 2 * (size_t)begin, (size_t)( bodyEnd - begin ) * B2L_STATE_SIZE );
+			b2gFlushLines( outStates + 2 * (size_t)begin, (size_t)( bodyEnd - begin ) * B2L_STATE_SIZE );
 		}
 	}
 
@@ -1160,6 +1283,10 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 					__atomic_fetch_or( hitBits + ( id >> 6 ), (uint64_t)1 << ( id & 63u ), __ATOMIC_RELAXED );
 				}
 			}
+			if ( local < localEnd )
+			{
+				b2gFlushLines( records + (size_t)local * b2g::kImpulseFloats, (size_t)( localEnd - local ) * b2g::kImpulseFloats * sizeof( float ) );
+			}
 			flat = s->flatStart[c + 1];
 			c += 1;
 		}
@@ -1182,6 +1309,11 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 			{
 				memcpy( sims + (size_t)i * B2L_JOINT_SIZE, outJoints + (size_t)( s->jointFlatStart[c] + i ) * b2g::kJointStride,
 						B2L_JOINT_SIZE );
+			}
+			if ( local < localEnd )
+			{
+				b2gFlushLines( outJoints + (size_t)( s->jointFlatStart[c] + local ) * b2g::kJointStride,
+							   (size_t)( localEnd - local ) * b2g::kJointStride );
 			}
 			flat = s->jointFlatStart[c + 1];
 			c += 1;
@@ -1226,6 +1358,7 @@ extern "C" int b2GpuSolverEndStep( b2GpuSolver* s, b2GpuStepResult* r )
 				uint64_t word = (uint64_t)bits[2 * i] | ( (uint64_t)bits[2 * i + 1] << 32 );
 				r->jointEventBits[i] |= word;
 			}
+			b2gFlushLines( bits, (size_t)P.jointWords * sizeof( uint32_t ) );
 		}
 		r->hasHitEvents = s->hControl->hasHitEvents;
 		r->kernelMs = s->lastKernelMs;

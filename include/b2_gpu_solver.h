@@ -181,6 +181,8 @@ B2GPU_API int b2GpuSolverDownload( b2GpuSolver* solver, const b2GpuStepDesc* des
 B2GPU_API int b2GpuSolverBeginStep( b2GpuSolver* solver, const b2GpuStepDesc* desc, b2GpuStepResult* result );
 B2GPU_API int b2GpuSolverGetPackItemCount( const b2GpuSolver* solver );
 B2GPU_API void b2GpuSolverPackRange( b2GpuSolver* solver, int begin, int end );
+/* optional: start the upload of items [0, itemEnd) (all packed) while the rest is still being packed */
+B2GPU_API int b2GpuSolverFlushPacked( b2GpuSolver* solver, int itemEnd );
 B2GPU_API int b2GpuSolverSubmit( b2GpuSolver* solver );
 B2GPU_API int b2GpuSolverWait( b2GpuSolver* solver );
 B2GPU_API int b2GpuSolverGetUnpackItemCount( const b2GpuSolver* solver );
