@@ -369,6 +369,20 @@ class Capture:
 
 # byte ranges of b2ContactSim that the solver writes (include/b2gpu_layout.h): manifold.rollingImpulse and, per
 # point, normalImpulse, tangentImpulse, totalNormalImpulse, normalVelocity
+def make_batch(captures, islands: bool = True):
+	"""Wire a list of captures into contiguous (StepDesc * n), (StepResult * n) arrays + the buffers that back them."""
+	n = len(captures)
+	descs = (StepDesc * n)()
+	results = (StepResult * n)()
+	keep = []
+	for i, cap in enumerate(captures):
+		d, r, bufs = cap.make_call(islands=islands)
+		ctypes.memmove(ctypes.byref(descs[i]), ctypes.byref(d), ctypes.sizeof(StepDesc))
+		ctypes.memmove(ctypes.byref(results[i]), ctypes.byref(r), ctypes.sizeof(StepResult))
+		keep.append(bufs)
+	return descs, results, keep
+
+
 def contact_output_view(contacts: np.ndarray) -> np.ndarray:
 	"""[n, 9] float32 view of the solver-written fields of a b2ContactSim byte array."""
 	n = contacts.size // CONTACT_SIZE
@@ -410,6 +424,19 @@ class GpuSolver:
 	def download(self, desc: StepDesc, result: StepResult) -> None:
 		self._check(self.lib.b2GpuSolverDownload(self.handle, ctypes.byref(desc), ctypes.byref(result)),
 					"b2GpuSolverDownload")
+
+	def step_batch(self, descs, results) -> None:
+		"""descs / results: ctypes arrays (StepDesc * n), (StepResult * n) -- b2GpuSolverStepBatch."""
+		self._check(self.lib.b2GpuSolverStepBatch(self.handle, descs, len(descs), results), "b2GpuSolverStepBatch")
+
+	def upload_batch(self, descs) -> None:
+		self._check(self.lib.b2GpuSolverUploadBatch(self.handle, descs, len(descs)), "b2GpuSolverUploadBatch")
+
+	def run_batch(self, result: StepResult) -> None:
+		self._check(self.lib.b2GpuSolverRunBatch(self.handle, ctypes.byref(result)), "b2GpuSolverRunBatch")
+
+	def download_batch(self, descs, results) -> None:
+		self._check(self.lib.b2GpuSolverDownloadBatch(self.handle, descs, len(descs), results), "b2GpuSolverDownloadBatch")
 
 	def launch_count(self) -> int:
 		return int(self.lib.b2GpuSolverGetLaunchCount(self.handle))

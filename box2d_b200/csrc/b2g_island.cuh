@@ -102,13 +102,19 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 		}
 		bool isOverflow = c == P.colorCount;
 		ColorRange color = isOverflow ? P.overflow : P.colors[c];
-		bool active = slot < color.contactStart + color.contactCount;
+		bool inRange = slot < color.contactStart + color.contactCount;
+		float4 head = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+		if ( inRange )
+		{
+			head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+		}
+		// dead slots (padding between the segments of a batch) have pointCount 0 and are not placed in any bin
+		bool active = inRange && ( __float_as_int( head.z ) & kMetaPointMask ) != 0;
 		int bits = simdGroupBits( P, slot, active && !isOverflow, lane );
 		int key = -1;
 		int bin = 0;
 		if ( active )
 		{
-			float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
 			int indexA = __float_as_int( head.x );
 			int indexB = __float_as_int( head.y );
 			bin = P.bodyBin[indexA >= 0 ? indexA : indexB];
@@ -189,7 +195,8 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 			c += 1;
 		}
 		ColorRange color = c == P.colorCount ? P.overflow : P.colors[c];
-		if ( slot < color.contactStart + color.contactCount )
+		if ( slot < color.contactStart + color.contactCount &&
+			 ( __float_as_int( P.wire[(size_t)slot * WR_COUNT + WR_HEAD].z ) & kMetaPointMask ) != 0 )
 		{
 			int2 br = P.contactBinRank[slot];
 			int dest = P.binColorStart[(size_t)br.x * kColorSlots + c] + br.y;

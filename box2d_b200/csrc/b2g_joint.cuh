@@ -1446,7 +1446,10 @@ B2G_DEV void jointEventTest( const StepParams& P, const b2lJointSim* sim )
 	float torque = angularImpulse * P.inv_h;
 	if ( force >= sim->forceThreshold || torque >= sim->torqueThreshold )
 	{
-		unsigned id = (unsigned)sim->jointId;
+		// the 4 padding bytes behind the 252-byte record carry the world's first bit in the joint-event set (0 for a
+		// single world, see b2GpuSolverPackRange)
+		int bitBase = *reinterpret_cast<const int*>( reinterpret_cast<const uint8_t*>( sim ) + B2L_JOINT_SIZE );
+		unsigned id = (unsigned)( sim->jointId + bitBase );
 		atomicOr( P.jointBits + ( id >> 5 ), 1u << ( id & 31u ) );
 	}
 }

@@ -14,6 +14,9 @@
 #include <cuda_runtime.h>
 
 #include <immintrin.h>
+#if defined( __x86_64__ )
+#include <cpuid.h>
+#endif
 
 #include <chrono>
 #include <cstdio>
@@ -262,7 +265,64 @@ struct ControlBlock
 	unsigned long long stageCycles[10];
 };
 
-constexpr int kMaxColorSlots = b2g::kMaxColors + 1; // active colours + overflow
+// segments of the step (see "the step as segments" below)
+struct b2gBodySeg
+{
+	uint8_t* states;
+	const uint8_t* sims;
+	const int* islands;
+	int islandCount;
+	int islandBase; // first island of this world in the batch-wide numbering
+	int count;
+	int base;		  // first body of this world in the batch-wide numbering
+	int jointBitBase; // first bit of this world in the joint-event bit set
+	int jointWords;
+};
+
+struct b2gContactSeg
+{
+	uint8_t* sims;
+	int count;
+	int slotStart; // wire slot of the segment's first contact (multiple of 4)
+	int world;
+	bool wide; // false for the overflow colour
+	int colorIndex;
+};
+
+struct b2gJointSeg
+{
+	uint8_t* sims;
+	int count;
+	int jointStart;
+	int world;
+};
+
+// host twin of b2g::jointIndexPair (b2g_joint.cuh)
+static int* b2gJointIndexPair( b2lJointSim* joint )
+{
+	switch ( joint->type )
+	{
+		case b2l_distanceJoint:
+			return &joint->u.distance.indexA;
+		case b2l_motorJoint:
+			return &joint->u.motor.indexA;
+		case b2l_moverJoint:
+			return &joint->u.mover.indexA;
+		case b2l_pogoJoint:
+			return &joint->u.pogo.indexA;
+		case b2l_prismaticJoint:
+			return &joint->u.prismatic.indexA;
+		case b2l_revoluteJoint:
+			return &joint->u.revolute.indexA;
+		case b2l_weldJoint:
+			return &joint->u.weld.indexA;
+		case b2l_wheelJoint:
+			return &joint->u.wheel.indexA;
+		default:
+			return nullptr;
+	}
+}
+
 
 struct b2GpuSolver
 {
@@ -307,14 +367,15 @@ struct b2GpuSolver
 	size_t outStates = 0, outImpulses = 0, outJoints = 0, outBits = 0, outTotal = 0;
 
 	// the step in flight
-	b2GpuStepDesc desc;
-	b2GpuStepResult* result = nullptr;
+	std::vector<b2GpuStepDesc> descs;
+	b2GpuStepResult* results = nullptr; // one per world, or NULL
+	std::vector<b2gBodySeg> bodySegs;
+	std::vector<b2gContactSeg> contactSegs;
+	std::vector<b2gJointSeg> jointSegs;
+	std::vector<int> bodyStart, contactStart, jointStart; // item prefix sums, one more entry than segments
+	std::vector<int> binBodies;
 	b2g::StepParams params;
-	int flatStart[kMaxColorSlots + 1];	// flat contact index of each colour slot's first contact (overflow last)
-	int slotStart[kMaxColorSlots];		// wire slot of each colour slot's first contact
-	int jointFlatStart[kMaxColorSlots + 1]; // flat joint index of each colour slot's first joint
 	int jointTotal = 0;
-	int colorSlotCount = 0;
 	int contactTotal = 0;
 	bool begun = false;
 	bool uploaded = false;
@@ -436,7 +497,6 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		return nullptr;
 	}
 	memset( &s->params, 0, sizeof( s->params ) );
-	memset( &s->desc, 0, sizeof( s->desc ) );
 	return s;
 }
 
@@ -507,41 +567,91 @@ extern "C" uint64_t b2GpuSolverGetLaunchCount( const b2GpuSolver* s )
 	return s != nullptr ? s->launchCount : 0;
 }
 
+// ---- the step as segments ---------------------------------------------------------------------------------------------
+// One step solves `worldCount` independent worlds (1 for b2GpuSolverStep, N for the batch API).  Their arrays are
+// addressed through segments: a body segment per world, a contact / joint segment per (colour slot, world).  Colour
+// slot c holds every world's c-th ACTIVE colour (the stage order only matters inside a world, and inside a world the
+// active colours are visited in ascending order, src/solver.c:1341-1367), the last slot is the overflow colour.
+// Item order for pack/unpack: all bodies world by world, all contacts in segment (= slot) order, all joints.
+static const b2GpuColorDesc& b2gColorSlot( const b2GpuStepDesc& d, int slot, int slotCount )
+{
+	return slot + 1 < slotCount && slot < d.activeColorCount ? d.colors[slot] : d.overflow;
+}
+
+static int b2gFindSegment( const std::vector<int>& starts, int flat )
+{
+	// starts has segmentCount + 1 entries; returns the segment that contains `flat`
+	int lo = 0, hi = (int)starts.size() - 1;
+	while ( hi - lo > 1 )
+	{
+		int mid = ( lo + hi ) >> 1;
+		if ( starts[mid] <= flat )
+		{
+			lo = mid;
+		}
+		else
+		{
+			hi = mid;
+		}
+	}
+	return lo;
+}
+
 // ---- island mode planning (host) --------------------------------------------------------------------------------
-// Pack the awake islands into at most one bin per SM, balanced by body count, and size the island kernel's shared
-// memory carve-up.  Island mode is used when the hint is present and the estimated bins fit; the device double-checks
+// Pack the awake islands of all worlds into bins balanced by body count and size the island kernel's shared memory
+// carve-up.  Island mode is used when every world brings the hint and the estimated bins fit; the device double-checks
 // the exact sizes (binFail -> the grid-barrier kernel takes the step).
 static int b2gPlanIslands( b2GpuSolver* s )
 {
-	const b2GpuStepDesc& d = s->desc;
 	b2g::StepParams& P = s->params;
 	s->islandMode = false;
 	P.binCount = 0;
 	int bodies = P.bodyCount;
-	if ( s->islandsEnabled == 0 || s->mode != 0 || d.bodyIsland == nullptr || d.islandCount <= 0 || bodies == 0 )
+	if ( s->islandsEnabled == 0 || s->mode != 0 || bodies == 0 )
 	{
 		return 0;
 	}
 
-	int islandCount = d.islandCount;
-	s->islandBodies.assign( (size_t)islandCount, 0 );
-	for ( int i = 0; i < bodies; ++i )
+	int islandCount = 0;
+	for ( b2gBodySeg& seg : s->bodySegs )
 	{
-		int island = d.bodyIsland[i];
-		if ( island < 0 || island >= islandCount )
+		if ( seg.islands == nullptr || seg.islandCount <= 0 )
 		{
-			return 0; // a body without an island: no partition guarantee, use the grid-barrier kernel
+			return 0;
 		}
-		s->islandBodies[island] += 1;
+		seg.islandBase = islandCount;
+		islandCount += seg.islandCount;
+	}
+	s->islandBodies.assign( (size_t)islandCount, 0 );
+	for ( const b2gBodySeg& seg : s->bodySegs )
+	{
+		for ( int i = 0; i < seg.count; ++i )
+		{
+			int island = seg.islands[i];
+			if ( island < 0 || island >= seg.islandCount )
+			{
+				return 0; // a body without an island: no partition guarantee, use the grid-barrier kernel
+			}
+			s->islandBodies[seg.islandBase + island] += 1;
+		}
 	}
 
+	// Bins: one per SM when a bin of that size fits a block's shared memory, otherwise as many as it takes (they run in
+	// waves).  Island i goes to the bin its first body falls in when the islands are laid end to end and cut every
+	// `target` bodies, so a bin gets between target - (largest island) and target + (largest island) bodies.
+	size_t budget = s->islandSmemBudget;
+	const double bytesPerBody = 52.0, bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0, bytesPerJoint = b2g::kJointStride + 12.0;
+	double totalBytes = bodies * bytesPerBody + s->contactTotal * bytesPerContact + s->jointTotal * bytesPerJoint;
 	int binLimit = s->smCount < islandCount ? s->smCount : islandCount;
+	int wanted = (int)( totalBytes * 1.6 / (double)budget ) + 1; // 60 % head room for uneven constraint density
+	if ( wanted > binLimit )
+	{
+		binLimit = wanted < islandCount ? wanted : islandCount;
+	}
 	int target = ( bodies + binLimit - 1 ) / binLimit;
 	s->islandBin.assign( (size_t)islandCount, 0 );
-	// island i goes to the bin its first body falls in when the islands are laid end to end and cut every `target`
-	// bodies: every bin gets between target - (largest island) and target + (largest island) bodies
-	s->islandBodies.push_back( 0 ); // scratch: per-bin totals are accumulated below
-	std::vector<int> binBodies( (size_t)binLimit, 0 );
+	std::vector<int>& binBodies = s->binBodies;
+	binBodies.assign( (size_t)binLimit, 0 );
 	int bin = 0, maxBin = 0;
 	long long before = 0;
 	for ( int i = 0; i < islandCount; ++i )
@@ -557,16 +667,11 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	}
 	int binCount = bin + 1;
 
-	// capacities: exact for bodies, proportional estimate with slack for constraints
-	auto roundUp4 = []( double v ) { return ( (int)v + 3 ) & ~3; };
-	int capB = roundUp4( maxBin );
+	// capacities: exact for bodies; the rest of the budget is split between contacts and joints in proportion to
+	// their estimated bytes, so a bin may hold several times its fair share before binFail trips
+	int capB = ( maxBin + 3 ) & ~3;
 	double share = (double)maxBin / (double)bodies;
 	double needC = share * s->contactTotal, needJ = share * s->jointTotal;
-	size_t budget = s->islandSmemBudget;
-	// The proportional need is only an estimate (constraint density differs between islands): hand the whole
-	// shared-memory budget to the bin -- bodies exactly, the rest split between contacts and joints in
-	// proportion to their estimated bytes -- so a bin may hold several times its fair share before binFail trips.
-	const double bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0, bytesPerJoint = b2g::kJointStride + 12.0;
 	size_t fixed = b2g::islandSharedBytes( capB, 0, 0 );
 	if ( fixed + (size_t)( needC * 1.1 * bytesPerContact + needJ * 1.1 * bytesPerJoint ) + 4096 > budget )
 	{
@@ -576,6 +681,13 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	double spare = (double)( budget - fixed ) - 64.0;
 	int capC = ( (int)( spare * weightC / ( weightC + weightJ ) / bytesPerContact ) ) & ~3;
 	int capJ = s->jointTotal > 0 ? ( (int)( spare * weightJ / ( weightC + weightJ ) / bytesPerJoint ) ) & ~3 : 0;
+	if ( binCount > s->smCount )
+	{
+		// many small bins (batches of worlds): do not hog the SM, several blocks should be co-resident
+		int tightC = ( (int)( needC * 2.0 ) + 35 ) & ~3, tightJ = s->jointTotal > 0 ? ( (int)( needJ * 2.0 ) + 11 ) & ~3 : 0;
+		capC = capC < tightC ? capC : tightC;
+		capJ = capJ < tightJ ? capJ : tightJ;
+	}
 	// no point in exceeding what exists
 	capC = capC > ( ( s->contactTotal + 3 ) & ~3 ) ? ( ( s->contactTotal + 3 ) & ~3 ) : capC;
 	capJ = capJ > ( ( s->jointTotal + 3 ) & ~3 ) ? ( ( s->jointTotal + 3 ) & ~3 ) : capJ;
@@ -625,28 +737,47 @@ static int b2gPlanIslands( b2GpuSolver* s )
 }
 
 // ---- phase 1: layout --------------------------------------------------------------------------------------------
-static const b2GpuColorDesc& b2gColorSlot( const b2GpuStepDesc& d, int slot )
+static bool b2gSameStepParams( const b2GpuStepDesc& a, const b2GpuStepDesc& b )
 {
-	return slot < d.activeColorCount ? d.colors[slot] : d.overflow;
+	return a.dt == b.dt && a.inv_dt == b.inv_dt && a.h == b.h && a.inv_h == b.inv_h && a.subStepCount == b.subStepCount &&
+		   memcmp( &a.contactSoftness, &b.contactSoftness, sizeof( a.contactSoftness ) ) == 0 &&
+		   memcmp( &a.staticSoftness, &b.staticSoftness, sizeof( a.staticSoftness ) ) == 0 &&
+		   a.restitutionThreshold == b.restitutionThreshold && a.maxLinearVelocity == b.maxLinearVelocity &&
+		   a.gravity[0] == b.gravity[0] && a.gravity[1] == b.gravity[1] && a.contactSpeed == b.contactSpeed &&
+		   a.contactHertz == b.contactHertz && a.contactDampingRatio == b.contactDampingRatio &&
+		   a.hitEventThreshold == b.hitEventThreshold && a.lengthUnitsPerMeter == b.lengthUnitsPerMeter &&
+		   a.enableWarmStarting == b.enableWarmStarting && a.enableContactSoftening == b.enableContactSoftening;
 }
 
-extern "C" int b2GpuSolverBeginStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuStepResult* r )
+static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount, b2GpuStepResult* results )
 {
-	if ( s == nullptr || d == nullptr )
+	if ( s == nullptr || descs == nullptr || worldCount <= 0 )
 	{
-		return b2gFailMsg( "b2GpuSolverBeginStep: null argument" );
-	}
-	if ( d->activeColorCount < 0 || d->activeColorCount > b2g::kMaxColors || d->awakeBodyCount < 0 || d->subStepCount < 0 )
-	{
-		return b2gFailMsg( "b2GpuSolverBeginStep: bad descriptor" );
+		return b2gFailMsg( "b2GpuSolverBeginStep: bad argument" );
 	}
 	B2G_CUDA( cudaSetDevice( s->device ) );
 	s->tBegin = std::chrono::steady_clock::now();
 	s->begun = false;
 	s->uploaded = false;
 	s->ran = false;
-	s->desc = *d;
-	s->result = r;
+	s->descs.assign( descs, descs + worldCount );
+	s->results = results;
+	const b2GpuStepDesc* d = descs;
+
+	int maxColors = 0;
+	for ( int w = 0; w < worldCount; ++w )
+	{
+		const b2GpuStepDesc& dw = descs[w];
+		if ( dw.activeColorCount < 0 || dw.activeColorCount > b2g::kMaxColors || dw.awakeBodyCount < 0 || dw.subStepCount < 0 )
+		{
+			return b2gFailMsg( "b2GpuSolverBeginStep: bad descriptor" );
+		}
+		if ( w > 0 && !b2gSameStepParams( descs[0], dw ) )
+		{
+			return b2gFailMsg( "b2GpuSolverStepBatch: all worlds of a batch must share the step parameters" );
+		}
+		maxColors = dw.activeColorCount > maxColors ? dw.activeColorCount : maxColors;
+	}
 
 	b2g::StepParams& P = s->params;
 	memset( &P, 0, sizeof( P ) );
@@ -668,58 +799,109 @@ extern "C" int b2GpuSolverBeginStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2G
 	P.lengthUnitsPerMeter = d->lengthUnitsPerMeter;
 	P.enableWarmStarting = d->enableWarmStarting;
 	P.enableSoftening = d->enableContactSoftening;
-	P.bodyCount = d->awakeBodyCount;
-	P.colorCount = d->activeColorCount;
+	P.colorCount = maxColors;
 
-	// slot layout: every colour starts on a multiple of 32, overflow last
-	s->colorSlotCount = d->activeColorCount + 1;
+	// body segments
+	s->bodySegs.clear();
+	s->bodyStart.assign( 1, 0 );
+	int bodies = 0, jointBitWords = 0;
+	for ( int w = 0; w < worldCount; ++w )
+	{
+		const b2GpuStepDesc& dw = descs[w];
+		b2gBodySeg seg;
+		seg.states = static_cast<uint8_t*>( dw.states );
+		seg.sims = static_cast<const uint8_t*>( dw.sims );
+		seg.islands = dw.bodyIsland;
+		seg.islandCount = dw.islandCount;
+		seg.islandBase = 0;
+		seg.count = dw.awakeBodyCount;
+		seg.base = bodies;
+		seg.jointBitBase = jointBitWords * 32;
+		seg.jointWords = 2 * ( ( dw.jointIdCapacity + 63 ) / 64 );
+		s->bodySegs.push_back( seg );
+		bodies += dw.awakeBodyCount;
+		jointBitWords += seg.jointWords;
+		s->bodyStart.push_back( bodies );
+	}
+	P.bodyCount = bodies;
+	P.jointWords = jointBitWords;
+
+	// constraint segments in slot order; every colour slot starts on a multiple of 32 slots, every segment on a multiple
+	// of 4 (the SIMD groups of the reference are per colour array); the gaps are dead slots (pointCount 0)
+	s->contactSegs.clear();
+	s->jointSegs.clear();
+	s->contactStart.assign( 1, 0 );
+	s->jointStart.assign( 1, 0 );
+	int slotCount = maxColors + 1;
 	int slot = 0, joint = 0, flat = 0;
-	for ( int c = 0; c < s->colorSlotCount; ++c )
+	for ( int c = 0; c < slotCount; ++c )
 	{
-		const b2GpuColorDesc& color = b2gColorSlot( *d, c );
-		if ( color.contactCount < 0 || color.jointCount < 0 )
-		{
-			return b2gFailMsg( "b2GpuSolverBeginStep: negative count" );
-		}
-		b2g::ColorRange& range = c < d->activeColorCount ? P.colors[c] : P.overflow;
+		bool isOverflow = c + 1 == slotCount;
+		b2g::ColorRange& range = isOverflow ? P.overflow : P.colors[c];
 		range.contactStart = slot;
-		range.contactCount = color.contactCount;
 		range.jointStart = joint;
-		range.jointCount = color.jointCount;
-		s->flatStart[c] = flat;
-		s->slotStart[c] = slot;
-		slot += b2gRoundUp32( color.contactCount );
-		joint += color.jointCount;
-		flat += color.contactCount;
+		for ( int w = 0; w < worldCount; ++w )
+		{
+			const b2GpuStepDesc& dw = descs[w];
+			if ( !isOverflow && c >= dw.activeColorCount )
+			{
+				continue;
+			}
+			const b2GpuColorDesc& color = isOverflow ? dw.overflow : dw.colors[c];
+			if ( color.contactCount < 0 || color.jointCount < 0 )
+			{
+				return b2gFailMsg( "b2GpuSolverBeginStep: negative count" );
+			}
+			if ( color.contactCount > 0 )
+			{
+				b2gContactSeg seg;
+				seg.sims = static_cast<uint8_t*>( color.contactSims );
+				seg.count = color.contactCount;
+				seg.slotStart = ( slot + 3 ) & ~3;
+				seg.world = w;
+				seg.wide = !isOverflow;
+				seg.colorIndex = color.colorIndex;
+				s->contactSegs.push_back( seg );
+				slot = seg.slotStart + seg.count;
+				flat += seg.count;
+				s->contactStart.push_back( flat );
+			}
+			if ( color.jointCount > 0 )
+			{
+				b2gJointSeg seg;
+				seg.sims = static_cast<uint8_t*>( color.jointSims );
+				seg.count = color.jointCount;
+				seg.jointStart = joint;
+				seg.world = w;
+				s->jointSegs.push_back( seg );
+				joint += seg.count;
+				s->jointStart.push_back( joint );
+			}
+		}
+		range.contactCount = slot - range.contactStart;
+		range.jointCount = joint - range.jointStart;
+		slot = b2gRoundUp32( slot );
 	}
-	s->flatStart[s->colorSlotCount] = flat;
 	s->contactTotal = flat;
-	for ( int c = 0; c < s->colorSlotCount; ++c )
-	{
-		const b2g::ColorRange& range = c < d->activeColorCount ? P.colors[c] : P.overflow;
-		s->jointFlatStart[c] = range.jointStart;
-	}
-	s->jointFlatStart[s->colorSlotCount] = joint;
 	s->jointTotal = joint;
 	P.contactSlots = slot;
 	P.jointCount = joint;
-	P.jointWords = 2 * ( ( d->jointIdCapacity + 63 ) / 64 );
 
-	size_t bodies = (size_t)P.bodyCount;
+	size_t nb = (size_t)bodies;
 	const size_t jointQuads = b2g::kJointStride / 16;
 	// input arena: [states 2/body][packed sims 2/body][bins 1/4 body][contacts 7/slot][joints 16/joint]; item order
 	// (bodies, contacts, joints) is address order, so a prefix of packed items is a prefix of the arena
 	s->inStates = 0;
-	s->inBody = s->inStates + 2 * bodies;
-	s->inBins = s->inBody + 2 * bodies;
-	s->inWire = s->inBins + ( bodies + 3 ) / 4;
+	s->inBody = s->inStates + 2 * nb;
+	s->inBins = s->inBody + 2 * nb;
+	s->inWire = s->inBins + ( nb + 3 ) / 4;
 	s->inJoints = s->inWire + (size_t)b2g::WR_COUNT * slot;
 	s->inTotal = s->inJoints + jointQuads * joint;
 	s->sentQuads = 0;
 	// output arena: [states 2/body][impulse records][joints 16/joint][joint event bits]
 	size_t impulseQuads = ( (size_t)slot * b2g::kImpulseFloats + 3 ) / 4;
 	s->outStates = 0;
-	s->outImpulses = s->outStates + 2 * bodies;
+	s->outImpulses = s->outStates + 2 * nb;
 	s->outJoints = s->outImpulses + impulseQuads;
 	s->outBits = s->outJoints + jointQuads * joint;
 	s->outTotal = s->outBits + ( (size_t)P.jointWords + 3 ) / 4;
@@ -728,10 +910,10 @@ extern "C" int b2GpuSolverBeginStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2G
 	B2G_CUDA( s->hWire.reserve( s->inTotal + 1 ) );
 	B2G_CUDA( s->outAll.reserve( s->outTotal + 1 ) );
 	B2G_CUDA( s->hOut.reserve( s->outTotal + 1 ) );
-	B2G_CUDA( s->vel.reserve( bodies + 1 ) );
-	B2G_CUDA( s->pos.reserve( bodies + 1 ) );
-	B2G_CUDA( s->bodyK.reserve( bodies + 1 ) );
-	B2G_CUDA( s->angDamp.reserve( bodies + 1 ) );
+	B2G_CUDA( s->vel.reserve( nb + 1 ) );
+	B2G_CUDA( s->pos.reserve( nb + 1 ) );
+	B2G_CUDA( s->bodyK.reserve( nb + 1 ) );
+	B2G_CUDA( s->angDamp.reserve( nb + 1 ) );
 	B2G_CUDA( s->cidx.reserve( (size_t)slot + 1 ) );
 	B2G_CUDA( s->cmeta.reserve( (size_t)slot + 1 ) );
 	// the SoA field stride follows cidx's capacity so that all per-slot arrays grow together
@@ -759,6 +941,23 @@ extern "C" int b2GpuSolverBeginStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2G
 	P.barrier = s->control->barrier;
 	P.stageCycles = s->control->stageCycles;
 
+	// dead slots between segments: a zero head (pointCount 0) is all the kernels look at
+	{
+		float4* wire = s->hWire.ptr + s->inWire;
+		size_t segmentCount = s->contactSegs.size();
+		for ( size_t k = 0; k < segmentCount; ++k )
+		{
+			int end = s->contactSegs[k].slotStart + s->contactSegs[k].count;
+			int next = k + 1 < segmentCount ? s->contactSegs[k + 1].slotStart : end;
+			int limit = ( end + 3 ) & ~3;
+			next = next < limit ? next : limit;
+			for ( int dead = end; dead < next; ++dead )
+			{
+				_mm_stream_ps( reinterpret_cast<float*>( wire + (size_t)dead * b2g::WR_COUNT + b2g::WR_HEAD ), _mm_setzero_ps() );
+			}
+		}
+	}
+
 	if ( b2gPlanIslands( s ) != 0 )
 	{
 		return 1;
@@ -768,7 +967,12 @@ extern "C" int b2GpuSolverBeginStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2G
 	return 0;
 }
 
-// pack items: [bodies][contacts, colour order, overflow last][joints, same order]
+extern "C" int b2GpuSolverBeginStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuStepResult* r )
+{
+	return b2gBegin( s, d, 1, r );
+}
+
+// pack items: [bodies][contacts, slot order, overflow last][joints, same order]
 extern "C" int b2GpuSolverGetPackItemCount( const b2GpuSolver* s )
 {
 	return s != nullptr && s->begun ? s->params.bodyCount + s->contactTotal + s->jointTotal : 0;
@@ -802,26 +1006,6 @@ static inline int b2gRdI( const uint8_t* p, int offset )
 	return v;
 }
 
-static inline int b2gColorSlotOfFlat( const b2GpuSolver* s, int flat )
-{
-	int c = 0;
-	while ( s->flatStart[c + 1] <= flat )
-	{
-		c += 1;
-	}
-	return c;
-}
-
-static inline int b2gSlotOfFlat( const int* starts, int flat )
-{
-	int c = 0;
-	while ( starts[c + 1] <= flat )
-	{
-		c += 1;
-	}
-	return c;
-}
-
 // non-temporal 16-byte stores: the staging buffer must not stay dirty in the CPU caches (see b2GpuSolver::hWire)
 static inline void b2gStream4( float4* dst, float a, float b, float c, float d )
 {
@@ -838,30 +1022,36 @@ static inline void b2gStreamCopy( float4* dst, const uint8_t* src, int quads )
 
 extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 {
-	const b2GpuStepDesc& d = s->desc;
 	int bodyCount = s->params.bodyCount;
 	float4* base = s->hWire.ptr;
 
 	// ---- bodies: the state as is + the 32 of b2BodySim's 96 bytes that integrate-velocities reads (src/solver.c:94-102)
 	{
-		const uint8_t* states = static_cast<const uint8_t*>( d.states );
-		const uint8_t* sims = static_cast<const uint8_t*>( d.sims );
 		float4* wireStates = base + s->inStates;
 		float4* wireBody = base + s->inBody;
 		int* wireBins = reinterpret_cast<int*>( base + s->inBins );
+		int i = begin;
 		int bodyEnd = end < bodyCount ? end : bodyCount;
-		for ( int i = begin; i < bodyEnd; ++i )
+		int w = i < bodyEnd ? b2gFindSegment( s->bodyStart, i ) : 0;
+		while ( i < bodyEnd )
 		{
-			if ( s->islandMode )
+			const b2gBodySeg& seg = s->bodySegs[w];
+			int segEnd = seg.base + seg.count < bodyEnd ? seg.base + seg.count : bodyEnd;
+			for ( ; i < segEnd; ++i )
 			{
-				_mm_stream_si32( wireBins + i, s->islandBin[d.bodyIsland[i]] );
+				int local = i - seg.base;
+				if ( s->islandMode )
+				{
+					_mm_stream_si32( wireBins + i, s->islandBin[seg.islandBase + seg.islands[local]] );
+				}
+				b2gStreamCopy( wireStates + 2 * (size_t)i, seg.states + (size_t)local * B2L_STATE_SIZE, 2 );
+				const uint8_t* sim = seg.sims + (size_t)local * B2L_SIM_SIZE;
+				b2gStream4( wireBody + 2 * (size_t)i + 0, b2gRdF( sim, B2L_SIM_INV_MASS ), b2gRdF( sim, B2L_SIM_INV_INERTIA ),
+							b2gRdF( sim, B2L_SIM_FORCE ), b2gRdF( sim, B2L_SIM_FORCE + 4 ) );
+				b2gStream4( wireBody + 2 * (size_t)i + 1, b2gRdF( sim, B2L_SIM_TORQUE ), b2gRdF( sim, B2L_SIM_LINEAR_DAMPING ),
+							b2gRdF( sim, B2L_SIM_ANGULAR_DAMPING ), b2gRdF( sim, B2L_SIM_GRAVITY_SCALE ) );
 			}
-			b2gStreamCopy( wireStates + 2 * (size_t)i, states + (size_t)i * B2L_STATE_SIZE, 2 );
-			const uint8_t* sim = sims + (size_t)i * B2L_SIM_SIZE;
-			b2gStream4( wireBody + 2 * (size_t)i + 0, b2gRdF( sim, B2L_SIM_INV_MASS ), b2gRdF( sim, B2L_SIM_INV_INERTIA ),
-						b2gRdF( sim, B2L_SIM_FORCE ), b2gRdF( sim, B2L_SIM_FORCE + 4 ) );
-			b2gStream4( wireBody + 2 * (size_t)i + 1, b2gRdF( sim, B2L_SIM_TORQUE ), b2gRdF( sim, B2L_SIM_LINEAR_DAMPING ),
-						b2gRdF( sim, B2L_SIM_ANGULAR_DAMPING ), b2gRdF( sim, B2L_SIM_GRAVITY_SCALE ) );
+			w += 1;
 		}
 	}
 
@@ -870,26 +1060,29 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		float4* wire = base + s->inWire;
 		int flat = ( begin > bodyCount ? begin : bodyCount ) - bodyCount;
 		int flatEnd = ( end - bodyCount < s->contactTotal ? end - bodyCount : s->contactTotal );
-		int c = flat < flatEnd ? b2gSlotOfFlat( s->flatStart, flat ) : 0;
+		int k = flat < flatEnd ? b2gFindSegment( s->contactStart, flat ) : 0;
 		while ( flat < flatEnd )
 		{
-			const b2GpuColorDesc& color = b2gColorSlot( d, c );
-			int local = flat - s->flatStart[c];
-			int localEnd = ( flatEnd < s->flatStart[c + 1] ? flatEnd : s->flatStart[c + 1] ) - s->flatStart[c];
-			const uint8_t* sims = static_cast<const uint8_t*>( color.contactSims );
-			int colorIndex = color.colorIndex;
+			const b2gContactSeg& seg = s->contactSegs[k];
+			int segFlat = s->contactStart[k];
+			int local = flat - segFlat;
+			int localEnd = ( flatEnd < s->contactStart[k + 1] ? flatEnd : s->contactStart[k + 1] ) - segFlat;
+			int bodyBase = s->bodySegs[seg.world].base;
 			for ( int i = local; i < localEnd; ++i )
 			{
-				const uint8_t* sim = sims + (size_t)i * B2L_CONTACT_SIZE;
+				const uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
 				const uint8_t* m = sim + B2L_CONTACT_MANIFOLD;
 				const uint8_t* p0 = m + B2L_MANIFOLD_POINTS;
 				const uint8_t* p1 = p0 + B2L_MP_SIZE;
 				int pointCount = b2gRdI( m, B2L_MANIFOLD_POINT_COUNT );
 				int hitEnable = ( (uint32_t)b2gRdI( sim, B2L_CONTACT_SIM_FLAGS ) & B2L_SIM_ENABLE_HIT_EVENT ) != 0 ? b2g::kMetaHitEnable : 0;
-				int meta = ( colorIndex << b2g::kMetaColorShift ) | hitEnable | ( pointCount & b2g::kMetaPointMask );
-				float4* w = wire + (size_t)( s->slotStart[c] + i ) * b2g::WR_COUNT;
-				b2gStream4( w + b2g::WR_HEAD, b2gIntBits( b2gRdI( sim, B2L_CONTACT_INDEX_A ) ), b2gIntBits( b2gRdI( sim, B2L_CONTACT_INDEX_B ) ),
-							b2gIntBits( meta ), b2gRdF( m, B2L_MANIFOLD_ROLLING_IMPULSE ) );
+				int meta = ( seg.colorIndex << b2g::kMetaColorShift ) | hitEnable | ( pointCount & b2g::kMetaPointMask );
+				int indexA = b2gRdI( sim, B2L_CONTACT_INDEX_A ), indexB = b2gRdI( sim, B2L_CONTACT_INDEX_B );
+				indexA = indexA >= 0 ? indexA + bodyBase : indexA;
+				indexB = indexB >= 0 ? indexB + bodyBase : indexB;
+				float4* w = wire + (size_t)( seg.slotStart + i ) * b2g::WR_COUNT;
+				b2gStream4( w + b2g::WR_HEAD, b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta ),
+							b2gRdF( m, B2L_MANIFOLD_ROLLING_IMPULSE ) );
 				b2gStream4( w + b2g::WR_MASS, b2gRdF( sim, B2L_CONTACT_INV_MASS_A ), b2gRdF( sim, B2L_CONTACT_INV_I_A ),
 							b2gRdF( sim, B2L_CONTACT_INV_MASS_B ), b2gRdF( sim, B2L_CONTACT_INV_I_B ) );
 				b2gStream4( w + b2g::WR_NORMAL, b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ),
@@ -903,32 +1096,43 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 				b2gStream4( w + b2g::WR_IMPULSE, b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ),
 							b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ) );
 			}
-			flat = s->flatStart[c + 1];
-			c += 1;
+			flat = s->contactStart[k + 1];
+			k += 1;
 		}
 	}
 
-	// ---- joints: the prepared b2JointSim as is, padded to 256 bytes
+	// ---- joints: the prepared b2JointSim padded to 256 bytes; bodies renumbered to the batch, and the world's base in
+	// the joint-event bit set stored in the padding (read by jointEventTest)
 	{
 		float4* wireJoints = base + s->inJoints;
 		int first = bodyCount + s->contactTotal;
 		int flat = ( begin > first ? begin : first ) - first;
 		int flatEnd = end - first;
-		int c = flat < flatEnd ? b2gSlotOfFlat( s->jointFlatStart, flat ) : 0;
+		int k = flat < flatEnd ? b2gFindSegment( s->jointStart, flat ) : 0;
 		while ( flat < flatEnd )
 		{
-			const b2GpuColorDesc& color = b2gColorSlot( d, c );
-			int local = flat - s->jointFlatStart[c];
-			int localEnd = ( flatEnd < s->jointFlatStart[c + 1] ? flatEnd : s->jointFlatStart[c + 1] ) - s->jointFlatStart[c];
-			const uint8_t* sims = static_cast<const uint8_t*>( color.jointSims );
+			const b2gJointSeg& seg = s->jointSegs[k];
+			int local = flat - s->jointStart[k];
+			int localEnd = ( flatEnd < s->jointStart[k + 1] ? flatEnd : s->jointStart[k + 1] ) - s->jointStart[k];
+			const b2gBodySeg& world = s->bodySegs[seg.world];
 			for ( int i = local; i < localEnd; ++i )
 			{
-				uint8_t padded[b2g::kJointStride] = { 0 };
-				memcpy( padded, sims + (size_t)i * B2L_JOINT_SIZE, B2L_JOINT_SIZE );
-				b2gStreamCopy( wireJoints + (size_t)( s->jointFlatStart[c] + i ) * ( b2g::kJointStride / 16 ), padded, b2g::kJointStride / 16 );
+				alignas( 16 ) uint8_t padded[b2g::kJointStride] = { 0 };
+				memcpy( padded, seg.sims + (size_t)i * B2L_JOINT_SIZE, B2L_JOINT_SIZE );
+				if ( world.base != 0 )
+				{
+					int* pair = b2gJointIndexPair( reinterpret_cast<b2lJointSim*>( padded ) );
+					if ( pair != nullptr )
+					{
+						pair[0] = pair[0] >= 0 ? pair[0] + world.base : pair[0];
+						pair[1] = pair[1] >= 0 ? pair[1] + world.base : pair[1];
+					}
+				}
+				memcpy( padded + B2L_JOINT_SIZE, &world.jointBitBase, 4 );
+				b2gStreamCopy( wireJoints + (size_t)( seg.jointStart + i ) * ( b2g::kJointStride / 16 ), padded, b2g::kJointStride / 16 );
 			}
-			flat = s->jointFlatStart[c + 1];
-			c += 1;
+			flat = s->jointStart[k + 1];
+			k += 1;
 		}
 	}
 	_mm_sfence();
@@ -950,12 +1154,8 @@ static size_t b2gArenaPrefix( const b2GpuSolver* s, int itemEnd )
 	}
 	if ( flat < s->contactTotal )
 	{
-		int c = 0;
-		while ( s->flatStart[c + 1] <= flat )
-		{
-			c += 1;
-		}
-		int slot = s->slotStart[c] + ( flat - s->flatStart[c] );
+		int k = b2gFindSegment( s->contactStart, flat );
+		int slot = s->contactSegs[k].slotStart + ( flat - s->contactStart[k] );
 		return s->inWire + (size_t)slot * b2g::WR_COUNT;
 	}
 	int joints = flat - s->contactTotal;
@@ -1175,13 +1375,10 @@ extern "C" int b2GpuSolverWait( b2GpuSolver* s )
 }
 
 // ---- phase 4: unpack (callable concurrently on disjoint ranges) ---------------------------------------------------------
-// Scatter the packed impulse records into the reference's manifolds: what b2StoreImpulsesTask
-// (src/contact_solver.c:2293-2320) and b2StoreImpulses_Overflow (:526-542) write.
 // Evict a consumed part of the D2H staging buffer from the CPU caches.  On the target hosts a DMA write into lines
 // that are still cached by several cores runs at ~7 GB/s instead of ~54 GB/s (tools/microbench/d2h_bench.cu); flushing
 // right after the unpack pass keeps the next step's download at full speed for ~0.03 ms of host work.
 #if defined( __x86_64__ )
-#include <cpuid.h>
 static bool b2gHasClflushopt()
 {
 	static int cached = -1;
@@ -1227,9 +1424,10 @@ static void b2gFlushLines( const void*, size_t )
 }
 #endif
 
+// Scatter the packed impulse records into the reference's manifolds: what b2StoreImpulsesTask
+// (src/contact_solver.c:2293-2320) and b2StoreImpulses_Overflow (:526-542) write.
 extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 {
-	const b2GpuStepDesc& d = s->desc;
 	if ( begin >= end )
 	{
 		return;
@@ -1239,37 +1437,44 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 
 	// ---- body states
 	{
-		uint8_t* states = static_cast<uint8_t*>( d.states );
 		const float4* outStates = base + s->outStates;
+		int i = begin;
 		int bodyEnd = end < bodyCount ? end : bodyCount;
-		if ( begin < bodyEnd )
+		int w = i < bodyEnd ? b2gFindSegment( s->bodyStart, i ) : 0;
+		while ( i < bodyEnd )
 		{
-			memcpy( states + (size_t)begin * B2L_STATE_SIZE, outStates + 2 * (size_t)begin, (size_t)( bodyEnd - begin ) * B2L_STATE_SIZE );
-			b2gFlushLines( outStates + 2 * (size_t)begin, (size_t)( bodyEnd - begin ) * B2L_STATE_SIZE );
+			const b2gBodySeg& seg = s->bodySegs[w];
+			int segEnd = seg.base + seg.count < bodyEnd ? seg.base + seg.count : bodyEnd;
+			if ( i < segEnd )
+			{
+				memcpy( seg.states + (size_t)( i - seg.base ) * B2L_STATE_SIZE, outStates + 2 * (size_t)i, (size_t)( segEnd - i ) * B2L_STATE_SIZE );
+				b2gFlushLines( outStates + 2 * (size_t)i, (size_t)( segEnd - i ) * B2L_STATE_SIZE );
+				i = segEnd;
+			}
+			w += 1;
 		}
 	}
 
 	// ---- contact impulses
 	{
-		uint64_t* hitBits = s->result != nullptr ? s->result->hitEventBits : nullptr;
 		const float* allRecords = reinterpret_cast<const float*>( base + s->outImpulses );
 		int flat = ( begin > bodyCount ? begin : bodyCount ) - bodyCount;
 		int flatEnd = ( end - bodyCount < s->contactTotal ? end - bodyCount : s->contactTotal );
-		int c = flat < flatEnd ? b2gSlotOfFlat( s->flatStart, flat ) : 0;
+		int k = flat < flatEnd ? b2gFindSegment( s->contactStart, flat ) : 0;
 		while ( flat < flatEnd )
 		{
-			bool wide = c < d.activeColorCount;
-			const b2GpuColorDesc& color = b2gColorSlot( d, c );
-			int local = flat - s->flatStart[c];
-			int localEnd = ( flatEnd < s->flatStart[c + 1] ? flatEnd : s->flatStart[c + 1] ) - s->flatStart[c];
-			uint8_t* sims = static_cast<uint8_t*>( color.contactSims );
-			const float* records = allRecords + (size_t)s->slotStart[c] * b2g::kImpulseFloats;
+			const b2gContactSeg& seg = s->contactSegs[k];
+			b2GpuStepResult* result = s->results != nullptr ? s->results + seg.world : nullptr;
+			uint64_t* hitBits = result != nullptr ? result->hitEventBits : nullptr;
+			int local = flat - s->contactStart[k];
+			int localEnd = ( flatEnd < s->contactStart[k + 1] ? flatEnd : s->contactStart[k + 1] ) - s->contactStart[k];
+			const float* records = allRecords + (size_t)seg.slotStart * b2g::kImpulseFloats;
 			for ( int i = local; i < localEnd; ++i )
 			{
-				uint8_t* sim = sims + (size_t)i * B2L_CONTACT_SIZE;
+				uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
 				uint8_t* manifold = sim + B2L_CONTACT_MANIFOLD;
 				const float* rec = records + (size_t)i * b2g::kImpulseFloats;
-				int pointCount = wide ? 2 : b2gRdI( manifold, B2L_MANIFOLD_POINT_COUNT );
+				int pointCount = seg.wide ? 2 : b2gRdI( manifold, B2L_MANIFOLD_POINT_COUNT );
 				memcpy( manifold + B2L_MANIFOLD_ROLLING_IMPULSE, rec + 0, 4 );
 				for ( int j = 0; j < pointCount; ++j )
 				{
@@ -1277,46 +1482,58 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 					// normalImpulse, tangentImpulse, totalNormalImpulse, normalVelocity are contiguous (collision.h:549-561)
 					memcpy( mp + B2L_MP_NORMAL_IMPULSE, rec + 1 + 4 * j, 16 );
 				}
-				if ( rec[9] != 0.0f && hitBits != nullptr )
+				if ( rec[9] != 0.0f && result != nullptr )
 				{
-					uint32_t id = (uint32_t)b2gRdI( sim, B2L_CONTACT_ID );
-					__atomic_fetch_or( hitBits + ( id >> 6 ), (uint64_t)1 << ( id & 63u ), __ATOMIC_RELAXED );
+					if ( hitBits != nullptr )
+					{
+						uint32_t id = (uint32_t)b2gRdI( sim, B2L_CONTACT_ID );
+						__atomic_fetch_or( hitBits + ( id >> 6 ), (uint64_t)1 << ( id & 63u ), __ATOMIC_RELAXED );
+					}
+					__atomic_store_n( &result->hasHitEvents, 1, __ATOMIC_RELAXED );
 				}
 			}
 			if ( local < localEnd )
 			{
 				b2gFlushLines( records + (size_t)local * b2g::kImpulseFloats, (size_t)( localEnd - local ) * b2g::kImpulseFloats * sizeof( float ) );
 			}
-			flat = s->flatStart[c + 1];
-			c += 1;
+			flat = s->contactStart[k + 1];
+			k += 1;
 		}
 	}
 
-	// ---- joints (accumulated impulses live in the record itself)
+	// ---- joints (accumulated impulses live in the record itself; body indices go back to the world's numbering)
 	{
 		const uint8_t* outJoints = reinterpret_cast<const uint8_t*>( base + s->outJoints );
 		int first = bodyCount + s->contactTotal;
 		int flat = ( begin > first ? begin : first ) - first;
 		int flatEnd = end - first;
-		int c = flat < flatEnd ? b2gSlotOfFlat( s->jointFlatStart, flat ) : 0;
+		int k = flat < flatEnd ? b2gFindSegment( s->jointStart, flat ) : 0;
 		while ( flat < flatEnd )
 		{
-			const b2GpuColorDesc& color = b2gColorSlot( d, c );
-			int local = flat - s->jointFlatStart[c];
-			int localEnd = ( flatEnd < s->jointFlatStart[c + 1] ? flatEnd : s->jointFlatStart[c + 1] ) - s->jointFlatStart[c];
-			uint8_t* sims = static_cast<uint8_t*>( color.jointSims );
+			const b2gJointSeg& seg = s->jointSegs[k];
+			int local = flat - s->jointStart[k];
+			int localEnd = ( flatEnd < s->jointStart[k + 1] ? flatEnd : s->jointStart[k + 1] ) - s->jointStart[k];
+			int bodyBase = s->bodySegs[seg.world].base;
 			for ( int i = local; i < localEnd; ++i )
 			{
-				memcpy( sims + (size_t)i * B2L_JOINT_SIZE, outJoints + (size_t)( s->jointFlatStart[c] + i ) * b2g::kJointStride,
-						B2L_JOINT_SIZE );
+				b2lJointSim* sim = reinterpret_cast<b2lJointSim*>( seg.sims + (size_t)i * B2L_JOINT_SIZE );
+				memcpy( sim, outJoints + (size_t)( seg.jointStart + i ) * b2g::kJointStride, B2L_JOINT_SIZE );
+				if ( bodyBase != 0 )
+				{
+					int* pair = b2gJointIndexPair( sim );
+					if ( pair != nullptr )
+					{
+						pair[0] = pair[0] >= 0 ? pair[0] - bodyBase : pair[0];
+						pair[1] = pair[1] >= 0 ? pair[1] - bodyBase : pair[1];
+					}
+				}
 			}
 			if ( local < localEnd )
 			{
-				b2gFlushLines( outJoints + (size_t)( s->jointFlatStart[c] + local ) * b2g::kJointStride,
-							   (size_t)( localEnd - local ) * b2g::kJointStride );
+				b2gFlushLines( outJoints + (size_t)( seg.jointStart + local ) * b2g::kJointStride, (size_t)( localEnd - local ) * b2g::kJointStride );
 			}
-			flat = s->jointFlatStart[c + 1];
-			c += 1;
+			flat = s->jointStart[k + 1];
+			k += 1;
 		}
 	}
 }
@@ -1337,51 +1554,60 @@ static void b2gFillTimers( b2GpuSolver* s, b2GpuStepResult* r )
 	r->gridBarriers = (int)c->stageCycles[8];
 }
 
-extern "C" int b2GpuSolverEndStep( b2GpuSolver* s, b2GpuStepResult* r )
+static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 {
 	if ( s == nullptr || !s->begun )
 	{
 		return b2gFailMsg( "b2GpuSolverEndStep: no step begun" );
 	}
-	const b2g::StepParams& P = s->params;
 	auto ms = []( std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b ) {
 		return std::chrono::duration<float, std::milli>( b - a ).count();
 	};
-	if ( r != nullptr )
+	if ( results != nullptr )
 	{
-		// uint32 pairs are the little-endian halves of the reference's uint64 blocks (src/bitset.h)
-		if ( r->jointEventBits != nullptr )
-		{
-			const uint32_t* bits = reinterpret_cast<const uint32_t*>( s->hOut.ptr + s->outBits );
-			for ( int i = 0; i < P.jointWords / 2; ++i )
-			{
-				uint64_t word = (uint64_t)bits[2 * i] | ( (uint64_t)bits[2 * i + 1] << 32 );
-				r->jointEventBits[i] |= word;
-			}
-			b2gFlushLines( bits, (size_t)P.jointWords * sizeof( uint32_t ) );
-		}
-		r->hasHitEvents = s->hControl->hasHitEvents;
-		r->kernelMs = s->lastKernelMs;
-		r->kernelLaunches = s->lastLaunches;
-		r->h2dBytes = s->lastH2D;
-		r->d2hBytes = s->lastD2H;
-		b2gFillTimers( s, r );
+		const uint32_t* bits = reinterpret_cast<const uint32_t*>( s->hOut.ptr + s->outBits );
 		auto now = std::chrono::steady_clock::now();
-		r->uploadMs = ms( s->tBegin, s->tSubmit );	 // layout + packing
-		r->waitMs = ms( s->tSubmit, s->tWaited );	 // H2D + kernels + D2H
-		r->scatterMs = ms( s->tWaited, now );		 // unpack + event bits
-		r->h2dMs = 0.0f;
-		cudaEventElapsedTime( &r->h2dMs, s->evUpload, s->evStart );
-		r->totalMs = ms( s->tBegin, now );
+		for ( size_t w = 0; w < s->bodySegs.size(); ++w )
+		{
+			const b2gBodySeg& seg = s->bodySegs[w];
+			b2GpuStepResult* r = results + w;
+			// uint32 pairs are the little-endian halves of the reference's uint64 blocks (src/bitset.h)
+			if ( r->jointEventBits != nullptr )
+			{
+				const uint32_t* mine = bits + seg.jointBitBase / 32;
+				for ( int i = 0; i < seg.jointWords / 2; ++i )
+				{
+					uint64_t word = (uint64_t)mine[2 * i] | ( (uint64_t)mine[2 * i + 1] << 32 );
+					r->jointEventBits[i] |= word;
+				}
+			}
+			r->kernelMs = s->lastKernelMs;
+			r->kernelLaunches = s->lastLaunches;
+			r->h2dBytes = s->lastH2D;
+			r->d2hBytes = s->lastD2H;
+			b2gFillTimers( s, r );
+			r->uploadMs = ms( s->tBegin, s->tSubmit );	 // layout + packing
+			r->waitMs = ms( s->tSubmit, s->tWaited );	 // H2D + kernels + D2H
+			r->scatterMs = ms( s->tWaited, now );		 // unpack + event bits
+			r->h2dMs = 0.0f;
+			cudaEventElapsedTime( &r->h2dMs, s->evUpload, s->evStart );
+			r->totalMs = ms( s->tBegin, now );
+		}
+		b2gFlushLines( bits, (size_t)s->params.jointWords * sizeof( uint32_t ) );
 	}
 	s->begun = false;
 	return 0;
 }
 
-// ---- the whole step, single host thread ----------------------------------------------------------------------------------
-extern "C" int b2GpuSolverStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuStepResult* r )
+extern "C" int b2GpuSolverEndStep( b2GpuSolver* s, b2GpuStepResult* r )
 {
-	if ( b2GpuSolverBeginStep( s, d, r ) != 0 )
+	return b2gEnd( s, r );
+}
+
+// ---- the whole step, single host thread ----------------------------------------------------------------------------------
+static int b2gStepAll( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount, b2GpuStepResult* results )
+{
+	if ( b2gBegin( s, descs, worldCount, results ) != 0 )
 	{
 		return 1;
 	}
@@ -1391,13 +1617,18 @@ extern "C" int b2GpuSolverStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuSte
 		return 1;
 	}
 	b2GpuSolverUnpackRange( s, 0, b2GpuSolverGetUnpackItemCount( s ) );
-	return b2GpuSolverEndStep( s, r );
+	return b2gEnd( s, results );
+}
+
+extern "C" int b2GpuSolverStep( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuStepResult* r )
+{
+	return b2gStepAll( s, d, 1, r );
 }
 
 // ---- split for benchmarks: Upload (pack + H2D), Run (kernels only, repeatable), Download (D2H + unpack) -------------------
-extern "C" int b2GpuSolverUpload( b2GpuSolver* s, const b2GpuStepDesc* d )
+static int b2gUploadAll( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount )
 {
-	if ( b2GpuSolverBeginStep( s, d, nullptr ) != 0 )
+	if ( b2gBegin( s, descs, worldCount, nullptr ) != 0 )
 	{
 		return 1;
 	}
@@ -1409,6 +1640,11 @@ extern "C" int b2GpuSolverUpload( b2GpuSolver* s, const b2GpuStepDesc* d )
 	}
 	B2G_CUDA( cudaStreamSynchronize( s->stream ) );
 	return 0;
+}
+
+extern "C" int b2GpuSolverUpload( b2GpuSolver* s, const b2GpuStepDesc* d )
+{
+	return b2gUploadAll( s, d, 1 );
 }
 
 extern "C" int b2GpuSolverRun( b2GpuSolver* s, b2GpuStepResult* r )
@@ -1434,24 +1670,49 @@ extern "C" int b2GpuSolverRun( b2GpuSolver* s, b2GpuStepResult* r )
 	return 0;
 }
 
-extern "C" int b2GpuSolverDownload( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuStepResult* r )
+static int b2gDownloadAll( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount, b2GpuStepResult* results )
 {
-	if ( s == nullptr || d == nullptr )
+	if ( s == nullptr || descs == nullptr )
 	{
 		return b2gFailMsg( "b2GpuSolverDownload: null argument" );
 	}
-	if ( !s->ran || !s->begun )
+	if ( !s->ran || !s->begun || (int)s->bodySegs.size() != worldCount )
 	{
-		return b2gFailMsg( "b2GpuSolverDownload: nothing has run" );
+		return b2gFailMsg( "b2GpuSolverDownload: nothing has run for these worlds" );
 	}
-	s->desc = *d;
-	s->result = r;
+	s->results = results;
 	if ( b2gEnqueueDownload( s ) != 0 || b2GpuSolverWait( s ) != 0 )
 	{
 		return 1;
 	}
 	b2GpuSolverUnpackRange( s, 0, b2GpuSolverGetUnpackItemCount( s ) );
-	return b2GpuSolverEndStep( s, r );
+	return b2gEnd( s, results );
+}
+
+extern "C" int b2GpuSolverDownload( b2GpuSolver* s, const b2GpuStepDesc* d, b2GpuStepResult* r )
+{
+	return b2gDownloadAll( s, d, 1, r );
+}
+
+// ---- batch of independent worlds -------------------------------------------------------------------------------------------
+extern "C" int b2GpuSolverStepBatch( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount, b2GpuStepResult* results )
+{
+	return b2gStepAll( s, descs, worldCount, results );
+}
+
+extern "C" int b2GpuSolverUploadBatch( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount )
+{
+	return b2gUploadAll( s, descs, worldCount );
+}
+
+extern "C" int b2GpuSolverRunBatch( b2GpuSolver* s, b2GpuStepResult* r )
+{
+	return b2GpuSolverRun( s, r );
+}
+
+extern "C" int b2GpuSolverDownloadBatch( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount, b2GpuStepResult* results )
+{
+	return b2gDownloadAll( s, descs, worldCount, results );
 }
 
 // =================================================================================================================

@@ -230,16 +230,35 @@ B2G_DEV b2lJointSim* jointAt( const SolveView& V, int index )
 }
 
 // ---- one stage of the grid-barrier path (view = global memory, wire slot == constraint slot) -----------------------
-B2G_DEV void prepareContactGlobal( const StepParams& P, int slot, bool active, bool wide, unsigned lane )
+B2G_DEV void prepareContactGlobal( const StepParams& P, int slot, bool inRange, bool wide, unsigned lane )
 {
+	float4 head = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+	if ( inRange )
+	{
+		head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+	}
+	// dead slots (padding between the segments of a batch) have pointCount 0
+	bool active = inRange && ( __float_as_int( head.z ) & kMetaPointMask ) != 0;
 	int groupBits = wide ? simdGroupBits( P, slot, active, lane ) : 0;
 	if ( active )
 	{
-		float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
 		int indexA = __float_as_int( head.x );
 		int indexB = __float_as_int( head.y );
 		prepareContact( P, P.g, slot, slot, indexA + 1, indexB + 1, wireVelocity( P, indexA ), wireVelocity( P, indexB ), wide,
 						groupBits );
+	}
+	else if ( inRange )
+	{
+		// an all-zero constraint on the static dummy is a no-op in every stage, like the zeroed tail lanes of the
+		// reference's last wide constraint (src/solver.c:1419-1425)
+		const float4 zero = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+#pragma unroll
+		for ( int f = 0; f < CF_COUNT; ++f )
+		{
+			storeField( P.g, f, slot, zero );
+		}
+		P.g.cidx[slot] = make_int2( 0, 0 );
+		P.g.cmeta[slot] = 0;
 	}
 }
 

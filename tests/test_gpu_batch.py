@@ -1,0 +1,56 @@
+"""Batch of independent worlds through b2GpuSolverStepBatch: every world of the batch must come out bit-identical to
+what the reference's CPU solver produced for that world alone (the captures), whatever the mix of scenes, joint types,
+overflow constraints and world sizes in the batch."""
+import ctypes
+
+import numpy as np
+import pytest
+
+import box2d_b200 as b2
+from test_gpu_capture import _check
+
+pytestmark = pytest.mark.gpu
+
+# captures that share the default step parameters (a batch must: the stage parameters are launch constants)
+NAMES = ["small_pyramid_000", "falling_hinges_120", "joint_zoo_045", "overflow_025", "small_pyramid_030", "joint_zoo_000",
+		 "falling_hinges_020", "overflow_001"]
+
+
+def _captures(repeat=1):
+	caps = [b2.Capture(b2.ROOT / "tests" / "golden" / f"{name}.b2cap.gz") for name in NAMES]
+	return caps * repeat
+
+
+@pytest.mark.parametrize("islands", [True, False])
+def test_batch_matches_each_world(islands):
+	caps = _captures(repeat=3)
+	descs, results, bufs = b2.make_batch(caps, islands=islands)
+	with b2.GpuSolver() as solver:
+		solver.step_batch(descs, results)
+	for cap, buf, res in zip(caps, bufs, results):
+		_check(cap, buf, res)
+	if islands:
+		assert results[0].gridBarriers == 0, "the island kernel should have solved the batch"
+
+
+def test_batch_split_phase_and_many_worlds():
+	caps = [b2.Capture(b2.ROOT / "tests" / "golden" / "small_pyramid_030.b2cap.gz")] * 700
+	descs, results, bufs = b2.make_batch(caps)
+	with b2.GpuSolver() as solver:
+		solver.upload_batch(descs)
+		r = b2.StepResult()
+		solver.run_batch(r)
+		solver.run_batch(r)
+		solver.download_batch(descs, results)
+		assert r.gridBarriers == 0
+	for i in (0, 1, 349, 698, 699):
+		_check(caps[i], bufs[i], results[i])
+
+
+def test_batch_rejects_mixed_step_parameters():
+	caps = [b2.Capture(b2.ROOT / "tests" / "golden" / "small_pyramid_030.b2cap.gz"),
+			b2.Capture(b2.ROOT / "tests" / "golden" / "pyramid_cold_003.b2cap.gz")]  # warm starting off
+	descs, results, bufs = b2.make_batch(caps)
+	with b2.GpuSolver() as solver:
+		with pytest.raises(RuntimeError):
+			solver.step_batch(descs, results)
