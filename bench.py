@@ -4,22 +4,23 @@
     python bench.py --gpus N --steps K --warmup W            # this repo's B200 solver
     python bench.py --impl reference --steps K --warmup W    # the reference's own CPU solver on the host cores
 
-Workload (config.workload): BASELINE.json configs[1], the reference's `many_pyramids` benchmark scene
+Workload (config.workload), default: BASELINE.json configs[1], the reference's `many_pyramids` benchmark scene
 (shared/benchmarks.c:157-195: 22 000 boxes, ~58 000 touching contacts, dt = 1/60, 4 sub-steps), created with the
 reference's own scene builder inside the host library.  At N > 1 every rank steps its own copy of the world on its
-own GPU (independent worlds, no data-path collective, weak scaling); NCCL is used only to reduce the result.
+own GPU (independent worlds, no data-path collective, weak scaling); NCCL only reduces the result.
+`--workload batch` is BASELINE.json configs[4]: 8192 independent base-10 pyramid worlds solved by
+b2GpuSolverStepBatch, sharded over the ranks (strong scaling).
 
 A "step" is one pass of the hot path (everything b2SolverTask runs, reference src/solver.c:1560-1616) over one
 world step's constraints.
   value       body-steps/s with the step's inputs already resident in HBM: K x b2GpuSolverRun on one captured world
               step, device time from CUDA events on the solver's stream, L2 flushed between iterations.
   e2e         the same metric through the reference-facing call: K real b2World_Step calls of the GPU host library,
-              summing b2Profile.constraints (host wall clock of the seam: host joint prepare, H2D of the reference's
-              own arrays from pinned memory, the step kernel, D2H of states / impulses / joints / event bits).
-  roofline    the step kernel (the only kernel of the step) against the measured HBM peak, algorithmic bytes per
-              SURVEY.md section 8d / DESIGN.md.
+              summing b2Profile.constraints (host wall clock of the seam: joint prepare, island labels, wire packing,
+              H2D, the kernels, D2H, impulse write-back).
+  roofline    the step's kernels against the measured HBM peak, algorithmic bytes per SURVEY.md section 8d / DESIGN.md.
   cpu_baseline  the untouched reference (oracle/_ref, gcc -O3 build of /root/reference) on the box's host cores over a
-              bounded sample of the same workload: sum of b2Profile.constraints.
+              bounded sample of the same workload: sum of b2Profile.constraints, best worker count.
 """
 from __future__ import annotations
 
@@ -31,17 +32,21 @@ import subprocess
 import sys
 import threading
 import time
+from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
+
+import numpy as np
 
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
 import box2d_b200 as b2  # noqa: E402
 
-SCENE_STEPS = {"many_pyramids": 200, "large_pyramid": 500, "joint_grid": 500, "rain": 1000, "tumbler": 750,
-			   "small_pyramid": 200}
+SCENES = ("many_pyramids", "large_pyramid", "joint_grid", "rain", "tumbler", "small_pyramid")
+SLEEPING_SCENES = ("rain", "tumbler")  # the awake set changes at the end of a step: no re-run of a captured step
 METRIC = "solver_body_steps_per_sec"
 UNIT = "body-steps/s"
+BATCH_WORLDS = 8192
 
 
 def algorithmic_bytes(bodies: int, contacts: int, joints: int, substeps: int) -> int:
@@ -57,6 +62,26 @@ def measured_peaks() -> tuple[float, str]:
 		except Exception:
 			pass
 	return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def shard_range(total: int, rank: int, world_size: int) -> tuple[int, int]:
+	"""Contiguous block of units for a rank: independent worlds shard with no exchange."""
+	base, extra = divmod(total, world_size)
+	begin = rank * base + min(rank, extra)
+	return begin, begin + base + (1 if rank < extra else 0)
+
+
+def reduce_over_ranks(seconds: list[float], work: float, device=None):
+	"""max over ranks of every timing, sum of the work: the only collective of the benchmark (result reduction)."""
+	import torch
+	import torch.distributed as dist
+
+	t = torch.tensor(seconds, dtype=torch.float64, device=device)
+	w = torch.tensor([work], dtype=torch.float64, device=device)
+	if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+		dist.all_reduce(t, op=dist.ReduceOp.MAX)
+		dist.all_reduce(w, op=dist.ReduceOp.SUM)
+	return [float(x) for x in t], float(w[0])
 
 
 class ClockSampler:
@@ -107,6 +132,7 @@ class ClockSampler:
 				"reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ---- the reference's CPU solver (oracle/_ref) -------------------------------------------------------------------
 def load_reference():
 	path = ROOT / "oracle" / "_ref" / "libbox2d_ref.so"
 	if not path.is_file():
@@ -141,22 +167,60 @@ def best_cpu_baseline(scene: str, warmup: int, steps: int) -> dict:
 	return best
 
 
+def cpu_batch_baseline(worlds: int, warmup: int, steps: int) -> dict:
+	"""The batch on the host: independent worlds stepped concurrently by a thread pool, one worker each (worlds are
+	independent, include/box2d/box2d.h:31-32).  A bounded sample of 96 worlds; the solver time per world-step is
+	sum(b2Profile.constraints) / threads, i.e. the solver-only share of a perfectly parallel host loop."""
+	lib = load_reference()
+	threads = min(os.cpu_count() or 1, 32)
+	sample = 96
+	ws = [b2.World(lib, "small_pyramid", 1) for _ in range(sample)]
+	for w in ws:
+		w.step(warmup)
+	bodies = ws[0].counters()["awakeBodyCount"]
+
+	def run(group):
+		return sum(w.bench(steps)["constraints_ms"] for w in group)
+
+	groups = [ws[i::threads] for i in range(threads)]
+	t0 = time.perf_counter()
+	with ThreadPoolExecutor(max_workers=threads) as pool:
+		constraints_ms = sum(pool.map(run, groups))
+	wall = time.perf_counter() - t0
+	for w in ws:
+		w.destroy()
+	solver_s = constraints_ms * 1e-3 / threads
+	return {"value": sample * steps * bodies / solver_s, "unit": UNIT, "cores": threads, "kind": "reference",
+			"us_per_world_step": constraints_ms * 1e3 / (sample * steps),
+			"sample": f"{sample} of the {worlds} base-10 pyramid worlds x {steps} steps, one worker per world, {threads} host "
+					  f"threads; sum of b2Profile.constraints / threads (whole loop wall {wall * 1e3:.1f} ms)"}
+
+
 def run_reference_arm(args) -> int:
 	"""--impl reference: the reference's own CPU implementation of the path, all host threads it can use."""
 	rank = int(os.environ.get("RANK", "0"))
 	if rank != 0:
 		return 0
-	best = best_cpu_baseline(args.scene, args.warmup, args.steps)
+	if args.workload == "batch":
+		b = cpu_batch_baseline(BATCH_WORLDS, args.warmup, args.steps)
+		line = {"impl": "reference", "metric": METRIC, "value": b["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+				"warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+				"dtype": "f32", "data": "synthetic", "config": {"workload": f"batch of {BATCH_WORLDS} small_pyramid worlds"},
+				"cpu_baseline": b, "e2e": {"value": b["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+				"gpu_launches": 0}
+		print(json.dumps(line))
+		return 0
+	best = best_cpu_baseline(args.workload, args.warmup, args.steps)
 	ms = best["constraints_ms"] / args.steps
 	value = best["bodies"] * args.steps / (best["constraints_ms"] * 1e-3)
 	line = {
 		"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
 		"warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
 		"dtype": "f32", "data": "synthetic",
-		"config": {"workload": args.scene, "bodies": best["bodies"], "contacts": best["contacts"], "joints": best["joints"],
+		"config": {"workload": args.workload, "bodies": best["bodies"], "contacts": best["contacts"], "joints": best["joints"],
 				   "substeps": 4, "dt": 1.0 / 60.0, "timed": "sum of b2Profile.constraints (reference src/solver.c:1561,1615)"},
 		"cpu_baseline": {"value": value, "unit": UNIT, "cores": best["workers"], "kind": "reference",
-						 "sample": f"{args.steps} steps of {args.scene} after {args.warmup} warm-up steps; best of worker counts "
+						 "sample": f"{args.steps} steps of {args.workload} after {args.warmup} warm-up steps; best of worker counts "
 								   f"{sorted(best['tried_ms_per_step'])} on {best['host_cores']} host cores",
 						 "ms_per_step_by_workers": best["tried_ms_per_step"]},
 		"e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -166,21 +230,29 @@ def run_reference_arm(args) -> int:
 	return 0
 
 
-def run_gpu_arm(args) -> int:
+# ---- the B200 arm ----------------------------------------------------------------------------------------------------
+def _setup_distributed():
 	import torch
 	import torch.distributed as dist
 
 	world_size = int(os.environ.get("WORLD_SIZE", "1"))
 	rank = int(os.environ.get("RANK", "0"))
 	local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-	distributed = world_size > 1
 	if not torch.cuda.is_available():
 		raise RuntimeError("bench.py needs a CUDA device: the solver has no CPU fallback")
 	torch.cuda.set_device(local_rank)
 	os.environ["B2GPU_DEVICE"] = str(local_rank)
-	if distributed:
+	if world_size > 1:
 		dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+	return world_size, rank, local_rank
 
+
+def run_scene(args) -> int:
+	import torch
+	import torch.distributed as dist
+
+	world_size, rank, local_rank = _setup_distributed()
+	distributed = world_size > 1
 	host = b2.host_lib()
 	host.b2GpuSeam_InstallPinnedAllocator()
 	flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -193,7 +265,8 @@ def run_gpu_arm(args) -> int:
 
 	sampler = ClockSampler(local_rank)
 	workers = min(os.cpu_count() or 1, 16)  # host phases of the GPU arm (collide, pack/unpack, finalize)
-	with b2.World(host, args.scene, workers) as world:
+	scene = args.workload
+	with b2.World(host, scene, workers) as world:
 		world.step(args.warmup)
 		widx = world.world_index()
 		counters = world.counters()
@@ -202,92 +275,226 @@ def run_gpu_arm(args) -> int:
 		contacts = sum(counters["colorCounts"]) - joints
 
 		# ---- e2e: K real b2World_Step calls, host buffers, copies inside the timed region ----
+		totals = b2.SeamTotals()
+		host.b2GpuSeam_GetTotals(widx, ctypes.byref(totals), 1)
 		sync_all()
 		sampler.start()
 		t0 = time.perf_counter()
 		e2e = world.bench(args.steps)
 		e2e_wall = time.perf_counter() - t0
+		host.b2GpuSeam_GetTotals(widx, ctypes.byref(totals), 1)
 		last = host.b2GpuSeam_GetLastResult(widx).contents
-		h2d, d2h = int(last.h2dBytes), int(last.d2hBytes)
-		e2e_launches = int(last.kernelLaunches) * args.steps
-		grid_barriers = int(last.gridBarriers)
-		e2e_kernel_ms_last = float(last.kernelMs)
-		e2e_split = {"upload_enqueue_ms": float(last.uploadMs), "h2d_ms": float(last.h2dMs), "wait_ms": float(last.waitMs),
-					 "scatter_ms": float(last.scatterMs), "abi_total_ms": float(last.totalMs)}
+		e2e_split = {"pack_ms": float(last.uploadMs), "h2d_kernels_d2h_ms": float(last.waitMs), "unpack_ms": float(last.scatterMs),
+					 "abi_total_ms": float(last.totalMs), "kernel_ms": float(last.kernelMs)}
+		e2e_launches = int(totals.launches)
+		h2d = totals.h2dBytes / max(1, totals.steps)
+		d2h = totals.d2hBytes / max(1, totals.steps)
+		e2e_kernel_s = totals.kernelMs * 1e-3
+		stage_ms = [totals.stageMs[i] / max(1, totals.steps) for i in range(8)]
+		grid_barriers = totals.gridBarriers / max(1, totals.steps)
+		launches_per_step = totals.launches / max(1, totals.steps)
 
 		# ---- value: the captured step resident in HBM, K x Run, CUDA events, L2 flushed in between ----
-		desc = host.b2GpuSeam_GetLastDesc(widx).contents
-		substeps = int(desc.subStepCount)
-		with b2.GpuSolver(device=local_rank) as solver:
-			# The desc still points at the world's arrays.  After b2World_Step returned they hold what the NEXT
-			# step would start from (finalize reset the state deltas, src/solver.c:611-612; manifolds carry the stored
+		resident = scene not in SLEEPING_SCENES
+		kernel_s = e2e_kernel_s
+		launches = 0
+		substeps = 4
+		if resident:
+			# The desc still points at the world's arrays.  After b2World_Step returned they hold what the NEXT step
+			# would start from (finalize reset the state deltas, src/solver.c:611-612; manifolds carry the stored
 			# impulses), i.e. a valid, representative solver input with the same constraint graph.
-			solver.upload(desc)
-			result = b2.StepResult()
-			for _ in range(max(3, args.warmup)):
-				solver.run(result)
-			sync_all()
-			kernel_ms = []
-			stage_ms = [0.0] * 8
-			for _ in range(args.steps):
-				flush.zero_()
-				torch.cuda.synchronize()
-				solver.run(result)
-				kernel_ms.append(float(result.kernelMs))
-				for i in range(8):
-					stage_ms[i] += float(result.stageMs[i])
-			launches = int(result.kernelLaunches) * args.steps
+			desc = host.b2GpuSeam_GetLastDesc(widx).contents
+			substeps = int(desc.subStepCount)
+			with b2.GpuSolver(device=local_rank) as solver:
+				solver.upload(desc)
+				result = b2.StepResult()
+				for _ in range(max(3, args.warmup)):
+					solver.run(result)
+				sync_all()
+				kernel_ms = []
+				stage_ms = [0.0] * 8
+				for _ in range(args.steps):
+					flush.zero_()
+					torch.cuda.synchronize()
+					solver.run(result)
+					kernel_ms.append(float(result.kernelMs))
+					for i in range(8):
+						stage_ms[i] += float(result.stageMs[i]) / args.steps
+				launches = int(result.kernelLaunches) * args.steps
+				launches_per_step = int(result.kernelLaunches)
+				grid_barriers = int(result.gridBarriers)
+			kernel_s = sum(kernel_ms) * 1e-3
 		sync_all()
 		clocks = sampler.stop()
 
-	total_kernel_s = sum(kernel_ms) * 1e-3
-	times = torch.tensor([total_kernel_s, e2e["constraints_ms"] * 1e-3], dtype=torch.float64, device="cuda")
-	work = torch.tensor([float(bodies * args.steps)], dtype=torch.float64, device="cuda")
-	if distributed:
-		dist.all_reduce(times, op=dist.ReduceOp.MAX)  # max over ranks
-		dist.all_reduce(work, op=dist.ReduceOp.SUM)   # result reduction only: no data-path collective
-	total_kernel_s, e2e_s = float(times[0]), float(times[1])
-	total_work = float(work[0])
+	(kernel_s, e2e_s), total_work = reduce_over_ranks([kernel_s, e2e["constraints_ms"] * 1e-3], float(bodies * args.steps), "cuda")
 
 	if rank == 0:
-		ms_per_step = total_kernel_s * 1e3 / args.steps
+		ms_per_step = kernel_s * 1e3 / args.steps
 		peak, peak_source = measured_peaks()
 		alg = algorithmic_bytes(bodies, contacts, joints, substeps)
 		achieved = alg / (ms_per_step * 1e-3) / 1e9
 		cpu = None
 		if args.cpu_baseline and not distributed:
 			sample_steps = min(args.steps, 60)
-			b = best_cpu_baseline(args.scene, args.warmup, sample_steps)
+			b = best_cpu_baseline(scene, args.warmup, sample_steps)
 			cpu = {"value": b["bodies"] * sample_steps / (b["constraints_ms"] * 1e-3), "unit": UNIT, "cores": b["workers"],
 				   "kind": "reference", "ms_per_step": b["constraints_ms"] / sample_steps,
-				   "sample": f"{sample_steps} steps of {args.scene} after {args.warmup} warm-up steps, sum of "
+				   "sample": f"{sample_steps} steps of {scene} after {args.warmup} warm-up steps, sum of "
 							 f"b2Profile.constraints; best of worker counts {sorted(b['tried_ms_per_step'])} on "
 							 f"{b['host_cores']} host cores (oracle/_ref = untouched reference, gcc -O3 SSE2)",
 				   "ms_per_step_by_workers": b["tried_ms_per_step"]}
 		line = {
-			"metric": METRIC, "value": total_work / total_kernel_s, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
+			"metric": METRIC, "value": total_work / kernel_s, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
 			"warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
 			"vs_baseline": None, "dtype": "f32", "data": "synthetic",
-			"config": {"workload": args.scene, "bodies": bodies, "contacts": contacts, "joints": joints, "substeps": substeps,
+			"config": {"workload": scene, "bodies": bodies, "contacts": contacts, "joints": joints, "substeps": substeps,
 					   "dt": 1.0 / 60.0, "colors": sum(1 for c in counters["colorCounts"][:23] if c > 0),
 					   "parallelism": f"{world_size} independent world(s), one per GPU",
-					   "l2": "flushed (256 MiB write) between timed iterations",
-					   "timed": "CUDA events on the solver stream around the step kernel, inputs resident"},
+					   "l2": "flushed (256 MiB write) between timed iterations" if resident else
+							 "not flushed: kernels timed inside the real steps (awake set changes every step)",
+					   "timed": "CUDA events on the solver stream around the step's kernels, inputs resident"},
 			"e2e": {"value": total_work / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3 / args.steps,
-					"h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+					"h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
 					"timed": "sum of b2Profile.constraints over K b2World_Step calls of libbox2d_b200.so",
 					"whole_step_ms": e2e["step_ms"] / args.steps, "wall_ms_per_step": e2e_wall * 1e3 / args.steps,
-					"kernel_ms_last_step": e2e_kernel_ms_last, "last_step_split": e2e_split},
+					"kernel_ms_per_step": e2e_kernel_s * 1e3 / args.steps, "last_step_split": e2e_split},
 			"gpu_launches": launches + e2e_launches,
 			"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
 						 "traffic": None, "algorithmic_bytes_per_launch": alg, "peak_source": peak_source,
-						 "grid_barriers_per_launch": grid_barriers,
-						 "note": "latency/barrier bound: see DESIGN.md (barrier floor) and profiles/"},
-			"stage_ms_per_step": {n: stage_ms[i] / args.steps for i, n in enumerate(b2.STAGE_NAMES)},
+						 "kernels_per_step": launches_per_step, "grid_barriers_per_step": grid_barriers,
+						 "note": "all kernels of the step (partition + island kernel, or the grid-barrier kernel); see DESIGN.md"},
+			"stage_ms_per_step": {n: stage_ms[i] for i, n in enumerate(b2.STAGE_NAMES)},
 			"clocks": clocks,
 		}
 		if cpu is not None:
 			line["cpu_baseline"] = cpu
+		print(json.dumps(line))
+	if distributed:
+		dist.destroy_process_group()
+	return 0
+
+
+def build_batch(host, worlds: int, warmup: int):
+	"""`worlds` independent copies of one settled base-10 pyramid world: every world gets its own host arrays."""
+	with b2.World(host, "small_pyramid", 1) as w:
+		w.step(warmup)
+		desc = host.b2GpuSeam_GetLastDesc(w.world_index()).contents
+		n = desc.awakeBodyCount
+
+		def grab(ptr, nbytes):
+			if nbytes == 0:
+				return np.zeros(0, np.uint8)
+			return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(nbytes,)).copy()
+
+		states = grab(desc.states, n * b2.STATE_SIZE)
+		sims = grab(desc.sims, n * b2.SIM_SIZE)
+		labels = np.ctypeslib.as_array(ctypes.cast(desc.bodyIsland, ctypes.POINTER(ctypes.c_int)), shape=(n,)).copy()
+		colors = [(grab(desc.colors[c].contactSims, desc.colors[c].contactCount * b2.CONTACT_SIZE), desc.colors[c].contactCount)
+				  for c in range(desc.activeColorCount)]
+		template = b2.StepDesc.from_buffer_copy(bytes(desc))
+		contacts = sum(cnt for _, cnt in colors)
+
+	descs = (b2.StepDesc * worlds)()
+	results = (b2.StepResult * worlds)()
+	keep = []
+	for i in range(worlds):
+		d = b2.StepDesc.from_buffer_copy(bytes(template))
+		st, sm, lb = states.copy(), sims.copy(), labels.copy()
+		cs = [a.copy() for a, _ in colors]
+		d.states, d.sims, d.bodyIsland = st.ctypes.data, sm.ctypes.data, lb.ctypes.data
+		for c, arr in enumerate(cs):
+			d.colors[c].contactSims = arr.ctypes.data
+		ctypes.memmove(ctypes.byref(descs[i]), ctypes.byref(d), ctypes.sizeof(b2.StepDesc))
+		keep.append((st, sm, lb, cs))
+	pristine = (states, [a for a, _ in colors])
+	return descs, results, keep, pristine, n, contacts, int(template.subStepCount)
+
+
+def run_batch(args) -> int:
+	import torch
+	import torch.distributed as dist
+
+	world_size, rank, local_rank = _setup_distributed()
+	distributed = world_size > 1
+	host = b2.host_lib()
+	begin, end = shard_range(BATCH_WORLDS, rank, world_size)
+	worlds = end - begin
+	descs, results, keep, pristine, bodies, contacts, substeps = build_batch(host, worlds, max(args.warmup, 30))
+	flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+	def sync_all():
+		torch.cuda.synchronize()
+		if distributed:
+			dist.barrier()
+		torch.cuda.synchronize()
+
+	def restore():
+		for st, _, _, cs in keep:
+			st[:] = pristine[0]
+			for a, p in zip(cs, pristine[1]):
+				a[:] = p
+
+	sampler = ClockSampler(local_rank)
+	with b2.GpuSolver(device=local_rank) as solver:
+		# value: inputs resident, K x RunBatch
+		solver.upload_batch(descs)
+		r = b2.StepResult()
+		for _ in range(3):
+			solver.run_batch(r)
+		sync_all()
+		sampler.start()
+		kernel_ms = []
+		for _ in range(args.steps):
+			flush.zero_()
+			torch.cuda.synchronize()
+			solver.run_batch(r)
+			kernel_ms.append(float(r.kernelMs))
+		launches = int(r.kernelLaunches) * args.steps
+		grid_barriers = int(r.gridBarriers)
+		# e2e: the whole b2GpuSolverStepBatch from host arrays (single host thread packs/unpacks), inputs restored untimed
+		e2e_steps = max(3, min(args.steps, 10))
+		e2e_s = 0.0
+		for _ in range(e2e_steps):
+			restore()
+			sync_all()
+			t0 = time.perf_counter()
+			solver.step_batch(descs, results)
+			e2e_s += time.perf_counter() - t0
+		h2d, d2h = int(results[0].h2dBytes), int(results[0].d2hBytes)
+		split = {"pack_ms": float(results[0].uploadMs), "h2d_kernels_d2h_ms": float(results[0].waitMs),
+				 "unpack_ms": float(results[0].scatterMs)}
+		launches += int(results[0].kernelLaunches) * e2e_steps
+	sync_all()
+	clocks = sampler.stop()
+
+	kernel_s = sum(kernel_ms) * 1e-3
+	(kernel_s, e2e_per_step), total_work = reduce_over_ranks([kernel_s, e2e_s / e2e_steps], float(worlds * bodies * args.steps), "cuda")
+	total_worlds = BATCH_WORLDS
+	if rank == 0:
+		ms_per_step = kernel_s * 1e3 / args.steps
+		peak, peak_source = measured_peaks()
+		alg = algorithmic_bytes(bodies, contacts, 0, substeps) * worlds
+		achieved = alg / (ms_per_step * 1e-3) / 1e9
+		line = {
+			"metric": METRIC, "value": total_work / kernel_s, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
+			"warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+			"vs_baseline": None, "dtype": "f32", "data": "synthetic",
+			"config": {"workload": f"batch of {total_worlds} small_pyramid worlds", "worlds": total_worlds, "worlds_per_gpu": worlds,
+					   "bodies_per_world": bodies, "contacts_per_world": contacts, "substeps": substeps,
+					   "world_steps_per_sec": total_worlds * args.steps / kernel_s,
+					   "parallelism": f"worlds sharded over {world_size} GPU(s), no exchange",
+					   "l2": "flushed (256 MiB write) between timed iterations"},
+			"e2e": {"value": total_worlds * bodies / e2e_per_step, "unit": UNIT, "ms_per_step": e2e_per_step * 1e3,
+					"h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "last_step_split": split,
+					"timed": "b2GpuSolverStepBatch wall clock (single host thread packs and unpacks)"},
+			"gpu_launches": launches,
+			"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+						 "algorithmic_bytes_per_launch": alg, "peak_source": peak_source, "grid_barriers_per_step": grid_barriers},
+			"clocks": clocks,
+		}
+		if args.cpu_baseline and not distributed:
+			line["cpu_baseline"] = cpu_batch_baseline(total_worlds, 30, min(args.steps, 40))
 		print(json.dumps(line))
 	if distributed:
 		dist.destroy_process_group()
@@ -300,13 +507,15 @@ def main() -> int:
 	ap.add_argument("--steps", type=int, default=100)
 	ap.add_argument("--warmup", type=int, default=20)
 	ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-	ap.add_argument("--scene", default="many_pyramids", choices=sorted(SCENE_STEPS))
+	ap.add_argument("--workload", "--scene", dest="workload", default="many_pyramids", choices=SCENES + ("batch",))
 	ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
 	args = ap.parse_args()
 	args.warmup = max(3, args.warmup)
 	if args.impl == "reference":
 		return run_reference_arm(args)
-	return run_gpu_arm(args)
+	if args.workload == "batch":
+		return run_batch(args)
+	return run_scene(args)
 
 
 if __name__ == "__main__":

@@ -85,6 +85,14 @@ class StepResult(ctypes.Structure):
 	]
 
 
+class SeamTotals(ctypes.Structure):
+	_fields_ = [
+		("kernelMs", ctypes.c_double), ("abiMs", ctypes.c_double), ("h2dBytes", ctypes.c_double), ("d2hBytes", ctypes.c_double),
+		("stageMs", ctypes.c_double * 8),
+		("steps", ctypes.c_longlong), ("launches", ctypes.c_longlong), ("gridBarriers", ctypes.c_longlong),
+	]
+
+
 class NativeLibraryMissing(RuntimeError):
 	pass
 
@@ -198,6 +206,8 @@ def host_lib() -> ctypes.CDLL:
 	lib.b2GpuSeam_GetLastResult.argtypes = [ctypes.c_int]
 	lib.b2GpuSeam_GetLastDesc.restype = ctypes.POINTER(StepDesc)
 	lib.b2GpuSeam_GetLastDesc.argtypes = [ctypes.c_int]
+	lib.b2GpuSeam_GetTotals.restype = None
+	lib.b2GpuSeam_GetTotals.argtypes = [ctypes.c_int, ctypes.POINTER(SeamTotals), ctypes.c_int]
 	lib.b2GpuSeam_InstallPinnedAllocator.restype = None
 	lib.b2GpuSeam_Shutdown.restype = None
 	_host_lib = lib

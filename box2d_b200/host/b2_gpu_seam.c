@@ -29,6 +29,7 @@ typedef struct b2SeamSlot
 	b2GpuSolver* solver;
 	int* islandLabels;
 	int islandLabelCapacity;
+	b2GpuSeamTotals totals;
 	b2GpuStepResult lastResult;
 	b2GpuStepDesc lastDesc;
 } b2SeamSlot;
@@ -97,6 +98,18 @@ void b2GpuSeam_Shutdown( void )
 const b2GpuStepResult* b2GpuSeam_GetLastResult( int worldIndex )
 {
 	return 0 <= worldIndex && worldIndex < B2_MAX_WORLDS ? &s_slots[worldIndex].lastResult : NULL;
+}
+
+void b2GpuSeam_GetTotals( int worldIndex, b2GpuSeamTotals* totals, int reset )
+{
+	if ( 0 <= worldIndex && worldIndex < B2_MAX_WORLDS )
+	{
+		*totals = s_slots[worldIndex].totals;
+		if ( reset )
+		{
+			memset( &s_slots[worldIndex].totals, 0, sizeof( b2GpuSeamTotals ) );
+		}
+	}
 }
 
 const b2GpuStepDesc* b2GpuSeam_GetLastDesc( int worldIndex )
@@ -197,6 +210,18 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 	if ( b2GpuSolverEndStep( slot->solver, result ) != 0 )
 	{
 		b2SeamFatal( "b2GpuSolverEndStep failed" );
+	}
+
+	slot->totals.steps += 1;
+	slot->totals.kernelMs += result->kernelMs;
+	slot->totals.abiMs += result->totalMs;
+	slot->totals.h2dBytes += (double)result->h2dBytes;
+	slot->totals.d2hBytes += (double)result->d2hBytes;
+	slot->totals.launches += result->kernelLaunches;
+	slot->totals.gridBarriers += result->gridBarriers;
+	for ( int i = 0; i < b2GpuStage_count; ++i )
+	{
+		slot->totals.stageMs[i] += result->stageMs[i];
 	}
 
 	// The event consumers at src/solver.c:1648-1820 read worker 0's sets after OR-ing the others in.

@@ -41,6 +41,17 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* stepContext );
  * Call before creating any world. */
 void b2GpuSeam_InstallPinnedAllocator( void );
 
+/* Sums over the steps of a world slot since the last reset (for benchmarks). */
+typedef struct b2GpuSeamTotals
+{
+	double kernelMs; /* CUDA-event time of the step's kernels */
+	double abiMs;	 /* host wall time of the phased C-ABI calls */
+	double h2dBytes, d2hBytes;
+	double stageMs[b2GpuStage_count];
+	long long steps, launches, gridBarriers;
+} b2GpuSeamTotals;
+void b2GpuSeam_GetTotals( int worldIndex, b2GpuSeamTotals* totals, int reset );
+
 /* Last step's device-side result for a world id slot (for benchmarks / tests). */
 const b2GpuStepResult* b2GpuSeam_GetLastResult( int worldIndex );
 const b2GpuStepDesc* b2GpuSeam_GetLastDesc( int worldIndex );
