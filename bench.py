@@ -173,7 +173,7 @@ def cpu_batch_baseline(worlds: int, warmup: int, steps: int) -> dict:
 	sum(b2Profile.constraints) / threads, i.e. the solver-only share of a perfectly parallel host loop."""
 	lib = load_reference()
 	threads = min(os.cpu_count() or 1, 32)
-	sample = 96
+	sample = 96  # B2_MAX_WORLDS is 128 (include/box2d/constants.h:38-40)
 	ws = [b2.World(lib, "small_pyramid", 1) for _ in range(sample)]
 	for w in ws:
 		w.step(warmup)
@@ -452,7 +452,7 @@ def run_batch(args) -> int:
 			kernel_ms.append(float(r.kernelMs))
 		launches = int(r.kernelLaunches) * args.steps
 		grid_barriers = int(r.gridBarriers)
-		# e2e: the whole b2GpuSolverStepBatch from host arrays (single host thread packs/unpacks), inputs restored untimed
+		# e2e: the whole b2GpuSolverStepBatch from host arrays, inputs restored untimed
 		e2e_steps = max(3, min(args.steps, 10))
 		e2e_s = 0.0
 		for _ in range(e2e_steps):
@@ -487,7 +487,7 @@ def run_batch(args) -> int:
 					   "l2": "flushed (256 MiB write) between timed iterations"},
 			"e2e": {"value": total_worlds * bodies / e2e_per_step, "unit": UNIT, "ms_per_step": e2e_per_step * 1e3,
 					"h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "last_step_split": split,
-					"timed": "b2GpuSolverStepBatch wall clock (single host thread packs and unpacks)"},
+					"timed": "b2GpuSolverStepBatch wall clock: host packing (library threads) + H2D + kernels + D2H + write-back"},
 			"gpu_launches": launches,
 			"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
 						 "algorithmic_bytes_per_launch": alg, "peak_source": peak_source, "grid_barriers_per_step": grid_barriers},

@@ -24,6 +24,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace b2g
@@ -1605,18 +1606,49 @@ extern "C" int b2GpuSolverEndStep( b2GpuSolver* s, b2GpuStepResult* r )
 }
 
 // ---- the whole step, single host thread ----------------------------------------------------------------------------------
+// The two host passes of the one-call entry points.  A world stepped through the seam uses the world's own workers
+// (b2ParallelFor); a caller of b2GpuSolverStep / StepBatch has no task system to offer, so large steps are split over
+// a few short-lived threads here (B2GPU_HOST_THREADS overrides the count, 1 = calling thread only).
+static void b2gParallelRanges( b2GpuSolver* s, int itemCount, void ( *fn )( b2GpuSolver*, int, int ) )
+{
+	static const int configured = []() {
+		const char* env = getenv( "B2GPU_HOST_THREADS" );
+		int n = env != nullptr ? atoi( env ) : (int)std::thread::hardware_concurrency();
+		return n < 1 ? 1 : ( n > 32 ? 32 : n );
+	}();
+	int threads = itemCount / 16384;
+	threads = threads > configured ? configured : threads;
+	if ( threads <= 1 )
+	{
+		fn( s, 0, itemCount );
+		return;
+	}
+	std::vector<std::thread> pool;
+	pool.reserve( (size_t)threads );
+	for ( int t = 0; t < threads; ++t )
+	{
+		int begin = (int)( (long long)itemCount * t / threads );
+		int end = (int)( (long long)itemCount * ( t + 1 ) / threads );
+		pool.emplace_back( fn, s, begin, end );
+	}
+	for ( std::thread& th : pool )
+	{
+		th.join();
+	}
+}
+
 static int b2gStepAll( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount, b2GpuStepResult* results )
 {
 	if ( b2gBegin( s, descs, worldCount, results ) != 0 )
 	{
 		return 1;
 	}
-	b2GpuSolverPackRange( s, 0, b2GpuSolverGetPackItemCount( s ) );
+	b2gParallelRanges( s, b2GpuSolverGetPackItemCount( s ), b2GpuSolverPackRange );
 	if ( b2GpuSolverSubmit( s ) != 0 || b2GpuSolverWait( s ) != 0 )
 	{
 		return 1;
 	}
-	b2GpuSolverUnpackRange( s, 0, b2GpuSolverGetUnpackItemCount( s ) );
+	b2gParallelRanges( s, b2GpuSolverGetUnpackItemCount( s ), b2GpuSolverUnpackRange );
 	return b2gEnd( s, results );
 }
 

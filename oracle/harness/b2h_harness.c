@@ -26,7 +26,7 @@
 #include <string.h>
 
 #define B2H_API __attribute__( ( visibility( "default" ) ) )
-#define B2H_MAX_WORLDS 64
+#define B2H_MAX_WORLDS 120
 
 typedef struct b2hWorld
 {
