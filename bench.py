@@ -292,6 +292,7 @@ def run_scene(args) -> int:
 		e2e_kernel_s = totals.kernelMs * 1e-3
 		stage_ms = [totals.stageMs[i] / max(1, totals.steps) for i in range(8)]
 		grid_barriers = totals.gridBarriers / max(1, totals.steps)
+		island_plan = None
 		launches_per_step = totals.launches / max(1, totals.steps)
 
 		# ---- value: the captured step resident in HBM, K x Run, CUDA events, L2 flushed in between ----
@@ -323,6 +324,7 @@ def run_scene(args) -> int:
 				launches = int(result.kernelLaunches) * args.steps
 				launches_per_step = int(result.kernelLaunches)
 				grid_barriers = int(result.gridBarriers)
+				island_plan = list(solver.island_plan())
 			kernel_s = sum(kernel_ms) * 1e-3
 		sync_all()
 		clocks = sampler.stop()
@@ -363,6 +365,7 @@ def run_scene(args) -> int:
 			"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
 						 "traffic": None, "algorithmic_bytes_per_launch": alg, "peak_source": peak_source,
 						 "kernels_per_step": launches_per_step, "grid_barriers_per_step": grid_barriers,
+						 "island_bins_blocks_per_bin": island_plan,
 						 "note": "all kernels of the step (partition + island kernel, or the grid-barrier kernel); see DESIGN.md"},
 			"stage_ms_per_step": {n: stage_ms[i] for i, n in enumerate(b2.STAGE_NAMES)},
 			"clocks": clocks,

@@ -162,6 +162,8 @@ def solver_lib() -> ctypes.CDLL:
 	lib.b2GpuGetVersion.restype = ctypes.c_int
 	lib.b2GpuSolverGetLaunchCount.restype = ctypes.c_uint64
 	lib.b2GpuSolverGetLaunchCount.argtypes = [ctypes.c_void_p]
+	lib.b2GpuSolverGetIslandPlan.restype = ctypes.c_int
+	lib.b2GpuSolverGetIslandPlan.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
 	_solver_lib = lib
 	return lib
 
@@ -450,6 +452,12 @@ class GpuSolver:
 
 	def launch_count(self) -> int:
 		return int(self.lib.b2GpuSolverGetLaunchCount(self.handle))
+
+	def island_plan(self) -> tuple[int, int]:
+		"""(bins, thread blocks per bin) of the last step; (0, 0) when it was planned for the grid-barrier kernel."""
+		bins, blocks = ctypes.c_int(0), ctypes.c_int(0)
+		self.lib.b2GpuSolverGetIslandPlan(self.handle, ctypes.byref(bins), ctypes.byref(blocks))
+		return bins.value, blocks.value
 
 	def close(self) -> None:
 		if self.handle:

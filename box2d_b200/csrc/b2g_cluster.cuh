@@ -1,0 +1,406 @@
+// b2g_cluster.cuh -- island-local execution for islands that outgrow one thread block: a thread-block CLUSTER per bin.
+//
+// One big island (a 5000-body pyramid, the contents of a tumbler) cannot be split: every colour of it has to be
+// finished before the next starts.  The grid-barrier kernel pays ~2 us per colour for that (1.2 us barrier + the L2
+// round trips of the stage body).  Here up to 16 thread blocks of one cluster share the bin instead:
+//   * the bin's bodies are dealt out in runs of 2^clusterShift, a block keeps its run in shared memory and the other
+//     blocks of the cluster read / write it through distributed shared memory (SolveView::clusterShift),
+//   * every colour of the bin is dealt out evenly over the blocks, a block keeps its share of the constraints in its
+//     own shared memory for the whole step,
+//   * colours are separated by the hardware cluster barrier (~0.25 us measured, tools/microbench/barrier_bench.cu).
+// The partition kernel is the same as for single-block bins (b2g_island.cuh), its lists are simply read in slices.
+// The bin's overflow colour (sequential, array order) is solved by one thread of the cluster's first block.
+#pragma once
+
+#include "b2g_island.cuh"
+
+namespace b2g
+{
+
+namespace cg = cooperative_groups;
+
+// colour of local constraint k given the exclusive local offsets (localStart has slotCount + 1 entries)
+B2G_DEV int colorOfLocal( const int* localStart, int slotCount, int k )
+{
+	int c = 0;
+	while ( c + 1 < slotCount && localStart[c + 1] <= k )
+	{
+		c += 1;
+	}
+	return c;
+}
+
+__global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( const __grid_constant__ StepParams P )
+{
+	if ( __ldcg( P.binFail ) != 0 )
+	{
+		return; // some bin does not fit (uniform for the whole grid): the grid-barrier kernel solves this step
+	}
+
+	extern __shared__ __align__( 16 ) uint8_t smem[];
+	// per colour slot (active colours, then the overflow bucket): first element of this block's share in the bin's
+	// list, local slot of its first constraint (+ total at the end) and the bin-wide count (uniform for the cluster)
+	__shared__ int listBeginC[kColorSlots], localStartC[kColorSlots + 1], binCountC[kColorSlots];
+	__shared__ int listBeginJ[kColorSlots], localStartJ[kColorSlots + 1], binCountJ[kColorSlots];
+	__shared__ int anyRestitution;
+	__shared__ int clusterRestitution;
+	// bytes of body writes this block receives in a pass over colour c (16 per dynamic body of mine that a contact of
+	// the colour touches), counted by the writers during prepare
+	__shared__ int expectBytes[kColorSlots];
+	__shared__ __align__( 8 ) unsigned long long arrivalBar;
+	__shared__ int overflowOrder[kMaxBinOverflow];
+
+	cg::cluster_group cluster = cg::this_cluster();
+	const int share = P.clusterSize;
+	const int rank = (int)cluster.block_rank();
+	const int bin = (int)blockIdx.x / share;
+	const int capB = P.capBodies, capC = P.capContacts, capJ = P.capJoints;
+	const int colorCount = P.colorCount;
+	const int slotCount = colorCount + 1; // + the overflow bucket
+
+	// carve-up: identical to the single-block island kernel, with per-block capacities
+	SolveView V;
+	uint8_t* cursor = smem;
+	V.vel = reinterpret_cast<float4*>( cursor );
+	cursor += (size_t)( capB + 1 ) * sizeof( float4 );
+	V.pos = reinterpret_cast<float4*>( cursor );
+	cursor += (size_t)( capB + 1 ) * sizeof( float4 );
+	V.bodyK = reinterpret_cast<float4*>( cursor );
+	cursor += (size_t)capB * sizeof( float4 );
+	V.cf = reinterpret_cast<float4*>( cursor );
+	cursor += (size_t)CF_COUNT * capC * sizeof( float4 );
+	V.cfStride = capC;
+	V.joints = cursor;
+	cursor += (size_t)capJ * kJointStride;
+	V.cidx = reinterpret_cast<int2*>( cursor );
+	cursor += (size_t)capC * sizeof( int2 );
+	int2* jointGlobal = reinterpret_cast<int2*>( cursor );
+	int* jointIndexOf = reinterpret_cast<int*>( jointGlobal + capJ );
+	cursor += (size_t)capJ * ( sizeof( int2 ) + sizeof( int ) );
+	V.angDamp = reinterpret_cast<float*>( cursor );
+	cursor += (size_t)capB * sizeof( float );
+	V.cmeta = reinterpret_cast<int*>( cursor );
+	cursor += (size_t)capC * sizeof( int );
+	int* wireSlot = reinterpret_cast<int*>( cursor );
+	V.anyRestitution = &anyRestitution;
+	V.clusterShift = P.clusterShift;
+	V.clusterMask = ( 1 << P.clusterShift ) - 1;
+	V.asyncBar = 0;
+	SolveView VA = V; // same view, body writes as counted st.async stores
+	const unsigned barAddr = (unsigned)__cvta_generic_to_shared( &arrivalBar );
+	VA.asyncBar = barAddr;
+	unsigned barPhase = 0;
+
+	// this block's run of the bin's bodies
+	const int binBodies = P.binBodyCount[bin];
+	const int bodyBegin = min( binBodies, rank << P.clusterShift );
+	const int bodyCount = min( binBodies - bodyBegin, 1 << P.clusterShift );
+	const int* bodyList = P.binBodyList + (size_t)bin * P.binCapBodies + bodyBegin;
+	const int* contactList = P.binContactList + (size_t)bin * P.binCapContacts;
+	const int* jointList = P.binJointList + (size_t)bin * P.binCapJoints;
+
+	StageClock clk;
+	clk.start();
+	long long begin = clk.last;
+
+	if ( threadIdx.x == 0 )
+	{
+		const int* startC = P.binColorStart + (size_t)bin * kColorSlots;
+		const int* startJ = P.binJointStart + (size_t)bin * kColorSlots;
+		int localC = 0, localJ = 0;
+		for ( int c = 0; c < slotCount; ++c )
+		{
+			bool isOverflow = c == colorCount;
+			int s0 = startC[c], n = startC[c + 1] - s0;
+			int lo = isOverflow ? s0 : s0 + n * rank / share;
+			int hi = isOverflow ? ( rank == 0 ? s0 + n : s0 ) : s0 + n * ( rank + 1 ) / share;
+			listBeginC[c] = lo;
+			localStartC[c] = localC;
+			binCountC[c] = n;
+			localC += hi - lo;
+
+			s0 = startJ[c], n = startJ[c + 1] - s0;
+			lo = isOverflow ? s0 : s0 + n * rank / share;
+			hi = isOverflow ? ( rank == 0 ? s0 + n : s0 ) : s0 + n * ( rank + 1 ) / share;
+			listBeginJ[c] = lo;
+			localStartJ[c] = localJ;
+			binCountJ[c] = n;
+			localJ += hi - lo;
+		}
+		localStartC[slotCount] = localC;
+		localStartJ[slotCount] = localJ;
+		V.vel[0] = make_float4( 0.0f, 0.0f, 0.0f, __uint_as_float( 0u ) );
+		V.pos[0] = make_float4( 0.0f, 0.0f, 1.0f, 0.0f );
+		anyRestitution = 0;
+		asm volatile( "mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"( barAddr ) : "memory" );
+		asm volatile( "fence.mbarrier_init.release.cluster;" ::: "memory" );
+	}
+	if ( threadIdx.x < kColorSlots )
+	{
+		expectBytes[threadIdx.x] = 0;
+	}
+	forEachLocal( bodyCount, [&]( int i ) { loadBody( P, V, bodyList[i], i + 1 ); } );
+	cluster.sync(); // every block of the cluster is running and its bodies are in place
+
+	const int contactCount = localStartC[slotCount];
+	const int jointCount = localStartJ[slotCount];
+	// the bin's overflow colour lives in the first block; whether it exists is uniform for the cluster
+	const bool hasOverflow = binCountC[colorCount] + binCountJ[colorCount] > 0;
+	const int ovCb = localStartC[colorCount], ovCe = localStartC[slotCount];
+	const int ovJb = localStartJ[colorCount], ovJe = localStartJ[slotCount];
+
+	// overflow constraints in ARRAY order (src/solver.c:1100-1101): rank-sort this bucket of the bin's list
+	auto sortOverflow = [&]( const int* list, int first, int count ) {
+		for ( int k = (int)threadIdx.x; k < count; k += (int)blockDim.x )
+		{
+			int mine = list[first + k], order = 0;
+			for ( int m = 0; m < count; ++m )
+			{
+				order += list[first + m] < mine ? 1 : 0;
+			}
+			overflowOrder[order] = mine;
+		}
+	};
+	sortOverflow( contactList, listBeginC[colorCount], ovCe - ovCb );
+	__syncthreads();
+
+	forEachLocal( contactCount, [&]( int k ) {
+		int c = colorOfLocal( localStartC, slotCount, k );
+		bool wide = c < colorCount;
+		int offset = k - localStartC[c];
+		int slot = wide ? contactList[listBeginC[c] + offset] : overflowOrder[offset];
+		float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+		int indexA = __float_as_int( head.x );
+		int indexB = __float_as_int( head.y );
+		int localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;
+		int localB = indexB >= 0 ? P.bodyLocal[indexB] : 0;
+		wireSlot[k] = slot;
+		float4 sA = gatherVel( V, localA ), sB = gatherVel( V, localB );
+		if ( wide )
+		{
+			// tell the owners of the two bodies what to expect from this contact in every pass over its colour
+			if ( ( __float_as_uint( sA.w ) & B2L_FLAG_DYNAMIC ) != 0 )
+			{
+				atomicAdd( cluster.map_shared_rank( expectBytes, ( (unsigned)localA - 1u ) >> P.clusterShift ) + c, (int)sizeof( float4 ) );
+			}
+			if ( ( __float_as_uint( sB.w ) & B2L_FLAG_DYNAMIC ) != 0 )
+			{
+				atomicAdd( cluster.map_shared_rank( expectBytes, ( (unsigned)localB - 1u ) >> P.clusterShift ) + c, (int)sizeof( float4 ) );
+			}
+		}
+		prepareContact( P, V, slot, k, localA, localB, sA, sB, wide, wide ? P.slotGroupBits[slot] : 0 );
+	} );
+	__syncthreads();
+	sortOverflow( jointList, listBeginJ[colorCount], ovJe - ovJb );
+	__syncthreads();
+	forEachLocal( jointCount, [&]( int k ) {
+		int c = colorOfLocal( localStartJ, slotCount, k );
+		int offset = k - localStartJ[c];
+		jointIndexOf[k] = c < colorCount ? jointList[listBeginJ[c] + offset] : overflowOrder[offset];
+	} );
+	__syncthreads();
+	{
+		const int quads = kJointStride / 16;
+		for ( int t = (int)threadIdx.x; t < jointCount * quads; t += (int)blockDim.x )
+		{
+			int k = t / quads, q = t - k * quads;
+			const float4* src = reinterpret_cast<const float4*>( P.rawJoints + (size_t)jointIndexOf[k] * kJointStride );
+			reinterpret_cast<float4*>( V.joints + (size_t)k * kJointStride )[q] = src[q];
+		}
+	}
+	__syncthreads();
+	forEachLocal( jointCount, [&]( int k ) {
+		int* pair = jointIndexPair( jointAt( V, k ) );
+		if ( pair != nullptr )
+		{
+			int a = pair[0], b = pair[1];
+			jointGlobal[k] = make_int2( a, b );
+			pair[0] = a >= 0 ? P.bodyLocal[a] - 1 : -1;
+			pair[1] = b >= 0 ? P.bodyLocal[b] - 1 : -1;
+		}
+	} );
+	cluster.sync();
+	// restitution is applied by the whole cluster or not at all
+	if ( threadIdx.x == 0 )
+	{
+		int any = 0;
+		for ( int r = 0; r < share; ++r )
+		{
+			any |= *cluster.map_shared_rank( &anyRestitution, (unsigned)r );
+		}
+		clusterRestitution = any;
+	}
+	__syncthreads();
+	clk.lap( b2GpuStage_prepareConstraints );
+
+	auto overflowPass = [&]( auto joint, auto contact ) {
+		if ( hasOverflow )
+		{
+			if ( rank == 0 && threadIdx.x == 0 )
+			{
+				for ( int k = ovJb; k < ovJe; ++k )
+				{
+					joint( k );
+				}
+				for ( int k = ovCb; k < ovCe; ++k )
+				{
+					contact( k );
+				}
+			}
+			cluster.sync();
+		}
+	};
+	// A pass over the colours.  Colours with joints end in a full cluster barrier (release / acquire: every writer fences
+	// its remote stores at GPU scope, MEMBAR.ALL.GPU, which costs more than the colour itself).  Colours with contacts
+	// only -- the common case -- use counted stores instead: the owner of a body waits until the bytes announced for
+	// the colour have landed in its shared memory (mbarrier transaction count) and only then joins a barrier that
+	// carries no fence.
+	auto colorPass = [&]( auto joint, auto contact ) {
+		for ( int c = 0; c < colorCount; ++c )
+		{
+			if ( binCountJ[c] == 0 && binCountC[c] == 0 )
+			{
+				continue; // colour not present in this bin (uniform for the cluster)
+			}
+			if ( binCountJ[c] != 0 )
+			{
+				forEachInLocalColor(
+					localStartJ[c], localStartJ[c + 1], localStartC[c], localStartC[c + 1], joint, [&]( int k ) { contact( V, k ); } );
+				cluster.sync();
+				continue;
+			}
+			if ( threadIdx.x == 0 )
+			{
+				int bytes = expectBytes[c];
+				if ( bytes > 0 )
+				{
+					asm volatile( "mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"( barAddr ), "r"( bytes ) : "memory" );
+				}
+				else
+				{
+					asm volatile( "mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"( barAddr ) : "memory" );
+				}
+			}
+			for ( int k = localStartC[c] + (int)threadIdx.x; k < localStartC[c + 1]; k += (int)blockDim.x )
+			{
+				contact( VA, k );
+			}
+			unsigned done = 0;
+			for ( int spin = 0; done == 0; ++spin )
+			{
+				asm volatile( "{\n"
+							  ".reg .pred p;\n"
+							  "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+							  "selp.u32 %0, 1, 0, p;\n"
+							  "}\n"
+							  : "=r"( done )
+							  : "r"( barAddr ), "r"( barPhase )
+							  : "memory" );
+				if ( spin > ( 1 << 22 ) )
+				{
+					__trap(); // the announced bytes never arrived: a bug, fail loudly instead of hanging the GPU
+				}
+			}
+			barPhase ^= 1u;
+			__syncwarp();
+			asm volatile( "barrier.cluster.arrive.relaxed.aligned;\nbarrier.cluster.wait.aligned;" ::: "memory" );
+		}
+	};
+
+	for ( int subStep = 0; subStep < P.subStepCount; ++subStep )
+	{
+		forEachLocal( bodyCount, [&]( int i ) { integrateVelocities( V, i ); } );
+		cluster.sync();
+		clk.lap( b2GpuStage_integrateVelocities );
+
+		overflowPass( [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); }, [&]( int k ) { warmStartContactOverflow( V, k ); } );
+		colorPass( [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); }, [&]( const SolveView& view, int k ) { warmStartContact( view, k ); } );
+		clk.lap( b2GpuStage_warmStart );
+
+		overflowPass( [&]( int k ) { solveJoint( P, V, jointAt( V, k ), true ); },
+					  [&]( int k ) { solveContactOverflow( P, V, k, true ); } );
+		colorPass(
+			[&]( int k ) {
+				b2lJointSim* joint = jointAt( V, k );
+				solveJoint( P, V, joint, true );
+				jointEventTest( P, joint );
+			},
+			[&]( const SolveView& view, int k ) { solveContact( P, view, k, true ); } );
+		clk.lap( b2GpuStage_solveImpulses );
+
+		forEachLocal( bodyCount, [&]( int i ) { integratePositions( P, V, i ); } );
+		cluster.sync();
+		clk.lap( b2GpuStage_integratePositions );
+
+		overflowPass( [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+					  [&]( int k ) { solveContactOverflow( P, V, k, false ); } );
+		colorPass( [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+				   [&]( const SolveView& view, int k ) { solveContact( P, view, k, false ); } );
+		clk.lap( b2GpuStage_relaxImpulses );
+	}
+
+	if ( clusterRestitution != 0 )
+	{
+		if ( binCountC[colorCount] > 0 )
+		{
+			if ( rank == 0 && threadIdx.x == 0 )
+			{
+				for ( int k = ovCb; k < ovCe; ++k )
+				{
+					restitutionContactOverflow( P, V, k );
+				}
+			}
+			cluster.sync();
+		}
+		for ( int c = 0; c < colorCount; ++c )
+		{
+			if ( binCountC[c] == 0 )
+			{
+				continue;
+			}
+			for ( int k = localStartC[c] + (int)threadIdx.x; k < localStartC[c + 1]; k += (int)blockDim.x )
+			{
+				restitutionContact( P, V, k );
+			}
+			cluster.sync();
+		}
+	}
+	clk.lap( b2GpuStage_applyRestitution );
+
+	// store: everything a block needs is in its own shared memory again
+	forEachLocal( contactCount, [&]( int k ) { storeContact( P, V, k, wireSlot[k], k < ovCb || k >= ovCe ); } );
+	forEachLocal( bodyCount, [&]( int i ) { storeBody( P, V, bodyList[i], i + 1 ); } );
+	forEachLocal( jointCount, [&]( int k ) {
+		int* pair = jointIndexPair( jointAt( V, k ) );
+		if ( pair != nullptr )
+		{
+			pair[0] = jointGlobal[k].x;
+			pair[1] = jointGlobal[k].y;
+		}
+	} );
+	__syncthreads();
+	{
+		const int quads = kJointStride / 16;
+		for ( int t = (int)threadIdx.x; t < jointCount * quads; t += (int)blockDim.x )
+		{
+			int k = t / quads, q = t - k * quads;
+			float4* dst = reinterpret_cast<float4*>( P.g.joints + (size_t)jointIndexOf[k] * kJointStride );
+			dst[q] = reinterpret_cast<const float4*>( V.joints + (size_t)k * kJointStride )[q];
+		}
+	}
+	clk.lap( b2GpuStage_storeImpulses );
+
+	if ( clk.lead )
+	{
+#pragma unroll
+		for ( int i = 0; i < b2GpuStage_count; ++i )
+		{
+			P.stageCycles[i] = (unsigned long long)clk.acc[i];
+		}
+		P.stageCycles[8] = 0;
+		P.stageCycles[9] = (unsigned long long)( clk.last - begin );
+	}
+	cluster.sync(); // no block leaves while a peer may still look at its shared memory
+}
+
+} // namespace b2g

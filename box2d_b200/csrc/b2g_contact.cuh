@@ -10,6 +10,8 @@
 
 #include "b2gpu_layout.h"
 
+#include <cooperative_groups.h>
+
 namespace b2g
 {
 
@@ -29,21 +31,63 @@ B2G_DEV int rawI( const uint8_t* base, int offset )
 // scatter is guarded by b2_dynamicFlag exactly like the reference (contact_solver.c:1531).
 // Plain generic loads/stores: the view may live in shared memory (island-local kernel) or in global memory
 // (grid-barrier kernel, where the barrier's release/acquire pair orders them across blocks).
+// distributed shared memory address of slot `index` of a per-block body array (cluster mode)
+template <typename T> B2G_DEV T* clusterSlot( const SolveView& V, T* localArray, int index )
+{
+	unsigned linear = (unsigned)index - 1u;
+	unsigned owner = linear >> V.clusterShift;
+	unsigned slot = ( linear & (unsigned)V.clusterMask ) + 1u;
+	T* remote = static_cast<T*>( __cluster_map_shared_rank( static_cast<void*>( localArray ), owner ) );
+	return remote + slot;
+}
+
 B2G_DEV float4 gatherVel( const SolveView& V, int index )
 {
-	return V.vel[index];
+	if ( V.clusterShift < 0 || index == 0 )
+	{
+		return V.vel[index];
+	}
+	return *clusterSlot( V, V.vel, index );
 }
 
 B2G_DEV float4 gatherPos( const SolveView& V, int index )
 {
-	return V.pos[index];
+	if ( V.clusterShift < 0 || index == 0 )
+	{
+		return V.pos[index];
+	}
+	return *clusterSlot( V, V.pos, index );
 }
 
 B2G_DEV void scatterVel( const SolveView& V, int index, float4 v )
 {
 	if ( ( __float_as_uint( v.w ) & B2L_FLAG_DYNAMIC ) != 0 )
 	{
-		V.vel[index] = v;
+		if ( V.clusterShift < 0 )
+		{
+			V.vel[index] = v;
+		}
+		else if ( V.asyncBar == 0 )
+		{
+			*clusterSlot( V, V.vel, index ) = v; // a dynamic body is never the static dummy
+		}
+		else
+		{
+			// the owner block counts the bytes that arrive for its bodies (mbarrier transaction count) instead of every
+			// writer fencing its stores at GPU scope
+			unsigned linear = (unsigned)index - 1u;
+			unsigned owner = linear >> V.clusterShift;
+			unsigned slot = ( linear & (unsigned)V.clusterMask ) + 1u;
+			unsigned local = (unsigned)__cvta_generic_to_shared( V.vel ) + slot * (unsigned)sizeof( float4 );
+			unsigned remote, remoteBar;
+			asm volatile( "mapa.shared::cluster.u32 %0, %1, %2;" : "=r"( remote ) : "r"( local ), "r"( owner ) );
+			asm volatile( "mapa.shared::cluster.u32 %0, %1, %2;" : "=r"( remoteBar ) : "r"( V.asyncBar ), "r"( owner ) );
+			asm volatile( "st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];"
+						  :
+						  : "r"( remote ), "r"( __float_as_uint( v.x ) ), "r"( __float_as_uint( v.y ) ), "r"( __float_as_uint( v.z ) ),
+							"r"( __float_as_uint( v.w ) ), "r"( remoteBar )
+						  : "memory" );
+		}
 	}
 }
 

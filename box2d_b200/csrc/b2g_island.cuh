@@ -81,9 +81,9 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 		int local = aggregatedAdd( P.binBodyCount, bin, active );
 		if ( active )
 		{
-			if ( local < P.capBodies )
+			if ( local < P.binCapBodies )
 			{
-				P.binBodyList[(size_t)bin * P.capBodies + local] = b;
+				P.binBodyList[(size_t)bin * P.binCapBodies + local] = b;
 			}
 			else
 			{
@@ -157,6 +157,10 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 			int* contactStart = P.binColorStart + (size_t)bin * kColorSlots;
 			int* jointStart = P.binJointStart + (size_t)bin * kColorSlots;
 			int contacts = 0, joints = 0;
+			// what the fullest block of the bin's cluster has to hold: a colour is dealt out evenly, the overflow
+			// colour goes to the first block as a whole
+			int blockContacts = 0, blockJoints = 0;
+			const int share = P.clusterSize;
 			for ( int c = 0; c <= P.colorCount; ++c ) // the bucket after the last colour is the overflow colour
 			{
 				int n = contactStart[c];
@@ -165,6 +169,8 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 				int m = jointStart[c];
 				jointStart[c] = joints;
 				joints += m;
+				blockContacts += c < P.colorCount ? ( n + share - 1 ) / share : n;
+				blockJoints += c < P.colorCount ? ( m + share - 1 ) / share : m;
 				if ( c == P.colorCount && ( n > kMaxBinOverflow || m > kMaxBinOverflow ) )
 				{
 					*P.binFail = 1;
@@ -175,7 +181,7 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 				contactStart[c] = contacts;
 				jointStart[c] = joints;
 			}
-			if ( contacts > P.capContacts || joints > P.capJoints )
+			if ( blockContacts > P.capContacts || blockJoints > P.capJoints )
 			{
 				*P.binFail = 1;
 			}
@@ -200,7 +206,7 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 		{
 			int2 br = P.contactBinRank[slot];
 			int dest = P.binColorStart[(size_t)br.x * kColorSlots + c] + br.y;
-			P.binContactList[(size_t)br.x * P.capContacts + dest] = slot;
+			P.binContactList[(size_t)br.x * P.binCapContacts + dest] = slot;
 		}
 	} );
 	forEachItem( P.jointCount, [&]( int j ) {
@@ -213,7 +219,7 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 			}
 			int2 br = P.jointBinRank[j];
 			int dest = P.binJointStart[(size_t)br.x * kColorSlots + c] + br.y;
-			P.binJointList[(size_t)br.x * P.capJoints + dest] = j;
+			P.binJointList[(size_t)br.x * P.binCapJoints + dest] = j;
 		}
 	} );
 }
@@ -290,6 +296,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	cursor += (size_t)capC * sizeof( int );
 	int* wireSlot = reinterpret_cast<int*>( cursor );
 	V.anyRestitution = &anyRestitution;
+	V.clusterShift = -1;
+	V.clusterMask = 0;
+	V.asyncBar = 0;
 
 	const int bodyCount = P.binBodyCount[bin];
 	const int* bodyList = P.binBodyList + (size_t)bin * capB;

@@ -9,7 +9,7 @@
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
 #include "b2_gpu_solver.h"
 
-#include "b2g_island.cuh"
+#include "b2g_cluster.cuh"
 
 #include <cuda_runtime.h>
 
@@ -351,6 +351,9 @@ struct b2GpuSolver
 	size_t binCounterCount = 0;
 	size_t islandSmemBytes = 0;
 	size_t islandSmemBudget = 0;
+	int clusterForce = 0;				 // testing: smallest cluster size the planner may use (B2GPU_CLUSTER_FORCE)
+	int clusterBins[4] = { 0, 0, 0, 0 }; // resident clusters of 2, 4, 8, 16 blocks (0 = not available)
+	int overflowContacts = 0, overflowJoints = 0; // overflow colour totals of the step (all worlds)
 	bool islandMode = false;
 	int islandsEnabled = 1;
 	int maxSharedOptin = 0;
@@ -471,9 +474,13 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 	{
 		cudaFuncAttributes attr;
 		int dynamicMax = 0;
-		if ( cudaFuncGetAttributes( &attr, b2g::b2gIslandKernel ) == cudaSuccess )
+		cudaFuncAttributes clusterAttr;
+		if ( cudaFuncGetAttributes( &attr, b2g::b2gIslandKernel ) == cudaSuccess &&
+			 cudaFuncGetAttributes( &clusterAttr, b2g::b2gClusterIslandKernel ) == cudaSuccess )
 		{
-			dynamicMax = s->maxSharedOptin - (int)attr.sharedSizeBytes - 256;
+			// one budget for both island kernels: the planner does not care which of them runs
+			size_t staticBytes = attr.sharedSizeBytes > clusterAttr.sharedSizeBytes ? attr.sharedSizeBytes : clusterAttr.sharedSizeBytes;
+			dynamicMax = s->maxSharedOptin - (int)staticBytes - 256;
 		}
 		if ( dynamicMax <= 0 ||
 			 cudaFuncSetAttribute( b2g::b2gIslandKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dynamicMax ) != cudaSuccess )
@@ -483,6 +490,36 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 			dynamicMax = 0;
 		}
 		s->islandSmemBudget = (size_t)dynamicMax;
+		// clusters of 2, 4, 8, 16 blocks with the same carve-up: how many can be resident at once
+		const char* forceEnv = getenv( "B2GPU_CLUSTER_FORCE" );
+		s->clusterForce = forceEnv != nullptr ? atoi( forceEnv ) : 0;
+		const char* clusterEnv = getenv( "B2GPU_CLUSTERS" );
+		bool clustersEnabled = s->islandsEnabled != 0 && ( clusterEnv == nullptr || atoi( clusterEnv ) != 0 );
+		if ( clustersEnabled && dynamicMax > 0 &&
+			 cudaFuncSetAttribute( b2g::b2gClusterIslandKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dynamicMax ) == cudaSuccess &&
+			 cudaFuncSetAttribute( b2g::b2gClusterIslandKernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1 ) == cudaSuccess )
+		{
+			for ( int k = 0; k < 4; ++k )
+			{
+				cudaLaunchConfig_t config = {};
+				config.gridDim = dim3( (unsigned)( ( 2 << k ) * s->smCount ) );
+				config.blockDim = dim3( b2g::kIslandThreads );
+				config.dynamicSmemBytes = (size_t)dynamicMax;
+				cudaLaunchAttribute attribute;
+				attribute.id = cudaLaunchAttributeClusterDimension;
+				attribute.val.clusterDim.x = (unsigned)( 2 << k );
+				attribute.val.clusterDim.y = 1;
+				attribute.val.clusterDim.z = 1;
+				config.attrs = &attribute;
+				config.numAttrs = 1;
+				int clusters = 0;
+				if ( cudaOccupancyMaxActiveClusters( &clusters, b2g::b2gClusterIslandKernel, &config ) == cudaSuccess )
+				{
+					s->clusterBins[k] = clusters;
+				}
+			}
+		}
+		cudaGetLastError();
 	}
 
 	bool ok = cudaStreamCreateWithFlags( &s->stream, cudaStreamNonBlocking ) == cudaSuccess;
@@ -568,6 +605,20 @@ extern "C" uint64_t b2GpuSolverGetLaunchCount( const b2GpuSolver* s )
 	return s != nullptr ? s->launchCount : 0;
 }
 
+extern "C" int b2GpuSolverGetIslandPlan( const b2GpuSolver* s, int* binCount, int* blocksPerBin )
+{
+	int bins = s != nullptr && s->islandMode ? s->params.binCount : 0;
+	if ( binCount != nullptr )
+	{
+		*binCount = bins;
+	}
+	if ( blocksPerBin != nullptr )
+	{
+		*blocksPerBin = bins > 0 ? s->params.clusterSize : 0;
+	}
+	return bins;
+}
+
 // ---- the step as segments ---------------------------------------------------------------------------------------------
 // One step solves `worldCount` independent worlds (1 for b2GpuSolverStep, N for the batch API).  Their arrays are
 // addressed through segments: a body segment per world, a contact / joint segment per (colour slot, world).  Colour
@@ -596,6 +647,106 @@ static int b2gFindSegment( const std::vector<int>& starts, int flat )
 		}
 	}
 	return lo;
+}
+
+struct b2gBinPlan
+{
+	int binCount, share, shift, capB, capC, capJ;
+};
+
+// Bins for blocks-per-bin = share.  Island i goes to the bin its first body falls in when the islands are laid end to
+// end and cut every `target` bodies, so a bin gets between target - (largest island) and target + (largest island)
+// bodies.  `waves`: more bins than `binLimit` are allowed when the data does not fit (they run in waves).
+static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimitIn, bool waves, b2gBinPlan* plan )
+{
+	const b2g::StepParams& P = s->params;
+	const int bodies = P.bodyCount;
+	size_t budget = s->islandSmemBudget;
+	const double bytesPerBody = 52.0, bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0, bytesPerJoint = b2g::kJointStride + 12.0;
+	double totalBytes = bodies * bytesPerBody + s->contactTotal * bytesPerContact + s->jointTotal * bytesPerJoint;
+	int binLimit = binLimitIn < islandCount ? binLimitIn : islandCount;
+	// head room for uneven constraint density between bins; a cluster exists for the few largest islands, deal exactly
+	double headRoom = share > 1 ? 1.1 : 1.6;
+	int wanted = (int)( totalBytes * headRoom / ( (double)budget * share ) ) + 1;
+	if ( wanted > binLimit )
+	{
+		if ( !waves )
+		{
+			return false;
+		}
+		binLimit = wanted < islandCount ? wanted : islandCount;
+	}
+	int target = ( bodies + binLimit - 1 ) / binLimit;
+	s->islandBin.assign( (size_t)islandCount, 0 );
+	std::vector<int>& binBodies = s->binBodies;
+	binBodies.assign( (size_t)binLimit, 0 );
+	int bin = 0, maxBin = 0;
+	long long before = 0;
+	for ( int i = 0; i < islandCount; ++i )
+	{
+		int n = s->islandBodies[i];
+		int b = (int)( before / target );
+		b = b < binLimit ? b : binLimit - 1;
+		s->islandBin[i] = b;
+		binBodies[b] += n;
+		maxBin = binBodies[b] > maxBin ? binBodies[b] : maxBin;
+		bin = b > bin ? b : bin;
+		before += n;
+	}
+	int binCount = bin + 1;
+
+	// capacities PER BLOCK: exact for bodies (a power of two per block when the bin is shared by a cluster); the rest
+	// of the budget is split between contacts and joints in proportion to their estimated bytes, so a bin may hold
+	// several times its fair share before binFail trips
+	int capB = ( maxBin + 3 ) & ~3, shift = -1;
+	if ( share > 1 )
+	{
+		int perBlock = ( maxBin + share - 1 ) / share;
+		shift = 2;
+		while ( ( 1 << shift ) < perBlock )
+		{
+			shift += 1;
+		}
+		capB = 1 << shift;
+	}
+	double fraction = (double)maxBin / (double)bodies / (double)share;
+	// a block of a cluster holds ceil(n / share) of every colour, the first block the bin's overflow colour on top
+	double slack = share > 1 ? (double)( b2g::kMaxColors + 1 ) : 0.0;
+	double needC = fraction * s->contactTotal + slack + ( share > 1 ? (double)s->overflowContacts : 0.0 );
+	double needJ = fraction * s->jointTotal + ( s->jointTotal > 0 ? slack : 0.0 ) + ( share > 1 ? (double)s->overflowJoints : 0.0 );
+	size_t fixed = b2g::islandSharedBytes( capB, 0, 0 );
+	if ( fixed + (size_t)( needC * 1.1 * bytesPerContact + needJ * 1.1 * bytesPerJoint ) + 4096 > budget )
+	{
+		return false;
+	}
+	double weightC = needC * bytesPerContact + 2048.0, weightJ = s->jointTotal > 0 ? needJ * bytesPerJoint + 2048.0 : 0.0;
+	double spare = (double)( budget - fixed ) - 64.0;
+	int capC = ( (int)( spare * weightC / ( weightC + weightJ ) / bytesPerContact ) ) & ~3;
+	int capJ = s->jointTotal > 0 ? ( (int)( spare * weightJ / ( weightC + weightJ ) / bytesPerJoint ) ) & ~3 : 0;
+	if ( binCount > s->smCount )
+	{
+		// many small bins (batches of worlds): do not hog the SM, several blocks should be co-resident
+		int tightC = ( (int)( needC * 2.0 ) + 35 ) & ~3, tightJ = s->jointTotal > 0 ? ( (int)( needJ * 2.0 ) + 11 ) & ~3 : 0;
+		capC = capC < tightC ? capC : tightC;
+		capJ = capJ < tightJ ? capJ : tightJ;
+	}
+	// no point in exceeding what exists
+	capC = capC > ( ( s->contactTotal + 3 ) & ~3 ) ? ( ( s->contactTotal + 3 ) & ~3 ) : capC;
+	capJ = capJ > ( ( s->jointTotal + 3 ) & ~3 ) ? ( ( s->jointTotal + 3 ) & ~3 ) : capJ;
+	capC = capC < 4 ? 4 : capC;
+	for ( int guard = 0; guard < 64 && b2g::islandSharedBytes( capB, capC, capJ ) > budget; ++guard )
+	{
+		capC = ( capC - capC / 32 - 4 ) & ~3; // rounding slack: shave ~3 % until it fits
+		capJ = capJ > 0 ? ( capJ - capJ / 32 - 4 ) & ~3 : 0;
+		capC = capC < 4 ? 4 : capC;
+		capJ = capJ < 0 ? 0 : capJ;
+	}
+	if ( b2g::islandSharedBytes( capB, capC, capJ ) > budget || capC < needC || capJ < needJ )
+	{
+		return false;
+	}
+	*plan = { binCount, share, shift, capB, capC, capJ };
+	return true;
 }
 
 // ---- island mode planning (host) --------------------------------------------------------------------------------
@@ -637,89 +788,45 @@ static int b2gPlanIslands( b2GpuSolver* s )
 		}
 	}
 
-	// Bins: one per SM when a bin of that size fits a block's shared memory, otherwise as many as it takes (they run in
-	// waves).  Island i goes to the bin its first body falls in when the islands are laid end to end and cut every
-	// `target` bodies, so a bin gets between target - (largest island) and target + (largest island) bodies.
-	size_t budget = s->islandSmemBudget;
-	const double bytesPerBody = 52.0, bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0, bytesPerJoint = b2g::kJointStride + 12.0;
-	double totalBytes = bodies * bytesPerBody + s->contactTotal * bytesPerContact + s->jointTotal * bytesPerJoint;
-	int binLimit = s->smCount < islandCount ? s->smCount : islandCount;
-	int wanted = (int)( totalBytes * 1.6 / (double)budget ) + 1; // 60 % head room for uneven constraint density
-	if ( wanted > binLimit )
+	// One block per bin when that fits; otherwise clusters of 2..16 blocks per bin (b2g_cluster.cuh), the smallest that
+	// holds the largest bin.  If nothing fits the grid-barrier kernel takes the step.
+	b2gBinPlan plan;
+	bool planned = s->clusterForce <= 1 && b2gPlanBins( s, islandCount, 1, s->smCount, true, &plan );
+	for ( int k = 0; !planned && k < 4; ++k )
 	{
-		binLimit = wanted < islandCount ? wanted : islandCount;
+		int share = 2 << k;
+		if ( s->clusterBins[k] > 0 && share >= s->clusterForce )
+		{
+			planned = b2gPlanBins( s, islandCount, share, s->clusterBins[k], false, &plan );
+		}
 	}
-	int target = ( bodies + binLimit - 1 ) / binLimit;
-	s->islandBin.assign( (size_t)islandCount, 0 );
-	std::vector<int>& binBodies = s->binBodies;
-	binBodies.assign( (size_t)binLimit, 0 );
-	int bin = 0, maxBin = 0;
-	long long before = 0;
-	for ( int i = 0; i < islandCount; ++i )
-	{
-		int n = s->islandBodies[i];
-		int b = (int)( before / target );
-		b = b < binLimit ? b : binLimit - 1;
-		s->islandBin[i] = b;
-		binBodies[b] += n;
-		maxBin = binBodies[b] > maxBin ? binBodies[b] : maxBin;
-		bin = b > bin ? b : bin;
-		before += n;
-	}
-	int binCount = bin + 1;
-
-	// capacities: exact for bodies; the rest of the budget is split between contacts and joints in proportion to
-	// their estimated bytes, so a bin may hold several times its fair share before binFail trips
-	int capB = ( maxBin + 3 ) & ~3;
-	double share = (double)maxBin / (double)bodies;
-	double needC = share * s->contactTotal, needJ = share * s->jointTotal;
-	size_t fixed = b2g::islandSharedBytes( capB, 0, 0 );
-	if ( fixed + (size_t)( needC * 1.1 * bytesPerContact + needJ * 1.1 * bytesPerJoint ) + 4096 > budget )
+	if ( !planned )
 	{
 		return 0;
 	}
-	double weightC = needC * bytesPerContact + 2048.0, weightJ = s->jointTotal > 0 ? needJ * bytesPerJoint + 2048.0 : 0.0;
-	double spare = (double)( budget - fixed ) - 64.0;
-	int capC = ( (int)( spare * weightC / ( weightC + weightJ ) / bytesPerContact ) ) & ~3;
-	int capJ = s->jointTotal > 0 ? ( (int)( spare * weightJ / ( weightC + weightJ ) / bytesPerJoint ) ) & ~3 : 0;
-	if ( binCount > s->smCount )
-	{
-		// many small bins (batches of worlds): do not hog the SM, several blocks should be co-resident
-		int tightC = ( (int)( needC * 2.0 ) + 35 ) & ~3, tightJ = s->jointTotal > 0 ? ( (int)( needJ * 2.0 ) + 11 ) & ~3 : 0;
-		capC = capC < tightC ? capC : tightC;
-		capJ = capJ < tightJ ? capJ : tightJ;
-	}
-	// no point in exceeding what exists
-	capC = capC > ( ( s->contactTotal + 3 ) & ~3 ) ? ( ( s->contactTotal + 3 ) & ~3 ) : capC;
-	capJ = capJ > ( ( s->jointTotal + 3 ) & ~3 ) ? ( ( s->jointTotal + 3 ) & ~3 ) : capJ;
-	capC = capC < 4 ? 4 : capC;
-	for ( int guard = 0; guard < 64 && b2g::islandSharedBytes( capB, capC, capJ ) > budget; ++guard )
-	{
-		capC = ( capC - capC / 32 - 4 ) & ~3; // rounding slack: shave ~3 % until it fits
-		capJ = capJ > 0 ? ( capJ - capJ / 32 - 4 ) & ~3 : 0;
-		capC = capC < 4 ? 4 : capC;
-		capJ = capJ < 0 ? 0 : capJ;
-	}
-	if ( b2g::islandSharedBytes( capB, capC, capJ ) > budget || capC < needC || capJ < needJ )
-	{
-		return 0;
-	}
+	const int binCount = plan.binCount, capB = plan.capB, capC = plan.capC, capJ = plan.capJ;
 
 	size_t slots = (size_t)P.contactSlots;
 	s->binCounterCount = (size_t)binCount * ( 1 + 2 * b2g::kColorSlots ) + 1;
 	B2G_CUDA( s->binCounters.reserve( s->binCounterCount ) );
 	B2G_CUDA( s->bodyLocal.reserve( (size_t)bodies + 1 ) );
-	B2G_CUDA( s->binBodyList.reserve( (size_t)binCount * capB + 1 ) );
+	const size_t share = (size_t)plan.share;
+	B2G_CUDA( s->binBodyList.reserve( (size_t)binCount * capB * share + 1 ) );
 	B2G_CUDA( s->slotGroupBits.reserve( slots + 1 ) );
 	B2G_CUDA( s->contactBinRank.reserve( slots + 1 ) );
-	B2G_CUDA( s->binContactList.reserve( (size_t)binCount * capC + 1 ) );
+	B2G_CUDA( s->binContactList.reserve( (size_t)binCount * capC * share + 1 ) );
 	B2G_CUDA( s->jointBinRank.reserve( (size_t)s->jointTotal + 1 ) );
-	B2G_CUDA( s->binJointList.reserve( (size_t)binCount * capJ + 1 ) );
+	B2G_CUDA( s->binJointList.reserve( (size_t)binCount * capJ * share + 1 ) );
 
 	P.binCount = binCount;
 	P.capBodies = capB;
 	P.capContacts = capC;
 	P.capJoints = capJ;
+	P.clusterSize = plan.share;
+	P.clusterShift = plan.shift;
+	P.binCapBodies = capB * plan.share;
+	P.binCapContacts = capC * plan.share;
+	P.binCapJoints = capJ * plan.share;
 	P.bodyBin = reinterpret_cast<const int*>( s->wireAll.ptr + s->inBins );
 	P.bodyLocal = s->bodyLocal.ptr;
 	P.binBodyCount = s->binCounters.ptr;
@@ -885,6 +992,8 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	}
 	s->contactTotal = flat;
 	s->jointTotal = joint;
+	s->overflowContacts = P.overflow.contactCount;
+	s->overflowJoints = P.overflow.jointCount;
 	P.contactSlots = slot;
 	P.jointCount = joint;
 
@@ -939,6 +1048,9 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	P.jointBits = reinterpret_cast<uint32_t*>( s->outAll.ptr + s->outBits );
 	P.hasHitEvents = &s->control->hasHitEvents;
 	P.g.anyRestitution = &s->control->anyRestitution;
+	P.g.clusterShift = -1;
+	P.g.clusterMask = 0;
+	P.g.asyncBar = 0;
 	P.barrier = s->control->barrier;
 	P.stageCycles = s->control->stageCycles;
 
@@ -1296,8 +1408,27 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 			{
 				return b2gFail( "b2gPartitionKernel launch", err );
 			}
-			err = cudaLaunchKernel( (const void*)b2g::b2gIslandKernel, dim3( s->params.binCount ), dim3( b2g::kIslandThreads ), args,
-									s->islandSmemBytes, s->stream );
+			if ( s->params.clusterSize > 1 )
+			{
+				cudaLaunchConfig_t config = {};
+				config.gridDim = dim3( (unsigned)( s->params.binCount * s->params.clusterSize ) );
+				config.blockDim = dim3( b2g::kIslandThreads );
+				config.dynamicSmemBytes = s->islandSmemBytes;
+				config.stream = s->stream;
+				cudaLaunchAttribute attribute;
+				attribute.id = cudaLaunchAttributeClusterDimension;
+				attribute.val.clusterDim.x = (unsigned)s->params.clusterSize;
+				attribute.val.clusterDim.y = 1;
+				attribute.val.clusterDim.z = 1;
+				config.attrs = &attribute;
+				config.numAttrs = 1;
+				err = cudaLaunchKernelEx( &config, b2g::b2gClusterIslandKernel, s->params );
+			}
+			else
+			{
+				err = cudaLaunchKernel( (const void*)b2g::b2gIslandKernel, dim3( s->params.binCount ), dim3( b2g::kIslandThreads ), args,
+										s->islandSmemBytes, s->stream );
+			}
 			if ( err != cudaSuccess )
 			{
 				return b2gFail( "b2gIslandKernel launch", err );

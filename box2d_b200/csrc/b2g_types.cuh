@@ -91,6 +91,14 @@ struct SolveView
 	int* cmeta;	   // kMeta* bits
 	uint8_t* joints; // b2JointSim working copy (indexA/indexB in the view's numbering, 0-based, -1 = static)
 	int* anyRestitution; // set by prepare when a contact of the view has restitution != 0
+	// Cluster mode (island kernel on a thread-block cluster): the body arrays are distributed over the blocks'
+	// shared memory; body index i (1-based, 0 = this block's own static dummy) lives in block (i-1) >> clusterShift at
+	// slot ((i-1) & clusterMask) + 1 and is reached through distributed shared memory.  clusterShift < 0: flat view.
+	int clusterShift;
+	int clusterMask;
+	// != 0: body writes are st.async stores that report to the owner block's mbarrier at this shared::cta address
+	// (b2g_cluster.cuh); 0: plain stores
+	unsigned asyncBar;
 };
 
 struct StepParams
@@ -137,20 +145,25 @@ struct StepParams
 	// island-local mode (b2g_island.cuh): islands are packed into bins, one thread block solves one bin entirely in
 	// shared memory.  Scratch written by the partition kernel, read by the island kernel.
 	int binCount;	   // 0 = island mode off for this step
-	int capBodies;	   // per-bin capacities the shared memory carve-up was sized for
+	int clusterSize;   // thread blocks per bin (1 = one block per bin, no cluster)
+	int clusterShift;  // log2 of the bodies per block in cluster mode
+	int capBodies;	   // per-BLOCK capacities the shared memory carve-up was sized for (a bin holds clusterSize times that)
 	int capContacts;
 	int capJoints;
+	int binCapBodies;  // strides of the per-bin lists: capacity of a whole bin (= per-block capacity * clusterSize)
+	int binCapContacts;
+	int binCapJoints;
 	const int* bodyBin;	 // [bodyCount] bin of each body (wire arena)
 	int* bodyLocal;		 // [bodyCount] 1-based index of the body inside its bin
 	int* binBodyCount;	 // [binCount]
-	int* binBodyList;	 // [binCount * capBodies] global body index
+	int* binBodyList;	 // [binCount * binCapBodies] global body index
 	int* binColorStart;	 // [binCount * (kMaxColors + 1)] contact counts per colour, then exclusive offsets (+ total)
 	int* binJointStart;	 // same for joints
 	int2* contactBinRank; // [contactSlots] bin, rank within (bin, colour)
 	int* slotGroupBits;	 // [contactSlots] kMetaGroup* bits in wire order
-	int* binContactList; // [binCount * capContacts] wire slots, colour-major
+	int* binContactList; // [binCount * binCapContacts] wire slots, colour-major
 	int2* jointBinRank;	 // [jointCount]
-	int* binJointList;	 // [binCount * capJoints] joint index, colour-major
+	int* binJointList;	 // [binCount * binCapJoints] joint index, colour-major
 	int* binFail;		 // set when some bin does not fit its capacities: the grid-barrier kernel takes the step
 
 	// sync + profiling

@@ -215,6 +215,9 @@ B2GPU_API int b2GpuGetDeviceCount( void );
 B2GPU_API int b2GpuGetVersion( void );
 /* Totals since creation */
 B2GPU_API uint64_t b2GpuSolverGetLaunchCount( const b2GpuSolver* solver );
+/* How the last step was laid out for the island-local kernels: number of bins (0 = the step was planned for the
+ * grid-barrier kernel) and thread blocks per bin (1, or the cluster size 2..16).  Returns binCount. */
+B2GPU_API int b2GpuSolverGetIslandPlan( const b2GpuSolver* solver, int* binCount, int* blocksPerBin );
 
 #ifdef __cplusplus
 }

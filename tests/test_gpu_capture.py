@@ -56,6 +56,25 @@ def test_captured_steps_bit_exact(solver, capture_files, mode, islands):
 		assert island_steps == 0
 
 
+@pytest.mark.parametrize("blocks", [2, 4, 16])
+def test_captured_steps_bit_exact_on_clusters(capture_files, blocks, monkeypatch):
+	"""Force the planner to share every bin between `blocks` thread blocks of a cluster (bodies in distributed shared
+	memory, colours dealt out over the blocks): same bits."""
+	monkeypatch.setenv("B2GPU_CLUSTER_FORCE", str(blocks))
+	cluster_steps = 0
+	with b2.GpuSolver() as solver:
+		for path in capture_files:
+			cap = b2.Capture(path)
+			desc, result, bufs = cap.make_call(islands=True)
+			solver.step(desc, result)
+			_check(cap, bufs, result)
+			bins, per_bin = solver.island_plan()
+			if bins > 0 and result.gridBarriers == 0:
+				assert per_bin >= blocks
+				cluster_steps += 1
+	assert cluster_steps > 0, "the cluster kernel never ran"
+
+
 def test_split_phase_is_repeatable(solver, capture_files):
 	"""Upload once, Run twice (inputs stay pristine on the device), Download: same bits as the one-shot step."""
 	solver.set_mode(0)
