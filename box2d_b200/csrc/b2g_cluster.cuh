@@ -34,6 +34,10 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 {
 	if ( __ldcg( P.binFail ) != 0 )
 	{
+		if ( blockIdx.x == 0 && threadIdx.x == 0 )
+		{
+			*P.islandFailed = 1;
+		}
 		return; // some bin does not fit (uniform for the whole grid): the grid-barrier kernel solves this step
 	}
 
@@ -105,8 +109,8 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 
 	if ( threadIdx.x == 0 )
 	{
-		const int* startC = P.binColorStart + (size_t)bin * kColorSlots;
-		const int* startJ = P.binJointStart + (size_t)bin * kColorSlots;
+		const int* startC = P.binColorOffset + (size_t)bin * kColorSlots;
+		const int* startJ = P.binJointOffset + (size_t)bin * kColorSlots;
 		int localC = 0, localJ = 0;
 		for ( int c = 0; c < slotCount; ++c )
 		{
@@ -264,8 +268,8 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 			}
 			if ( binCountJ[c] != 0 )
 			{
-				forEachInLocalColor(
-					localStartJ[c], localStartJ[c + 1], localStartC[c], localStartC[c + 1], joint, [&]( int k ) { contact( V, k ); } );
+				forEachInLocalColor( make_int4( localStartJ[c], localStartJ[c + 1], localStartC[c], localStartC[c + 1] ), joint,
+									 [&]( int k ) { contact( V, k ); } );
 				cluster.sync();
 				continue;
 			}

@@ -23,6 +23,7 @@ namespace b2g
 {
 
 constexpr int kIslandThreads = 512;
+constexpr int kPartitionThreads = 1024; // one block per SM: few arrivals at the grid barrier, enough threads for one item each
 constexpr int kColorSlots = kMaxColors + 2; // per-bin offsets: active colours, then the overflow bucket, then the total
 constexpr int kMaxBinOverflow = 256;		   // overflow constraints (contacts or joints) one bin can order
 
@@ -61,7 +62,7 @@ B2G_DEV int aggregatedAdd( int* counters, int key, bool active )
 
 // ---- partition ---------------------------------------------------------------------------------------------------------
 // counters (binBodyCount, binColorStart, binJointStart, binFail) are zeroed by the host before the launch
-__global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const __grid_constant__ StepParams P )
+__global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( const __grid_constant__ StepParams P )
 {
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned blocks = gridDim.x;
@@ -150,12 +151,16 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 	} );
 	gridBarrier( P.barrier + 1, blocks );
 
-	// phase 2: per bin, counts -> exclusive offsets (colour-major layout of the bin's lists), capacity check
+	// phase 2: the counts are final.  One thread per bin turns them into the exclusive offsets the island kernels read
+	// (colour-major layout of the bin's lists) and checks the capacities; the placement passes below do not wait for
+	// that, every constraint sums the counts of the colours before its own (a handful of L2 hits).
 	forEachItem( P.binCount, [&]( int bin ) {
 		if ( bin < P.binCount )
 		{
-			int* contactStart = P.binColorStart + (size_t)bin * kColorSlots;
-			int* jointStart = P.binJointStart + (size_t)bin * kColorSlots;
+			const int* contactCount = P.binColorStart + (size_t)bin * kColorSlots;
+			const int* jointCount = P.binJointStart + (size_t)bin * kColorSlots;
+			int* contactOffset = P.binColorOffset + (size_t)bin * kColorSlots;
+			int* jointOffset = P.binJointOffset + (size_t)bin * kColorSlots;
 			int contacts = 0, joints = 0;
 			// what the fullest block of the bin's cluster has to hold: a colour is dealt out evenly, the overflow
 			// colour goes to the first block as a whole
@@ -163,11 +168,11 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 			const int share = P.clusterSize;
 			for ( int c = 0; c <= P.colorCount; ++c ) // the bucket after the last colour is the overflow colour
 			{
-				int n = contactStart[c];
-				contactStart[c] = contacts;
+				int n = contactCount[c];
+				contactOffset[c] = contacts;
 				contacts += n;
-				int m = jointStart[c];
-				jointStart[c] = joints;
+				int m = jointCount[c];
+				jointOffset[c] = joints;
 				joints += m;
 				blockContacts += c < P.colorCount ? ( n + share - 1 ) / share : n;
 				blockJoints += c < P.colorCount ? ( m + share - 1 ) / share : m;
@@ -178,8 +183,8 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 			}
 			for ( int c = P.colorCount + 1; c < kColorSlots; ++c )
 			{
-				contactStart[c] = contacts;
-				jointStart[c] = joints;
+				contactOffset[c] = contacts;
+				jointOffset[c] = joints;
 			}
 			if ( blockContacts > P.capContacts || blockJoints > P.capJoints )
 			{
@@ -187,13 +192,16 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 			}
 		}
 	} );
-	gridBarrier( P.barrier + 1, 2 * blocks );
-	if ( __ldcg( P.binFail ) != 0 )
-	{
-		return;
-	}
 
-	// phase 3: place every constraint in its bin's list (flat passes again)
+	auto offsetOf = [&]( const int* counts, int bin, int c ) -> int {
+		const int* row = counts + (size_t)bin * kColorSlots;
+		int offset = 0;
+		for ( int k = 0; k < c; ++k )
+		{
+			offset += row[k];
+		}
+		return offset;
+	};
 	forEachItem( P.contactSlots, [&]( int slot ) {
 		int c = 0;
 		while ( c < P.colorCount && ( c + 1 < P.colorCount ? P.colors[c + 1].contactStart : P.overflow.contactStart ) <= slot )
@@ -205,8 +213,11 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 			 ( __float_as_int( P.wire[(size_t)slot * WR_COUNT + WR_HEAD].z ) & kMetaPointMask ) != 0 )
 		{
 			int2 br = P.contactBinRank[slot];
-			int dest = P.binColorStart[(size_t)br.x * kColorSlots + c] + br.y;
-			P.binContactList[(size_t)br.x * P.binCapContacts + dest] = slot;
+			int dest = offsetOf( P.binColorStart, br.x, c ) + br.y;
+			if ( dest < P.binCapContacts ) // a bin that does not fit raised binFail above
+			{
+				P.binContactList[(size_t)br.x * P.binCapContacts + dest] = slot;
+			}
 		}
 	} );
 	forEachItem( P.jointCount, [&]( int j ) {
@@ -218,8 +229,11 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gPartitionKernel( const 
 				c += 1;
 			}
 			int2 br = P.jointBinRank[j];
-			int dest = P.binJointStart[(size_t)br.x * kColorSlots + c] + br.y;
-			P.binJointList[(size_t)br.x * P.binCapJoints + dest] = j;
+			int dest = offsetOf( P.binJointStart, br.x, c ) + br.y;
+			if ( dest < P.binCapJoints )
+			{
+				P.binJointList[(size_t)br.x * P.binCapJoints + dest] = j;
+			}
 		}
 	} );
 }
@@ -233,26 +247,18 @@ template <typename F> B2G_DEV void forEachLocal( int itemCount, F f )
 	}
 }
 
-// joints on the first warps, contacts from the next multiple of 32: a warp never mixes the two kinds
-template <typename FJ, typename FC> B2G_DEV void forEachInLocalColor( int jointBegin, int jointEnd, int contactBegin, int contactEnd, FJ joint,
-																	   FC contact )
+// One colour of a bin: joints [r.x, r.y) are taken by the block's first threads, contacts [r.z, r.w) by its LAST threads
+// (thread blockDim-1 takes the first contact), so that joints and contacts of the colour run side by side in different
+// warps as long as the block has a thread for each.  The header is one broadcast 16-byte shared load.
+template <typename FJ, typename FC> B2G_DEV void forEachInLocalColor( int4 r, FJ joint, FC contact )
 {
-	int jointCount = jointEnd - jointBegin;
-	int jointSpan = roundUp32( jointCount );
-	int itemCount = jointSpan + ( contactEnd - contactBegin );
-	for ( int t = (int)threadIdx.x; t < itemCount; t += (int)blockDim.x )
+	for ( int k = r.x + (int)threadIdx.x; k < r.y; k += (int)blockDim.x )
 	{
-		if ( t < jointSpan )
-		{
-			if ( t < jointCount )
-			{
-				joint( jointBegin + t );
-			}
-		}
-		else
-		{
-			contact( contactBegin + ( t - jointSpan ) );
-		}
+		joint( k );
+	}
+	for ( int k = r.z + ( (int)blockDim.x - 1 - (int)threadIdx.x ); k < r.w; k += (int)blockDim.x )
+	{
+		contact( k );
 	}
 }
 
@@ -260,6 +266,10 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 {
 	if ( __ldcg( P.binFail ) != 0 )
 	{
+		if ( blockIdx.x == 0 && threadIdx.x == 0 )
+		{
+			*P.islandFailed = 1;
+		}
 		return; // some bin does not fit: the grid-barrier kernel solves this step
 	}
 
@@ -268,6 +278,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	__shared__ int colorStartJ[kColorSlots];
 	__shared__ int anyRestitution;
 	__shared__ int overflowOrder[kMaxBinOverflow]; // scratch for ordering the bin's overflow constraints
+	// the colours that are present in this bin, in order: { jointBegin, jointEnd, contactBegin, contactEnd }
+	__shared__ __align__( 16 ) int4 passRange[kMaxColors];
+	__shared__ int passCount;
 
 	const int bin = (int)blockIdx.x;
 	const int capB = P.capBodies, capC = P.capContacts, capJ = P.capJoints;
@@ -311,8 +324,8 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 
 	if ( threadIdx.x < kColorSlots )
 	{
-		colorStartC[threadIdx.x] = P.binColorStart[(size_t)bin * kColorSlots + threadIdx.x];
-		colorStartJ[threadIdx.x] = P.binJointStart[(size_t)bin * kColorSlots + threadIdx.x];
+		colorStartC[threadIdx.x] = P.binColorOffset[(size_t)bin * kColorSlots + threadIdx.x];
+		colorStartJ[threadIdx.x] = P.binJointOffset[(size_t)bin * kColorSlots + threadIdx.x];
 	}
 	if ( threadIdx.x == 0 )
 	{
@@ -326,6 +339,19 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	const int contactCount = colorStartC[kColorSlots - 1];
 	const int jointCount = colorStartJ[kColorSlots - 1];
 	const int colorCount = P.colorCount;
+	if ( threadIdx.x == 0 )
+	{
+		int passes = 0;
+		for ( int c = 0; c < colorCount; ++c )
+		{
+			int4 r = make_int4( colorStartJ[c], colorStartJ[c + 1], colorStartC[c], colorStartC[c + 1] );
+			if ( r.x != r.y || r.z != r.w )
+			{
+				passRange[passes++] = r; // a colour that is not present in this bin has nothing to order
+			}
+		}
+		passCount = passes;
+	}
 	// the overflow colour's constraints of this bin, solved by one thread in array order
 	const int ovCb = colorStartC[colorCount], ovCe = colorStartC[colorCount + 1];
 	const int ovJb = colorStartJ[colorCount], ovJe = colorStartJ[colorCount + 1];
@@ -404,6 +430,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	__syncthreads();
 	clk.lap( b2GpuStage_prepareConstraints );
 
+	const int passes = passCount;
 	for ( int subStep = 0; subStep < P.subStepCount; ++subStep )
 	{
 		forEachLocal( bodyCount, [&]( int i ) { integrateVelocities( V, i ); } );
@@ -425,15 +452,10 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			}
 			__syncthreads();
 		}
-		for ( int c = 0; c < colorCount; ++c )
+		for ( int pass = 0; pass < passes; ++pass )
 		{
-			int jb = colorStartJ[c], je = colorStartJ[c + 1], cb = colorStartC[c], ce = colorStartC[c + 1];
-			if ( jb == je && cb == ce )
-			{
-				continue; // colour not present in this bin: nothing to order (uniform for the block)
-			}
 			forEachInLocalColor(
-				jb, je, cb, ce, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); }, [&]( int k ) { warmStartContact( V, k ); } );
+				passRange[pass], [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); }, [&]( int k ) { warmStartContact( V, k ); } );
 			__syncthreads();
 		}
 		clk.lap( b2GpuStage_warmStart );
@@ -453,15 +475,10 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			}
 			__syncthreads();
 		}
-		for ( int c = 0; c < colorCount; ++c )
+		for ( int pass = 0; pass < passes; ++pass )
 		{
-			int jb = colorStartJ[c], je = colorStartJ[c + 1], cb = colorStartC[c], ce = colorStartC[c + 1];
-			if ( jb == je && cb == ce )
-			{
-				continue;
-			}
 			forEachInLocalColor(
-				jb, je, cb, ce,
+				passRange[pass],
 				[&]( int k ) {
 					b2lJointSim* joint = jointAt( V, k );
 					solveJoint( P, V, joint, true );
@@ -491,15 +508,10 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			}
 			__syncthreads();
 		}
-		for ( int c = 0; c < colorCount; ++c )
+		for ( int pass = 0; pass < passes; ++pass )
 		{
-			int jb = colorStartJ[c], je = colorStartJ[c + 1], cb = colorStartC[c], ce = colorStartC[c + 1];
-			if ( jb == je && cb == ce )
-			{
-				continue;
-			}
 			forEachInLocalColor(
-				jb, je, cb, ce, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+				passRange[pass], [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
 				[&]( int k ) { solveContact( P, V, k, false ); } );
 			__syncthreads();
 		}
@@ -519,14 +531,14 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			}
 			__syncthreads();
 		}
-		for ( int c = 0; c < colorCount; ++c )
+		for ( int pass = 0; pass < passes; ++pass )
 		{
-			int cb = colorStartC[c], ce = colorStartC[c + 1];
-			if ( cb == ce )
+			int4 r = passRange[pass];
+			if ( r.z == r.w )
 			{
 				continue;
 			}
-			for ( int k = cb + (int)threadIdx.x; k < ce; k += (int)blockDim.x )
+			for ( int k = r.z + (int)threadIdx.x; k < r.w; k += (int)blockDim.x )
 			{
 				restitutionContact( P, V, k );
 			}

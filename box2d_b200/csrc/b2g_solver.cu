@@ -264,6 +264,8 @@ struct ControlBlock
 	int hasHitEvents;
 	int anyRestitution;
 	unsigned long long stageCycles[10];
+	int islandFailed; // a bin did not fit its block (binFail): the host reruns the step on the grid-barrier kernel
+	int reserved;
 };
 
 // segments of the step (see "the step as segments" below)
@@ -351,6 +353,7 @@ struct b2GpuSolver
 	size_t binCounterCount = 0;
 	size_t islandSmemBytes = 0;
 	size_t islandSmemBudget = 0;
+	bool testTightBins = false;			 // testing: B2GPU_TEST_TIGHT_BINS=1 makes every island step fail over to the grid kernel
 	int clusterForce = 0;				 // testing: smallest cluster size the planner may use (B2GPU_CLUSTER_FORCE)
 	int clusterBins[4] = { 0, 0, 0, 0 }; // resident clusters of 2, 4, 8, 16 blocks (0 = not available)
 	int overflowContacts = 0, overflowJoints = 0; // overflow colour totals of the step (all worlds)
@@ -491,6 +494,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		}
 		s->islandSmemBudget = (size_t)dynamicMax;
 		// clusters of 2, 4, 8, 16 blocks with the same carve-up: how many can be resident at once
+		const char* tightEnv = getenv( "B2GPU_TEST_TIGHT_BINS" );
+		s->testTightBins = tightEnv != nullptr && atoi( tightEnv ) != 0;
 		const char* forceEnv = getenv( "B2GPU_CLUSTER_FORCE" );
 		s->clusterForce = forceEnv != nullptr ? atoi( forceEnv ) : 0;
 		const char* clusterEnv = getenv( "B2GPU_CLUSTERS" );
@@ -804,11 +809,15 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	{
 		return 0;
 	}
+	if ( s->testTightBins )
+	{
+		plan.capC = 4; // testing: no bin fits, every step takes the rerun path
+	}
 	const int binCount = plan.binCount, capB = plan.capB, capC = plan.capC, capJ = plan.capJ;
 
 	size_t slots = (size_t)P.contactSlots;
-	s->binCounterCount = (size_t)binCount * ( 1 + 2 * b2g::kColorSlots ) + 1;
-	B2G_CUDA( s->binCounters.reserve( s->binCounterCount ) );
+	s->binCounterCount = (size_t)binCount * ( 1 + 2 * b2g::kColorSlots ) + 1; // the part that is zeroed every step
+	B2G_CUDA( s->binCounters.reserve( s->binCounterCount + (size_t)binCount * 2 * b2g::kColorSlots ) );
 	B2G_CUDA( s->bodyLocal.reserve( (size_t)bodies + 1 ) );
 	const size_t share = (size_t)plan.share;
 	B2G_CUDA( s->binBodyList.reserve( (size_t)binCount * capB * share + 1 ) );
@@ -833,6 +842,8 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	P.binColorStart = s->binCounters.ptr + binCount;
 	P.binJointStart = P.binColorStart + (size_t)binCount * b2g::kColorSlots;
 	P.binFail = P.binJointStart + (size_t)binCount * b2g::kColorSlots;
+	P.binColorOffset = P.binFail + 1;
+	P.binJointOffset = P.binColorOffset + (size_t)binCount * b2g::kColorSlots;
 	P.binBodyList = s->binBodyList.ptr;
 	P.contactBinRank = s->contactBinRank.ptr;
 	P.slotGroupBits = s->slotGroupBits.ptr;
@@ -1048,6 +1059,7 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	P.jointBits = reinterpret_cast<uint32_t*>( s->outAll.ptr + s->outBits );
 	P.hasHitEvents = &s->control->hasHitEvents;
 	P.g.anyRestitution = &s->control->anyRestitution;
+	P.islandFailed = &s->control->islandFailed;
 	P.g.clusterShift = -1;
 	P.g.clusterMask = 0;
 	P.g.asyncBar = 0;
@@ -1376,6 +1388,60 @@ static int b2gRunStages( b2GpuSolver* s )
 	return 0;
 }
 
+static int b2gEnqueueDownload( b2GpuSolver* s );
+
+static int b2gLaunchGridKernel( b2GpuSolver* s )
+{
+	void* args[] = { (void*)&s->params };
+	cudaError_t err;
+	if ( s->cooperative )
+	{
+		err = cudaLaunchCooperativeKernel( (const void*)b2g::b2gStepKernel, dim3( s->gridBlocks ), dim3( b2g::kBlockThreads ), args, 0,
+										   s->stream );
+	}
+	else
+	{
+		err = cudaLaunchKernel( (const void*)b2g::b2gStepKernel, dim3( s->gridBlocks ), dim3( b2g::kBlockThreads ), args, 0, s->stream );
+	}
+	if ( err != cudaSuccess )
+	{
+		return b2gFail( "b2gStepKernel launch", err );
+	}
+	s->lastLaunches += 1;
+	return 0;
+}
+
+// The island kernels give up when a bin turns out not to fit its block (rare: the planner sizes the bins from the body
+// counts and cannot see how the constraints spread).  The flag comes back with the control block; the step is then run
+// again on the grid-barrier kernel from the untouched inputs.  Called after the stream has been synchronised.
+static int b2gRerunIfIslandsFailed( b2GpuSolver* s, bool download )
+{
+	if ( !s->islandMode || s->mode != 0 || s->hControl->islandFailed == 0 )
+	{
+		return 0;
+	}
+	B2G_CUDA( cudaMemsetAsync( s->control, 0, sizeof( ControlBlock ), s->stream ) );
+	if ( b2gLaunchGridKernel( s ) != 0 )
+	{
+		return 1;
+	}
+	B2G_CUDA( cudaEventRecord( s->evStop, s->stream ) );
+	s->launchCount += 1;
+	if ( download )
+	{
+		if ( b2gEnqueueDownload( s ) != 0 )
+		{
+			return 1;
+		}
+	}
+	else
+	{
+		B2G_CUDA( cudaMemcpyAsync( s->hControl, s->control, sizeof( ControlBlock ), cudaMemcpyDeviceToHost, s->stream ) );
+	}
+	B2G_CUDA( cudaStreamSynchronize( s->stream ) );
+	return 0;
+}
+
 static int b2gEnqueueRun( b2GpuSolver* s )
 {
 	if ( !s->uploaded )
@@ -1392,16 +1458,17 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 		cudaError_t err;
 		if ( s->islandMode )
 		{
-			// partition -> island kernel; the grid-barrier kernel below only runs if a bin did not fit (binFail)
+			// partition -> island kernel; if a bin does not fit (binFail) the host reruns the step on the grid-barrier
+			// kernel once the flag has come back (b2gRerunIfIslandsFailed)
 			B2G_CUDA( cudaMemsetAsync( s->binCounters.ptr, 0, s->binCounterCount * sizeof( int ), s->stream ) );
 			if ( s->cooperative )
 			{
 				err = cudaLaunchCooperativeKernel( (const void*)b2g::b2gPartitionKernel, dim3( s->gridBlocks ),
-												   dim3( b2g::kBlockThreads ), args, 0, s->stream );
+												   dim3( b2g::kPartitionThreads ), args, 0, s->stream );
 			}
 			else
 			{
-				err = cudaLaunchKernel( (const void*)b2g::b2gPartitionKernel, dim3( s->gridBlocks ), dim3( b2g::kBlockThreads ), args, 0,
+				err = cudaLaunchKernel( (const void*)b2g::b2gPartitionKernel, dim3( s->gridBlocks ), dim3( b2g::kPartitionThreads ), args, 0,
 										s->stream );
 			}
 			if ( err != cudaSuccess )
@@ -1435,21 +1502,10 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 			}
 			s->lastLaunches += 2;
 		}
-		if ( s->cooperative )
+		else if ( b2gLaunchGridKernel( s ) != 0 )
 		{
-			err = cudaLaunchCooperativeKernel( (const void*)b2g::b2gStepKernel, dim3( s->gridBlocks ), dim3( b2g::kBlockThreads ),
-											   args, 0, s->stream );
+			return 1;
 		}
-		else
-		{
-			err = cudaLaunchKernel( (const void*)b2g::b2gStepKernel, dim3( s->gridBlocks ), dim3( b2g::kBlockThreads ), args, 0,
-									s->stream );
-		}
-		if ( err != cudaSuccess )
-		{
-			return b2gFail( "b2gStepKernel launch", err );
-		}
-		s->lastLaunches += 1;
 	}
 	else
 	{
@@ -1498,6 +1554,10 @@ extern "C" int b2GpuSolverWait( b2GpuSolver* s )
 		return b2gFailMsg( "b2GpuSolverWait: null solver" );
 	}
 	B2G_CUDA( cudaStreamSynchronize( s->stream ) );
+	if ( s->ran && b2gRerunIfIslandsFailed( s, true ) != 0 )
+	{
+		return 1;
+	}
 	s->tWaited = std::chrono::steady_clock::now();
 	if ( s->ran )
 	{
@@ -1822,6 +1882,10 @@ extern "C" int b2GpuSolverRun( b2GpuSolver* s, b2GpuStepResult* r )
 	}
 	B2G_CUDA( cudaMemcpyAsync( s->hControl, s->control, sizeof( ControlBlock ), cudaMemcpyDeviceToHost, s->stream ) );
 	B2G_CUDA( cudaStreamSynchronize( s->stream ) );
+	if ( b2gRerunIfIslandsFailed( s, false ) != 0 )
+	{
+		return 1;
+	}
 	B2G_CUDA( cudaEventElapsedTime( &s->lastKernelMs, s->evStart, s->evStop ) );
 	if ( r != nullptr )
 	{

@@ -157,13 +157,16 @@ struct StepParams
 	int* bodyLocal;		 // [bodyCount] 1-based index of the body inside its bin
 	int* binBodyCount;	 // [binCount]
 	int* binBodyList;	 // [binCount * binCapBodies] global body index
-	int* binColorStart;	 // [binCount * (kMaxColors + 1)] contact counts per colour, then exclusive offsets (+ total)
+	int* binColorStart;	 // [binCount * kColorSlots] contact counts per colour (+ the overflow bucket)
 	int* binJointStart;	 // same for joints
+	int* binColorOffset; // [binCount * kColorSlots] exclusive offsets of the colours in the bin's contact list (+ total)
+	int* binJointOffset; // same for joints
 	int2* contactBinRank; // [contactSlots] bin, rank within (bin, colour)
 	int* slotGroupBits;	 // [contactSlots] kMetaGroup* bits in wire order
 	int* binContactList; // [binCount * binCapContacts] wire slots, colour-major
 	int2* jointBinRank;	 // [jointCount]
 	int* binJointList;	 // [binCount * binCapJoints] joint index, colour-major
+	int* islandFailed;	 // control block: set by the island kernels when they give up (binFail), read by the host
 	int* binFail;		 // set when some bin does not fit its capacities: the grid-barrier kernel takes the step
 
 	// sync + profiling

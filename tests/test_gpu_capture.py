@@ -75,6 +75,29 @@ def test_captured_steps_bit_exact_on_clusters(capture_files, blocks, monkeypatch
 	assert cluster_steps > 0, "the cluster kernel never ran"
 
 
+def test_island_failure_reruns_on_grid_kernel(capture_files, monkeypatch):
+	"""When a bin does not fit its block the island kernels give up and the step is run again on the grid-barrier
+	kernel from the untouched inputs: same bits, one more launch."""
+	monkeypatch.setenv("B2GPU_TEST_TIGHT_BINS", "1")
+	reruns = 0
+	with b2.GpuSolver() as solver:
+		for path in capture_files:
+			cap = b2.Capture(path)
+			desc, result, bufs = cap.make_call(islands=True)
+			solver.step(desc, result)
+			_check(cap, bufs, result)
+			if solver.island_plan()[0] > 0 and result.gridBarriers > 0:
+				reruns += 1
+				assert result.kernelLaunches == 3
+			# and through the split-phase API (fresh buffers: the step above wrote its results into the inputs)
+			desc, result, bufs = cap.make_call(islands=True)
+			solver.upload(desc)
+			solver.run(result)
+			solver.download(desc, result)
+			_check(cap, bufs, result)
+	assert reruns > 0, "the rerun path never ran"
+
+
 def test_split_phase_is_repeatable(solver, capture_files):
 	"""Upload once, Run twice (inputs stay pristine on the device), Download: same bits as the one-shot step."""
 	solver.set_mode(0)
