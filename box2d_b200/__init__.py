@@ -143,8 +143,6 @@ def solver_lib() -> ctypes.CDLL:
 		fn = getattr(lib, name)
 		fn.restype = ctypes.c_int
 		fn.argtypes = [ctypes.c_void_p]
-	lib.b2GpuSolverFlushPacked.restype = ctypes.c_int
-	lib.b2GpuSolverFlushPacked.argtypes = [ctypes.c_void_p, ctypes.c_int]
 	for name in ("b2GpuSolverPackRange", "b2GpuSolverUnpackRange"):
 		fn = getattr(lib, name)
 		fn.restype = None
@@ -162,6 +160,10 @@ def solver_lib() -> ctypes.CDLL:
 	lib.b2GpuGetVersion.restype = ctypes.c_int
 	lib.b2GpuSolverGetLaunchCount.restype = ctypes.c_uint64
 	lib.b2GpuSolverGetLaunchCount.argtypes = [ctypes.c_void_p]
+	lib.b2GpuSolverPackWork.restype = ctypes.c_int
+	lib.b2GpuSolverPackWork.argtypes = [ctypes.c_void_p, ctypes.c_int]
+	lib.b2GpuSolverUnpackWork.restype = ctypes.c_int
+	lib.b2GpuSolverUnpackWork.argtypes = [ctypes.c_void_p, ctypes.c_int]
 	lib.b2GpuSolverGetIslandPlan.restype = ctypes.c_int
 	lib.b2GpuSolverGetIslandPlan.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
 	_solver_lib = lib

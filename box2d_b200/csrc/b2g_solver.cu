@@ -18,7 +18,9 @@
 #include <cpuid.h>
 #endif
 
+#include <atomic>
 #include <chrono>
+#include <memory>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -370,7 +372,7 @@ struct b2GpuSolver
 
 	// arena layouts, in float4 units
 	size_t inStates = 0, inBody = 0, inWire = 0, inJoints = 0, inBins = 0, inTotal = 0;
-	size_t sentQuads = 0; // prefix of the input arena already enqueued for upload (b2GpuSolverFlushPacked)
+	size_t sentQuads = 0; // prefix of the input arena already enqueued for upload (b2gPumpUploads)
 	size_t outStates = 0, outImpulses = 0, outJoints = 0, outBits = 0, outTotal = 0;
 
 	// the step in flight
@@ -394,6 +396,27 @@ struct b2GpuSolver
 	int lastLaunches = 0;
 	float lastKernelMs = 0.0f;
 	std::chrono::steady_clock::time_point tBegin, tSubmit, tWaited;
+
+	// pipelined host passes (b2GpuSolverPackWork / b2GpuSolverUnpackWork): the items are dealt out in blocks, claimed in
+	// increasing order; one caller (the pump) moves the finished prefix over PCIe while the others keep packing, and
+	// publishes how much of the output arena has arrived while the others unpack behind it
+	std::atomic<int> workNext{ 0 };
+	int workBlocks = 0;
+	int workItems = 0;
+	std::unique_ptr<std::atomic<unsigned char>[]> workDone;
+	size_t workDoneCapacity = 0;
+	int pumpPrefix = 0; // pump only: blocks [0, pumpPrefix) are packed
+	std::atomic<size_t> arrivedQuads{ 0 };
+	std::atomic<int> workFailed{ 0 };
+	std::vector<cudaEvent_t> chunkEvents;
+	std::vector<size_t> chunkEnd;
+	int chunkCount = 0;
+	int chunkNext = 0; // pump only
+	cudaEvent_t evControl = nullptr;
+	bool trace = false; // B2GPU_TRACE=1: print the timeline of the pipelined transfers at EndStep (stderr)
+	std::vector<std::pair<float, size_t>> traceSends, traceArrivals;
+	float traceBegun = 0.0f, traceSubmit = 0.0f, traceControl = 0.0f;
+	bool controlSeen = false;
 };
 
 static int b2gRoundUp32( int n )
@@ -494,6 +517,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		}
 		s->islandSmemBudget = (size_t)dynamicMax;
 		// clusters of 2, 4, 8, 16 blocks with the same carve-up: how many can be resident at once
+		const char* traceEnv = getenv( "B2GPU_TRACE" );
+		s->trace = traceEnv != nullptr && atoi( traceEnv ) != 0;
 		const char* tightEnv = getenv( "B2GPU_TEST_TIGHT_BINS" );
 		s->testTightBins = tightEnv != nullptr && atoi( tightEnv ) != 0;
 		const char* forceEnv = getenv( "B2GPU_CLUSTER_FORCE" );
@@ -531,6 +556,7 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 	ok = ok && cudaEventCreate( &s->evStart ) == cudaSuccess;
 	ok = ok && cudaEventCreate( &s->evStop ) == cudaSuccess;
 	ok = ok && cudaEventCreate( &s->evUpload ) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags( &s->evControl, cudaEventDisableTiming ) == cudaSuccess;
 	ok = ok && cudaMalloc( &s->control, sizeof( ControlBlock ) ) == cudaSuccess;
 	ok = ok && cudaHostAlloc( &s->hControl, sizeof( ControlBlock ), cudaHostAllocDefault ) == cudaSuccess;
 	if ( !ok )
@@ -581,12 +607,16 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	{
 		cudaFreeHost( s->hControl );
 	}
-	for ( cudaEvent_t ev : { s->evStart, s->evStop, s->evUpload } )
+	for ( cudaEvent_t ev : { s->evStart, s->evStop, s->evUpload, s->evControl } )
 	{
 		if ( ev != nullptr )
 		{
 			cudaEventDestroy( ev );
 		}
+	}
+	for ( cudaEvent_t ev : s->chunkEvents )
+	{
+		cudaEventDestroy( ev );
 	}
 	if ( s->stream != nullptr )
 	{
@@ -855,6 +885,34 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	return 0;
 }
 
+// ---- blocks of host work --------------------------------------------------------------------------------------------
+constexpr int kWorkBlockItems = 512;
+constexpr size_t kTransferQuads = 64 * 1024; // 1 MiB: granularity of the pipelined uploads
+constexpr size_t kDownloadQuads = 32 * 1024; // 512 KiB: the unpack pass runs this far behind the download
+
+static int b2gBlocksFor( int itemCount )
+{
+	return ( itemCount + kWorkBlockItems - 1 ) / kWorkBlockItems;
+}
+
+static void b2gResetWork( b2GpuSolver* s, int itemCount, int blockCount )
+{
+	s->workItems = itemCount;
+	s->workBlocks = blockCount;
+	if ( (size_t)s->workBlocks > s->workDoneCapacity )
+	{
+		s->workDoneCapacity = (size_t)s->workBlocks * 2 + 64;
+		s->workDone.reset( new std::atomic<unsigned char>[s->workDoneCapacity] );
+	}
+	for ( int i = 0; i < s->workBlocks; ++i )
+	{
+		s->workDone[i].store( 0, std::memory_order_relaxed );
+	}
+	s->pumpPrefix = 0;
+	s->workFailed.store( 0, std::memory_order_relaxed );
+	s->workNext.store( 0, std::memory_order_release );
+}
+
 // ---- phase 1: layout --------------------------------------------------------------------------------------------
 static bool b2gSameStepParams( const b2GpuStepDesc& a, const b2GpuStepDesc& b )
 {
@@ -1010,14 +1068,16 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 
 	size_t nb = (size_t)bodies;
 	const size_t jointQuads = b2g::kJointStride / 16;
-	// input arena: [states 2/body][packed sims 2/body][bins 1/4 body][contacts 7/slot][joints 16/joint]; item order
-	// (bodies, contacts, joints) is address order, so a prefix of packed items is a prefix of the arena
-	s->inStates = 0;
+	// input arena: [contacts 7/slot][joints 16/joint][states 2/body][packed sims 2/body][bins 1/4 body].  The pipelined
+	// pack pass (b2GpuSolverPackWork) works through it in address order -- constraints first, the three body regions
+	// last -- so that a finished prefix of its blocks is a prefix of the arena and the upload can start with the first
+	// megabyte of contacts.
+	s->inWire = 0;
+	s->inJoints = s->inWire + (size_t)b2g::WR_COUNT * slot;
+	s->inStates = s->inJoints + jointQuads * joint;
 	s->inBody = s->inStates + 2 * nb;
 	s->inBins = s->inBody + 2 * nb;
-	s->inWire = s->inBins + ( nb + 3 ) / 4;
-	s->inJoints = s->inWire + (size_t)b2g::WR_COUNT * slot;
-	s->inTotal = s->inJoints + jointQuads * joint;
+	s->inTotal = s->inBins + ( nb + 3 ) / 4;
 	s->sentQuads = 0;
 	// output arena: [states 2/body][impulse records][joints 16/joint][joint event bits]
 	size_t impulseQuads = ( (size_t)slot * b2g::kImpulseFloats + 3 ) / 4;
@@ -1083,11 +1143,16 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 		}
 	}
 
+	_mm_sfence();
+
 	if ( b2gPlanIslands( s ) != 0 )
 	{
 		return 1;
 	}
 
+	// pack blocks: the constraints' blocks, then the bodies' blocks (b2gPackBlockRange)
+	b2gResetWork( s, P.bodyCount + s->contactTotal + s->jointTotal, b2gBlocksFor( s->contactTotal + s->jointTotal ) + b2gBlocksFor( P.bodyCount ) );
+	s->traceBegun = std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count();
 	s->begun = true;
 	return 0;
 }
@@ -1265,27 +1330,46 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 
 // ---- phase 3: H2D + kernels + D2H, all asynchronous on the solver's stream -------------------------------------------
 // quads of the input arena that hold items [0, itemEnd) (bodies, then contacts in slot order, then joints)
-static size_t b2gArenaPrefix( const b2GpuSolver* s, int itemEnd )
+// The pack pass claims blocks in ARENA order: first the blocks of the constraints (items [bodyCount, itemCount)), then
+// the blocks of the bodies (items [0, bodyCount)).
+static void b2gPackBlockRange( const b2GpuSolver* s, int block, int* begin, int* end )
 {
 	int bodyCount = s->params.bodyCount;
-	if ( itemEnd < bodyCount )
+	int restItems = s->workItems - bodyCount;
+	int restBlocks = ( restItems + kWorkBlockItems - 1 ) / kWorkBlockItems;
+	if ( block < restBlocks )
 	{
-		return 0; // the three body regions are interleaved by region, not by body: wait for all bodies
+		*begin = bodyCount + block * kWorkBlockItems;
+		*end = *begin + kWorkBlockItems < s->workItems ? *begin + kWorkBlockItems : s->workItems;
 	}
-	int flat = itemEnd - bodyCount;
-	if ( flat <= 0 )
+	else
 	{
-		return s->inWire;
+		*begin = ( block - restBlocks ) * kWorkBlockItems;
+		*end = *begin + kWorkBlockItems < bodyCount ? *begin + kWorkBlockItems : bodyCount;
 	}
+}
+
+// quads of the input arena that are complete once the first `blocksDone` blocks (in claim order) are packed
+static size_t b2gPackedPrefix( const b2GpuSolver* s, int blocksDone )
+{
+	int restItems = s->contactTotal + s->jointTotal;
+	int restBlocks = ( restItems + kWorkBlockItems - 1 ) / kWorkBlockItems;
+	if ( blocksDone >= s->workBlocks )
+	{
+		return s->inTotal;
+	}
+	if ( blocksDone >= restBlocks )
+	{
+		return s->inStates; // the three body regions are interleaved by region, not by body: wait for all bodies
+	}
+	int flat = blocksDone * kWorkBlockItems; // constraints [0, flat) are packed, flat < restItems
 	if ( flat < s->contactTotal )
 	{
 		int k = b2gFindSegment( s->contactStart, flat );
 		int slot = s->contactSegs[k].slotStart + ( flat - s->contactStart[k] );
 		return s->inWire + (size_t)slot * b2g::WR_COUNT;
 	}
-	int joints = flat - s->contactTotal;
-	joints = joints < s->jointTotal ? joints : s->jointTotal;
-	return s->inJoints + (size_t)joints * ( b2g::kJointStride / 16 );
+	return s->inJoints + (size_t)( flat - s->contactTotal ) * ( b2g::kJointStride / 16 );
 }
 
 static int b2gSendArena( b2GpuSolver* s, size_t uptoQuads )
@@ -1296,22 +1380,15 @@ static int b2gSendArena( b2GpuSolver* s, size_t uptoQuads )
 	}
 	if ( uptoQuads > s->sentQuads )
 	{
+		if ( s->trace )
+		{
+			s->traceSends.emplace_back( std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(), uptoQuads );
+		}
 		B2G_CUDA( cudaMemcpyAsync( s->wireAll.ptr + s->sentQuads, s->hWire.ptr + s->sentQuads,
 								   ( uptoQuads - s->sentQuads ) * sizeof( float4 ), cudaMemcpyHostToDevice, s->stream ) );
 		s->sentQuads = uptoQuads;
 	}
 	return 0;
-}
-
-// Start uploading what has been packed so far (items [0, itemEnd) must be complete): overlaps the PCIe transfer with
-// the packing of the remaining items.
-extern "C" int b2GpuSolverFlushPacked( b2GpuSolver* s, int itemEnd )
-{
-	if ( s == nullptr || !s->begun )
-	{
-		return b2gFailMsg( "b2GpuSolverFlushPacked: no step begun" );
-	}
-	return b2gSendArena( s, b2gArenaPrefix( s, itemEnd ) );
 }
 
 static int b2gEnqueueUpload( b2GpuSolver* s )
@@ -1522,14 +1599,33 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 
 static int b2gEnqueueDownload( b2GpuSolver* s )
 {
+	// the control block first (it says whether the island kernels gave up), then the output arena in chunks with an
+	// event each, so that unpacking can start behind the transfer
 	cudaStream_t st = s->stream;
-	size_t bytes = s->outTotal * sizeof( float4 );
-	if ( bytes > 0 )
-	{
-		B2G_CUDA( cudaMemcpyAsync( s->hOut.ptr, s->outAll.ptr, bytes, cudaMemcpyDeviceToHost, st ) );
-	}
 	B2G_CUDA( cudaMemcpyAsync( s->hControl, s->control, sizeof( ControlBlock ), cudaMemcpyDeviceToHost, st ) );
-	s->lastD2H = bytes + sizeof( ControlBlock );
+	B2G_CUDA( cudaEventRecord( s->evControl, st ) );
+	s->controlSeen = false;
+	size_t total = s->outTotal;
+	int chunks = (int)( ( total + kDownloadQuads - 1 ) / kDownloadQuads );
+	while ( (int)s->chunkEvents.size() < chunks )
+	{
+		cudaEvent_t ev = nullptr;
+		B2G_CUDA( cudaEventCreateWithFlags( &ev, cudaEventDisableTiming ) );
+		s->chunkEvents.push_back( ev );
+	}
+	s->chunkEnd.resize( (size_t)chunks );
+	for ( int i = 0; i < chunks; ++i )
+	{
+		size_t begin = (size_t)i * kDownloadQuads;
+		size_t end = begin + kDownloadQuads < total ? begin + kDownloadQuads : total;
+		B2G_CUDA( cudaMemcpyAsync( s->hOut.ptr + begin, s->outAll.ptr + begin, ( end - begin ) * sizeof( float4 ), cudaMemcpyDeviceToHost, st ) );
+		B2G_CUDA( cudaEventRecord( s->chunkEvents[(size_t)i], st ) );
+		s->chunkEnd[(size_t)i] = end;
+	}
+	s->chunkCount = chunks;
+	s->chunkNext = 0;
+	s->arrivedQuads.store( 0, std::memory_order_release );
+	s->lastD2H = total * sizeof( float4 ) + sizeof( ControlBlock );
 	return 0;
 }
 
@@ -1540,10 +1636,12 @@ extern "C" int b2GpuSolverSubmit( b2GpuSolver* s )
 		return b2gFailMsg( "b2GpuSolverSubmit: no step begun" );
 	}
 	s->tSubmit = std::chrono::steady_clock::now();
+	s->traceSubmit = std::chrono::duration<float, std::micro>( s->tSubmit - s->tBegin ).count();
 	if ( b2gEnqueueUpload( s ) != 0 || b2gEnqueueRun( s ) != 0 || b2gEnqueueDownload( s ) != 0 )
 	{
 		return 1;
 	}
+	b2gResetWork( s, b2GpuSolverGetUnpackItemCount( s ), b2gBlocksFor( b2GpuSolverGetUnpackItemCount( s ) ) );
 	return 0;
 }
 
@@ -1558,6 +1656,9 @@ extern "C" int b2GpuSolverWait( b2GpuSolver* s )
 	{
 		return 1;
 	}
+	s->controlSeen = true;
+	s->chunkNext = s->chunkCount;
+	s->arrivedQuads.store( s->outTotal, std::memory_order_release );
 	s->tWaited = std::chrono::steady_clock::now();
 	if ( s->ran )
 	{
@@ -1730,6 +1831,200 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 	}
 }
 
+// ---- pipelined host passes ------------------------------------------------------------------------------------------------
+// b2GpuSolverPackWork / b2GpuSolverUnpackWork are called by ANY number of host threads at the same time (the world's
+// workers); each call claims blocks of items until none are left.  Exactly one caller passes pump = 1: besides packing
+// it starts the upload of every finished prefix of the arena (PCIe runs behind the packing instead of after it), and
+// besides unpacking it watches the download events and tells the others how much of the output has arrived (unpacking
+// runs behind the download).
+static int b2gPumpUploads( b2GpuSolver* s, bool everything )
+{
+	while ( s->pumpPrefix < s->workBlocks && s->workDone[s->pumpPrefix].load( std::memory_order_acquire ) != 0 )
+	{
+		s->pumpPrefix += 1;
+	}
+	bool complete = s->pumpPrefix == s->workBlocks;
+	size_t ready = b2gPackedPrefix( s, s->pumpPrefix );
+	if ( ready > s->sentQuads && ( ( complete && everything ) || ready - s->sentQuads >= kTransferQuads ) )
+	{
+		return b2gSendArena( s, ready );
+	}
+	return 0;
+}
+
+extern "C" int b2GpuSolverPackWork( b2GpuSolver* s, int pump )
+{
+	if ( s == nullptr || !s->begun )
+	{
+		return b2gFailMsg( "b2GpuSolverPackWork: no step begun" );
+	}
+	if ( pump != 0 )
+	{
+		cudaSetDevice( s->device );
+	}
+	for ( ;; )
+	{
+		if ( pump != 0 && b2gPumpUploads( s, false ) != 0 )
+		{
+			s->workFailed.store( 1 );
+			return 1;
+		}
+		int block = s->workNext.fetch_add( 1, std::memory_order_acq_rel );
+		if ( block >= s->workBlocks )
+		{
+			break;
+		}
+		int begin, end;
+		b2gPackBlockRange( s, block, &begin, &end );
+		b2GpuSolverPackRange( s, begin, end ); // ends with an sfence: the streaming stores are visible to the DMA engine
+		s->workDone[block].store( 1, std::memory_order_release );
+	}
+	if ( pump != 0 )
+	{
+		// the others may still be packing the blocks they claimed
+		while ( s->pumpPrefix < s->workBlocks )
+		{
+			if ( b2gPumpUploads( s, false ) != 0 )
+			{
+				return 1;
+			}
+			_mm_pause();
+		}
+		return b2gPumpUploads( s, true );
+	}
+	return 0;
+}
+
+// quads of the output arena that must have arrived before items [0, itemEnd) can be unpacked
+static size_t b2gOutPrefix( const b2GpuSolver* s, int itemEnd )
+{
+	int bodyCount = s->params.bodyCount;
+	if ( itemEnd <= bodyCount )
+	{
+		return s->outStates + 2 * (size_t)itemEnd;
+	}
+	int flat = itemEnd - bodyCount;
+	if ( flat <= s->contactTotal )
+	{
+		// the record of the last contact of the range
+		int k = b2gFindSegment( s->contactStart, flat - 1 );
+		int slot = s->contactSegs[k].slotStart + ( flat - 1 - s->contactStart[k] );
+		return s->outImpulses + ( (size_t)( slot + 1 ) * b2g::kImpulseFloats + 3 ) / 4;
+	}
+	int joints = flat - s->contactTotal;
+	joints = joints < s->jointTotal ? joints : s->jointTotal;
+	return s->outJoints + (size_t)joints * ( b2g::kJointStride / 16 );
+}
+
+static int b2gPumpDownloads( b2GpuSolver* s )
+{
+	if ( !s->controlSeen )
+	{
+		// kernels done?  (the control block is the first thing that comes back)
+		cudaError_t err = cudaEventQuery( s->evControl );
+		if ( err == cudaErrorNotReady )
+		{
+			return 0;
+		}
+		if ( err != cudaSuccess )
+		{
+			return b2gFail( "device solve", err );
+		}
+		if ( s->ran && s->islandMode && s->hControl->islandFailed != 0 )
+		{
+			// rare: rerun on the grid-barrier kernel; that re-enqueues the downloads and waits for them
+			B2G_CUDA( cudaStreamSynchronize( s->stream ) );
+			if ( b2gRerunIfIslandsFailed( s, true ) != 0 )
+			{
+				return 1;
+			}
+			s->chunkNext = s->chunkCount;
+			s->arrivedQuads.store( s->outTotal, std::memory_order_release );
+		}
+		s->controlSeen = true;
+		s->tWaited = std::chrono::steady_clock::now();
+		s->traceControl = std::chrono::duration<float, std::micro>( s->tWaited - s->tBegin ).count();
+	}
+	while ( s->chunkNext < s->chunkCount )
+	{
+		cudaError_t err = cudaEventQuery( s->chunkEvents[(size_t)s->chunkNext] );
+		if ( err == cudaErrorNotReady )
+		{
+			break;
+		}
+		if ( err != cudaSuccess )
+		{
+			return b2gFail( "download", err );
+		}
+		s->arrivedQuads.store( s->chunkEnd[(size_t)s->chunkNext], std::memory_order_release );
+		if ( s->trace )
+		{
+			s->traceArrivals.emplace_back( std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(),
+										   s->chunkEnd[(size_t)s->chunkNext] );
+		}
+		s->chunkNext += 1;
+	}
+	return 0;
+}
+
+extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
+{
+	if ( s == nullptr || !s->begun )
+	{
+		return b2gFailMsg( "b2GpuSolverUnpackWork: no step begun" );
+	}
+	if ( pump != 0 )
+	{
+		cudaSetDevice( s->device );
+	}
+	for ( ;; )
+	{
+		int block = s->workNext.fetch_add( 1, std::memory_order_acq_rel );
+		if ( block >= s->workBlocks )
+		{
+			break;
+		}
+		int begin = block * kWorkBlockItems;
+		int end = begin + kWorkBlockItems < s->workItems ? begin + kWorkBlockItems : s->workItems;
+		size_t need = b2gOutPrefix( s, end );
+		while ( s->arrivedQuads.load( std::memory_order_acquire ) < need )
+		{
+			if ( pump != 0 )
+			{
+				if ( b2gPumpDownloads( s ) != 0 )
+				{
+					s->workFailed.store( 1 );
+					return 1;
+				}
+			}
+			else if ( s->workFailed.load( std::memory_order_relaxed ) != 0 )
+			{
+				return 1;
+			}
+			_mm_pause();
+		}
+		b2GpuSolverUnpackRange( s, begin, end );
+	}
+	if ( pump != 0 )
+	{
+		// the tail of the arena (joint event bits) is consumed by EndStep
+		while ( !s->controlSeen || s->chunkNext < s->chunkCount )
+		{
+			if ( b2gPumpDownloads( s ) != 0 )
+			{
+				s->workFailed.store( 1 );
+				return 1;
+			}
+			_mm_pause();
+		}
+		if ( s->ran )
+		{
+			B2G_CUDA( cudaEventElapsedTime( &s->lastKernelMs, s->evStart, s->evStop ) );
+		}
+	}
+	return 0;
+}
+
 static void b2gFillTimers( b2GpuSolver* s, b2GpuStepResult* r )
 {
 	// stage split from the in-kernel cycle counters, scaled to the CUDA-event kernel time
@@ -1787,6 +2082,23 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 		}
 		b2gFlushLines( bits, (size_t)s->params.jointWords * sizeof( uint32_t ) );
 	}
+	if ( s->trace )
+	{
+		fprintf( stderr, "[b2gpu] in %zu quads, out %zu quads | begun %.0f | sends (us: upto):", s->inTotal, s->outTotal, s->traceBegun );
+		for ( auto& e : s->traceSends )
+		{
+			fprintf( stderr, " %.0f:%zu", e.first, e.second );
+		}
+		fprintf( stderr, " | submit %.0f | kernels done %.0f | arrivals:", s->traceSubmit, s->traceControl );
+		for ( auto& e : s->traceArrivals )
+		{
+			fprintf( stderr, " %.0f:%zu", e.first, e.second );
+		}
+		fprintf( stderr, " | end %.0f | kernel %.0f us\n",
+				 std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(), s->lastKernelMs * 1000.0f );
+	}
+	s->traceSends.clear();
+	s->traceArrivals.clear();
 	s->begun = false;
 	return 0;
 }
@@ -1800,32 +2112,26 @@ extern "C" int b2GpuSolverEndStep( b2GpuSolver* s, b2GpuStepResult* r )
 // The two host passes of the one-call entry points.  A world stepped through the seam uses the world's own workers
 // (b2ParallelFor); a caller of b2GpuSolverStep / StepBatch has no task system to offer, so large steps are split over
 // a few short-lived threads here (B2GPU_HOST_THREADS overrides the count, 1 = calling thread only).
-static void b2gParallelRanges( b2GpuSolver* s, int itemCount, void ( *fn )( b2GpuSolver*, int, int ) )
+static int b2gWorkWithThreads( b2GpuSolver* s, int ( *work )( b2GpuSolver*, int ) )
 {
 	static const int configured = []() {
 		const char* env = getenv( "B2GPU_HOST_THREADS" );
 		int n = env != nullptr ? atoi( env ) : (int)std::thread::hardware_concurrency();
 		return n < 1 ? 1 : ( n > 32 ? 32 : n );
 	}();
-	int threads = itemCount / 16384;
+	int threads = s->workItems / 16384;
 	threads = threads > configured ? configured : threads;
-	if ( threads <= 1 )
+	std::vector<std::thread> helpers;
+	for ( int t = 1; t < threads; ++t )
 	{
-		fn( s, 0, itemCount );
-		return;
+		helpers.emplace_back( work, s, 0 );
 	}
-	std::vector<std::thread> pool;
-	pool.reserve( (size_t)threads );
-	for ( int t = 0; t < threads; ++t )
-	{
-		int begin = (int)( (long long)itemCount * t / threads );
-		int end = (int)( (long long)itemCount * ( t + 1 ) / threads );
-		pool.emplace_back( fn, s, begin, end );
-	}
-	for ( std::thread& th : pool )
+	int rc = work( s, 1 ); // the calling thread is the pump
+	for ( std::thread& th : helpers )
 	{
 		th.join();
 	}
+	return rc != 0 || s->workFailed.load() != 0 ? 1 : 0;
 }
 
 static int b2gStepAll( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount, b2GpuStepResult* results )
@@ -1834,12 +2140,11 @@ static int b2gStepAll( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCoun
 	{
 		return 1;
 	}
-	b2gParallelRanges( s, b2GpuSolverGetPackItemCount( s ), b2GpuSolverPackRange );
-	if ( b2GpuSolverSubmit( s ) != 0 || b2GpuSolverWait( s ) != 0 )
+	if ( b2gWorkWithThreads( s, b2GpuSolverPackWork ) != 0 || b2GpuSolverSubmit( s ) != 0 ||
+		 b2gWorkWithThreads( s, b2GpuSolverUnpackWork ) != 0 )
 	{
 		return 1;
 	}
-	b2gParallelRanges( s, b2GpuSolverGetUnpackItemCount( s ), b2GpuSolverUnpackRange );
 	return b2gEnd( s, results );
 }
 

@@ -122,23 +122,44 @@ void b2GpuSeam_InstallPinnedAllocator( void )
 	b2SetAllocator( b2GpuHostAlloc, b2GpuHostFree );
 }
 
-typedef struct b2SeamPackRange
+/* The two memory-bound host passes run on the world's own workers: workerCount - 1 tasks go through the world's task
+ * callbacks (the same ones b2ParallelFor uses, src/parallel_for.c:108-132) and claim blocks of items from the device
+ * library; the calling thread works along and pumps the PCIe transfers (b2GpuSolverPackWork / UnpackWork, pump = 1). */
+static void b2SeamPackWorker( void* taskContext )
 {
-	b2GpuSolver* solver;
-	int offset;
-} b2SeamPackRange;
-
-static void b2SeamPackTask( int startIndex, int endIndex, int workerIndex, void* taskContext )
-{
-	(void)workerIndex;
-	b2SeamPackRange* range = taskContext;
-	b2GpuSolverPackRange( range->solver, range->offset + startIndex, range->offset + endIndex );
+	b2GpuSolverPackWork( taskContext, 0 );
 }
 
-static void b2SeamUnpackTask( int startIndex, int endIndex, int workerIndex, void* taskContext )
+static void b2SeamUnpackWorker( void* taskContext )
 {
-	(void)workerIndex;
-	b2GpuSolverUnpackRange( taskContext, startIndex, endIndex );
+	b2GpuSolverUnpackWork( taskContext, 0 );
+}
+
+static void b2SeamWorkOnItems( b2World* world, b2GpuSolver* solver, int itemCount, b2TaskCallback* worker,
+							   int ( *work )( b2GpuSolver*, int ), const char* what )
+{
+	void* handles[B2_MAX_WORKERS];
+	int helperCount = world->workerCount - 1;
+	int useful = itemCount / 2048; /* a helper that wakes up for less than that only costs */
+	helperCount = helperCount < useful ? helperCount : useful;
+	int enqueued = 0;
+	for ( int i = 0; i < helperCount && world->taskCount < B2_MAX_TASKS; ++i )
+	{
+		handles[enqueued++] = world->enqueueTaskFcn( worker, solver, world->userTaskContext );
+		world->taskCount += 1;
+	}
+	int rc = work( solver, 1 );
+	for ( int i = 0; i < enqueued; ++i )
+	{
+		if ( handles[i] != NULL )
+		{
+			world->finishTaskFcn( handles[i], world->userTaskContext );
+		}
+	}
+	if ( rc != 0 )
+	{
+		b2SeamFatal( what );
+	}
 }
 
 /* ---- the seam ------------------------------------------------------------------------------------------- */
@@ -180,33 +201,18 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 	result->hitEventBits = taskContext0->hitEventBitSet.bits;
 	result->jointEventBits = taskContext0->jointStateBitSet.bits;
 
-	// The two memory-bound host passes (wire packing, impulse write-back) run on the world's own workers.
 	if ( b2GpuSolverBeginStep( slot->solver, desc, result ) != 0 )
 	{
 		b2SeamFatal( "b2GpuSolverBeginStep failed" );
 	}
-	// pack in a few chunks and start each chunk's upload as soon as it is packed: PCIe overlaps the packing
-	{
-		int itemCount = b2GpuSolverGetPackItemCount( slot->solver );
-		int chunkCount = itemCount > 400000 ? 4 : 1; // measured: below that the extra parallel-for wake-ups cost more than the overlap wins
-		int done = 0;
-		for ( int chunk = 0; chunk < chunkCount; ++chunk )
-		{
-			int end = chunk + 1 == chunkCount ? itemCount : (int)( (long long)itemCount * ( chunk + 1 ) / chunkCount );
-			b2SeamPackRange range = { slot->solver, done };
-			b2ParallelFor( world, b2SeamPackTask, end - done, 512, &range );
-			done = end;
-			if ( chunk + 1 < chunkCount )
-			{
-				b2GpuSolverFlushPacked( slot->solver, done );
-			}
-		}
-	}
-	if ( b2GpuSolverSubmit( slot->solver ) != 0 || b2GpuSolverWait( slot->solver ) != 0 )
+	int itemCount = b2GpuSolverGetPackItemCount( slot->solver );
+	b2SeamWorkOnItems( world, slot->solver, itemCount, b2SeamPackWorker, b2GpuSolverPackWork, "packing / upload failed" );
+	if ( b2GpuSolverSubmit( slot->solver ) != 0 )
 	{
 		b2SeamFatal( "device solve failed" );
 	}
-	b2ParallelFor( world, b2SeamUnpackTask, b2GpuSolverGetUnpackItemCount( slot->solver ), 512, slot->solver );
+	// the helpers are woken while the kernels run and unpack behind the download
+	b2SeamWorkOnItems( world, slot->solver, itemCount, b2SeamUnpackWorker, b2GpuSolverUnpackWork, "device solve / download failed" );
 	if ( b2GpuSolverEndStep( slot->solver, result ) != 0 )
 	{
 		b2SeamFatal( "b2GpuSolverEndStep failed" );

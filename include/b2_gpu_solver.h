@@ -181,13 +181,21 @@ B2GPU_API int b2GpuSolverDownload( b2GpuSolver* solver, const b2GpuStepDesc* des
 B2GPU_API int b2GpuSolverBeginStep( b2GpuSolver* solver, const b2GpuStepDesc* desc, b2GpuStepResult* result );
 B2GPU_API int b2GpuSolverGetPackItemCount( const b2GpuSolver* solver );
 B2GPU_API void b2GpuSolverPackRange( b2GpuSolver* solver, int begin, int end );
-/* optional: start the upload of items [0, itemEnd) (all packed) while the rest is still being packed */
-B2GPU_API int b2GpuSolverFlushPacked( b2GpuSolver* solver, int itemEnd );
 B2GPU_API int b2GpuSolverSubmit( b2GpuSolver* solver );
 B2GPU_API int b2GpuSolverWait( b2GpuSolver* solver );
 B2GPU_API int b2GpuSolverGetUnpackItemCount( const b2GpuSolver* solver );
 B2GPU_API void b2GpuSolverUnpackRange( b2GpuSolver* solver, int begin, int end );
 B2GPU_API int b2GpuSolverEndStep( b2GpuSolver* solver, b2GpuStepResult* result );
+
+/* Pipelined form of the two host passes.  After Begin, every participating host thread calls PackWork once; a call
+ * claims blocks of items until none are left.  Exactly one of the callers passes pump = 1: it also starts the upload
+ * of every finished prefix of the wire buffer, so PCIe runs behind the packing instead of after it.  When all calls
+ * have returned the caller of pump = 1 calls Submit (kernels + chunked download), then every participating thread
+ * calls UnpackWork: blocks are unpacked as soon as their part of the download has arrived (the pump = 1 caller watches
+ * the download events and handles the island-kernel fallback), so unpacking runs behind the download.  UnpackWork
+ * replaces Wait + UnpackRange.  Both return 0 on success. */
+B2GPU_API int b2GpuSolverPackWork( b2GpuSolver* solver, int pump );
+B2GPU_API int b2GpuSolverUnpackWork( b2GpuSolver* solver, int pump );
 
 /* Batch of independent worlds (the RL-style workload): one launch solves all of them, one thread block
  * per world with the world's bodies and constraints resident in shared memory for all sub-steps.  Each
