@@ -395,6 +395,8 @@ struct b2GpuSolver
 	uint64_t lastD2H = 0;
 	int lastLaunches = 0;
 	float lastKernelMs = 0.0f;
+	std::vector<std::vector<b2gContactSeg>> scratchContactSegs;
+	std::vector<std::vector<b2gJointSeg>> scratchJointSegs;
 	std::chrono::steady_clock::time_point tBegin, tSubmit, tWaited;
 
 	// pipelined host passes (b2GpuSolverPackWork / b2GpuSolverUnpackWork): the items are dealt out in blocks, claimed in
@@ -416,6 +418,7 @@ struct b2GpuSolver
 	bool trace = false; // B2GPU_TRACE=1: print the timeline of the pipelined transfers at EndStep (stderr)
 	std::vector<std::pair<float, size_t>> traceSends, traceArrivals;
 	float traceBegun = 0.0f, traceSubmit = 0.0f, traceControl = 0.0f;
+	float traceMarks[8] = { 0 };
 	bool controlSeen = false;
 };
 
@@ -926,6 +929,7 @@ static bool b2gSameStepParams( const b2GpuStepDesc& a, const b2GpuStepDesc& b )
 		   a.enableWarmStarting == b.enableWarmStarting && a.enableContactSoftening == b.enableContactSoftening;
 }
 
+#define B2G_MARK( i ) s->traceMarks[i] = std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count()
 static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount, b2GpuStepResult* results )
 {
 	if ( s == nullptr || descs == nullptr || worldCount <= 0 )
@@ -937,7 +941,6 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	s->begun = false;
 	s->uploaded = false;
 	s->ran = false;
-	s->descs.assign( descs, descs + worldCount );
 	s->results = results;
 	const b2GpuStepDesc* d = descs;
 
@@ -956,6 +959,7 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 		maxColors = dw.activeColorCount > maxColors ? dw.activeColorCount : maxColors;
 	}
 
+	B2G_MARK( 0 );
 	b2g::StepParams& P = s->params;
 	memset( &P, 0, sizeof( P ) );
 	P.dt = d->dt;
@@ -1005,11 +1009,59 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 
 	// constraint segments in slot order; every colour slot starts on a multiple of 32 slots, every segment on a multiple
 	// of 4 (the SIMD groups of the reference are per colour array); the gaps are dead slots (pointCount 0)
+	B2G_MARK( 1 );
 	s->contactSegs.clear();
 	s->jointSegs.clear();
 	s->contactStart.assign( 1, 0 );
 	s->jointStart.assign( 1, 0 );
 	int slotCount = maxColors + 1;
+	// one pass over the descriptors (they are large and there may be thousands): per colour slot, the worlds that
+	// bring a segment; then the segments are laid out slot by slot
+	{
+		std::vector<std::vector<b2gContactSeg>>& contactsOfSlot = s->scratchContactSegs;
+		std::vector<std::vector<b2gJointSeg>>& jointsOfSlot = s->scratchJointSegs;
+		contactsOfSlot.resize( (size_t)b2g::kMaxColors + 1 );
+		jointsOfSlot.resize( (size_t)b2g::kMaxColors + 1 );
+		for ( int c = 0; c < slotCount; ++c )
+		{
+			contactsOfSlot[(size_t)c].clear();
+			jointsOfSlot[(size_t)c].clear();
+		}
+		for ( int w = 0; w < worldCount; ++w )
+		{
+			const b2GpuStepDesc& dw = descs[w];
+			for ( int c = 0; c <= dw.activeColorCount; ++c )
+			{
+				bool isOverflow = c == dw.activeColorCount;
+				const b2GpuColorDesc& color = isOverflow ? dw.overflow : dw.colors[c];
+				int slotIndex = isOverflow ? slotCount - 1 : c;
+				if ( color.contactCount < 0 || color.jointCount < 0 )
+				{
+					return b2gFailMsg( "b2GpuSolverBeginStep: negative count" );
+				}
+				if ( color.contactCount > 0 )
+				{
+					b2gContactSeg seg;
+					seg.sims = static_cast<uint8_t*>( color.contactSims );
+					seg.count = color.contactCount;
+					seg.slotStart = 0;
+					seg.world = w;
+					seg.wide = !isOverflow;
+					seg.colorIndex = color.colorIndex;
+					contactsOfSlot[(size_t)slotIndex].push_back( seg );
+				}
+				if ( color.jointCount > 0 )
+				{
+					b2gJointSeg seg;
+					seg.sims = static_cast<uint8_t*>( color.jointSims );
+					seg.count = color.jointCount;
+					seg.jointStart = 0;
+					seg.world = w;
+					jointsOfSlot[(size_t)slotIndex].push_back( seg );
+				}
+			}
+		}
+	}
 	int slot = 0, joint = 0, flat = 0;
 	for ( int c = 0; c < slotCount; ++c )
 	{
@@ -1017,48 +1069,26 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 		b2g::ColorRange& range = isOverflow ? P.overflow : P.colors[c];
 		range.contactStart = slot;
 		range.jointStart = joint;
-		for ( int w = 0; w < worldCount; ++w )
+		for ( b2gContactSeg seg : s->scratchContactSegs[(size_t)c] )
 		{
-			const b2GpuStepDesc& dw = descs[w];
-			if ( !isOverflow && c >= dw.activeColorCount )
-			{
-				continue;
-			}
-			const b2GpuColorDesc& color = isOverflow ? dw.overflow : dw.colors[c];
-			if ( color.contactCount < 0 || color.jointCount < 0 )
-			{
-				return b2gFailMsg( "b2GpuSolverBeginStep: negative count" );
-			}
-			if ( color.contactCount > 0 )
-			{
-				b2gContactSeg seg;
-				seg.sims = static_cast<uint8_t*>( color.contactSims );
-				seg.count = color.contactCount;
-				seg.slotStart = ( slot + 3 ) & ~3;
-				seg.world = w;
-				seg.wide = !isOverflow;
-				seg.colorIndex = color.colorIndex;
-				s->contactSegs.push_back( seg );
-				slot = seg.slotStart + seg.count;
-				flat += seg.count;
-				s->contactStart.push_back( flat );
-			}
-			if ( color.jointCount > 0 )
-			{
-				b2gJointSeg seg;
-				seg.sims = static_cast<uint8_t*>( color.jointSims );
-				seg.count = color.jointCount;
-				seg.jointStart = joint;
-				seg.world = w;
-				s->jointSegs.push_back( seg );
-				joint += seg.count;
-				s->jointStart.push_back( joint );
-			}
+			seg.slotStart = ( slot + 3 ) & ~3;
+			s->contactSegs.push_back( seg );
+			slot = seg.slotStart + seg.count;
+			flat += seg.count;
+			s->contactStart.push_back( flat );
+		}
+		for ( b2gJointSeg seg : s->scratchJointSegs[(size_t)c] )
+		{
+			seg.jointStart = joint;
+			s->jointSegs.push_back( seg );
+			joint += seg.count;
+			s->jointStart.push_back( joint );
 		}
 		range.contactCount = slot - range.contactStart;
 		range.jointCount = joint - range.jointStart;
 		slot = b2gRoundUp32( slot );
 	}
+	B2G_MARK( 2 );
 	s->contactTotal = flat;
 	s->jointTotal = joint;
 	s->overflowContacts = P.overflow.contactCount;
@@ -1126,24 +1156,9 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	P.barrier = s->control->barrier;
 	P.stageCycles = s->control->stageCycles;
 
-	// dead slots between segments: a zero head (pointCount 0) is all the kernels look at
-	{
-		float4* wire = s->hWire.ptr + s->inWire;
-		size_t segmentCount = s->contactSegs.size();
-		for ( size_t k = 0; k < segmentCount; ++k )
-		{
-			int end = s->contactSegs[k].slotStart + s->contactSegs[k].count;
-			int next = k + 1 < segmentCount ? s->contactSegs[k + 1].slotStart : end;
-			int limit = ( end + 3 ) & ~3;
-			next = next < limit ? next : limit;
-			for ( int dead = end; dead < next; ++dead )
-			{
-				_mm_stream_ps( reinterpret_cast<float*>( wire + (size_t)dead * b2g::WR_COUNT + b2g::WR_HEAD ), _mm_setzero_ps() );
-			}
-		}
-	}
-
+	B2G_MARK( 3 );
 	_mm_sfence();
+	B2G_MARK( 4 );
 
 	if ( b2gPlanIslands( s ) != 0 )
 	{
@@ -1285,6 +1300,19 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 							b2gRdF( p1, B2L_MP_ANCHOR_B ), b2gRdF( p1, B2L_MP_ANCHOR_B + 4 ) );
 				b2gStream4( w + b2g::WR_IMPULSE, b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ),
 							b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ) );
+			}
+			if ( localEnd == seg.count )
+			{
+				// dead slots between this segment and the next (segments start on multiples of 4 slots): a zero head
+				// (pointCount 0) is all the kernels look at
+				int segEnd = seg.slotStart + seg.count;
+				int next = (size_t)k + 1 < s->contactSegs.size() ? s->contactSegs[(size_t)k + 1].slotStart : segEnd;
+				int limit = ( segEnd + 3 ) & ~3;
+				next = next < limit ? next : limit;
+				for ( int dead = segEnd; dead < next; ++dead )
+				{
+					_mm_stream_ps( reinterpret_cast<float*>( wire + (size_t)dead * b2g::WR_COUNT + b2g::WR_HEAD ), _mm_setzero_ps() );
+				}
 			}
 			flat = s->contactStart[k + 1];
 			k += 1;
@@ -2054,6 +2082,8 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 	{
 		const uint32_t* bits = reinterpret_cast<const uint32_t*>( s->hOut.ptr + s->outBits );
 		auto now = std::chrono::steady_clock::now();
+		float h2dMs = 0.0f;
+		cudaEventElapsedTime( &h2dMs, s->evUpload, s->evStart ); // one driver call, not one per world
 		for ( size_t w = 0; w < s->bodySegs.size(); ++w )
 		{
 			const b2gBodySeg& seg = s->bodySegs[w];
@@ -2076,15 +2106,15 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 			r->uploadMs = ms( s->tBegin, s->tSubmit );	 // layout + packing
 			r->waitMs = ms( s->tSubmit, s->tWaited );	 // H2D + kernels + D2H
 			r->scatterMs = ms( s->tWaited, now );		 // unpack + event bits
-			r->h2dMs = 0.0f;
-			cudaEventElapsedTime( &r->h2dMs, s->evUpload, s->evStart );
+			r->h2dMs = h2dMs;
 			r->totalMs = ms( s->tBegin, now );
 		}
 		b2gFlushLines( bits, (size_t)s->params.jointWords * sizeof( uint32_t ) );
 	}
 	if ( s->trace )
 	{
-		fprintf( stderr, "[b2gpu] in %zu quads, out %zu quads | begun %.0f | sends (us: upto):", s->inTotal, s->outTotal, s->traceBegun );
+		fprintf( stderr, "[b2gpu] in %zu quads, out %zu quads | begin marks %.0f %.0f %.0f %.0f %.0f | begun %.0f | sends (us: upto):", s->inTotal, s->outTotal,
+				 s->traceMarks[0], s->traceMarks[1], s->traceMarks[2], s->traceMarks[3], s->traceMarks[4], s->traceBegun );
 		for ( auto& e : s->traceSends )
 		{
 			fprintf( stderr, " %.0f:%zu", e.first, e.second );
