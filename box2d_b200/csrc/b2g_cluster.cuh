@@ -53,6 +53,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	__shared__ int expectBytes[kColorSlots];
 	__shared__ __align__( 8 ) unsigned long long arrivalBar;
 	__shared__ int overflowOrder[kMaxBinOverflow];
+	__shared__ OverflowSchedule overflow; // of the bin's overflow colour (held by the cluster's first block)
 
 	cg::cluster_group cluster = cg::this_cluster();
 	const int share = P.clusterSize;
@@ -223,7 +224,31 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 			pair[1] = b >= 0 ? P.bodyLocal[b] - 1 : -1;
 		}
 	} );
+	const int ovJoints = ovJe - ovJb;
+	if ( hasOverflow && rank == 0 )
+	{
+		__syncthreads();
+		buildOverflowSchedule( overflow, ovJoints + ( ovCe - ovCb ), [&]( int i, int& a, int& b ) {
+			if ( i < ovJoints )
+			{
+				const int* pair = jointIndexPair( jointAt( V, ovJb + i ) );
+				a = pair != nullptr ? pair[0] + 1 : 0; // bin-local, -1 = static
+				b = pair != nullptr ? pair[1] + 1 : 0;
+			}
+			else
+			{
+				int2 idx = V.cidx[ovCb + ( i - ovJoints )];
+				a = idx.x;
+				b = idx.y;
+			}
+			a = ( __float_as_uint( gatherVel( V, a ).w ) & B2L_FLAG_DYNAMIC ) != 0 ? a : 0;
+			b = ( __float_as_uint( gatherVel( V, b ).w ) & B2L_FLAG_DYNAMIC ) != 0 ? b : 0;
+		} );
+	}
 	cluster.sync();
+	// the number of overflow levels is needed by every block of the cluster (they all take part in the barriers)
+	const int overflowLevelCount = hasOverflow ? *cluster.map_shared_rank( &overflow.levelCount, 0 ) : 0;
+	auto clusterSync = [&]() { cluster.sync(); };
 	// restitution is applied by the whole cluster or not at all
 	if ( threadIdx.x == 0 )
 	{
@@ -238,21 +263,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	clk.lap( b2GpuStage_prepareConstraints );
 
 	auto overflowPass = [&]( auto joint, auto contact ) {
-		if ( hasOverflow )
-		{
-			if ( rank == 0 && threadIdx.x == 0 )
-			{
-				for ( int k = ovJb; k < ovJe; ++k )
-				{
-					joint( k );
-				}
-				for ( int k = ovCb; k < ovCe; ++k )
-				{
-					contact( k );
-				}
-			}
-			cluster.sync();
-		}
+		overflowLevels( overflow, overflowLevelCount, rank == 0, ovJoints, ovJb, ovCb, joint, contact, clusterSync );
 	};
 	// A pass over the colours.  Colours with joints end in a full cluster barrier (release / acquire: every writer fences
 	// its remote stores at GPU scope, MEMBAR.ALL.GPU, which costs more than the colour itself).  Colours with contacts
@@ -347,14 +358,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	{
 		if ( binCountC[colorCount] > 0 )
 		{
-			if ( rank == 0 && threadIdx.x == 0 )
-			{
-				for ( int k = ovCb; k < ovCe; ++k )
-				{
-					restitutionContactOverflow( P, V, k );
-				}
-			}
-			cluster.sync();
+			overflowPass( []( int ) {}, [&]( int k ) { restitutionContactOverflow( P, V, k ); } );
 		}
 		for ( int c = 0; c < colorCount; ++c )
 		{

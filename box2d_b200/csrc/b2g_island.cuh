@@ -238,6 +238,163 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 	} );
 }
 
+// ---- the overflow colour of a bin, levelised ------------------------------------------------------------------------------
+// The reference solves the overflow colour one constraint after the other (joints, then contacts, in array order:
+// src/solver.c:1100-1101, src/joint.c:1576-1591, src/contact_solver.c:216-340).  Two constraints only interact through
+// a DYNAMIC body they share (nothing else is written), so the sequence can be cut into levels: the level of a constraint
+// is one more than the highest level among the earlier constraints it shares a dynamic body with.  Constraints of one
+// level touch disjoint dynamic bodies and every pair that shares one keeps its order, hence solving the levels one after
+// the other -- each level in parallel -- gives every body exactly the sequence of updates the reference gives it.
+// Typical overflow sets (everything touching one kinematic or very crowded body) have one or two levels.
+constexpr int kMaxOverflowItems = 2 * kMaxBinOverflow; // joints + contacts
+
+struct OverflowSchedule
+{
+	int bodyA[kMaxOverflowItems]; // dynamic bodies of item i (bin-local, 1-based), 0 = none
+	int bodyB[kMaxOverflowItems];
+	short level[kMaxOverflowItems];
+	short order[kMaxOverflowItems];			// items sorted by (level, position in the sequence)
+	short levelStart[kMaxOverflowItems + 2]; // first entry of `order` with a level >= L
+	int levelCount;
+	int changed;
+};
+
+// Called by all threads of the block that holds the bin's overflow constraints.  bodiesOf( i, a, b ) returns the dynamic
+// bodies of the i-th constraint of the sequence.
+template <typename BodiesOf> B2G_DEV void buildOverflowSchedule( OverflowSchedule& S, int itemCount, BodiesOf bodiesOf )
+{
+	for ( int i = (int)threadIdx.x; i < itemCount; i += (int)blockDim.x )
+	{
+		int a = 0, b = 0;
+		bodiesOf( i, a, b );
+		S.bodyA[i] = a;
+		S.bodyB[i] = b;
+		S.level[i] = 1;
+	}
+	if ( threadIdx.x == 0 )
+	{
+		S.levelCount = 0;
+		S.levelStart[0] = (short)itemCount;
+	}
+	__syncthreads();
+	// chaotic iteration towards the least fixed point: levels only grow, a sweep without a change ends it.  A deep chain
+	// (every constraint touches the same dynamic body, e.g. the drum of the tumbler scene) gains nothing from levels and
+	// would pay a barrier per constraint: give up after a few sweeps, the caller then solves the sequence on one thread.
+	const int sweepLimit = itemCount / 4 + 2;
+	for ( int sweep = 0;; ++sweep )
+	{
+		if ( sweep > sweepLimit )
+		{
+			if ( threadIdx.x == 0 )
+			{
+				S.levelCount = -1;
+			}
+			__syncthreads();
+			return;
+		}
+		if ( threadIdx.x == 0 )
+		{
+			S.changed = 0;
+		}
+		__syncthreads();
+		for ( int i = (int)threadIdx.x; i < itemCount; i += (int)blockDim.x )
+		{
+			int a = S.bodyA[i], b = S.bodyB[i];
+			int level = 1;
+			for ( int j = 0; j < i; ++j )
+			{
+				int ja = S.bodyA[j], jb = S.bodyB[j];
+				bool shares = ( a != 0 && ( a == ja || a == jb ) ) || ( b != 0 && ( b == ja || b == jb ) );
+				int after = (int)S.level[j] + 1;
+				level = shares && after > level ? after : level;
+			}
+			if ( level != (int)S.level[i] )
+			{
+				S.level[i] = (short)level;
+				S.changed = 1;
+			}
+		}
+		__syncthreads();
+		bool done = S.changed == 0;
+		__syncthreads();
+		if ( done )
+		{
+			break;
+		}
+	}
+	for ( int i = (int)threadIdx.x; i < itemCount; i += (int)blockDim.x )
+	{
+		int mine = S.level[i], rank = 0;
+		for ( int j = 0; j < itemCount; ++j )
+		{
+			int other = S.level[j];
+			rank += ( other < mine || ( other == mine && j < i ) ) ? 1 : 0;
+		}
+		S.order[rank] = (short)i;
+		atomicMax( &S.levelCount, mine );
+	}
+	__syncthreads();
+	for ( int level = (int)threadIdx.x; level <= S.levelCount + 1; level += (int)blockDim.x )
+	{
+		int below = 0;
+		for ( int j = 0; j < itemCount; ++j )
+		{
+			below += (int)S.level[j] < level ? 1 : 0;
+		}
+		S.levelStart[level] = (short)below;
+	}
+	__syncthreads();
+}
+
+// One pass over the overflow colour: level by level, `sync` between the levels.  `holder` is false for the blocks of a
+// cluster that do not hold the bin's overflow constraints (they only take part in the barriers).
+template <typename FJ, typename FC, typename Sync>
+B2G_DEV void overflowLevels( const OverflowSchedule& S, int levelCount, bool holder, int jointCount, int jointBegin, int contactBegin, FJ joint,
+							 FC contact, Sync sync )
+{
+	if ( levelCount < 0 )
+	{
+		// deep chain: the sequence as it is, on one thread
+		if ( holder && threadIdx.x == 0 )
+		{
+			int itemCount = (int)S.levelStart[0];
+			for ( int item = 0; item < itemCount; ++item )
+			{
+				if ( item < jointCount )
+				{
+					joint( jointBegin + item );
+				}
+				else
+				{
+					contact( contactBegin + ( item - jointCount ) );
+				}
+			}
+		}
+		sync();
+		return;
+	}
+	for ( int level = 1; level <= levelCount; ++level )
+	{
+		if ( holder )
+		{
+			int end = S.levelStart[level + 1];
+			for ( int t = (int)S.levelStart[level] + (int)threadIdx.x; t < end; t += (int)blockDim.x )
+			{
+				int item = S.order[t];
+				if ( item < jointCount )
+				{
+					joint( jointBegin + item );
+				}
+				else
+				{
+					contact( contactBegin + ( item - jointCount ) );
+				}
+			}
+		}
+		sync();
+	}
+}
+
 // ---- island kernel -------------------------------------------------------------------------------------------------------
 template <typename F> B2G_DEV void forEachLocal( int itemCount, F f )
 {
@@ -278,6 +435,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	__shared__ int colorStartJ[kColorSlots];
 	__shared__ int anyRestitution;
 	__shared__ int overflowOrder[kMaxBinOverflow]; // scratch for ordering the bin's overflow constraints
+	__shared__ OverflowSchedule overflow;
 	// the colours that are present in this bin, in order: { jointBegin, jointEnd, contactBegin, contactEnd }
 	__shared__ __align__( 16 ) int4 passRange[kMaxColors];
 	__shared__ int passCount;
@@ -428,6 +586,28 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		}
 	} );
 	__syncthreads();
+	const int ovJoints = ovJe - ovJb;
+	if ( hasOverflow )
+	{
+		buildOverflowSchedule( overflow, ovJoints + ( ovCe - ovCb ), [&]( int i, int& a, int& b ) {
+			if ( i < ovJoints )
+			{
+				const int* pair = jointIndexPair( jointAt( V, ovJb + i ) );
+				a = pair != nullptr ? pair[0] + 1 : 0; // bin-local, -1 = static
+				b = pair != nullptr ? pair[1] + 1 : 0;
+			}
+			else
+			{
+				int2 idx = V.cidx[ovCb + ( i - ovJoints )];
+				a = idx.x;
+				b = idx.y;
+			}
+			a = ( __float_as_uint( V.vel[a].w ) & B2L_FLAG_DYNAMIC ) != 0 ? a : 0;
+			b = ( __float_as_uint( V.vel[b].w ) & B2L_FLAG_DYNAMIC ) != 0 ? b : 0;
+		} );
+	}
+	const int overflowLevelCount = hasOverflow ? overflow.levelCount : 0;
+	auto blockSync = []() { __syncthreads(); };
 	clk.lap( b2GpuStage_prepareConstraints );
 
 	const int passes = passCount;
@@ -437,21 +617,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		__syncthreads();
 		clk.lap( b2GpuStage_integrateVelocities );
 
-		if ( hasOverflow )
-		{
-			if ( threadIdx.x == 0 )
-			{
-				for ( int k = ovJb; k < ovJe; ++k )
-				{
-					warmStartJoint( P, V, jointAt( V, k ) );
-				}
-				for ( int k = ovCb; k < ovCe; ++k )
-				{
-					warmStartContactOverflow( V, k );
-				}
-			}
-			__syncthreads();
-		}
+		overflowLevels(
+			overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); },
+			[&]( int k ) { warmStartContactOverflow( V, k ); }, blockSync );
 		for ( int pass = 0; pass < passes; ++pass )
 		{
 			forEachInLocalColor(
@@ -460,21 +628,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		}
 		clk.lap( b2GpuStage_warmStart );
 
-		if ( hasOverflow )
-		{
-			if ( threadIdx.x == 0 )
-			{
-				for ( int k = ovJb; k < ovJe; ++k )
-				{
-					solveJoint( P, V, jointAt( V, k ), true );
-				}
-				for ( int k = ovCb; k < ovCe; ++k )
-				{
-					solveContactOverflow( P, V, k, true );
-				}
-			}
-			__syncthreads();
-		}
+		overflowLevels(
+			overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), true ); },
+			[&]( int k ) { solveContactOverflow( P, V, k, true ); }, blockSync );
 		for ( int pass = 0; pass < passes; ++pass )
 		{
 			forEachInLocalColor(
@@ -493,21 +649,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		__syncthreads();
 		clk.lap( b2GpuStage_integratePositions );
 
-		if ( hasOverflow )
-		{
-			if ( threadIdx.x == 0 )
-			{
-				for ( int k = ovJb; k < ovJe; ++k )
-				{
-					solveJoint( P, V, jointAt( V, k ), false );
-				}
-				for ( int k = ovCb; k < ovCe; ++k )
-				{
-					solveContactOverflow( P, V, k, false );
-				}
-			}
-			__syncthreads();
-		}
+		overflowLevels(
+			overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+			[&]( int k ) { solveContactOverflow( P, V, k, false ); }, blockSync );
 		for ( int pass = 0; pass < passes; ++pass )
 		{
 			forEachInLocalColor(
@@ -522,14 +666,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	{
 		if ( ovCe > ovCb )
 		{
-			if ( threadIdx.x == 0 )
-			{
-				for ( int k = ovCb; k < ovCe; ++k )
-				{
-					restitutionContactOverflow( P, V, k );
-				}
-			}
-			__syncthreads();
+			overflowLevels(
+				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, []( int ) {}, [&]( int k ) { restitutionContactOverflow( P, V, k ); },
+				blockSync );
 		}
 		for ( int pass = 0; pass < passes; ++pass )
 		{

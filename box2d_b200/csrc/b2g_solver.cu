@@ -752,6 +752,8 @@ static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimi
 	double slack = share > 1 ? (double)( b2g::kMaxColors + 1 ) : 0.0;
 	double needC = fraction * s->contactTotal + slack + ( share > 1 ? (double)s->overflowContacts : 0.0 );
 	double needJ = fraction * s->jointTotal + ( s->jointTotal > 0 ? slack : 0.0 ) + ( share > 1 ? (double)s->overflowJoints : 0.0 );
+	needC = needC < (double)s->contactTotal ? needC : (double)s->contactTotal;
+	needJ = needJ < (double)s->jointTotal ? needJ : (double)s->jointTotal;
 	size_t fixed = b2g::islandSharedBytes( capB, 0, 0 );
 	if ( fixed + (size_t)( needC * 1.1 * bytesPerContact + needJ * 1.1 * bytesPerJoint ) + 4096 > budget )
 	{
