@@ -247,6 +247,16 @@ def _setup_distributed():
 	return world_size, rank, local_rank
 
 
+def measured_traffic(workload: str):
+	"""DRAM bytes per step of the workload's kernels from the committed ncu --set full captures (profiles/), or None."""
+	path = ROOT / "profiles" / "r01_traffic.json"
+	try:
+		entry = json.loads(path.read_text()).get(workload)
+	except (OSError, ValueError):
+		return None
+	return entry["bytes"] if entry else None
+
+
 def run_scene(args) -> int:
 	import torch
 	import torch.distributed as dist
@@ -363,7 +373,7 @@ def run_scene(args) -> int:
 					"kernel_ms_per_step": e2e_kernel_s * 1e3 / args.steps, "last_step_split": e2e_split},
 			"gpu_launches": launches + e2e_launches,
 			"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-						 "traffic": None, "algorithmic_bytes_per_launch": alg, "peak_source": peak_source,
+						 "traffic": measured_traffic(scene), "algorithmic_bytes_per_launch": alg, "peak_source": peak_source,
 						 "kernels_per_step": launches_per_step, "grid_barriers_per_step": grid_barriers,
 						 "island_bins_blocks_per_bin": island_plan,
 						 "note": "all kernels of the step (partition + island kernel, or the grid-barrier kernel); see DESIGN.md"},
@@ -455,6 +465,7 @@ def run_batch(args) -> int:
 			kernel_ms.append(float(r.kernelMs))
 		launches = int(r.kernelLaunches) * args.steps
 		grid_barriers = int(r.gridBarriers)
+		island_plan = list(solver.island_plan())
 		# e2e: the whole b2GpuSolverStepBatch from host arrays, inputs restored untimed
 		e2e_steps = max(3, min(args.steps, 10))
 		e2e_s = 0.0
@@ -493,7 +504,8 @@ def run_batch(args) -> int:
 					"timed": "b2GpuSolverStepBatch wall clock: host packing (library threads) + H2D + kernels + D2H + write-back"},
 			"gpu_launches": launches,
 			"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-						 "algorithmic_bytes_per_launch": alg, "peak_source": peak_source, "grid_barriers_per_step": grid_barriers},
+						 "algorithmic_bytes_per_launch": alg, "peak_source": peak_source, "grid_barriers_per_step": grid_barriers,
+						 "island_bins_blocks_per_bin": island_plan},
 			"clocks": clocks,
 		}
 		if args.cpu_baseline and not distributed:

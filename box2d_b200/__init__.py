@@ -439,6 +439,47 @@ class GpuSolver:
 		self._check(self.lib.b2GpuSolverDownload(self.handle, ctypes.byref(desc), ctypes.byref(result)),
 					"b2GpuSolverDownload")
 
+	def step_phased(self, desc: StepDesc, result: StepResult, workers: int = 4, pipelined: bool = True) -> None:
+		"""The step through the phased entry points the seam uses, with `workers` host threads (ctypes drops the GIL):
+		pipelined = BeginStep, PackWork x workers, Submit, UnpackWork x workers, EndStep;
+		otherwise  = BeginStep, PackRange x workers, Submit, Wait, UnpackRange x workers, EndStep."""
+		import threading
+
+		lib, h = self.lib, self.handle
+		self._check(lib.b2GpuSolverBeginStep(h, ctypes.byref(desc), ctypes.byref(result)), "b2GpuSolverBeginStep")
+		failures = []
+
+		def run_all(fn_for):
+			threads = [threading.Thread(target=fn_for(i)) for i in range(1, workers)]
+			for t in threads:
+				t.start()
+			fn_for(0)()
+			for t in threads:
+				t.join()
+
+		if pipelined:
+			def pack(i):
+				return lambda: failures.append("pack") if lib.b2GpuSolverPackWork(h, 1 if i == 0 else 0) != 0 else None
+
+			def unpack(i):
+				return lambda: failures.append("unpack") if lib.b2GpuSolverUnpackWork(h, 1 if i == 0 else 0) != 0 else None
+
+			run_all(pack)
+			self._check(lib.b2GpuSolverSubmit(h), "b2GpuSolverSubmit")
+			run_all(unpack)
+		else:
+			n = lib.b2GpuSolverGetPackItemCount(h)
+			cuts = [n * i // workers for i in range(workers + 1)]
+			run_all(lambda i: (lambda: lib.b2GpuSolverPackRange(h, cuts[i], cuts[i + 1])))
+			self._check(lib.b2GpuSolverSubmit(h), "b2GpuSolverSubmit")
+			self._check(lib.b2GpuSolverWait(h), "b2GpuSolverWait")
+			m = lib.b2GpuSolverGetUnpackItemCount(h)
+			cuts = [m * i // workers for i in range(workers + 1)]
+			run_all(lambda i: (lambda: lib.b2GpuSolverUnpackRange(h, cuts[i], cuts[i + 1])))
+		if failures:
+			raise RuntimeError(f"phased step failed in {failures}: " + lib.b2GpuGetLastError().decode())
+		self._check(lib.b2GpuSolverEndStep(h, ctypes.byref(result)), "b2GpuSolverEndStep")
+
 	def step_batch(self, descs, results) -> None:
 		"""descs / results: ctypes arrays (StepDesc * n), (StepResult * n) -- b2GpuSolverStepBatch."""
 		self._check(self.lib.b2GpuSolverStepBatch(self.handle, descs, len(descs), results), "b2GpuSolverStepBatch")

@@ -54,3 +54,14 @@ def test_batch_rejects_mixed_step_parameters():
 	with b2.GpuSolver() as solver:
 		with pytest.raises(RuntimeError):
 			solver.step_batch(descs, results)
+
+
+def test_large_batch_through_the_pipelined_host_passes():
+	"""700 worlds = ~140 000 pack items: the one-call entry point splits the two host passes over several threads that claim
+	blocks concurrently while the pump thread moves finished prefixes over PCIe (b2GpuSolverPackWork / UnpackWork)."""
+	caps = [b2.Capture(b2.ROOT / "tests" / "golden" / f"{name}.b2cap.gz") for name in ("small_pyramid_030", "falling_hinges_120")] * 350
+	descs, results, bufs = b2.make_batch(caps)
+	with b2.GpuSolver() as solver:
+		solver.step_batch(descs, results)
+	for cap, buf, res in zip(caps, bufs, results):
+		_check(cap, buf, res)

@@ -98,6 +98,19 @@ def test_island_failure_reruns_on_grid_kernel(capture_files, monkeypatch):
 	assert reruns > 0, "the rerun path never ran"
 
 
+@pytest.mark.parametrize("pipelined", [True, False])
+def test_phased_entry_points_with_host_threads(solver, capture_files, pipelined):
+	"""The phases the seam drives from the world's workers: BeginStep, PackWork / UnpackWork (or PackRange / Wait /
+	UnpackRange) called concurrently by several host threads, Submit, EndStep."""
+	solver.set_mode(0)
+	for path in capture_files:
+		cap = b2.Capture(path)
+		desc, result, bufs = cap.make_call(islands=True)
+		solver.step_phased(desc, result, workers=4, pipelined=pipelined)
+		_check(cap, bufs, result)
+		assert result.kernelLaunches >= 1
+
+
 def test_split_phase_is_repeatable(solver, capture_files):
 	"""Upload once, Run twice (inputs stay pristine on the device), Download: same bits as the one-shot step."""
 	solver.set_mode(0)
