@@ -102,6 +102,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	const int bodyCount = min( binBodies - bodyBegin, 1 << P.clusterShift );
 	const int* bodyList = P.binBodyList + (size_t)bin * P.binCapBodies + bodyBegin;
 	const int* contactList = P.binContactList + (size_t)bin * P.binCapContacts;
+	const int4* contactInfo = P.binContactInfo + (size_t)bin * P.binCapContacts;
 	const int* jointList = P.binJointList + (size_t)bin * P.binCapJoints;
 
 	StageClock clk;
@@ -146,6 +147,19 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	}
 	forEachLocal( bodyCount, [&]( int i ) { loadBody( P, V, bodyList[i], i + 1 ); } );
 	cluster.sync(); // every block of the cluster is running and its bodies are in place
+	// every block has read the bin's counters: leave them zeroed for the next step's partition kernel
+	if ( rank == 0 )
+	{
+		if ( threadIdx.x < kColorSlots )
+		{
+			P.binColorStart[(size_t)bin * kColorSlots + threadIdx.x] = 0;
+			P.binJointStart[(size_t)bin * kColorSlots + threadIdx.x] = 0;
+		}
+		if ( threadIdx.x == 0 )
+		{
+			P.binBodyCount[bin] = 0;
+		}
+	}
 
 	const int contactCount = localStartC[slotCount];
 	const int jointCount = localStartJ[slotCount];
@@ -173,12 +187,21 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		int c = colorOfLocal( localStartC, slotCount, k );
 		bool wide = c < colorCount;
 		int offset = k - localStartC[c];
-		int slot = wide ? contactList[listBeginC[c] + offset] : overflowOrder[offset];
-		float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
-		int indexA = __float_as_int( head.x );
-		int indexB = __float_as_int( head.y );
-		int localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;
-		int localB = indexB >= 0 ? P.bodyLocal[indexB] : 0;
+		int slot, localA, localB, groupBits = 0;
+		if ( wide )
+		{
+			int4 info = contactInfo[listBeginC[c] + offset]; // resolved by the partition kernel
+			slot = info.x, localA = info.y, localB = info.z, groupBits = info.w;
+		}
+		else
+		{
+			slot = overflowOrder[offset];
+			float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+			int indexA = __float_as_int( head.x );
+			int indexB = __float_as_int( head.y );
+			localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;
+			localB = indexB >= 0 ? P.bodyLocal[indexB] : 0;
+		}
 		wireSlot[k] = slot;
 		float4 sA = gatherVel( V, localA ), sB = gatherVel( V, localB );
 		if ( wide )
@@ -193,7 +216,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 				atomicAdd( cluster.map_shared_rank( expectBytes, ( (unsigned)localB - 1u ) >> P.clusterShift ) + c, (int)sizeof( float4 ) );
 			}
 		}
-		prepareContact( P, V, slot, k, localA, localB, sA, sB, wide, wide ? P.slotGroupBits[slot] : 0 );
+		prepareContact( P, V, slot, k, localA, localB, sA, sB, wide, groupBits );
 	} );
 	__syncthreads();
 	sortOverflow( jointList, listBeginJ[colorCount], ovJe - ovJb );

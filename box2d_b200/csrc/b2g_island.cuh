@@ -209,14 +209,25 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 			c += 1;
 		}
 		ColorRange color = c == P.colorCount ? P.overflow : P.colors[c];
-		if ( slot < color.contactStart + color.contactCount &&
-			 ( __float_as_int( P.wire[(size_t)slot * WR_COUNT + WR_HEAD].z ) & kMetaPointMask ) != 0 )
+		bool inRange = slot < color.contactStart + color.contactCount;
+		float4 head = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+		if ( inRange )
+		{
+			head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+		}
+		if ( inRange && ( __float_as_int( head.z ) & kMetaPointMask ) != 0 )
 		{
 			int2 br = P.contactBinRank[slot];
 			int dest = offsetOf( P.binColorStart, br.x, c ) + br.y;
 			if ( dest < P.binCapContacts ) // a bin that does not fit raised binFail above
 			{
+				// everything the island kernel needs to start preparing the contact without chasing pointers: the
+				// wire slot, the bodies' indices inside the bin, the SIMD-group bits
+				int indexA = __float_as_int( head.x ), indexB = __float_as_int( head.y );
+				int localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;
+				int localB = indexB >= 0 ? P.bodyLocal[indexB] : 0;
 				P.binContactList[(size_t)br.x * P.binCapContacts + dest] = slot;
+				P.binContactInfo[(size_t)br.x * P.binCapContacts + dest] = make_int4( slot, localA, localB, P.slotGroupBits[slot] );
 			}
 		}
 	} );
@@ -493,6 +504,16 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	}
 	forEachLocal( bodyCount, [&]( int i ) { loadBody( P, V, bodyList[i], i + 1 ); } );
 	__syncthreads();
+	// this block is the last reader of its bin's counters: leave them zeroed for the next step's partition kernel
+	if ( threadIdx.x < kColorSlots )
+	{
+		P.binColorStart[(size_t)bin * kColorSlots + threadIdx.x] = 0;
+		P.binJointStart[(size_t)bin * kColorSlots + threadIdx.x] = 0;
+	}
+	if ( threadIdx.x == 0 )
+	{
+		P.binBodyCount[bin] = 0;
+	}
 
 	const int contactCount = colorStartC[kColorSlots - 1];
 	const int jointCount = colorStartJ[kColorSlots - 1];
@@ -536,16 +557,26 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	__syncthreads();
 
 	// prepare: contacts read the bodies' initial velocities from the view (identical to the wire states here)
+	const int4* contactInfo = P.binContactInfo + (size_t)bin * capC;
 	forEachLocal( contactCount, [&]( int k ) {
-		int slot = orderedIndex( contactList, ovCb, ovCe, k );
-		float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
-		int indexA = __float_as_int( head.x );
-		int indexB = __float_as_int( head.y );
-		int localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;
-		int localB = indexB >= 0 ? P.bodyLocal[indexB] : 0;
-		wireSlot[k] = slot;
 		bool wide = k < ovCb || k >= ovCe;
-		prepareContact( P, V, slot, k, localA, localB, V.vel[localA], V.vel[localB], wide, wide ? P.slotGroupBits[slot] : 0 );
+		int slot, localA, localB, groupBits = 0;
+		if ( wide )
+		{
+			int4 info = contactInfo[k]; // resolved by the partition kernel
+			slot = info.x, localA = info.y, localB = info.z, groupBits = info.w;
+		}
+		else
+		{
+			slot = overflowOrder[k - ovCb];
+			float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+			int indexA = __float_as_int( head.x );
+			int indexB = __float_as_int( head.y );
+			localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;
+			localB = indexB >= 0 ? P.bodyLocal[indexB] : 0;
+		}
+		wireSlot[k] = slot;
+		prepareContact( P, V, slot, k, localA, localB, V.vel[localA], V.vel[localB], wide, groupBits );
 	} );
 	__syncthreads();
 	// joints: copy the prepared record into shared memory, renumber its bodies to the bin

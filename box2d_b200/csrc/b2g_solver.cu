@@ -349,6 +349,9 @@ struct b2GpuSolver
 	// island mode scratch (b2g_island.cuh)
 	DeviceBuffer<int> binCounters; // [binBodyCount | binColorStart | binJointStart | binFail], zeroed every run
 	DeviceBuffer<int> bodyLocal, binBodyList, slotGroupBits, binContactList, binJointList;
+	DeviceBuffer<int4> binContactInfo;
+	int countersBinCount = 0;
+	bool countersClean = false; // the bin counters are all zero (the island kernels zero what they have read)
 	DeviceBuffer<int2> contactBinRank, jointBinRank;
 	std::vector<int> islandBin;	 // host: bin of every awake island
 	std::vector<int> islandBodies; // host: bodies per island, then per bin
@@ -599,6 +602,7 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	s->binBodyList.release();
 	s->slotGroupBits.release();
 	s->binContactList.release();
+	s->binContactInfo.release();
 	s->binJointList.release();
 	s->contactBinRank.release();
 	s->jointBinRank.release();
@@ -852,13 +856,22 @@ static int b2gPlanIslands( b2GpuSolver* s )
 
 	size_t slots = (size_t)P.contactSlots;
 	s->binCounterCount = (size_t)binCount * ( 1 + 2 * b2g::kColorSlots ) + 1; // the part that is zeroed every step
-	B2G_CUDA( s->binCounters.reserve( s->binCounterCount + (size_t)binCount * 2 * b2g::kColorSlots ) );
+	{
+		const int* before = s->binCounters.ptr;
+		B2G_CUDA( s->binCounters.reserve( s->binCounterCount + (size_t)binCount * 2 * b2g::kColorSlots ) );
+		if ( s->binCounters.ptr != before || binCount != s->countersBinCount )
+		{
+			s->countersClean = false; // fresh memory, or the tables move (the offset tables behind them are not zero)
+		}
+		s->countersBinCount = binCount;
+	}
 	B2G_CUDA( s->bodyLocal.reserve( (size_t)bodies + 1 ) );
 	const size_t share = (size_t)plan.share;
 	B2G_CUDA( s->binBodyList.reserve( (size_t)binCount * capB * share + 1 ) );
 	B2G_CUDA( s->slotGroupBits.reserve( slots + 1 ) );
 	B2G_CUDA( s->contactBinRank.reserve( slots + 1 ) );
 	B2G_CUDA( s->binContactList.reserve( (size_t)binCount * capC * share + 1 ) );
+	B2G_CUDA( s->binContactInfo.reserve( (size_t)binCount * capC * share + 1 ) );
 	B2G_CUDA( s->jointBinRank.reserve( (size_t)s->jointTotal + 1 ) );
 	B2G_CUDA( s->binJointList.reserve( (size_t)binCount * capJ * share + 1 ) );
 
@@ -883,6 +896,7 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	P.contactBinRank = s->contactBinRank.ptr;
 	P.slotGroupBits = s->slotGroupBits.ptr;
 	P.binContactList = s->binContactList.ptr;
+	P.binContactInfo = s->binContactInfo.ptr;
 	P.jointBinRank = s->jointBinRank.ptr;
 	P.binJointList = s->binJointList.ptr;
 	s->islandSmemBytes = b2g::islandSharedBytes( capB, capC, capJ );
@@ -1527,6 +1541,7 @@ static int b2gRerunIfIslandsFailed( b2GpuSolver* s, bool download )
 	{
 		return 0;
 	}
+	s->countersClean = false; // the island kernels returned before zeroing their counters
 	B2G_CUDA( cudaMemsetAsync( s->control, 0, sizeof( ControlBlock ), s->stream ) );
 	if ( b2gLaunchGridKernel( s ) != 0 )
 	{
@@ -1567,7 +1582,11 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 		{
 			// partition -> island kernel; if a bin does not fit (binFail) the host reruns the step on the grid-barrier
 			// kernel once the flag has come back (b2gRerunIfIslandsFailed)
-			B2G_CUDA( cudaMemsetAsync( s->binCounters.ptr, 0, s->binCounterCount * sizeof( int ), s->stream ) );
+			if ( !s->countersClean )
+			{
+				B2G_CUDA( cudaMemsetAsync( s->binCounters.ptr, 0, s->binCounters.capacity * sizeof( int ), s->stream ) );
+			}
+			s->countersClean = true; // the island kernels zero the counters they have read
 			if ( s->cooperative )
 			{
 				err = cudaLaunchCooperativeKernel( (const void*)b2g::b2gPartitionKernel, dim3( s->gridBlocks ),

@@ -164,6 +164,7 @@ struct StepParams
 	int2* contactBinRank; // [contactSlots] bin, rank within (bin, colour)
 	int* slotGroupBits;	 // [contactSlots] kMetaGroup* bits in wire order
 	int* binContactList; // [binCount * binCapContacts] wire slots, colour-major
+	int4* binContactInfo; // same layout: { wire slot, bin-local body A, bin-local body B, SIMD-group bits }
 	int2* jointBinRank;	 // [jointCount]
 	int* binJointList;	 // [binCount * binCapJoints] joint index, colour-major
 	int* islandFailed;	 // control block: set by the island kernels when they give up (binFail), read by the host
