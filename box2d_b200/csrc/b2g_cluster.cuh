@@ -188,14 +188,15 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		bool wide = c < colorCount;
 		int offset = k - localStartC[c];
 		int slot, localA, localB, groupBits = 0;
-		if ( wide )
+		if ( wide && P.resolveContacts != 0 )
 		{
 			int4 info = contactInfo[listBeginC[c] + offset]; // resolved by the partition kernel
 			slot = info.x, localA = info.y, localB = info.z, groupBits = info.w;
 		}
 		else
 		{
-			slot = overflowOrder[offset];
+			slot = wide ? contactList[listBeginC[c] + offset] : overflowOrder[offset];
+			groupBits = wide ? P.slotGroupBits[slot] : 0;
 			float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
 			int indexA = __float_as_int( head.x );
 			int indexB = __float_as_int( head.y );
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	clk.lap( b2GpuStage_prepareConstraints );
 
 	auto overflowPass = [&]( auto joint, auto contact ) {
-		overflowLevels( overflow, overflowLevelCount, rank == 0, ovJoints, ovJb, ovCb, joint, contact, clusterSync );
+		overflowLevels( overflow, overflowLevelCount, rank == 0, ovJoints, ovJb, ovCb, joint, contact, clusterSync, (int)blockDim.x );
 	};
 	// A pass over the colours.  Colours with joints end in a full cluster barrier (release / acquire: every writer fences
 	// its remote stores at GPU scope, MEMBAR.ALL.GPU, which costs more than the colour itself).  Colours with contacts

@@ -223,11 +223,14 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 			{
 				// everything the island kernel needs to start preparing the contact without chasing pointers: the
 				// wire slot, the bodies' indices inside the bin, the SIMD-group bits
-				int indexA = __float_as_int( head.x ), indexB = __float_as_int( head.y );
-				int localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;
-				int localB = indexB >= 0 ? P.bodyLocal[indexB] : 0;
 				P.binContactList[(size_t)br.x * P.binCapContacts + dest] = slot;
-				P.binContactInfo[(size_t)br.x * P.binCapContacts + dest] = make_int4( slot, localA, localB, P.slotGroupBits[slot] );
+				if ( P.resolveContacts != 0 )
+				{
+					int indexA = __float_as_int( head.x ), indexB = __float_as_int( head.y );
+					int localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;
+					int localB = indexB >= 0 ? P.bodyLocal[indexB] : 0;
+					P.binContactInfo[(size_t)br.x * P.binCapContacts + dest] = make_int4( slot, localA, localB, P.slotGroupBits[slot] );
+				}
 			}
 		}
 	} );
@@ -361,7 +364,7 @@ template <typename BodiesOf> B2G_DEV void buildOverflowSchedule( OverflowSchedul
 // cluster that do not hold the bin's overflow constraints (they only take part in the barriers).
 template <typename FJ, typename FC, typename Sync>
 B2G_DEV void overflowLevels( const OverflowSchedule& S, int levelCount, bool holder, int jointCount, int jointBegin, int contactBegin, FJ joint,
-							 FC contact, Sync sync )
+							 FC contact, Sync sync, int threads )
 {
 	if ( levelCount < 0 )
 	{
@@ -389,7 +392,7 @@ B2G_DEV void overflowLevels( const OverflowSchedule& S, int levelCount, bool hol
 		if ( holder )
 		{
 			int end = S.levelStart[level + 1];
-			for ( int t = (int)S.levelStart[level] + (int)threadIdx.x; t < end; t += (int)blockDim.x )
+			for ( int t = (int)S.levelStart[level] + (int)threadIdx.x; t < end; t += threads )
 			{
 				int item = S.order[t];
 				if ( item < jointCount )
@@ -415,19 +418,33 @@ template <typename F> B2G_DEV void forEachLocal( int itemCount, F f )
 	}
 }
 
-// One colour of a bin: joints [r.x, r.y) are taken by the block's first threads, contacts [r.z, r.w) by its LAST threads
-// (thread blockDim-1 takes the first contact), so that joints and contacts of the colour run side by side in different
-// warps as long as the block has a thread for each.  The header is one broadcast 16-byte shared load.
-template <typename FJ, typename FC> B2G_DEV void forEachInLocalColor( int4 r, FJ joint, FC contact )
+// the same for the first `threads` threads of the block only
+template <typename F> B2G_DEV void forEachLocal( int itemCount, int threads, F f )
 {
-	for ( int k = r.x + (int)threadIdx.x; k < r.y; k += (int)blockDim.x )
+	for ( int i = (int)threadIdx.x; i < itemCount; i += threads )
+	{
+		f( i );
+	}
+}
+
+// One colour of a bin: joints [r.x, r.y) are taken by the block's first threads, contacts [r.z, r.w) by its LAST threads
+// (the last thread takes the first contact), so that joints and contacts of the colour run side by side in different
+// warps as long as the block has a thread for each.  The header is one broadcast 16-byte shared load.
+template <typename FJ, typename FC> B2G_DEV void forEachInLocalColor( int4 r, int threads, FJ joint, FC contact )
+{
+	for ( int k = r.x + (int)threadIdx.x; k < r.y; k += threads )
 	{
 		joint( k );
 	}
-	for ( int k = r.z + ( (int)blockDim.x - 1 - (int)threadIdx.x ); k < r.w; k += (int)blockDim.x )
+	for ( int k = r.z + ( threads - 1 - (int)threadIdx.x ); k < r.w; k += threads )
 	{
 		contact( k );
 	}
+}
+
+template <typename FJ, typename FC> B2G_DEV void forEachInLocalColor( int4 r, FJ joint, FC contact )
+{
+	forEachInLocalColor( r, (int)blockDim.x, joint, contact );
 }
 
 __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __grid_constant__ StepParams P )
@@ -450,6 +467,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	// the colours that are present in this bin, in order: { jointBegin, jointEnd, contactBegin, contactEnd }
 	__shared__ __align__( 16 ) int4 passRange[kMaxColors];
 	__shared__ int passCount;
+	__shared__ int stageThreadCount; // threads that run the stage loops: enough for the bin's largest colour
 
 	const int bin = (int)blockIdx.x;
 	const int capB = P.capBodies, capC = P.capContacts, capJ = P.capJoints;
@@ -520,16 +538,19 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	const int colorCount = P.colorCount;
 	if ( threadIdx.x == 0 )
 	{
-		int passes = 0;
+		int passes = 0, widest = 32;
 		for ( int c = 0; c < colorCount; ++c )
 		{
 			int4 r = make_int4( colorStartJ[c], colorStartJ[c + 1], colorStartC[c], colorStartC[c + 1] );
 			if ( r.x != r.y || r.z != r.w )
 			{
 				passRange[passes++] = r; // a colour that is not present in this bin has nothing to order
+				int width = roundUp32( r.y - r.x ) + roundUp32( r.w - r.z );
+				widest = width > widest ? width : widest;
 			}
 		}
 		passCount = passes;
+		stageThreadCount = widest < (int)blockDim.x && P.stageAllThreads == 0 ? widest : (int)blockDim.x;
 	}
 	// the overflow colour's constraints of this bin, solved by one thread in array order
 	const int ovCb = colorStartC[colorCount], ovCe = colorStartC[colorCount + 1];
@@ -561,14 +582,15 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	forEachLocal( contactCount, [&]( int k ) {
 		bool wide = k < ovCb || k >= ovCe;
 		int slot, localA, localB, groupBits = 0;
-		if ( wide )
+		if ( wide && P.resolveContacts != 0 )
 		{
 			int4 info = contactInfo[k]; // resolved by the partition kernel
 			slot = info.x, localA = info.y, localB = info.z, groupBits = info.w;
 		}
 		else
 		{
-			slot = overflowOrder[k - ovCb];
+			slot = wide ? contactList[k] : overflowOrder[k - ovCb];
+			groupBits = wide ? P.slotGroupBits[slot] : 0;
 			float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
 			int indexA = __float_as_int( head.x );
 			int indexB = __float_as_int( head.y );
@@ -638,84 +660,92 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		} );
 	}
 	const int overflowLevelCount = hasOverflow ? overflow.levelCount : 0;
-	auto blockSync = []() { __syncthreads(); };
 	clk.lap( b2GpuStage_prepareConstraints );
 
+	// The stage loops: a colour of a bin keeps only a few warps busy, and every other warp of the block would still walk
+	// the loops and arrive at ~100 barriers.  Only the first `stageThreads` threads (whole warps, enough for the bin's
+	// widest colour) take part; they meet at a named barrier of their own, the rest waits for the store phase.
 	const int passes = passCount;
-	for ( int subStep = 0; subStep < P.subStepCount; ++subStep )
+	const int stageThreads = stageThreadCount;
+	auto blockSync = [&]() { asm volatile( "bar.sync 1, %0;" ::"r"( stageThreads ) : "memory" ); };
+	if ( (int)threadIdx.x < stageThreads )
 	{
-		forEachLocal( bodyCount, [&]( int i ) { integrateVelocities( V, i ); } );
-		__syncthreads();
-		clk.lap( b2GpuStage_integrateVelocities );
-
-		overflowLevels(
-			overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); },
-			[&]( int k ) { warmStartContactOverflow( V, k ); }, blockSync );
-		for ( int pass = 0; pass < passes; ++pass )
+		for ( int subStep = 0; subStep < P.subStepCount; ++subStep )
 		{
-			forEachInLocalColor(
-				passRange[pass], [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); }, [&]( int k ) { warmStartContact( V, k ); } );
-			__syncthreads();
-		}
-		clk.lap( b2GpuStage_warmStart );
+			forEachLocal( bodyCount, stageThreads, [&]( int i ) { integrateVelocities( V, i ); } );
+			blockSync();
+			clk.lap( b2GpuStage_integrateVelocities );
 
-		overflowLevels(
-			overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), true ); },
-			[&]( int k ) { solveContactOverflow( P, V, k, true ); }, blockSync );
-		for ( int pass = 0; pass < passes; ++pass )
-		{
-			forEachInLocalColor(
-				passRange[pass],
-				[&]( int k ) {
-					b2lJointSim* joint = jointAt( V, k );
-					solveJoint( P, V, joint, true );
-					jointEventTest( P, joint );
-				},
-				[&]( int k ) { solveContact( P, V, k, true ); } );
-			__syncthreads();
-		}
-		clk.lap( b2GpuStage_solveImpulses );
-
-		forEachLocal( bodyCount, [&]( int i ) { integratePositions( P, V, i ); } );
-		__syncthreads();
-		clk.lap( b2GpuStage_integratePositions );
-
-		overflowLevels(
-			overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
-			[&]( int k ) { solveContactOverflow( P, V, k, false ); }, blockSync );
-		for ( int pass = 0; pass < passes; ++pass )
-		{
-			forEachInLocalColor(
-				passRange[pass], [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
-				[&]( int k ) { solveContact( P, V, k, false ); } );
-			__syncthreads();
-		}
-		clk.lap( b2GpuStage_relaxImpulses );
-	}
-
-	if ( anyRestitution != 0 )
-	{
-		if ( ovCe > ovCb )
-		{
 			overflowLevels(
-				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, []( int ) {}, [&]( int k ) { restitutionContactOverflow( P, V, k ); },
-				blockSync );
+				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); },
+				[&]( int k ) { warmStartContactOverflow( V, k ); }, blockSync, stageThreads );
+			for ( int pass = 0; pass < passes; ++pass )
+			{
+				forEachInLocalColor(
+					passRange[pass], stageThreads, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); }, [&]( int k ) { warmStartContact( V, k ); } );
+				blockSync();
+			}
+			clk.lap( b2GpuStage_warmStart );
+
+			overflowLevels(
+				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), true ); },
+				[&]( int k ) { solveContactOverflow( P, V, k, true ); }, blockSync, stageThreads );
+			for ( int pass = 0; pass < passes; ++pass )
+			{
+				forEachInLocalColor(
+					passRange[pass], stageThreads,
+					[&]( int k ) {
+						b2lJointSim* joint = jointAt( V, k );
+						solveJoint( P, V, joint, true );
+						jointEventTest( P, joint );
+					},
+					[&]( int k ) { solveContact( P, V, k, true ); } );
+				blockSync();
+			}
+			clk.lap( b2GpuStage_solveImpulses );
+
+			forEachLocal( bodyCount, stageThreads, [&]( int i ) { integratePositions( P, V, i ); } );
+			blockSync();
+			clk.lap( b2GpuStage_integratePositions );
+
+			overflowLevels(
+				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+				[&]( int k ) { solveContactOverflow( P, V, k, false ); }, blockSync, stageThreads );
+			for ( int pass = 0; pass < passes; ++pass )
+			{
+				forEachInLocalColor(
+					passRange[pass], stageThreads, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+					[&]( int k ) { solveContact( P, V, k, false ); } );
+				blockSync();
+			}
+			clk.lap( b2GpuStage_relaxImpulses );
 		}
-		for ( int pass = 0; pass < passes; ++pass )
+
+		if ( anyRestitution != 0 )
 		{
-			int4 r = passRange[pass];
-			if ( r.z == r.w )
+			if ( ovCe > ovCb )
 			{
-				continue;
+				overflowLevels(
+					overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, []( int ) {}, [&]( int k ) { restitutionContactOverflow( P, V, k ); },
+					blockSync, stageThreads );
 			}
-			for ( int k = r.z + (int)threadIdx.x; k < r.w; k += (int)blockDim.x )
+			for ( int pass = 0; pass < passes; ++pass )
 			{
-				restitutionContact( P, V, k );
+				int4 r = passRange[pass];
+				if ( r.z == r.w )
+				{
+					continue;
+				}
+				for ( int k = r.z + (int)threadIdx.x; k < r.w; k += stageThreads )
+				{
+					restitutionContact( P, V, k );
+				}
+				blockSync();
 			}
-			__syncthreads();
 		}
+		clk.lap( b2GpuStage_applyRestitution );
 	}
-	clk.lap( b2GpuStage_applyRestitution );
+	__syncthreads();
 
 	// store: impulses by wire slot, states by global body index, joints with their global body indices restored
 	forEachLocal( contactCount, [&]( int k ) { storeContact( P, V, k, wireSlot[k], k < ovCb || k >= ovCe ); } );

@@ -350,6 +350,8 @@ struct b2GpuSolver
 	DeviceBuffer<int> binCounters; // [binBodyCount | binColorStart | binJointStart | binFail], zeroed every run
 	DeviceBuffer<int> bodyLocal, binBodyList, slotGroupBits, binContactList, binJointList;
 	DeviceBuffer<int4> binContactInfo;
+	double islandHeadRoom = 1.3; // bins are sized for this many times the average bytes per bin
+	int headRoomCooldown = 0;	 // steps to wait after a failure before lowering it again
 	int countersBinCount = 0;
 	bool countersClean = false; // the bin counters are all zero (the island kernels zero what they have read)
 	DeviceBuffer<int2> contactBinRank, jointBinRank;
@@ -358,6 +360,8 @@ struct b2GpuSolver
 	size_t binCounterCount = 0;
 	size_t islandSmemBytes = 0;
 	size_t islandSmemBudget = 0;
+	bool resolveContacts = true; // diagnostics: B2GPU_RESOLVE=0 makes the island kernels chase head -> bodyLocal themselves
+	bool stageAllThreads = false;
 	bool testTightBins = false;			 // testing: B2GPU_TEST_TIGHT_BINS=1 makes every island step fail over to the grid kernel
 	int clusterForce = 0;				 // testing: smallest cluster size the planner may use (B2GPU_CLUSTER_FORCE)
 	int clusterBins[4] = { 0, 0, 0, 0 }; // resident clusters of 2, 4, 8, 16 blocks (0 = not available)
@@ -525,6 +529,10 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		// clusters of 2, 4, 8, 16 blocks with the same carve-up: how many can be resident at once
 		const char* traceEnv = getenv( "B2GPU_TRACE" );
 		s->trace = traceEnv != nullptr && atoi( traceEnv ) != 0;
+		const char* resolveEnv = getenv( "B2GPU_RESOLVE" );
+		s->resolveContacts = resolveEnv == nullptr || atoi( resolveEnv ) != 0;
+		const char* stageEnv = getenv( "B2GPU_STAGE_ALL" );
+		s->stageAllThreads = stageEnv != nullptr && atoi( stageEnv ) != 0;
 		const char* tightEnv = getenv( "B2GPU_TEST_TIGHT_BINS" );
 		s->testTightBins = tightEnv != nullptr && atoi( tightEnv ) != 0;
 		const char* forceEnv = getenv( "B2GPU_CLUSTER_FORCE" );
@@ -707,8 +715,9 @@ static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimi
 	const double bytesPerBody = 52.0, bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0, bytesPerJoint = b2g::kJointStride + 12.0;
 	double totalBytes = bodies * bytesPerBody + s->contactTotal * bytesPerContact + s->jointTotal * bytesPerJoint;
 	int binLimit = binLimitIn < islandCount ? binLimitIn : islandCount;
-	// head room for uneven constraint density between bins; a cluster exists for the few largest islands, deal exactly
-	double headRoom = share > 1 ? 1.1 : 1.6;
+	// head room for uneven constraint density between bins (adaptive: raised when a bin did not fit, lowered slowly while
+	// all is well); a cluster exists for the few largest islands, deal exactly
+	double headRoom = share > 1 ? 1.1 : s->islandHeadRoom;
 	int wanted = (int)( totalBytes * headRoom / ( (double)budget * share ) ) + 1;
 	if ( wanted > binLimit )
 	{
@@ -834,6 +843,14 @@ static int b2gPlanIslands( b2GpuSolver* s )
 
 	// One block per bin when that fits; otherwise clusters of 2..16 blocks per bin (b2g_cluster.cuh), the smallest that
 	// holds the largest bin.  If nothing fits the grid-barrier kernel takes the step.
+	if ( s->headRoomCooldown > 0 )
+	{
+		s->headRoomCooldown -= 1;
+	}
+	else if ( s->islandHeadRoom > 1.2 )
+	{
+		s->islandHeadRoom = s->islandHeadRoom * 0.995 > 1.2 ? s->islandHeadRoom * 0.995 : 1.2;
+	}
 	b2gBinPlan plan;
 	bool planned = s->clusterForce <= 1 && b2gPlanBins( s, islandCount, 1, s->smCount, true, &plan );
 	for ( int k = 0; !planned && k < 4; ++k )
@@ -880,6 +897,8 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	P.capContacts = capC;
 	P.capJoints = capJ;
 	P.clusterSize = plan.share;
+	P.stageAllThreads = s->stageAllThreads ? 1 : 0;
+	P.resolveContacts = s->resolveContacts ? 1 : 0;
 	P.clusterShift = plan.shift;
 	P.binCapBodies = capB * plan.share;
 	P.binCapContacts = capC * plan.share;
@@ -1542,6 +1561,8 @@ static int b2gRerunIfIslandsFailed( b2GpuSolver* s, bool download )
 		return 0;
 	}
 	s->countersClean = false; // the island kernels returned before zeroing their counters
+	s->islandHeadRoom = s->islandHeadRoom * 1.3 < 3.0 ? s->islandHeadRoom * 1.3 : 3.0;
+	s->headRoomCooldown = 512;
 	B2G_CUDA( cudaMemsetAsync( s->control, 0, sizeof( ControlBlock ), s->stream ) );
 	if ( b2gLaunchGridKernel( s ) != 0 )
 	{

@@ -146,6 +146,8 @@ struct StepParams
 	// shared memory.  Scratch written by the partition kernel, read by the island kernel.
 	int binCount;	   // 0 = island mode off for this step
 	int clusterSize;   // thread blocks per bin (1 = one block per bin, no cluster)
+	int resolveContacts; // the partition kernel fills binContactInfo; 0 (diagnostics): the island kernels chase head -> bodyLocal themselves
+	int stageAllThreads; // diagnostics: every thread of a block walks the stage loops (B2GPU_STAGE_ALL=1)
 	int clusterShift;  // log2 of the bodies per block in cluster mode
 	int capBodies;	   // per-BLOCK capacities the shared memory carve-up was sized for (a bin holds clusterSize times that)
 	int capContacts;
