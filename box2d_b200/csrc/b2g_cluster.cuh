@@ -3,8 +3,8 @@
 // One big island (a 5000-body pyramid, the contents of a tumbler) cannot be split: every colour of it has to be
 // finished before the next starts.  The grid-barrier kernel pays ~2 us per colour for that (1.2 us barrier + the L2
 // round trips of the stage body).  Here up to 16 thread blocks of one cluster share the bin instead:
-//   * the bin's bodies are dealt out in runs of 2^clusterShift, a block keeps its run in shared memory and the other
-//     blocks of the cluster read / write it through distributed shared memory (SolveView::clusterShift),
+//   * the bin's bodies are dealt out in equal runs, a block keeps its run in shared memory and the other blocks of the
+//     cluster read / write it through distributed shared memory (SolveView::clusterRun),
 //   * every colour of the bin is dealt out evenly over the blocks, a block keeps its share of the constraints in its
 //     own shared memory for the whole step,
 //   * colours are separated by the hardware cluster barrier (~0.25 us measured, tools/microbench/barrier_bench.cu).
@@ -88,8 +88,8 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	cursor += (size_t)capC * sizeof( int );
 	int* wireSlot = reinterpret_cast<int*>( cursor );
 	V.anyRestitution = &anyRestitution;
-	V.clusterShift = P.clusterShift;
-	V.clusterMask = ( 1 << P.clusterShift ) - 1;
+	V.clusterRun = P.clusterRun;
+	V.clusterMagic = P.clusterMagic;
 	V.asyncBar = 0;
 	SolveView VA = V; // same view, body writes as counted st.async stores
 	const unsigned barAddr = (unsigned)__cvta_generic_to_shared( &arrivalBar );
@@ -98,12 +98,15 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 
 	// this block's run of the bin's bodies
 	const int binBodies = P.binBodyCount[bin];
-	const int bodyBegin = min( binBodies, rank << P.clusterShift );
-	const int bodyCount = min( binBodies - bodyBegin, 1 << P.clusterShift );
+	const int bodyBegin = min( binBodies, rank * P.clusterRun );
+	const int bodyCount = min( binBodies - bodyBegin, P.clusterRun );
 	const int* bodyList = P.binBodyList + (size_t)bin * P.binCapBodies + bodyBegin;
-	const int* contactList = P.binContactList + (size_t)bin * P.binCapContacts;
-	const int4* contactInfo = P.binContactInfo + (size_t)bin * P.binCapContacts;
-	const int* jointList = P.binJointList + (size_t)bin * P.binCapJoints;
+	// the constraint lists this block reads: its slice of the bin's lists, or -- owner lists -- its own list
+	const bool ownerLists = P.ownerLists != 0;
+	const int list = ownerLists ? rank : bin;
+	const int* contactList = P.binContactList + (size_t)list * P.listCapContacts;
+	const int4* contactInfo = P.binContactInfo + (size_t)list * P.listCapContacts;
+	const int* jointList = P.binJointList + (size_t)list * P.listCapJoints;
 
 	StageClock clk;
 	clk.start();
@@ -111,26 +114,28 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 
 	if ( threadIdx.x == 0 )
 	{
-		const int* startC = P.binColorOffset + (size_t)bin * kColorSlots;
-		const int* startJ = P.binJointOffset + (size_t)bin * kColorSlots;
+		const int* startC = P.binColorOffset + (size_t)list * kColorSlots;
+		const int* startJ = P.binJointOffset + (size_t)list * kColorSlots;
 		int localC = 0, localJ = 0;
 		for ( int c = 0; c < slotCount; ++c )
 		{
 			bool isOverflow = c == colorCount;
+			// even dealing: a slice of the bin's colour; owner lists: the whole colour of this block's own list
+			bool whole = ownerLists || isOverflow;
 			int s0 = startC[c], n = startC[c + 1] - s0;
-			int lo = isOverflow ? s0 : s0 + n * rank / share;
-			int hi = isOverflow ? ( rank == 0 ? s0 + n : s0 ) : s0 + n * ( rank + 1 ) / share;
+			int lo = whole ? s0 : s0 + n * rank / share;
+			int hi = whole ? ( ownerLists || rank == 0 ? s0 + n : s0 ) : s0 + n * ( rank + 1 ) / share;
 			listBeginC[c] = lo;
 			localStartC[c] = localC;
-			binCountC[c] = n;
+			binCountC[c] = ownerLists ? P.binColorTotal[c] : n;
 			localC += hi - lo;
 
 			s0 = startJ[c], n = startJ[c + 1] - s0;
-			lo = isOverflow ? s0 : s0 + n * rank / share;
-			hi = isOverflow ? ( rank == 0 ? s0 + n : s0 ) : s0 + n * ( rank + 1 ) / share;
+			lo = whole ? s0 : s0 + n * rank / share;
+			hi = whole ? ( ownerLists || rank == 0 ? s0 + n : s0 ) : s0 + n * ( rank + 1 ) / share;
 			listBeginJ[c] = lo;
 			localStartJ[c] = localJ;
-			binCountJ[c] = n;
+			binCountJ[c] = ownerLists ? P.binColorTotal[kColorSlots + c] : n;
 			localJ += hi - lo;
 		}
 		localStartC[slotCount] = localC;
@@ -148,14 +153,19 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	forEachLocal( bodyCount, [&]( int i ) { loadBody( P, V, bodyList[i], i + 1 ); } );
 	cluster.sync(); // every block of the cluster is running and its bodies are in place
 	// every block has read the bin's counters: leave them zeroed for the next step's partition kernel
-	if ( rank == 0 )
+	if ( rank == 0 || ownerLists )
 	{
 		if ( threadIdx.x < kColorSlots )
 		{
-			P.binColorStart[(size_t)bin * kColorSlots + threadIdx.x] = 0;
-			P.binJointStart[(size_t)bin * kColorSlots + threadIdx.x] = 0;
+			P.binColorStart[(size_t)list * kColorSlots + threadIdx.x] = 0;
+			P.binJointStart[(size_t)list * kColorSlots + threadIdx.x] = 0;
+			if ( ownerLists && rank == 0 )
+			{
+				P.binColorTotal[threadIdx.x] = 0;
+				P.binColorTotal[kColorSlots + threadIdx.x] = 0;
+			}
 		}
-		if ( threadIdx.x == 0 )
+		if ( threadIdx.x == 0 && rank == 0 )
 		{
 			P.binBodyCount[bin] = 0;
 		}
@@ -210,11 +220,11 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 			// tell the owners of the two bodies what to expect from this contact in every pass over its colour
 			if ( ( __float_as_uint( sA.w ) & B2L_FLAG_DYNAMIC ) != 0 )
 			{
-				atomicAdd( cluster.map_shared_rank( expectBytes, ( (unsigned)localA - 1u ) >> P.clusterShift ) + c, (int)sizeof( float4 ) );
+				atomicAdd( cluster.map_shared_rank( expectBytes, clusterOwner( V, (unsigned)localA - 1u ) ) + c, (int)sizeof( float4 ) );
 			}
 			if ( ( __float_as_uint( sB.w ) & B2L_FLAG_DYNAMIC ) != 0 )
 			{
-				atomicAdd( cluster.map_shared_rank( expectBytes, ( (unsigned)localB - 1u ) >> P.clusterShift ) + c, (int)sizeof( float4 ) );
+				atomicAdd( cluster.map_shared_rank( expectBytes, clusterOwner( V, (unsigned)localB - 1u ) ) + c, (int)sizeof( float4 ) );
 			}
 		}
 		prepareContact( P, V, slot, k, localA, localB, sA, sB, wide, groupBits );

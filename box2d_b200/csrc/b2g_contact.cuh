@@ -31,19 +31,25 @@ B2G_DEV int rawI( const uint8_t* base, int offset )
 // scatter is guarded by b2_dynamicFlag exactly like the reference (contact_solver.c:1531).
 // Plain generic loads/stores: the view may live in shared memory (island-local kernel) or in global memory
 // (grid-barrier kernel, where the barrier's release/acquire pair orders them across blocks).
+// block of the cluster that owns body `linear` (0-based index inside the bin): linear / clusterRun
+B2G_DEV unsigned clusterOwner( const SolveView& V, unsigned linear )
+{
+	return __umulhi( linear, V.clusterMagic );
+}
+
 // distributed shared memory address of slot `index` of a per-block body array (cluster mode)
 template <typename T> B2G_DEV T* clusterSlot( const SolveView& V, T* localArray, int index )
 {
 	unsigned linear = (unsigned)index - 1u;
-	unsigned owner = linear >> V.clusterShift;
-	unsigned slot = ( linear & (unsigned)V.clusterMask ) + 1u;
+	unsigned owner = clusterOwner( V, linear );
+	unsigned slot = linear - owner * (unsigned)V.clusterRun + 1u;
 	T* remote = static_cast<T*>( __cluster_map_shared_rank( static_cast<void*>( localArray ), owner ) );
 	return remote + slot;
 }
 
 B2G_DEV float4 gatherVel( const SolveView& V, int index )
 {
-	if ( V.clusterShift < 0 || index == 0 )
+	if ( V.clusterRun == 0 || index == 0 )
 	{
 		return V.vel[index];
 	}
@@ -52,7 +58,7 @@ B2G_DEV float4 gatherVel( const SolveView& V, int index )
 
 B2G_DEV float4 gatherPos( const SolveView& V, int index )
 {
-	if ( V.clusterShift < 0 || index == 0 )
+	if ( V.clusterRun == 0 || index == 0 )
 	{
 		return V.pos[index];
 	}
@@ -63,7 +69,7 @@ B2G_DEV void scatterVel( const SolveView& V, int index, float4 v )
 {
 	if ( ( __float_as_uint( v.w ) & B2L_FLAG_DYNAMIC ) != 0 )
 	{
-		if ( V.clusterShift < 0 )
+		if ( V.clusterRun == 0 )
 		{
 			V.vel[index] = v;
 		}
@@ -76,8 +82,8 @@ B2G_DEV void scatterVel( const SolveView& V, int index, float4 v )
 			// the owner block counts the bytes that arrive for its bodies (mbarrier transaction count) instead of every
 			// writer fencing its stores at GPU scope
 			unsigned linear = (unsigned)index - 1u;
-			unsigned owner = linear >> V.clusterShift;
-			unsigned slot = ( linear & (unsigned)V.clusterMask ) + 1u;
+			unsigned owner = clusterOwner( V, linear );
+			unsigned slot = linear - owner * (unsigned)V.clusterRun + 1u;
 			unsigned local = (unsigned)__cvta_generic_to_shared( V.vel ) + slot * (unsigned)sizeof( float4 );
 			unsigned remote, remoteBar;
 			asm volatile( "mapa.shared::cluster.u32 %0, %1, %2;" : "=r"( remote ) : "r"( local ), "r"( owner ) );

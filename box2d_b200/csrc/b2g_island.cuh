@@ -76,7 +76,25 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 			P.jointBits[i] = 0u;
 		}
 	} );
-	forEachItem( P.bodyCount, [&]( int b ) {
+	// Owner lists (one bin shared by a cluster): the bodies keep their order -- neighbours in the awake set are neighbours
+	// in the scene more often than not -- and every constraint goes to the list of the block that owns its first body,
+	// so that most gathers and scatters of the cluster kernel stay in the block's own shared memory.
+	const bool ownerLists = P.ownerLists != 0;
+	if ( ownerLists )
+	{
+		forEachItem( P.bodyCount, [&]( int b ) {
+			if ( b < P.bodyCount )
+			{
+				P.binBodyList[b] = b;
+				P.bodyLocal[b] = b + 1;
+			}
+		} );
+		if ( blockIdx.x == 0 && threadIdx.x == 0 )
+		{
+			P.binBodyCount[0] = P.bodyCount;
+		}
+	}
+	forEachItem( ownerLists ? 0 : P.bodyCount, [&]( int b ) {
 		bool active = b < P.bodyCount;
 		int bin = active ? P.bodyBin[b] : -1;
 		int local = aggregatedAdd( P.binBodyCount, bin, active );
@@ -118,7 +136,10 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 		{
 			int indexA = __float_as_int( head.x );
 			int indexB = __float_as_int( head.y );
-			bin = P.bodyBin[indexA >= 0 ? indexA : indexB];
+			int first = indexA >= 0 ? indexA : indexB;
+			// the list of the constraint: its bin, or -- owner lists -- the block that owns its first body (the overflow
+			// colour is solved by the cluster's first block)
+			bin = ownerLists ? ( isOverflow ? 0 : (int)__umulhi( (unsigned)first, P.clusterMagic ) ) : P.bodyBin[first];
 			key = bin * kColorSlots + c;
 		}
 		int rank = aggregatedAdd( P.binColorStart, key, active );
@@ -140,7 +161,7 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 			}
 			int body = jointBodyForBin( P.rawJoints + (size_t)j * kJointStride );
 			// a filter joint has no solver data: park it in bin 0, it is a no-op in every stage
-			bin = body >= 0 ? P.bodyBin[body] : 0;
+			bin = body < 0 ? 0 : ownerLists ? ( c == P.colorCount ? 0 : (int)__umulhi( (unsigned)body, P.clusterMagic ) ) : P.bodyBin[body];
 			key = bin * kColorSlots + c;
 		}
 		int rank = aggregatedAdd( P.binJointStart, key, active );
@@ -154,8 +175,8 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 	// phase 2: the counts are final.  One thread per bin turns them into the exclusive offsets the island kernels read
 	// (colour-major layout of the bin's lists) and checks the capacities; the placement passes below do not wait for
 	// that, every constraint sums the counts of the colours before its own (a handful of L2 hits).
-	forEachItem( P.binCount, [&]( int bin ) {
-		if ( bin < P.binCount )
+	forEachItem( P.listCount, [&]( int bin ) {
+		if ( bin < P.listCount )
 		{
 			const int* contactCount = P.binColorStart + (size_t)bin * kColorSlots;
 			const int* jointCount = P.binJointStart + (size_t)bin * kColorSlots;
@@ -174,8 +195,14 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 				int m = jointCount[c];
 				jointOffset[c] = joints;
 				joints += m;
-				blockContacts += c < P.colorCount ? ( n + share - 1 ) / share : n;
-				blockJoints += c < P.colorCount ? ( m + share - 1 ) / share : m;
+				blockContacts += c < P.colorCount && !ownerLists ? ( n + share - 1 ) / share : n;
+				blockJoints += c < P.colorCount && !ownerLists ? ( m + share - 1 ) / share : m;
+				if ( ownerLists && ( n | m ) != 0 )
+				{
+					// what the whole bin has of this colour (every block of the cluster must agree on skipping a colour)
+					atomicAdd( P.binColorTotal + c, n );
+					atomicAdd( P.binColorTotal + kColorSlots + c, m );
+				}
 				if ( c == P.colorCount && ( n > kMaxBinOverflow || m > kMaxBinOverflow ) )
 				{
 					*P.binFail = 1;
@@ -219,17 +246,17 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 		{
 			int2 br = P.contactBinRank[slot];
 			int dest = offsetOf( P.binColorStart, br.x, c ) + br.y;
-			if ( dest < P.binCapContacts ) // a bin that does not fit raised binFail above
+			if ( dest < P.listCapContacts ) // a list that does not fit raised binFail above
 			{
 				// everything the island kernel needs to start preparing the contact without chasing pointers: the
 				// wire slot, the bodies' indices inside the bin, the SIMD-group bits
-				P.binContactList[(size_t)br.x * P.binCapContacts + dest] = slot;
+				P.binContactList[(size_t)br.x * P.listCapContacts + dest] = slot;
 				if ( P.resolveContacts != 0 )
 				{
 					int indexA = __float_as_int( head.x ), indexB = __float_as_int( head.y );
 					int localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;
 					int localB = indexB >= 0 ? P.bodyLocal[indexB] : 0;
-					P.binContactInfo[(size_t)br.x * P.binCapContacts + dest] = make_int4( slot, localA, localB, P.slotGroupBits[slot] );
+					P.binContactInfo[(size_t)br.x * P.listCapContacts + dest] = make_int4( slot, localA, localB, P.slotGroupBits[slot] );
 				}
 			}
 		}
@@ -244,9 +271,9 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 			}
 			int2 br = P.jointBinRank[j];
 			int dest = offsetOf( P.binJointStart, br.x, c ) + br.y;
-			if ( dest < P.binCapJoints )
+			if ( dest < P.listCapJoints )
 			{
-				P.binJointList[(size_t)br.x * P.binCapJoints + dest] = j;
+				P.binJointList[(size_t)br.x * P.listCapJoints + dest] = j;
 			}
 		}
 	} );
@@ -496,8 +523,8 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	cursor += (size_t)capC * sizeof( int );
 	int* wireSlot = reinterpret_cast<int*>( cursor );
 	V.anyRestitution = &anyRestitution;
-	V.clusterShift = -1;
-	V.clusterMask = 0;
+	V.clusterRun = 0;
+	V.clusterMagic = 0;
 	V.asyncBar = 0;
 
 	const int bodyCount = P.binBodyCount[bin];

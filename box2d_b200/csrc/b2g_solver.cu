@@ -352,7 +352,9 @@ struct b2GpuSolver
 	DeviceBuffer<int4> binContactInfo;
 	double islandHeadRoom = 1.3; // bins are sized for this many times the average bytes per bin
 	int headRoomCooldown = 0;	 // steps to wait after a failure before lowering it again
-	int countersBinCount = 0;
+	int countersBinCount = 0, countersListCount = 0;
+	int ownerListsOff = 0;		 // steps during which owner lists stay off after a block's share did not fit
+	bool ownerListsEnabled = true; // B2GPU_OWNER_LISTS=0 turns them off
 	bool countersClean = false; // the bin counters are all zero (the island kernels zero what they have read)
 	DeviceBuffer<int2> contactBinRank, jointBinRank;
 	std::vector<int> islandBin;	 // host: bin of every awake island
@@ -529,6 +531,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		// clusters of 2, 4, 8, 16 blocks with the same carve-up: how many can be resident at once
 		const char* traceEnv = getenv( "B2GPU_TRACE" );
 		s->trace = traceEnv != nullptr && atoi( traceEnv ) != 0;
+		const char* ownerEnv = getenv( "B2GPU_OWNER_LISTS" );
+		s->ownerListsEnabled = ownerEnv == nullptr || atoi( ownerEnv ) != 0;
 		const char* resolveEnv = getenv( "B2GPU_RESOLVE" );
 		s->resolveContacts = resolveEnv == nullptr || atoi( resolveEnv ) != 0;
 		const char* stageEnv = getenv( "B2GPU_STAGE_ALL" );
@@ -701,7 +705,7 @@ static int b2gFindSegment( const std::vector<int>& starts, int flat )
 
 struct b2gBinPlan
 {
-	int binCount, share, shift, capB, capC, capJ;
+	int binCount, share, capB, capC, capJ;
 };
 
 // Bins for blocks-per-bin = share.  Island i goes to the bin its first body falls in when the islands are laid end to
@@ -749,16 +753,16 @@ static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimi
 	// capacities PER BLOCK: exact for bodies (a power of two per block when the bin is shared by a cluster); the rest
 	// of the budget is split between contacts and joints in proportion to their estimated bytes, so a bin may hold
 	// several times its fair share before binFail trips
-	int capB = ( maxBin + 3 ) & ~3, shift = -1;
+	int capB = ( maxBin + 3 ) & ~3;
 	if ( share > 1 )
 	{
-		int perBlock = ( maxBin + share - 1 ) / share;
-		shift = 2;
-		while ( ( 1 << shift ) < perBlock )
+		// equal runs of the bin's bodies (a multiple of 4 keeps the carve-up 16-byte aligned); the owner of a body is
+		// found with a multiply-high, exact below 65536 bodies per bin
+		capB = ( ( maxBin + share - 1 ) / share + 3 ) & ~3;
+		if ( maxBin >= 65536 )
 		{
-			shift += 1;
+			return false;
 		}
-		capB = 1 << shift;
 	}
 	double fraction = (double)maxBin / (double)bodies / (double)share;
 	// a block of a cluster holds ceil(n / share) of every colour, the first block the bin's overflow colour on top
@@ -798,7 +802,7 @@ static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimi
 	{
 		return false;
 	}
-	*plan = { binCount, share, shift, capB, capC, capJ };
+	*plan = { binCount, share, capB, capC, capJ };
 	return true;
 }
 
@@ -871,16 +875,27 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	}
 	const int binCount = plan.binCount, capB = plan.capB, capC = plan.capC, capJ = plan.capJ;
 
+	// Owner lists (b2g_island.cuh): one bin shared by a cluster, constraints go to the block that owns their first body.
+	// The blocks' shares are then as uneven as the scene; if one does not fit, the step is rerun and even dealing is used
+	// for a while.
+	if ( s->ownerListsOff > 0 )
+	{
+		s->ownerListsOff -= 1;
+	}
+	const bool ownerLists = plan.share > 1 && binCount == 1 && s->ownerListsOff == 0 && s->ownerListsEnabled;
+	const int listCount = ownerLists ? plan.share : binCount;
 	size_t slots = (size_t)P.contactSlots;
-	s->binCounterCount = (size_t)binCount * ( 1 + 2 * b2g::kColorSlots ) + 1; // the part that is zeroed every step
+	// zeroed every step: [binBodyCount][contact counts per list and colour][joint counts][binFail][bin-wide totals]
+	s->binCounterCount = (size_t)binCount + (size_t)listCount * 2 * b2g::kColorSlots + 1 + 2 * b2g::kColorSlots;
 	{
 		const int* before = s->binCounters.ptr;
-		B2G_CUDA( s->binCounters.reserve( s->binCounterCount + (size_t)binCount * 2 * b2g::kColorSlots ) );
-		if ( s->binCounters.ptr != before || binCount != s->countersBinCount )
+		B2G_CUDA( s->binCounters.reserve( s->binCounterCount + (size_t)listCount * 2 * b2g::kColorSlots ) );
+		if ( s->binCounters.ptr != before || binCount != s->countersBinCount || listCount != s->countersListCount )
 		{
 			s->countersClean = false; // fresh memory, or the tables move (the offset tables behind them are not zero)
 		}
 		s->countersBinCount = binCount;
+		s->countersListCount = listCount;
 	}
 	B2G_CUDA( s->bodyLocal.reserve( (size_t)bodies + 1 ) );
 	const size_t share = (size_t)plan.share;
@@ -899,18 +914,24 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	P.clusterSize = plan.share;
 	P.stageAllThreads = s->stageAllThreads ? 1 : 0;
 	P.resolveContacts = s->resolveContacts ? 1 : 0;
-	P.clusterShift = plan.shift;
+	P.clusterRun = plan.share > 1 ? plan.capB : 0;
+	P.clusterMagic = plan.share > 1 ? (unsigned)( ( ( 1ull << 32 ) + (unsigned)plan.capB - 1ull ) / (unsigned)plan.capB ) : 0u;
 	P.binCapBodies = capB * plan.share;
 	P.binCapContacts = capC * plan.share;
 	P.binCapJoints = capJ * plan.share;
 	P.bodyBin = reinterpret_cast<const int*>( s->wireAll.ptr + s->inBins );
 	P.bodyLocal = s->bodyLocal.ptr;
+	P.ownerLists = ownerLists ? 1 : 0;
+	P.listCount = listCount;
+	P.listCapContacts = ownerLists ? capC : capC * plan.share;
+	P.listCapJoints = ownerLists ? capJ : capJ * plan.share;
 	P.binBodyCount = s->binCounters.ptr;
 	P.binColorStart = s->binCounters.ptr + binCount;
-	P.binJointStart = P.binColorStart + (size_t)binCount * b2g::kColorSlots;
-	P.binFail = P.binJointStart + (size_t)binCount * b2g::kColorSlots;
-	P.binColorOffset = P.binFail + 1;
-	P.binJointOffset = P.binColorOffset + (size_t)binCount * b2g::kColorSlots;
+	P.binJointStart = P.binColorStart + (size_t)listCount * b2g::kColorSlots;
+	P.binFail = P.binJointStart + (size_t)listCount * b2g::kColorSlots;
+	P.binColorTotal = P.binFail + 1;
+	P.binColorOffset = P.binColorTotal + 2 * b2g::kColorSlots;
+	P.binJointOffset = P.binColorOffset + (size_t)listCount * b2g::kColorSlots;
 	P.binBodyList = s->binBodyList.ptr;
 	P.contactBinRank = s->contactBinRank.ptr;
 	P.slotGroupBits = s->slotGroupBits.ptr;
@@ -1185,8 +1206,8 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	P.hasHitEvents = &s->control->hasHitEvents;
 	P.g.anyRestitution = &s->control->anyRestitution;
 	P.islandFailed = &s->control->islandFailed;
-	P.g.clusterShift = -1;
-	P.g.clusterMask = 0;
+	P.g.clusterRun = 0;
+	P.g.clusterMagic = 0;
 	P.g.asyncBar = 0;
 	P.barrier = s->control->barrier;
 	P.stageCycles = s->control->stageCycles;
@@ -1561,8 +1582,15 @@ static int b2gRerunIfIslandsFailed( b2GpuSolver* s, bool download )
 		return 0;
 	}
 	s->countersClean = false; // the island kernels returned before zeroing their counters
-	s->islandHeadRoom = s->islandHeadRoom * 1.3 < 3.0 ? s->islandHeadRoom * 1.3 : 3.0;
-	s->headRoomCooldown = 512;
+	if ( s->params.ownerLists != 0 )
+	{
+		s->ownerListsOff = 512; // a block's share did not fit: deal the colours out evenly for a while
+	}
+	else
+	{
+		s->islandHeadRoom = s->islandHeadRoom * 1.3 < 3.0 ? s->islandHeadRoom * 1.3 : 3.0;
+		s->headRoomCooldown = 512;
+	}
 	B2G_CUDA( cudaMemsetAsync( s->control, 0, sizeof( ControlBlock ), s->stream ) );
 	if ( b2gLaunchGridKernel( s ) != 0 )
 	{

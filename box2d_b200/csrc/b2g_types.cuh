@@ -91,11 +91,12 @@ struct SolveView
 	int* cmeta;	   // kMeta* bits
 	uint8_t* joints; // b2JointSim working copy (indexA/indexB in the view's numbering, 0-based, -1 = static)
 	int* anyRestitution; // set by prepare when a contact of the view has restitution != 0
-	// Cluster mode (island kernel on a thread-block cluster): the body arrays are distributed over the blocks'
-	// shared memory; body index i (1-based, 0 = this block's own static dummy) lives in block (i-1) >> clusterShift at
-	// slot ((i-1) & clusterMask) + 1 and is reached through distributed shared memory.  clusterShift < 0: flat view.
-	int clusterShift;
-	int clusterMask;
+	// Cluster mode (island kernel on a thread-block cluster): the body arrays are distributed over the blocks' shared
+	// memory in runs of clusterRun bodies; body index i (1-based, 0 = this block's own static dummy) lives in block
+	// (i-1) / clusterRun at slot (i-1) % clusterRun + 1 and is reached through distributed shared memory.  The division
+	// is a multiply-high with clusterMagic = ceil(2^32 / clusterRun), exact for i < 65536.  clusterRun == 0: flat view.
+	int clusterRun;
+	unsigned clusterMagic;
 	// != 0: body writes are st.async stores that report to the owner block's mbarrier at this shared::cta address
 	// (b2g_cluster.cuh); 0: plain stores
 	unsigned asyncBar;
@@ -148,10 +149,15 @@ struct StepParams
 	int clusterSize;   // thread blocks per bin (1 = one block per bin, no cluster)
 	int resolveContacts; // the partition kernel fills binContactInfo; 0 (diagnostics): the island kernels chase head -> bodyLocal themselves
 	int stageAllThreads; // diagnostics: every thread of a block walks the stage loops (B2GPU_STAGE_ALL=1)
-	int clusterShift;  // log2 of the bodies per block in cluster mode
+	int clusterRun;	   // bodies per block in cluster mode
+	unsigned clusterMagic; // ceil(2^32 / clusterRun)
 	int capBodies;	   // per-BLOCK capacities the shared memory carve-up was sized for (a bin holds clusterSize times that)
 	int capContacts;
 	int capJoints;
+	int ownerLists;	   // one bin shared by a cluster: constraint lists per BLOCK, keyed by the owner of the first body
+	int listCount;	   // number of constraint lists: binCount, or clusterSize with owner lists
+	int listCapContacts; // stride of the constraint lists (binCap*, or the per-block capacity with owner lists)
+	int listCapJoints;
 	int binCapBodies;  // strides of the per-bin lists: capacity of a whole bin (= per-block capacity * clusterSize)
 	int binCapContacts;
 	int binCapJoints;
@@ -161,6 +167,7 @@ struct StepParams
 	int* binBodyList;	 // [binCount * binCapBodies] global body index
 	int* binColorStart;	 // [binCount * kColorSlots] contact counts per colour (+ the overflow bucket)
 	int* binJointStart;	 // same for joints
+	int* binColorTotal;	 // [2 * kColorSlots] owner lists: contacts / joints of the whole bin per colour
 	int* binColorOffset; // [binCount * kColorSlots] exclusive offsets of the colours in the bin's contact list (+ total)
 	int* binJointOffset; // same for joints
 	int2* contactBinRank; // [contactSlots] bin, rank within (bin, colour)
