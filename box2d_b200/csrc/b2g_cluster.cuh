@@ -112,10 +112,20 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	clk.start();
 	long long begin = clk.last;
 
+	// the tables of this block's list: loaded by one thread per entry (a dependent global load each), combined by one
+	__shared__ int rawStartC[kColorSlots], rawStartJ[kColorSlots], rawTotal[2 * kColorSlots];
+	if ( threadIdx.x < kColorSlots )
+	{
+		rawStartC[threadIdx.x] = P.binColorOffset[(size_t)list * kColorSlots + threadIdx.x];
+		rawStartJ[threadIdx.x] = P.binJointOffset[(size_t)list * kColorSlots + threadIdx.x];
+		rawTotal[threadIdx.x] = ownerLists ? P.binColorTotal[threadIdx.x] : 0;
+		rawTotal[kColorSlots + threadIdx.x] = ownerLists ? P.binColorTotal[kColorSlots + threadIdx.x] : 0;
+	}
+	__syncthreads();
 	if ( threadIdx.x == 0 )
 	{
-		const int* startC = P.binColorOffset + (size_t)list * kColorSlots;
-		const int* startJ = P.binJointOffset + (size_t)list * kColorSlots;
+		const int* startC = rawStartC;
+		const int* startJ = rawStartJ;
 		int localC = 0, localJ = 0;
 		for ( int c = 0; c < slotCount; ++c )
 		{
@@ -127,7 +137,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 			int hi = whole ? ( ownerLists || rank == 0 ? s0 + n : s0 ) : s0 + n * ( rank + 1 ) / share;
 			listBeginC[c] = lo;
 			localStartC[c] = localC;
-			binCountC[c] = ownerLists ? P.binColorTotal[c] : n;
+			binCountC[c] = ownerLists ? rawTotal[c] : n;
 			localC += hi - lo;
 
 			s0 = startJ[c], n = startJ[c + 1] - s0;
@@ -135,7 +145,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 			hi = whole ? ( ownerLists || rank == 0 ? s0 + n : s0 ) : s0 + n * ( rank + 1 ) / share;
 			listBeginJ[c] = lo;
 			localStartJ[c] = localJ;
-			binCountJ[c] = ownerLists ? P.binColorTotal[kColorSlots + c] : n;
+			binCountJ[c] = ownerLists ? rawTotal[kColorSlots + c] : n;
 			localJ += hi - lo;
 		}
 		localStartC[slotCount] = localC;
@@ -284,14 +294,14 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	const int overflowLevelCount = hasOverflow ? *cluster.map_shared_rank( &overflow.levelCount, 0 ) : 0;
 	auto clusterSync = [&]() { cluster.sync(); };
 	// restitution is applied by the whole cluster or not at all
-	if ( threadIdx.x == 0 )
+	if ( threadIdx.x < 32 )
 	{
-		int any = 0;
-		for ( int r = 0; r < share; ++r )
+		int mine = (int)threadIdx.x < share ? *cluster.map_shared_rank( &anyRestitution, threadIdx.x ) : 0;
+		unsigned any = __ballot_sync( 0xffffffffu, mine != 0 );
+		if ( threadIdx.x == 0 )
 		{
-			any |= *cluster.map_shared_rank( &anyRestitution, (unsigned)r );
+			clusterRestitution = any != 0u ? 1 : 0;
 		}
-		clusterRestitution = any;
 	}
 	__syncthreads();
 	clk.lap( b2GpuStage_prepareConstraints );

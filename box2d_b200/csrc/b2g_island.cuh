@@ -322,7 +322,28 @@ template <typename BodiesOf> B2G_DEV void buildOverflowSchedule( OverflowSchedul
 	// (every constraint touches the same dynamic body, e.g. the drum of the tumbler scene) gains nothing from levels and
 	// would pay a barrier per constraint: give up after a few sweeps, the caller then solves the sequence on one thread.
 	const int sweepLimit = itemCount / 4 + 2;
-	for ( int sweep = 0;; ++sweep )
+	// quick test first: a dynamic body shared by m constraints forces m levels
+	if ( threadIdx.x == 0 )
+	{
+		S.changed = 0;
+	}
+	__syncthreads();
+	for ( int i = (int)threadIdx.x; i < itemCount; i += (int)blockDim.x )
+	{
+		int a = S.bodyA[i], b = S.bodyB[i];
+		int degreeA = 0, degreeB = 0;
+		for ( int j = 0; j < itemCount; ++j )
+		{
+			int ja = S.bodyA[j], jb = S.bodyB[j];
+			degreeA += ( a != 0 && ( a == ja || a == jb ) ) ? 1 : 0;
+			degreeB += ( b != 0 && ( b == ja || b == jb ) ) ? 1 : 0;
+		}
+		atomicMax( &S.changed, degreeA > degreeB ? degreeA : degreeB );
+	}
+	__syncthreads();
+	const bool hub = S.changed > sweepLimit;
+	__syncthreads();
+	for ( int sweep = hub ? sweepLimit + 1 : 0;; ++sweep )
 	{
 		if ( sweep > sweepLimit )
 		{
