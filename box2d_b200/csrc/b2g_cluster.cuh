@@ -75,8 +75,12 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	V.cf = reinterpret_cast<float4*>( cursor );
 	cursor += (size_t)CF_COUNT * capC * sizeof( float4 );
 	V.cfStride = capC;
-	V.joints = cursor;
-	cursor += (size_t)capJ * kJointStride;
+	// joints: resident in shared memory, or -- spilled: a big jointed island whose records do not fit -- left in the
+	// global working copy (L2); a record is only ever touched by the thread that owns the joint, the bodies stay in
+	// distributed shared memory either way
+	const bool jointsSpilled = P.jointsSpilled != 0;
+	V.joints = jointsSpilled ? P.g.joints : cursor;
+	cursor += jointsSpilled ? 0 : (size_t)capJ * kJointStride;
 	V.cidx = reinterpret_cast<int2*>( cursor );
 	cursor += (size_t)capC * sizeof( int2 );
 	int2* jointGlobal = reinterpret_cast<int2*>( cursor );
@@ -95,6 +99,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	const unsigned barAddr = (unsigned)__cvta_generic_to_shared( &arrivalBar );
 	VA.asyncBar = barAddr;
 	unsigned barPhase = 0;
+	auto jointRecord = [&]( int k ) -> b2lJointSim* {
+		return jointAt( V, jointsSpilled ? jointIndexOf[k] : k );
+	};
 
 	// this block's run of the bin's bodies
 	const int binBodies = P.binBodyCount[bin];
@@ -254,18 +261,36 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		{
 			int k = t / quads, q = t - k * quads;
 			const float4* src = reinterpret_cast<const float4*>( P.rawJoints + (size_t)jointIndexOf[k] * kJointStride );
-			reinterpret_cast<float4*>( V.joints + (size_t)k * kJointStride )[q] = src[q];
+			reinterpret_cast<float4*>( jointRecord( k ) )[q] = src[q];
 		}
 	}
 	__syncthreads();
 	forEachLocal( jointCount, [&]( int k ) {
-		int* pair = jointIndexPair( jointAt( V, k ) );
+		b2lJointSim* joint = jointRecord( k );
+		int* pair = jointIndexPair( joint );
 		if ( pair != nullptr )
 		{
 			int a = pair[0], b = pair[1];
 			jointGlobal[k] = make_int2( a, b );
-			pair[0] = a >= 0 ? P.bodyLocal[a] - 1 : -1;
-			pair[1] = b >= 0 ? P.bodyLocal[b] - 1 : -1;
+			a = a >= 0 ? P.bodyLocal[a] - 1 : -1;
+			b = b >= 0 ? P.bodyLocal[b] - 1 : -1;
+			pair[0] = a;
+			pair[1] = b;
+			// tell the owners of the two bodies what to expect from this joint in every pass over its colour: every joint
+			// type writes both bodies back once per pass, except a pogo joint without a spring (src/pogo_joint.c:165,203)
+			int c = colorOfLocal( localStartJ, slotCount, k );
+			bool writes = !( joint->type == b2l_pogoJoint && joint->u.pogo.hertz == 0.0f );
+			if ( c < colorCount && writes )
+			{
+				if ( a >= 0 && ( __float_as_uint( gatherVel( V, a + 1 ).w ) & B2L_FLAG_DYNAMIC ) != 0 )
+				{
+					atomicAdd( cluster.map_shared_rank( expectBytes, clusterOwner( V, (unsigned)a ) ) + c, (int)sizeof( float4 ) );
+				}
+				if ( b >= 0 && ( __float_as_uint( gatherVel( V, b + 1 ).w ) & B2L_FLAG_DYNAMIC ) != 0 )
+				{
+					atomicAdd( cluster.map_shared_rank( expectBytes, clusterOwner( V, (unsigned)b ) ) + c, (int)sizeof( float4 ) );
+				}
+			}
 		}
 	} );
 	const int ovJoints = ovJe - ovJb;
@@ -275,7 +300,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		buildOverflowSchedule( overflow, ovJoints + ( ovCe - ovCb ), [&]( int i, int& a, int& b ) {
 			if ( i < ovJoints )
 			{
-				const int* pair = jointIndexPair( jointAt( V, ovJb + i ) );
+				const int* pair = jointIndexPair( jointRecord( ovJb + i ) );
 				a = pair != nullptr ? pair[0] + 1 : 0; // bin-local, -1 = static
 				b = pair != nullptr ? pair[1] + 1 : 0;
 			}
@@ -309,24 +334,16 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	auto overflowPass = [&]( auto joint, auto contact ) {
 		overflowLevels( overflow, overflowLevelCount, rank == 0, ovJoints, ovJb, ovCb, joint, contact, clusterSync, (int)blockDim.x );
 	};
-	// A pass over the colours.  Colours with joints end in a full cluster barrier (release / acquire: every writer fences
-	// its remote stores at GPU scope, MEMBAR.ALL.GPU, which costs more than the colour itself).  Colours with contacts
-	// only -- the common case -- use counted stores instead: the owner of a body waits until the bytes announced for
-	// the colour have landed in its shared memory (mbarrier transaction count) and only then joins a barrier that
-	// carries no fence.
+	// A pass over the colours.  A full cluster barrier (release / acquire) makes every writer fence its remote stores at
+	// GPU scope (MEMBAR.ALL.GPU), which costs more than the colour itself.  The colours use counted stores instead: the
+	// owner of a body waits until the bytes announced for the colour have landed in its shared memory (mbarrier
+	// transaction count) and only then joins a barrier that carries no fence.
 	auto colorPass = [&]( auto joint, auto contact ) {
 		for ( int c = 0; c < colorCount; ++c )
 		{
 			if ( binCountJ[c] == 0 && binCountC[c] == 0 )
 			{
 				continue; // colour not present in this bin (uniform for the cluster)
-			}
-			if ( binCountJ[c] != 0 )
-			{
-				forEachInLocalColor( make_int4( localStartJ[c], localStartJ[c + 1], localStartC[c], localStartC[c + 1] ), joint,
-									 [&]( int k ) { contact( V, k ); } );
-				cluster.sync();
-				continue;
 			}
 			if ( threadIdx.x == 0 )
 			{
@@ -340,10 +357,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 					asm volatile( "mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"( barAddr ) : "memory" );
 				}
 			}
-			for ( int k = localStartC[c] + (int)threadIdx.x; k < localStartC[c + 1]; k += (int)blockDim.x )
-			{
-				contact( VA, k );
-			}
+			forEachInLocalColor(
+				make_int4( localStartJ[c], localStartJ[c + 1], localStartC[c], localStartC[c + 1] ), [&]( int k ) { joint( VA, k ); },
+				[&]( int k ) { contact( VA, k ); } );
 			unsigned done = 0;
 			for ( int spin = 0; done == 0; ++spin )
 			{
@@ -372,16 +388,17 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		cluster.sync();
 		clk.lap( b2GpuStage_integrateVelocities );
 
-		overflowPass( [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); }, [&]( int k ) { warmStartContactOverflow( V, k ); } );
-		colorPass( [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); }, [&]( const SolveView& view, int k ) { warmStartContact( view, k ); } );
+		overflowPass( [&]( int k ) { warmStartJoint( P, V, jointRecord( k ) ); }, [&]( int k ) { warmStartContactOverflow( V, k ); } );
+		colorPass( [&]( const SolveView& view, int k ) { warmStartJoint( P, view, jointRecord( k ) ); },
+				   [&]( const SolveView& view, int k ) { warmStartContact( view, k ); } );
 		clk.lap( b2GpuStage_warmStart );
 
-		overflowPass( [&]( int k ) { solveJoint( P, V, jointAt( V, k ), true ); },
+		overflowPass( [&]( int k ) { solveJoint( P, V, jointRecord( k ), true ); },
 					  [&]( int k ) { solveContactOverflow( P, V, k, true ); } );
 		colorPass(
-			[&]( int k ) {
-				b2lJointSim* joint = jointAt( V, k );
-				solveJoint( P, V, joint, true );
+			[&]( const SolveView& view, int k ) {
+				b2lJointSim* joint = jointRecord( k );
+				solveJoint( P, view, joint, true );
 				jointEventTest( P, joint );
 			},
 			[&]( const SolveView& view, int k ) { solveContact( P, view, k, true ); } );
@@ -391,9 +408,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		cluster.sync();
 		clk.lap( b2GpuStage_integratePositions );
 
-		overflowPass( [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+		overflowPass( [&]( int k ) { solveJoint( P, V, jointRecord( k ), false ); },
 					  [&]( int k ) { solveContactOverflow( P, V, k, false ); } );
-		colorPass( [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+		colorPass( [&]( const SolveView& view, int k ) { solveJoint( P, view, jointRecord( k ), false ); },
 				   [&]( const SolveView& view, int k ) { solveContact( P, view, k, false ); } );
 		clk.lap( b2GpuStage_relaxImpulses );
 	}
@@ -423,7 +440,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	forEachLocal( contactCount, [&]( int k ) { storeContact( P, V, k, wireSlot[k], k < ovCb || k >= ovCe ); } );
 	forEachLocal( bodyCount, [&]( int i ) { storeBody( P, V, bodyList[i], i + 1 ); } );
 	forEachLocal( jointCount, [&]( int k ) {
-		int* pair = jointIndexPair( jointAt( V, k ) );
+		int* pair = jointIndexPair( jointRecord( k ) );
 		if ( pair != nullptr )
 		{
 			pair[0] = jointGlobal[k].x;
@@ -433,7 +450,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	__syncthreads();
 	{
 		const int quads = kJointStride / 16;
-		for ( int t = (int)threadIdx.x; t < jointCount * quads; t += (int)blockDim.x )
+		for ( int t = (int)threadIdx.x; t < ( jointsSpilled ? 0 : jointCount * quads ); t += (int)blockDim.x )
 		{
 			int k = t / quads, q = t - k * quads;
 			float4* dst = reinterpret_cast<float4*>( P.g.joints + (size_t)jointIndexOf[k] * kJointStride );

@@ -830,14 +830,15 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	}
 }
 
-// bytes of dynamic shared memory the island kernel needs for the given capacities
-inline size_t islandSharedBytes( int capB, int capC, int capJ )
+// bytes of dynamic shared memory the island kernels need for the given per-block capacities; jointsResident = false:
+// the joint records themselves stay in global memory (cluster kernel with spilled joints)
+inline size_t islandSharedBytes( int capB, int capC, int capJ, bool jointsResident = true )
 {
 	size_t bytes = 0;
 	bytes += 2 * (size_t)( capB + 1 ) * sizeof( float4 ); // vel, pos
 	bytes += (size_t)capB * sizeof( float4 );			  // bodyK
 	bytes += (size_t)CF_COUNT * capC * sizeof( float4 );  // contact fields
-	bytes += (size_t)capJ * kJointStride;				  // joints
+	bytes += jointsResident ? (size_t)capJ * kJointStride : 0; // joints
 	bytes += (size_t)capC * sizeof( int2 );				  // cidx
 	bytes += (size_t)capJ * ( sizeof( int2 ) + sizeof( int ) ); // jointGlobal, jointIndexOf
 	bytes += (size_t)capB * sizeof( float );			  // angDamp

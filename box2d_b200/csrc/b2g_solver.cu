@@ -362,6 +362,11 @@ struct b2GpuSolver
 	size_t binCounterCount = 0;
 	size_t islandSmemBytes = 0;
 	size_t islandSmemBudget = 0;
+	// B2GPU_SPILL_JOINTS=1: allow a cluster plan with the joint records left in global memory.  Off by default: measured
+	// on joint_grid it loses to the grid-barrier kernel (0.47 vs 0.25 ms) -- 16 SMs cannot pull 19 800 records of 256 B
+	// per stage through L2 as fast as 148 SMs can
+	bool spillJointsEnabled = false;
+	bool spillJointsForced = false; // B2GPU_SPILL_JOINTS=2 (testing): steps with joints take that plan first
 	bool resolveContacts = true; // diagnostics: B2GPU_RESOLVE=0 makes the island kernels chase head -> bodyLocal themselves
 	bool stageAllThreads = false;
 	bool testTightBins = false;			 // testing: B2GPU_TEST_TIGHT_BINS=1 makes every island step fail over to the grid kernel
@@ -531,6 +536,9 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		// clusters of 2, 4, 8, 16 blocks with the same carve-up: how many can be resident at once
 		const char* traceEnv = getenv( "B2GPU_TRACE" );
 		s->trace = traceEnv != nullptr && atoi( traceEnv ) != 0;
+		const char* spillEnv = getenv( "B2GPU_SPILL_JOINTS" );
+		s->spillJointsEnabled = spillEnv != nullptr && atoi( spillEnv ) != 0;
+		s->spillJointsForced = spillEnv != nullptr && atoi( spillEnv ) == 2;
 		const char* ownerEnv = getenv( "B2GPU_OWNER_LISTS" );
 		s->ownerListsEnabled = ownerEnv == nullptr || atoi( ownerEnv ) != 0;
 		const char* resolveEnv = getenv( "B2GPU_RESOLVE" );
@@ -706,17 +714,19 @@ static int b2gFindSegment( const std::vector<int>& starts, int flat )
 struct b2gBinPlan
 {
 	int binCount, share, capB, capC, capJ;
+	bool spillJoints;
 };
 
 // Bins for blocks-per-bin = share.  Island i goes to the bin its first body falls in when the islands are laid end to
 // end and cut every `target` bodies, so a bin gets between target - (largest island) and target + (largest island)
 // bodies.  `waves`: more bins than `binLimit` are allowed when the data does not fit (they run in waves).
-static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimitIn, bool waves, b2gBinPlan* plan )
+static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimitIn, bool waves, bool spillJoints, b2gBinPlan* plan )
 {
 	const b2g::StepParams& P = s->params;
 	const int bodies = P.bodyCount;
 	size_t budget = s->islandSmemBudget;
-	const double bytesPerBody = 52.0, bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0, bytesPerJoint = b2g::kJointStride + 12.0;
+	const double bytesPerBody = 52.0, bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0;
+	const double bytesPerJoint = ( spillJoints ? 0.0 : (double)b2g::kJointStride ) + 12.0;
 	double totalBytes = bodies * bytesPerBody + s->contactTotal * bytesPerContact + s->jointTotal * bytesPerJoint;
 	int binLimit = binLimitIn < islandCount ? binLimitIn : islandCount;
 	// head room for uneven constraint density between bins (adaptive: raised when a bin did not fit, lowered slowly while
@@ -771,7 +781,7 @@ static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimi
 	double needJ = fraction * s->jointTotal + ( s->jointTotal > 0 ? slack : 0.0 ) + ( share > 1 ? (double)s->overflowJoints : 0.0 );
 	needC = needC < (double)s->contactTotal ? needC : (double)s->contactTotal;
 	needJ = needJ < (double)s->jointTotal ? needJ : (double)s->jointTotal;
-	size_t fixed = b2g::islandSharedBytes( capB, 0, 0 );
+	size_t fixed = b2g::islandSharedBytes( capB, 0, 0, !spillJoints );
 	if ( fixed + (size_t)( needC * 1.1 * bytesPerContact + needJ * 1.1 * bytesPerJoint ) + 4096 > budget )
 	{
 		return false;
@@ -791,18 +801,18 @@ static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimi
 	capC = capC > ( ( s->contactTotal + 3 ) & ~3 ) ? ( ( s->contactTotal + 3 ) & ~3 ) : capC;
 	capJ = capJ > ( ( s->jointTotal + 3 ) & ~3 ) ? ( ( s->jointTotal + 3 ) & ~3 ) : capJ;
 	capC = capC < 4 ? 4 : capC;
-	for ( int guard = 0; guard < 64 && b2g::islandSharedBytes( capB, capC, capJ ) > budget; ++guard )
+	for ( int guard = 0; guard < 64 && b2g::islandSharedBytes( capB, capC, capJ, !spillJoints ) > budget; ++guard )
 	{
 		capC = ( capC - capC / 32 - 4 ) & ~3; // rounding slack: shave ~3 % until it fits
 		capJ = capJ > 0 ? ( capJ - capJ / 32 - 4 ) & ~3 : 0;
 		capC = capC < 4 ? 4 : capC;
 		capJ = capJ < 0 ? 0 : capJ;
 	}
-	if ( b2g::islandSharedBytes( capB, capC, capJ ) > budget || capC < needC || capJ < needJ )
+	if ( b2g::islandSharedBytes( capB, capC, capJ, !spillJoints ) > budget || capC < needC || capJ < needJ )
 	{
 		return false;
 	}
-	*plan = { binCount, share, capB, capC, capJ };
+	*plan = { binCount, share, capB, capC, capJ, spillJoints };
 	return true;
 }
 
@@ -856,13 +866,24 @@ static int b2gPlanIslands( b2GpuSolver* s )
 		s->islandHeadRoom = s->islandHeadRoom * 0.995 > 1.2 ? s->islandHeadRoom * 0.995 : 1.2;
 	}
 	b2gBinPlan plan;
-	bool planned = s->clusterForce <= 1 && b2gPlanBins( s, islandCount, 1, s->smCount, true, &plan );
-	for ( int k = 0; !planned && k < 4; ++k )
+	const bool residentFirst = !( s->spillJointsForced && s->jointTotal > 0 );
+	bool planned = residentFirst && s->clusterForce <= 1 && b2gPlanBins( s, islandCount, 1, s->smCount, true, false, &plan );
+	for ( int k = 0; !planned && residentFirst && k < 4; ++k )
 	{
 		int share = 2 << k;
 		if ( s->clusterBins[k] > 0 && share >= s->clusterForce )
 		{
-			planned = b2gPlanBins( s, islandCount, share, s->clusterBins[k], false, &plan );
+			planned = b2gPlanBins( s, islandCount, share, s->clusterBins[k], false, false, &plan );
+		}
+	}
+	// a jointed island too big for that (joint_grid: 19 800 joints x 256 B): the largest cluster with the joint records
+	// left in global memory -- the bodies, which is what the blocks share, still live in distributed shared memory
+	for ( int k = 3; !planned && k >= 0 && s->jointTotal > 0 && s->spillJointsEnabled; --k )
+	{
+		int share = 2 << k;
+		if ( s->clusterBins[k] > 0 && share >= s->clusterForce )
+		{
+			planned = b2gPlanBins( s, islandCount, share, s->clusterBins[k], false, true, &plan );
 		}
 	}
 	if ( !planned )
@@ -922,6 +943,7 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	P.bodyBin = reinterpret_cast<const int*>( s->wireAll.ptr + s->inBins );
 	P.bodyLocal = s->bodyLocal.ptr;
 	P.ownerLists = ownerLists ? 1 : 0;
+	P.jointsSpilled = plan.spillJoints ? 1 : 0;
 	P.listCount = listCount;
 	P.listCapContacts = ownerLists ? capC : capC * plan.share;
 	P.listCapJoints = ownerLists ? capJ : capJ * plan.share;
@@ -939,7 +961,7 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	P.binContactInfo = s->binContactInfo.ptr;
 	P.jointBinRank = s->jointBinRank.ptr;
 	P.binJointList = s->binJointList.ptr;
-	s->islandSmemBytes = b2g::islandSharedBytes( capB, capC, capJ );
+	s->islandSmemBytes = b2g::islandSharedBytes( capB, capC, capJ, !plan.spillJoints );
 	s->islandMode = true;
 	return 0;
 }

@@ -154,6 +154,7 @@ struct StepParams
 	int capBodies;	   // per-BLOCK capacities the shared memory carve-up was sized for (a bin holds clusterSize times that)
 	int capContacts;
 	int capJoints;
+	int jointsSpilled; // cluster kernel: the joint records stay in the global working copy instead of shared memory
 	int ownerLists;	   // one bin shared by a cluster: constraint lists per BLOCK, keyed by the owner of the first body
 	int listCount;	   // number of constraint lists: binCount, or clusterSize with owner lists
 	int listCapContacts; // stride of the constraint lists (binCap*, or the per-block capacity with owner lists)

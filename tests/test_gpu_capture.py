@@ -75,6 +75,22 @@ def test_captured_steps_bit_exact_on_clusters(capture_files, blocks, monkeypatch
 	assert cluster_steps > 0, "the cluster kernel never ran"
 
 
+def test_cluster_with_joint_records_left_in_global_memory(capture_files, monkeypatch):
+	"""B2GPU_SPILL_JOINTS: the joint records stay in the global working copy, the bodies in distributed
+	shared memory (an option the planner only takes when nothing else fits): same bits."""
+	monkeypatch.setenv("B2GPU_SPILL_JOINTS", "2")  # 2 = take that plan first whenever the step has joints
+	spilled = 0
+	with b2.GpuSolver() as solver:
+		for path in capture_files:
+			cap = b2.Capture(path)
+			desc, result, bufs = cap.make_call(islands=True)
+			solver.step(desc, result)
+			_check(cap, bufs, result)
+			if cap.joint_count > 0 and solver.island_plan()[1] > 1 and result.gridBarriers == 0:
+				spilled += 1
+	assert spilled > 0
+
+
 def test_island_failure_reruns_on_grid_kernel(capture_files, monkeypatch):
 	"""When a bin does not fit its block the island kernels give up and the step is run again on the grid-barrier
 	kernel from the untouched inputs: same bits, one more launch."""
