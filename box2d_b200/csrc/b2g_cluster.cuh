@@ -83,9 +83,8 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	cursor += jointsSpilled ? 0 : (size_t)capJ * kJointStride;
 	V.cidx = reinterpret_cast<int2*>( cursor );
 	cursor += (size_t)capC * sizeof( int2 );
-	int2* jointGlobal = reinterpret_cast<int2*>( cursor );
-	int* jointIndexOf = reinterpret_cast<int*>( jointGlobal + capJ );
-	cursor += (size_t)capJ * ( sizeof( int2 ) + sizeof( int ) );
+	int* jointIndexOf = reinterpret_cast<int*>( cursor );
+	cursor += (size_t)capJ * sizeof( int );
 	V.angDamp = reinterpret_cast<float*>( cursor );
 	cursor += (size_t)capB * sizeof( float );
 	V.cmeta = reinterpret_cast<int*>( cursor );
@@ -271,7 +270,6 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		if ( pair != nullptr )
 		{
 			int a = pair[0], b = pair[1];
-			jointGlobal[k] = make_int2( a, b );
 			a = a >= 0 ? P.bodyLocal[a] - 1 : -1;
 			b = b >= 0 ? P.bodyLocal[b] - 1 : -1;
 			pair[0] = a;
@@ -439,24 +437,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	// store: everything a block needs is in its own shared memory again
 	forEachLocal( contactCount, [&]( int k ) { storeContact( P, V, k, wireSlot[k], k < ovCb || k >= ovCe ); } );
 	forEachLocal( bodyCount, [&]( int i ) { storeBody( P, V, bodyList[i], i + 1 ); } );
-	forEachLocal( jointCount, [&]( int k ) {
-		int* pair = jointIndexPair( jointRecord( k ) );
-		if ( pair != nullptr )
-		{
-			pair[0] = jointGlobal[k].x;
-			pair[1] = jointGlobal[k].y;
-		}
-	} );
-	__syncthreads();
-	{
-		const int quads = kJointStride / 16;
-		for ( int t = (int)threadIdx.x; t < ( jointsSpilled ? 0 : jointCount * quads ); t += (int)blockDim.x )
-		{
-			int k = t / quads, q = t - k * quads;
-			float4* dst = reinterpret_cast<float4*>( P.g.joints + (size_t)jointIndexOf[k] * kJointStride );
-			dst[q] = reinterpret_cast<const float4*>( V.joints + (size_t)k * kJointStride )[q];
-		}
-	}
+	forEachLocal( jointCount, [&]( int k ) { storeJointImpulses( P, jointIndexOf[k], jointRecord( k ) ); } );
 	clk.lap( b2GpuStage_storeImpulses );
 
 	if ( clk.lead )

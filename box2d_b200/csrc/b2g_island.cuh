@@ -536,8 +536,8 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	cursor += (size_t)capJ * kJointStride;
 	V.cidx = reinterpret_cast<int2*>( cursor );
 	cursor += (size_t)capC * sizeof( int2 );
-	int2* jointGlobal = reinterpret_cast<int2*>( cursor ); // the joints' global body indices, restored at the end
-	cursor += (size_t)capJ * ( sizeof( int2 ) + sizeof( int ) ); // + jointIndexOf
+	int* jointIndexOf = reinterpret_cast<int*>( cursor ); // [capJ] global joint index of every local joint
+	cursor += (size_t)capJ * sizeof( int );
 	V.angDamp = reinterpret_cast<float*>( cursor );
 	cursor += (size_t)capB * sizeof( float );
 	V.cmeta = reinterpret_cast<int*>( cursor );
@@ -663,7 +663,6 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		}
 	}
 	__syncthreads();
-	int* jointIndexOf = reinterpret_cast<int*>( jointGlobal + capJ ); // [capJ] global joint index of every local joint
 	forEachLocal( jointCount, [&]( int k ) { jointIndexOf[k] = orderedIndex( jointList, ovJb, ovJe, k ); } );
 	__syncthreads();
 	{
@@ -681,7 +680,6 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		if ( pair != nullptr )
 		{
 			int a = pair[0], b = pair[1];
-			jointGlobal[k] = make_int2( a, b );
 			pair[0] = a >= 0 ? P.bodyLocal[a] - 1 : -1;
 			pair[1] = b >= 0 ? P.bodyLocal[b] - 1 : -1;
 		}
@@ -795,27 +793,10 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	}
 	__syncthreads();
 
-	// store: impulses by wire slot, states by global body index, joints with their global body indices restored
+	// store: impulses by wire slot, states by global body index, the joints' accumulated impulses by joint index
 	forEachLocal( contactCount, [&]( int k ) { storeContact( P, V, k, wireSlot[k], k < ovCb || k >= ovCe ); } );
 	forEachLocal( bodyCount, [&]( int i ) { storeBody( P, V, bodyList[i], i + 1 ); } );
-	forEachLocal( jointCount, [&]( int k ) {
-		int* pair = jointIndexPair( jointAt( V, k ) );
-		if ( pair != nullptr )
-		{
-			pair[0] = jointGlobal[k].x;
-			pair[1] = jointGlobal[k].y;
-		}
-	} );
-	__syncthreads();
-	{
-		const int quads = kJointStride / 16;
-		for ( int t = (int)threadIdx.x; t < jointCount * quads; t += (int)blockDim.x )
-		{
-			int k = t / quads, q = t - k * quads;
-			float4* dst = reinterpret_cast<float4*>( P.g.joints + (size_t)jointIndexOf[k] * kJointStride );
-			dst[q] = reinterpret_cast<const float4*>( V.joints + (size_t)k * kJointStride )[q];
-		}
-	}
+	forEachLocal( jointCount, [&]( int k ) { storeJointImpulses( P, jointIndexOf[k], jointAt( V, k ) ); } );
 	clk.lap( b2GpuStage_storeImpulses );
 
 	if ( clk.lead )
@@ -840,7 +821,7 @@ inline size_t islandSharedBytes( int capB, int capC, int capJ, bool jointsReside
 	bytes += (size_t)CF_COUNT * capC * sizeof( float4 );  // contact fields
 	bytes += jointsResident ? (size_t)capJ * kJointStride : 0; // joints
 	bytes += (size_t)capC * sizeof( int2 );				  // cidx
-	bytes += (size_t)capJ * ( sizeof( int2 ) + sizeof( int ) ); // jointGlobal, jointIndexOf
+	bytes += (size_t)capJ * sizeof( int );				  // jointIndexOf
 	bytes += (size_t)capB * sizeof( float );			  // angDamp
 	bytes += 2 * (size_t)capC * sizeof( int );			  // cmeta, wireSlot
 	return bytes;

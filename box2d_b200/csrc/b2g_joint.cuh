@@ -1310,6 +1310,24 @@ B2G_DEV int* jointIndexPair( b2lJointSim* joint )
 	}
 }
 
+// What the device returns per joint: the fields the stages wrote (accumulated impulses, ...), B2L_JOINT_OUT_FLOATS floats.
+// The reference solves joints in place in b2JointSim (no store stage, src/solver.h:73-74); the host copies these runs back.
+B2G_DEV void storeJointImpulses( const StepParams& P, int jointIndex, const b2lJointSim* joint )
+{
+	int offsets[2], floats[2];
+	int runs = b2lJointMutableRuns( joint->type, offsets, floats );
+	float* out = P.outJoints + (size_t)jointIndex * B2L_JOINT_OUT_FLOATS;
+	int n = 0;
+	for ( int r = 0; r < runs; ++r )
+	{
+		const float* src = reinterpret_cast<const float*>( reinterpret_cast<const uint8_t*>( joint ) + offsets[r] );
+		for ( int f = 0; f < floats[r]; ++f )
+		{
+			out[n++] = src[f];
+		}
+	}
+}
+
 // ---- dispatch (src/joint.c:1454-1540) ----------------------------------------------------------------------------
 B2G_DEV void warmStartJoint( const StepParams& P, const SolveView& V, b2lJointSim* joint )
 {

@@ -350,6 +350,7 @@ struct b2GpuSolver
 	DeviceBuffer<int> binCounters; // [binBodyCount | binColorStart | binJointStart | binFail], zeroed every run
 	DeviceBuffer<int> bodyLocal, binBodyList, slotGroupBits, binContactList, binJointList;
 	DeviceBuffer<int4> binContactInfo;
+	DeviceBuffer<float4> jointWork;
 	double islandHeadRoom = 1.3; // bins are sized for this many times the average bytes per bin
 	int headRoomCooldown = 0;	 // steps to wait after a failure before lowering it again
 	int countersBinCount = 0, countersListCount = 0;
@@ -623,6 +624,7 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	s->slotGroupBits.release();
 	s->binContactList.release();
 	s->binContactInfo.release();
+	s->jointWork.release();
 	s->binJointList.release();
 	s->contactBinRank.release();
 	s->jointBinRank.release();
@@ -687,11 +689,6 @@ extern "C" int b2GpuSolverGetIslandPlan( const b2GpuSolver* s, int* binCount, in
 // slot c holds every world's c-th ACTIVE colour (the stage order only matters inside a world, and inside a world the
 // active colours are visited in ascending order, src/solver.c:1341-1367), the last slot is the overflow colour.
 // Item order for pack/unpack: all bodies world by world, all contacts in segment (= slot) order, all joints.
-static const b2GpuColorDesc& b2gColorSlot( const b2GpuStepDesc& d, int slot, int slotCount )
-{
-	return slot + 1 < slotCount && slot < d.activeColorCount ? d.colors[slot] : d.overflow;
-}
-
 static int b2gFindSegment( const std::vector<int>& starts, int flat )
 {
 	// starts has segmentCount + 1 entries; returns the segment that contains `flat`
@@ -726,7 +723,7 @@ static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimi
 	const int bodies = P.bodyCount;
 	size_t budget = s->islandSmemBudget;
 	const double bytesPerBody = 52.0, bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0;
-	const double bytesPerJoint = ( spillJoints ? 0.0 : (double)b2g::kJointStride ) + 12.0;
+	const double bytesPerJoint = ( spillJoints ? 0.0 : (double)b2g::kJointStride ) + 4.0;
 	double totalBytes = bodies * bytesPerBody + s->contactTotal * bytesPerContact + s->jointTotal * bytesPerJoint;
 	int binLimit = binLimitIn < islandCount ? binLimitIn : islandCount;
 	// head room for uneven constraint density between bins (adaptive: raised when a bin did not fit, lowered slowly while
@@ -1187,18 +1184,19 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	s->inBins = s->inBody + 2 * nb;
 	s->inTotal = s->inBins + ( nb + 3 ) / 4;
 	s->sentQuads = 0;
-	// output arena: [states 2/body][impulse records][joints 16/joint][joint event bits]
+	// output arena: [states 2/body][impulse records][joint impulse records 3/joint][joint event bits]
 	size_t impulseQuads = ( (size_t)slot * b2g::kImpulseFloats + 3 ) / 4;
 	s->outStates = 0;
 	s->outImpulses = s->outStates + 2 * nb;
 	s->outJoints = s->outImpulses + impulseQuads;
-	s->outBits = s->outJoints + jointQuads * joint;
+	s->outBits = s->outJoints + (size_t)( B2L_JOINT_OUT_FLOATS / 4 ) * joint;
 	s->outTotal = s->outBits + ( (size_t)P.jointWords + 3 ) / 4;
 
 	B2G_CUDA( s->wireAll.reserve( s->inTotal + 1 ) );
 	B2G_CUDA( s->hWire.reserve( s->inTotal + 1 ) );
 	B2G_CUDA( s->outAll.reserve( s->outTotal + 1 ) );
 	B2G_CUDA( s->hOut.reserve( s->outTotal + 1 ) );
+	B2G_CUDA( s->jointWork.reserve( jointQuads * joint + 1 ) );
 	B2G_CUDA( s->vel.reserve( nb + 1 ) );
 	B2G_CUDA( s->pos.reserve( nb + 1 ) );
 	B2G_CUDA( s->bodyK.reserve( nb + 1 ) );
@@ -1221,7 +1219,8 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	P.g.cfStride = (int)slotCapacity;
 	P.g.cidx = s->cidx.ptr;
 	P.g.cmeta = s->cmeta.ptr;
-	P.g.joints = reinterpret_cast<uint8_t*>( s->outAll.ptr + s->outJoints ); // the working copy IS the output
+	P.g.joints = reinterpret_cast<uint8_t*>( s->jointWork.ptr ); // working copy of the joint records (grid kernel, spilled joints)
+	P.outJoints = reinterpret_cast<float*>( s->outAll.ptr + s->outJoints );
 	P.outStates = reinterpret_cast<uint8_t*>( s->outAll.ptr + s->outStates );
 	P.outImpulses = reinterpret_cast<float*>( s->outAll.ptr + s->outImpulses );
 	P.jointBits = reinterpret_cast<uint32_t*>( s->outAll.ptr + s->outBits );
@@ -1914,9 +1913,9 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 		}
 	}
 
-	// ---- joints (accumulated impulses live in the record itself; body indices go back to the world's numbering)
+	// ---- joints: the fields the stages wrote (b2lJointMutableRuns) go back into the reference's b2JointSim in place
 	{
-		const uint8_t* outJoints = reinterpret_cast<const uint8_t*>( base + s->outJoints );
+		const float* outJoints = reinterpret_cast<const float*>( base + s->outJoints );
 		int first = bodyCount + s->contactTotal;
 		int flat = ( begin > first ? begin : first ) - first;
 		int flatEnd = end - first;
@@ -1926,24 +1925,22 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 			const b2gJointSeg& seg = s->jointSegs[k];
 			int local = flat - s->jointStart[k];
 			int localEnd = ( flatEnd < s->jointStart[k + 1] ? flatEnd : s->jointStart[k + 1] ) - s->jointStart[k];
-			int bodyBase = s->bodySegs[seg.world].base;
 			for ( int i = local; i < localEnd; ++i )
 			{
-				b2lJointSim* sim = reinterpret_cast<b2lJointSim*>( seg.sims + (size_t)i * B2L_JOINT_SIZE );
-				memcpy( sim, outJoints + (size_t)( seg.jointStart + i ) * b2g::kJointStride, B2L_JOINT_SIZE );
-				if ( bodyBase != 0 )
+				uint8_t* sim = seg.sims + (size_t)i * B2L_JOINT_SIZE;
+				const float* record = outJoints + (size_t)( seg.jointStart + i ) * B2L_JOINT_OUT_FLOATS;
+				int offsets[2], floats[2];
+				int runs = b2lJointMutableRuns( b2gRdI( sim, offsetof( b2lJointSim, type ) ), offsets, floats );
+				for ( int r = 0; r < runs; ++r )
 				{
-					int* pair = b2gJointIndexPair( sim );
-					if ( pair != nullptr )
-					{
-						pair[0] = pair[0] >= 0 ? pair[0] - bodyBase : pair[0];
-						pair[1] = pair[1] >= 0 ? pair[1] - bodyBase : pair[1];
-					}
+					memcpy( sim + offsets[r], record, (size_t)floats[r] * sizeof( float ) );
+					record += floats[r];
 				}
 			}
 			if ( local < localEnd )
 			{
-				b2gFlushLines( outJoints + (size_t)( seg.jointStart + local ) * b2g::kJointStride, (size_t)( localEnd - local ) * b2g::kJointStride );
+				b2gFlushLines( outJoints + (size_t)( seg.jointStart + local ) * B2L_JOINT_OUT_FLOATS,
+							   (size_t)( localEnd - local ) * B2L_JOINT_OUT_FLOATS * sizeof( float ) );
 			}
 			flat = s->jointStart[k + 1];
 			k += 1;
@@ -2033,7 +2030,7 @@ static size_t b2gOutPrefix( const b2GpuSolver* s, int itemEnd )
 	}
 	int joints = flat - s->contactTotal;
 	joints = joints < s->jointTotal ? joints : s->jointTotal;
-	return s->outJoints + (size_t)joints * ( b2g::kJointStride / 16 );
+	return s->outJoints + (size_t)joints * ( B2L_JOINT_OUT_FLOATS / 4 );
 }
 
 static int b2gPumpDownloads( b2GpuSolver* s )

@@ -447,6 +447,12 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 					storeBody( P, V, i, i + 1 );
 				}
 			} );
+			forEachItem( P.jointCount, [&]( int j ) {
+				if ( j < P.jointCount )
+				{
+					storeJointImpulses( P, j, jointAt( V, j ) );
+				}
+			} );
 		}
 		break;
 

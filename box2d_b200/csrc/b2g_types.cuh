@@ -140,6 +140,7 @@ struct StepParams
 	// outputs
 	uint8_t* outStates; // b2BodyState[bodyCount]
 	float* outImpulses; // kImpulseFloats per slot
+	float* outJoints;	// B2L_JOINT_OUT_FLOATS per joint: the fields the stages wrote (b2lJointMutableRuns)
 	uint32_t* jointBits;
 	int* hasHitEvents;
 

@@ -251,6 +251,53 @@ typedef struct b2lJointSim
 	} u;
 } b2lJointSim;
 
+/* What the solver stages WRITE in a joint sim (everything else is input): the accumulated impulses of every type
+ * (src/*_joint.c: b2WarmStart*Joint / b2Solve*Joint), plus the motor joint's linearMass (src/motor_joint.c, recomputed
+ * in the solve) and the pogo joint's velocity.  At most two runs of consecutive floats per type, at most
+ * B2L_JOINT_OUT_FLOATS floats: this is the record the device sends back per joint. */
+#define B2L_JOINT_OUT_FLOATS 12
+#if defined( __CUDACC__ )
+#define B2L_HD __host__ __device__
+#else
+#define B2L_HD
+#endif
+#include <stddef.h>
+/* returns the number of runs; offsets are bytes from the start of b2JointSim */
+static inline B2L_HD int b2lJointMutableRuns( int type, int offsets[2], int floats[2] )
+{
+	switch ( type )
+	{
+		case b2l_distanceJoint:
+			offsets[0] = (int)offsetof( b2lJointSim, u.distance.impulse ), floats[0] = 4;
+			return 1;
+		case b2l_motorJoint:
+			offsets[0] = (int)offsetof( b2lJointSim, u.motor.linearVelocityImpulse ), floats[0] = 6;
+			offsets[1] = (int)offsetof( b2lJointSim, u.motor.linearMass ), floats[1] = 4;
+			return 2;
+		case b2l_moverJoint:
+			offsets[0] = (int)offsetof( b2lJointSim, u.mover.linearVelocityImpulse ), floats[0] = 2;
+			return 1;
+		case b2l_pogoJoint:
+			offsets[0] = (int)offsetof( b2lJointSim, u.pogo.impulse ), floats[0] = 1;
+			offsets[1] = (int)offsetof( b2lJointSim, u.pogo.velocity ), floats[1] = 1;
+			return 2;
+		case b2l_prismaticJoint:
+			offsets[0] = (int)offsetof( b2lJointSim, u.prismatic.impulse ), floats[0] = 6;
+			return 1;
+		case b2l_revoluteJoint:
+			offsets[0] = (int)offsetof( b2lJointSim, u.revolute.linearImpulse ), floats[0] = 6;
+			return 1;
+		case b2l_weldJoint:
+			offsets[0] = (int)offsetof( b2lJointSim, u.weld.linearImpulse ), floats[0] = 3;
+			return 1;
+		case b2l_wheelJoint:
+			offsets[0] = (int)offsetof( b2lJointSim, u.wheel.perpImpulse ), floats[0] = 5;
+			return 1;
+		default:
+			return 0; /* filter joint: nothing */
+	}
+}
+
 #if defined( __cplusplus )
 static_assert( sizeof( b2lJointSim ) == B2L_JOINT_SIZE, "b2JointSim mirror size" );
 static_assert( sizeof( b2lRevolute ) == 120 && sizeof( b2lWeld ) == 104 && sizeof( b2lPrismatic ) == 116, "joint mirrors" );
