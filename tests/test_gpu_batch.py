@@ -65,3 +65,18 @@ def test_large_batch_through_the_pipelined_host_passes():
 		solver.step_batch(descs, results)
 	for cap, buf, res in zip(caps, bufs, results):
 		_check(cap, buf, res)
+
+
+@pytest.mark.parametrize("blocks", [2, 8])
+def test_batch_on_clusters(blocks, monkeypatch):
+	"""Several bins, each shared by a cluster: the colours are dealt out evenly over the blocks (owner lists need a
+	single bin), joints and contacts use counted stores."""
+	monkeypatch.setenv("B2GPU_CLUSTER_FORCE", str(blocks))
+	caps = _captures(repeat=2)
+	descs, results, bufs = b2.make_batch(caps)
+	with b2.GpuSolver() as solver:
+		solver.step_batch(descs, results)
+		bins, per_bin = solver.island_plan()
+		assert bins > 1 and per_bin >= blocks
+	for cap, buf, res in zip(caps, bufs, results):
+		_check(cap, buf, res)
