@@ -410,8 +410,6 @@ struct b2GpuSolver
 	uint64_t lastD2H = 0;
 	int lastLaunches = 0;
 	float lastKernelMs = 0.0f;
-	std::vector<std::vector<b2gContactSeg>> scratchContactSegs;
-	std::vector<std::vector<b2gJointSeg>> scratchJointSegs;
 	std::chrono::steady_clock::time_point tBegin, tSubmit, tWaited;
 
 	// pipelined host passes (b2GpuSolverPackWork / b2GpuSolverUnpackWork): the items are dealt out in blocks, claimed in
@@ -841,6 +839,12 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	s->islandBodies.assign( (size_t)islandCount, 0 );
 	for ( const b2gBodySeg& seg : s->bodySegs )
 	{
+		if ( seg.islandCount == 1 )
+		{
+			// a world that is one island (the worlds of a batch usually are): nothing to count, nothing to look up
+			s->islandBodies[(size_t)seg.islandBase] = seg.count;
+			continue;
+		}
 		for ( int i = 0; i < seg.count; ++i )
 		{
 			int island = seg.islands[i];
@@ -1085,23 +1089,39 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	// constraint segments in slot order; every colour slot starts on a multiple of 32 slots, every segment on a multiple
 	// of 4 (the SIMD groups of the reference are per colour array); the gaps are dead slots (pointCount 0)
 	B2G_MARK( 1 );
-	s->contactSegs.clear();
-	s->jointSegs.clear();
 	s->contactStart.assign( 1, 0 );
 	s->jointStart.assign( 1, 0 );
 	int slotCount = maxColors + 1;
-	// one pass over the descriptors (they are large and there may be thousands): per colour slot, the worlds that
-	// bring a segment; then the segments are laid out slot by slot
+	// two light passes over the descriptors (they are large and there may be thousands): count the segments of every
+	// colour slot, then place each segment at its final position -- slot by slot, world by world inside a slot
+	int contactSegStart[b2g::kMaxColors + 2] = { 0 }, jointSegStart[b2g::kMaxColors + 2] = { 0 };
+	for ( int w = 0; w < worldCount; ++w )
 	{
-		std::vector<std::vector<b2gContactSeg>>& contactsOfSlot = s->scratchContactSegs;
-		std::vector<std::vector<b2gJointSeg>>& jointsOfSlot = s->scratchJointSegs;
-		contactsOfSlot.resize( (size_t)b2g::kMaxColors + 1 );
-		jointsOfSlot.resize( (size_t)b2g::kMaxColors + 1 );
-		for ( int c = 0; c < slotCount; ++c )
+		const b2GpuStepDesc& dw = descs[w];
+		for ( int c = 0; c <= dw.activeColorCount; ++c )
 		{
-			contactsOfSlot[(size_t)c].clear();
-			jointsOfSlot[(size_t)c].clear();
+			bool isOverflow = c == dw.activeColorCount;
+			const b2GpuColorDesc& color = isOverflow ? dw.overflow : dw.colors[c];
+			int slotIndex = isOverflow ? slotCount - 1 : c;
+			if ( color.contactCount < 0 || color.jointCount < 0 )
+			{
+				return b2gFailMsg( "b2GpuSolverBeginStep: negative count" );
+			}
+			contactSegStart[slotIndex + 1] += color.contactCount > 0 ? 1 : 0;
+			jointSegStart[slotIndex + 1] += color.jointCount > 0 ? 1 : 0;
 		}
+	}
+	for ( int c = 0; c < slotCount; ++c )
+	{
+		contactSegStart[c + 1] += contactSegStart[c];
+		jointSegStart[c + 1] += jointSegStart[c];
+	}
+	s->contactSegs.resize( (size_t)contactSegStart[slotCount] );
+	s->jointSegs.resize( (size_t)jointSegStart[slotCount] );
+	{
+		int contactCursor[b2g::kMaxColors + 2], jointCursor[b2g::kMaxColors + 2];
+		memcpy( contactCursor, contactSegStart, sizeof( contactCursor ) );
+		memcpy( jointCursor, jointSegStart, sizeof( jointCursor ) );
 		for ( int w = 0; w < worldCount; ++w )
 		{
 			const b2GpuStepDesc& dw = descs[w];
@@ -1110,33 +1130,29 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 				bool isOverflow = c == dw.activeColorCount;
 				const b2GpuColorDesc& color = isOverflow ? dw.overflow : dw.colors[c];
 				int slotIndex = isOverflow ? slotCount - 1 : c;
-				if ( color.contactCount < 0 || color.jointCount < 0 )
-				{
-					return b2gFailMsg( "b2GpuSolverBeginStep: negative count" );
-				}
 				if ( color.contactCount > 0 )
 				{
-					b2gContactSeg seg;
+					b2gContactSeg& seg = s->contactSegs[(size_t)contactCursor[slotIndex]++];
 					seg.sims = static_cast<uint8_t*>( color.contactSims );
 					seg.count = color.contactCount;
 					seg.slotStart = 0;
 					seg.world = w;
 					seg.wide = !isOverflow;
 					seg.colorIndex = color.colorIndex;
-					contactsOfSlot[(size_t)slotIndex].push_back( seg );
 				}
 				if ( color.jointCount > 0 )
 				{
-					b2gJointSeg seg;
+					b2gJointSeg& seg = s->jointSegs[(size_t)jointCursor[slotIndex]++];
 					seg.sims = static_cast<uint8_t*>( color.jointSims );
 					seg.count = color.jointCount;
 					seg.jointStart = 0;
 					seg.world = w;
-					jointsOfSlot[(size_t)slotIndex].push_back( seg );
 				}
 			}
 		}
 	}
+	s->contactStart.resize( s->contactSegs.size() + 1 );
+	s->jointStart.resize( s->jointSegs.size() + 1 );
 	int slot = 0, joint = 0, flat = 0;
 	for ( int c = 0; c < slotCount; ++c )
 	{
@@ -1144,20 +1160,20 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 		b2g::ColorRange& range = isOverflow ? P.overflow : P.colors[c];
 		range.contactStart = slot;
 		range.jointStart = joint;
-		for ( b2gContactSeg seg : s->scratchContactSegs[(size_t)c] )
+		for ( int k = contactSegStart[c]; k < contactSegStart[c + 1]; ++k )
 		{
+			b2gContactSeg& seg = s->contactSegs[(size_t)k];
 			seg.slotStart = ( slot + 3 ) & ~3;
-			s->contactSegs.push_back( seg );
 			slot = seg.slotStart + seg.count;
 			flat += seg.count;
-			s->contactStart.push_back( flat );
+			s->contactStart[(size_t)k + 1] = flat;
 		}
-		for ( b2gJointSeg seg : s->scratchJointSegs[(size_t)c] )
+		for ( int k = jointSegStart[c]; k < jointSegStart[c + 1]; ++k )
 		{
+			b2gJointSeg& seg = s->jointSegs[(size_t)k];
 			seg.jointStart = joint;
-			s->jointSegs.push_back( seg );
 			joint += seg.count;
-			s->jointStart.push_back( joint );
+			s->jointStart[(size_t)k + 1] = joint;
 		}
 		range.contactCount = slot - range.contactStart;
 		range.jointCount = joint - range.jointStart;
@@ -1324,7 +1340,7 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 				int local = i - seg.base;
 				if ( s->islandMode )
 				{
-					_mm_stream_si32( wireBins + i, s->islandBin[seg.islandBase + seg.islands[local]] );
+					_mm_stream_si32( wireBins + i, s->islandBin[seg.islandBase + ( seg.islandCount == 1 ? 0 : seg.islands[local] )] );
 				}
 				b2gStreamCopy( wireStates + 2 * (size_t)i, seg.states + (size_t)local * B2L_STATE_SIZE, 2 );
 				const uint8_t* sim = seg.sims + (size_t)local * B2L_SIM_SIZE;
