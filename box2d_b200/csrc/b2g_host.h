@@ -1,0 +1,305 @@
+// b2g_host.h -- internals shared by the host-side translation units of the device library (not part of the ABI).
+#pragma once
+
+#include "b2_gpu_solver.h"
+#include "b2g_types.cuh"
+
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <chrono>
+#include <memory>
+#include <string>
+#include <utility>
+#include <vector>
+
+// error reporting (b2g_solver.cu): the text of the last failure of the calling thread, returned by b2GpuGetLastError
+int b2gFail( const char* what, cudaError_t err );
+int b2gFailMsg( const char* what );
+
+#define B2G_CUDA( call )                                                                                                         \
+	do                                                                                                                           \
+	{                                                                                                                            \
+		cudaError_t err_ = ( call );                                                                                             \
+		if ( err_ != cudaSuccess )                                                                                               \
+		{                                                                                                                        \
+			return b2gFail( #call, err_ );                                                                                       \
+		}                                                                                                                        \
+	}                                                                                                                            \
+	while ( 0 )
+
+template <typename T> struct DeviceBuffer
+{
+	T* ptr = nullptr;
+	size_t capacity = 0; // elements
+
+	// grow geometrically, contents are not preserved
+	cudaError_t reserve( size_t count )
+	{
+		if ( count <= capacity )
+		{
+			return cudaSuccess;
+		}
+		size_t newCapacity = capacity < 1024 ? 1024 : capacity;
+		while ( newCapacity < count )
+		{
+			newCapacity += newCapacity / 2;
+		}
+		if ( ptr != nullptr )
+		{
+			cudaFree( ptr );
+			ptr = nullptr;
+			capacity = 0;
+		}
+		cudaError_t err = cudaMalloc( &ptr, newCapacity * sizeof( T ) );
+		if ( err == cudaSuccess )
+		{
+			capacity = newCapacity;
+		}
+		return err;
+	}
+
+	void release()
+	{
+		if ( ptr != nullptr )
+		{
+			cudaFree( ptr );
+		}
+		ptr = nullptr;
+		capacity = 0;
+	}
+};
+
+template <typename T> struct PinnedBuffer
+{
+	T* ptr = nullptr;
+	size_t capacity = 0;
+
+	cudaError_t reserve( size_t count )
+	{
+		if ( count <= capacity )
+		{
+			return cudaSuccess;
+		}
+		size_t newCapacity = capacity < 1024 ? 1024 : capacity;
+		while ( newCapacity < count )
+		{
+			newCapacity += newCapacity / 2;
+		}
+		if ( ptr != nullptr )
+		{
+			cudaFreeHost( ptr );
+			ptr = nullptr;
+			capacity = 0;
+		}
+		cudaError_t err = cudaHostAlloc( &ptr, newCapacity * sizeof( T ), cudaHostAllocDefault );
+		if ( err == cudaSuccess )
+		{
+			capacity = newCapacity;
+		}
+		return err;
+	}
+
+	void release()
+	{
+		if ( ptr != nullptr )
+		{
+			cudaFreeHost( ptr );
+		}
+		ptr = nullptr;
+		capacity = 0;
+	}
+};
+
+// control block, zeroed before every run
+struct ControlBlock
+{
+	unsigned int barrier[2];
+	int hasHitEvents;
+	int anyRestitution;
+	unsigned long long stageCycles[10];
+	int islandFailed; // a bin did not fit its block (binFail): the host reruns the step on the grid-barrier kernel
+	int reserved;
+};
+
+// segments of the step (see "the step as segments" below)
+struct b2gBodySeg
+{
+	uint8_t* states;
+	const uint8_t* sims;
+	const int* islands;
+	int islandCount;
+	int islandBase; // first island of this world in the batch-wide numbering
+	int count;
+	int base;		  // first body of this world in the batch-wide numbering
+	int jointBitBase; // first bit of this world in the joint-event bit set
+	int jointWords;
+};
+
+struct b2gContactSeg
+{
+	uint8_t* sims;
+	int count;
+	int slotStart; // wire slot of the segment's first contact (multiple of 4)
+	int world;
+	bool wide; // false for the overflow colour
+	int colorIndex;
+};
+
+struct b2gJointSeg
+{
+	uint8_t* sims;
+	int count;
+	int jointStart;
+	int world;
+};
+
+// host twin of b2g::jointIndexPair (b2g_joint.cuh)
+struct b2GpuSolver
+{
+	int device = 0;
+	int smCount = 0;
+	int gridBlocks = 0;
+	int mode = 0;
+	bool cooperative = false;
+	cudaStream_t stream = nullptr;
+	cudaEvent_t evStart = nullptr, evStop = nullptr, evUpload = nullptr;
+
+	// device: one input arena (mirror of the host wire staging), one output arena, the SoA solver state
+	DeviceBuffer<float4> wireAll, outAll, vel, pos, bodyK, cf;
+	DeviceBuffer<float> angDamp;
+	DeviceBuffer<int2> cidx;
+	DeviceBuffer<int> cmeta;
+	ControlBlock* control = nullptr;
+
+	// island mode scratch (b2g_island.cuh)
+	DeviceBuffer<int> binCounters; // [binBodyCount | binColorStart | binJointStart | binFail], zeroed every run
+	DeviceBuffer<int> bodyLocal, binBodyList, slotGroupBits, binContactList, binJointList;
+	DeviceBuffer<int4> binContactInfo;
+	DeviceBuffer<float4> jointWork;
+	double islandHeadRoom = 1.3; // bins are sized for this many times the average bytes per bin
+	int headRoomCooldown = 0;	 // steps to wait after a failure before lowering it again
+	int countersBinCount = 0, countersListCount = 0;
+	int ownerListsOff = 0;		 // steps during which owner lists stay off after a block's share did not fit
+	bool ownerListsEnabled = true; // B2GPU_OWNER_LISTS=0 turns them off
+	bool countersClean = false; // the bin counters are all zero (the island kernels zero what they have read)
+	DeviceBuffer<int2> contactBinRank, jointBinRank;
+	std::vector<int> islandBin;	 // host: bin of every awake island
+	std::vector<int> islandBodies; // host: bodies per island, then per bin
+	size_t binCounterCount = 0;
+	size_t islandSmemBytes = 0;
+	size_t islandSmemBudget = 0;
+	// B2GPU_SPILL_JOINTS=1: allow a cluster plan with the joint records left in global memory.  Off by default: measured
+	// on joint_grid it loses to the grid-barrier kernel (0.47 vs 0.25 ms) -- 16 SMs cannot pull 19 800 records of 256 B
+	// per stage through L2 as fast as 148 SMs can
+	bool spillJointsEnabled = false;
+	bool spillJointsForced = false; // B2GPU_SPILL_JOINTS=2 (testing): steps with joints take that plan first
+	bool resolveContacts = true; // diagnostics: B2GPU_RESOLVE=0 makes the island kernels chase head -> bodyLocal themselves
+	bool stageAllThreads = false;
+	bool testTightBins = false;			 // testing: B2GPU_TEST_TIGHT_BINS=1 makes every island step fail over to the grid kernel
+	int clusterForce = 0;				 // testing: smallest cluster size the planner may use (B2GPU_CLUSTER_FORCE)
+	int clusterBins[4] = { 0, 0, 0, 0 }; // resident clusters of 2, 4, 8, 16 blocks (0 = not available)
+	int overflowContacts = 0, overflowJoints = 0; // overflow colour totals of the step (all worlds)
+	bool islandMode = false;
+	int islandsEnabled = 1;
+	int maxSharedOptin = 0;
+
+	// page-locked staging owned by the library.  The input staging is written with non-temporal stores: on the
+	// target hosts a DMA read of lines that sit dirty in several cores' caches runs at ~6 GB/s instead of ~53 GB/s
+	// (tools/microbench/h2d_bench.cu, profiles/).
+	PinnedBuffer<float4> hWire;
+	PinnedBuffer<float4> hOut;
+	ControlBlock* hControl = nullptr;
+
+	// arena layouts, in float4 units
+	size_t inStates = 0, inBody = 0, inWire = 0, inJoints = 0, inBins = 0, inTotal = 0;
+	size_t sentQuads = 0; // prefix of the input arena already enqueued for upload (b2gPumpUploads)
+	size_t outStates = 0, outImpulses = 0, outJoints = 0, outBits = 0, outTotal = 0;
+
+	// the step in flight
+	std::vector<b2GpuStepDesc> descs;
+	b2GpuStepResult* results = nullptr; // one per world, or NULL
+	std::vector<b2gBodySeg> bodySegs;
+	std::vector<b2gContactSeg> contactSegs;
+	std::vector<b2gJointSeg> jointSegs;
+	std::vector<int> bodyStart, contactStart, jointStart; // item prefix sums, one more entry than segments
+	std::vector<int> binBodies;
+	b2g::StepParams params;
+	int jointTotal = 0;
+	int contactTotal = 0;
+	bool begun = false;
+	bool uploaded = false;
+	bool ran = false;
+
+	uint64_t launchCount = 0;
+	uint64_t lastH2D = 0;
+	uint64_t lastD2H = 0;
+	int lastLaunches = 0;
+	float lastKernelMs = 0.0f;
+	std::chrono::steady_clock::time_point tBegin, tSubmit, tWaited;
+
+	// pipelined host passes (b2GpuSolverPackWork / b2GpuSolverUnpackWork): the items are dealt out in blocks, claimed in
+	// increasing order; one caller (the pump) moves the finished prefix over PCIe while the others keep packing, and
+	// publishes how much of the output arena has arrived while the others unpack behind it
+	std::atomic<int> workNext{ 0 };
+	int workBlocks = 0;
+	int workItems = 0;
+	std::unique_ptr<std::atomic<unsigned char>[]> workDone;
+	size_t workDoneCapacity = 0;
+	int pumpPrefix = 0; // pump only: blocks [0, pumpPrefix) are packed
+	std::atomic<size_t> arrivedQuads{ 0 };
+	std::atomic<int> workFailed{ 0 };
+	std::vector<cudaEvent_t> chunkEvents;
+	std::vector<size_t> chunkEnd;
+	int chunkCount = 0;
+	int chunkNext = 0; // pump only
+	cudaEvent_t evControl = nullptr;
+	bool trace = false; // B2GPU_TRACE=1: print the timeline of the pipelined transfers at EndStep (stderr)
+	std::vector<std::pair<float, size_t>> traceSends, traceArrivals;
+	float traceBegun = 0.0f, traceSubmit = 0.0f, traceControl = 0.0f;
+	float traceMarks[8] = { 0 };
+	bool controlSeen = false;
+};
+
+inline int b2gRoundUp32( int n )
+{
+	return ( n + 31 ) & ~31;
+}
+
+// ---- the step as segments ---------------------------------------------------------------------------------------------
+// One step solves `worldCount` independent worlds (1 for b2GpuSolverStep, N for the batch API).  Their arrays are
+// addressed through segments: a body segment per world, a contact / joint segment per (colour slot, world).  Colour
+// slot c holds every world's c-th ACTIVE colour (the stage order only matters inside a world, and inside a world the
+// active colours are visited in ascending order, src/solver.c:1341-1367), the last slot is the overflow colour.
+// Item order for pack/unpack: all bodies world by world, all contacts in segment (= slot) order, all joints.
+inline int b2gFindSegment( const std::vector<int>& starts, int flat )
+{
+	// starts has segmentCount + 1 entries; returns the segment that contains `flat`
+	int lo = 0, hi = (int)starts.size() - 1;
+	while ( hi - lo > 1 )
+	{
+		int mid = ( lo + hi ) >> 1;
+		if ( starts[mid] <= flat )
+		{
+			lo = mid;
+		}
+		else
+		{
+			hi = mid;
+		}
+	}
+	return lo;
+}
+
+// ---- blocks of host work --------------------------------------------------------------------------------------------
+constexpr int kWorkBlockItems = 512;
+constexpr size_t kTransferQuads = 64 * 1024; // 1 MiB: granularity of the pipelined uploads
+constexpr size_t kDownloadQuads = 32 * 1024; // 512 KiB: the unpack pass runs this far behind the download
+
+// b2g_wire.cu
+int b2gSendArena( b2GpuSolver* s, size_t uptoQuads );
+void b2gFlushLines( const void* ptr, size_t bytes );
+// b2g_solver.cu
+int b2gEnqueueDownload( b2GpuSolver* s );
+int b2gRerunIfIslandsFailed( b2GpuSolver* s, bool download );
+

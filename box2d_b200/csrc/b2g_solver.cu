@@ -1,15 +1,14 @@
-// b2g_solver.cu -- kernels + the C-ABI of include/b2_gpu_solver.h.
+// b2g_solver.cu -- host side of the device library: the C-ABI of include/b2_gpu_solver.h.
 //
-// Single world: ONE persistent cooperative kernel per step (b2gStepKernel) runs the whole b2SolverTask
-// stage sequence (reference src/solver.c:1055-1197) with a grid-wide barrier where the reference's
-// orchestrator spins on stage->completionCount (src/solver.c:999-1005).  Body and constraint state stay
-// resident on the device across all sub-steps; the host sees one launch.
-// Debug/profiling path: the same device functions, one kernel launch per stage (mode 1).
+// Layout of a step (segments, arenas), the island plan, the wire packing / unpacking passes with their pipelined PCIe
+// transfers, and the launches.  The kernels live in b2g_island.cuh (partition + one block per bin), b2g_cluster.cuh
+// (one thread-block cluster per bin) and b2g_grid.cuh (grid-barrier kernels); DESIGN.md has the map.
 //
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false -prec-div=true -prec-sqrt=true -ftz=false
-#include "b2_gpu_solver.h"
+#include "b2g_host.h"
 
 #include "b2g_cluster.cuh"
+#include "b2g_grid.cuh"
 
 #include <cuda_runtime.h>
 
@@ -29,123 +28,6 @@
 #include <thread>
 #include <vector>
 
-namespace b2g
-{
-
-// The whole step.  Stage order and barrier placement = b2SolverTask (src/solver.c:1055-1197); the stage timers
-// are the reference's b2Profile split (src/solver.c:1080,1097,1112,1132,1141,1159,1182,1191).
-__global__ void __launch_bounds__( kBlockThreads, 1 ) b2gStepKernel( const __grid_constant__ StepParams P )
-{
-	if ( P.binCount > 0 && __ldcg( P.binFail ) == 0 )
-	{
-		return; // the island kernel solved this step
-	}
-
-	unsigned int epoch = 0;
-	const unsigned int blocks = gridDim.x;
-	auto sync = [&]() {
-		epoch += 1;
-		gridBarrier( P.barrier, epoch * blocks );
-	};
-
-	StageClock clk;
-	clk.start();
-	long long begin = clk.last;
-
-	const bool hasOverflow = P.overflow.contactCount + P.overflow.jointCount > 0;
-	const int colorCount = P.colorCount;
-
-	runStage( P, OP_PREPARE, 0 );
-	sync();
-	clk.lap( b2GpuStage_prepareConstraints );
-
-	for ( int subStep = 0; subStep < P.subStepCount; ++subStep )
-	{
-		runStage( P, OP_INTEGRATE_VELOCITIES, 0 );
-		sync();
-		clk.lap( b2GpuStage_integrateVelocities );
-
-		if ( hasOverflow )
-		{
-			runStage( P, OP_OVERFLOW_WARM, 0 );
-			sync();
-		}
-		for ( int c = 0; c < colorCount; ++c )
-		{
-			runStage( P, OP_WARM, c );
-			sync();
-		}
-		clk.lap( b2GpuStage_warmStart );
-
-		if ( hasOverflow )
-		{
-			runStage( P, OP_OVERFLOW_SOLVE, 0 );
-			sync();
-		}
-		for ( int c = 0; c < colorCount; ++c )
-		{
-			runStage( P, OP_SOLVE, c );
-			sync();
-		}
-		clk.lap( b2GpuStage_solveImpulses );
-
-		runStage( P, OP_INTEGRATE_POSITIONS, 0 );
-		sync();
-		clk.lap( b2GpuStage_integratePositions );
-
-		if ( hasOverflow )
-		{
-			runStage( P, OP_OVERFLOW_RELAX, 0 );
-			sync();
-		}
-		for ( int c = 0; c < colorCount; ++c )
-		{
-			runStage( P, OP_RELAX, c );
-			sync();
-		}
-		clk.lap( b2GpuStage_relaxImpulses );
-	}
-
-	// Restitution: the reference skips every SIMD group whose lanes all have restitution 0
-	// (src/contact_solver.c:2131, :432); when NO contact of the step has any, all groups skip, so the colour
-	// stages and their barriers are skipped as a whole.
-	if ( __ldcg( P.g.anyRestitution ) != 0 )
-	{
-		if ( hasOverflow )
-		{
-			runStage( P, OP_OVERFLOW_RESTITUTION, 0 );
-			sync();
-		}
-		for ( int c = 0; c < colorCount; ++c )
-		{
-			runStage( P, OP_RESTITUTION, c );
-			sync();
-		}
-	}
-	clk.lap( b2GpuStage_applyRestitution );
-
-	runStage( P, OP_STORE, 0 );
-	clk.lap( b2GpuStage_storeImpulses );
-
-	if ( clk.lead )
-	{
-#pragma unroll
-		for ( int i = 0; i < b2GpuStage_count; ++i )
-		{
-			P.stageCycles[i] = (unsigned long long)clk.acc[i];
-		}
-		P.stageCycles[8] = epoch;
-		P.stageCycles[9] = (unsigned long long)( clk.last - begin );
-	}
-}
-
-// One stage per launch (mode 1): same device code, the stream orders the stages.
-__global__ void __launch_bounds__( kBlockThreads, 1 ) b2gStageKernel( const __grid_constant__ StepParams P, int op, int colorIndex )
-{
-	runStage( P, op, colorIndex );
-}
-
-} // namespace b2g
 
 // =================================================================================================================
 // Host side
@@ -153,291 +35,16 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gStageKernel( const __gr
 
 static thread_local std::string t_lastError;
 
-static int b2gFail( const char* what, cudaError_t err )
+int b2gFail( const char* what, cudaError_t err )
 {
 	t_lastError = std::string( what ) + ": " + cudaGetErrorString( err );
 	return 1;
 }
 
-static int b2gFailMsg( const char* what )
+int b2gFailMsg( const char* what )
 {
 	t_lastError = what;
 	return 1;
-}
-
-#define B2G_CUDA( call )                                                                                                         \
-	do                                                                                                                           \
-	{                                                                                                                            \
-		cudaError_t err_ = ( call );                                                                                             \
-		if ( err_ != cudaSuccess )                                                                                               \
-		{                                                                                                                        \
-			return b2gFail( #call, err_ );                                                                                       \
-		}                                                                                                                        \
-	}                                                                                                                            \
-	while ( 0 )
-
-template <typename T> struct DeviceBuffer
-{
-	T* ptr = nullptr;
-	size_t capacity = 0; // elements
-
-	// grow geometrically, contents are not preserved
-	cudaError_t reserve( size_t count )
-	{
-		if ( count <= capacity )
-		{
-			return cudaSuccess;
-		}
-		size_t newCapacity = capacity < 1024 ? 1024 : capacity;
-		while ( newCapacity < count )
-		{
-			newCapacity += newCapacity / 2;
-		}
-		if ( ptr != nullptr )
-		{
-			cudaFree( ptr );
-			ptr = nullptr;
-			capacity = 0;
-		}
-		cudaError_t err = cudaMalloc( &ptr, newCapacity * sizeof( T ) );
-		if ( err == cudaSuccess )
-		{
-			capacity = newCapacity;
-		}
-		return err;
-	}
-
-	void release()
-	{
-		if ( ptr != nullptr )
-		{
-			cudaFree( ptr );
-		}
-		ptr = nullptr;
-		capacity = 0;
-	}
-};
-
-template <typename T> struct PinnedBuffer
-{
-	T* ptr = nullptr;
-	size_t capacity = 0;
-
-	cudaError_t reserve( size_t count )
-	{
-		if ( count <= capacity )
-		{
-			return cudaSuccess;
-		}
-		size_t newCapacity = capacity < 1024 ? 1024 : capacity;
-		while ( newCapacity < count )
-		{
-			newCapacity += newCapacity / 2;
-		}
-		if ( ptr != nullptr )
-		{
-			cudaFreeHost( ptr );
-			ptr = nullptr;
-			capacity = 0;
-		}
-		cudaError_t err = cudaHostAlloc( &ptr, newCapacity * sizeof( T ), cudaHostAllocDefault );
-		if ( err == cudaSuccess )
-		{
-			capacity = newCapacity;
-		}
-		return err;
-	}
-
-	void release()
-	{
-		if ( ptr != nullptr )
-		{
-			cudaFreeHost( ptr );
-		}
-		ptr = nullptr;
-		capacity = 0;
-	}
-};
-
-// control block, zeroed before every run
-struct ControlBlock
-{
-	unsigned int barrier[2];
-	int hasHitEvents;
-	int anyRestitution;
-	unsigned long long stageCycles[10];
-	int islandFailed; // a bin did not fit its block (binFail): the host reruns the step on the grid-barrier kernel
-	int reserved;
-};
-
-// segments of the step (see "the step as segments" below)
-struct b2gBodySeg
-{
-	uint8_t* states;
-	const uint8_t* sims;
-	const int* islands;
-	int islandCount;
-	int islandBase; // first island of this world in the batch-wide numbering
-	int count;
-	int base;		  // first body of this world in the batch-wide numbering
-	int jointBitBase; // first bit of this world in the joint-event bit set
-	int jointWords;
-};
-
-struct b2gContactSeg
-{
-	uint8_t* sims;
-	int count;
-	int slotStart; // wire slot of the segment's first contact (multiple of 4)
-	int world;
-	bool wide; // false for the overflow colour
-	int colorIndex;
-};
-
-struct b2gJointSeg
-{
-	uint8_t* sims;
-	int count;
-	int jointStart;
-	int world;
-};
-
-// host twin of b2g::jointIndexPair (b2g_joint.cuh)
-static int* b2gJointIndexPair( b2lJointSim* joint )
-{
-	switch ( joint->type )
-	{
-		case b2l_distanceJoint:
-			return &joint->u.distance.indexA;
-		case b2l_motorJoint:
-			return &joint->u.motor.indexA;
-		case b2l_moverJoint:
-			return &joint->u.mover.indexA;
-		case b2l_pogoJoint:
-			return &joint->u.pogo.indexA;
-		case b2l_prismaticJoint:
-			return &joint->u.prismatic.indexA;
-		case b2l_revoluteJoint:
-			return &joint->u.revolute.indexA;
-		case b2l_weldJoint:
-			return &joint->u.weld.indexA;
-		case b2l_wheelJoint:
-			return &joint->u.wheel.indexA;
-		default:
-			return nullptr;
-	}
-}
-
-
-struct b2GpuSolver
-{
-	int device = 0;
-	int smCount = 0;
-	int gridBlocks = 0;
-	int mode = 0;
-	bool cooperative = false;
-	cudaStream_t stream = nullptr;
-	cudaEvent_t evStart = nullptr, evStop = nullptr, evUpload = nullptr;
-
-	// device: one input arena (mirror of the host wire staging), one output arena, the SoA solver state
-	DeviceBuffer<float4> wireAll, outAll, vel, pos, bodyK, cf;
-	DeviceBuffer<float> angDamp;
-	DeviceBuffer<int2> cidx;
-	DeviceBuffer<int> cmeta;
-	ControlBlock* control = nullptr;
-
-	// island mode scratch (b2g_island.cuh)
-	DeviceBuffer<int> binCounters; // [binBodyCount | binColorStart | binJointStart | binFail], zeroed every run
-	DeviceBuffer<int> bodyLocal, binBodyList, slotGroupBits, binContactList, binJointList;
-	DeviceBuffer<int4> binContactInfo;
-	DeviceBuffer<float4> jointWork;
-	double islandHeadRoom = 1.3; // bins are sized for this many times the average bytes per bin
-	int headRoomCooldown = 0;	 // steps to wait after a failure before lowering it again
-	int countersBinCount = 0, countersListCount = 0;
-	int ownerListsOff = 0;		 // steps during which owner lists stay off after a block's share did not fit
-	bool ownerListsEnabled = true; // B2GPU_OWNER_LISTS=0 turns them off
-	bool countersClean = false; // the bin counters are all zero (the island kernels zero what they have read)
-	DeviceBuffer<int2> contactBinRank, jointBinRank;
-	std::vector<int> islandBin;	 // host: bin of every awake island
-	std::vector<int> islandBodies; // host: bodies per island, then per bin
-	size_t binCounterCount = 0;
-	size_t islandSmemBytes = 0;
-	size_t islandSmemBudget = 0;
-	// B2GPU_SPILL_JOINTS=1: allow a cluster plan with the joint records left in global memory.  Off by default: measured
-	// on joint_grid it loses to the grid-barrier kernel (0.47 vs 0.25 ms) -- 16 SMs cannot pull 19 800 records of 256 B
-	// per stage through L2 as fast as 148 SMs can
-	bool spillJointsEnabled = false;
-	bool spillJointsForced = false; // B2GPU_SPILL_JOINTS=2 (testing): steps with joints take that plan first
-	bool resolveContacts = true; // diagnostics: B2GPU_RESOLVE=0 makes the island kernels chase head -> bodyLocal themselves
-	bool stageAllThreads = false;
-	bool testTightBins = false;			 // testing: B2GPU_TEST_TIGHT_BINS=1 makes every island step fail over to the grid kernel
-	int clusterForce = 0;				 // testing: smallest cluster size the planner may use (B2GPU_CLUSTER_FORCE)
-	int clusterBins[4] = { 0, 0, 0, 0 }; // resident clusters of 2, 4, 8, 16 blocks (0 = not available)
-	int overflowContacts = 0, overflowJoints = 0; // overflow colour totals of the step (all worlds)
-	bool islandMode = false;
-	int islandsEnabled = 1;
-	int maxSharedOptin = 0;
-
-	// page-locked staging owned by the library.  The input staging is written with non-temporal stores: on the
-	// target hosts a DMA read of lines that sit dirty in several cores' caches runs at ~6 GB/s instead of ~53 GB/s
-	// (tools/microbench/h2d_bench.cu, profiles/).
-	PinnedBuffer<float4> hWire;
-	PinnedBuffer<float4> hOut;
-	ControlBlock* hControl = nullptr;
-
-	// arena layouts, in float4 units
-	size_t inStates = 0, inBody = 0, inWire = 0, inJoints = 0, inBins = 0, inTotal = 0;
-	size_t sentQuads = 0; // prefix of the input arena already enqueued for upload (b2gPumpUploads)
-	size_t outStates = 0, outImpulses = 0, outJoints = 0, outBits = 0, outTotal = 0;
-
-	// the step in flight
-	std::vector<b2GpuStepDesc> descs;
-	b2GpuStepResult* results = nullptr; // one per world, or NULL
-	std::vector<b2gBodySeg> bodySegs;
-	std::vector<b2gContactSeg> contactSegs;
-	std::vector<b2gJointSeg> jointSegs;
-	std::vector<int> bodyStart, contactStart, jointStart; // item prefix sums, one more entry than segments
-	std::vector<int> binBodies;
-	b2g::StepParams params;
-	int jointTotal = 0;
-	int contactTotal = 0;
-	bool begun = false;
-	bool uploaded = false;
-	bool ran = false;
-
-	uint64_t launchCount = 0;
-	uint64_t lastH2D = 0;
-	uint64_t lastD2H = 0;
-	int lastLaunches = 0;
-	float lastKernelMs = 0.0f;
-	std::chrono::steady_clock::time_point tBegin, tSubmit, tWaited;
-
-	// pipelined host passes (b2GpuSolverPackWork / b2GpuSolverUnpackWork): the items are dealt out in blocks, claimed in
-	// increasing order; one caller (the pump) moves the finished prefix over PCIe while the others keep packing, and
-	// publishes how much of the output arena has arrived while the others unpack behind it
-	std::atomic<int> workNext{ 0 };
-	int workBlocks = 0;
-	int workItems = 0;
-	std::unique_ptr<std::atomic<unsigned char>[]> workDone;
-	size_t workDoneCapacity = 0;
-	int pumpPrefix = 0; // pump only: blocks [0, pumpPrefix) are packed
-	std::atomic<size_t> arrivedQuads{ 0 };
-	std::atomic<int> workFailed{ 0 };
-	std::vector<cudaEvent_t> chunkEvents;
-	std::vector<size_t> chunkEnd;
-	int chunkCount = 0;
-	int chunkNext = 0; // pump only
-	cudaEvent_t evControl = nullptr;
-	bool trace = false; // B2GPU_TRACE=1: print the timeline of the pipelined transfers at EndStep (stderr)
-	std::vector<std::pair<float, size_t>> traceSends, traceArrivals;
-	float traceBegun = 0.0f, traceSubmit = 0.0f, traceControl = 0.0f;
-	float traceMarks[8] = { 0 };
-	bool controlSeen = false;
-};
-
-static int b2gRoundUp32( int n )
-{
-	return ( n + 31 ) & ~31;
 }
 
 extern "C" int b2GpuGetVersion( void )
@@ -679,31 +286,6 @@ extern "C" int b2GpuSolverGetIslandPlan( const b2GpuSolver* s, int* binCount, in
 		*blocksPerBin = bins > 0 ? s->params.clusterSize : 0;
 	}
 	return bins;
-}
-
-// ---- the step as segments ---------------------------------------------------------------------------------------------
-// One step solves `worldCount` independent worlds (1 for b2GpuSolverStep, N for the batch API).  Their arrays are
-// addressed through segments: a body segment per world, a contact / joint segment per (colour slot, world).  Colour
-// slot c holds every world's c-th ACTIVE colour (the stage order only matters inside a world, and inside a world the
-// active colours are visited in ascending order, src/solver.c:1341-1367), the last slot is the overflow colour.
-// Item order for pack/unpack: all bodies world by world, all contacts in segment (= slot) order, all joints.
-static int b2gFindSegment( const std::vector<int>& starts, int flat )
-{
-	// starts has segmentCount + 1 entries; returns the segment that contains `flat`
-	int lo = 0, hi = (int)starts.size() - 1;
-	while ( hi - lo > 1 )
-	{
-		int mid = ( lo + hi ) >> 1;
-		if ( starts[mid] <= flat )
-		{
-			lo = mid;
-		}
-		else
-		{
-			hi = mid;
-		}
-	}
-	return lo;
 }
 
 struct b2gBinPlan
@@ -966,11 +548,6 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	s->islandMode = true;
 	return 0;
 }
-
-// ---- blocks of host work --------------------------------------------------------------------------------------------
-constexpr int kWorkBlockItems = 512;
-constexpr size_t kTransferQuads = 64 * 1024; // 1 MiB: granularity of the pipelined uploads
-constexpr size_t kDownloadQuads = 32 * 1024; // 512 KiB: the unpack pass runs this far behind the download
 
 static int b2gBlocksFor( int itemCount )
 {
@@ -1282,236 +859,6 @@ extern "C" int b2GpuSolverGetUnpackItemCount( const b2GpuSolver* s )
 	return b2GpuSolverGetPackItemCount( s );
 }
 
-// ---- phase 2: pack the reference's arrays into the wire format (callable concurrently on disjoint ranges) ---------
-static inline float b2gRdF( const uint8_t* p, int offset )
-{
-	float v;
-	memcpy( &v, p + offset, 4 );
-	return v;
-}
-
-static inline float b2gIntBits( int v )
-{
-	float f;
-	memcpy( &f, &v, 4 );
-	return f;
-}
-
-static inline int b2gRdI( const uint8_t* p, int offset )
-{
-	int v;
-	memcpy( &v, p + offset, 4 );
-	return v;
-}
-
-// non-temporal 16-byte stores: the staging buffer must not stay dirty in the CPU caches (see b2GpuSolver::hWire)
-static inline void b2gStream4( float4* dst, float a, float b, float c, float d )
-{
-	_mm_stream_ps( reinterpret_cast<float*>( dst ), _mm_set_ps( d, c, b, a ) );
-}
-
-static inline void b2gStreamCopy( float4* dst, const uint8_t* src, int quads )
-{
-	for ( int q = 0; q < quads; ++q )
-	{
-		_mm_stream_si128( reinterpret_cast<__m128i*>( dst + q ), _mm_loadu_si128( reinterpret_cast<const __m128i*>( src + 16 * q ) ) );
-	}
-}
-
-extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
-{
-	int bodyCount = s->params.bodyCount;
-	float4* base = s->hWire.ptr;
-
-	// ---- bodies: the state as is + the 32 of b2BodySim's 96 bytes that integrate-velocities reads (src/solver.c:94-102)
-	{
-		float4* wireStates = base + s->inStates;
-		float4* wireBody = base + s->inBody;
-		int* wireBins = reinterpret_cast<int*>( base + s->inBins );
-		int i = begin;
-		int bodyEnd = end < bodyCount ? end : bodyCount;
-		int w = i < bodyEnd ? b2gFindSegment( s->bodyStart, i ) : 0;
-		while ( i < bodyEnd )
-		{
-			const b2gBodySeg& seg = s->bodySegs[w];
-			int segEnd = seg.base + seg.count < bodyEnd ? seg.base + seg.count : bodyEnd;
-			for ( ; i < segEnd; ++i )
-			{
-				int local = i - seg.base;
-				if ( s->islandMode )
-				{
-					_mm_stream_si32( wireBins + i, s->islandBin[seg.islandBase + ( seg.islandCount == 1 ? 0 : seg.islands[local] )] );
-				}
-				b2gStreamCopy( wireStates + 2 * (size_t)i, seg.states + (size_t)local * B2L_STATE_SIZE, 2 );
-				const uint8_t* sim = seg.sims + (size_t)local * B2L_SIM_SIZE;
-				b2gStream4( wireBody + 2 * (size_t)i + 0, b2gRdF( sim, B2L_SIM_INV_MASS ), b2gRdF( sim, B2L_SIM_INV_INERTIA ),
-							b2gRdF( sim, B2L_SIM_FORCE ), b2gRdF( sim, B2L_SIM_FORCE + 4 ) );
-				b2gStream4( wireBody + 2 * (size_t)i + 1, b2gRdF( sim, B2L_SIM_TORQUE ), b2gRdF( sim, B2L_SIM_LINEAR_DAMPING ),
-							b2gRdF( sim, B2L_SIM_ANGULAR_DAMPING ), b2gRdF( sim, B2L_SIM_GRAVITY_SCALE ) );
-			}
-			w += 1;
-		}
-	}
-
-	// ---- contacts: the 112 of b2ContactSim's 200 bytes that prepare reads (src/contact_solver.c:1629-1785)
-	{
-		float4* wire = base + s->inWire;
-		int flat = ( begin > bodyCount ? begin : bodyCount ) - bodyCount;
-		int flatEnd = ( end - bodyCount < s->contactTotal ? end - bodyCount : s->contactTotal );
-		int k = flat < flatEnd ? b2gFindSegment( s->contactStart, flat ) : 0;
-		while ( flat < flatEnd )
-		{
-			const b2gContactSeg& seg = s->contactSegs[k];
-			int segFlat = s->contactStart[k];
-			int local = flat - segFlat;
-			int localEnd = ( flatEnd < s->contactStart[k + 1] ? flatEnd : s->contactStart[k + 1] ) - segFlat;
-			int bodyBase = s->bodySegs[seg.world].base;
-			for ( int i = local; i < localEnd; ++i )
-			{
-				const uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
-				const uint8_t* m = sim + B2L_CONTACT_MANIFOLD;
-				const uint8_t* p0 = m + B2L_MANIFOLD_POINTS;
-				const uint8_t* p1 = p0 + B2L_MP_SIZE;
-				int pointCount = b2gRdI( m, B2L_MANIFOLD_POINT_COUNT );
-				int hitEnable = ( (uint32_t)b2gRdI( sim, B2L_CONTACT_SIM_FLAGS ) & B2L_SIM_ENABLE_HIT_EVENT ) != 0 ? b2g::kMetaHitEnable : 0;
-				int meta = ( seg.colorIndex << b2g::kMetaColorShift ) | hitEnable | ( pointCount & b2g::kMetaPointMask );
-				int indexA = b2gRdI( sim, B2L_CONTACT_INDEX_A ), indexB = b2gRdI( sim, B2L_CONTACT_INDEX_B );
-				indexA = indexA >= 0 ? indexA + bodyBase : indexA;
-				indexB = indexB >= 0 ? indexB + bodyBase : indexB;
-				float4* w = wire + (size_t)( seg.slotStart + i ) * b2g::WR_COUNT;
-				b2gStream4( w + b2g::WR_HEAD, b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta ),
-							b2gRdF( m, B2L_MANIFOLD_ROLLING_IMPULSE ) );
-				b2gStream4( w + b2g::WR_MASS, b2gRdF( sim, B2L_CONTACT_INV_MASS_A ), b2gRdF( sim, B2L_CONTACT_INV_I_A ),
-							b2gRdF( sim, B2L_CONTACT_INV_MASS_B ), b2gRdF( sim, B2L_CONTACT_INV_I_B ) );
-				b2gStream4( w + b2g::WR_NORMAL, b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ),
-							b2gRdF( sim, B2L_CONTACT_FRICTION ), b2gRdF( sim, B2L_CONTACT_TANGENT_SPEED ) );
-				b2gStream4( w + b2g::WR_MATERIAL, b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ), b2gRdF( sim, B2L_CONTACT_RESTITUTION ),
-							b2gRdF( p0, B2L_MP_SEPARATION ), b2gRdF( p1, B2L_MP_SEPARATION ) );
-				b2gStream4( w + b2g::WR_ANCHOR1, b2gRdF( p0, B2L_MP_ANCHOR_A ), b2gRdF( p0, B2L_MP_ANCHOR_A + 4 ),
-							b2gRdF( p0, B2L_MP_ANCHOR_B ), b2gRdF( p0, B2L_MP_ANCHOR_B + 4 ) );
-				b2gStream4( w + b2g::WR_ANCHOR2, b2gRdF( p1, B2L_MP_ANCHOR_A ), b2gRdF( p1, B2L_MP_ANCHOR_A + 4 ),
-							b2gRdF( p1, B2L_MP_ANCHOR_B ), b2gRdF( p1, B2L_MP_ANCHOR_B + 4 ) );
-				b2gStream4( w + b2g::WR_IMPULSE, b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ),
-							b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ) );
-			}
-			if ( localEnd == seg.count )
-			{
-				// dead slots between this segment and the next (segments start on multiples of 4 slots): a zero head
-				// (pointCount 0) is all the kernels look at
-				int segEnd = seg.slotStart + seg.count;
-				int next = (size_t)k + 1 < s->contactSegs.size() ? s->contactSegs[(size_t)k + 1].slotStart : segEnd;
-				int limit = ( segEnd + 3 ) & ~3;
-				next = next < limit ? next : limit;
-				for ( int dead = segEnd; dead < next; ++dead )
-				{
-					_mm_stream_ps( reinterpret_cast<float*>( wire + (size_t)dead * b2g::WR_COUNT + b2g::WR_HEAD ), _mm_setzero_ps() );
-				}
-			}
-			flat = s->contactStart[k + 1];
-			k += 1;
-		}
-	}
-
-	// ---- joints: the prepared b2JointSim padded to 256 bytes; bodies renumbered to the batch, and the world's base in
-	// the joint-event bit set stored in the padding (read by jointEventTest)
-	{
-		float4* wireJoints = base + s->inJoints;
-		int first = bodyCount + s->contactTotal;
-		int flat = ( begin > first ? begin : first ) - first;
-		int flatEnd = end - first;
-		int k = flat < flatEnd ? b2gFindSegment( s->jointStart, flat ) : 0;
-		while ( flat < flatEnd )
-		{
-			const b2gJointSeg& seg = s->jointSegs[k];
-			int local = flat - s->jointStart[k];
-			int localEnd = ( flatEnd < s->jointStart[k + 1] ? flatEnd : s->jointStart[k + 1] ) - s->jointStart[k];
-			const b2gBodySeg& world = s->bodySegs[seg.world];
-			for ( int i = local; i < localEnd; ++i )
-			{
-				alignas( 16 ) uint8_t padded[b2g::kJointStride] = { 0 };
-				memcpy( padded, seg.sims + (size_t)i * B2L_JOINT_SIZE, B2L_JOINT_SIZE );
-				if ( world.base != 0 )
-				{
-					int* pair = b2gJointIndexPair( reinterpret_cast<b2lJointSim*>( padded ) );
-					if ( pair != nullptr )
-					{
-						pair[0] = pair[0] >= 0 ? pair[0] + world.base : pair[0];
-						pair[1] = pair[1] >= 0 ? pair[1] + world.base : pair[1];
-					}
-				}
-				memcpy( padded + B2L_JOINT_SIZE, &world.jointBitBase, 4 );
-				b2gStreamCopy( wireJoints + (size_t)( seg.jointStart + i ) * ( b2g::kJointStride / 16 ), padded, b2g::kJointStride / 16 );
-			}
-			flat = s->jointStart[k + 1];
-			k += 1;
-		}
-	}
-	_mm_sfence();
-}
-
-// ---- phase 3: H2D + kernels + D2H, all asynchronous on the solver's stream -------------------------------------------
-// quads of the input arena that hold items [0, itemEnd) (bodies, then contacts in slot order, then joints)
-// The pack pass claims blocks in ARENA order: first the blocks of the constraints (items [bodyCount, itemCount)), then
-// the blocks of the bodies (items [0, bodyCount)).
-static void b2gPackBlockRange( const b2GpuSolver* s, int block, int* begin, int* end )
-{
-	int bodyCount = s->params.bodyCount;
-	int restItems = s->workItems - bodyCount;
-	int restBlocks = ( restItems + kWorkBlockItems - 1 ) / kWorkBlockItems;
-	if ( block < restBlocks )
-	{
-		*begin = bodyCount + block * kWorkBlockItems;
-		*end = *begin + kWorkBlockItems < s->workItems ? *begin + kWorkBlockItems : s->workItems;
-	}
-	else
-	{
-		*begin = ( block - restBlocks ) * kWorkBlockItems;
-		*end = *begin + kWorkBlockItems < bodyCount ? *begin + kWorkBlockItems : bodyCount;
-	}
-}
-
-// quads of the input arena that are complete once the first `blocksDone` blocks (in claim order) are packed
-static size_t b2gPackedPrefix( const b2GpuSolver* s, int blocksDone )
-{
-	int restItems = s->contactTotal + s->jointTotal;
-	int restBlocks = ( restItems + kWorkBlockItems - 1 ) / kWorkBlockItems;
-	if ( blocksDone >= s->workBlocks )
-	{
-		return s->inTotal;
-	}
-	if ( blocksDone >= restBlocks )
-	{
-		return s->inStates; // the three body regions are interleaved by region, not by body: wait for all bodies
-	}
-	int flat = blocksDone * kWorkBlockItems; // constraints [0, flat) are packed, flat < restItems
-	if ( flat < s->contactTotal )
-	{
-		int k = b2gFindSegment( s->contactStart, flat );
-		int slot = s->contactSegs[k].slotStart + ( flat - s->contactStart[k] );
-		return s->inWire + (size_t)slot * b2g::WR_COUNT;
-	}
-	return s->inJoints + (size_t)( flat - s->contactTotal ) * ( b2g::kJointStride / 16 );
-}
-
-static int b2gSendArena( b2GpuSolver* s, size_t uptoQuads )
-{
-	if ( s->sentQuads == 0 )
-	{
-		B2G_CUDA( cudaEventRecord( s->evUpload, s->stream ) );
-	}
-	if ( uptoQuads > s->sentQuads )
-	{
-		if ( s->trace )
-		{
-			s->traceSends.emplace_back( std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(), uptoQuads );
-		}
-		B2G_CUDA( cudaMemcpyAsync( s->wireAll.ptr + s->sentQuads, s->hWire.ptr + s->sentQuads,
-								   ( uptoQuads - s->sentQuads ) * sizeof( float4 ), cudaMemcpyHostToDevice, s->stream ) );
-		s->sentQuads = uptoQuads;
-	}
-	return 0;
-}
-
 static int b2gEnqueueUpload( b2GpuSolver* s )
 {
 	if ( b2gSendArena( s, s->inTotal ) != 0 )
@@ -1586,7 +933,6 @@ static int b2gRunStages( b2GpuSolver* s )
 	return 0;
 }
 
-static int b2gEnqueueDownload( b2GpuSolver* s );
 
 static int b2gLaunchGridKernel( b2GpuSolver* s )
 {
@@ -1612,7 +958,7 @@ static int b2gLaunchGridKernel( b2GpuSolver* s )
 // The island kernels give up when a bin turns out not to fit its block (rare: the planner sizes the bins from the body
 // counts and cannot see how the constraints spread).  The flag comes back with the control block; the step is then run
 // again on the grid-barrier kernel from the untouched inputs.  Called after the stream has been synchronised.
-static int b2gRerunIfIslandsFailed( b2GpuSolver* s, bool download )
+int b2gRerunIfIslandsFailed( b2GpuSolver* s, bool download )
 {
 	if ( !s->islandMode || s->mode != 0 || s->hControl->islandFailed == 0 )
 	{
@@ -1732,7 +1078,7 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 	return 0;
 }
 
-static int b2gEnqueueDownload( b2GpuSolver* s )
+int b2gEnqueueDownload( b2GpuSolver* s )
 {
 	// the control block first (it says whether the island kernels gave up), then the output arena in chunks with an
 	// event each, so that unpacking can start behind the transfer
@@ -1798,362 +1144,6 @@ extern "C" int b2GpuSolverWait( b2GpuSolver* s )
 	if ( s->ran )
 	{
 		B2G_CUDA( cudaEventElapsedTime( &s->lastKernelMs, s->evStart, s->evStop ) );
-	}
-	return 0;
-}
-
-// ---- phase 4: unpack (callable concurrently on disjoint ranges) ---------------------------------------------------------
-// Evict a consumed part of the D2H staging buffer from the CPU caches.  On the target hosts a DMA write into lines
-// that are still cached by several cores runs at ~7 GB/s instead of ~54 GB/s (tools/microbench/d2h_bench.cu); flushing
-// right after the unpack pass keeps the next step's download at full speed for ~0.03 ms of host work.
-#if defined( __x86_64__ )
-static bool b2gHasClflushopt()
-{
-	static int cached = -1;
-	if ( cached < 0 )
-	{
-		unsigned a = 0, b = 0, c = 0, d = 0;
-		cached = ( __get_cpuid_count( 7, 0, &a, &b, &c, &d ) != 0 && ( b & ( 1u << 23 ) ) != 0 ) ? 1 : 0;
-	}
-	return cached == 1;
-}
-
-__attribute__( ( target( "clflushopt" ) ) ) static void b2gFlushOpt( const char* p, const char* end )
-{
-	for ( ; p < end; p += 64 )
-	{
-		_mm_clflushopt( const_cast<char*>( p ) );
-	}
-}
-
-static void b2gFlushLines( const void* ptr, size_t bytes )
-{
-	if ( bytes == 0 )
-	{
-		return;
-	}
-	const char* p = reinterpret_cast<const char*>( reinterpret_cast<uintptr_t>( ptr ) & ~uintptr_t( 63 ) );
-	const char* end = static_cast<const char*>( ptr ) + bytes;
-	if ( b2gHasClflushopt() )
-	{
-		b2gFlushOpt( p, end );
-	}
-	else
-	{
-		for ( ; p < end; p += 64 )
-		{
-			_mm_clflush( p );
-		}
-	}
-}
-#else
-static void b2gFlushLines( const void*, size_t )
-{
-}
-#endif
-
-// Scatter the packed impulse records into the reference's manifolds: what b2StoreImpulsesTask
-// (src/contact_solver.c:2293-2320) and b2StoreImpulses_Overflow (:526-542) write.
-extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
-{
-	if ( begin >= end )
-	{
-		return;
-	}
-	int bodyCount = s->params.bodyCount;
-	const float4* base = s->hOut.ptr;
-
-	// ---- body states
-	{
-		const float4* outStates = base + s->outStates;
-		int i = begin;
-		int bodyEnd = end < bodyCount ? end : bodyCount;
-		int w = i < bodyEnd ? b2gFindSegment( s->bodyStart, i ) : 0;
-		while ( i < bodyEnd )
-		{
-			const b2gBodySeg& seg = s->bodySegs[w];
-			int segEnd = seg.base + seg.count < bodyEnd ? seg.base + seg.count : bodyEnd;
-			if ( i < segEnd )
-			{
-				memcpy( seg.states + (size_t)( i - seg.base ) * B2L_STATE_SIZE, outStates + 2 * (size_t)i, (size_t)( segEnd - i ) * B2L_STATE_SIZE );
-				b2gFlushLines( outStates + 2 * (size_t)i, (size_t)( segEnd - i ) * B2L_STATE_SIZE );
-				i = segEnd;
-			}
-			w += 1;
-		}
-	}
-
-	// ---- contact impulses
-	{
-		const float* allRecords = reinterpret_cast<const float*>( base + s->outImpulses );
-		int flat = ( begin > bodyCount ? begin : bodyCount ) - bodyCount;
-		int flatEnd = ( end - bodyCount < s->contactTotal ? end - bodyCount : s->contactTotal );
-		int k = flat < flatEnd ? b2gFindSegment( s->contactStart, flat ) : 0;
-		while ( flat < flatEnd )
-		{
-			const b2gContactSeg& seg = s->contactSegs[k];
-			b2GpuStepResult* result = s->results != nullptr ? s->results + seg.world : nullptr;
-			uint64_t* hitBits = result != nullptr ? result->hitEventBits : nullptr;
-			int local = flat - s->contactStart[k];
-			int localEnd = ( flatEnd < s->contactStart[k + 1] ? flatEnd : s->contactStart[k + 1] ) - s->contactStart[k];
-			const float* records = allRecords + (size_t)seg.slotStart * b2g::kImpulseFloats;
-			for ( int i = local; i < localEnd; ++i )
-			{
-				uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
-				uint8_t* manifold = sim + B2L_CONTACT_MANIFOLD;
-				const float* rec = records + (size_t)i * b2g::kImpulseFloats;
-				int pointCount = seg.wide ? 2 : b2gRdI( manifold, B2L_MANIFOLD_POINT_COUNT );
-				memcpy( manifold + B2L_MANIFOLD_ROLLING_IMPULSE, rec + 0, 4 );
-				for ( int j = 0; j < pointCount; ++j )
-				{
-					uint8_t* mp = manifold + B2L_MANIFOLD_POINTS + j * B2L_MP_SIZE;
-					// normalImpulse, tangentImpulse, totalNormalImpulse, normalVelocity are contiguous (collision.h:549-561)
-					memcpy( mp + B2L_MP_NORMAL_IMPULSE, rec + 1 + 4 * j, 16 );
-				}
-				if ( rec[9] != 0.0f && result != nullptr )
-				{
-					if ( hitBits != nullptr )
-					{
-						uint32_t id = (uint32_t)b2gRdI( sim, B2L_CONTACT_ID );
-						__atomic_fetch_or( hitBits + ( id >> 6 ), (uint64_t)1 << ( id & 63u ), __ATOMIC_RELAXED );
-					}
-					__atomic_store_n( &result->hasHitEvents, 1, __ATOMIC_RELAXED );
-				}
-			}
-			if ( local < localEnd )
-			{
-				b2gFlushLines( records + (size_t)local * b2g::kImpulseFloats, (size_t)( localEnd - local ) * b2g::kImpulseFloats * sizeof( float ) );
-			}
-			flat = s->contactStart[k + 1];
-			k += 1;
-		}
-	}
-
-	// ---- joints: the fields the stages wrote (b2lJointMutableRuns) go back into the reference's b2JointSim in place
-	{
-		const float* outJoints = reinterpret_cast<const float*>( base + s->outJoints );
-		int first = bodyCount + s->contactTotal;
-		int flat = ( begin > first ? begin : first ) - first;
-		int flatEnd = end - first;
-		int k = flat < flatEnd ? b2gFindSegment( s->jointStart, flat ) : 0;
-		while ( flat < flatEnd )
-		{
-			const b2gJointSeg& seg = s->jointSegs[k];
-			int local = flat - s->jointStart[k];
-			int localEnd = ( flatEnd < s->jointStart[k + 1] ? flatEnd : s->jointStart[k + 1] ) - s->jointStart[k];
-			for ( int i = local; i < localEnd; ++i )
-			{
-				uint8_t* sim = seg.sims + (size_t)i * B2L_JOINT_SIZE;
-				const float* record = outJoints + (size_t)( seg.jointStart + i ) * B2L_JOINT_OUT_FLOATS;
-				int offsets[2], floats[2];
-				int runs = b2lJointMutableRuns( b2gRdI( sim, offsetof( b2lJointSim, type ) ), offsets, floats );
-				for ( int r = 0; r < runs; ++r )
-				{
-					memcpy( sim + offsets[r], record, (size_t)floats[r] * sizeof( float ) );
-					record += floats[r];
-				}
-			}
-			if ( local < localEnd )
-			{
-				b2gFlushLines( outJoints + (size_t)( seg.jointStart + local ) * B2L_JOINT_OUT_FLOATS,
-							   (size_t)( localEnd - local ) * B2L_JOINT_OUT_FLOATS * sizeof( float ) );
-			}
-			flat = s->jointStart[k + 1];
-			k += 1;
-		}
-	}
-}
-
-// ---- pipelined host passes ------------------------------------------------------------------------------------------------
-// b2GpuSolverPackWork / b2GpuSolverUnpackWork are called by ANY number of host threads at the same time (the world's
-// workers); each call claims blocks of items until none are left.  Exactly one caller passes pump = 1: besides packing
-// it starts the upload of every finished prefix of the arena (PCIe runs behind the packing instead of after it), and
-// besides unpacking it watches the download events and tells the others how much of the output has arrived (unpacking
-// runs behind the download).
-static int b2gPumpUploads( b2GpuSolver* s, bool everything )
-{
-	while ( s->pumpPrefix < s->workBlocks && s->workDone[s->pumpPrefix].load( std::memory_order_acquire ) != 0 )
-	{
-		s->pumpPrefix += 1;
-	}
-	bool complete = s->pumpPrefix == s->workBlocks;
-	size_t ready = b2gPackedPrefix( s, s->pumpPrefix );
-	if ( ready > s->sentQuads && ( ( complete && everything ) || ready - s->sentQuads >= kTransferQuads ) )
-	{
-		return b2gSendArena( s, ready );
-	}
-	return 0;
-}
-
-extern "C" int b2GpuSolverPackWork( b2GpuSolver* s, int pump )
-{
-	if ( s == nullptr || !s->begun )
-	{
-		return b2gFailMsg( "b2GpuSolverPackWork: no step begun" );
-	}
-	if ( pump != 0 )
-	{
-		cudaSetDevice( s->device );
-	}
-	for ( ;; )
-	{
-		if ( pump != 0 && b2gPumpUploads( s, false ) != 0 )
-		{
-			s->workFailed.store( 1 );
-			return 1;
-		}
-		int block = s->workNext.fetch_add( 1, std::memory_order_acq_rel );
-		if ( block >= s->workBlocks )
-		{
-			break;
-		}
-		int begin, end;
-		b2gPackBlockRange( s, block, &begin, &end );
-		b2GpuSolverPackRange( s, begin, end ); // ends with an sfence: the streaming stores are visible to the DMA engine
-		s->workDone[block].store( 1, std::memory_order_release );
-	}
-	if ( pump != 0 )
-	{
-		// the others may still be packing the blocks they claimed
-		while ( s->pumpPrefix < s->workBlocks )
-		{
-			if ( b2gPumpUploads( s, false ) != 0 )
-			{
-				return 1;
-			}
-			_mm_pause();
-		}
-		return b2gPumpUploads( s, true );
-	}
-	return 0;
-}
-
-// quads of the output arena that must have arrived before items [0, itemEnd) can be unpacked
-static size_t b2gOutPrefix( const b2GpuSolver* s, int itemEnd )
-{
-	int bodyCount = s->params.bodyCount;
-	if ( itemEnd <= bodyCount )
-	{
-		return s->outStates + 2 * (size_t)itemEnd;
-	}
-	int flat = itemEnd - bodyCount;
-	if ( flat <= s->contactTotal )
-	{
-		// the record of the last contact of the range
-		int k = b2gFindSegment( s->contactStart, flat - 1 );
-		int slot = s->contactSegs[k].slotStart + ( flat - 1 - s->contactStart[k] );
-		return s->outImpulses + ( (size_t)( slot + 1 ) * b2g::kImpulseFloats + 3 ) / 4;
-	}
-	int joints = flat - s->contactTotal;
-	joints = joints < s->jointTotal ? joints : s->jointTotal;
-	return s->outJoints + (size_t)joints * ( B2L_JOINT_OUT_FLOATS / 4 );
-}
-
-static int b2gPumpDownloads( b2GpuSolver* s )
-{
-	if ( !s->controlSeen )
-	{
-		// kernels done?  (the control block is the first thing that comes back)
-		cudaError_t err = cudaEventQuery( s->evControl );
-		if ( err == cudaErrorNotReady )
-		{
-			return 0;
-		}
-		if ( err != cudaSuccess )
-		{
-			return b2gFail( "device solve", err );
-		}
-		if ( s->ran && s->islandMode && s->hControl->islandFailed != 0 )
-		{
-			// rare: rerun on the grid-barrier kernel; that re-enqueues the downloads and waits for them
-			B2G_CUDA( cudaStreamSynchronize( s->stream ) );
-			if ( b2gRerunIfIslandsFailed( s, true ) != 0 )
-			{
-				return 1;
-			}
-			s->chunkNext = s->chunkCount;
-			s->arrivedQuads.store( s->outTotal, std::memory_order_release );
-		}
-		s->controlSeen = true;
-		s->tWaited = std::chrono::steady_clock::now();
-		s->traceControl = std::chrono::duration<float, std::micro>( s->tWaited - s->tBegin ).count();
-	}
-	while ( s->chunkNext < s->chunkCount )
-	{
-		cudaError_t err = cudaEventQuery( s->chunkEvents[(size_t)s->chunkNext] );
-		if ( err == cudaErrorNotReady )
-		{
-			break;
-		}
-		if ( err != cudaSuccess )
-		{
-			return b2gFail( "download", err );
-		}
-		s->arrivedQuads.store( s->chunkEnd[(size_t)s->chunkNext], std::memory_order_release );
-		if ( s->trace )
-		{
-			s->traceArrivals.emplace_back( std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(),
-										   s->chunkEnd[(size_t)s->chunkNext] );
-		}
-		s->chunkNext += 1;
-	}
-	return 0;
-}
-
-extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
-{
-	if ( s == nullptr || !s->begun )
-	{
-		return b2gFailMsg( "b2GpuSolverUnpackWork: no step begun" );
-	}
-	if ( pump != 0 )
-	{
-		cudaSetDevice( s->device );
-	}
-	for ( ;; )
-	{
-		int block = s->workNext.fetch_add( 1, std::memory_order_acq_rel );
-		if ( block >= s->workBlocks )
-		{
-			break;
-		}
-		int begin = block * kWorkBlockItems;
-		int end = begin + kWorkBlockItems < s->workItems ? begin + kWorkBlockItems : s->workItems;
-		size_t need = b2gOutPrefix( s, end );
-		while ( s->arrivedQuads.load( std::memory_order_acquire ) < need )
-		{
-			if ( pump != 0 )
-			{
-				if ( b2gPumpDownloads( s ) != 0 )
-				{
-					s->workFailed.store( 1 );
-					return 1;
-				}
-			}
-			else if ( s->workFailed.load( std::memory_order_relaxed ) != 0 )
-			{
-				return 1;
-			}
-			_mm_pause();
-		}
-		b2GpuSolverUnpackRange( s, begin, end );
-	}
-	if ( pump != 0 )
-	{
-		// the tail of the arena (joint event bits) is consumed by EndStep
-		while ( !s->controlSeen || s->chunkNext < s->chunkCount )
-		{
-			if ( b2gPumpDownloads( s ) != 0 )
-			{
-				s->workFailed.store( 1 );
-				return 1;
-			}
-			_mm_pause();
-		}
-		if ( s->ran )
-		{
-			B2G_CUDA( cudaEventElapsedTime( &s->lastKernelMs, s->evStart, s->evStop ) );
-		}
 	}
 	return 0;
 }
@@ -2382,137 +1372,3 @@ extern "C" int b2GpuSolverDownloadBatch( b2GpuSolver* s, const b2GpuStepDesc* de
 	return b2gDownloadAll( s, descs, worldCount, results );
 }
 
-// =================================================================================================================
-// Page-locked host allocator for b2SetAllocator (include/box2d/base.h:86)
-// =================================================================================================================
-namespace
-{
-
-struct PinnedPool
-{
-	static constexpr int kMinShift = 6;	 // 64 B: every block is at least cache-line aligned
-	static constexpr int kMaxShift = 40;
-	static constexpr size_t kSlabBytes = size_t( 32 ) << 20;
-
-	std::mutex mutex;
-	std::vector<void*> freeLists[kMaxShift + 1];
-	std::vector<std::pair<char*, size_t>> slabs;
-	char* cursor = nullptr;
-	size_t remaining = 0;
-	bool pinned = true;
-
-	static int classOf( size_t size )
-	{
-		int shift = kMinShift;
-		while ( ( size_t( 1 ) << shift ) < size )
-		{
-			shift += 1;
-		}
-		return shift;
-	}
-
-	char* newSlab( size_t bytes )
-	{
-		void* mem = nullptr;
-		if ( pinned )
-		{
-			if ( cudaHostAlloc( &mem, bytes, cudaHostAllocPortable ) != cudaSuccess )
-			{
-				cudaGetLastError();
-				pinned = false; // no driver: plain memory keeps the host library usable for CPU-only tests
-				mem = nullptr;
-			}
-		}
-		if ( mem == nullptr )
-		{
-			if ( posix_memalign( &mem, 4096, bytes ) != 0 )
-			{
-				return nullptr;
-			}
-		}
-		slabs.emplace_back( static_cast<char*>( mem ), bytes );
-		return static_cast<char*>( mem );
-	}
-
-	void* allocate( size_t size )
-	{
-		int shift = classOf( size );
-		size_t bytes = size_t( 1 ) << shift;
-		std::lock_guard<std::mutex> lock( mutex );
-		std::vector<void*>& list = freeLists[shift];
-		if ( !list.empty() )
-		{
-			void* mem = list.back();
-			list.pop_back();
-			return mem;
-		}
-		if ( bytes >= kSlabBytes / 4 )
-		{
-			return newSlab( bytes ); // big blocks get their own registration
-		}
-		if ( remaining < bytes )
-		{
-			cursor = newSlab( kSlabBytes );
-			remaining = cursor != nullptr ? kSlabBytes : 0;
-			if ( cursor == nullptr )
-			{
-				return nullptr;
-			}
-		}
-		// keep natural alignment of the size class (up to 4 KiB)
-		size_t align = bytes < 4096 ? bytes : 4096;
-		size_t misalign = reinterpret_cast<uintptr_t>( cursor ) & ( align - 1 );
-		if ( misalign != 0 )
-		{
-			size_t skip = align - misalign;
-			if ( skip + bytes > remaining )
-			{
-				cursor = newSlab( kSlabBytes );
-				remaining = cursor != nullptr ? kSlabBytes : 0;
-				if ( cursor == nullptr )
-				{
-					return nullptr;
-				}
-			}
-			else
-			{
-				cursor += skip;
-				remaining -= skip;
-			}
-		}
-		void* mem = cursor;
-		cursor += bytes;
-		remaining -= bytes;
-		return mem;
-	}
-
-	void release( void* mem, size_t size )
-	{
-		if ( mem == nullptr )
-		{
-			return;
-		}
-		int shift = classOf( size );
-		std::lock_guard<std::mutex> lock( mutex );
-		freeLists[shift].push_back( mem );
-	}
-};
-
-PinnedPool& pinnedPool()
-{
-	static PinnedPool* pool = new PinnedPool(); // intentionally leaked: outlives every world
-	return *pool;
-}
-
-} // namespace
-
-extern "C" void* b2GpuHostAlloc( size_t size, int alignment )
-{
-	(void)alignment; // blocks are aligned to min(size class, 4096) >= any alignment Box2D asks for (<= 64)
-	return pinnedPool().allocate( size == 0 ? 1 : size );
-}
-
-extern "C" void b2GpuHostFree( void* mem, size_t size )
-{
-	pinnedPool().release( mem, size == 0 ? 1 : size );
-}

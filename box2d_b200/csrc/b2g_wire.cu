@@ -1,0 +1,630 @@
+// b2g_wire.cu -- the two memory-bound host passes of a step and their PCIe transfers.
+//
+// Pack: the reference's arrays -> the wire format in the page-locked input arena (non-temporal stores); unpack: the
+// output arena -> the reference's arrays in place.  Both run on however many host threads the caller brings
+// (b2GpuSolverPackWork / UnpackWork): blocks of items are claimed in order, one caller pumps the transfers.
+#include "b2g_host.h"
+
+#include "b2gpu_layout.h"
+
+#include <immintrin.h>
+#if defined( __x86_64__ )
+#include <cpuid.h>
+#endif
+
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+
+static int* b2gJointIndexPair( b2lJointSim* joint )
+{
+	switch ( joint->type )
+	{
+		case b2l_distanceJoint:
+			return &joint->u.distance.indexA;
+		case b2l_motorJoint:
+			return &joint->u.motor.indexA;
+		case b2l_moverJoint:
+			return &joint->u.mover.indexA;
+		case b2l_pogoJoint:
+			return &joint->u.pogo.indexA;
+		case b2l_prismaticJoint:
+			return &joint->u.prismatic.indexA;
+		case b2l_revoluteJoint:
+			return &joint->u.revolute.indexA;
+		case b2l_weldJoint:
+			return &joint->u.weld.indexA;
+		case b2l_wheelJoint:
+			return &joint->u.wheel.indexA;
+		default:
+			return nullptr;
+	}
+}
+
+
+// ---- phase 2: pack the reference's arrays into the wire format (callable concurrently on disjoint ranges) ---------
+static inline float b2gRdF( const uint8_t* p, int offset )
+{
+	float v;
+	memcpy( &v, p + offset, 4 );
+	return v;
+}
+
+static inline float b2gIntBits( int v )
+{
+	float f;
+	memcpy( &f, &v, 4 );
+	return f;
+}
+
+static inline int b2gRdI( const uint8_t* p, int offset )
+{
+	int v;
+	memcpy( &v, p + offset, 4 );
+	return v;
+}
+
+// non-temporal 16-byte stores: the staging buffer must not stay dirty in the CPU caches (see b2GpuSolver::hWire)
+static inline void b2gStream4( float4* dst, float a, float b, float c, float d )
+{
+	_mm_stream_ps( reinterpret_cast<float*>( dst ), _mm_set_ps( d, c, b, a ) );
+}
+
+static inline void b2gStreamCopy( float4* dst, const uint8_t* src, int quads )
+{
+	for ( int q = 0; q < quads; ++q )
+	{
+		_mm_stream_si128( reinterpret_cast<__m128i*>( dst + q ), _mm_loadu_si128( reinterpret_cast<const __m128i*>( src + 16 * q ) ) );
+	}
+}
+
+extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
+{
+	int bodyCount = s->params.bodyCount;
+	float4* base = s->hWire.ptr;
+
+	// ---- bodies: the state as is + the 32 of b2BodySim's 96 bytes that integrate-velocities reads (src/solver.c:94-102)
+	{
+		float4* wireStates = base + s->inStates;
+		float4* wireBody = base + s->inBody;
+		int* wireBins = reinterpret_cast<int*>( base + s->inBins );
+		int i = begin;
+		int bodyEnd = end < bodyCount ? end : bodyCount;
+		int w = i < bodyEnd ? b2gFindSegment( s->bodyStart, i ) : 0;
+		while ( i < bodyEnd )
+		{
+			const b2gBodySeg& seg = s->bodySegs[w];
+			int segEnd = seg.base + seg.count < bodyEnd ? seg.base + seg.count : bodyEnd;
+			for ( ; i < segEnd; ++i )
+			{
+				int local = i - seg.base;
+				if ( s->islandMode )
+				{
+					_mm_stream_si32( wireBins + i, s->islandBin[seg.islandBase + ( seg.islandCount == 1 ? 0 : seg.islands[local] )] );
+				}
+				b2gStreamCopy( wireStates + 2 * (size_t)i, seg.states + (size_t)local * B2L_STATE_SIZE, 2 );
+				const uint8_t* sim = seg.sims + (size_t)local * B2L_SIM_SIZE;
+				b2gStream4( wireBody + 2 * (size_t)i + 0, b2gRdF( sim, B2L_SIM_INV_MASS ), b2gRdF( sim, B2L_SIM_INV_INERTIA ),
+							b2gRdF( sim, B2L_SIM_FORCE ), b2gRdF( sim, B2L_SIM_FORCE + 4 ) );
+				b2gStream4( wireBody + 2 * (size_t)i + 1, b2gRdF( sim, B2L_SIM_TORQUE ), b2gRdF( sim, B2L_SIM_LINEAR_DAMPING ),
+							b2gRdF( sim, B2L_SIM_ANGULAR_DAMPING ), b2gRdF( sim, B2L_SIM_GRAVITY_SCALE ) );
+			}
+			w += 1;
+		}
+	}
+
+	// ---- contacts: the 112 of b2ContactSim's 200 bytes that prepare reads (src/contact_solver.c:1629-1785)
+	{
+		float4* wire = base + s->inWire;
+		int flat = ( begin > bodyCount ? begin : bodyCount ) - bodyCount;
+		int flatEnd = ( end - bodyCount < s->contactTotal ? end - bodyCount : s->contactTotal );
+		int k = flat < flatEnd ? b2gFindSegment( s->contactStart, flat ) : 0;
+		while ( flat < flatEnd )
+		{
+			const b2gContactSeg& seg = s->contactSegs[k];
+			int segFlat = s->contactStart[k];
+			int local = flat - segFlat;
+			int localEnd = ( flatEnd < s->contactStart[k + 1] ? flatEnd : s->contactStart[k + 1] ) - segFlat;
+			int bodyBase = s->bodySegs[seg.world].base;
+			for ( int i = local; i < localEnd; ++i )
+			{
+				const uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
+				const uint8_t* m = sim + B2L_CONTACT_MANIFOLD;
+				const uint8_t* p0 = m + B2L_MANIFOLD_POINTS;
+				const uint8_t* p1 = p0 + B2L_MP_SIZE;
+				int pointCount = b2gRdI( m, B2L_MANIFOLD_POINT_COUNT );
+				int hitEnable = ( (uint32_t)b2gRdI( sim, B2L_CONTACT_SIM_FLAGS ) & B2L_SIM_ENABLE_HIT_EVENT ) != 0 ? b2g::kMetaHitEnable : 0;
+				int meta = ( seg.colorIndex << b2g::kMetaColorShift ) | hitEnable | ( pointCount & b2g::kMetaPointMask );
+				int indexA = b2gRdI( sim, B2L_CONTACT_INDEX_A ), indexB = b2gRdI( sim, B2L_CONTACT_INDEX_B );
+				indexA = indexA >= 0 ? indexA + bodyBase : indexA;
+				indexB = indexB >= 0 ? indexB + bodyBase : indexB;
+				float4* w = wire + (size_t)( seg.slotStart + i ) * b2g::WR_COUNT;
+				b2gStream4( w + b2g::WR_HEAD, b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta ),
+							b2gRdF( m, B2L_MANIFOLD_ROLLING_IMPULSE ) );
+				b2gStream4( w + b2g::WR_MASS, b2gRdF( sim, B2L_CONTACT_INV_MASS_A ), b2gRdF( sim, B2L_CONTACT_INV_I_A ),
+							b2gRdF( sim, B2L_CONTACT_INV_MASS_B ), b2gRdF( sim, B2L_CONTACT_INV_I_B ) );
+				b2gStream4( w + b2g::WR_NORMAL, b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ),
+							b2gRdF( sim, B2L_CONTACT_FRICTION ), b2gRdF( sim, B2L_CONTACT_TANGENT_SPEED ) );
+				b2gStream4( w + b2g::WR_MATERIAL, b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ), b2gRdF( sim, B2L_CONTACT_RESTITUTION ),
+							b2gRdF( p0, B2L_MP_SEPARATION ), b2gRdF( p1, B2L_MP_SEPARATION ) );
+				b2gStream4( w + b2g::WR_ANCHOR1, b2gRdF( p0, B2L_MP_ANCHOR_A ), b2gRdF( p0, B2L_MP_ANCHOR_A + 4 ),
+							b2gRdF( p0, B2L_MP_ANCHOR_B ), b2gRdF( p0, B2L_MP_ANCHOR_B + 4 ) );
+				b2gStream4( w + b2g::WR_ANCHOR2, b2gRdF( p1, B2L_MP_ANCHOR_A ), b2gRdF( p1, B2L_MP_ANCHOR_A + 4 ),
+							b2gRdF( p1, B2L_MP_ANCHOR_B ), b2gRdF( p1, B2L_MP_ANCHOR_B + 4 ) );
+				b2gStream4( w + b2g::WR_IMPULSE, b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ),
+							b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ) );
+			}
+			if ( localEnd == seg.count )
+			{
+				// dead slots between this segment and the next (segments start on multiples of 4 slots): a zero head
+				// (pointCount 0) is all the kernels look at
+				int segEnd = seg.slotStart + seg.count;
+				int next = (size_t)k + 1 < s->contactSegs.size() ? s->contactSegs[(size_t)k + 1].slotStart : segEnd;
+				int limit = ( segEnd + 3 ) & ~3;
+				next = next < limit ? next : limit;
+				for ( int dead = segEnd; dead < next; ++dead )
+				{
+					_mm_stream_ps( reinterpret_cast<float*>( wire + (size_t)dead * b2g::WR_COUNT + b2g::WR_HEAD ), _mm_setzero_ps() );
+				}
+			}
+			flat = s->contactStart[k + 1];
+			k += 1;
+		}
+	}
+
+	// ---- joints: the prepared b2JointSim padded to 256 bytes; bodies renumbered to the batch, and the world's base in
+	// the joint-event bit set stored in the padding (read by jointEventTest)
+	{
+		float4* wireJoints = base + s->inJoints;
+		int first = bodyCount + s->contactTotal;
+		int flat = ( begin > first ? begin : first ) - first;
+		int flatEnd = end - first;
+		int k = flat < flatEnd ? b2gFindSegment( s->jointStart, flat ) : 0;
+		while ( flat < flatEnd )
+		{
+			const b2gJointSeg& seg = s->jointSegs[k];
+			int local = flat - s->jointStart[k];
+			int localEnd = ( flatEnd < s->jointStart[k + 1] ? flatEnd : s->jointStart[k + 1] ) - s->jointStart[k];
+			const b2gBodySeg& world = s->bodySegs[seg.world];
+			for ( int i = local; i < localEnd; ++i )
+			{
+				alignas( 16 ) uint8_t padded[b2g::kJointStride] = { 0 };
+				memcpy( padded, seg.sims + (size_t)i * B2L_JOINT_SIZE, B2L_JOINT_SIZE );
+				if ( world.base != 0 )
+				{
+					int* pair = b2gJointIndexPair( reinterpret_cast<b2lJointSim*>( padded ) );
+					if ( pair != nullptr )
+					{
+						pair[0] = pair[0] >= 0 ? pair[0] + world.base : pair[0];
+						pair[1] = pair[1] >= 0 ? pair[1] + world.base : pair[1];
+					}
+				}
+				memcpy( padded + B2L_JOINT_SIZE, &world.jointBitBase, 4 );
+				b2gStreamCopy( wireJoints + (size_t)( seg.jointStart + i ) * ( b2g::kJointStride / 16 ), padded, b2g::kJointStride / 16 );
+			}
+			flat = s->jointStart[k + 1];
+			k += 1;
+		}
+	}
+	_mm_sfence();
+}
+
+// ---- phase 3: H2D + kernels + D2H, all asynchronous on the solver's stream -------------------------------------------
+// quads of the input arena that hold items [0, itemEnd) (bodies, then contacts in slot order, then joints)
+// The pack pass claims blocks in ARENA order: first the blocks of the constraints (items [bodyCount, itemCount)), then
+// the blocks of the bodies (items [0, bodyCount)).
+static void b2gPackBlockRange( const b2GpuSolver* s, int block, int* begin, int* end )
+{
+	int bodyCount = s->params.bodyCount;
+	int restItems = s->workItems - bodyCount;
+	int restBlocks = ( restItems + kWorkBlockItems - 1 ) / kWorkBlockItems;
+	if ( block < restBlocks )
+	{
+		*begin = bodyCount + block * kWorkBlockItems;
+		*end = *begin + kWorkBlockItems < s->workItems ? *begin + kWorkBlockItems : s->workItems;
+	}
+	else
+	{
+		*begin = ( block - restBlocks ) * kWorkBlockItems;
+		*end = *begin + kWorkBlockItems < bodyCount ? *begin + kWorkBlockItems : bodyCount;
+	}
+}
+
+// quads of the input arena that are complete once the first `blocksDone` blocks (in claim order) are packed
+static size_t b2gPackedPrefix( const b2GpuSolver* s, int blocksDone )
+{
+	int restItems = s->contactTotal + s->jointTotal;
+	int restBlocks = ( restItems + kWorkBlockItems - 1 ) / kWorkBlockItems;
+	if ( blocksDone >= s->workBlocks )
+	{
+		return s->inTotal;
+	}
+	if ( blocksDone >= restBlocks )
+	{
+		return s->inStates; // the three body regions are interleaved by region, not by body: wait for all bodies
+	}
+	int flat = blocksDone * kWorkBlockItems; // constraints [0, flat) are packed, flat < restItems
+	if ( flat < s->contactTotal )
+	{
+		int k = b2gFindSegment( s->contactStart, flat );
+		int slot = s->contactSegs[k].slotStart + ( flat - s->contactStart[k] );
+		return s->inWire + (size_t)slot * b2g::WR_COUNT;
+	}
+	return s->inJoints + (size_t)( flat - s->contactTotal ) * ( b2g::kJointStride / 16 );
+}
+
+int b2gSendArena( b2GpuSolver* s, size_t uptoQuads )
+{
+	if ( s->sentQuads == 0 )
+	{
+		B2G_CUDA( cudaEventRecord( s->evUpload, s->stream ) );
+	}
+	if ( uptoQuads > s->sentQuads )
+	{
+		if ( s->trace )
+		{
+			s->traceSends.emplace_back( std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(), uptoQuads );
+		}
+		B2G_CUDA( cudaMemcpyAsync( s->wireAll.ptr + s->sentQuads, s->hWire.ptr + s->sentQuads,
+								   ( uptoQuads - s->sentQuads ) * sizeof( float4 ), cudaMemcpyHostToDevice, s->stream ) );
+		s->sentQuads = uptoQuads;
+	}
+	return 0;
+}
+
+// ---- phase 4: unpack (callable concurrently on disjoint ranges) ---------------------------------------------------------
+// Evict a consumed part of the D2H staging buffer from the CPU caches.  On the target hosts a DMA write into lines
+// that are still cached by several cores runs at ~7 GB/s instead of ~54 GB/s (tools/microbench/d2h_bench.cu); flushing
+// right after the unpack pass keeps the next step's download at full speed for ~0.03 ms of host work.
+#if defined( __x86_64__ )
+static bool b2gHasClflushopt()
+{
+	static int cached = -1;
+	if ( cached < 0 )
+	{
+		unsigned a = 0, b = 0, c = 0, d = 0;
+		cached = ( __get_cpuid_count( 7, 0, &a, &b, &c, &d ) != 0 && ( b & ( 1u << 23 ) ) != 0 ) ? 1 : 0;
+	}
+	return cached == 1;
+}
+
+__attribute__( ( target( "clflushopt" ) ) ) static void b2gFlushOpt( const char* p, const char* end )
+{
+	for ( ; p < end; p += 64 )
+	{
+		_mm_clflushopt( const_cast<char*>( p ) );
+	}
+}
+
+void b2gFlushLines( const void* ptr, size_t bytes )
+{
+	if ( bytes == 0 )
+	{
+		return;
+	}
+	const char* p = reinterpret_cast<const char*>( reinterpret_cast<uintptr_t>( ptr ) & ~uintptr_t( 63 ) );
+	const char* end = static_cast<const char*>( ptr ) + bytes;
+	if ( b2gHasClflushopt() )
+	{
+		b2gFlushOpt( p, end );
+	}
+	else
+	{
+		for ( ; p < end; p += 64 )
+		{
+			_mm_clflush( p );
+		}
+	}
+}
+#else
+void b2gFlushLines( const void*, size_t )
+{
+}
+#endif
+
+// Scatter the packed impulse records into the reference's manifolds: what b2StoreImpulsesTask
+// (src/contact_solver.c:2293-2320) and b2StoreImpulses_Overflow (:526-542) write.
+extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
+{
+	if ( begin >= end )
+	{
+		return;
+	}
+	int bodyCount = s->params.bodyCount;
+	const float4* base = s->hOut.ptr;
+
+	// ---- body states
+	{
+		const float4* outStates = base + s->outStates;
+		int i = begin;
+		int bodyEnd = end < bodyCount ? end : bodyCount;
+		int w = i < bodyEnd ? b2gFindSegment( s->bodyStart, i ) : 0;
+		while ( i < bodyEnd )
+		{
+			const b2gBodySeg& seg = s->bodySegs[w];
+			int segEnd = seg.base + seg.count < bodyEnd ? seg.base + seg.count : bodyEnd;
+			if ( i < segEnd )
+			{
+				memcpy( seg.states + (size_t)( i - seg.base ) * B2L_STATE_SIZE, outStates + 2 * (size_t)i, (size_t)( segEnd - i ) * B2L_STATE_SIZE );
+				b2gFlushLines( outStates + 2 * (size_t)i, (size_t)( segEnd - i ) * B2L_STATE_SIZE );
+				i = segEnd;
+			}
+			w += 1;
+		}
+	}
+
+	// ---- contact impulses
+	{
+		const float* allRecords = reinterpret_cast<const float*>( base + s->outImpulses );
+		int flat = ( begin > bodyCount ? begin : bodyCount ) - bodyCount;
+		int flatEnd = ( end - bodyCount < s->contactTotal ? end - bodyCount : s->contactTotal );
+		int k = flat < flatEnd ? b2gFindSegment( s->contactStart, flat ) : 0;
+		while ( flat < flatEnd )
+		{
+			const b2gContactSeg& seg = s->contactSegs[k];
+			b2GpuStepResult* result = s->results != nullptr ? s->results + seg.world : nullptr;
+			uint64_t* hitBits = result != nullptr ? result->hitEventBits : nullptr;
+			int local = flat - s->contactStart[k];
+			int localEnd = ( flatEnd < s->contactStart[k + 1] ? flatEnd : s->contactStart[k + 1] ) - s->contactStart[k];
+			const float* records = allRecords + (size_t)seg.slotStart * b2g::kImpulseFloats;
+			for ( int i = local; i < localEnd; ++i )
+			{
+				uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
+				uint8_t* manifold = sim + B2L_CONTACT_MANIFOLD;
+				const float* rec = records + (size_t)i * b2g::kImpulseFloats;
+				int pointCount = seg.wide ? 2 : b2gRdI( manifold, B2L_MANIFOLD_POINT_COUNT );
+				memcpy( manifold + B2L_MANIFOLD_ROLLING_IMPULSE, rec + 0, 4 );
+				for ( int j = 0; j < pointCount; ++j )
+				{
+					uint8_t* mp = manifold + B2L_MANIFOLD_POINTS + j * B2L_MP_SIZE;
+					// normalImpulse, tangentImpulse, totalNormalImpulse, normalVelocity are contiguous (collision.h:549-561)
+					memcpy( mp + B2L_MP_NORMAL_IMPULSE, rec + 1 + 4 * j, 16 );
+				}
+				if ( rec[9] != 0.0f && result != nullptr )
+				{
+					if ( hitBits != nullptr )
+					{
+						uint32_t id = (uint32_t)b2gRdI( sim, B2L_CONTACT_ID );
+						__atomic_fetch_or( hitBits + ( id >> 6 ), (uint64_t)1 << ( id & 63u ), __ATOMIC_RELAXED );
+					}
+					__atomic_store_n( &result->hasHitEvents, 1, __ATOMIC_RELAXED );
+				}
+			}
+			if ( local < localEnd )
+			{
+				b2gFlushLines( records + (size_t)local * b2g::kImpulseFloats, (size_t)( localEnd - local ) * b2g::kImpulseFloats * sizeof( float ) );
+			}
+			flat = s->contactStart[k + 1];
+			k += 1;
+		}
+	}
+
+	// ---- joints: the fields the stages wrote (b2lJointMutableRuns) go back into the reference's b2JointSim in place
+	{
+		const float* outJoints = reinterpret_cast<const float*>( base + s->outJoints );
+		int first = bodyCount + s->contactTotal;
+		int flat = ( begin > first ? begin : first ) - first;
+		int flatEnd = end - first;
+		int k = flat < flatEnd ? b2gFindSegment( s->jointStart, flat ) : 0;
+		while ( flat < flatEnd )
+		{
+			const b2gJointSeg& seg = s->jointSegs[k];
+			int local = flat - s->jointStart[k];
+			int localEnd = ( flatEnd < s->jointStart[k + 1] ? flatEnd : s->jointStart[k + 1] ) - s->jointStart[k];
+			for ( int i = local; i < localEnd; ++i )
+			{
+				uint8_t* sim = seg.sims + (size_t)i * B2L_JOINT_SIZE;
+				const float* record = outJoints + (size_t)( seg.jointStart + i ) * B2L_JOINT_OUT_FLOATS;
+				int offsets[2], floats[2];
+				int runs = b2lJointMutableRuns( b2gRdI( sim, offsetof( b2lJointSim, type ) ), offsets, floats );
+				for ( int r = 0; r < runs; ++r )
+				{
+					memcpy( sim + offsets[r], record, (size_t)floats[r] * sizeof( float ) );
+					record += floats[r];
+				}
+			}
+			if ( local < localEnd )
+			{
+				b2gFlushLines( outJoints + (size_t)( seg.jointStart + local ) * B2L_JOINT_OUT_FLOATS,
+							   (size_t)( localEnd - local ) * B2L_JOINT_OUT_FLOATS * sizeof( float ) );
+			}
+			flat = s->jointStart[k + 1];
+			k += 1;
+		}
+	}
+}
+
+// ---- pipelined host passes ------------------------------------------------------------------------------------------------
+// b2GpuSolverPackWork / b2GpuSolverUnpackWork are called by ANY number of host threads at the same time (the world's
+// workers); each call claims blocks of items until none are left.  Exactly one caller passes pump = 1: besides packing
+// it starts the upload of every finished prefix of the arena (PCIe runs behind the packing instead of after it), and
+// besides unpacking it watches the download events and tells the others how much of the output has arrived (unpacking
+// runs behind the download).
+static int b2gPumpUploads( b2GpuSolver* s, bool everything )
+{
+	while ( s->pumpPrefix < s->workBlocks && s->workDone[s->pumpPrefix].load( std::memory_order_acquire ) != 0 )
+	{
+		s->pumpPrefix += 1;
+	}
+	bool complete = s->pumpPrefix == s->workBlocks;
+	size_t ready = b2gPackedPrefix( s, s->pumpPrefix );
+	if ( ready > s->sentQuads && ( ( complete && everything ) || ready - s->sentQuads >= kTransferQuads ) )
+	{
+		return b2gSendArena( s, ready );
+	}
+	return 0;
+}
+
+extern "C" int b2GpuSolverPackWork( b2GpuSolver* s, int pump )
+{
+	if ( s == nullptr || !s->begun )
+	{
+		return b2gFailMsg( "b2GpuSolverPackWork: no step begun" );
+	}
+	if ( pump != 0 )
+	{
+		cudaSetDevice( s->device );
+	}
+	for ( ;; )
+	{
+		if ( pump != 0 && b2gPumpUploads( s, false ) != 0 )
+		{
+			s->workFailed.store( 1 );
+			return 1;
+		}
+		int block = s->workNext.fetch_add( 1, std::memory_order_acq_rel );
+		if ( block >= s->workBlocks )
+		{
+			break;
+		}
+		int begin, end;
+		b2gPackBlockRange( s, block, &begin, &end );
+		b2GpuSolverPackRange( s, begin, end ); // ends with an sfence: the streaming stores are visible to the DMA engine
+		s->workDone[block].store( 1, std::memory_order_release );
+	}
+	if ( pump != 0 )
+	{
+		// the others may still be packing the blocks they claimed
+		while ( s->pumpPrefix < s->workBlocks )
+		{
+			if ( b2gPumpUploads( s, false ) != 0 )
+			{
+				return 1;
+			}
+			_mm_pause();
+		}
+		return b2gPumpUploads( s, true );
+	}
+	return 0;
+}
+
+// quads of the output arena that must have arrived before items [0, itemEnd) can be unpacked
+static size_t b2gOutPrefix( const b2GpuSolver* s, int itemEnd )
+{
+	int bodyCount = s->params.bodyCount;
+	if ( itemEnd <= bodyCount )
+	{
+		return s->outStates + 2 * (size_t)itemEnd;
+	}
+	int flat = itemEnd - bodyCount;
+	if ( flat <= s->contactTotal )
+	{
+		// the record of the last contact of the range
+		int k = b2gFindSegment( s->contactStart, flat - 1 );
+		int slot = s->contactSegs[k].slotStart + ( flat - 1 - s->contactStart[k] );
+		return s->outImpulses + ( (size_t)( slot + 1 ) * b2g::kImpulseFloats + 3 ) / 4;
+	}
+	int joints = flat - s->contactTotal;
+	joints = joints < s->jointTotal ? joints : s->jointTotal;
+	return s->outJoints + (size_t)joints * ( B2L_JOINT_OUT_FLOATS / 4 );
+}
+
+static int b2gPumpDownloads( b2GpuSolver* s )
+{
+	if ( !s->controlSeen )
+	{
+		// kernels done?  (the control block is the first thing that comes back)
+		cudaError_t err = cudaEventQuery( s->evControl );
+		if ( err == cudaErrorNotReady )
+		{
+			return 0;
+		}
+		if ( err != cudaSuccess )
+		{
+			return b2gFail( "device solve", err );
+		}
+		if ( s->ran && s->islandMode && s->hControl->islandFailed != 0 )
+		{
+			// rare: rerun on the grid-barrier kernel; that re-enqueues the downloads and waits for them
+			B2G_CUDA( cudaStreamSynchronize( s->stream ) );
+			if ( b2gRerunIfIslandsFailed( s, true ) != 0 )
+			{
+				return 1;
+			}
+			s->chunkNext = s->chunkCount;
+			s->arrivedQuads.store( s->outTotal, std::memory_order_release );
+		}
+		s->controlSeen = true;
+		s->tWaited = std::chrono::steady_clock::now();
+		s->traceControl = std::chrono::duration<float, std::micro>( s->tWaited - s->tBegin ).count();
+	}
+	while ( s->chunkNext < s->chunkCount )
+	{
+		cudaError_t err = cudaEventQuery( s->chunkEvents[(size_t)s->chunkNext] );
+		if ( err == cudaErrorNotReady )
+		{
+			break;
+		}
+		if ( err != cudaSuccess )
+		{
+			return b2gFail( "download", err );
+		}
+		s->arrivedQuads.store( s->chunkEnd[(size_t)s->chunkNext], std::memory_order_release );
+		if ( s->trace )
+		{
+			s->traceArrivals.emplace_back( std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(),
+										   s->chunkEnd[(size_t)s->chunkNext] );
+		}
+		s->chunkNext += 1;
+	}
+	return 0;
+}
+
+extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
+{
+	if ( s == nullptr || !s->begun )
+	{
+		return b2gFailMsg( "b2GpuSolverUnpackWork: no step begun" );
+	}
+	if ( pump != 0 )
+	{
+		cudaSetDevice( s->device );
+	}
+	for ( ;; )
+	{
+		int block = s->workNext.fetch_add( 1, std::memory_order_acq_rel );
+		if ( block >= s->workBlocks )
+		{
+			break;
+		}
+		int begin = block * kWorkBlockItems;
+		int end = begin + kWorkBlockItems < s->workItems ? begin + kWorkBlockItems : s->workItems;
+		size_t need = b2gOutPrefix( s, end );
+		while ( s->arrivedQuads.load( std::memory_order_acquire ) < need )
+		{
+			if ( pump != 0 )
+			{
+				if ( b2gPumpDownloads( s ) != 0 )
+				{
+					s->workFailed.store( 1 );
+					return 1;
+				}
+			}
+			else if ( s->workFailed.load( std::memory_order_relaxed ) != 0 )
+			{
+				return 1;
+			}
+			_mm_pause();
+		}
+		b2GpuSolverUnpackRange( s, begin, end );
+	}
+	if ( pump != 0 )
+	{
+		// the tail of the arena (joint event bits) is consumed by EndStep
+		while ( !s->controlSeen || s->chunkNext < s->chunkCount )
+		{
+			if ( b2gPumpDownloads( s ) != 0 )
+			{
+				s->workFailed.store( 1 );
+				return 1;
+			}
+			_mm_pause();
+		}
+		if ( s->ran )
+		{
+			B2G_CUDA( cudaEventElapsedTime( &s->lastKernelMs, s->evStart, s->evStop ) );
+		}
+	}
+	return 0;
+}
+
