@@ -44,6 +44,9 @@ import box2d_b200 as b2  # noqa: E402
 
 SCENES = ("many_pyramids", "large_pyramid", "joint_grid", "rain", "tumbler", "small_pyramid")
 SLEEPING_SCENES = ("rain", "tumbler")  # the awake set changes at the end of a step: no re-run of a captured step
+# scenes that need time to reach their steady state (rain: ~10 300 bodies in ragdolls on the ground; tumbler: everything in
+# one island): extra untimed steps before the warm-up, on both arms
+SETTLE_STEPS = {"rain": 400, "tumbler": 130}
 METRIC = "solver_body_steps_per_sec"
 UNIT = "body-steps/s"
 BATCH_WORLDS = 8192
@@ -144,7 +147,7 @@ def cpu_solver_run(scene: str, workers: int, warmup: int, steps: int) -> dict:
 	"""Time the reference's CPU solver: sum of b2Profile.constraints over `steps` world steps after `warmup`."""
 	lib = load_reference()
 	with b2.World(lib, scene, workers) as w:
-		w.step(warmup)
+		w.step(SETTLE_STEPS.get(scene, 0) + warmup)
 		bodies = w.counters()["awakeBodyCount"]
 		r = w.bench(steps)
 		c = w.counters()
@@ -217,7 +220,7 @@ def run_reference_arm(args) -> int:
 		"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
 		"warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
 		"dtype": "f32", "data": "synthetic",
-		"config": {"workload": args.workload, "bodies": best["bodies"], "contacts": best["contacts"], "joints": best["joints"],
+		"config": {"workload": args.workload, "settle_steps": SETTLE_STEPS.get(args.workload, 0), "bodies": best["bodies"], "contacts": best["contacts"], "joints": best["joints"],
 				   "substeps": 4, "dt": 1.0 / 60.0, "timed": "sum of b2Profile.constraints (reference src/solver.c:1561,1615)"},
 		"cpu_baseline": {"value": value, "unit": UNIT, "cores": best["workers"], "kind": "reference",
 						 "sample": f"{args.steps} steps of {args.workload} after {args.warmup} warm-up steps; best of worker counts "
@@ -277,7 +280,7 @@ def run_scene(args) -> int:
 	workers = min(os.cpu_count() or 1, 16)  # host phases of the GPU arm (collide, pack/unpack, finalize)
 	scene = args.workload
 	with b2.World(host, scene, workers) as world:
-		world.step(args.warmup)
+		world.step(SETTLE_STEPS.get(scene, 0) + args.warmup)
 		widx = world.world_index()
 		counters = world.counters()
 		bodies = counters["awakeBodyCount"]
@@ -360,7 +363,7 @@ def run_scene(args) -> int:
 			"metric": METRIC, "value": total_work / kernel_s, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
 			"warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
 			"vs_baseline": None, "dtype": "f32", "data": "synthetic",
-			"config": {"workload": scene, "bodies": bodies, "contacts": contacts, "joints": joints, "substeps": substeps,
+			"config": {"workload": scene, "settle_steps": SETTLE_STEPS.get(scene, 0), "bodies": bodies, "contacts": contacts, "joints": joints, "substeps": substeps,
 					   "dt": 1.0 / 60.0, "colors": sum(1 for c in counters["colorCounts"][:23] if c > 0),
 					   "parallelism": f"{world_size} independent world(s), one per GPU",
 					   "l2": "flushed (256 MiB write) between timed iterations" if resident else
