@@ -277,7 +277,8 @@ def run_scene(args) -> int:
 		torch.cuda.synchronize()
 
 	sampler = ClockSampler(local_rank)
-	workers = min(os.cpu_count() or 1, 16)  # host phases of the GPU arm (collide, pack/unpack, finalize)
+	# host phases of the GPU arm (collide, pack/unpack, finalize): the ranks of one box share its cores
+	workers = max(1, min((os.cpu_count() or 1) // max(1, world_size), 16))
 	scene = args.workload
 	with b2.World(host, scene, workers) as world:
 		world.step(SETTLE_STEPS.get(scene, 0) + args.warmup)
@@ -365,7 +366,7 @@ def run_scene(args) -> int:
 			"vs_baseline": None, "dtype": "f32", "data": "synthetic",
 			"config": {"workload": scene, "settle_steps": SETTLE_STEPS.get(scene, 0), "bodies": bodies, "contacts": contacts, "joints": joints, "substeps": substeps,
 					   "dt": 1.0 / 60.0, "colors": sum(1 for c in counters["colorCounts"][:23] if c > 0),
-					   "parallelism": f"{world_size} independent world(s), one per GPU",
+					   "parallelism": f"{world_size} independent world(s), one per GPU", "host_workers_per_world": workers,
 					   "l2": "flushed (256 MiB write) between timed iterations" if resident else
 							 "not flushed: kernels timed inside the real steps (awake set changes every step)",
 					   "timed": "CUDA events on the solver stream around the step's kernels, inputs resident"},
@@ -433,6 +434,8 @@ def run_batch(args) -> int:
 
 	world_size, rank, local_rank = _setup_distributed()
 	distributed = world_size > 1
+	# the library packs / unpacks a batch on its own threads: the ranks of one box share its cores
+	os.environ.setdefault("B2GPU_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world_size))))
 	host = b2.host_lib()
 	begin, end = shard_range(BATCH_WORLDS, rank, world_size)
 	worlds = end - begin
