@@ -316,6 +316,16 @@ static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimi
 		{
 			return false;
 		}
+		// The bins run in waves of one block per SM and a wave takes the same time however full its blocks are (the step
+		// is a chain of latency-bound stages): a few bins more than a whole number of waves cost a whole wave.  Give up
+		// some of the head room if that saves one.
+		int perWave = s->smCount;
+		int waveCount = ( wanted + perWave - 1 ) / perWave;
+		int tight = (int)( totalBytes * 1.05 / (double)budget ) + 1;
+		if ( waveCount > 1 && ( waveCount - 1 ) * perWave >= tight )
+		{
+			wanted = ( waveCount - 1 ) * perWave;
+		}
 		binLimit = wanted < islandCount ? wanted : islandCount;
 	}
 	int target = ( bodies + binLimit - 1 ) / binLimit;
