@@ -143,9 +143,21 @@ def load_reference():
 	return b2._bind_harness(ctypes.CDLL(str(path)))
 
 
-def cpu_solver_run(scene: str, workers: int, warmup: int, steps: int) -> dict:
+def load_reference_avx2():
+	"""The reference built with its optional 8-wide path (BOX2D_AVX2), or None when absent / not supported by this host."""
+	path = ROOT / "oracle" / "_ref" / "libbox2d_ref_avx2.so"
+	try:
+		flags = open("/proc/cpuinfo").read()
+	except OSError:
+		flags = ""
+	if not path.is_file() or " avx2" not in flags:
+		return None
+	return b2._bind_harness(ctypes.CDLL(str(path)))
+
+
+def cpu_solver_run(scene: str, workers: int, warmup: int, steps: int, lib=None) -> dict:
 	"""Time the reference's CPU solver: sum of b2Profile.constraints over `steps` world steps after `warmup`."""
-	lib = load_reference()
+	lib = lib or load_reference()
 	with b2.World(lib, scene, workers) as w:
 		w.step(SETTLE_STEPS.get(scene, 0) + warmup)
 		bodies = w.counters()["awakeBodyCount"]
@@ -167,6 +179,9 @@ def best_cpu_baseline(scene: str, warmup: int, steps: int) -> dict:
 			best = r
 	best["tried_ms_per_step"] = tried
 	best["host_cores"] = cores
+	# second data point: the reference's optional AVX2 build at the best worker count (the default build is SSE2)
+	avx2 = load_reference_avx2()
+	best["avx2_ms_per_step"] = cpu_solver_run(scene, best["workers"], warmup, steps, avx2)["constraints_ms"] / steps if avx2 else None
 	return best
 
 
@@ -225,7 +240,8 @@ def run_reference_arm(args) -> int:
 		"cpu_baseline": {"value": value, "unit": UNIT, "cores": best["workers"], "kind": "reference",
 						 "sample": f"{args.steps} steps of {args.workload} after {args.warmup} warm-up steps; best of worker counts "
 								   f"{sorted(best['tried_ms_per_step'])} on {best['host_cores']} host cores",
-						 "ms_per_step_by_workers": best["tried_ms_per_step"]},
+						 "ms_per_step_by_workers": best["tried_ms_per_step"],
+						 "avx2_build_ms_per_step": best["avx2_ms_per_step"]},
 		"e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
 		"gpu_launches": 0,
 	}
@@ -359,7 +375,8 @@ def run_scene(args) -> int:
 				   "sample": f"{sample_steps} steps of {scene} after {args.warmup} warm-up steps, sum of "
 							 f"b2Profile.constraints; best of worker counts {sorted(b['tried_ms_per_step'])} on "
 							 f"{b['host_cores']} host cores (oracle/_ref = untouched reference, gcc -O3 SSE2)",
-				   "ms_per_step_by_workers": b["tried_ms_per_step"]}
+				   "ms_per_step_by_workers": b["tried_ms_per_step"],
+				   "avx2_build_ms_per_step": b["avx2_ms_per_step"]}
 		line = {
 			"metric": METRIC, "value": total_work / kernel_s, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
 			"warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

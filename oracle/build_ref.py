@@ -2,7 +2,7 @@
 """Recipe for oracle/_ref/: compile the UNTOUCHED reference (where it lies under /root/reference) with gcc into
 shared libraries the tests and bench.py's cpu_baseline / --impl reference arm load.  Test infrastructure only.
 
-    python oracle/build_ref.py            # libbox2d_ref.so, libbox2d_refcap.so (+ liboracle.so, the C restatement)
+    python oracle/build_ref.py            # libbox2d_ref.so, libbox2d_refcap.so, libbox2d_ref_avx2.so (+ liboracle.so)
 """
 import sys
 from pathlib import Path
@@ -16,6 +16,7 @@ def main() -> int:
 	libs = buildlib.build_reference_libs(verbose=True)
 	for name, path in libs.items():
 		print(name, path)
+	print(buildlib.build_reference_avx2(verbose=True))  # second CPU baseline for bench.py (8-wide path)
 	return 0
 
 

@@ -178,6 +178,35 @@ def build_host_lib(verbose: bool = False) -> Path:
 	return target
 
 
+def build_reference_avx2(verbose: bool = False) -> Path:
+	"""oracle/_ref/libbox2d_ref_avx2.so: the untouched reference with its optional 8-wide path (BOX2D_AVX2, -mavx2: reference
+	src/CMakeLists.txt:187-190).  Only a second CPU baseline for bench.py -- not bit-compatible with the default build (the
+	reference documents the wrappers' differences, src/contact_solver.c:641-645) and not used as a checker."""
+	if not reference_available():
+		raise RuntimeError(f"reference sources not found at {REFERENCE}")
+	out = REF_OUT / "obj_avx2"
+	out.mkdir(parents=True, exist_ok=True)
+	flags = [*REF_CFLAGS, "-DBOX2D_AVX2", "-mavx2"]
+	jobs = [(src, out / f"src_{src.stem}.o") for src in sorted((REFERENCE / "src").glob("*.c"))]
+	jobs += [(src, out / f"shared_{src.stem}.o") for src in sorted((REFERENCE / "shared").glob("*.c"))]
+	harness = ROOT / "oracle" / "harness" / "b2h_harness.c"
+	jobs.append((harness, out / "own_b2h_harness.o"))
+
+	def one(job):
+		src, obj = job
+		if _stale(obj, [src]):
+			_run([CC, *flags, *own_includes(), *ref_includes(), "-c", str(src), "-o", str(obj)])
+		return obj
+
+	with ThreadPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
+		objs = list(pool.map(one, jobs))
+	target = REF_OUT / "libbox2d_ref_avx2.so"
+	link_shared(target, objs)
+	if verbose:
+		print(f"built {target}")
+	return target
+
+
 def build_oracle_lib(verbose: bool = False) -> Path:
 	"""oracle/liboracle.so: the plain-C restatement of the solver (checker only, needs nothing from the reference)."""
 	odir = ROOT / "oracle"
