@@ -481,11 +481,13 @@ def run_batch(args) -> int:
 		sync_all()
 		sampler.start()
 		kernel_ms = []
+		torch.cuda.profiler.start()  # lets `ncu --profile-from-start off` skip the thousands of one-world warm-up launches
 		for _ in range(args.steps):
 			flush.zero_()
 			torch.cuda.synchronize()
 			solver.run_batch(r)
 			kernel_ms.append(float(r.kernelMs))
+		torch.cuda.profiler.stop()
 		launches = int(r.kernelLaunches) * args.steps
 		grid_barriers = int(r.gridBarriers)
 		island_plan = list(solver.island_plan())
@@ -526,7 +528,8 @@ def run_batch(args) -> int:
 					"h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "last_step_split": split,
 					"timed": "b2GpuSolverStepBatch wall clock: host packing (library threads) + H2D + kernels + D2H + write-back"},
 			"gpu_launches": launches,
-			"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+			"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+						 "traffic": measured_traffic("batch") if world_size == 1 else None,
 						 "algorithmic_bytes_per_launch": alg, "peak_source": peak_source, "grid_barriers_per_step": grid_barriers,
 						 "island_bins_blocks_per_bin": island_plan},
 			"clocks": clocks,

@@ -15,5 +15,5 @@ timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gI
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gPartitionKernel -c 1 -s 8 -o $O/${R}_partition -f python bench.py --steps 3 --warmup 3 > $O/${R}_ncu_partition.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gClusterIslandKernel -c 1 -s 8 -o $O/${R}_cluster -f python bench.py --workload large_pyramid --steps 3 --warmup 3 > $O/${R}_ncu_cluster.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gStepKernel -c 1 -s 8 -o $O/${R}_grid -f python bench.py --workload joint_grid --steps 3 --warmup 3 > $O/${R}_ncu_grid.log 2>&1
-timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gIslandKernel -c 1 -s 4 -o $O/${R}_island_batch -f python bench.py --workload batch --steps 2 --warmup 3 > $O/${R}_ncu_island_batch.log 2>&1
+timeout 300 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:b2gIslandKernel -c 1 -o $O/${R}_island_batch -f python bench.py --workload batch --steps 2 --warmup 3 > $O/${R}_ncu_island_batch.log 2>&1
 ls -la $O | tail -30
