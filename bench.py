@@ -424,6 +424,7 @@ def build_batch(host, worlds: int, warmup: int):
 		states = grab(desc.states, n * b2.STATE_SIZE)
 		sims = grab(desc.sims, n * b2.SIM_SIZE)
 		labels = np.ctypeslib.as_array(ctypes.cast(desc.bodyIsland, ctypes.POINTER(ctypes.c_int)), shape=(n,)).copy()
+		sizes = grab(desc.islandSizes, desc.islandCount * ctypes.sizeof(b2.IslandSize)) if desc.islandSizes else None
 		colors = [(grab(desc.colors[c].contactSims, desc.colors[c].contactCount * b2.CONTACT_SIZE), desc.colors[c].contactCount)
 				  for c in range(desc.activeColorCount)]
 		template = b2.StepDesc.from_buffer_copy(bytes(desc))
@@ -437,10 +438,12 @@ def build_batch(host, worlds: int, warmup: int):
 		st, sm, lb = states.copy(), sims.copy(), labels.copy()
 		cs = [a.copy() for a, _ in colors]
 		d.states, d.sims, d.bodyIsland = st.ctypes.data, sm.ctypes.data, lb.ctypes.data
+		d.islandSizes = sizes.ctypes.data if sizes is not None else None  # read-only, shared by the copies
 		for c, arr in enumerate(cs):
 			d.colors[c].contactSims = arr.ctypes.data
 		ctypes.memmove(ctypes.byref(descs[i]), ctypes.byref(d), ctypes.sizeof(b2.StepDesc))
 		keep.append((st, sm, lb, cs))
+	descs._island_sizes = sizes  # keep-alive
 	pristine = (states, [a for a, _ in colors])
 	return descs, results, keep, pristine, n, contacts, int(template.subStepCount)
 

@@ -63,7 +63,12 @@ class StepDesc(ctypes.Structure):
 		("overflow", ColorDesc),
 		("contactIdCapacity", ctypes.c_int), ("jointIdCapacity", ctypes.c_int),
 		("bodyIsland", ctypes.c_void_p), ("islandCount", ctypes.c_int), ("reserved0", ctypes.c_int),
+		("islandSizes", ctypes.c_void_p),
 	]
+
+
+class IslandSize(ctypes.Structure):
+	_fields_ = [("bodyCount", ctypes.c_int), ("contactCount", ctypes.c_int), ("jointCount", ctypes.c_int), ("reserved", ctypes.c_int)]
 
 
 class StepResult(ctypes.Structure):
@@ -164,6 +169,8 @@ def solver_lib() -> ctypes.CDLL:
 	lib.b2GpuSolverPackWork.argtypes = [ctypes.c_void_p, ctypes.c_int]
 	lib.b2GpuSolverUnpackWork.restype = ctypes.c_int
 	lib.b2GpuSolverUnpackWork.argtypes = [ctypes.c_void_p, ctypes.c_int]
+	lib.b2GpuCountIslandSizes.restype = ctypes.c_int
+	lib.b2GpuCountIslandSizes.argtypes = [P(StepDesc), P(IslandSize)]
 	lib.b2GpuSolverGetIslandPlan.restype = ctypes.c_int
 	lib.b2GpuSolverGetIslandPlan.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
 	_solver_lib = lib
@@ -305,9 +312,10 @@ class Capture:
 		if raw[:8] != b"B2CAP003":
 			raise ValueError(f"{path}: not a B2CAP003 capture")
 		desc_bytes = int.from_bytes(raw[8:12], "little")
-		if desc_bytes != ctypes.sizeof(StepDesc):
-			raise ValueError(f"{path}: descriptor size {desc_bytes} != {ctypes.sizeof(StepDesc)}")
-		self.desc = StepDesc.from_buffer_copy(raw[12:12 + desc_bytes])
+		# the descriptor only ever grows at its end (optional hints, NULL = absent): older captures are zero-extended
+		if desc_bytes > ctypes.sizeof(StepDesc) or desc_bytes < StepDesc.islandSizes.offset:
+			raise ValueError(f"{path}: descriptor size {desc_bytes}, expected {ctypes.sizeof(StepDesc)}")
+		self.desc = StepDesc.from_buffer_copy(raw[12:12 + desc_bytes].ljust(ctypes.sizeof(StepDesc), b"\0"))
 		self._pos = 12 + desc_bytes
 		self._raw = raw
 		d = self.desc
@@ -351,9 +359,10 @@ class Capture:
 	def joint_count(self) -> int:
 		return sum(j for _, j in self.color_counts)
 
-	def make_call(self, islands: bool = True):
+	def make_call(self, islands: bool = True, sizes: bool = False):
 		"""Fresh, writable copies of the inputs wired into a StepDesc + StepResult (the arrays must outlive the call).
-		islands=False drops the island hint: the step is then solved by the grid-barrier kernel."""
+		islands=False drops the island hint: the step is then solved by the grid-barrier kernel.  sizes=True adds the
+		optional b2GpuStepDesc::islandSizes (bins packed by their real size)."""
 		d = StepDesc.from_buffer_copy(bytes(self.desc))
 		bufs = {
 			"states": self.states_in.copy(),
@@ -378,19 +387,25 @@ class Capture:
 		r = StepResult()
 		r.hitEventBits = bufs["hit"].ctypes.data
 		r.jointEventBits = bufs["joint"].ctypes.data
+		if sizes and d.bodyIsland and d.islandCount > 0:
+			# what the seam reads off b2Island (src/island.h:64-73), recounted from the labels by the library's host utility
+			bufs["sizes"] = (IslandSize * d.islandCount)()
+			if solver_lib().b2GpuCountIslandSizes(ctypes.byref(d), bufs["sizes"]) != 0:
+				raise RuntimeError("b2GpuCountIslandSizes failed")
+			d.islandSizes = ctypes.addressof(bufs["sizes"])
 		return d, r, bufs
 
 
 # byte ranges of b2ContactSim that the solver writes (include/b2gpu_layout.h): manifold.rollingImpulse and, per
 # point, normalImpulse, tangentImpulse, totalNormalImpulse, normalVelocity
-def make_batch(captures, islands: bool = True):
+def make_batch(captures, islands: bool = True, sizes: bool = False):
 	"""Wire a list of captures into contiguous (StepDesc * n), (StepResult * n) arrays + the buffers that back them."""
 	n = len(captures)
 	descs = (StepDesc * n)()
 	results = (StepResult * n)()
 	keep = []
 	for i, cap in enumerate(captures):
-		d, r, bufs = cap.make_call(islands=islands)
+		d, r, bufs = cap.make_call(islands=islands, sizes=sizes)
 		ctypes.memmove(ctypes.byref(descs[i]), ctypes.byref(d), ctypes.sizeof(StepDesc))
 		ctypes.memmove(ctypes.byref(results[i]), ctypes.byref(r), ctypes.sizeof(StepResult))
 		keep.append(bufs)

@@ -128,6 +128,7 @@ struct b2gBodySeg
 	uint8_t* states;
 	const uint8_t* sims;
 	const int* islands;
+	const b2GpuIslandSize* islandSizes; // optional
 	int islandCount;
 	int islandBase; // first island of this world in the batch-wide numbering
 	int count;
@@ -185,7 +186,12 @@ struct b2GpuSolver
 	bool countersClean = false; // the bin counters are all zero (the island kernels zero what they have read)
 	DeviceBuffer<int2> contactBinRank, jointBinRank;
 	std::vector<int> islandBin;	 // host: bin of every awake island
-	std::vector<int> islandBodies; // host: bodies per island, then per bin
+	std::vector<int> islandBodies; // host: bodies per island
+	std::vector<int> islandContacts, islandJoints; // host: with exact island sizes (b2GpuStepDesc::islandSizes)
+	bool islandSizesExact = false;
+	double exactHeadRoom = 1.05; // like islandHeadRoom, for bins packed by their real size
+	double binSqueeze = 1.0;	 // extra bins (factor) the last plan needed before its fullest bin fit, see b2gPlanBins
+	int binSqueezeAge = 0;
 	size_t binCounterCount = 0;
 	size_t islandSmemBytes = 0;
 	size_t islandSmemBudget = 0;
@@ -223,7 +229,7 @@ struct b2GpuSolver
 	std::vector<b2gContactSeg> contactSegs;
 	std::vector<b2gJointSeg> jointSegs;
 	std::vector<int> bodyStart, contactStart, jointStart; // item prefix sums, one more entry than segments
-	std::vector<int> binBodies;
+	std::vector<int> binBodies, binContacts, binJoints;
 	b2g::StepParams params;
 	int jointTotal = 0;
 	int contactTotal = 0;

@@ -297,18 +297,44 @@ struct b2gBinPlan
 // Bins for blocks-per-bin = share.  Island i goes to the bin its first body falls in when the islands are laid end to
 // end and cut every `target` bodies, so a bin gets between target - (largest island) and target + (largest island)
 // bodies.  `waves`: more bins than `binLimit` are allowed when the data does not fit (they run in waves).
-static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimitIn, bool waves, bool spillJoints, b2gBinPlan* plan )
+static bool b2gPlanBinsOnce( b2GpuSolver* s, int islandCount, int share, int binLimitIn, bool waves, bool spillJoints, double squeeze,
+							  b2gBinPlan* plan, bool* hopeless = nullptr )
 {
 	const b2g::StepParams& P = s->params;
 	const int bodies = P.bodyCount;
 	size_t budget = s->islandSmemBudget;
 	const double bytesPerBody = 52.0, bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0;
 	const double bytesPerJoint = ( spillJoints ? 0.0 : (double)b2g::kJointStride ) + 4.0;
-	double totalBytes = bodies * bytesPerBody + s->contactTotal * bytesPerContact + s->jointTotal * bytesPerJoint;
+	const bool exact = s->islandSizesExact;
+	// bytes of shared memory an island needs: from its real size, or -- no sizes given -- from its bodies and the step's
+	// average constraint density
+	const double densityC = bodies > 0 ? (double)s->contactTotal / bodies : 0.0, densityJ = bodies > 0 ? (double)s->jointTotal / bodies : 0.0;
+	auto islandBytes = [&]( int i ) -> double {
+		double nb = s->islandBodies[(size_t)i];
+		double nc = exact ? (double)s->islandContacts[(size_t)i] : nb * densityC;
+		double nj = exact ? (double)s->islandJoints[(size_t)i] : nb * densityJ;
+		return nb * bytesPerBody + nc * bytesPerContact + nj * bytesPerJoint;
+	};
+	double totalBytes = 0.0, largest = 0.0;
+	for ( int i = 0; i < islandCount; ++i )
+	{
+		double bytes = islandBytes( i );
+		totalBytes += bytes;
+		largest = bytes > largest ? bytes : largest;
+	}
+	if ( largest > (double)budget * share )
+	{
+		// an island that is too big for a bin whatever the number of bins
+		if ( hopeless != nullptr )
+		{
+			*hopeless = true;
+		}
+		return false;
+	}
 	int binLimit = binLimitIn < islandCount ? binLimitIn : islandCount;
-	// head room for uneven constraint density between bins (adaptive: raised when a bin did not fit, lowered slowly while
-	// all is well); a cluster exists for the few largest islands, deal exactly
-	double headRoom = share > 1 ? 1.1 : s->islandHeadRoom;
+	// head room between the average bin and the capacity (adaptive: raised when a bin did not fit, lowered slowly while
+	// all is well): generous when the constraint density of the islands is only an estimate, small when the sizes are real
+	double headRoom = ( exact ? s->exactHeadRoom : ( share > 1 ? 1.1 : s->islandHeadRoom ) ) * squeeze;
 	int wanted = (int)( totalBytes * headRoom / ( (double)budget * share ) ) + 1;
 	if ( wanted > binLimit )
 	{
@@ -321,29 +347,39 @@ static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimi
 		// some of the head room if that saves one.
 		int perWave = s->smCount;
 		int waveCount = ( wanted + perWave - 1 ) / perWave;
-		int tight = (int)( totalBytes * 1.05 / (double)budget ) + 1;
+		int tight = (int)( totalBytes * ( exact ? 1.02 : 1.05 ) * squeeze / (double)budget ) + 1;
 		if ( waveCount > 1 && ( waveCount - 1 ) * perWave >= tight )
 		{
 			wanted = ( waveCount - 1 ) * perWave;
 		}
 		binLimit = wanted < islandCount ? wanted : islandCount;
 	}
-	int target = ( bodies + binLimit - 1 ) / binLimit;
+	// islands laid end to end and cut every `target` bytes
+	double target = totalBytes / binLimit;
+	target = target > 1.0 ? target : 1.0;
 	s->islandBin.assign( (size_t)islandCount, 0 );
 	std::vector<int>& binBodies = s->binBodies;
 	binBodies.assign( (size_t)binLimit, 0 );
-	int bin = 0, maxBin = 0;
-	long long before = 0;
+	s->binContacts.assign( (size_t)binLimit, 0 );
+	s->binJoints.assign( (size_t)binLimit, 0 );
+	int bin = 0, maxBin = 0, maxBinContacts = 0, maxBinJoints = 0;
+	double before = 0.0;
 	for ( int i = 0; i < islandCount; ++i )
 	{
-		int n = s->islandBodies[i];
 		int b = (int)( before / target );
 		b = b < binLimit ? b : binLimit - 1;
 		s->islandBin[i] = b;
-		binBodies[b] += n;
+		binBodies[b] += s->islandBodies[i];
 		maxBin = binBodies[b] > maxBin ? binBodies[b] : maxBin;
+		if ( exact )
+		{
+			s->binContacts[b] += s->islandContacts[i];
+			s->binJoints[b] += s->islandJoints[i];
+			maxBinContacts = s->binContacts[b] > maxBinContacts ? s->binContacts[b] : maxBinContacts;
+			maxBinJoints = s->binJoints[b] > maxBinJoints ? s->binJoints[b] : maxBinJoints;
+		}
 		bin = b > bin ? b : bin;
-		before += n;
+		before += islandBytes( i );
 	}
 	int binCount = bin + 1;
 
@@ -364,12 +400,15 @@ static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimi
 	double fraction = (double)maxBin / (double)bodies / (double)share;
 	// a block of a cluster holds ceil(n / share) of every colour, the first block the bin's overflow colour on top
 	double slack = share > 1 ? (double)( b2g::kMaxColors + 1 ) : 0.0;
-	double needC = fraction * s->contactTotal + slack + ( share > 1 ? (double)s->overflowContacts : 0.0 );
-	double needJ = fraction * s->jointTotal + ( s->jointTotal > 0 ? slack : 0.0 ) + ( share > 1 ? (double)s->overflowJoints : 0.0 );
+	double binC = exact ? (double)maxBinContacts / share : fraction * s->contactTotal;
+	double binJ = exact ? (double)maxBinJoints / share : fraction * s->jointTotal;
+	double needC = binC + slack + ( share > 1 ? (double)s->overflowContacts : 0.0 );
+	double needJ = binJ + ( s->jointTotal > 0 ? slack : 0.0 ) + ( share > 1 ? (double)s->overflowJoints : 0.0 );
 	needC = needC < (double)s->contactTotal ? needC : (double)s->contactTotal;
 	needJ = needJ < (double)s->jointTotal ? needJ : (double)s->jointTotal;
 	size_t fixed = b2g::islandSharedBytes( capB, 0, 0, !spillJoints );
-	if ( fixed + (size_t)( needC * 1.1 * bytesPerContact + needJ * 1.1 * bytesPerJoint ) + 4096 > budget )
+	const double margin = exact ? 1.02 : 1.1;
+	if ( fixed + (size_t)( needC * margin * bytesPerContact + needJ * margin * bytesPerJoint ) + 4096 > budget )
 	{
 		return false;
 	}
@@ -403,6 +442,40 @@ static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimi
 	return true;
 }
 
+// A cut every `target` bytes can leave a bin one island above the average; when the bins run in waves (a batch of worlds:
+// islands that are a sizeable fraction of a block) the fullest bin may then miss the budget by a little.  More bins cure
+// that: retry with a few per cent more until the plan fits.
+static bool b2gPlanBins( b2GpuSolver* s, int islandCount, int share, int binLimitIn, bool waves, bool spillJoints, b2gBinPlan* plan )
+{
+	if ( !waves )
+	{
+		return b2gPlanBinsOnce( s, islandCount, share, binLimitIn, false, spillJoints, 1.0, plan );
+	}
+	// start from what worked last step; now and then try one notch less
+	s->binSqueezeAge += 1;
+	if ( s->binSqueezeAge >= 64 )
+	{
+		s->binSqueezeAge = 0;
+		s->binSqueeze = s->binSqueeze / 1.01 > 1.0 ? s->binSqueeze / 1.01 : 1.0;
+	}
+	double squeeze = s->binSqueeze;
+	for ( int attempt = 0; attempt < 40 && squeeze < 1.5; ++attempt )
+	{
+		bool hopeless = false;
+		if ( b2gPlanBinsOnce( s, islandCount, share, binLimitIn, true, spillJoints, squeeze, plan, &hopeless ) )
+		{
+			s->binSqueeze = squeeze;
+			return true;
+		}
+		if ( hopeless )
+		{
+			return false;
+		}
+		squeeze *= 1.01;
+	}
+	return false;
+}
+
 // ---- island mode planning (host) --------------------------------------------------------------------------------
 // Pack the awake islands of all worlds into bins balanced by body count and size the island kernel's shared memory
 // carve-up.  Island mode is used when every world brings the hint and the estimated bins fit; the device double-checks
@@ -429,8 +502,37 @@ static int b2gPlanIslands( b2GpuSolver* s )
 		islandCount += seg.islandCount;
 	}
 	s->islandBodies.assign( (size_t)islandCount, 0 );
+	s->islandSizesExact = true;
 	for ( const b2gBodySeg& seg : s->bodySegs )
 	{
+		s->islandSizesExact = s->islandSizesExact && seg.islandSizes != nullptr;
+	}
+	if ( s->islandSizesExact )
+	{
+		// the caller knows its islands (the seam reads b2Island::bodies/contacts/joints.count): nothing to count here
+		s->islandContacts.assign( (size_t)islandCount, 0 );
+		s->islandJoints.assign( (size_t)islandCount, 0 );
+		for ( const b2gBodySeg& seg : s->bodySegs )
+		{
+			for ( int i = 0; i < seg.islandCount; ++i )
+			{
+				const b2GpuIslandSize& size = seg.islandSizes[i];
+				if ( size.bodyCount < 0 || size.contactCount < 0 || size.jointCount < 0 )
+				{
+					return 0;
+				}
+				s->islandBodies[(size_t)( seg.islandBase + i )] = size.bodyCount;
+				s->islandContacts[(size_t)( seg.islandBase + i )] = size.contactCount;
+				s->islandJoints[(size_t)( seg.islandBase + i )] = size.jointCount;
+			}
+		}
+	}
+	for ( const b2gBodySeg& seg : s->bodySegs )
+	{
+		if ( s->islandSizesExact )
+		{
+			break;
+		}
 		if ( seg.islandCount == 1 )
 		{
 			// a world that is one island (the worlds of a batch usually are): nothing to count, nothing to look up
@@ -454,9 +556,10 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	{
 		s->headRoomCooldown -= 1;
 	}
-	else if ( s->islandHeadRoom > 1.2 )
+	else
 	{
 		s->islandHeadRoom = s->islandHeadRoom * 0.995 > 1.2 ? s->islandHeadRoom * 0.995 : 1.2;
+		s->exactHeadRoom = s->exactHeadRoom * 0.998 > 1.05 ? s->exactHeadRoom * 0.998 : 1.05;
 	}
 	b2gBinPlan plan;
 	const bool residentFirst = !( s->spillJointsForced && s->jointTotal > 0 );
@@ -659,6 +762,7 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 		seg.states = static_cast<uint8_t*>( dw.states );
 		seg.sims = static_cast<const uint8_t*>( dw.sims );
 		seg.islands = dw.bodyIsland;
+		seg.islandSizes = dw.islandSizes;
 		seg.islandCount = dw.islandCount;
 		seg.islandBase = 0;
 		seg.count = dw.awakeBodyCount;
@@ -978,6 +1082,11 @@ int b2gRerunIfIslandsFailed( b2GpuSolver* s, bool download )
 	if ( s->params.ownerLists != 0 )
 	{
 		s->ownerListsOff = 512; // a block's share did not fit: deal the colours out evenly for a while
+	}
+	else if ( s->islandSizesExact )
+	{
+		s->exactHeadRoom = s->exactHeadRoom * 1.15 < 3.0 ? s->exactHeadRoom * 1.15 : 3.0;
+		s->headRoomCooldown = 512;
 	}
 	else
 	{

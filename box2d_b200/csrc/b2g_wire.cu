@@ -100,7 +100,11 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 				int local = i - seg.base;
 				if ( s->islandMode )
 				{
-					_mm_stream_si32( wireBins + i, s->islandBin[seg.islandBase + ( seg.islandCount == 1 ? 0 : seg.islands[local] )] );
+					// a label out of range (a body without an island has no constraints) goes to the world's first island:
+					// harmless for the result, and if it overfills a bin the device notices (binFail)
+					int label = seg.islandCount == 1 ? 0 : seg.islands[local];
+					label = label >= 0 && label < seg.islandCount ? label : 0;
+					_mm_stream_si32( wireBins + i, s->islandBin[seg.islandBase + label] );
 				}
 				b2gStreamCopy( wireStates + 2 * (size_t)i, seg.states + (size_t)local * B2L_STATE_SIZE, 2 );
 				const uint8_t* sim = seg.sims + (size_t)local * B2L_SIM_SIZE;
@@ -628,3 +632,51 @@ extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 	return 0;
 }
 
+
+// ---- host utility: island sizes from labels ---------------------------------------------------------------------------------
+extern "C" int b2GpuCountIslandSizes( const b2GpuStepDesc* d, b2GpuIslandSize* sizes )
+{
+	if ( d == nullptr || sizes == nullptr || d->bodyIsland == nullptr || d->islandCount <= 0 )
+	{
+		return b2gFailMsg( "b2GpuCountIslandSizes: no island labels" );
+	}
+	memset( sizes, 0, (size_t)d->islandCount * sizeof( b2GpuIslandSize ) );
+	auto islandOf = [&]( int body ) -> int {
+		int label = body >= 0 && body < d->awakeBodyCount ? d->bodyIsland[body] : -1;
+		return label >= 0 && label < d->islandCount ? label : -1;
+	};
+	for ( int i = 0; i < d->awakeBodyCount; ++i )
+	{
+		int island = islandOf( i );
+		if ( island >= 0 )
+		{
+			sizes[island].bodyCount += 1;
+		}
+	}
+	for ( int c = 0; c <= d->activeColorCount; ++c )
+	{
+		const b2GpuColorDesc& color = c < d->activeColorCount ? d->colors[c] : d->overflow;
+		const uint8_t* contacts = static_cast<const uint8_t*>( color.contactSims );
+		for ( int i = 0; i < color.contactCount; ++i )
+		{
+			const uint8_t* sim = contacts + (size_t)i * B2L_CONTACT_SIZE;
+			int a = b2gRdI( sim, B2L_CONTACT_INDEX_A ), b = b2gRdI( sim, B2L_CONTACT_INDEX_B );
+			int island = islandOf( a >= 0 ? a : b );
+			if ( island >= 0 )
+			{
+				sizes[island].contactCount += 1;
+			}
+		}
+		uint8_t* joints = static_cast<uint8_t*>( color.jointSims );
+		for ( int i = 0; i < color.jointCount; ++i )
+		{
+			const int* pair = b2gJointIndexPair( reinterpret_cast<b2lJointSim*>( joints + (size_t)i * B2L_JOINT_SIZE ) );
+			int island = pair != nullptr ? islandOf( pair[0] >= 0 ? pair[0] : pair[1] ) : -1;
+			if ( island >= 0 )
+			{
+				sizes[island].jointCount += 1;
+			}
+		}
+	}
+	return 0;
+}

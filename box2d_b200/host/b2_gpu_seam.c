@@ -14,6 +14,7 @@
 #include "parallel_for.h"
 #include "physics_world.h"
 #include "solver.h"
+#include "solver_set.h"
 
 #include "box2d/base.h"
 #include "box2d/constants.h"
@@ -29,6 +30,8 @@ typedef struct b2SeamSlot
 	b2GpuSolver* solver;
 	int* islandLabels;
 	int islandLabelCapacity;
+	b2GpuIslandSize* islandSizes;
+	int islandSizeCapacity;
 	b2GpuSeamTotals totals;
 	b2GpuStepResult lastResult;
 	b2GpuStepDesc lastDesc;
@@ -91,6 +94,9 @@ void b2GpuSeam_Shutdown( void )
 			free( s_slots[i].islandLabels );
 			s_slots[i].islandLabels = NULL;
 			s_slots[i].islandLabelCapacity = 0;
+			free( s_slots[i].islandSizes );
+			s_slots[i].islandSizes = NULL;
+			s_slots[i].islandSizeCapacity = 0;
 		}
 	}
 }
@@ -193,7 +199,14 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 		slot->islandLabelCapacity = desc->awakeBodyCount + desc->awakeBodyCount / 2 + 64;
 		slot->islandLabels = malloc( (size_t)slot->islandLabelCapacity * sizeof( int ) );
 	}
-	b2GpuSeam_FillIslands( world, desc, slot->islandLabels, true );
+	b2SolverSet* awakeSet = world->solverSets.data + b2_awakeSet;
+	if ( slot->islandSizeCapacity < awakeSet->islandSims.count )
+	{
+		free( slot->islandSizes );
+		slot->islandSizeCapacity = awakeSet->islandSims.count + awakeSet->islandSims.count / 2 + 64;
+		slot->islandSizes = malloc( (size_t)slot->islandSizeCapacity * sizeof( b2GpuIslandSize ) );
+	}
+	b2GpuSeam_FillIslands( world, desc, slot->islandLabels, slot->islandSizes, true );
 
 	b2GpuStepResult* result = &slot->lastResult;
 	memset( result, 0, sizeof( *result ) );

@@ -25,9 +25,10 @@ extern "C"
  * prepared (b2PrepareJoint, src/joint.c:1406).  Shared by the product seam and the oracle's capture hook. */
 void b2GpuSeam_BuildDesc( b2World* world, b2StepContext* stepContext, b2GpuStepDesc* desc );
 
-/* Fill the optional island hint of the descriptor: labels[i] = index of awake body i's island among the awake islands.
- * `labels` must hold awakeBodyCount ints and stay valid for the duration of the solver call. */
-void b2GpuSeam_FillIslands( b2World* world, b2GpuStepDesc* desc, int* labels, bool parallel );
+/* Fill the optional island hint of the descriptor: labels[i] = index of awake body i's island among the awake islands,
+ * sizes[k] = bodies / touching contacts / joints of awake island k (may be NULL).  `labels` must hold awakeBodyCount
+ * ints, `sizes` one entry per awake island; both must stay valid for the duration of the solver call. */
+void b2GpuSeam_FillIslands( b2World* world, b2GpuStepDesc* desc, int* labels, b2GpuIslandSize* sizes, bool parallel );
 
 /* Prepare every awake joint on the host (b2ParallelFor over the flat joint range + the overflow colour),
  * i.e. the b2_stagePrepareJoints stage and b2PrepareJoints_Overflow (src/solver.c:1060-1077). */

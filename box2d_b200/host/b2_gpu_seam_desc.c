@@ -307,9 +307,24 @@ static void b2SeamIslandLabelsTask( int startIndex, int endIndex, int workerInde
 	}
 }
 
-void b2GpuSeam_FillIslands( b2World* world, b2GpuStepDesc* desc, int* labels, bool parallel )
+void b2GpuSeam_FillIslands( b2World* world, b2GpuStepDesc* desc, int* labels, b2GpuIslandSize* sizes, bool parallel )
 {
 	b2SolverSet* awakeSet = world->solverSets.data + b2_awakeSet;
+	if ( sizes != NULL )
+	{
+		// what the reference already keeps per island (src/island.h:64-73): its bodies, its touching contacts, its joints
+		const b2Island* islands = world->islands.data;
+		int islandCount = awakeSet->islandSims.count;
+		for ( int i = 0; i < islandCount; ++i )
+		{
+			const b2Island* island = islands + awakeSet->islandSims.data[i].islandId;
+			sizes[i].bodyCount = island->bodies.count;
+			sizes[i].contactCount = island->contacts.count;
+			sizes[i].jointCount = island->joints.count;
+			sizes[i].reserved = 0;
+		}
+	}
+	desc->islandSizes = sizes;
 	b2SeamIslandTask task = { world, awakeSet->bodySims.data, labels };
 	int count = awakeSet->bodySims.count;
 	if ( parallel )

@@ -63,6 +63,15 @@ typedef struct b2GpuColorDesc
 	int reserved;
 } b2GpuColorDesc;
 
+/* size of one awake island, see b2GpuStepDesc::islandSizes */
+typedef struct b2GpuIslandSize
+{
+	int bodyCount;
+	int contactCount; /* touching contacts of the island, incl. those with static bodies */
+	int jointCount;
+	int reserved;
+} b2GpuIslandSize;
+
 /* Everything b2SolverTask reads from b2StepContext (src/solver.h:155-237) and b2World
  * (src/physics_world.h:162-216). */
 typedef struct b2GpuStepDesc
@@ -111,6 +120,12 @@ typedef struct b2GpuStepDesc
 	const int* bodyIsland;
 	int islandCount;
 	int reserved0;
+
+	/* Optional, with bodyIsland: how big every island is (b2Island::bodies / contacts / joints .count, src/island.h:64-73).
+	 * With it the bins are packed by their real size instead of an estimate from the body counts, and nothing has to be
+	 * counted on the step's critical path.  Counts may be slightly off (they are only used for sizing; the device checks).
+	 * NULL = the library counts the bodies per island itself and estimates the rest. */
+	const struct b2GpuIslandSize* islandSizes;
 } b2GpuStepDesc;
 
 /* Index of each per-stage timer, same split as b2Profile (include/box2d/types.h:526-551) filled by the
@@ -226,6 +241,9 @@ B2GPU_API uint64_t b2GpuSolverGetLaunchCount( const b2GpuSolver* solver );
 /* How the last step was laid out for the island-local kernels: number of bins (0 = the step was planned for the
  * grid-barrier kernel) and thread blocks per bin (1, or the cluster size 2..16).  Returns binCount. */
 B2GPU_API int b2GpuSolverGetIslandPlan( const b2GpuSolver* solver, int* binCount, int* blocksPerBin );
+/* Host utility for callers that have island labels but no island bookkeeping: fill sizes[desc->islandCount] from
+ * desc->bodyIsland and the constraint arrays (one pass over the constraints).  Returns 0 on success. */
+B2GPU_API int b2GpuCountIslandSizes( const b2GpuStepDesc* desc, b2GpuIslandSize* sizes );
 
 #ifdef __cplusplus
 }

@@ -71,7 +71,7 @@ void b2OracleHook_BeforeSolve( b2World* world, b2StepContext* context )
 	b2GpuStepDesc* desc = &s_capture.desc;
 	b2GpuSeam_BuildDesc( world, context, desc );
 	int* labels = malloc( (size_t)( desc->awakeBodyCount + 1 ) * sizeof( int ) );
-	b2GpuSeam_FillIslands( world, desc, labels, false );
+	b2GpuSeam_FillIslands( world, desc, labels, NULL, false );
 
 	uint32_t descBytes = (uint32_t)sizeof( b2GpuStepDesc );
 	b2hWrite( "B2CAP003", 8 );
@@ -82,6 +82,7 @@ void b2OracleHook_BeforeSolve( b2World* world, b2StepContext* context )
 	b2hWrite( labels, (size_t)desc->awakeBodyCount * sizeof( int ) );
 	free( labels );
 	desc->bodyIsland = NULL;
+	desc->islandSizes = NULL;
 
 	for ( int c = 0; c <= desc->activeColorCount; ++c )
 	{

@@ -79,3 +79,23 @@ def test_pinned_allocator_round_trip():
 	again = lib.b2GpuHostAlloc(200, 32)
 	assert again in [p for p, _ in blocks]  # recycled from the free list
 	lib.b2GpuHostFree(again, 200)
+
+
+def test_island_sizes_from_labels(capture_files):
+	"""b2GpuCountIslandSizes (host utility, no device): every awake body, touching contact and joint is counted once,
+	in the island of its bodies."""
+	import numpy as np
+
+	for path in capture_files:
+		cap = b2.Capture(path)
+		d, _, bufs = cap.make_call(sizes=True)
+		if "sizes" not in bufs:
+			continue
+		sizes = np.frombuffer(bufs["sizes"], dtype=np.int32).reshape(-1, 4)
+		labels = cap.island_labels
+		valid = (labels >= 0) & (labels < d.islandCount)
+		assert np.array_equal(sizes[:, 0], np.bincount(labels[valid], minlength=d.islandCount))
+		assert sizes[:, 1].sum() <= cap.contact_count and sizes[:, 2].sum() <= cap.joint_count
+		if valid.all():
+			assert sizes[:, 1].sum() == cap.contact_count
+		assert (sizes[:, 3] == 0).all()

@@ -47,6 +47,19 @@ def test_batch_split_phase_and_many_worlds():
 		_check(caps[i], bufs[i], results[i])
 
 
+def test_many_worlds_with_island_sizes_run_in_waves():
+	"""Islands that are a sizeable fraction of a block, more bins than SMs: the planner packs by the real sizes and still
+	has to find a bin count whose fullest bin fits (b2gPlanBins retries with more bins)."""
+	caps = [b2.Capture(b2.ROOT / "tests" / "golden" / "small_pyramid_030.b2cap.gz")] * 2500
+	descs, results, bufs = b2.make_batch(caps, sizes=True)
+	with b2.GpuSolver() as solver:
+		solver.step_batch(descs, results)
+		bins, blocks = solver.island_plan()
+		assert results[0].gridBarriers == 0 and bins > 148 and blocks == 1, "the island kernel should have solved the batch in waves"
+	for i in (0, 1, 1250, 2498, 2499):
+		_check(caps[i], bufs[i], results[i])
+
+
 def test_batch_rejects_mixed_step_parameters():
 	caps = [b2.Capture(b2.ROOT / "tests" / "golden" / "small_pyramid_030.b2cap.gz"),
 			b2.Capture(b2.ROOT / "tests" / "golden" / "pyramid_cold_003.b2cap.gz")]  # warm starting off

@@ -56,6 +56,19 @@ def test_captured_steps_bit_exact(solver, capture_files, mode, islands):
 		assert island_steps == 0
 
 
+def test_captured_steps_bit_exact_with_island_sizes(solver, capture_files):
+	"""b2GpuStepDesc::islandSizes: the bins are packed by the islands' real sizes instead of an estimate."""
+	solver.set_mode(0)
+	island_steps = 0
+	for path in capture_files:
+		cap = b2.Capture(path)
+		desc, result, bufs = cap.make_call(sizes=True)
+		solver.step(desc, result)
+		_check(cap, bufs, result)
+		island_steps += 1 if result.gridBarriers == 0 and (cap.contact_count + cap.joint_count) > 0 else 0
+	assert island_steps > 0, "the island-local kernel never ran"
+
+
 @pytest.mark.parametrize("blocks", [2, 4, 16])
 def test_captured_steps_bit_exact_on_clusters(capture_files, blocks, monkeypatch):
 	"""Force the planner to share every bin between `blocks` thread blocks of a cluster (bodies in distributed shared
