@@ -183,6 +183,7 @@ struct b2GpuSolver
 	int countersBinCount = 0, countersListCount = 0;
 	int ownerListsOff = 0;		 // steps during which owner lists stay off after a block's share did not fit
 	bool ownerListsEnabled = true; // B2GPU_OWNER_LISTS=0 turns them off
+	bool flatListsEnabled = true;  // B2GPU_FLAT_LISTS=0: two-phase partition kernel for one block per bin too
 	bool countersClean = false; // the bin counters are all zero (the island kernels zero what they have read)
 	DeviceBuffer<int2> contactBinRank, jointBinRank;
 	std::vector<int> islandBin;	 // host: bin of every awake island

@@ -279,6 +279,109 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 	} );
 }
 
+// ---- partition, one block per bin: single pass ------------------------------------------------------------------------------
+// With one thread block per bin the colour-major order of a bin's lists need not be built here: every body and every
+// constraint is appended to its bin's list in ONE flat pass (a warp-aggregated atomic on the bin's counter), tagged with
+// its colour, and the island kernel sorts its own few hundred entries by colour in shared memory.  No grid barrier, no
+// second pass over the constraints, no cooperative launch.  The counters of bin b: binBodyCount[b], contacts
+// binColorStart[b * kColorSlots + {0: all, 1: overflow colour}], joints binJointStart[...] likewise.
+constexpr int kFlatColorShift = 8;	// binContactInfo.w = SIMD-group bits | colour slot << 8
+constexpr int kFlatJointShift = 26; // binJointList entry = joint index | colour slot << 26
+
+__global__ void __launch_bounds__( 256 ) b2gScatterKernel( const __grid_constant__ StepParams P )
+{
+	const unsigned lane = threadIdx.x & 31u;
+	forEachItem( P.jointWords, [&]( int i ) {
+		if ( i < P.jointWords )
+		{
+			P.jointBits[i] = 0u;
+		}
+	} );
+	forEachItem( P.bodyCount, [&]( int b ) {
+		bool active = b < P.bodyCount;
+		int bin = active ? P.bodyBin[b] : -1;
+		int local = aggregatedAdd( P.binBodyCount, bin, active );
+		if ( active )
+		{
+			if ( local < P.binCapBodies )
+			{
+				P.binBodyList[(size_t)bin * P.binCapBodies + local] = b;
+			}
+			else
+			{
+				*P.binFail = 1;
+			}
+			P.bodyLocal[b] = local + 1;
+		}
+	} );
+	forEachItem( P.contactSlots, [&]( int slot ) {
+		int c = 0;
+		while ( c < P.colorCount && ( c + 1 < P.colorCount ? P.colors[c + 1].contactStart : P.overflow.contactStart ) <= slot )
+		{
+			c += 1;
+		}
+		bool isOverflow = c == P.colorCount;
+		ColorRange color = isOverflow ? P.overflow : P.colors[c];
+		bool inRange = slot < color.contactStart + color.contactCount;
+		float4 head = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+		if ( inRange )
+		{
+			head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+		}
+		// dead slots (padding between the segments of a batch) have pointCount 0 and are not placed in any bin
+		bool active = inRange && ( __float_as_int( head.z ) & kMetaPointMask ) != 0;
+		int bits = simdGroupBits( P, slot, active && !isOverflow, lane );
+		int indexA = __float_as_int( head.x ), indexB = __float_as_int( head.y );
+		int bin = active ? P.bodyBin[indexA >= 0 ? indexA : indexB] : -1;
+		int position = aggregatedAdd( P.binColorStart, bin * kColorSlots, active );
+		if ( active )
+		{
+			if ( position < P.binCapContacts )
+			{
+				P.binContactInfo[(size_t)bin * P.binCapContacts + position] = make_int4( slot, indexA, indexB, bits | ( c << kFlatColorShift ) );
+			}
+			else
+			{
+				*P.binFail = 1;
+			}
+			if ( isOverflow && atomicAdd( P.binColorStart + (size_t)bin * kColorSlots + 1, 1 ) >= kMaxBinOverflow )
+			{
+				*P.binFail = 1;
+			}
+		}
+	} );
+	forEachItem( P.jointCount, [&]( int j ) {
+		bool active = j < P.jointCount;
+		int bin = -1, c = 0;
+		if ( active )
+		{
+			while ( c < P.colorCount && ( c + 1 < P.colorCount ? P.colors[c + 1].jointStart : P.overflow.jointStart ) <= j )
+			{
+				c += 1;
+			}
+			int body = jointBodyForBin( P.rawJoints + (size_t)j * kJointStride );
+			// a filter joint has no solver data: park it in bin 0, it is a no-op in every stage
+			bin = body < 0 ? 0 : P.bodyBin[body];
+		}
+		int position = aggregatedAdd( P.binJointStart, bin * kColorSlots, active );
+		if ( active )
+		{
+			if ( position < P.binCapJoints )
+			{
+				P.binJointList[(size_t)bin * P.binCapJoints + position] = j | ( c << kFlatJointShift );
+			}
+			else
+			{
+				*P.binFail = 1;
+			}
+			if ( c == P.colorCount && atomicAdd( P.binJointStart + (size_t)bin * kColorSlots + 1, 1 ) >= kMaxBinOverflow )
+			{
+				*P.binFail = 1;
+			}
+		}
+	} );
+}
+
 // ---- the overflow colour of a bin, levelised ------------------------------------------------------------------------------
 // The reference solves the overflow colour one constraint after the other (joints, then contacts, in array order:
 // src/solver.c:1100-1101, src/joint.c:1576-1591, src/contact_solver.c:216-340).  Two constraints only interact through
@@ -511,6 +614,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	__shared__ int colorStartJ[kColorSlots];
 	__shared__ int anyRestitution;
 	__shared__ int overflowOrder[kMaxBinOverflow]; // scratch for ordering the bin's overflow constraints
+	__shared__ int overflowOrderJ[kMaxBinOverflow]; // flat lists: the same for its overflow joints
+	__shared__ int flatCursorC[kColorSlots], flatCursorJ[kColorSlots]; // flat lists: entries per colour, then the colours' cursors
+	__shared__ int flatOverflowCount[2];
 	__shared__ OverflowSchedule overflow;
 	// the colours that are present in this bin, in order: { jointBegin, jointEnd, contactBegin, contactEnd }
 	__shared__ __align__( 16 ) int4 passRange[kMaxColors];
@@ -557,7 +663,48 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	clk.start();
 	long long begin = clk.last;
 
-	if ( threadIdx.x < kColorSlots )
+	// Flat lists (b2gScatterKernel): the bin's constraints arrive in arrival order, tagged with their colour; a counting
+	// sort in shared memory puts them colour-major -- pass 1 counts (while the bodies are on their way), one thread turns
+	// the counts into offsets, pass 2 hands out the slots.  The order inside a colour stays arbitrary (see the file
+	// header); the overflow colour is ranked by wire slot / joint index, i.e. back into array order.
+	const bool flat = P.flatLists != 0;
+	const int4* contactInfo = P.binContactInfo + (size_t)bin * capC;
+	constexpr int kFlatJointMask = ( 1 << kFlatJointShift ) - 1;
+	int flatContacts = 0, flatJoints = 0;
+	if ( flat )
+	{
+		if ( threadIdx.x < kColorSlots )
+		{
+			flatCursorC[threadIdx.x] = 0;
+			flatCursorJ[threadIdx.x] = 0;
+		}
+		if ( threadIdx.x < 2 )
+		{
+			flatOverflowCount[threadIdx.x] = 0;
+		}
+		flatContacts = P.binColorStart[(size_t)bin * kColorSlots];
+		flatJoints = P.binJointStart[(size_t)bin * kColorSlots];
+		__syncthreads();
+		forEachLocal( flatContacts, [&]( int k ) {
+			int4 info = __ldg( contactInfo + k );
+			int c = info.w >> kFlatColorShift;
+			atomicAdd( &flatCursorC[c], 1 );
+			if ( c == P.colorCount )
+			{
+				overflowOrder[atomicAdd( &flatOverflowCount[0], 1 )] = info.x;
+			}
+		} );
+		forEachLocal( flatJoints, [&]( int k ) {
+			int entry = __ldg( jointList + k );
+			int c = entry >> kFlatJointShift;
+			atomicAdd( &flatCursorJ[c], 1 );
+			if ( c == P.colorCount )
+			{
+				overflowOrderJ[atomicAdd( &flatOverflowCount[1], 1 )] = entry & kFlatJointMask;
+			}
+		} );
+	}
+	else if ( threadIdx.x < kColorSlots )
 	{
 		colorStartC[threadIdx.x] = P.binColorOffset[(size_t)bin * kColorSlots + threadIdx.x];
 		colorStartJ[threadIdx.x] = P.binJointOffset[(size_t)bin * kColorSlots + threadIdx.x];
@@ -581,11 +728,23 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		P.binBodyCount[bin] = 0;
 	}
 
-	const int contactCount = colorStartC[kColorSlots - 1];
-	const int jointCount = colorStartJ[kColorSlots - 1];
 	const int colorCount = P.colorCount;
 	if ( threadIdx.x == 0 )
 	{
+		if ( flat )
+		{
+			int contacts = 0, joints = 0;
+			for ( int c = 0; c < kColorSlots; ++c )
+			{
+				int n = flatCursorC[c], m = flatCursorJ[c]; // nothing was counted beyond the overflow bucket
+				colorStartC[c] = contacts;
+				colorStartJ[c] = joints;
+				flatCursorC[c] = contacts;
+				flatCursorJ[c] = joints;
+				contacts += n;
+				joints += m;
+			}
+		}
 		int passes = 0, widest = 32;
 		for ( int c = 0; c < colorCount; ++c )
 		{
@@ -600,6 +759,12 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		passCount = passes;
 		stageThreadCount = widest < (int)blockDim.x && P.stageAllThreads == 0 ? widest : (int)blockDim.x;
 	}
+	if ( flat )
+	{
+		__syncthreads(); // the offsets
+	}
+	const int contactCount = colorStartC[kColorSlots - 1];
+	const int jointCount = colorStartJ[kColorSlots - 1];
 	// the overflow colour's constraints of this bin, solved by one thread in array order
 	const int ovCb = colorStartC[colorCount], ovCe = colorStartC[colorCount + 1];
 	const int ovJb = colorStartJ[colorCount], ovJe = colorStartJ[colorCount + 1];
@@ -611,7 +776,16 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		// returns the element of list[begin, end) whose rank is (k - begin) in ascending order
 		return k < begin || k >= end ? list[k] : overflowOrder[k - begin];
 	};
-	if ( ovCe > ovCb )
+	// rank of `mine` among the n distinct values of `values`
+	auto rankAmong = [&]( const int* values, int n, int mine ) -> int {
+		int rank = 0;
+		for ( int m = 0; m < n; ++m )
+		{
+			rank += values[m] < mine ? 1 : 0;
+		}
+		return rank;
+	};
+	if ( !flat && ovCe > ovCb )
 	{
 		for ( int k = ovCb + (int)threadIdx.x; k < ovCe; k += (int)blockDim.x )
 		{
@@ -623,48 +797,76 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			overflowOrder[rank] = mine;
 		}
 	}
-	__syncthreads();
+	if ( !flat )
+	{
+		__syncthreads();
+	}
 
 	// prepare: contacts read the bodies' initial velocities from the view (identical to the wire states here)
-	const int4* contactInfo = P.binContactInfo + (size_t)bin * capC;
-	forEachLocal( contactCount, [&]( int k ) {
-		bool wide = k < ovCb || k >= ovCe;
-		int slot, localA, localB, groupBits = 0;
-		if ( wide && P.resolveContacts != 0 )
-		{
-			int4 info = contactInfo[k]; // resolved by the partition kernel
-			slot = info.x, localA = info.y, localB = info.z, groupBits = info.w;
-		}
-		else
-		{
-			slot = wide ? contactList[k] : overflowOrder[k - ovCb];
-			groupBits = wide ? P.slotGroupBits[slot] : 0;
-			float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
-			int indexA = __float_as_int( head.x );
-			int indexB = __float_as_int( head.y );
-			localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;
-			localB = indexB >= 0 ? P.bodyLocal[indexB] : 0;
-		}
-		wireSlot[k] = slot;
-		prepareContact( P, V, slot, k, localA, localB, V.vel[localA], V.vel[localB], wide, groupBits );
-	} );
-	__syncthreads();
-	// joints: copy the prepared record into shared memory, renumber its bodies to the bin
-	if ( ovJe > ovJb )
+	if ( flat )
 	{
-		for ( int k = ovJb + (int)threadIdx.x; k < ovJe; k += (int)blockDim.x )
-		{
-			int mine = jointList[k], rank = 0;
-			for ( int m = ovJb; m < ovJe; ++m )
+		forEachLocal( flatContacts, [&]( int k ) {
+			int4 info = __ldg( contactInfo + k );
+			int c = info.w >> kFlatColorShift;
+			bool wide = c != colorCount;
+			int dest = wide ? atomicAdd( &flatCursorC[c], 1 ) : ovCb + rankAmong( overflowOrder, ovCe - ovCb, info.x );
+			int localA = info.y >= 0 ? P.bodyLocal[info.y] : 0;
+			int localB = info.z >= 0 ? P.bodyLocal[info.z] : 0;
+			wireSlot[dest] = info.x;
+			prepareContact( P, V, info.x, dest, localA, localB, V.vel[localA], V.vel[localB], wide,
+							info.w & ( kMetaGroupRolling | kMetaGroupRestitution ) );
+		} );
+		forEachLocal( flatJoints, [&]( int k ) {
+			int entry = __ldg( jointList + k );
+			int c = entry >> kFlatJointShift, j = entry & kFlatJointMask;
+			int dest = c != colorCount ? atomicAdd( &flatCursorJ[c], 1 ) : ovJb + rankAmong( overflowOrderJ, ovJe - ovJb, j );
+			jointIndexOf[dest] = j;
+		} );
+	}
+	else
+	{
+		forEachLocal( contactCount, [&]( int k ) {
+			bool wide = k < ovCb || k >= ovCe;
+			int slot, localA, localB, groupBits = 0;
+			if ( wide && P.resolveContacts != 0 )
 			{
-				rank += jointList[m] < mine ? 1 : 0;
+				int4 info = contactInfo[k]; // resolved by the partition kernel
+				slot = info.x, localA = info.y, localB = info.z, groupBits = info.w;
 			}
-			overflowOrder[rank] = mine;
-		}
+			else
+			{
+				slot = wide ? contactList[k] : overflowOrder[k - ovCb];
+				groupBits = wide ? P.slotGroupBits[slot] : 0;
+				float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+				int indexA = __float_as_int( head.x );
+				int indexB = __float_as_int( head.y );
+				localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;
+				localB = indexB >= 0 ? P.bodyLocal[indexB] : 0;
+			}
+			wireSlot[k] = slot;
+			prepareContact( P, V, slot, k, localA, localB, V.vel[localA], V.vel[localB], wide, groupBits );
+		} );
 	}
 	__syncthreads();
-	forEachLocal( jointCount, [&]( int k ) { jointIndexOf[k] = orderedIndex( jointList, ovJb, ovJe, k ); } );
-	__syncthreads();
+	// joints: copy the prepared record into shared memory, renumber its bodies to the bin
+	if ( !flat )
+	{
+		if ( ovJe > ovJb )
+		{
+			for ( int k = ovJb + (int)threadIdx.x; k < ovJe; k += (int)blockDim.x )
+			{
+				int mine = jointList[k], rank = 0;
+				for ( int m = ovJb; m < ovJe; ++m )
+				{
+					rank += jointList[m] < mine ? 1 : 0;
+				}
+				overflowOrder[rank] = mine;
+			}
+		}
+		__syncthreads();
+		forEachLocal( jointCount, [&]( int k ) { jointIndexOf[k] = orderedIndex( jointList, ovJb, ovJe, k ); } );
+		__syncthreads();
+	}
 	{
 		const int quads = kJointStride / 16;
 		for ( int t = (int)threadIdx.x; t < jointCount * quads; t += (int)blockDim.x )
@@ -714,60 +916,91 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	const int passes = passCount;
 	const int stageThreads = stageThreadCount;
 	auto blockSync = [&]() { asm volatile( "bar.sync 1, %0;" ::"r"( stageThreads ) : "memory" ); };
-	if ( (int)threadIdx.x < stageThreads )
+	// The body stages (two per sub-step) get a thread per body: when that is more than the colour stages need, the extra
+	// warps join for the body stages only and wait at a second named barrier in between.
+	int bodyThreads = roundUp32( bodyCount ) < (int)blockDim.x ? roundUp32( bodyCount ) : (int)blockDim.x;
+	bodyThreads = bodyThreads > stageThreads && P.stageAllThreads == 0 ? bodyThreads : stageThreads;
+	const bool wideBodies = bodyThreads > stageThreads;
+	auto bodySync = [&]() {
+		if ( wideBodies )
+		{
+			asm volatile( "bar.sync 2, %0;" ::"r"( bodyThreads ) : "memory" );
+		}
+		else
+		{
+			blockSync();
+		}
+	};
+	auto joinBodies = [&]() {
+		if ( wideBodies )
+		{
+			asm volatile( "bar.sync 2, %0;" ::"r"( bodyThreads ) : "memory" );
+		}
+	};
+	if ( (int)threadIdx.x < bodyThreads )
 	{
+		const bool stager = (int)threadIdx.x < stageThreads;
 		for ( int subStep = 0; subStep < P.subStepCount; ++subStep )
 		{
-			forEachLocal( bodyCount, stageThreads, [&]( int i ) { integrateVelocities( V, i ); } );
-			blockSync();
+			forEachLocal( bodyCount, bodyThreads, [&]( int i ) { integrateVelocities( V, i ); } );
+			bodySync();
 			clk.lap( b2GpuStage_integrateVelocities );
 
-			overflowLevels(
-				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); },
-				[&]( int k ) { warmStartContactOverflow( V, k ); }, blockSync, stageThreads );
-			for ( int pass = 0; pass < passes; ++pass )
+			if ( stager )
 			{
-				forEachInLocalColor(
-					passRange[pass], stageThreads, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); }, [&]( int k ) { warmStartContact( V, k ); } );
-				blockSync();
-			}
-			clk.lap( b2GpuStage_warmStart );
+				overflowLevels(
+					overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); },
+					[&]( int k ) { warmStartContactOverflow( V, k ); }, blockSync, stageThreads );
+				for ( int pass = 0; pass < passes; ++pass )
+				{
+					forEachInLocalColor(
+						passRange[pass], stageThreads, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); },
+						[&]( int k ) { warmStartContact( V, k ); } );
+					blockSync();
+				}
+				clk.lap( b2GpuStage_warmStart );
 
-			overflowLevels(
-				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), true ); },
-				[&]( int k ) { solveContactOverflow( P, V, k, true ); }, blockSync, stageThreads );
-			for ( int pass = 0; pass < passes; ++pass )
-			{
-				forEachInLocalColor(
-					passRange[pass], stageThreads,
-					[&]( int k ) {
-						b2lJointSim* joint = jointAt( V, k );
-						solveJoint( P, V, joint, true );
-						jointEventTest( P, joint );
-					},
-					[&]( int k ) { solveContact( P, V, k, true ); } );
-				blockSync();
+				overflowLevels(
+					overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), true ); },
+					[&]( int k ) { solveContactOverflow( P, V, k, true ); }, blockSync, stageThreads );
+				for ( int pass = 0; pass < passes; ++pass )
+				{
+					forEachInLocalColor(
+						passRange[pass], stageThreads,
+						[&]( int k ) {
+							b2lJointSim* joint = jointAt( V, k );
+							solveJoint( P, V, joint, true );
+							jointEventTest( P, joint );
+						},
+						[&]( int k ) { solveContact( P, V, k, true ); } );
+					blockSync();
+				}
+				clk.lap( b2GpuStage_solveImpulses );
 			}
-			clk.lap( b2GpuStage_solveImpulses );
+			joinBodies();
 
-			forEachLocal( bodyCount, stageThreads, [&]( int i ) { integratePositions( P, V, i ); } );
-			blockSync();
+			forEachLocal( bodyCount, bodyThreads, [&]( int i ) { integratePositions( P, V, i ); } );
+			bodySync();
 			clk.lap( b2GpuStage_integratePositions );
 
-			overflowLevels(
-				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
-				[&]( int k ) { solveContactOverflow( P, V, k, false ); }, blockSync, stageThreads );
-			for ( int pass = 0; pass < passes; ++pass )
+			if ( stager )
 			{
-				forEachInLocalColor(
-					passRange[pass], stageThreads, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
-					[&]( int k ) { solveContact( P, V, k, false ); } );
-				blockSync();
+				overflowLevels(
+					overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+					[&]( int k ) { solveContactOverflow( P, V, k, false ); }, blockSync, stageThreads );
+				for ( int pass = 0; pass < passes; ++pass )
+				{
+					forEachInLocalColor(
+						passRange[pass], stageThreads, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+						[&]( int k ) { solveContact( P, V, k, false ); } );
+					blockSync();
+				}
+				clk.lap( b2GpuStage_relaxImpulses );
 			}
-			clk.lap( b2GpuStage_relaxImpulses );
+			joinBodies();
 		}
 
-		if ( anyRestitution != 0 )
+		if ( stager && anyRestitution != 0 )
 		{
 			if ( ovCe > ovCb )
 			{

@@ -147,6 +147,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		s->spillJointsForced = spillEnv != nullptr && atoi( spillEnv ) == 2;
 		const char* ownerEnv = getenv( "B2GPU_OWNER_LISTS" );
 		s->ownerListsEnabled = ownerEnv == nullptr || atoi( ownerEnv ) != 0;
+		const char* flatEnv = getenv( "B2GPU_FLAT_LISTS" );
+		s->flatListsEnabled = flatEnv == nullptr || atoi( flatEnv ) != 0;
 		const char* resolveEnv = getenv( "B2GPU_RESOLVE" );
 		s->resolveContacts = resolveEnv == nullptr || atoi( resolveEnv ) != 0;
 		const char* stageEnv = getenv( "B2GPU_STAGE_ALL" );
@@ -641,6 +643,7 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	P.ownerLists = ownerLists ? 1 : 0;
 	P.jointsSpilled = plan.spillJoints ? 1 : 0;
 	P.listCount = listCount;
+	P.flatLists = plan.share == 1 && s->flatListsEnabled && s->resolveContacts && s->jointTotal < ( 1 << b2g::kFlatJointShift ) ? 1 : 0;
 	P.listCapContacts = ownerLists ? capC : capC * plan.share;
 	P.listCapJoints = ownerLists ? capJ : capJ * plan.share;
 	P.binBodyCount = s->binCounters.ptr;
@@ -1138,7 +1141,17 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 				B2G_CUDA( cudaMemsetAsync( s->binCounters.ptr, 0, s->binCounters.capacity * sizeof( int ), s->stream ) );
 			}
 			s->countersClean = true; // the island kernels zero the counters they have read
-			if ( s->cooperative )
+			if ( s->params.flatLists != 0 )
+			{
+				// one flat pass, one item per thread
+				const b2g::StepParams& P = s->params;
+				int items = P.bodyCount > P.contactSlots ? P.bodyCount : P.contactSlots;
+				items = items > P.jointCount ? items : P.jointCount;
+				int blocks = ( items + 255 ) / 256;
+				blocks = blocks < 1 ? 1 : blocks > s->smCount * 8 ? s->smCount * 8 : blocks;
+				err = cudaLaunchKernel( (const void*)b2g::b2gScatterKernel, dim3( blocks ), dim3( 256 ), args, 0, s->stream );
+			}
+			else if ( s->cooperative )
 			{
 				err = cudaLaunchCooperativeKernel( (const void*)b2g::b2gPartitionKernel, dim3( s->gridBlocks ),
 												   dim3( b2g::kPartitionThreads ), args, 0, s->stream );
