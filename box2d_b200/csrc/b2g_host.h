@@ -183,6 +183,7 @@ struct b2GpuSolver
 	int countersBinCount = 0, countersListCount = 0;
 	int ownerListsOff = 0;		 // steps during which owner lists stay off after a block's share did not fit
 	bool ownerListsEnabled = true; // B2GPU_OWNER_LISTS=0 turns them off
+	bool dependentLaunch = true;   // B2GPU_PDL=0: the island kernel is launched after the scatter kernel has drained
 	bool flatListsEnabled = true;  // B2GPU_FLAT_LISTS=0: two-phase partition kernel for one block per bin too
 	bool countersClean = false; // the bin counters are all zero (the island kernels zero what they have read)
 	DeviceBuffer<int2> contactBinRank, jointBinRank;
@@ -262,7 +263,7 @@ struct b2GpuSolver
 	int chunkNext = 0; // pump only
 	cudaEvent_t evControl = nullptr;
 	bool trace = false; // B2GPU_TRACE=1: print the timeline of the pipelined transfers at EndStep (stderr)
-	std::vector<std::pair<float, size_t>> traceSends, traceArrivals;
+	std::vector<std::pair<float, size_t>> traceSends, traceArrivals, tracePump;
 	float traceBegun = 0.0f, traceSubmit = 0.0f, traceControl = 0.0f;
 	float traceMarks[8] = { 0 };
 	bool controlSeen = false;

@@ -290,6 +290,9 @@ constexpr int kFlatJointShift = 26; // binJointList entry = joint index | colour
 
 __global__ void __launch_bounds__( 256 ) b2gScatterKernel( const __grid_constant__ StepParams P )
 {
+	// programmatic dependent launch: the island kernel's blocks may be set up on the SMs while this grid is still running;
+	// they wait (griddepcontrol.wait) for this grid to complete before they read anything
+	asm volatile( "griddepcontrol.launch_dependents;" );
 	const unsigned lane = threadIdx.x & 31u;
 	forEachItem( P.jointWords, [&]( int i ) {
 		if ( i < P.jointWords )
@@ -600,6 +603,9 @@ template <typename FJ, typename FC> B2G_DEV void forEachInLocalColor( int4 r, FJ
 
 __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __grid_constant__ StepParams P )
 {
+	// launched as a programmatic dependent of b2gScatterKernel: everything below reads what that grid wrote (a no-op
+	// after an ordinary launch)
+	asm volatile( "griddepcontrol.wait;" ::: "memory" );
 	if ( __ldcg( P.binFail ) != 0 )
 	{
 		if ( blockIdx.x == 0 && threadIdx.x == 0 )
@@ -689,6 +695,13 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			int4 info = __ldg( contactInfo + k );
 			int c = info.w >> kFlatColorShift;
 			atomicAdd( &flatCursorC[c], 1 );
+			// the wire record is read by the prepare pass, two block-wide barriers from here: start it on its way
+			const uint8_t* record = reinterpret_cast<const uint8_t*>( P.wire + (size_t)info.x * WR_COUNT );
+#pragma unroll
+			for ( int sector = 0; sector < WR_COUNT * 16; sector += 32 )
+			{
+				asm volatile( "prefetch.global.L2 [%0];" ::"l"( record + sector ) );
+			}
 			if ( c == P.colorCount )
 			{
 				overflowOrder[atomicAdd( &flatOverflowCount[0], 1 )] = info.x;
@@ -729,35 +742,59 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	}
 
 	const int colorCount = P.colorCount;
-	if ( threadIdx.x == 0 )
+	if ( threadIdx.x < 32 )
 	{
+		// one lane per colour slot: offsets of the colours (flat lists: exclusive scan of the counts), then the table of the
+		// colours that are present in this bin
+		const int lane = (int)threadIdx.x;
+		int nC = 0, nJ = 0, startC = 0, startJ = 0;
 		if ( flat )
 		{
-			int contacts = 0, joints = 0;
-			for ( int c = 0; c < kColorSlots; ++c )
+			nC = lane < kColorSlots ? flatCursorC[lane] : 0; // nothing was counted beyond the overflow bucket
+			nJ = lane < kColorSlots ? flatCursorJ[lane] : 0;
+			int sumC = nC, sumJ = nJ;
+#pragma unroll
+			for ( int d = 1; d < 32; d <<= 1 )
 			{
-				int n = flatCursorC[c], m = flatCursorJ[c]; // nothing was counted beyond the overflow bucket
-				colorStartC[c] = contacts;
-				colorStartJ[c] = joints;
-				flatCursorC[c] = contacts;
-				flatCursorJ[c] = joints;
-				contacts += n;
-				joints += m;
+				int upC = __shfl_up_sync( 0xffffffffu, sumC, d ), upJ = __shfl_up_sync( 0xffffffffu, sumJ, d );
+				sumC += lane >= d ? upC : 0;
+				sumJ += lane >= d ? upJ : 0;
+			}
+			startC = sumC - nC;
+			startJ = sumJ - nJ;
+			if ( lane < kColorSlots )
+			{
+				colorStartC[lane] = startC;
+				colorStartJ[lane] = startJ;
+				flatCursorC[lane] = startC;
+				flatCursorJ[lane] = startJ;
 			}
 		}
-		int passes = 0, widest = 32;
-		for ( int c = 0; c < colorCount; ++c )
+		else if ( lane + 1 < kColorSlots )
 		{
-			int4 r = make_int4( colorStartJ[c], colorStartJ[c + 1], colorStartC[c], colorStartC[c + 1] );
-			if ( r.x != r.y || r.z != r.w )
-			{
-				passRange[passes++] = r; // a colour that is not present in this bin has nothing to order
-				int width = roundUp32( r.y - r.x ) + roundUp32( r.w - r.z );
-				widest = width > widest ? width : widest;
-			}
+			startC = colorStartC[lane];
+			startJ = colorStartJ[lane];
+			nC = colorStartC[lane + 1] - startC;
+			nJ = colorStartJ[lane + 1] - startJ;
 		}
-		passCount = passes;
-		stageThreadCount = widest < (int)blockDim.x && P.stageAllThreads == 0 ? widest : (int)blockDim.x;
+		const bool present = lane < colorCount && ( nC | nJ ) != 0; // a colour that is not present in this bin has nothing to order
+		const unsigned presentMask = __ballot_sync( 0xffffffffu, present );
+		if ( present )
+		{
+			passRange[__popc( presentMask & ( ( 1u << lane ) - 1u ) )] = make_int4( startJ, startJ + nJ, startC, startC + nC );
+		}
+		int widest = present ? roundUp32( nJ ) + roundUp32( nC ) : 32;
+#pragma unroll
+		for ( int d = 16; d > 0; d >>= 1 )
+		{
+			int other = __shfl_xor_sync( 0xffffffffu, widest, d );
+			widest = other > widest ? other : widest;
+		}
+		if ( lane == 0 )
+		{
+			passCount = __popc( presentMask );
+			stageThreadCount = widest < (int)blockDim.x && P.stageAllThreads == 0 ? widest : (int)blockDim.x;
+		}
 	}
 	if ( flat )
 	{
@@ -916,91 +953,63 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	const int passes = passCount;
 	const int stageThreads = stageThreadCount;
 	auto blockSync = [&]() { asm volatile( "bar.sync 1, %0;" ::"r"( stageThreads ) : "memory" ); };
-	// The body stages (two per sub-step) get a thread per body: when that is more than the colour stages need, the extra
-	// warps join for the body stages only and wait at a second named barrier in between.
-	int bodyThreads = roundUp32( bodyCount ) < (int)blockDim.x ? roundUp32( bodyCount ) : (int)blockDim.x;
-	bodyThreads = bodyThreads > stageThreads && P.stageAllThreads == 0 ? bodyThreads : stageThreads;
-	const bool wideBodies = bodyThreads > stageThreads;
-	auto bodySync = [&]() {
-		if ( wideBodies )
-		{
-			asm volatile( "bar.sync 2, %0;" ::"r"( bodyThreads ) : "memory" );
-		}
-		else
-		{
-			blockSync();
-		}
-	};
-	auto joinBodies = [&]() {
-		if ( wideBodies )
-		{
-			asm volatile( "bar.sync 2, %0;" ::"r"( bodyThreads ) : "memory" );
-		}
-	};
-	if ( (int)threadIdx.x < bodyThreads )
+	// (Tried: a thread per body for the two body stages of a sub-step, the extra warps waiting at a second named barrier
+	// in between.  The wider barriers cost more than the shorter body loops saved: 0.0607 -> 0.0623 ms on many_pyramids.)
+	if ( (int)threadIdx.x < stageThreads )
 	{
-		const bool stager = (int)threadIdx.x < stageThreads;
 		for ( int subStep = 0; subStep < P.subStepCount; ++subStep )
 		{
-			forEachLocal( bodyCount, bodyThreads, [&]( int i ) { integrateVelocities( V, i ); } );
-			bodySync();
+			forEachLocal( bodyCount, stageThreads, [&]( int i ) { integrateVelocities( V, i ); } );
+			blockSync();
 			clk.lap( b2GpuStage_integrateVelocities );
 
-			if ( stager )
+			overflowLevels(
+				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); },
+				[&]( int k ) { warmStartContactOverflow( V, k ); }, blockSync, stageThreads );
+			for ( int pass = 0; pass < passes; ++pass )
 			{
-				overflowLevels(
-					overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); },
-					[&]( int k ) { warmStartContactOverflow( V, k ); }, blockSync, stageThreads );
-				for ( int pass = 0; pass < passes; ++pass )
-				{
-					forEachInLocalColor(
-						passRange[pass], stageThreads, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); },
-						[&]( int k ) { warmStartContact( V, k ); } );
-					blockSync();
-				}
-				clk.lap( b2GpuStage_warmStart );
-
-				overflowLevels(
-					overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), true ); },
-					[&]( int k ) { solveContactOverflow( P, V, k, true ); }, blockSync, stageThreads );
-				for ( int pass = 0; pass < passes; ++pass )
-				{
-					forEachInLocalColor(
-						passRange[pass], stageThreads,
-						[&]( int k ) {
-							b2lJointSim* joint = jointAt( V, k );
-							solveJoint( P, V, joint, true );
-							jointEventTest( P, joint );
-						},
-						[&]( int k ) { solveContact( P, V, k, true ); } );
-					blockSync();
-				}
-				clk.lap( b2GpuStage_solveImpulses );
+				forEachInLocalColor(
+					passRange[pass], stageThreads, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); },
+					[&]( int k ) { warmStartContact( V, k ); } );
+				blockSync();
 			}
-			joinBodies();
+			clk.lap( b2GpuStage_warmStart );
 
-			forEachLocal( bodyCount, bodyThreads, [&]( int i ) { integratePositions( P, V, i ); } );
-			bodySync();
+			overflowLevels(
+				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), true ); },
+				[&]( int k ) { solveContactOverflow( P, V, k, true ); }, blockSync, stageThreads );
+			for ( int pass = 0; pass < passes; ++pass )
+			{
+				forEachInLocalColor(
+					passRange[pass], stageThreads,
+					[&]( int k ) {
+						b2lJointSim* joint = jointAt( V, k );
+						solveJoint( P, V, joint, true );
+						jointEventTest( P, joint );
+					},
+					[&]( int k ) { solveContact( P, V, k, true ); } );
+				blockSync();
+			}
+			clk.lap( b2GpuStage_solveImpulses );
+
+			forEachLocal( bodyCount, stageThreads, [&]( int i ) { integratePositions( P, V, i ); } );
+			blockSync();
 			clk.lap( b2GpuStage_integratePositions );
 
-			if ( stager )
+			overflowLevels(
+				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+				[&]( int k ) { solveContactOverflow( P, V, k, false ); }, blockSync, stageThreads );
+			for ( int pass = 0; pass < passes; ++pass )
 			{
-				overflowLevels(
-					overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
-					[&]( int k ) { solveContactOverflow( P, V, k, false ); }, blockSync, stageThreads );
-				for ( int pass = 0; pass < passes; ++pass )
-				{
-					forEachInLocalColor(
-						passRange[pass], stageThreads, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
-						[&]( int k ) { solveContact( P, V, k, false ); } );
-					blockSync();
-				}
-				clk.lap( b2GpuStage_relaxImpulses );
+				forEachInLocalColor(
+					passRange[pass], stageThreads, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+					[&]( int k ) { solveContact( P, V, k, false ); } );
+				blockSync();
 			}
-			joinBodies();
+			clk.lap( b2GpuStage_relaxImpulses );
 		}
 
-		if ( stager && anyRestitution != 0 )
+		if ( anyRestitution != 0 )
 		{
 			if ( ovCe > ovCb )
 			{

@@ -147,6 +147,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		s->spillJointsForced = spillEnv != nullptr && atoi( spillEnv ) == 2;
 		const char* ownerEnv = getenv( "B2GPU_OWNER_LISTS" );
 		s->ownerListsEnabled = ownerEnv == nullptr || atoi( ownerEnv ) != 0;
+		const char* pdlEnv = getenv( "B2GPU_PDL" );
+		s->dependentLaunch = pdlEnv == nullptr || atoi( pdlEnv ) != 0;
 		const char* flatEnv = getenv( "B2GPU_FLAT_LISTS" );
 		s->flatListsEnabled = flatEnv == nullptr || atoi( flatEnv ) != 0;
 		const char* resolveEnv = getenv( "B2GPU_RESOLVE" );
@@ -1183,8 +1185,17 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 			}
 			else
 			{
-				err = cudaLaunchKernel( (const void*)b2g::b2gIslandKernel, dim3( s->params.binCount ), dim3( b2g::kIslandThreads ), args,
-										s->islandSmemBytes, s->stream );
+				cudaLaunchConfig_t config = {};
+				config.gridDim = dim3( (unsigned)s->params.binCount );
+				config.blockDim = dim3( b2g::kIslandThreads );
+				config.dynamicSmemBytes = s->islandSmemBytes;
+				config.stream = s->stream;
+				cudaLaunchAttribute attribute;
+				attribute.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+				attribute.val.programmaticStreamSerializationAllowed = 1;
+				config.attrs = &attribute;
+				config.numAttrs = s->params.flatLists != 0 && s->dependentLaunch ? 1 : 0;
+				err = cudaLaunchKernelEx( &config, b2g::b2gIslandKernel, s->params );
 			}
 			if ( err != cudaSuccess )
 			{
@@ -1346,6 +1357,11 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 		{
 			fprintf( stderr, " %.0f:%zu", e.first, e.second );
 		}
+		fprintf( stderr, " | pump saw (us: blocks of %d):", s->workBlocks );
+		for ( auto& e : s->tracePump )
+		{
+			fprintf( stderr, " %.0f:%zu", e.first, e.second );
+		}
 		fprintf( stderr, " | submit %.0f | kernels done %.0f | arrivals:", s->traceSubmit, s->traceControl );
 		for ( auto& e : s->traceArrivals )
 		{
@@ -1355,6 +1371,7 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 				 std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(), s->lastKernelMs * 1000.0f );
 	}
 	s->traceSends.clear();
+	s->tracePump.clear();
 	s->traceArrivals.clear();
 	s->begun = false;
 	return 0;

@@ -452,6 +452,10 @@ static int b2gPumpUploads( b2GpuSolver* s, bool everything )
 	}
 	bool complete = s->pumpPrefix == s->workBlocks;
 	size_t ready = b2gPackedPrefix( s, s->pumpPrefix );
+	if ( s->trace && s->tracePump.size() < 48 && ( s->tracePump.empty() || s->tracePump.back().second != (size_t)s->pumpPrefix ) )
+	{
+		s->tracePump.emplace_back( std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(), (size_t)s->pumpPrefix );
+	}
 	if ( ready > s->sentQuads && ( ( complete && everything ) || ready - s->sentQuads >= kTransferQuads ) )
 	{
 		return b2gSendArena( s, ready );
