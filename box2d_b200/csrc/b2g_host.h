@@ -221,7 +221,11 @@ struct b2GpuSolver
 
 	// arena layouts, in float4 units
 	size_t inStates = 0, inBody = 0, inWire = 0, inJoints = 0, inBins = 0, inTotal = 0;
-	size_t sentQuads = 0; // prefix of the input arena already enqueued for upload (b2gPumpUploads)
+	bool uploadStarted = false;		// evUpload recorded (first copy of the step)
+	bool arenaSent = false;			// the whole input arena has been enqueued for upload
+	std::vector<uint8_t> blockSent; // pack blocks whose part of the input arena has been enqueued for upload (b2gPumpUploads)
+	int sendScan = 0;				// every block before this one has been sent
+	size_t sendThreshold = 0;		// a run of packed blocks goes out when it is this long (quads)
 	size_t outStates = 0, outImpulses = 0, outJoints = 0, outBits = 0, outTotal = 0;
 
 	// the step in flight
@@ -254,7 +258,8 @@ struct b2GpuSolver
 	int workItems = 0;
 	std::unique_ptr<std::atomic<unsigned char>[]> workDone;
 	size_t workDoneCapacity = 0;
-	int pumpPrefix = 0; // pump only: blocks [0, pumpPrefix) are packed
+	int pumpPrefix = 0; // blocks [0, pumpPrefix) are packed (owned by whoever holds pumpBusy)
+	std::atomic<int> pumpBusy{ 0 }; // a thread is enqueueing uploads
 	std::atomic<size_t> arrivedQuads{ 0 };
 	std::atomic<int> workFailed{ 0 };
 	std::vector<cudaEvent_t> chunkEvents;
@@ -301,7 +306,8 @@ inline int b2gFindSegment( const std::vector<int>& starts, int flat )
 
 // ---- blocks of host work --------------------------------------------------------------------------------------------
 constexpr int kWorkBlockItems = 512;
-constexpr size_t kTransferQuads = 64 * 1024; // 1 MiB: granularity of the pipelined uploads
+constexpr size_t kTransferQuads = 16 * 1024;	  // 256 KiB: the first piece of a pipelined upload; the pieces double up to
+constexpr size_t kTransferQuadsMax = 256 * 1024; // 4 MiB
 constexpr size_t kDownloadQuads = 32 * 1024; // 512 KiB: the unpack pass runs this far behind the download
 
 // b2g_wire.cu

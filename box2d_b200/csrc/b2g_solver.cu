@@ -686,6 +686,9 @@ static void b2gResetWork( b2GpuSolver* s, int itemCount, int blockCount )
 		s->workDone[i].store( 0, std::memory_order_relaxed );
 	}
 	s->pumpPrefix = 0;
+	s->sendScan = 0;
+	s->sendThreshold = kTransferQuads;
+	s->blockSent.assign( (size_t)blockCount, 0 );
 	s->workFailed.store( 0, std::memory_order_relaxed );
 	s->workNext.store( 0, std::memory_order_release );
 }
@@ -895,7 +898,8 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	s->inBody = s->inStates + 2 * nb;
 	s->inBins = s->inBody + 2 * nb;
 	s->inTotal = s->inBins + ( nb + 3 ) / 4;
-	s->sentQuads = 0;
+	s->uploadStarted = false;
+	s->arenaSent = false;
 	// output arena: [states 2/body][impulse records][joint impulse records 3/joint][joint event bits]
 	size_t impulseQuads = ( (size_t)slot * b2g::kImpulseFloats + 3 ) / 4;
 	s->outStates = 0;
@@ -1316,12 +1320,14 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 	auto ms = []( std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b ) {
 		return std::chrono::duration<float, std::milli>( b - a ).count();
 	};
+	s->traceMarks[6] = std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count();
 	if ( results != nullptr )
 	{
 		const uint32_t* bits = reinterpret_cast<const uint32_t*>( s->hOut.ptr + s->outBits );
 		auto now = std::chrono::steady_clock::now();
 		float h2dMs = 0.0f;
 		cudaEventElapsedTime( &h2dMs, s->evUpload, s->evStart ); // one driver call, not one per world
+		s->traceMarks[7] = std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count();
 		for ( size_t w = 0; w < s->bodySegs.size(); ++w )
 		{
 			const b2gBodySeg& seg = s->bodySegs[w];
@@ -1362,11 +1368,18 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 		{
 			fprintf( stderr, " %.0f:%zu", e.first, e.second );
 		}
+		{
+			float h2dMs = 0.0f;
+			cudaEventElapsedTime( &h2dMs, s->evUpload, s->evStart );
+			fprintf( stderr, " | first copy to kernels %.0f us (device clock)", h2dMs * 1000.0f );
+		}
 		fprintf( stderr, " | submit %.0f | kernels done %.0f | arrivals:", s->traceSubmit, s->traceControl );
 		for ( auto& e : s->traceArrivals )
 		{
 			fprintf( stderr, " %.0f:%zu", e.first, e.second );
 		}
+		fprintf( stderr, " | pump out of blocks %.0f | EndStep %.0f | h2d timer read %.0f | results filled %.0f", s->traceMarks[5], s->traceMarks[6],
+				 s->traceMarks[7], std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count() );
 		fprintf( stderr, " | end %.0f | kernel %.0f us\n",
 				 std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(), s->lastKernelMs * 1000.0f );
 	}

@@ -257,23 +257,35 @@ static size_t b2gPackedPrefix( const b2GpuSolver* s, int blocksDone )
 	return s->inJoints + (size_t)( flat - s->contactTotal ) * ( b2g::kJointStride / 16 );
 }
 
-int b2gSendArena( b2GpuSolver* s, size_t uptoQuads )
+// enqueue the upload of quads [fromQuads, uptoQuads) of the input arena
+static int b2gSendRange( b2GpuSolver* s, size_t fromQuads, size_t uptoQuads )
 {
-	if ( s->sentQuads == 0 )
+	if ( !s->uploadStarted )
 	{
 		B2G_CUDA( cudaEventRecord( s->evUpload, s->stream ) );
+		s->uploadStarted = true;
 	}
-	if ( uptoQuads > s->sentQuads )
+	if ( uptoQuads > fromQuads )
 	{
 		if ( s->trace )
 		{
 			s->traceSends.emplace_back( std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(), uptoQuads );
 		}
-		B2G_CUDA( cudaMemcpyAsync( s->wireAll.ptr + s->sentQuads, s->hWire.ptr + s->sentQuads,
-								   ( uptoQuads - s->sentQuads ) * sizeof( float4 ), cudaMemcpyHostToDevice, s->stream ) );
-		s->sentQuads = uptoQuads;
+		B2G_CUDA( cudaMemcpyAsync( s->wireAll.ptr + fromQuads, s->hWire.ptr + fromQuads, ( uptoQuads - fromQuads ) * sizeof( float4 ),
+								   cudaMemcpyHostToDevice, s->stream ) );
 	}
 	return 0;
+}
+
+// the whole input arena in one piece (callers that packed it with b2GpuSolverPackRange)
+int b2gSendArena( b2GpuSolver* s, size_t uptoQuads )
+{
+	if ( s->arenaSent )
+	{
+		return 0; // the pipelined pack pass has sent it piece by piece
+	}
+	s->arenaSent = true;
+	return b2gSendRange( s, 0, uptoQuads );
 }
 
 // ---- phase 4: unpack (callable concurrently on disjoint ranges) ---------------------------------------------------------
@@ -444,23 +456,76 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 // it starts the upload of every finished prefix of the arena (PCIe runs behind the packing instead of after it), and
 // besides unpacking it watches the download events and tells the others how much of the output has arrived (unpacking
 // runs behind the download).
+// Uploads what has been packed.  The constraint blocks come first in the arena and block b fills the quads
+// [b2gPackedPrefix( b ), b2gPackedPrefix( b + 1 )): every long enough run of finished, unsent blocks goes out as one
+// copy -- runs, not just the finished PREFIX, so that one slow block (a worker that was descheduled in the middle of it)
+// does not hold back everything behind it.  The three body regions are interleaved by region, not by body: they follow
+// in one piece when all blocks are done (`everything`: also the runs that stayed short).
 static int b2gPumpUploads( b2GpuSolver* s, bool everything )
 {
+	const int restItems = s->contactTotal + s->jointTotal;
+	const int restBlocks = ( restItems + kWorkBlockItems - 1 ) / kWorkBlockItems;
 	while ( s->pumpPrefix < s->workBlocks && s->workDone[s->pumpPrefix].load( std::memory_order_acquire ) != 0 )
 	{
 		s->pumpPrefix += 1;
 	}
-	bool complete = s->pumpPrefix == s->workBlocks;
-	size_t ready = b2gPackedPrefix( s, s->pumpPrefix );
+	const bool complete = s->pumpPrefix == s->workBlocks;
 	if ( s->trace && s->tracePump.size() < 48 && ( s->tracePump.empty() || s->tracePump.back().second != (size_t)s->pumpPrefix ) )
 	{
 		s->tracePump.emplace_back( std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(), (size_t)s->pumpPrefix );
 	}
-	if ( ready > s->sentQuads && ( ( complete && everything ) || ready - s->sentQuads >= kTransferQuads ) )
+	while ( s->sendScan < restBlocks && s->blockSent[(size_t)s->sendScan] != 0 )
 	{
-		return b2gSendArena( s, ready );
+		s->sendScan += 1;
+	}
+	for ( int i = s->sendScan; i < restBlocks; )
+	{
+		if ( s->blockSent[(size_t)i] != 0 || s->workDone[i].load( std::memory_order_acquire ) == 0 )
+		{
+			i += 1;
+			continue;
+		}
+		int j = i + 1;
+		while ( j < restBlocks && s->blockSent[(size_t)j] == 0 && s->workDone[j].load( std::memory_order_acquire ) != 0 )
+		{
+			j += 1;
+		}
+		size_t from = b2gPackedPrefix( s, i ), upto = b2gPackedPrefix( s, j );
+		if ( upto - from >= s->sendThreshold || ( complete && everything ) )
+		{
+			if ( b2gSendRange( s, from, upto ) != 0 )
+			{
+				return 1;
+			}
+			// small pieces first (the link starts early), then larger ones (a copy costs a few microseconds of set-up; the
+			// packing runs ahead of the link, so there is always more to send)
+			s->sendThreshold = s->sendThreshold * 2 < kTransferQuadsMax ? s->sendThreshold * 2 : kTransferQuadsMax;
+			for ( int k = i; k < j; ++k )
+			{
+				s->blockSent[(size_t)k] = 1;
+			}
+		}
+		i = j;
+	}
+	if ( complete && everything )
+	{
+		s->arenaSent = true;
+		return b2gSendRange( s, s->inStates, s->inTotal );
 	}
 	return 0;
+}
+
+// Whoever has just finished a block looks after the uploads, unless somebody else is already doing that: the transfers do
+// not wait for one particular thread (which may be in the middle of a block, or descheduled).
+static int b2gTryPumpUploads( b2GpuSolver* s )
+{
+	if ( s->pumpBusy.exchange( 1, std::memory_order_acquire ) != 0 )
+	{
+		return 0;
+	}
+	int rc = b2gPumpUploads( s, false );
+	s->pumpBusy.store( 0, std::memory_order_release );
+	return rc;
 }
 
 extern "C" int b2GpuSolverPackWork( b2GpuSolver* s, int pump )
@@ -469,17 +534,9 @@ extern "C" int b2GpuSolverPackWork( b2GpuSolver* s, int pump )
 	{
 		return b2gFailMsg( "b2GpuSolverPackWork: no step begun" );
 	}
-	if ( pump != 0 )
-	{
-		cudaSetDevice( s->device );
-	}
+	cudaSetDevice( s->device );
 	for ( ;; )
 	{
-		if ( pump != 0 && b2gPumpUploads( s, false ) != 0 )
-		{
-			s->workFailed.store( 1 );
-			return 1;
-		}
 		int block = s->workNext.fetch_add( 1, std::memory_order_acq_rel );
 		if ( block >= s->workBlocks )
 		{
@@ -489,19 +546,42 @@ extern "C" int b2GpuSolverPackWork( b2GpuSolver* s, int pump )
 		b2gPackBlockRange( s, block, &begin, &end );
 		b2GpuSolverPackRange( s, begin, end ); // ends with an sfence: the streaming stores are visible to the DMA engine
 		s->workDone[block].store( 1, std::memory_order_release );
+		if ( b2gTryPumpUploads( s ) != 0 )
+		{
+			s->workFailed.store( 1 );
+			return 1;
+		}
 	}
 	if ( pump != 0 )
 	{
-		// the others may still be packing the blocks they claimed
-		while ( s->pumpPrefix < s->workBlocks )
+		// the others may still be packing the blocks they claimed; the last bytes go out from here
+		for ( ;; )
 		{
-			if ( b2gPumpUploads( s, false ) != 0 )
+			if ( s->pumpBusy.exchange( 1, std::memory_order_acquire ) == 0 )
+			{
+				int rc = b2gPumpUploads( s, false );
+				bool complete = s->pumpPrefix == s->workBlocks;
+				if ( rc == 0 && complete )
+				{
+					rc = b2gPumpUploads( s, true );
+				}
+				s->pumpBusy.store( 0, std::memory_order_release );
+				if ( rc != 0 )
+				{
+					s->workFailed.store( 1 );
+					return 1;
+				}
+				if ( complete )
+				{
+					break;
+				}
+			}
+			if ( s->workFailed.load( std::memory_order_relaxed ) != 0 )
 			{
 				return 1;
 			}
 			_mm_pause();
 		}
-		return b2gPumpUploads( s, true );
 	}
 	return 0;
 }
@@ -578,6 +658,9 @@ static int b2gPumpDownloads( b2GpuSolver* s )
 	return 0;
 }
 
+// (Tried: each thread unpacks the blocks it packed, so that the b2ContactSim lines it writes are still in its own cache.
+// No measurable gain on the 16-core hosts -- the tail of the unpack pass stayed ~60 us on many_pyramids -- and the
+// search for one's own blocks does not scale to the thousands of blocks of a batch; blocks are claimed in order.)
 extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 {
 	if ( s == nullptr || !s->begun )
@@ -618,6 +701,7 @@ extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 	}
 	if ( pump != 0 )
 	{
+		s->traceMarks[5] = std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count();
 		// the tail of the arena (joint event bits) is consumed by EndStep
 		while ( !s->controlSeen || s->chunkNext < s->chunkCount )
 		{
