@@ -397,7 +397,7 @@ def run_scene(args) -> int:
 						 "traffic": measured_traffic(scene), "algorithmic_bytes_per_launch": alg, "peak_source": peak_source,
 						 "kernels_per_step": launches_per_step, "grid_barriers_per_step": grid_barriers,
 						 "island_bins_blocks_per_bin": island_plan,
-						 "note": "all kernels of the step (partition + island kernel, or the grid-barrier kernel); see DESIGN.md"},
+						 "note": "all kernels of the step (scatter or partition kernel + island or cluster kernel, or the grid-barrier kernel); see DESIGN.md"},
 			"stage_ms_per_step": {n: stage_ms[i] for i, n in enumerate(b2.STAGE_NAMES)},
 			"clocks": clocks,
 		}

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	__shared__ __align__( 8 ) unsigned long long arrivalBar;
 	__shared__ int overflowOrder[kMaxBinOverflow];
 	__shared__ OverflowSchedule overflow; // of the bin's overflow colour (held by the cluster's first block)
+	__shared__ int overflowCacheCount;	  // > 0: the bodies of a deep overflow chain are cached in the first block (see below)
 
 	cg::cluster_group cluster = cg::this_cluster();
 	const int share = P.clusterSize;
@@ -312,9 +313,112 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 			b = ( __float_as_uint( gatherVel( V, b ).w ) & B2L_FLAG_DYNAMIC ) != 0 ? b : 0;
 		} );
 	}
+	// A deep overflow chain (every contact touches the same dynamic body: the drum of the tumbler scene) is walked by ONE
+	// thread, and in a cluster each of its gathers and scatters is a distributed-shared-memory round trip (~215 cycles):
+	// 0.42 us per contact.  The bodies of the chain are therefore cached in the first block for the duration of a pass --
+	// filled and written back by all threads in parallel, the sequential walk in between only touches local shared
+	// memory.  The cache lives in the part of the schedule that a deep chain does not use (bodyA .. order); the contacts'
+	// body indices are replaced by cache slots (nothing else reads the indices of overflow contacts after this point).
+	constexpr int kOverflowCacheSlots = ( 2 * kMaxOverflowItems * (int)sizeof( int ) + 2 * kMaxOverflowItems * (int)sizeof( short ) ) / 36;
+	float4* const cacheVel = reinterpret_cast<float4*>( &overflow );
+	float4* const cachePos = cacheVel + kOverflowCacheSlots;
+	int* const cacheBody = reinterpret_cast<int*>( cachePos + kOverflowCacheSlots );
+	static_assert( offsetof( OverflowSchedule, levelStart ) >= (size_t)kOverflowCacheSlots * 36, "the overflow cache overlaps the live part of the schedule" );
+	if ( threadIdx.x == 0 )
+	{
+		overflowCacheCount = 0;
+	}
+	if ( hasOverflow && rank == 0 )
+	{
+		__syncthreads();
+		const int chain = ovCe - ovCb, entries = 2 * chain;
+		if ( overflow.levelCount < 0 && ovJoints == 0 && entries <= kMaxOverflowItems )
+		{
+			auto bodyOfEntry = [&]( int e ) -> int {
+				int2 idx = V.cidx[ovCb + ( e >> 1 )];
+				return ( e & 1 ) != 0 ? idx.y : idx.x;
+			};
+			// first occurrence of every body (0 = the static dummy keeps slot 0)
+			short* firstFlag = overflow.levelStart + 1;
+			int* slotOfFirst = reinterpret_cast<int*>( cacheVel ); // scratch until the cache is filled for the first time
+			for ( int e = (int)threadIdx.x; e < entries; e += (int)blockDim.x )
+			{
+				int body = bodyOfEntry( e );
+				bool first = body != 0;
+				for ( int f = 0; f < e && first; ++f )
+				{
+					first = bodyOfEntry( f ) != body;
+				}
+				firstFlag[e] = first ? 1 : 0;
+			}
+			__syncthreads();
+			for ( int e = (int)threadIdx.x; e < entries; e += (int)blockDim.x )
+			{
+				int before = 0;
+				for ( int f = 0; f < e; ++f )
+				{
+					before += firstFlag[f];
+				}
+				slotOfFirst[e] = firstFlag[e] != 0 ? 1 + before : 0;
+				if ( e == entries - 1 )
+				{
+					overflowCacheCount = before + firstFlag[e]; // distinct bodies
+				}
+			}
+			__syncthreads();
+			const int distinct = overflowCacheCount;
+			int mySlot[( kMaxOverflowItems + kIslandThreads - 1 ) / kIslandThreads];
+			int myBody[( kMaxOverflowItems + kIslandThreads - 1 ) / kIslandThreads];
+			if ( distinct + 1 <= kOverflowCacheSlots )
+			{
+				int n = 0;
+				for ( int e = (int)threadIdx.x; e < entries; e += (int)blockDim.x, ++n )
+				{
+					int body = bodyOfEntry( e ), slot = 0;
+					for ( int f = 0; f <= e && body != 0 && slot == 0; ++f )
+					{
+						slot = bodyOfEntry( f ) == body ? slotOfFirst[f] : 0;
+					}
+					mySlot[n] = slot;
+					myBody[n] = body;
+				}
+				__syncthreads(); // everybody has read the indices and the scratch
+				n = 0;
+				for ( int e = (int)threadIdx.x; e < entries; e += (int)blockDim.x, ++n )
+				{
+					int* pair = reinterpret_cast<int*>( V.cidx + ovCb + ( e >> 1 ) );
+					pair[e & 1] = mySlot[n];
+					if ( firstFlag[e] != 0 )
+					{
+						cacheBody[mySlot[n]] = myBody[n];
+					}
+				}
+				if ( threadIdx.x == 0 )
+				{
+					cacheBody[0] = 0;
+				}
+				__syncthreads();
+				if ( threadIdx.x == 0 )
+				{
+					cacheVel[0] = make_float4( 0.0f, 0.0f, 0.0f, __uint_as_float( 0u ) );
+					cachePos[0] = make_float4( 0.0f, 0.0f, 1.0f, 0.0f );
+				}
+			}
+			else if ( threadIdx.x == 0 )
+			{
+				overflowCacheCount = 0; // too many bodies: the chain is walked through distributed shared memory
+			}
+		}
+	}
 	cluster.sync();
 	// the number of overflow levels is needed by every block of the cluster (they all take part in the barriers)
 	const int overflowLevelCount = hasOverflow ? *cluster.map_shared_rank( &overflow.levelCount, 0 ) : 0;
+	const int overflowCached = hasOverflow ? *cluster.map_shared_rank( &overflowCacheCount, 0 ) : 0;
+	SolveView VO = V; // the first block's cache of a deep chain's bodies as a flat view
+	VO.vel = cacheVel;
+	VO.pos = cachePos;
+	VO.clusterRun = 0;
+	VO.clusterMagic = 0;
 	auto clusterSync = [&]() { cluster.sync(); };
 	// restitution is applied by the whole cluster or not at all
 	if ( threadIdx.x < 32 )
@@ -330,7 +434,34 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	clk.lap( b2GpuStage_prepareConstraints );
 
 	auto overflowPass = [&]( auto joint, auto contact ) {
-		overflowLevels( overflow, overflowLevelCount, rank == 0, ovJoints, ovJb, ovCb, joint, contact, clusterSync, (int)blockDim.x );
+		if ( overflowCached > 0 )
+		{
+			if ( rank == 0 )
+			{
+				for ( int slot = 1 + (int)threadIdx.x; slot <= overflowCached; slot += (int)blockDim.x )
+				{
+					cacheVel[slot] = gatherVel( V, cacheBody[slot] );
+					cachePos[slot] = gatherPos( V, cacheBody[slot] );
+				}
+				__syncthreads();
+				if ( threadIdx.x == 0 )
+				{
+					for ( int k = ovCb; k < ovCe; ++k )
+					{
+						contact( VO, k );
+					}
+				}
+				__syncthreads();
+				for ( int slot = 1 + (int)threadIdx.x; slot <= overflowCached; slot += (int)blockDim.x )
+				{
+					scatterVel( V, cacheBody[slot], cacheVel[slot] ); // dynamic bodies only, like every scatter
+				}
+			}
+			cluster.sync();
+			return;
+		}
+		overflowLevels(
+			overflow, overflowLevelCount, rank == 0, ovJoints, ovJb, ovCb, joint, [&]( int k ) { contact( V, k ); }, clusterSync, (int)blockDim.x );
 	};
 	// A pass over the colours.  A full cluster barrier (release / acquire) makes every writer fence its remote stores at
 	// GPU scope (MEMBAR.ALL.GPU), which costs more than the colour itself.  The colours use counted stores instead: the
@@ -386,13 +517,14 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		cluster.sync();
 		clk.lap( b2GpuStage_integrateVelocities );
 
-		overflowPass( [&]( int k ) { warmStartJoint( P, V, jointRecord( k ) ); }, [&]( int k ) { warmStartContactOverflow( V, k ); } );
+		overflowPass( [&]( int k ) { warmStartJoint( P, V, jointRecord( k ) ); },
+					  [&]( const SolveView& view, int k ) { warmStartContactOverflow( view, k ); } );
 		colorPass( [&]( const SolveView& view, int k ) { warmStartJoint( P, view, jointRecord( k ) ); },
 				   [&]( const SolveView& view, int k ) { warmStartContact( view, k ); } );
 		clk.lap( b2GpuStage_warmStart );
 
 		overflowPass( [&]( int k ) { solveJoint( P, V, jointRecord( k ), true ); },
-					  [&]( int k ) { solveContactOverflow( P, V, k, true ); } );
+					  [&]( const SolveView& view, int k ) { solveContactOverflow( P, view, k, true ); } );
 		colorPass(
 			[&]( const SolveView& view, int k ) {
 				b2lJointSim* joint = jointRecord( k );
@@ -407,7 +539,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		clk.lap( b2GpuStage_integratePositions );
 
 		overflowPass( [&]( int k ) { solveJoint( P, V, jointRecord( k ), false ); },
-					  [&]( int k ) { solveContactOverflow( P, V, k, false ); } );
+					  [&]( const SolveView& view, int k ) { solveContactOverflow( P, view, k, false ); } );
 		colorPass( [&]( const SolveView& view, int k ) { solveJoint( P, view, jointRecord( k ), false ); },
 				   [&]( const SolveView& view, int k ) { solveContact( P, view, k, false ); } );
 		clk.lap( b2GpuStage_relaxImpulses );
@@ -417,7 +549,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	{
 		if ( binCountC[colorCount] > 0 )
 		{
-			overflowPass( []( int ) {}, [&]( int k ) { restitutionContactOverflow( P, V, k ); } );
+			overflowPass( []( int ) {}, [&]( const SolveView& view, int k ) { restitutionContactOverflow( P, view, k ); } );
 		}
 		for ( int c = 0; c < colorCount; ++c )
 		{

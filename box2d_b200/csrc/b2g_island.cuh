@@ -395,7 +395,7 @@ __global__ void __launch_bounds__( 256 ) b2gScatterKernel( const __grid_constant
 // Typical overflow sets (everything touching one kinematic or very crowded body) have one or two levels.
 constexpr int kMaxOverflowItems = 2 * kMaxBinOverflow; // joints + contacts
 
-struct OverflowSchedule
+struct alignas( 16 ) OverflowSchedule
 {
 	int bodyA[kMaxOverflowItems]; // dynamic bodies of item i (bin-local, 1-based), 0 = none
 	int bodyB[kMaxOverflowItems];

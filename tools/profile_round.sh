@@ -8,11 +8,13 @@ python bench.py > $O/${R}_bench_default.json 2> $O/${R}_bench_default.err
 for w in large_pyramid joint_grid rain tumbler; do
   timeout 300 python bench.py --workload $w --steps 60 --warmup 10 2>/dev/null | tail -1 > $O/${R}_bench_$w.json
 done
+B2GPU_TRACE=1 python bench.py --steps 8 --warmup 3 --no-cpu-baseline 2>&1 >/dev/null | grep b2gpu | tail -4 > $O/${R}_e2e_trace.txt
 timeout 300 python bench.py --workload batch --steps 10 --warmup 3 2>/dev/null | tail -1 > $O/${R}_bench_batch.json
 timeout 300 python bench.py --impl reference --steps 20 --warmup 5 2>/dev/null | tail -1 > $O/${R}_bench_reference_arm.json
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/${R}_launches_default.csv python bench.py --steps 3 --warmup 3 > $O/${R}_ncu_launches.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gIslandKernel -c 1 -s 8 -o $O/${R}_island -f python bench.py --steps 3 --warmup 3 > $O/${R}_ncu_island.log 2>&1
-timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gPartitionKernel -c 1 -s 8 -o $O/${R}_partition -f python bench.py --steps 3 --warmup 3 > $O/${R}_ncu_partition.log 2>&1
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gScatterKernel -c 1 -s 8 -o $O/${R}_scatter -f python bench.py --steps 3 --warmup 3 > $O/${R}_ncu_scatter.log 2>&1
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gPartitionKernel -c 1 -s 8 -o $O/${R}_partition -f python bench.py --workload large_pyramid --steps 3 --warmup 3 > $O/${R}_ncu_partition.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gClusterIslandKernel -c 1 -s 8 -o $O/${R}_cluster -f python bench.py --workload large_pyramid --steps 3 --warmup 3 > $O/${R}_ncu_cluster.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gStepKernel -c 1 -s 8 -o $O/${R}_grid -f python bench.py --workload joint_grid --steps 3 --warmup 3 > $O/${R}_ncu_grid.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:b2gIslandKernel -c 1 -o $O/${R}_island_batch -f python bench.py --workload batch --steps 2 --warmup 3 > $O/${R}_ncu_island_batch.log 2>&1

@@ -103,12 +103,13 @@ def main() -> None:
 	rnd = sys.argv[1] if len(sys.argv) > 1 else "r01"
 	PROF.mkdir(exist_ok=True)
 	launch_summary(rnd)
-	for name, note in (("island", "many_pyramids, one block per bin"), ("partition", "many_pyramids"),
+	for name, note in (("island", "many_pyramids, one block per bin"), ("scatter", "many_pyramids, single-pass partition for one block per bin"),
+					   ("partition", "large_pyramid, two-phase partition for a cluster with owner lists"),
 					   ("cluster", "large_pyramid, one 16-block cluster for the single island"),
 					   ("grid", "joint_grid, grid-barrier kernel: the island does not fit any cluster"),
 					   ("island_batch", "batch of 8192 small_pyramid worlds")):
 		kernel_summary(rnd, name, note)
-	for f in OUT.glob(f"{rnd}_bench_*.json"):
+	for f in list(OUT.glob(f"{rnd}_bench_*.json")) + list(OUT.glob(f"{rnd}_e2e_trace.txt")):
 		if f.stat().st_size > 0:
 			shutil.copy(f, PROF / f.name)
 
