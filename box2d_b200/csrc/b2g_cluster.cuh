@@ -433,7 +433,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	__syncthreads();
 	clk.lap( b2GpuStage_prepareConstraints );
 
-	auto overflowPass = [&]( auto joint, auto contact ) {
+	auto overflowPass = [&]( auto op, auto joint, auto contact ) {
 		if ( overflowCached > 0 )
 		{
 			if ( rank == 0 )
@@ -444,12 +444,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 					cachePos[slot] = gatherPos( V, cacheBody[slot] );
 				}
 				__syncthreads();
-				if ( threadIdx.x == 0 )
+				if ( threadIdx.x < 32 )
 				{
-					for ( int k = ovCb; k < ovCe; ++k )
-					{
-						contact( VO, k );
-					}
+					overflowChainWarp<decltype( op )::value>( P, VO, ovCb, ovCe ); // one warp, the lanes take turns
 				}
 				__syncthreads();
 				for ( int slot = 1 + (int)threadIdx.x; slot <= overflowCached; slot += (int)blockDim.x )
@@ -517,13 +514,13 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		cluster.sync();
 		clk.lap( b2GpuStage_integrateVelocities );
 
-		overflowPass( [&]( int k ) { warmStartJoint( P, V, jointRecord( k ) ); },
+		overflowPass( std::integral_constant<int, OV_WARM>{}, [&]( int k ) { warmStartJoint( P, V, jointRecord( k ) ); },
 					  [&]( const SolveView& view, int k ) { warmStartContactOverflow( view, k ); } );
 		colorPass( [&]( const SolveView& view, int k ) { warmStartJoint( P, view, jointRecord( k ) ); },
 				   [&]( const SolveView& view, int k ) { warmStartContact( view, k ); } );
 		clk.lap( b2GpuStage_warmStart );
 
-		overflowPass( [&]( int k ) { solveJoint( P, V, jointRecord( k ), true ); },
+		overflowPass( std::integral_constant<int, OV_SOLVE>{}, [&]( int k ) { solveJoint( P, V, jointRecord( k ), true ); },
 					  [&]( const SolveView& view, int k ) { solveContactOverflow( P, view, k, true ); } );
 		colorPass(
 			[&]( const SolveView& view, int k ) {
@@ -538,7 +535,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		cluster.sync();
 		clk.lap( b2GpuStage_integratePositions );
 
-		overflowPass( [&]( int k ) { solveJoint( P, V, jointRecord( k ), false ); },
+		overflowPass( std::integral_constant<int, OV_RELAX>{}, [&]( int k ) { solveJoint( P, V, jointRecord( k ), false ); },
 					  [&]( const SolveView& view, int k ) { solveContactOverflow( P, view, k, false ); } );
 		colorPass( [&]( const SolveView& view, int k ) { solveJoint( P, view, jointRecord( k ), false ); },
 				   [&]( const SolveView& view, int k ) { solveContact( P, view, k, false ); } );
@@ -549,7 +546,8 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	{
 		if ( binCountC[colorCount] > 0 )
 		{
-			overflowPass( []( int ) {}, [&]( const SolveView& view, int k ) { restitutionContactOverflow( P, view, k ); } );
+			overflowPass( std::integral_constant<int, OV_RESTITUTION>{}, []( int ) {},
+						  [&]( const SolveView& view, int k ) { restitutionContactOverflow( P, view, k ); } );
 		}
 		for ( int c = 0; c < colorCount; ++c )
 		{

@@ -847,4 +847,257 @@ B2G_DEV void restitutionContactOverflow( const StepParams& P, const SolveView& V
 	scatterVel( V, idx.y, make_float4( vB.x, vB.y, wB, sB.w ) );
 }
 
+// ===========================================================================================================
+// A deep overflow chain walked by ONE WARP (contacts [begin, end) of the view, in order).
+// ===========================================================================================================
+// The sequence of updates a body sees must be the reference's (one contact after the other, array order), but only the
+// part of a contact that READS OR WRITES BODY VELOCITIES is sequential.  Lane L takes contact base + L: it loads the
+// constraint and evaluates everything that does not depend on velocities (anchors, separation, bias and softness per
+// point, the warm-start impulse vectors) together with the other 31 lanes; then the lanes take turns -- gather {v, w},
+// the dependent chain, scatter -- and finally all store their impulses together.  Every expression is the one of the
+// scalar functions above, evaluated in the same order; only the loads and the velocity-independent terms move.
+enum OverflowOp
+{
+	OV_WARM = 0,
+	OV_SOLVE = 1, // useBias
+	OV_RELAX = 2,
+	OV_RESTITUTION = 3
+};
+
+template <int Op> B2G_DEV void overflowChainWarp( const StepParams& P, const SolveView& V, int begin, int end )
+{
+	const int lane = (int)( threadIdx.x & 31u );
+	constexpr bool useBias = Op == OV_SOLVE;
+	for ( int base = begin; base < end; base += 32 )
+	{
+		const int k = base + lane;
+		bool valid = k < end;
+		const int slot = valid ? k : begin;
+
+		// ---- together: the constraint and what does not depend on velocities
+		int2 idx = V.cidx[slot];
+		int pointCount = V.cmeta[slot] & kMetaPointMask;
+		float4 mass = loadField( V, CF_MASS, slot );
+		float mA = mass.x, iA = mass.y, mB = mass.z, iB = mass.w;
+		float4 nrm = loadField( V, CF_NORMAL, slot );
+		V2 normal = v2( nrm.x, nrm.y );
+		V2 tangent = rightPerp( normal );
+		float friction = nrm.z;
+		float tangentSpeed = nrm.w;
+		float4 roll = loadField( V, CF_ROLL, slot );
+		float4 imp[2] = { loadField( V, CF_IMP1, slot ), loadField( V, CF_IMP2, slot ) };
+		float4 anc[2] = { loadField( V, CF_ANCHOR1, slot ), loadField( V, CF_ANCHOR2, slot ) };
+		float normalMass[2] = { 0.0f, 0.0f }, tangentMass[2] = { 0.0f, 0.0f };
+		float velocityBias[2] = { 0.0f, 0.0f }, massScale[2] = { 1.0f, 1.0f }, impulseScale[2] = { 0.0f, 0.0f };
+		float relativeVelocity[2] = { 0.0f, 0.0f };
+		bool skipPoint[2] = { false, false };
+		V2 warmP[2] = { v2( 0.0f, 0.0f ), v2( 0.0f, 0.0f ) };
+
+		if ( Op == OV_WARM )
+		{
+#pragma unroll
+			for ( int j = 0; j < 2; ++j )
+			{
+				if ( j >= pointCount )
+				{
+					continue;
+				}
+				warmP[j] = add( mulSV( imp[j].x, normal ), mulSV( imp[j].y, tangent ) );
+				imp[j].z += imp[j].x;
+			}
+		}
+		else if ( Op == OV_RESTITUTION )
+		{
+			float4 pmass = loadField( V, CF_PMASS, slot );
+			float4 baseField = loadField( V, CF_BASE, slot );
+			normalMass[0] = pmass.x, normalMass[1] = pmass.z;
+			relativeVelocity[0] = baseField.z, relativeVelocity[1] = baseField.w;
+			valid = valid && !( roll.y == 0.0f );
+			float threshold = P.restitutionThreshold;
+#pragma unroll
+			for ( int j = 0; j < 2; ++j )
+			{
+				skipPoint[j] = relativeVelocity[j] > -threshold || imp[j].z == 0.0f;
+			}
+		}
+		else
+		{
+			float4 soft = loadField( V, CF_SOFT, slot );
+			float4 pmass = loadField( V, CF_PMASS, slot );
+			float4 baseField = loadField( V, CF_BASE, slot );
+			normalMass[0] = pmass.x, normalMass[1] = pmass.z;
+			tangentMass[0] = pmass.y, tangentMass[1] = pmass.w;
+			float baseSeparation[2] = { baseField.x, baseField.y };
+			float4 qA = gatherPos( V, idx.x );
+			float4 qB = gatherPos( V, idx.y );
+			Rot dqA, dqB;
+			dqA.c = qA.z, dqA.s = qA.w;
+			dqB.c = qB.z, dqB.s = qB.w;
+			V2 dp = sub( v2( qB.x, qB.y ), v2( qA.x, qA.y ) );
+#pragma unroll
+			for ( int j = 0; j < 2; ++j )
+			{
+				if ( j >= pointCount )
+				{
+					continue;
+				}
+				V2 rA = v2( anc[j].x, anc[j].y );
+				V2 rB = v2( anc[j].z, anc[j].w );
+				V2 ds = add( dp, sub( rotate( dqB, rB ), rotate( dqA, rA ) ) );
+				float sep = baseSeparation[j] + dot( ds, normal );
+				if ( sep > 0.0f )
+				{
+					velocityBias[j] = sep * P.inv_h;
+				}
+				else if ( useBias )
+				{
+					velocityBias[j] = maxf_( soft.y * soft.x * sep, -P.contactSpeed );
+					massScale[j] = soft.y;
+					impulseScale[j] = soft.z;
+				}
+			}
+		}
+
+		// ---- one after the other: the part that reads and writes body velocities
+		const int turns = end - base < 32 ? end - base : 32;
+		for ( int turn = 0; turn < turns; ++turn )
+		{
+			if ( lane == turn && valid )
+			{
+				float4 sA = gatherVel( V, idx.x );
+				float4 sB = gatherVel( V, idx.y );
+				V2 vA = v2( sA.x, sA.y );
+				float wA = sA.z;
+				V2 vB = v2( sB.x, sB.y );
+				float wB = sB.z;
+
+				if ( Op == OV_WARM )
+				{
+#pragma unroll
+					for ( int j = 0; j < 2; ++j )
+					{
+						if ( j >= pointCount )
+						{
+							continue;
+						}
+						V2 rA = v2( anc[j].x, anc[j].y );
+						V2 rB = v2( anc[j].z, anc[j].w );
+						V2 Pv = warmP[j];
+						wA -= iA * cross( rA, Pv );
+						vA = mulAdd( vA, -mA, Pv );
+						wB += iB * cross( rB, Pv );
+						vB = mulAdd( vB, mB, Pv );
+					}
+					wA -= iA * imp[0].w;
+					wB += iB * imp[0].w;
+				}
+				else if ( Op == OV_RESTITUTION )
+				{
+					float restitution = roll.y;
+#pragma unroll
+					for ( int j = 0; j < 2; ++j )
+					{
+						if ( j >= pointCount )
+						{
+							continue;
+						}
+						if ( skipPoint[j] )
+						{
+							continue;
+						}
+						V2 rA = v2( anc[j].x, anc[j].y );
+						V2 rB = v2( anc[j].z, anc[j].w );
+						V2 vrB = add( vB, crossSV( wB, rB ) );
+						V2 vrA = add( vA, crossSV( wA, rA ) );
+						float vn = dot( sub( vrB, vrA ), normal );
+						float impulse = -normalMass[j] * ( vn + restitution * relativeVelocity[j] );
+						float newImpulse = maxf_( imp[j].x + impulse, 0.0f );
+						impulse = newImpulse - imp[j].x;
+						imp[j].x = newImpulse;
+						imp[j].z += impulse;
+						V2 Pv = mulSV( impulse, normal );
+						vA = mulSub( vA, mA, Pv );
+						wA -= iA * cross( rA, Pv );
+						vB = mulAdd( vB, mB, Pv );
+						wB += iB * cross( rB, Pv );
+					}
+				}
+				else
+				{
+					float totalNormalImpulse = 0.0f;
+#pragma unroll
+					for ( int j = 0; j < 2; ++j )
+					{
+						if ( j >= pointCount )
+						{
+							continue;
+						}
+						V2 rA = v2( anc[j].x, anc[j].y );
+						V2 rB = v2( anc[j].z, anc[j].w );
+						V2 vrA = add( vA, crossSV( wA, rA ) );
+						V2 vrB = add( vB, crossSV( wB, rB ) );
+						float vn = dot( sub( vrB, vrA ), normal );
+						float impulse = -normalMass[j] * ( massScale[j] * vn + velocityBias[j] ) - impulseScale[j] * imp[j].x;
+						float newImpulse = maxf_( imp[j].x + impulse, 0.0f );
+						impulse = newImpulse - imp[j].x;
+						imp[j].x = newImpulse;
+						imp[j].z += impulse;
+						totalNormalImpulse += newImpulse;
+						V2 Pv = mulSV( impulse, normal );
+						vA = mulSub( vA, mA, Pv );
+						wA -= iA * cross( rA, Pv );
+						vB = mulAdd( vB, mB, Pv );
+						wB += iB * cross( rB, Pv );
+					}
+					if ( useBias == false )
+					{
+#pragma unroll
+						for ( int j = 0; j < 2; ++j )
+						{
+							if ( j >= pointCount )
+							{
+								continue;
+							}
+							V2 rA = v2( anc[j].x, anc[j].y );
+							V2 rB = v2( anc[j].z, anc[j].w );
+							V2 vrB = add( vB, crossSV( wB, rB ) );
+							V2 vrA = add( vA, crossSV( wA, rA ) );
+							float vt = dot( sub( vrB, vrA ), tangent ) - tangentSpeed;
+							float impulse = tangentMass[j] * ( -vt );
+							float maxFriction = friction * imp[j].x;
+							float newImpulse = clampf_( imp[j].y + impulse, -maxFriction, maxFriction );
+							impulse = newImpulse - imp[j].y;
+							imp[j].y = newImpulse;
+							V2 Pv = mulSV( impulse, tangent );
+							vA = mulSub( vA, mA, Pv );
+							wA -= iA * cross( rA, Pv );
+							vB = mulAdd( vB, mB, Pv );
+							wB += iB * cross( rB, Pv );
+						}
+						{
+							float deltaLambda = -roll.z * ( wB - wA );
+							float lambda = imp[0].w;
+							float maxLambda = roll.x * totalNormalImpulse;
+							imp[0].w = clampf_( lambda + deltaLambda, -maxLambda, maxLambda );
+							deltaLambda = imp[0].w - lambda;
+							wA -= iA * deltaLambda;
+							wB += iB * deltaLambda;
+						}
+					}
+				}
+				scatterVel( V, idx.x, make_float4( vA.x, vA.y, wA, sA.w ) );
+				scatterVel( V, idx.y, make_float4( vB.x, vB.y, wB, sB.w ) );
+			}
+			__syncwarp();
+		}
+
+		// ---- together again
+		if ( valid )
+		{
+			storeField( V, CF_IMP1, slot, imp[0] );
+			storeField( V, CF_IMP2, slot, imp[1] );
+		}
+	}
+}
+
 } // namespace b2g

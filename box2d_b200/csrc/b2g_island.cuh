@@ -945,6 +945,8 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		} );
 	}
 	const int overflowLevelCount = hasOverflow ? overflow.levelCount : 0;
+	// a deep chain of contacts is walked by one warp whose lanes take turns (overflowChainWarp) instead of by one thread
+	const bool chainWalk = overflowLevelCount < 0 && ovJoints == 0;
 	clk.lap( b2GpuStage_prepareConstraints );
 
 	// The stage loops: a colour of a bin keeps only a few warps busy, and every other warp of the block would still walk
@@ -963,9 +965,20 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			blockSync();
 			clk.lap( b2GpuStage_integrateVelocities );
 
-			overflowLevels(
-				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); },
-				[&]( int k ) { warmStartContactOverflow( V, k ); }, blockSync, stageThreads );
+			if ( chainWalk )
+			{
+				if ( threadIdx.x < 32 )
+				{
+					overflowChainWarp<OV_WARM>( P, V, ovCb, ovCe );
+				}
+				blockSync();
+			}
+			else
+			{
+				overflowLevels(
+					overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { warmStartJoint( P, V, jointAt( V, k ) ); },
+					[&]( int k ) { warmStartContactOverflow( V, k ); }, blockSync, stageThreads );
+			}
 			for ( int pass = 0; pass < passes; ++pass )
 			{
 				forEachInLocalColor(
@@ -975,9 +988,20 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			}
 			clk.lap( b2GpuStage_warmStart );
 
-			overflowLevels(
-				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), true ); },
-				[&]( int k ) { solveContactOverflow( P, V, k, true ); }, blockSync, stageThreads );
+			if ( chainWalk )
+			{
+				if ( threadIdx.x < 32 )
+				{
+					overflowChainWarp<OV_SOLVE>( P, V, ovCb, ovCe );
+				}
+				blockSync();
+			}
+			else
+			{
+				overflowLevels(
+					overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), true ); },
+					[&]( int k ) { solveContactOverflow( P, V, k, true ); }, blockSync, stageThreads );
+			}
 			for ( int pass = 0; pass < passes; ++pass )
 			{
 				forEachInLocalColor(
@@ -996,9 +1020,20 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			blockSync();
 			clk.lap( b2GpuStage_integratePositions );
 
-			overflowLevels(
-				overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
-				[&]( int k ) { solveContactOverflow( P, V, k, false ); }, blockSync, stageThreads );
+			if ( chainWalk )
+			{
+				if ( threadIdx.x < 32 )
+				{
+					overflowChainWarp<OV_RELAX>( P, V, ovCb, ovCe );
+				}
+				blockSync();
+			}
+			else
+			{
+				overflowLevels(
+					overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, [&]( int k ) { solveJoint( P, V, jointAt( V, k ), false ); },
+					[&]( int k ) { solveContactOverflow( P, V, k, false ); }, blockSync, stageThreads );
+			}
 			for ( int pass = 0; pass < passes; ++pass )
 			{
 				forEachInLocalColor(
@@ -1011,7 +1046,15 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 
 		if ( anyRestitution != 0 )
 		{
-			if ( ovCe > ovCb )
+			if ( ovCe > ovCb && chainWalk )
+			{
+				if ( threadIdx.x < 32 )
+				{
+					overflowChainWarp<OV_RESTITUTION>( P, V, ovCb, ovCe );
+				}
+				blockSync();
+			}
+			else if ( ovCe > ovCb )
 			{
 				overflowLevels(
 					overflow, overflowLevelCount, true, ovJoints, ovJb, ovCb, []( int ) {}, [&]( int k ) { restitutionContactOverflow( P, V, k ); },
