@@ -72,3 +72,44 @@ def test_perturbed_captures_gpu_equals_oracle(oracle, capture_files, seed):
 				assert np.array_equal(got["hit"], want["hit"]), tag + ": hit bits"
 				assert np.array_equal(got["joint"], want["joint"]), tag + ": joint bits"
 				assert bool(r.hasHitEvents) == bool(r0.hasHitEvents), tag
+
+
+def _drop_joints(cap: b2.Capture) -> None:
+	"""Remove every joint of a capture: what is left of overflow_025 is a dynamic tray that ~20 overflow CONTACTS share --
+	a deep sequential chain with no joints in it (the tumbler's drum in small)."""
+	d = cap.desc
+	for i in range(d.activeColorCount):
+		d.colors[i].jointCount = 0
+	d.overflow.jointCount = 0
+	cap.joints_in = [np.zeros(0, np.uint8) for _ in cap.joints_in]
+	cap.joints_out = [np.zeros(0, np.uint8) for _ in cap.joints_out]
+	cap.color_counts = [(c, 0) for c, _ in cap.color_counts]
+
+
+@pytest.mark.parametrize("blocks", [1, 2, 4])
+def test_deep_overflow_chain_of_contacts(oracle, blocks, monkeypatch):
+	"""The chain is walked by one warp whose lanes take turns (overflowChainWarp); in a cluster its bodies are cached in
+	the first block for the duration of a pass.  Same bits as the oracle's one-after-the-other loop."""
+	if blocks > 1:
+		monkeypatch.setenv("B2GPU_CLUSTER_FORCE", str(blocks))
+	rng = np.random.default_rng(7)
+	with b2.GpuSolver() as solver:
+		for round_ in range(3):
+			cap = b2.Capture(b2.ROOT / "tests" / "golden" / "overflow_025.b2cap.gz")
+			_drop_joints(cap)
+			assert cap.color_counts[-1][0] >= 16 and cap.joint_count == 0
+			if round_ > 0:
+				_perturb(cap, rng)
+			d0, r0, want = cap.make_call()
+			assert oracle.b2OracleSolverStep(ctypes.byref(d0), ctypes.byref(r0)) == 0
+			d, r, got = cap.make_call(islands=True)
+			solver.step(d, r)
+			assert r.gridBarriers == 0, "expected the island-local kernels"
+			bins, per_bin = solver.island_plan()
+			assert per_bin >= blocks
+			tag = f"round {round_} blocks {blocks}"
+			assert np.array_equal(got["states"], want["states"]), tag + ": states"
+			for a, b in zip(got["contacts"], want["contacts"]):
+				assert np.array_equal(a, b), tag + ": contact sims"
+			assert np.array_equal(got["hit"], want["hit"]), tag + ": hit bits"
+			assert bool(r.hasHitEvents) == bool(r0.hasHitEvents), tag
