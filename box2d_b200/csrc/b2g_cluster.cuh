@@ -32,6 +32,8 @@ B2G_DEV int colorOfLocal( const int* localStart, int slotCount, int k )
 
 __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( const __grid_constant__ StepParams P )
 {
+	// launched as a programmatic dependent of the partition kernel: everything below reads what that grid wrote
+	asm volatile( "griddepcontrol.wait;" ::: "memory" );
 	if ( __ldcg( P.binFail ) != 0 )
 	{
 		if ( blockIdx.x == 0 && threadIdx.x == 0 )

@@ -21,6 +21,24 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gStepKernel( const __gri
 		return; // the island kernel solved this step
 	}
 
+	// this block's joints stay in shared memory for the whole step (JointCache, b2g_stages.cuh)
+	extern __shared__ __align__( 16 ) uint8_t gridSmem[];
+	__shared__ JointCache jointCache;
+	if ( threadIdx.x == 0 )
+	{
+		jointCache.base = gridSmem;
+		jointCache.capacity = P.gridJointCache;
+		int slots = 0;
+		for ( int c = 0; c < P.colorCount; ++c )
+		{
+			jointCache.colorBase[c] = slots;
+			slots += jointCacheSlots( P.colors[c].jointCount );
+		}
+		jointCache.colorBase[P.colorCount] = slots;
+	}
+	__syncthreads();
+	const JointCache* cache = P.gridJointCache > 0 ? &jointCache : nullptr;
+
 	unsigned int epoch = 0;
 	const unsigned int blocks = gridDim.x;
 	auto sync = [&]() {
@@ -35,7 +53,7 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gStepKernel( const __gri
 	const bool hasOverflow = P.overflow.contactCount + P.overflow.jointCount > 0;
 	const int colorCount = P.colorCount;
 
-	runStage( P, OP_PREPARE, 0 );
+	runStage( P, OP_PREPARE, 0, cache );
 	sync();
 	clk.lap( b2GpuStage_prepareConstraints );
 
@@ -52,7 +70,7 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gStepKernel( const __gri
 		}
 		for ( int c = 0; c < colorCount; ++c )
 		{
-			runStage( P, OP_WARM, c );
+			runStage( P, OP_WARM, c, cache );
 			sync();
 		}
 		clk.lap( b2GpuStage_warmStart );
@@ -64,7 +82,7 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gStepKernel( const __gri
 		}
 		for ( int c = 0; c < colorCount; ++c )
 		{
-			runStage( P, OP_SOLVE, c );
+			runStage( P, OP_SOLVE, c, cache );
 			sync();
 		}
 		clk.lap( b2GpuStage_solveImpulses );
@@ -80,7 +98,7 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gStepKernel( const __gri
 		}
 		for ( int c = 0; c < colorCount; ++c )
 		{
-			runStage( P, OP_RELAX, c );
+			runStage( P, OP_RELAX, c, cache );
 			sync();
 		}
 		clk.lap( b2GpuStage_relaxImpulses );
@@ -104,7 +122,7 @@ __global__ void __launch_bounds__( kBlockThreads, 1 ) b2gStepKernel( const __gri
 	}
 	clk.lap( b2GpuStage_applyRestitution );
 
-	runStage( P, OP_STORE, 0 );
+	runStage( P, OP_STORE, 0, cache );
 	clk.lap( b2GpuStage_storeImpulses );
 
 	if ( clk.lead )

@@ -183,6 +183,9 @@ struct b2GpuSolver
 	int countersBinCount = 0, countersListCount = 0;
 	int ownerListsOff = 0;		 // steps during which owner lists stay off after a block's share did not fit
 	bool ownerListsEnabled = true; // B2GPU_OWNER_LISTS=0 turns them off
+	size_t downloadQuads = 32 * 1024; // chunk of the pipelined download (B2GPU_DOWNLOAD_KIB)
+	bool gridJointCacheEnabled = true; // B2GPU_GRID_JOINT_CACHE=0: the grid-barrier kernel solves its joints in the global working copy
+	int gridJointCacheMax = 0;		   // joints per block that fit the kernel's shared memory
 	bool dependentLaunch = true;   // B2GPU_PDL=0: the island kernel is launched after the scatter kernel has drained
 	bool flatListsEnabled = true;  // B2GPU_FLAT_LISTS=0: two-phase partition kernel for one block per bin too
 	bool countersClean = false; // the bin counters are all zero (the island kernels zero what they have read)

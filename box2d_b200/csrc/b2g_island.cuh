@@ -64,6 +64,8 @@ B2G_DEV int aggregatedAdd( int* counters, int key, bool active )
 // counters (binBodyCount, binColorStart, binJointStart, binFail) are zeroed by the host before the launch
 __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( const __grid_constant__ StepParams P )
 {
+	// the cluster kernel is launched as a programmatic dependent: its blocks may be set up while this grid is running
+	asm volatile( "griddepcontrol.launch_dependents;" );
 	const unsigned lane = threadIdx.x & 31u;
 	const unsigned blocks = gridDim.x;
 

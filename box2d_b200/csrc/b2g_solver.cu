@@ -109,6 +109,19 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		delete s;
 		return nullptr;
 	}
+	{
+		// the grid-barrier kernel keeps its blocks' joints in shared memory (b2g_stages.cuh, JointCache)
+		const char* cacheEnv = getenv( "B2GPU_GRID_JOINT_CACHE" );
+		s->gridJointCacheEnabled = cacheEnv == nullptr || atoi( cacheEnv ) != 0;
+		int bytes = (int)prop.sharedMemPerBlockOptin - 8 * 1024;
+		bytes = bytes > 192 * 1024 ? 192 * 1024 : bytes;
+		if ( bytes < 0 || cudaFuncSetAttribute( b2g::b2gStepKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes ) != cudaSuccess )
+		{
+			cudaGetLastError();
+			bytes = 0;
+		}
+		s->gridJointCacheMax = bytes / b2g::kJointStride;
+	}
 	// one persistent block per SM: the grid barrier needs every block co-resident
 	s->gridBlocks = s->smCount;
 	const char* gridEnv = getenv( "B2GPU_GRID" );
@@ -147,6 +160,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		s->spillJointsForced = spillEnv != nullptr && atoi( spillEnv ) == 2;
 		const char* ownerEnv = getenv( "B2GPU_OWNER_LISTS" );
 		s->ownerListsEnabled = ownerEnv == nullptr || atoi( ownerEnv ) != 0;
+		const char* chunkEnv = getenv( "B2GPU_DOWNLOAD_KIB" );
+		s->downloadQuads = chunkEnv != nullptr && atoi( chunkEnv ) >= 16 ? (size_t)atoi( chunkEnv ) * 64 : kDownloadQuads;
 		const char* pdlEnv = getenv( "B2GPU_PDL" );
 		s->dependentLaunch = pdlEnv == nullptr || atoi( pdlEnv ) != 0;
 		const char* flatEnv = getenv( "B2GPU_FLAT_LISTS" );
@@ -885,6 +900,17 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	s->overflowJoints = P.overflow.jointCount;
 	P.contactSlots = slot;
 	P.jointCount = joint;
+	{
+		// joints the fullest block (block 0) of the grid-barrier kernel would cache: whole chunks of 32 per colour
+		int slots = 0;
+		for ( int c = 0; c < P.colorCount; ++c )
+		{
+			int chunks = ( P.colors[c].jointCount + 31 ) / 32;
+			slots += 32 * ( ( chunks + s->gridBlocks - 1 ) / s->gridBlocks );
+		}
+		P.gridJointCache = s->gridJointCacheEnabled ? ( slots < s->gridJointCacheMax ? slots : s->gridJointCacheMax ) : 0;
+		P.gridJointsAllCached = P.gridJointCache > 0 && P.gridJointCache >= slots ? 1 : 0;
+	}
 
 	size_t nb = (size_t)bodies;
 	const size_t jointQuads = b2g::kJointStride / 16;
@@ -1063,12 +1089,13 @@ static int b2gLaunchGridKernel( b2GpuSolver* s )
 	cudaError_t err;
 	if ( s->cooperative )
 	{
-		err = cudaLaunchCooperativeKernel( (const void*)b2g::b2gStepKernel, dim3( s->gridBlocks ), dim3( b2g::kBlockThreads ), args, 0,
-										   s->stream );
+		err = cudaLaunchCooperativeKernel( (const void*)b2g::b2gStepKernel, dim3( s->gridBlocks ), dim3( b2g::kBlockThreads ), args,
+										   (size_t)s->params.gridJointCache * b2g::kJointStride, s->stream );
 	}
 	else
 	{
-		err = cudaLaunchKernel( (const void*)b2g::b2gStepKernel, dim3( s->gridBlocks ), dim3( b2g::kBlockThreads ), args, 0, s->stream );
+		err = cudaLaunchKernel( (const void*)b2g::b2gStepKernel, dim3( s->gridBlocks ), dim3( b2g::kBlockThreads ), args,
+								(size_t)s->params.gridJointCache * b2g::kJointStride, s->stream );
 	}
 	if ( err != cudaSuccess )
 	{
@@ -1178,13 +1205,15 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 				config.blockDim = dim3( b2g::kIslandThreads );
 				config.dynamicSmemBytes = s->islandSmemBytes;
 				config.stream = s->stream;
-				cudaLaunchAttribute attribute;
-				attribute.id = cudaLaunchAttributeClusterDimension;
-				attribute.val.clusterDim.x = (unsigned)s->params.clusterSize;
-				attribute.val.clusterDim.y = 1;
-				attribute.val.clusterDim.z = 1;
-				config.attrs = &attribute;
-				config.numAttrs = 1;
+				cudaLaunchAttribute attribute[2];
+				attribute[0].id = cudaLaunchAttributeClusterDimension;
+				attribute[0].val.clusterDim.x = (unsigned)s->params.clusterSize;
+				attribute[0].val.clusterDim.y = 1;
+				attribute[0].val.clusterDim.z = 1;
+				attribute[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+				attribute[1].val.programmaticStreamSerializationAllowed = 1;
+				config.attrs = attribute;
+				config.numAttrs = s->dependentLaunch ? 2 : 1;
 				err = cudaLaunchKernelEx( &config, b2g::b2gClusterIslandKernel, s->params );
 			}
 			else
@@ -1234,7 +1263,8 @@ int b2gEnqueueDownload( b2GpuSolver* s )
 	B2G_CUDA( cudaEventRecord( s->evControl, st ) );
 	s->controlSeen = false;
 	size_t total = s->outTotal;
-	int chunks = (int)( ( total + kDownloadQuads - 1 ) / kDownloadQuads );
+	const size_t chunkQuads = s->downloadQuads;
+	int chunks = (int)( ( total + chunkQuads - 1 ) / chunkQuads );
 	while ( (int)s->chunkEvents.size() < chunks )
 	{
 		cudaEvent_t ev = nullptr;
@@ -1244,8 +1274,8 @@ int b2gEnqueueDownload( b2GpuSolver* s )
 	s->chunkEnd.resize( (size_t)chunks );
 	for ( int i = 0; i < chunks; ++i )
 	{
-		size_t begin = (size_t)i * kDownloadQuads;
-		size_t end = begin + kDownloadQuads < total ? begin + kDownloadQuads : total;
+		size_t begin = (size_t)i * chunkQuads;
+		size_t end = begin + chunkQuads < total ? begin + chunkQuads : total;
 		B2G_CUDA( cudaMemcpyAsync( s->hOut.ptr + begin, s->outAll.ptr + begin, ( end - begin ) * sizeof( float4 ), cudaMemcpyDeviceToHost, st ) );
 		B2G_CUDA( cudaEventRecord( s->chunkEvents[(size_t)i], st ) );
 		s->chunkEnd[(size_t)i] = end;

@@ -229,6 +229,41 @@ B2G_DEV b2lJointSim* jointAt( const SolveView& V, int index )
 	return reinterpret_cast<b2lJointSim*>( V.joints + (size_t)index * kJointStride );
 }
 
+// ---- joints of the grid-barrier kernel, cached by the block that solves them --------------------------------------------
+// forEachInColor gives joint t of a colour to chunk t / 32, i.e. to block (t / 32) % gridDim -- the same thread in every
+// stage of the step.  The persistent kernel therefore keeps the 256-byte records of ITS joints in shared memory for the
+// whole step instead of paying the L2 round trips of their fields (several dependent ones: flags -> branch -> more fields)
+// in each of the ~80 stages; the bodies stay in global memory, they are what the blocks share.  Joints beyond the
+// capacity and the overflow colour's joints stay in the global working copy.
+struct JointCache
+{
+	uint8_t* base; // capacity * kJointStride bytes of shared memory
+	int capacity;
+	int colorBase[kMaxColors + 1]; // first slot of every colour's joints of this block
+};
+
+// slots this block needs for a colour with `jointCount` joints (whole chunks of 32)
+B2G_DEV int jointCacheSlots( int jointCount )
+{
+	int chunks = ( jointCount + 31 ) >> 5;
+	int mine = (int)blockIdx.x < chunks ? ( chunks - (int)blockIdx.x + (int)gridDim.x - 1 ) / (int)gridDim.x : 0;
+	return mine * 32;
+}
+
+// joint t of colour c (this thread owns it): its cached record, or the global working copy
+B2G_DEV b2lJointSim* jointOfColor( const SolveView& V, const JointCache* cache, int c, const ColorRange& color, int t )
+{
+	if ( cache != nullptr )
+	{
+		int local = cache->colorBase[c] + ( ( t >> 5 ) / (int)gridDim.x ) * 32 + ( t & 31 );
+		if ( local < cache->capacity )
+		{
+			return reinterpret_cast<b2lJointSim*>( cache->base + (size_t)local * kJointStride );
+		}
+	}
+	return jointAt( V, color.jointStart + t );
+}
+
 // ---- one stage of the grid-barrier path (view = global memory, wire slot == constraint slot) -----------------------
 B2G_DEV void prepareContactGlobal( const StepParams& P, int slot, bool inRange, bool wide, unsigned lane )
 {
@@ -262,7 +297,7 @@ B2G_DEV void prepareContactGlobal( const StepParams& P, int slot, bool inRange, 
 	}
 }
 
-B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
+B2G_DEV void runStage( const StepParams& P, int op, int colorIndex, const JointCache* cache = nullptr )
 {
 	const SolveView& V = P.g;
 	switch ( op )
@@ -295,9 +330,12 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 			} );
 			// stage the host-prepared joints into the working copy + clear the joint event bit set
 			{
-				int words = P.jointCount * ( kJointStride / 4 );
-				const uint32_t* src = reinterpret_cast<const uint32_t*>( P.rawJoints );
-				uint32_t* dst = reinterpret_cast<uint32_t*>( V.joints );
+				// (when every coloured joint is cached by its block, only the overflow colour's joints need the working copy)
+				const bool allCached = cache != nullptr && cache->capacity >= cache->colorBase[P.colorCount] && P.gridJointsAllCached != 0;
+				int firstWord = allCached ? P.overflow.jointStart * ( kJointStride / 4 ) : 0;
+				int words = P.jointCount * ( kJointStride / 4 ) - firstWord;
+				const uint32_t* src = reinterpret_cast<const uint32_t*>( P.rawJoints ) + firstWord;
+				uint32_t* dst = reinterpret_cast<uint32_t*>( V.joints ) + firstWord;
 				forEachItem( words, [&]( int i ) {
 					if ( i < words )
 					{
@@ -310,6 +348,31 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 						P.jointBits[i] = 0u;
 					}
 				} );
+				if ( cache != nullptr )
+				{
+					// a chunk of 32 joints is 8 KB in a row, in the wire arena and in the cache: the warp copies it as such
+					const int lane = (int)( threadIdx.x & 31u );
+					for ( int c = 0; c < P.colorCount; ++c )
+					{
+						ColorRange color = P.colors[c];
+						forEachItem( color.jointCount, [&]( int t ) {
+							int first = t - lane; // the chunk's first joint
+							int count = color.jointCount - first < 32 ? color.jointCount - first : 32;
+							int local = cache->colorBase[c] + ( ( first >> 5 ) / (int)gridDim.x ) * 32;
+							count = local + count <= cache->capacity ? count : cache->capacity - local; // the rest is not cached
+							const int quads = kJointStride / 16;
+							const float4* from = reinterpret_cast<const float4*>( P.rawJoints + (size_t)( color.jointStart + first ) * kJointStride );
+							float4* to = reinterpret_cast<float4*>( cache->base + (size_t)local * kJointStride );
+							for ( int q = lane; q < count * quads; q += 32 )
+							{
+								// asynchronous copies: the chunks of all colours are in flight together
+								unsigned target = (unsigned)__cvta_generic_to_shared( to + q );
+								asm volatile( "cp.async.cg.shared.global [%0], [%1], 16;" ::"r"( target ), "l"( from + q ) : "memory" );
+							}
+						} );
+					}
+					asm volatile( "cp.async.wait_all;" ::: "memory" );
+				}
 			}
 		}
 		break;
@@ -334,7 +397,8 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 
 		case OP_WARM:
 			forEachInColor(
-				P.colors[colorIndex], [&]( int j ) { warmStartJoint( P, V, jointAt( V, j ) ); },
+				P.colors[colorIndex],
+				[&]( int j ) { warmStartJoint( P, V, jointOfColor( V, cache, colorIndex, P.colors[colorIndex], j - P.colors[colorIndex].jointStart ) ); },
 				[&]( int slot, bool active, unsigned ) {
 					if ( active )
 					{
@@ -347,7 +411,7 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 			forEachInColor(
 				P.colors[colorIndex],
 				[&]( int j ) {
-					b2lJointSim* joint = jointAt( V, j );
+					b2lJointSim* joint = jointOfColor( V, cache, colorIndex, P.colors[colorIndex], j - P.colors[colorIndex].jointStart );
 					solveJoint( P, V, joint, true );
 					jointEventTest( P, joint );
 				},
@@ -361,7 +425,8 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 
 		case OP_RELAX:
 			forEachInColor(
-				P.colors[colorIndex], [&]( int j ) { solveJoint( P, V, jointAt( V, j ), false ); },
+				P.colors[colorIndex],
+				[&]( int j ) { solveJoint( P, V, jointOfColor( V, cache, colorIndex, P.colors[colorIndex], j - P.colors[colorIndex].jointStart ), false ); },
 				[&]( int slot, bool active, unsigned ) {
 					if ( active )
 					{
@@ -447,10 +512,21 @@ B2G_DEV void runStage( const StepParams& P, int op, int colorIndex )
 					storeBody( P, V, i, i + 1 );
 				}
 			} );
-			forEachItem( P.jointCount, [&]( int j ) {
-				if ( j < P.jointCount )
+			// joints colour by colour, by the thread that solved them (its record may live in the block's shared memory)
+			for ( int c = 0; c < P.colorCount; ++c )
+			{
+				ColorRange color = P.colors[c];
+				forEachItem( color.jointCount, [&]( int t ) {
+					if ( t < color.jointCount )
+					{
+						storeJointImpulses( P, color.jointStart + t, jointOfColor( V, cache, c, color, t ) );
+					}
+				} );
+			}
+			forEachItem( P.overflow.jointCount, [&]( int t ) {
+				if ( t < P.overflow.jointCount )
 				{
-					storeJointImpulses( P, j, jointAt( V, j ) );
+					storeJointImpulses( P, P.overflow.jointStart + t, jointAt( V, P.overflow.jointStart + t ) );
 				}
 			} );
 		}

@@ -182,6 +182,10 @@ struct StepParams
 	int* islandFailed;	 // control block: set by the island kernels when they give up (binFail), read by the host
 	int* binFail;		 // set when some bin does not fit its capacities: the grid-barrier kernel takes the step
 
+	// grid-barrier kernel: joints per block it may keep in shared memory for the whole step (b2g_stages.cuh, JointCache)
+	int gridJointCache;
+	int gridJointsAllCached; // the capacity covers the fullest block: no coloured joint needs the global working copy
+
 	// sync + profiling
 	unsigned int* barrier;			 // [0] arrival counter, [1] exit counter
 	unsigned long long* stageCycles; // kStageTimerCount clock64 accumulators, [8] barrier count, [9] total cycles
