@@ -228,6 +228,7 @@ struct b2GpuSolver
 	bool arenaSent = false;			// the whole input arena has been enqueued for upload
 	std::vector<uint8_t> blockSent; // pack blocks whose part of the input arena has been enqueued for upload (b2gPumpUploads)
 	int sendScan = 0;				// every block before this one has been sent
+	int blockItems = 512;			// items per block of the pack / unpack passes of this step (b2gBegin)
 	size_t sendThreshold = 0;		// a run of packed blocks goes out when it is this long (quads)
 	size_t outStates = 0, outImpulses = 0, outJoints = 0, outBits = 0, outTotal = 0;
 
@@ -308,7 +309,7 @@ inline int b2gFindSegment( const std::vector<int>& starts, int flat )
 }
 
 // ---- blocks of host work --------------------------------------------------------------------------------------------
-constexpr int kWorkBlockItems = 512;
+constexpr int kWorkBlockItems = 512; // largest block of the host passes
 constexpr size_t kTransferQuads = 16 * 1024;	  // 256 KiB: the first piece of a pipelined upload; the pieces double up to
 constexpr size_t kTransferQuadsMax = 256 * 1024; // 4 MiB
 constexpr size_t kDownloadQuads = 32 * 1024; // 512 KiB: the unpack pass runs this far behind the download

@@ -160,6 +160,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		s->spillJointsForced = spillEnv != nullptr && atoi( spillEnv ) == 2;
 		const char* ownerEnv = getenv( "B2GPU_OWNER_LISTS" );
 		s->ownerListsEnabled = ownerEnv == nullptr || atoi( ownerEnv ) != 0;
+		// (Tried: write-combined memory for the upload staging buffer -- the device-clock upload time of many_pyramids stayed
+		// at ~192 us, the link is the limit, not snoops.)
 		const char* chunkEnv = getenv( "B2GPU_DOWNLOAD_KIB" );
 		s->downloadQuads = chunkEnv != nullptr && atoi( chunkEnv ) >= 16 ? (size_t)atoi( chunkEnv ) * 64 : kDownloadQuads;
 		const char* pdlEnv = getenv( "B2GPU_PDL" );
@@ -682,9 +684,9 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	return 0;
 }
 
-static int b2gBlocksFor( int itemCount )
+static int b2gBlocksFor( const b2GpuSolver* s, int itemCount )
 {
-	return ( itemCount + kWorkBlockItems - 1 ) / kWorkBlockItems;
+	return ( itemCount + s->blockItems - 1 ) / s->blockItems;
 }
 
 static void b2gResetWork( b2GpuSolver* s, int itemCount, int blockCount )
@@ -985,7 +987,14 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	}
 
 	// pack blocks: the constraints' blocks, then the bodies' blocks (b2gPackBlockRange)
-	b2gResetWork( s, P.bodyCount + s->contactTotal + s->jointTotal, b2gBlocksFor( s->contactTotal + s->jointTotal ) + b2gBlocksFor( P.bodyCount ) );
+	{
+		// blocks of the host passes: ~128 per step so that a small step still spreads evenly over the host's workers and its
+		// first bytes go out early, at most 512 items (a block is claimed with one atomic and ends with a fence)
+		int items = P.bodyCount + s->contactTotal + s->jointTotal;
+		int perBlock = ( items / 128 + 63 ) & ~63;
+		s->blockItems = perBlock < 128 ? 128 : perBlock > kWorkBlockItems ? kWorkBlockItems : perBlock;
+	}
+	b2gResetWork( s, P.bodyCount + s->contactTotal + s->jointTotal, b2gBlocksFor( s, s->contactTotal + s->jointTotal ) + b2gBlocksFor( s, P.bodyCount ) );
 	s->traceBegun = std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count();
 	s->begun = true;
 	return 0;
@@ -1299,7 +1308,7 @@ extern "C" int b2GpuSolverSubmit( b2GpuSolver* s )
 	{
 		return 1;
 	}
-	b2gResetWork( s, b2GpuSolverGetUnpackItemCount( s ), b2gBlocksFor( b2GpuSolverGetUnpackItemCount( s ) ) );
+	b2gResetWork( s, b2GpuSolverGetUnpackItemCount( s ), b2gBlocksFor( s, b2GpuSolverGetUnpackItemCount( s ) ) );
 	return 0;
 }
 

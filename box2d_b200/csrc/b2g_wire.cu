@@ -221,16 +221,16 @@ static void b2gPackBlockRange( const b2GpuSolver* s, int block, int* begin, int*
 {
 	int bodyCount = s->params.bodyCount;
 	int restItems = s->workItems - bodyCount;
-	int restBlocks = ( restItems + kWorkBlockItems - 1 ) / kWorkBlockItems;
+	int restBlocks = ( restItems + s->blockItems - 1 ) / s->blockItems;
 	if ( block < restBlocks )
 	{
-		*begin = bodyCount + block * kWorkBlockItems;
-		*end = *begin + kWorkBlockItems < s->workItems ? *begin + kWorkBlockItems : s->workItems;
+		*begin = bodyCount + block * s->blockItems;
+		*end = *begin + s->blockItems < s->workItems ? *begin + s->blockItems : s->workItems;
 	}
 	else
 	{
-		*begin = ( block - restBlocks ) * kWorkBlockItems;
-		*end = *begin + kWorkBlockItems < bodyCount ? *begin + kWorkBlockItems : bodyCount;
+		*begin = ( block - restBlocks ) * s->blockItems;
+		*end = *begin + s->blockItems < bodyCount ? *begin + s->blockItems : bodyCount;
 	}
 }
 
@@ -238,7 +238,7 @@ static void b2gPackBlockRange( const b2GpuSolver* s, int block, int* begin, int*
 static size_t b2gPackedPrefix( const b2GpuSolver* s, int blocksDone )
 {
 	int restItems = s->contactTotal + s->jointTotal;
-	int restBlocks = ( restItems + kWorkBlockItems - 1 ) / kWorkBlockItems;
+	int restBlocks = ( restItems + s->blockItems - 1 ) / s->blockItems;
 	if ( blocksDone >= s->workBlocks )
 	{
 		return s->inTotal;
@@ -247,7 +247,7 @@ static size_t b2gPackedPrefix( const b2GpuSolver* s, int blocksDone )
 	{
 		return s->inStates; // the three body regions are interleaved by region, not by body: wait for all bodies
 	}
-	int flat = blocksDone * kWorkBlockItems; // constraints [0, flat) are packed, flat < restItems
+	int flat = blocksDone * s->blockItems; // constraints [0, flat) are packed, flat < restItems
 	if ( flat < s->contactTotal )
 	{
 		int k = b2gFindSegment( s->contactStart, flat );
@@ -464,7 +464,7 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 static int b2gPumpUploads( b2GpuSolver* s, bool everything )
 {
 	const int restItems = s->contactTotal + s->jointTotal;
-	const int restBlocks = ( restItems + kWorkBlockItems - 1 ) / kWorkBlockItems;
+	const int restBlocks = ( restItems + s->blockItems - 1 ) / s->blockItems;
 	while ( s->pumpPrefix < s->workBlocks && s->workDone[s->pumpPrefix].load( std::memory_order_acquire ) != 0 )
 	{
 		s->pumpPrefix += 1;
@@ -659,18 +659,28 @@ static int b2gPumpDownloads( b2GpuSolver* s )
 }
 
 // (Tried: each thread unpacks the blocks it packed, so that the b2ContactSim lines it writes are still in its own cache.
-// No measurable gain on the 16-core hosts -- the tail of the unpack pass stayed ~60 us on many_pyramids -- and the
-// search for one's own blocks does not scale to the thousands of blocks of a batch; blocks are claimed in order.)
+// No measurable gain on the 16-core hosts, and the search for one's own blocks does not scale to the thousands of blocks
+// of a batch; blocks are claimed in order.)
+// Whoever waits for output looks after the download events, unless somebody else is already doing that (the pump = 1
+// caller may be in the middle of a block: with a few large blocks per thread the others would wait for it to look up).
+static int b2gTryPumpDownloads( b2GpuSolver* s )
+{
+	if ( s->pumpBusy.exchange( 1, std::memory_order_acquire ) != 0 )
+	{
+		return 0;
+	}
+	int rc = b2gPumpDownloads( s );
+	s->pumpBusy.store( 0, std::memory_order_release );
+	return rc;
+}
+
 extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 {
 	if ( s == nullptr || !s->begun )
 	{
 		return b2gFailMsg( "b2GpuSolverUnpackWork: no step begun" );
 	}
-	if ( pump != 0 )
-	{
-		cudaSetDevice( s->device );
-	}
+	cudaSetDevice( s->device );
 	for ( ;; )
 	{
 		int block = s->workNext.fetch_add( 1, std::memory_order_acq_rel );
@@ -678,20 +688,17 @@ extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 		{
 			break;
 		}
-		int begin = block * kWorkBlockItems;
-		int end = begin + kWorkBlockItems < s->workItems ? begin + kWorkBlockItems : s->workItems;
+		int begin = block * s->blockItems;
+		int end = begin + s->blockItems < s->workItems ? begin + s->blockItems : s->workItems;
 		size_t need = b2gOutPrefix( s, end );
 		while ( s->arrivedQuads.load( std::memory_order_acquire ) < need )
 		{
-			if ( pump != 0 )
+			if ( b2gTryPumpDownloads( s ) != 0 )
 			{
-				if ( b2gPumpDownloads( s ) != 0 )
-				{
-					s->workFailed.store( 1 );
-					return 1;
-				}
+				s->workFailed.store( 1 );
+				return 1;
 			}
-			else if ( s->workFailed.load( std::memory_order_relaxed ) != 0 )
+			if ( s->workFailed.load( std::memory_order_relaxed ) != 0 )
 			{
 				return 1;
 			}
@@ -703,11 +710,25 @@ extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 	{
 		s->traceMarks[5] = std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count();
 		// the tail of the arena (joint event bits) is consumed by EndStep
-		while ( !s->controlSeen || s->chunkNext < s->chunkCount )
+		for ( ;; )
 		{
-			if ( b2gPumpDownloads( s ) != 0 )
+			if ( s->pumpBusy.exchange( 1, std::memory_order_acquire ) == 0 )
 			{
-				s->workFailed.store( 1 );
+				int rc = b2gPumpDownloads( s );
+				bool done = s->controlSeen && s->chunkNext >= s->chunkCount;
+				s->pumpBusy.store( 0, std::memory_order_release );
+				if ( rc != 0 )
+				{
+					s->workFailed.store( 1 );
+					return 1;
+				}
+				if ( done )
+				{
+					break;
+				}
+			}
+			if ( s->workFailed.load( std::memory_order_relaxed ) != 0 )
+			{
 				return 1;
 			}
 			_mm_pause();
