@@ -118,7 +118,19 @@ B2G_DEV void prepareContact( const StepParams& P, const SolveView& V, int wireSl
 {
 	const float4* w = P.wire + (size_t)wireSlot * WR_COUNT;
 	float4 head = w[WR_HEAD];
-	float4 mass = w[WR_MASS];
+	float4 mass;
+	if ( P.massFromBodies != 0 )
+	{
+		// the contact's masses are its bodies' (the pack pass compared them bit for bit); a static body has none
+		int indexA = __float_as_int( head.x ), indexB = __float_as_int( head.y );
+		float4 a = indexA >= 0 ? P.wireBody[2 * (size_t)indexA] : make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+		float4 b = indexB >= 0 ? P.wireBody[2 * (size_t)indexB] : make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+		mass = make_float4( a.x, a.y, b.x, b.y );
+	}
+	else
+	{
+		mass = P.wireMass[wireSlot];
+	}
 	float4 nrm = w[WR_NORMAL];
 	float4 mat = w[WR_MATERIAL];
 	float4 imp = w[WR_IMPULSE];

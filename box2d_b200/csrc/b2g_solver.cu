@@ -925,7 +925,9 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	s->inStates = s->inJoints + jointQuads * joint;
 	s->inBody = s->inStates + 2 * nb;
 	s->inBins = s->inBody + 2 * nb;
-	s->inTotal = s->inBins + ( nb + 3 ) / 4;
+	s->inMass = s->inBins + ( nb + 3 ) / 4; // optional tail: one quad per contact slot, see b2g::WireRow
+	s->inTotal = s->inMass + slot;
+	s->massMismatch.store( 0, std::memory_order_relaxed );
 	s->uploadStarted = false;
 	s->arenaSent = false;
 	// output arena: [states 2/body][impulse records][joint impulse records 3/joint][joint event bits]
@@ -953,6 +955,8 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 
 	P.rawStates = reinterpret_cast<const uint8_t*>( s->wireAll.ptr + s->inStates );
 	P.wireBody = s->wireAll.ptr + s->inBody;
+	P.wireMass = s->wireAll.ptr + s->inMass;
+	P.massFromBodies = 0; // decided when the packing is done (b2gEnqueueUpload)
 	P.wire = s->wireAll.ptr + s->inWire;
 	P.rawJoints = reinterpret_cast<const uint8_t*>( s->wireAll.ptr + s->inJoints );
 	P.g.vel = s->vel.ptr;
@@ -1023,7 +1027,9 @@ static int b2gEnqueueUpload( b2GpuSolver* s )
 	{
 		return 1;
 	}
-	s->lastH2D = s->inTotal * sizeof( float4 );
+	const bool massSent = s->massMismatch.load( std::memory_order_acquire ) != 0;
+	s->params.massFromBodies = massSent ? 0 : 1;
+	s->lastH2D = ( massSent ? s->inTotal : s->inMass ) * sizeof( float4 );
 	s->uploaded = true;
 	return 0;
 }

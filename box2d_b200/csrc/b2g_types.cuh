@@ -3,7 +3,8 @@
 // Wire format (what crosses PCIe, packed by the host side of the C-ABI from the reference's own arrays):
 //     states   b2BodyState[bodyCount]      32 B each, copied as is
 //     wireBody 2 float4 per body           {invMass, invInertia, force.x, force.y} {torque, linDamping, angDamping, gravityScale}
-//     wire     7 float4 per contact slot   the 112 of b2ContactSim's 200 bytes the solver reads (see WireRow); colour c
+//     wire     6 float4 per contact slot   96 of the 112 bytes of b2ContactSim's 200 the solver reads (see WireRow; the
+//                                          masses travel separately and only when they differ from the bodies'); colour c
 //                                          occupies slots [colors[c].contactStart, +contactCount), starts are multiples of 32
 //     joints   b2JointSim[jointCount]      252 B each padded to 256, prepared on the host; solved in place in a working copy
 //
@@ -47,14 +48,18 @@ enum ContactField
 enum WireRow
 {
 	WR_HEAD = 0,	// indexA (int), indexB (int), meta (int: colour<<8 | hitEnable<<2 | pointCount), rollingImpulse
-	WR_MASS = 1,	// invMassA, invIA, invMassB, invIB
-	WR_NORMAL = 2,	// normal.x, normal.y, friction, tangentSpeed
-	WR_MATERIAL = 3, // rollingResistance, restitution, separation1, separation2
-	WR_ANCHOR1 = 4, // anchorA1.xy, anchorB1.xy
-	WR_ANCHOR2 = 5, // anchorA2.xy, anchorB2.xy
-	WR_IMPULSE = 6, // normalImpulse1, tangentImpulse1, normalImpulse2, tangentImpulse2
-	WR_COUNT = 7
+	WR_NORMAL = 1,	// normal.x, normal.y, friction, tangentSpeed
+	WR_MATERIAL = 2, // rollingResistance, restitution, separation1, separation2
+	WR_ANCHOR1 = 3, // anchorA1.xy, anchorB1.xy
+	WR_ANCHOR2 = 4, // anchorA2.xy, anchorB2.xy
+	WR_IMPULSE = 5, // normalImpulse1, tangentImpulse1, normalImpulse2, tangentImpulse2
+	WR_COUNT = 6
 };
+// The seventh row -- invMassA, invIA, invMassB, invIB of b2ContactSim (src/contact.h:103-142) -- has a region of its own at
+// the end of the input arena (StepParams::wireMass).  The reference copies these from the bodies when a contact enters the
+// constraint graph (src/constraint_graph.c, b2AddContactToGraph), so they almost always equal what the body constants
+// already carry; the pack pass checks that bit for bit and the region is only uploaded for a step in which some contact
+// differs (a body whose mass changed under a persisting contact).
 
 constexpr int kMetaPointMask = 3;
 constexpr int kMetaHitEnable = 4;
@@ -133,6 +138,8 @@ struct StepParams
 	const float4* wireBody;
 	const float4* wire;		  // WR_COUNT float4 per slot, AoS
 	const uint8_t* rawJoints; // pristine prepared joints as uploaded
+	const float4* wireMass;	  // [contactSlots] invMassA, invIA, invMassB, invIB of every contact -- valid when massFromBodies == 0
+	int massFromBodies;		  // every contact's masses equal its bodies' (checked by the pack pass): read them from wireBody
 
 	// solver state in global memory (the grid-barrier kernel's view)
 	SolveView g;

@@ -120,6 +120,8 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 	// ---- contacts: the 112 of b2ContactSim's 200 bytes that prepare reads (src/contact_solver.c:1629-1785)
 	{
 		float4* wire = base + s->inWire;
+		float4* wireMass = base + s->inMass;
+		bool massDiffers = false;
 		int flat = ( begin > bodyCount ? begin : bodyCount ) - bodyCount;
 		int flatEnd = ( end - bodyCount < s->contactTotal ? end - bodyCount : s->contactTotal );
 		int k = flat < flatEnd ? b2gFindSegment( s->contactStart, flat ) : 0;
@@ -130,6 +132,7 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 			int local = flat - segFlat;
 			int localEnd = ( flatEnd < s->contactStart[k + 1] ? flatEnd : s->contactStart[k + 1] ) - segFlat;
 			int bodyBase = s->bodySegs[seg.world].base;
+			const uint8_t* worldSims = s->bodySegs[seg.world].sims;
 			for ( int i = local; i < localEnd; ++i )
 			{
 				const uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
@@ -140,12 +143,21 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 				int hitEnable = ( (uint32_t)b2gRdI( sim, B2L_CONTACT_SIM_FLAGS ) & B2L_SIM_ENABLE_HIT_EVENT ) != 0 ? b2g::kMetaHitEnable : 0;
 				int meta = ( seg.colorIndex << b2g::kMetaColorShift ) | hitEnable | ( pointCount & b2g::kMetaPointMask );
 				int indexA = b2gRdI( sim, B2L_CONTACT_INDEX_A ), indexB = b2gRdI( sim, B2L_CONTACT_INDEX_B );
+				{
+					// invMass, invInertia of the two bodies as the contact remembers them vs. as the bodies have them now
+					// (adjacent floats in both structures; bitwise, so that "equal" means the device may use either)
+					static const uint8_t zero[8] = { 0 };
+					const uint8_t* bodyA = indexA >= 0 ? worldSims + (size_t)indexA * B2L_SIM_SIZE + B2L_SIM_INV_MASS : zero;
+					const uint8_t* bodyB = indexB >= 0 ? worldSims + (size_t)indexB * B2L_SIM_SIZE + B2L_SIM_INV_MASS : zero;
+					massDiffers = massDiffers || memcmp( sim + B2L_CONTACT_INV_MASS_A, bodyA, 8 ) != 0 ||
+								  memcmp( sim + B2L_CONTACT_INV_MASS_B, bodyB, 8 ) != 0;
+				}
 				indexA = indexA >= 0 ? indexA + bodyBase : indexA;
 				indexB = indexB >= 0 ? indexB + bodyBase : indexB;
 				float4* w = wire + (size_t)( seg.slotStart + i ) * b2g::WR_COUNT;
 				b2gStream4( w + b2g::WR_HEAD, b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta ),
 							b2gRdF( m, B2L_MANIFOLD_ROLLING_IMPULSE ) );
-				b2gStream4( w + b2g::WR_MASS, b2gRdF( sim, B2L_CONTACT_INV_MASS_A ), b2gRdF( sim, B2L_CONTACT_INV_I_A ),
+				b2gStream4( wireMass + ( seg.slotStart + i ), b2gRdF( sim, B2L_CONTACT_INV_MASS_A ), b2gRdF( sim, B2L_CONTACT_INV_I_A ),
 							b2gRdF( sim, B2L_CONTACT_INV_MASS_B ), b2gRdF( sim, B2L_CONTACT_INV_I_B ) );
 				b2gStream4( w + b2g::WR_NORMAL, b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ),
 							b2gRdF( sim, B2L_CONTACT_FRICTION ), b2gRdF( sim, B2L_CONTACT_TANGENT_SPEED ) );
@@ -173,6 +185,10 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 			}
 			flat = s->contactStart[k + 1];
 			k += 1;
+		}
+		if ( massDiffers )
+		{
+			s->massMismatch.store( 1, std::memory_order_release );
 		}
 	}
 
@@ -285,7 +301,12 @@ int b2gSendArena( b2GpuSolver* s, size_t uptoQuads )
 		return 0; // the pipelined pack pass has sent it piece by piece
 	}
 	s->arenaSent = true;
-	return b2gSendRange( s, 0, uptoQuads );
+	(void)uptoQuads;
+	if ( b2gSendRange( s, 0, s->inMass ) != 0 )
+	{
+		return 1;
+	}
+	return s->massMismatch.load( std::memory_order_acquire ) != 0 ? b2gSendRange( s, s->inMass, s->inTotal ) : 0;
 }
 
 // ---- phase 4: unpack (callable concurrently on disjoint ranges) ---------------------------------------------------------
@@ -510,7 +531,8 @@ static int b2gPumpUploads( b2GpuSolver* s, bool everything )
 	if ( complete && everything )
 	{
 		s->arenaSent = true;
-		return b2gSendRange( s, s->inStates, s->inTotal );
+		// the masses' region only when some contact's differ from its bodies' (b2g::WireRow)
+		return b2gSendRange( s, s->inStates, s->massMismatch.load( std::memory_order_acquire ) != 0 ? s->inTotal : s->inMass );
 	}
 	return 0;
 }

@@ -113,3 +113,32 @@ def test_deep_overflow_chain_of_contacts(oracle, blocks, monkeypatch):
 				assert np.array_equal(a, b), tag + ": contact sims"
 			assert np.array_equal(got["hit"], want["hit"]), tag + ": hit bits"
 			assert bool(r.hasHitEvents) == bool(r0.hasHitEvents), tag
+
+
+def test_contact_masses_that_differ_from_the_bodies(oracle, capture_files):
+	"""b2ContactSim carries its own copy of the bodies' inverse masses (set when the contact enters the graph).  The wire
+	format leaves them out when they equal the bodies' -- the usual case -- and uploads them when any contact differs:
+	both ways must give the oracle's bits, and the second must move more bytes."""
+	with b2.GpuSolver() as solver:
+		for path in capture_files:
+			cap = b2.Capture(path)
+			if cap.contact_count == 0:
+				continue
+			d, r, got = cap.make_call()
+			solver.step(d, r)
+			plain_bytes = int(r.h2dBytes)
+			for arr in cap.contacts_in:
+				if arr.size:
+					c = arr.reshape(-1, b2.CONTACT_SIZE)
+					inv = c[:, 52:68].view(np.float32)  # invMassA, invIA, invMassB, invIB
+					inv[::2] *= np.float32(0.75)
+			d0, r0, want = cap.make_call()
+			assert oracle.b2OracleSolverStep(ctypes.byref(d0), ctypes.byref(r0)) == 0
+			for islands in (True, False):
+				d, r, got = cap.make_call(islands=islands)
+				solver.step(d, r)
+				tag = f"{path.name} islands {islands}"
+				assert np.array_equal(got["states"], want["states"]), tag + ": states"
+				for a, b in zip(got["contacts"], want["contacts"]):
+					assert np.array_equal(a, b), tag + ": contact sims"
+				assert int(r.h2dBytes) > plain_bytes, tag + ": the masses were not uploaded"
