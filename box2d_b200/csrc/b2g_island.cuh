@@ -4,17 +4,20 @@
 // merge the islands of the two bodies, static bodies belong to none), so islands can be solved independently and the
 // colour order only has to be respected INSIDE an island.  The host packs the awake islands into `binCount` bins
 // (b2GpuStepDesc::bodyIsland -> bodyBin); here
-//   * b2gPartitionKernel buckets bodies, contacts and joints by (bin, colour) with atomics (three grid barriers), and
+//   * b2gScatterKernel appends every body and constraint to its bin's list in one flat pass (one block per bin; the
+//     island kernel sorts its list by colour in shared memory), or -- bins shared by a cluster -- b2gPartitionKernel
+//     buckets them by (bin, colour) with atomics and one grid barrier into colour-major lists, and
 //   * b2gIslandKernel gives each bin to ONE thread block that keeps the bin's body state, contact constraints and
-//     joints in shared memory for the whole step and separates colours with __syncthreads() (~10 ns) instead of a
+//     joints in shared memory for the whole step and separates colours with __syncthreads() (~20 ns) instead of a
 //     grid-wide barrier (~1.2 us measured, tools/microbench/barrier_bench.cu).
 // The order of constraints inside a (bin, colour) bucket comes from atomics and is not deterministic, but constraints
 // of one colour touch disjoint dynamic bodies (src/constraint_graph.c:84-133), so every body sees exactly the same
 // sequence of updates as in the reference: results are bit-identical (tests/test_gpu_lockstep.py).  The SIMD-group
 // early-outs of the wide path depend on the reference's array order; they are evaluated in wire order by the
-// partition kernel and travel with the constraint (kMetaGroup* bits).
-// When a bin does not fit its shared-memory budget the partition kernel raises binFail and the grid-barrier kernel
-// (b2g_solver.cu) solves the step instead; the overflow colour (strictly sequential) also uses that kernel.
+// scatter / partition kernel and travel with the constraint (kMetaGroup* bits).
+// When a bin does not fit its shared-memory budget the scatter / partition kernel raises binFail and the grid-barrier
+// kernel (b2g_grid.cuh) solves the step instead.  The overflow colour of a bin (strictly sequential in the reference) is
+// levelised, or -- a deep chain -- walked by one warp whose lanes take turns (overflowChainWarp, b2g_contact.cuh).
 #pragma once
 
 #include "b2g_stages.cuh"
