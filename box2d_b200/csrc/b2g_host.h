@@ -224,6 +224,7 @@ struct b2GpuSolver
 
 	// arena layouts, in float4 units
 	size_t inStates = 0, inBody = 0, inWire = 0, inJoints = 0, inBins = 0, inMass = 0, inTotal = 0;
+	bool checkMasses = true; // this step's pack pass compares the contacts' masses with the bodies'
 	std::atomic<int> massMismatch{ 0 }; // pack pass: some contact's masses differ from its bodies' -> the mass region is uploaded
 	bool uploadStarted = false;		// evUpload recorded (first copy of the step)
 	bool arenaSent = false;			// the whole input arena has been enqueued for upload

@@ -143,6 +143,7 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 				int hitEnable = ( (uint32_t)b2gRdI( sim, B2L_CONTACT_SIM_FLAGS ) & B2L_SIM_ENABLE_HIT_EVENT ) != 0 ? b2g::kMetaHitEnable : 0;
 				int meta = ( seg.colorIndex << b2g::kMetaColorShift ) | hitEnable | ( pointCount & b2g::kMetaPointMask );
 				int indexA = b2gRdI( sim, B2L_CONTACT_INDEX_A ), indexB = b2gRdI( sim, B2L_CONTACT_INDEX_B );
+				if ( s->checkMasses )
 				{
 					// invMass, invInertia of the two bodies as the contact remembers them vs. as the bodies have them now
 					// (adjacent floats in both structures; bitwise, so that "equal" means the device may use either)
