@@ -160,3 +160,27 @@ def test_empty_and_tiny_steps(solver):
 	desc, result, bufs = cap.make_call()
 	solver.step(desc, result)
 	_check(cap, bufs, result)
+
+
+@pytest.mark.parametrize("distortion", ["zero", "half", "tenfold"])
+def test_wrong_island_sizes_only_cost_time(solver, capture_files, distortion):
+	"""b2GpuStepDesc::islandSizes is a sizing hint: counts that are off may make a bin overflow (the device notices, the
+	step is rerun on the grid-barrier kernel) or waste bins, but never change a bit of the result."""
+	import ctypes
+
+	solver.set_mode(0)
+	for path in capture_files:
+		cap = b2.Capture(path)
+		desc, result, bufs = cap.make_call(sizes=True)
+		if "sizes" not in bufs:
+			continue
+		sizes = np.frombuffer(bufs["sizes"], dtype=np.int32).reshape(-1, 4)
+		if distortion == "zero":
+			sizes[:, 0:3] = 0
+		elif distortion == "half":
+			sizes[:, 0:3] //= 2
+		else:
+			sizes[:, 0:3] *= 10
+		assert desc.islandSizes == ctypes.addressof(bufs["sizes"])
+		solver.step(desc, result)
+		_check(cap, bufs, result)
