@@ -488,7 +488,11 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 			forEachInLocalColor(
 				make_int4( localStartJ[c], localStartJ[c + 1], localStartC[c], localStartC[c + 1] ), [&]( int k ) { joint( VA, k ); },
 				[&]( int k ) { contact( VA, k ); } );
-			unsigned done = 0;
+			// ONE warp waits for the announced bytes (a try_wait with cluster-scope acquire carries an L1 invalidation: with all
+			// 16 warps spinning, the CCTL of the idle ones was 30 % of the kernel's stall samples and competed with the warps
+			// that still had constraints to solve); the others go straight to the cluster barrier, which cannot complete before
+			// the waiting warp of every block has arrived
+			unsigned done = threadIdx.x < 32 ? 0u : 1u;
 			for ( int spin = 0; done == 0; ++spin )
 			{
 				asm volatile( "{\n"
