@@ -187,6 +187,7 @@ struct b2GpuSolver
 	bool gridJointCacheEnabled = true; // B2GPU_GRID_JOINT_CACHE=0: the grid-barrier kernel solves its joints in the global working copy
 	int gridJointCacheMax = 0;		   // joints per block that fit the kernel's shared memory
 	bool dependentLaunch = true;   // B2GPU_PDL=0: the island kernel is launched after the scatter kernel has drained
+	bool leveliseEnabled = true;   // B2GPU_LEVELISE=0: jointless bins keep the reference's colours as their stages
 	bool flatListsEnabled = true;  // B2GPU_FLAT_LISTS=0: two-phase partition kernel for one block per bin too
 	bool countersClean = false; // the bin counters are all zero (the island kernels zero what they have read)
 	DeviceBuffer<int2> contactBinRank, jointBinRank;

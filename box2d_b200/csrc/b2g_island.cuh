@@ -747,6 +747,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	}
 
 	const int colorCount = P.colorCount;
+	auto buildColourTable = [&]() {
 	if ( threadIdx.x < 32 )
 	{
 		// one lane per colour slot: offsets of the colours (flat lists: exclusive scan of the counts), then the table of the
@@ -801,9 +802,96 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			stageThreadCount = widest < (int)blockDim.x && P.stageAllThreads == 0 ? widest : (int)blockDim.x;
 		}
 	}
+	};
+	buildColourTable();
 	if ( flat )
 	{
 		__syncthreads(); // the offsets
+	}
+
+	// Levels instead of colours (bins without joints).  The reference's colours are global: a colour stage of this bin must
+	// wait for the previous one even when none of its contacts touches a body of that colour.  What bit-exactness needs is
+	// only that every DYNAMIC BODY sees its contacts in colour order.  So the coloured contacts are levelised like the
+	// overflow colour: walking the colours in order, level( contact ) = 1 + the highest level among the earlier contacts of
+	// its dynamic bodies (kept per body).  Contacts of one level touch disjoint dynamic bodies, a body's contacts have
+	// strictly increasing levels in colour order, hence solving level by level gives every body the reference's sequence
+	// of updates -- in fewer stages (a base-10 pyramid: 7 levels for 8-9 colours).  From here on "colour c" of this bin
+	// means level c + 1.
+	constexpr int kOwnContacts = 3; // contacts per thread kept in registers across the levelisation
+	int ownLevel[kOwnContacts] = { 0, 0, 0 }, ownA[kOwnContacts] = { 0, 0, 0 }, ownB[kOwnContacts] = { 0, 0, 0 };
+	const bool levelise = flat && P.leveliseContacts != 0 && flatJoints == 0 && flatContacts <= kOwnContacts * (int)blockDim.x &&
+						  colorStartC[colorCount] > 0 && (size_t)( bodyCount + 1 ) * sizeof( int ) <= (size_t)CF_COUNT * capC * sizeof( float4 );
+	if ( levelise )
+	{
+		int* bodyLevel = reinterpret_cast<int*>( V.cf ); // scratch: the constraint fields are written by the prepare pass below
+		for ( int i = (int)threadIdx.x; i <= bodyCount; i += (int)blockDim.x )
+		{
+			bodyLevel[i] = 0;
+		}
+		int ownColour[kOwnContacts];
+#pragma unroll
+		for ( int j = 0; j < kOwnContacts; ++j )
+		{
+			int k = (int)threadIdx.x + j * (int)blockDim.x;
+			ownColour[j] = -1;
+			if ( k < flatContacts )
+			{
+				int4 info = __ldg( contactInfo + k );
+				int c = info.w >> kFlatColorShift;
+				ownColour[j] = c < colorCount ? c : -1; // the overflow colour keeps its own bucket and order
+				int localA = info.y >= 0 ? P.bodyLocal[info.y] : 0;
+				int localB = info.z >= 0 ? P.bodyLocal[info.z] : 0;
+				// only dynamic bodies order their contacts (nothing else is written)
+				ownA[j] = ( __float_as_uint( V.vel[localA].w ) & B2L_FLAG_DYNAMIC ) != 0 ? localA : -localA;
+				ownB[j] = ( __float_as_uint( V.vel[localB].w ) & B2L_FLAG_DYNAMIC ) != 0 ? localB : -localB;
+			}
+		}
+		const int overflowContacts = colorStartC[colorCount + 1] - colorStartC[colorCount];
+		__syncthreads();
+		for ( int c = 0; c < colorCount; ++c )
+		{
+			if ( colorStartC[c + 1] == colorStartC[c] )
+			{
+				continue; // colour not present in this bin (uniform for the block)
+			}
+#pragma unroll
+			for ( int j = 0; j < kOwnContacts; ++j )
+			{
+				if ( ownColour[j] == c )
+				{
+					// a dynamic body has at most one contact per colour: nobody else reads or writes these two entries now
+					int la = ownA[j] > 0 ? bodyLevel[ownA[j]] : 0;
+					int lb = ownB[j] > 0 ? bodyLevel[ownB[j]] : 0;
+					int level = 1 + ( la > lb ? la : lb );
+					ownLevel[j] = level;
+					if ( ownA[j] > 0 )
+					{
+						bodyLevel[ownA[j]] = level;
+					}
+					if ( ownB[j] > 0 )
+					{
+						bodyLevel[ownB[j]] = level;
+					}
+				}
+			}
+			__syncthreads();
+		}
+		if ( threadIdx.x < kColorSlots )
+		{
+			flatCursorC[threadIdx.x] = (int)threadIdx.x == colorCount ? overflowContacts : 0;
+		}
+		__syncthreads();
+#pragma unroll
+		for ( int j = 0; j < kOwnContacts; ++j )
+		{
+			if ( ownLevel[j] > 0 )
+			{
+				atomicAdd( &flatCursorC[ownLevel[j] - 1], 1 );
+			}
+		}
+		__syncthreads();
+		buildColourTable(); // the same table, of levels
+		__syncthreads();
 	}
 	const int contactCount = colorStartC[kColorSlots - 1];
 	const int jointCount = colorStartJ[kColorSlots - 1];
@@ -847,17 +935,38 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	// prepare: contacts read the bodies' initial velocities from the view (identical to the wire states here)
 	if ( flat )
 	{
-		forEachLocal( flatContacts, [&]( int k ) {
+		auto prepareOwn = [&]( int k, int bucket, int localA, int localB ) {
 			int4 info = __ldg( contactInfo + k );
 			int c = info.w >> kFlatColorShift;
 			bool wide = c != colorCount;
-			int dest = wide ? atomicAdd( &flatCursorC[c], 1 ) : ovCb + rankAmong( overflowOrder, ovCe - ovCb, info.x );
-			int localA = info.y >= 0 ? P.bodyLocal[info.y] : 0;
-			int localB = info.z >= 0 ? P.bodyLocal[info.z] : 0;
+			int dest = wide ? atomicAdd( &flatCursorC[bucket >= 0 ? bucket : c], 1 ) : ovCb + rankAmong( overflowOrder, ovCe - ovCb, info.x );
+			if ( localA < 0 )
+			{
+				localA = info.y >= 0 ? P.bodyLocal[info.y] : 0;
+				localB = info.z >= 0 ? P.bodyLocal[info.z] : 0;
+			}
 			wireSlot[dest] = info.x;
 			prepareContact( P, V, info.x, dest, localA, localB, V.vel[localA], V.vel[localB], wide,
 							info.w & ( kMetaGroupRolling | kMetaGroupRestitution ) );
-		} );
+		};
+		if ( levelise )
+		{
+			// (the levelisation's scratch lives in the field array: all of it was read before the barrier above)
+#pragma unroll
+			for ( int j = 0; j < kOwnContacts; ++j )
+			{
+				int k = (int)threadIdx.x + j * (int)blockDim.x;
+				if ( k < flatContacts )
+				{
+					int localA = ownA[j] < 0 ? -ownA[j] : ownA[j], localB = ownB[j] < 0 ? -ownB[j] : ownB[j];
+					prepareOwn( k, ownLevel[j] - 1, localA, localB ); // level 0 = an overflow contact: bucket -1, unused
+				}
+			}
+		}
+		else
+		{
+			forEachLocal( flatContacts, [&]( int k ) { prepareOwn( k, -1, -1, -1 ); } );
+		}
 		forEachLocal( flatJoints, [&]( int k ) {
 			int entry = __ldg( jointList + k );
 			int c = entry >> kFlatJointShift, j = entry & kFlatJointMask;

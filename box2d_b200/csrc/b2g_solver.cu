@@ -166,6 +166,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		s->downloadQuads = chunkEnv != nullptr && atoi( chunkEnv ) >= 16 ? (size_t)atoi( chunkEnv ) * 64 : kDownloadQuads;
 		const char* pdlEnv = getenv( "B2GPU_PDL" );
 		s->dependentLaunch = pdlEnv == nullptr || atoi( pdlEnv ) != 0;
+		const char* levelEnv = getenv( "B2GPU_LEVELISE" );
+		s->leveliseEnabled = levelEnv == nullptr || atoi( levelEnv ) != 0;
 		const char* flatEnv = getenv( "B2GPU_FLAT_LISTS" );
 		s->flatListsEnabled = flatEnv == nullptr || atoi( flatEnv ) != 0;
 		const char* resolveEnv = getenv( "B2GPU_RESOLVE" );
@@ -662,6 +664,7 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	P.ownerLists = ownerLists ? 1 : 0;
 	P.jointsSpilled = plan.spillJoints ? 1 : 0;
 	P.listCount = listCount;
+	P.leveliseContacts = s->leveliseEnabled ? 1 : 0;
 	P.flatLists = plan.share == 1 && s->flatListsEnabled && s->resolveContacts && s->jointTotal < ( 1 << b2g::kFlatJointShift ) ? 1 : 0;
 	P.listCapContacts = ownerLists ? capC : capC * plan.share;
 	P.listCapJoints = ownerLists ? capJ : capJ * plan.share;
