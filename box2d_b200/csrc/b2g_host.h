@@ -176,6 +176,7 @@ struct b2GpuSolver
 	// island mode scratch (b2g_island.cuh)
 	DeviceBuffer<int> binCounters; // [binBodyCount | binColorStart | binJointStart | binFail], zeroed every run
 	DeviceBuffer<int> bodyLocal, binBodyList, slotGroupBits, binContactList, binJointList;
+	DeviceBuffer<int2> binJointBodies;
 	DeviceBuffer<int4> binContactInfo;
 	DeviceBuffer<float4> jointWork;
 	double islandHeadRoom = 1.3; // bins are sized for this many times the average bytes per bin

@@ -361,13 +361,16 @@ __global__ void __launch_bounds__( 256 ) b2gScatterKernel( const __grid_constant
 	forEachItem( P.jointCount, [&]( int j ) {
 		bool active = j < P.jointCount;
 		int bin = -1, c = 0;
+		int2 bodies = make_int2( -1, -1 );
 		if ( active )
 		{
 			while ( c < P.colorCount && ( c + 1 < P.colorCount ? P.colors[c + 1].jointStart : P.overflow.jointStart ) <= j )
 			{
 				c += 1;
 			}
-			int body = jointBodyForBin( P.rawJoints + (size_t)j * kJointStride );
+			const int* pair = jointIndexPair( reinterpret_cast<b2lJointSim*>( const_cast<uint8_t*>( P.rawJoints + (size_t)j * kJointStride ) ) );
+			bodies = pair != nullptr ? make_int2( pair[0], pair[1] ) : make_int2( -1, -1 );
+			int body = bodies.x >= 0 ? bodies.x : bodies.y;
 			// a filter joint has no solver data: park it in bin 0, it is a no-op in every stage
 			bin = body < 0 ? 0 : P.bodyBin[body];
 		}
@@ -377,6 +380,7 @@ __global__ void __launch_bounds__( 256 ) b2gScatterKernel( const __grid_constant
 			if ( position < P.binCapJoints )
 			{
 				P.binJointList[(size_t)bin * P.binCapJoints + position] = j | ( c << kFlatJointShift );
+				P.binJointBodies[(size_t)bin * P.binCapJoints + position] = bodies; // for the island kernel's levelisation
 			}
 			else
 			{
@@ -809,18 +813,21 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		__syncthreads(); // the offsets
 	}
 
-	// Levels instead of colours (bins without joints).  The reference's colours are global: a colour stage of this bin must
-	// wait for the previous one even when none of its contacts touches a body of that colour.  What bit-exactness needs is
+	// Levels instead of colours.  The reference's colours are global: a colour stage of this bin must
+	// wait for the previous one even when none of its constraints touches a body of that colour.  What bit-exactness needs is
 	// only that every DYNAMIC BODY sees its contacts in colour order.  So the coloured contacts are levelised like the
 	// overflow colour: walking the colours in order, level( contact ) = 1 + the highest level among the earlier contacts of
 	// its dynamic bodies (kept per body).  Contacts of one level touch disjoint dynamic bodies, a body's contacts have
 	// strictly increasing levels in colour order, hence solving level by level gives every body the reference's sequence
 	// of updates -- in fewer stages (a base-10 pyramid: 7 levels for 8-9 colours).  From here on "colour c" of this bin
 	// means level c + 1.
-	constexpr int kOwnContacts = 3; // contacts per thread kept in registers across the levelisation
+	constexpr int kOwnContacts = 3, kOwnJoints = 2; // constraints per thread kept in registers across the levelisation
 	int ownLevel[kOwnContacts] = { 0, 0, 0 }, ownA[kOwnContacts] = { 0, 0, 0 }, ownB[kOwnContacts] = { 0, 0, 0 };
-	const bool levelise = flat && P.leveliseContacts != 0 && flatJoints == 0 && flatContacts <= kOwnContacts * (int)blockDim.x &&
-						  colorStartC[colorCount] > 0 && (size_t)( bodyCount + 1 ) * sizeof( int ) <= (size_t)CF_COUNT * capC * sizeof( float4 );
+	int ownJointLevel[kOwnJoints] = { 0, 0 };
+	const int2* jointBodies = P.binJointBodies + (size_t)bin * capJ;
+	const bool levelise = flat && P.leveliseContacts != 0 && flatContacts <= kOwnContacts * (int)blockDim.x &&
+						  flatJoints <= kOwnJoints * (int)blockDim.x && colorStartC[colorCount] + colorStartJ[colorCount] > 0 &&
+						  (size_t)( bodyCount + 1 ) * sizeof( int ) <= (size_t)CF_COUNT * capC * sizeof( float4 );
 	if ( levelise )
 	{
 		int* bodyLevel = reinterpret_cast<int*>( V.cf ); // scratch: the constraint fields are written by the prepare pass below
@@ -846,13 +853,52 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 				ownB[j] = ( __float_as_uint( V.vel[localB].w ) & B2L_FLAG_DYNAMIC ) != 0 ? localB : -localB;
 			}
 		}
+		int ownJointColour[kOwnJoints], ownJA[kOwnJoints], ownJB[kOwnJoints];
+#pragma unroll
+		for ( int j = 0; j < kOwnJoints; ++j )
+		{
+			int k = (int)threadIdx.x + j * (int)blockDim.x;
+			ownJointColour[j] = -1;
+			ownJA[j] = ownJB[j] = 0;
+			if ( k < flatJoints )
+			{
+				int c = __ldg( jointList + k ) >> kFlatJointShift;
+				ownJointColour[j] = c < colorCount ? c : -1;
+				int2 bodies = __ldg( jointBodies + k );
+				int localA = bodies.x >= 0 ? P.bodyLocal[bodies.x] : 0;
+				int localB = bodies.y >= 0 ? P.bodyLocal[bodies.y] : 0;
+				ownJA[j] = ( __float_as_uint( V.vel[localA].w ) & B2L_FLAG_DYNAMIC ) != 0 ? localA : 0;
+				ownJB[j] = ( __float_as_uint( V.vel[localB].w ) & B2L_FLAG_DYNAMIC ) != 0 ? localB : 0;
+			}
+		}
 		const int overflowContacts = colorStartC[colorCount + 1] - colorStartC[colorCount];
+		const int overflowJoints = colorStartJ[colorCount + 1] - colorStartJ[colorCount];
 		__syncthreads();
 		for ( int c = 0; c < colorCount; ++c )
 		{
-			if ( colorStartC[c + 1] == colorStartC[c] )
+			if ( colorStartC[c + 1] == colorStartC[c] && colorStartJ[c + 1] == colorStartJ[c] )
 			{
 				continue; // colour not present in this bin (uniform for the block)
+			}
+#pragma unroll
+			for ( int j = 0; j < kOwnJoints; ++j )
+			{
+				if ( ownJointColour[j] == c )
+				{
+					// joints and contacts of one colour touch disjoint dynamic bodies too (one graph colouring for both)
+					int la = ownJA[j] > 0 ? bodyLevel[ownJA[j]] : 0;
+					int lb = ownJB[j] > 0 ? bodyLevel[ownJB[j]] : 0;
+					int level = 1 + ( la > lb ? la : lb );
+					ownJointLevel[j] = level;
+					if ( ownJA[j] > 0 )
+					{
+						bodyLevel[ownJA[j]] = level;
+					}
+					if ( ownJB[j] > 0 )
+					{
+						bodyLevel[ownJB[j]] = level;
+					}
+				}
 			}
 #pragma unroll
 			for ( int j = 0; j < kOwnContacts; ++j )
@@ -879,6 +925,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		if ( threadIdx.x < kColorSlots )
 		{
 			flatCursorC[threadIdx.x] = (int)threadIdx.x == colorCount ? overflowContacts : 0;
+			flatCursorJ[threadIdx.x] = (int)threadIdx.x == colorCount ? overflowJoints : 0;
 		}
 		__syncthreads();
 #pragma unroll
@@ -887,6 +934,14 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			if ( ownLevel[j] > 0 )
 			{
 				atomicAdd( &flatCursorC[ownLevel[j] - 1], 1 );
+			}
+		}
+#pragma unroll
+		for ( int j = 0; j < kOwnJoints; ++j )
+		{
+			if ( ownJointLevel[j] > 0 )
+			{
+				atomicAdd( &flatCursorJ[ownJointLevel[j] - 1], 1 );
 			}
 		}
 		__syncthreads();
@@ -967,12 +1022,28 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		{
 			forEachLocal( flatContacts, [&]( int k ) { prepareOwn( k, -1, -1, -1 ); } );
 		}
-		forEachLocal( flatJoints, [&]( int k ) {
+		auto placeJoint = [&]( int k, int bucket ) {
 			int entry = __ldg( jointList + k );
 			int c = entry >> kFlatJointShift, j = entry & kFlatJointMask;
-			int dest = c != colorCount ? atomicAdd( &flatCursorJ[c], 1 ) : ovJb + rankAmong( overflowOrderJ, ovJe - ovJb, j );
+			int dest = c != colorCount ? atomicAdd( &flatCursorJ[bucket >= 0 ? bucket : c], 1 ) : ovJb + rankAmong( overflowOrderJ, ovJe - ovJb, j );
 			jointIndexOf[dest] = j;
-		} );
+		};
+		if ( levelise )
+		{
+#pragma unroll
+			for ( int j = 0; j < kOwnJoints; ++j )
+			{
+				int k = (int)threadIdx.x + j * (int)blockDim.x;
+				if ( k < flatJoints )
+				{
+					placeJoint( k, ownJointLevel[j] - 1 );
+				}
+			}
+		}
+		else
+		{
+			forEachLocal( flatJoints, [&]( int k ) { placeJoint( k, -1 ); } );
+		}
 	}
 	else
 	{

@@ -254,6 +254,7 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	s->binContactInfo.release();
 	s->jointWork.release();
 	s->binJointList.release();
+	s->binJointBodies.release();
 	s->contactBinRank.release();
 	s->jointBinRank.release();
 	if ( s->control != nullptr )
@@ -646,6 +647,7 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	B2G_CUDA( s->binContactInfo.reserve( (size_t)binCount * capC * share + 1 ) );
 	B2G_CUDA( s->jointBinRank.reserve( (size_t)s->jointTotal + 1 ) );
 	B2G_CUDA( s->binJointList.reserve( (size_t)binCount * capJ * share + 1 ) );
+	B2G_CUDA( s->binJointBodies.reserve( (size_t)binCount * capJ * share + 1 ) );
 
 	P.binCount = binCount;
 	P.capBodies = capB;
@@ -682,6 +684,7 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	P.binContactInfo = s->binContactInfo.ptr;
 	P.jointBinRank = s->jointBinRank.ptr;
 	P.binJointList = s->binJointList.ptr;
+	P.binJointBodies = s->binJointBodies.ptr;
 	s->islandSmemBytes = b2g::islandSharedBytes( capB, capC, capJ, !plan.spillJoints );
 	s->islandMode = true;
 	return 0;

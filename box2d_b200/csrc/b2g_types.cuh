@@ -187,6 +187,7 @@ struct StepParams
 	int4* binContactInfo; // same layout: { wire slot, bin-local body A, bin-local body B, SIMD-group bits }
 	int2* jointBinRank;	 // [jointCount]
 	int* binJointList;	 // [binCount * binCapJoints] joint index, colour-major
+	int2* binJointBodies; // flat lists: the two bodies (wire indices, -1 = static) of every entry of binJointList
 	int* islandFailed;	 // control block: set by the island kernels when they give up (binFail), read by the host
 	int* binFail;		 // set when some bin does not fit its capacities: the grid-barrier kernel takes the step
 
