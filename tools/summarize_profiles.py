@@ -51,9 +51,13 @@ def launch_summary(rnd: str) -> None:
 
 def kernel_summary(rnd: str, name: str, note: str) -> None:
 	rep = OUT / f"{rnd}_{name}.ncu-rep"
-	if not rep.exists():
+	page = OUT / f"{rnd}_{name}.rawpage.csv"  # written on the GPU box by tools/profile_round.sh (the reports are too big to bring back)
+	if page.exists() and page.stat().st_size > 0:
+		raw = page.read_text()
+	elif rep.exists():
+		raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+	else:
 		return
-	raw = subprocess.run(["ncu", "-i", str(rep), "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 	rows = list(csv.reader(io.StringIO(raw)))
 	if len(rows) < 3:
 		return
