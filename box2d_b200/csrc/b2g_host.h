@@ -208,7 +208,7 @@ struct b2GpuSolver
 	bool spillJointsEnabled = false;
 	bool spillJointsForced = false; // B2GPU_SPILL_JOINTS=2 (testing): steps with joints take that plan first
 	bool resolveContacts = true; // diagnostics: B2GPU_RESOLVE=0 makes the island kernels chase head -> bodyLocal themselves
-	bool stageAllThreads = false;
+	int stageAllThreads = false;
 	bool testTightBins = false;			 // testing: B2GPU_TEST_TIGHT_BINS=1 makes every island step fail over to the grid kernel
 	int clusterForce = 0;				 // testing: smallest cluster size the planner may use (B2GPU_CLUSTER_FORCE)
 	int clusterBins[4] = { 0, 0, 0, 0 }; // resident clusters of 2, 4, 8, 16 blocks (0 = not available)

@@ -803,7 +803,15 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		if ( lane == 0 )
 		{
 			passCount = __popc( presentMask );
-			stageThreadCount = widest < (int)blockDim.x && P.stageAllThreads == 0 ? widest : (int)blockDim.x;
+			if ( P.stageAllThreads != 2 )
+			{
+				// ... and for one body each in the two body stages of a sub-step (integrate-positions is a chain of an IEEE
+				// square root and a division: a second round of it costs more than a few more warps at the barriers;
+				// B2GPU_STAGE_ALL=2 sizes by the colours only)
+				int bodies = roundUp32( bodyCount );
+				widest = bodies > widest ? bodies : widest;
+			}
+			stageThreadCount = widest < (int)blockDim.x && P.stageAllThreads != 1 ? widest : (int)blockDim.x;
 		}
 	}
 	};
@@ -1140,8 +1148,8 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	const int passes = passCount;
 	const int stageThreads = stageThreadCount;
 	auto blockSync = [&]() { asm volatile( "bar.sync 1, %0;" ::"r"( stageThreads ) : "memory" ); };
-	// (Tried: a thread per body for the two body stages of a sub-step, the extra warps waiting at a second named barrier
-	// in between.  The wider barriers cost more than the shorter body loops saved: 0.0607 -> 0.0623 ms on many_pyramids.)
+	// (Tried: the extra warps of the body stages waiting at a SECOND named barrier while the colours run: slower than
+	// simply letting them walk the colour loops, 0.0607 -> 0.0623 ms on many_pyramids.)
 	if ( (int)threadIdx.x < stageThreads )
 	{
 		for ( int subStep = 0; subStep < P.subStepCount; ++subStep )

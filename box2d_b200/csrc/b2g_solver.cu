@@ -173,7 +173,7 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		const char* resolveEnv = getenv( "B2GPU_RESOLVE" );
 		s->resolveContacts = resolveEnv == nullptr || atoi( resolveEnv ) != 0;
 		const char* stageEnv = getenv( "B2GPU_STAGE_ALL" );
-		s->stageAllThreads = stageEnv != nullptr && atoi( stageEnv ) != 0;
+		s->stageAllThreads = stageEnv != nullptr ? atoi( stageEnv ) : 0;
 		const char* tightEnv = getenv( "B2GPU_TEST_TIGHT_BINS" );
 		s->testTightBins = tightEnv != nullptr && atoi( tightEnv ) != 0;
 		const char* forceEnv = getenv( "B2GPU_CLUSTER_FORCE" );
@@ -654,7 +654,7 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	P.capContacts = capC;
 	P.capJoints = capJ;
 	P.clusterSize = plan.share;
-	P.stageAllThreads = s->stageAllThreads ? 1 : 0;
+	P.stageAllThreads = s->stageAllThreads;
 	P.resolveContacts = s->resolveContacts ? 1 : 0;
 	P.clusterRun = plan.share > 1 ? plan.capB : 0;
 	P.clusterMagic = plan.share > 1 ? (unsigned)( ( ( 1ull << 32 ) + (unsigned)plan.capB - 1ull ) / (unsigned)plan.capB ) : 0u;
