@@ -95,6 +95,7 @@ class SeamTotals(ctypes.Structure):
 		("kernelMs", ctypes.c_double), ("abiMs", ctypes.c_double), ("h2dBytes", ctypes.c_double), ("d2hBytes", ctypes.c_double),
 		("stageMs", ctypes.c_double * 8),
 		("steps", ctypes.c_longlong), ("launches", ctypes.c_longlong), ("gridBarriers", ctypes.c_longlong),
+		("seamMs", ctypes.c_double), ("packMs", ctypes.c_double), ("waitMs", ctypes.c_double), ("unpackMs", ctypes.c_double),
 	]
 
 
@@ -171,6 +172,8 @@ def solver_lib() -> ctypes.CDLL:
 	lib.b2GpuSolverUnpackWork.argtypes = [ctypes.c_void_p, ctypes.c_int]
 	lib.b2GpuCountIslandSizes.restype = ctypes.c_int
 	lib.b2GpuCountIslandSizes.argtypes = [P(StepDesc), P(IslandSize)]
+	lib.b2GpuSolverGetResidentStats.restype = ctypes.c_int
+	lib.b2GpuSolverGetResidentStats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
 	lib.b2GpuSolverGetIslandPlan.restype = ctypes.c_int
 	lib.b2GpuSolverGetIslandPlan.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
 	_solver_lib = lib
@@ -178,7 +181,7 @@ def solver_lib() -> ctypes.CDLL:
 
 
 def _bind_harness(lib: ctypes.CDLL) -> ctypes.CDLL:
-	"""Prototypes of oracle/harness/b2h_harness.c (linked into every host library variant)."""
+	"""Prototypes of box2d_b200/host/b2h_harness.c (linked into every host library variant)."""
 	lib.b2h_create.restype = ctypes.c_int
 	lib.b2h_create.argtypes = [ctypes.c_char_p, ctypes.c_int]
 	lib.b2h_destroy.argtypes = [ctypes.c_int]
@@ -516,6 +519,13 @@ class GpuSolver:
 		bins, blocks = ctypes.c_int(0), ctypes.c_int(0)
 		self.lib.b2GpuSolverGetIslandPlan(self.handle, ctypes.byref(bins), ctypes.byref(blocks))
 		return bins.value, blocks.value
+
+	def resident_stats(self):
+		"""(full contact records, dirty bodies) of the last step, or None when it did not run in resident mode."""
+		full, dirty = ctypes.c_int(0), ctypes.c_int(0)
+		if self.lib.b2GpuSolverGetResidentStats(self.handle, ctypes.byref(full), ctypes.byref(dirty)) == 0:
+			return None
+		return full.value, dirty.value
 
 	def close(self) -> None:
 		if self.handle:

@@ -226,7 +226,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		{
 			slot = wide ? contactList[listBeginC[c] + offset] : overflowOrder[offset];
 			groupBits = wide ? P.slotGroupBits[slot] : 0;
-			float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+			float4 head = wireHead( P, slot );
 			int indexA = __float_as_int( head.x );
 			int indexB = __float_as_int( head.y );
 			localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;

@@ -107,6 +107,64 @@ B2G_DEV void storeField( const SolveView& V, int field, int slot, float4 value )
 	V.cf[(size_t)field * V.cfStride + slot] = value;
 }
 
+// ---- the wire record of a slot ------------------------------------------------------------------------------
+// Plain mode: WR_COUNT rows per slot in P.wire.  Resident mode (P.light != nullptr, b2g_types.cuh): the slot's light
+// record names the contact id and where the rest lives -- the resident table + the previous step's output record, or
+// a full record of this step.
+
+// WR_HEAD of a slot with the SIMD-group bits in its meta word; pointCount 0 = dead slot
+B2G_DEV float4 wireHead( const StepParams& P, int slot )
+{
+	if ( P.light == nullptr )
+	{
+		return P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+	}
+	float4 L = P.light[slot];
+	int key = __float_as_int( L.x );
+	if ( key < 0 )
+	{
+		return make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
+	}
+	int ref = __float_as_int( L.w );
+	float4 head = ref < 0 ? P.full[(size_t)( ~ref ) * WR_COUNT + WR_HEAD] : P.table[(size_t)( key & kLightIdMask ) * kTableRows + WR_HEAD];
+	head.z = __int_as_float( __float_as_int( head.z ) | ( ( ( key >> kLightGroupShift ) & 3 ) << 3 ) );
+	return head;
+}
+
+// starts the slot's record on its way into L2 (the prepare pass reads it a few barriers later)
+B2G_DEV void prefetchWire( const StepParams& P, int slot )
+{
+	const uint8_t* record;
+	int bytes = WR_COUNT * 16;
+	if ( P.light == nullptr )
+	{
+		record = reinterpret_cast<const uint8_t*>( P.wire + (size_t)slot * WR_COUNT );
+	}
+	else
+	{
+		float4 L = P.light[slot];
+		int key = __float_as_int( L.x ), ref = __float_as_int( L.w );
+		if ( key < 0 )
+		{
+			return;
+		}
+		if ( ref < 0 )
+		{
+			record = reinterpret_cast<const uint8_t*>( P.full + (size_t)( ~ref ) * WR_COUNT );
+		}
+		else
+		{
+			record = reinterpret_cast<const uint8_t*>( P.table + (size_t)( key & kLightIdMask ) * kTableRows );
+			bytes = kTableRows * 16;
+			asm volatile( "prefetch.global.L2 [%0];" ::"l"( P.prevImpulses + (size_t)ref * kImpulseFloats ) );
+		}
+	}
+	for ( int sector = 0; sector < bytes; sector += 32 )
+	{
+		asm volatile( "prefetch.global.L2 [%0];" ::"l"( record + sector ) );
+	}
+}
+
 // ---- prepare ---------------------------------------------------------------------------------------------
 // b2PrepareContactsTask (src/contact_solver.c:1573-1809) per lane; with wide == false it is
 // b2PrepareContacts_Overflow (src/contact_solver.c:24-160): no contact-softening branch.
@@ -116,8 +174,42 @@ B2G_DEV void storeField( const SolveView& V, int field, int slot, float4 value )
 B2G_DEV void prepareContact( const StepParams& P, const SolveView& V, int wireSlot, int slot, int localA, int localB, float4 sA,
 							 float4 sB, bool wide, int groupBits )
 {
-	const float4* w = P.wire + (size_t)wireSlot * WR_COUNT;
-	float4 head = w[WR_HEAD];
+	float4 head, nrm, mat, imp, anchor1, anchor2;
+	if ( P.light == nullptr )
+	{
+		const float4* w = P.wire + (size_t)wireSlot * WR_COUNT;
+		head = w[WR_HEAD];
+		nrm = w[WR_NORMAL];
+		mat = w[WR_MATERIAL];
+		anchor1 = w[WR_ANCHOR1];
+		anchor2 = w[WR_ANCHOR2];
+		imp = w[WR_IMPULSE];
+	}
+	else
+	{
+		float4 L = P.light[wireSlot];
+		int key = __float_as_int( L.x ), ref = __float_as_int( L.w );
+		const float4* w = ref < 0 ? P.full + (size_t)( ~ref ) * WR_COUNT : P.table + (size_t)( key & kLightIdMask ) * kTableRows;
+		head = w[WR_HEAD];
+		nrm = w[WR_NORMAL];
+		mat = w[WR_MATERIAL];
+		anchor1 = w[WR_ANCHOR1];
+		anchor2 = w[WR_ANCHOR2];
+		mat.z = L.y; // this step's separations
+		mat.w = L.z;
+		if ( ref < 0 )
+		{
+			imp = w[WR_IMPULSE];
+		}
+		else
+		{
+			// the device's own output of the previous step (storeContact): what the host would send back
+			const float2* r = reinterpret_cast<const float2*>( P.prevImpulses + (size_t)ref * kImpulseFloats );
+			float2 r0 = r[0], r1 = r[1], r2 = r[2], r3 = r[3];
+			head.w = r0.x;
+			imp = make_float4( r0.y, r1.x, r2.y, r3.x );
+		}
+	}
 	float4 mass;
 	if ( P.massFromBodies != 0 )
 	{
@@ -131,9 +223,6 @@ B2G_DEV void prepareContact( const StepParams& P, const SolveView& V, int wireSl
 	{
 		mass = P.wireMass[wireSlot];
 	}
-	float4 nrm = w[WR_NORMAL];
-	float4 mat = w[WR_MATERIAL];
-	float4 imp = w[WR_IMPULSE];
 	int meta = __float_as_int( head.z );
 	int pointCount = meta & kMetaPointMask;
 
@@ -181,7 +270,7 @@ B2G_DEV void prepareContact( const StepParams& P, const SolveView& V, int wireSl
 	float restitution = mat.y;
 	float rollingImpulse = warmStartScale * head.w;
 
-	float4 anchors[2] = { w[WR_ANCHOR1], w[WR_ANCHOR2] };
+	float4 anchors[2] = { anchor1, anchor2 };
 	float separation[2] = { mat.z, mat.w };
 	float wireNormalImpulse[2] = { imp.x, imp.z };
 	float wireTangentImpulse[2] = { imp.y, imp.w };
@@ -255,32 +344,9 @@ B2G_DEV void prepareContact( const StepParams& P, const SolveView& V, int wireSl
 
 // The reference skips rolling resistance / restitution for a whole SIMD register when all its lanes have none
 // (src/contact_solver.c:2021, :2131).  The default build is SSE2 with 4 lanes, so the test is over aligned groups of
-// 4 consecutive constraints of the colour's array.  Evaluated once per step from the wire order by a full warp
-// (lane == colour-local index modulo 32); the result travels with the constraint in cmeta.
-B2G_DEV int simdGroupBits( const StepParams& P, int wireSlot, bool active, unsigned lane )
-{
-	float rollingResistance = 0.0f, restitution = 0.0f;
-	if ( active )
-	{
-		float4 mat = P.wire[(size_t)wireSlot * WR_COUNT + WR_MATERIAL];
-		rollingResistance = mat.x;
-		restitution = mat.y;
-	}
-	// x == 0 is false for NaN, like _mm_cmpeq_ps (ordered)
-	unsigned rolling = __ballot_sync( 0xffffffffu, !( rollingResistance == 0.0f ) );
-	unsigned bouncy = __ballot_sync( 0xffffffffu, !( restitution == 0.0f ) );
-	unsigned shift = lane & ~3u;
-	int bits = 0;
-	if ( ( ( rolling >> shift ) & 0xFu ) != 0 )
-	{
-		bits |= kMetaGroupRolling;
-	}
-	if ( ( ( bouncy >> shift ) & 0xFu ) != 0 )
-	{
-		bits |= kMetaGroupRestitution;
-	}
-	return bits;
-}
+// 4 consecutive constraints of the colour's array.  The pack pass evaluates it in array order (b2g_wire.cu); the result
+// arrives in the meta word (kMetaGroup*, see wireHead) and travels with the constraint in cmeta.
+constexpr int kMetaGroupMask = kMetaGroupRolling | kMetaGroupRestitution;
 
 // ===========================================================================================================
 // Wide path (coloured contacts)

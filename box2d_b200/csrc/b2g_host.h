@@ -155,7 +155,24 @@ struct b2gJointSeg
 	int world;
 };
 
-// host twin of b2g::jointIndexPair (b2g_joint.cuh)
+// ---- resident mode: host-side shadows of what the device holds (b2g_types.cuh, b2g_resident.cuh) -----------------------
+// One per home (graph colour, index in the colour's array): which contact lives there, the static rows of the record the
+// device has in its table, the impulses it computed last (what the unpack pass wrote into the manifold).  A contact is
+// "clean" when it was at the same home in the previous step and the record the pack pass would send equals this, bit for
+// bit, separations aside.  Homes follow the colour arrays, so both host passes walk the shadows front to back.
+struct b2gShadowContact
+{
+	uint32_t rows[b2g::kTableRows * 4]; // WR_HEAD .. WR_ANCHOR2 with the rolling impulse and the separations zeroed
+	uint32_t impulses[4];				// normalImpulse1, tangentImpulse1, normalImpulse2, tangentImpulse2
+	uint32_t rollingImpulse;
+	int contactId;
+	uint32_t reserved[2];
+};
+
+constexpr int kHomeColors = B2GPU_GRAPH_COLOR_COUNT;
+
+constexpr int kStreamChunk = 16; // records a pack block reserves at a time in the full / dirty-body streams
+
 struct b2GpuSolver
 {
 	int device = 0;
@@ -216,6 +233,30 @@ struct b2GpuSolver
 	bool islandMode = false;
 	int islandsEnabled = 1;
 	int maxSharedOptin = 0;
+
+	// resident mode (single worlds): see b2gShadowContact
+	bool residentEnabled = true; // B2GPU_RESIDENT=0: every step uploads everything (plain wire)
+	bool resident = false;		 // this step
+	bool cacheValid = false;	 // the shadows describe what the device holds (false: the next resident step sends everything)
+	bool cacheUsable = false;	 // ... and this step's pack pass may rely on them
+	int parity = 0;				 // which of the double-buffered arrays this step WRITES (outAll, residentStates)
+	std::vector<b2gShadowContact> shadowContacts; // by home
+	int homeBase[kHomeColors + 1] = { 0 };		   // first home of every graph colour (persistent layout with spare room)
+	int homeCount[kHomeColors] = { 0 };			   // contacts the colour had in the previous resident step
+	int homeSlot[kHomeColors] = { 0 };			   // ... and the slot its array started at
+	int segHome[kHomeColors] = { 0 };			   // this step: home colour of every contact segment
+	std::vector<float4> shadowStates, shadowBody;  // by awake index: what residentStates[in] / residentBody hold
+	int shadowBodyCount = 0;
+	DeviceBuffer<float4> table, residentStates[2], residentBody, outOther, fullStream, dirtyStream;
+	PinnedBuffer<float4> hFull, hDirty;
+	std::atomic<int> fullCursor{ 0 }, dirtyCursor{ 0 }; // records handed out in the two streams (whole chunks)
+	int fullCapacity = 0, dirtyCapacity = 0;
+	size_t prevOutImpulses = 0; // where the previous step's impulse records start in ITS output arena (quads)
+	int homeTotal = 0;
+	int wireQuads = b2g::WR_COUNT; // quads per contact slot in the input arena: WR_COUNT, or 1 (light records)
+	int fullSent = 0, dirtySent = 0;
+	std::atomic<int> streamOverflow{ 0 };
+	std::atomic<int> fullCount{ 0 }, dirtyCount{ 0 }; // records actually written (statistics)
 
 	// page-locked staging owned by the library.  The input staging is written with non-temporal stores: on the
 	// target hosts a DMA read of lines that sit dirty in several cores' caches runs at ~6 GB/s instead of ~53 GB/s

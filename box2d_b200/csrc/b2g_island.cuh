@@ -69,7 +69,6 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 {
 	// the cluster kernel is launched as a programmatic dependent: its blocks may be set up while this grid is running
 	asm volatile( "griddepcontrol.launch_dependents;" );
-	const unsigned lane = threadIdx.x & 31u;
 	const unsigned blocks = gridDim.x;
 
 	// phase 1: local index of every body in its bin, (bin, rank) of every constraint, SIMD-group bits in wire order.
@@ -130,11 +129,11 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 		float4 head = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
 		if ( inRange )
 		{
-			head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+			head = wireHead( P, slot );
 		}
 		// dead slots (padding between the segments of a batch) have pointCount 0 and are not placed in any bin
 		bool active = inRange && ( __float_as_int( head.z ) & kMetaPointMask ) != 0;
-		int bits = simdGroupBits( P, slot, active && !isOverflow, lane );
+		int bits = isOverflow ? 0 : __float_as_int( head.z ) & kMetaGroupMask;
 		int key = -1;
 		int bin = 0;
 		if ( active )
@@ -245,7 +244,7 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 		float4 head = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
 		if ( inRange )
 		{
-			head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+			head = wireHead( P, slot );
 		}
 		if ( inRange && ( __float_as_int( head.z ) & kMetaPointMask ) != 0 )
 		{
@@ -298,7 +297,6 @@ __global__ void __launch_bounds__( 256 ) b2gScatterKernel( const __grid_constant
 	// programmatic dependent launch: the island kernel's blocks may be set up on the SMs while this grid is still running;
 	// they wait (griddepcontrol.wait) for this grid to complete before they read anything
 	asm volatile( "griddepcontrol.launch_dependents;" );
-	const unsigned lane = threadIdx.x & 31u;
 	forEachItem( P.jointWords, [&]( int i ) {
 		if ( i < P.jointWords )
 		{
@@ -334,11 +332,11 @@ __global__ void __launch_bounds__( 256 ) b2gScatterKernel( const __grid_constant
 		float4 head = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
 		if ( inRange )
 		{
-			head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+			head = wireHead( P, slot );
 		}
 		// dead slots (padding between the segments of a batch) have pointCount 0 and are not placed in any bin
 		bool active = inRange && ( __float_as_int( head.z ) & kMetaPointMask ) != 0;
-		int bits = simdGroupBits( P, slot, active && !isOverflow, lane );
+		int bits = isOverflow ? 0 : __float_as_int( head.z ) & kMetaGroupMask;
 		int indexA = __float_as_int( head.x ), indexB = __float_as_int( head.y );
 		int bin = active ? P.bodyBin[indexA >= 0 ? indexA : indexB] : -1;
 		int position = aggregatedAdd( P.binColorStart, bin * kColorSlots, active );
@@ -705,12 +703,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			int c = info.w >> kFlatColorShift;
 			atomicAdd( &flatCursorC[c], 1 );
 			// the wire record is read by the prepare pass, two block-wide barriers from here: start it on its way
-			const uint8_t* record = reinterpret_cast<const uint8_t*>( P.wire + (size_t)info.x * WR_COUNT );
-#pragma unroll
-			for ( int sector = 0; sector < WR_COUNT * 16; sector += 32 )
-			{
-				asm volatile( "prefetch.global.L2 [%0];" ::"l"( record + sector ) );
-			}
+			prefetchWire( P, info.x );
 			if ( c == P.colorCount )
 			{
 				overflowOrder[atomicAdd( &flatOverflowCount[0], 1 )] = info.x;
@@ -1067,7 +1060,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			{
 				slot = wide ? contactList[k] : overflowOrder[k - ovCb];
 				groupBits = wide ? P.slotGroupBits[slot] : 0;
-				float4 head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+				float4 head = wireHead( P, slot );
 				int indexA = __float_as_int( head.x );
 				int indexB = __float_as_int( head.y );
 				localA = indexA >= 0 ? P.bodyLocal[indexA] : 0;

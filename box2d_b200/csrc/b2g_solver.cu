@@ -9,6 +9,7 @@
 
 #include "b2g_cluster.cuh"
 #include "b2g_grid.cuh"
+#include "b2g_resident.cuh"
 
 #include <cuda_runtime.h>
 
@@ -164,6 +165,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		// at ~192 us, the link is the limit, not snoops.)
 		const char* chunkEnv = getenv( "B2GPU_DOWNLOAD_KIB" );
 		s->downloadQuads = chunkEnv != nullptr && atoi( chunkEnv ) >= 16 ? (size_t)atoi( chunkEnv ) * 64 : kDownloadQuads;
+		const char* residentEnv = getenv( "B2GPU_RESIDENT" );
+		s->residentEnabled = residentEnv == nullptr || atoi( residentEnv ) != 0;
 		const char* pdlEnv = getenv( "B2GPU_PDL" );
 		s->dependentLaunch = pdlEnv == nullptr || atoi( pdlEnv ) != 0;
 		const char* levelEnv = getenv( "B2GPU_LEVELISE" );
@@ -246,6 +249,15 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	s->cmeta.release();
 	s->hWire.release();
 	s->hOut.release();
+	s->table.release();
+	s->residentStates[0].release();
+	s->residentStates[1].release();
+	s->residentBody.release();
+	s->outOther.release();
+	s->fullStream.release();
+	s->dirtyStream.release();
+	s->hFull.release();
+	s->hDirty.release();
 	s->binCounters.release();
 	s->bodyLocal.release();
 	s->binBodyList.release();
@@ -310,6 +322,23 @@ extern "C" int b2GpuSolverGetIslandPlan( const b2GpuSolver* s, int* binCount, in
 		*blocksPerBin = bins > 0 ? s->params.clusterSize : 0;
 	}
 	return bins;
+}
+
+extern "C" int b2GpuSolverGetResidentStats( const b2GpuSolver* s, int* fullContacts, int* dirtyBodies )
+{
+	if ( s == nullptr || !s->resident )
+	{
+		return 0;
+	}
+	if ( fullContacts != nullptr )
+	{
+		*fullContacts = s->fullCount.load( std::memory_order_relaxed );
+	}
+	if ( dirtyBodies != nullptr )
+	{
+		*dirtyBodies = s->dirtyCount.load( std::memory_order_relaxed );
+	}
+	return 1;
 }
 
 struct b2gBinPlan
@@ -922,15 +951,24 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 
 	size_t nb = (size_t)bodies;
 	const size_t jointQuads = b2g::kJointStride / 16;
-	// input arena: [contacts 7/slot][joints 16/joint][states 2/body][packed sims 2/body][bins 1/4 body].  The pipelined
-	// pack pass (b2GpuSolverPackWork) works through it in address order -- constraints first, the three body regions
-	// last -- so that a finished prefix of its blocks is a prefix of the arena and the upload can start with the first
-	// megabyte of contacts.
+	// Resident mode (single worlds, b2g_types.cuh): the arena carries a 16-byte light record per slot instead of the
+	// 96-byte wire record and no body regions; full records and dirty bodies travel in two streams of their own.
+	s->resident = s->residentEnabled && worldCount == 1 && slot < b2g::kLightIdMask / 4;
+	if ( !s->resident )
+	{
+		s->cacheValid = false; // a plain step reuses the arenas the resident copies live in
+	}
+	s->wireQuads = s->resident ? 1 : b2g::WR_COUNT;
+	const size_t bodyQuads = s->resident ? 0 : 2;
+	// input arena: [contacts 6/slot or 1/slot][joints 16/joint][states 2/body][packed sims 2/body][bins 1/4 body].  The
+	// pipelined pack pass (b2GpuSolverPackWork) works through it in address order -- constraints first, the three body
+	// regions last -- so that a finished prefix of its blocks is a prefix of the arena and the upload can start with the
+	// first megabyte of contacts.
 	s->inWire = 0;
-	s->inJoints = s->inWire + (size_t)b2g::WR_COUNT * slot;
+	s->inJoints = s->inWire + (size_t)s->wireQuads * slot;
 	s->inStates = s->inJoints + jointQuads * joint;
-	s->inBody = s->inStates + 2 * nb;
-	s->inBins = s->inBody + 2 * nb;
+	s->inBody = s->inStates + bodyQuads * nb;
+	s->inBins = s->inBody + bodyQuads * nb;
 	s->inMass = s->inBins + ( nb + 3 ) / 4; // optional tail: one quad per contact slot, see b2g::WireRow
 	s->inTotal = s->inMass + slot;
 	// A batch packs colour slot by colour slot across all worlds: looking up the bodies of every contact there would stream
@@ -963,12 +1001,116 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	// the SoA field stride follows cidx's capacity so that all per-slot arrays grow together
 	size_t slotCapacity = s->cidx.capacity;
 	B2G_CUDA( s->cf.reserve( slotCapacity * b2g::CF_COUNT ) );
+	if ( s->resident )
+	{
+		// the persistent copies: growing one of them loses its contents, the step then sends everything
+		auto persistent = [&]( DeviceBuffer<float4>& buffer, size_t count ) -> cudaError_t {
+			if ( count > buffer.capacity )
+			{
+				s->cacheValid = false;
+			}
+			return buffer.reserve( count );
+		};
+		// Homes: every graph colour owns a region of the table whose place does not change from step to step, so that a
+		// contact keeps its home as long as it keeps its place in its colour's array.  The regions have spare room; when a
+		// colour outgrows its region everything is laid out again (and sent again).  The key of a segment is its graph
+		// colour index when the descriptor's indices are what the reference produces (ascending, overflow last), else its
+		// ordinal.
+		{
+			bool ordered = true;
+			int last = -1;
+			for ( const b2gContactSeg& seg : s->contactSegs )
+			{
+				int index = seg.colorIndex;
+				ordered = ordered && ( seg.wide ? index > last && index < kHomeColors - 1 : index == kHomeColors - 1 );
+				last = seg.wide ? index : last;
+			}
+			bool fits = true;
+			int ordinal = 0;
+			for ( size_t k = 0; k < s->contactSegs.size(); ++k )
+			{
+				const b2gContactSeg& seg = s->contactSegs[k];
+				int key = !seg.wide ? kHomeColors - 1 : ordered ? seg.colorIndex : ordinal++;
+				s->segHome[k] = key;
+				fits = fits && seg.count <= s->homeBase[key + 1] - s->homeBase[key];
+			}
+			if ( !fits )
+			{
+				int need[kHomeColors] = { 0 };
+				for ( size_t k = 0; k < s->contactSegs.size(); ++k )
+				{
+					need[s->segHome[k]] = s->contactSegs[k].count;
+				}
+				int base = 0;
+				for ( int key = 0; key < kHomeColors; ++key )
+				{
+					int have = s->homeBase[key + 1] - s->homeBase[key]; // (of the old layout: read before it is overwritten below)
+					int room = need[key] > have ? need[key] + need[key] / 2 + 64 : have;
+					need[key] = room;
+				}
+				for ( int key = 0; key < kHomeColors; ++key )
+				{
+					s->homeBase[key] = base;
+					base += need[key];
+					s->homeCount[key] = 0;
+				}
+				s->homeBase[kHomeColors] = base;
+				s->cacheValid = false;
+			}
+			s->homeTotal = s->homeBase[kHomeColors];
+		}
+		B2G_CUDA( persistent( s->table, (size_t)( s->homeTotal + 1 ) * b2g::kTableRows ) );
+		B2G_CUDA( persistent( s->residentStates[0], 2 * nb + 2 ) );
+		B2G_CUDA( persistent( s->residentStates[1], 2 * nb + 2 ) );
+		B2G_CUDA( persistent( s->residentBody, 2 * nb + 2 ) );
+		s->fullCapacity = ( slot + kStreamChunk ) & ~( kStreamChunk - 1 );
+		s->dirtyCapacity = ( bodies + kStreamChunk ) & ~( kStreamChunk - 1 );
+		// every pack block may leave one chunk partly used
+		int packBlocks = ( bodies + s->contactTotal + s->jointTotal ) / 128 + 2;
+		s->fullCapacity += packBlocks * kStreamChunk;
+		s->dirtyCapacity += packBlocks * kStreamChunk;
+		B2G_CUDA( s->fullStream.reserve( (size_t)s->fullCapacity * b2g::WR_COUNT ) );
+		B2G_CUDA( s->hFull.reserve( (size_t)s->fullCapacity * b2g::WR_COUNT ) );
+		B2G_CUDA( s->dirtyStream.reserve( (size_t)s->dirtyCapacity * b2g::kDirtyBodyQuads ) );
+		B2G_CUDA( s->hDirty.reserve( (size_t)s->dirtyCapacity * b2g::kDirtyBodyQuads ) );
+		s->fullCursor.store( 0, std::memory_order_relaxed );
+		s->dirtyCursor.store( 0, std::memory_order_relaxed );
+		s->fullSent = s->dirtySent = 0;
+		s->streamOverflow.store( 0, std::memory_order_relaxed );
+		s->fullCount.store( 0, std::memory_order_relaxed );
+		s->dirtyCount.store( 0, std::memory_order_relaxed );
+		if ( s->shadowContacts.size() < (size_t)s->homeTotal + 1 )
+		{
+			s->shadowContacts.resize( (size_t)s->homeTotal + 1, b2gShadowContact{} );
+		}
+		if ( s->shadowStates.size() < 2 * nb + 2 )
+		{
+			s->shadowStates.resize( 2 * nb + 2 + nb );
+			s->shadowBody.resize( 2 * nb + 2 + nb );
+		}
+		if ( !s->cacheValid )
+		{
+			s->shadowBodyCount = 0;
+		}
+	}
+	// the shadows are trusted by this step's pack pass only; they count again once the step has ended (b2gEnd)
+	s->cacheUsable = s->resident && s->cacheValid;
+	s->cacheValid = false;
 
-	P.rawStates = reinterpret_cast<const uint8_t*>( s->wireAll.ptr + s->inStates );
-	P.wireBody = s->wireAll.ptr + s->inBody;
+	P.rawStates = reinterpret_cast<const uint8_t*>( s->resident ? s->residentStates[0].ptr : s->wireAll.ptr + s->inStates );
+	P.wireBody = s->resident ? s->residentBody.ptr : s->wireAll.ptr + s->inBody;
 	P.wireMass = s->wireAll.ptr + s->inMass;
 	P.massFromBodies = 0; // decided when the packing is done (b2gEnqueueUpload)
 	P.wire = s->wireAll.ptr + s->inWire;
+	P.light = s->resident ? s->wireAll.ptr + s->inWire : nullptr;
+	P.table = s->table.ptr;
+	P.full = s->fullStream.ptr;
+	P.prevImpulses = s->outOther.ptr != nullptr ? reinterpret_cast<const float*>( s->outOther.ptr + s->prevOutImpulses ) : nullptr;
+	P.residentOut = s->resident ? reinterpret_cast<uint8_t*>( s->residentStates[1].ptr ) : nullptr;
+	P.residentStates = s->residentStates[0].ptr;
+	P.residentBody = s->residentBody.ptr;
+	P.dirtyBodies = s->dirtyStream.ptr;
+	P.dirtyBodyCapacity = 0; // decided when the packing is done
 	P.rawJoints = reinterpret_cast<const uint8_t*>( s->wireAll.ptr + s->inJoints );
 	P.g.vel = s->vel.ptr;
 	P.g.pos = s->pos.ptr;
@@ -1041,7 +1183,33 @@ static int b2gEnqueueUpload( b2GpuSolver* s )
 	const bool massSent = s->massMismatch.load( std::memory_order_acquire ) != 0;
 	s->params.massFromBodies = massSent ? 0 : 1;
 	s->lastH2D = ( massSent ? s->inTotal : s->inMass ) * sizeof( float4 );
+	if ( s->resident )
+	{
+		s->params.dirtyBodyCapacity = s->dirtySent;
+		s->lastH2D += ( (size_t)s->fullSent * b2g::WR_COUNT + (size_t)s->dirtySent * b2g::kDirtyBodyQuads ) * sizeof( float4 );
+	}
 	s->uploaded = true;
+	return 0;
+}
+
+// resident mode, after the step's kernels: the static rows of the step's full records go into the table (b2g_resident.cuh)
+static int b2gEnqueueCommit( b2GpuSolver* s )
+{
+	if ( !s->resident || s->fullSent == 0 )
+	{
+		return 0;
+	}
+	int rows = s->params.contactSlots * b2g::kTableRows;
+	int blocks = ( rows + 255 ) / 256;
+	blocks = blocks < 1 ? 1 : blocks > s->smCount * 8 ? s->smCount * 8 : blocks;
+	b2g::b2gCommitKernel<<<blocks, 256, 0, s->stream>>>( s->params );
+	cudaError_t err = cudaGetLastError();
+	if ( err != cudaSuccess )
+	{
+		return b2gFail( "b2gCommitKernel launch", err );
+	}
+	s->lastLaunches += 1;
+	s->launchCount += 1;
 	return 0;
 }
 
@@ -1187,6 +1355,19 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 	s->lastLaunches = 0;
 	B2G_CUDA( cudaMemsetAsync( s->control, 0, sizeof( ControlBlock ), s->stream ) );
 	B2G_CUDA( cudaEventRecord( s->evStart, s->stream ) );
+	if ( s->resident && s->params.dirtyBodyCapacity > 0 )
+	{
+		// bodies the host touched since the last step overwrite their resident copies first (b2g_resident.cuh)
+		int blocks = ( s->params.dirtyBodyCapacity + 255 ) / 256;
+		blocks = blocks > s->smCount * 8 ? s->smCount * 8 : blocks;
+		b2g::b2gApplyBodiesKernel<<<blocks, 256, 0, s->stream>>>( s->params );
+		cudaError_t applyErr = cudaGetLastError();
+		if ( applyErr != cudaSuccess )
+		{
+			return b2gFail( "b2gApplyBodiesKernel launch", applyErr );
+		}
+		s->lastLaunches += 1;
+	}
 	if ( s->mode == 0 )
 	{
 		void* args[] = { (void*)&s->params };
@@ -1310,7 +1491,8 @@ int b2gEnqueueDownload( b2GpuSolver* s )
 	s->chunkNext = 0;
 	s->arrivedQuads.store( 0, std::memory_order_release );
 	s->lastD2H = total * sizeof( float4 ) + sizeof( ControlBlock );
-	return 0;
+	// behind the download, off the host's critical path
+	return b2gEnqueueCommit( s );
 }
 
 extern "C" int b2GpuSolverSubmit( b2GpuSolver* s )
@@ -1443,6 +1625,24 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 	s->tracePump.clear();
 	s->traceArrivals.clear();
 	s->begun = false;
+	if ( s->resident && s->ran && s->workFailed.load() == 0 )
+	{
+		// this step's outputs are the next step's resident inputs
+		std::swap( s->outAll, s->outOther );
+		std::swap( s->residentStates[0], s->residentStates[1] );
+		s->prevOutImpulses = s->outImpulses;
+		s->shadowBodyCount = s->params.bodyCount;
+		for ( int key = 0; key < kHomeColors; ++key )
+		{
+			s->homeCount[key] = 0;
+		}
+		for ( size_t k = 0; k < s->contactSegs.size(); ++k )
+		{
+			s->homeCount[s->segHome[k]] = s->contactSegs[k].count;
+			s->homeSlot[s->segHome[k]] = s->contactSegs[k].slotStart;
+		}
+		s->cacheValid = true;
+	}
 	return 0;
 }
 

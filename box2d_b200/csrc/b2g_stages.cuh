@@ -165,8 +165,18 @@ B2G_DEV void integratePositions( const StepParams& P, const SolveView& V, int i 
 B2G_DEV void storeBody( const StepParams& P, const SolveView& V, int body, int local )
 {
 	float4* out = reinterpret_cast<float4*>( P.outStates + (size_t)body * B2L_STATE_SIZE );
-	out[0] = V.vel[local];
+	float4 v = V.vel[local];
+	out[0] = v;
 	out[1] = V.pos[local];
+	if ( P.residentOut != nullptr )
+	{
+		// what the host's state will be when the next step begins, unless somebody touches the body in between (the pack
+		// pass checks): b2FinalizeBodiesTask resets the deltas and clears the transient flags (src/solver.c:611-612, :632)
+		float4* next = reinterpret_cast<float4*>( P.residentOut + (size_t)body * B2L_STATE_SIZE );
+		v.w = __uint_as_float( __float_as_uint( v.w ) & ~B2L_FLAG_TRANSIENT );
+		next[0] = v;
+		next[1] = make_float4( 0.0f, 0.0f, 1.0f, 0.0f );
+	}
 }
 
 // {v, w} of a body as the prepare stage needs it, straight from the wire states (0 for the static dummy)
@@ -270,11 +280,12 @@ B2G_DEV void prepareContactGlobal( const StepParams& P, int slot, bool inRange, 
 	float4 head = make_float4( 0.0f, 0.0f, 0.0f, 0.0f );
 	if ( inRange )
 	{
-		head = P.wire[(size_t)slot * WR_COUNT + WR_HEAD];
+		head = wireHead( P, slot );
 	}
 	// dead slots (padding between the segments of a batch) have pointCount 0
 	bool active = inRange && ( __float_as_int( head.z ) & kMetaPointMask ) != 0;
-	int groupBits = wide ? simdGroupBits( P, slot, active, lane ) : 0;
+	int groupBits = wide ? __float_as_int( head.z ) & kMetaGroupMask : 0;
+	(void)lane;
 	if ( active )
 	{
 		int indexA = __float_as_int( head.x );

@@ -67,6 +67,22 @@ constexpr int kMetaGroupRolling = 8;	   // some lane of this constraint's SIMD g
 constexpr int kMetaGroupRestitution = 16; // ... has restitution
 constexpr int kMetaColorShift = 8;
 
+// ---- resident mode (single worlds): the device keeps what does not change from step to step ------------------------------
+// Every contact has a HOME: (graph colour, index in the colour's array) mapped into a table that keeps its layout from
+// step to step (the colours' regions have spare room, see b2gBegin).  The pack pass compares every contact with a
+// host-side shadow of what the device holds at its home and every body with what came back from the previous step.
+// Per step and contact slot only a 16-byte LIGHT record is uploaded: { key, separation1, separation2, ref }.  A contact
+// whose record is unchanged but for its separations -- the reference's recycled manifolds, src/physics_world.c:508-560 --
+// is read from the resident TABLE (static rows, by home) and its warm-start impulses from the previous step's own output
+// records (ref = its slot in that step); anything else -- a re-evaluated manifold, a contact that is new at its home
+// after a swap-remove (src/constraint_graph.c:198-211) -- travels as a FULL record (ref = ~index into the step's full
+// stream) and is copied into the table after the solve.
+//   key  bits 0..27 home, bit 28/29 the SIMD-group bits (kMetaGroup*), negative = dead slot
+constexpr int kLightIdMask = ( 1 << 28 ) - 1;
+constexpr int kLightGroupShift = 28; // key >> 28 & 3 -> kMetaGroupRolling | kMetaGroupRestitution after << 3
+constexpr int kTableRows = 5;		 // WR_HEAD .. WR_ANCHOR2 of a contact, by home
+constexpr int kDirtyBodyQuads = 5;	 // { body index, -, -, - }, the b2BodyState (2 quads), the packed constants (2 quads)
+
 struct ColorRange
 {
 	int contactStart; // slot of the colour's first contact (multiple of 32)
@@ -140,6 +156,17 @@ struct StepParams
 	const uint8_t* rawJoints; // pristine prepared joints as uploaded
 	const float4* wireMass;	  // [contactSlots] invMassA, invIA, invMassB, invIB of every contact -- valid when massFromBodies == 0
 	int massFromBodies;		  // every contact's masses equal its bodies' (checked by the pack pass): read them from wireBody
+
+	// resident mode (light != nullptr): `wire` is unused, rawStates / wireBody point at the resident body arrays
+	const float4* light;		// [contactSlots] { key, separation1, separation2, ref }
+	float4* table;				// [homes * kTableRows] static rows of the contacts, by home
+	const float4* full;			// the step's full records (WR_COUNT rows each)
+	const float* prevImpulses;	// the previous step's impulse records (kImpulseFloats per slot of THAT step)
+	uint8_t* residentOut;		// [bodyCount] b2BodyState the next step starts from: this step's v, w, flags with the deltas reset
+	float4* residentStates;		// writable aliases of rawStates / wireBody for the apply pass (dirty bodies)
+	float4* residentBody;
+	const float4* dirtyBodies;	// [dirtyBodyCapacity * kDirtyBodyQuads] bodies whose state or constants the host changed
+	int dirtyBodyCapacity;
 
 	// solver state in global memory (the grid-barrier kernel's view)
 	SolveView g;

@@ -78,16 +78,52 @@ static inline void b2gStreamCopy( float4* dst, const uint8_t* src, int quads )
 	}
 }
 
+// A pack block's window into one of the two variable-length streams of resident mode (full contact records, dirty
+// bodies): whole chunks of kStreamChunk records are reserved from the shared cursor, so blocks packed concurrently never
+// contend for a record and a stream is one dense prefix [0, cursor) when the packing is done.
+struct b2gStreamChunk
+{
+	std::atomic<int>* cursor;
+	int capacity;
+	int next, end;
+	std::atomic<int>* failed;
+	int taken = 0;
+};
+
+static inline int b2gStreamTake( b2gStreamChunk& chunk )
+{
+	if ( chunk.next == chunk.end )
+	{
+		chunk.next = chunk.cursor->fetch_add( kStreamChunk, std::memory_order_relaxed );
+		chunk.end = chunk.next + kStreamChunk;
+		if ( chunk.end > chunk.capacity )
+		{
+			// only a caller that packs in ranges far smaller than the blocks b2gBegin planned for can get here (the streams
+			// hold every record plus a chunk per planned block): the step fails at Submit
+			chunk.failed->store( 1, std::memory_order_relaxed );
+			chunk.next = 0;
+			chunk.end = kStreamChunk;
+		}
+	}
+	chunk.taken += 1;
+	return chunk.next++;
+}
+
 extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 {
 	int bodyCount = s->params.bodyCount;
 	float4* base = s->hWire.ptr;
 
-	// ---- bodies: the state as is + the 32 of b2BodySim's 96 bytes that integrate-velocities reads (src/solver.c:94-102)
+	// ---- bodies: the state as is + the 32 of b2BodySim's 96 bytes that integrate-velocities reads (src/solver.c:94-102).
+	// Resident mode: only the bodies whose state or constants differ from what the device holds (the shadows) travel, as
+	// records of the dirty-body stream.
 	{
 		float4* wireStates = base + s->inStates;
 		float4* wireBody = base + s->inBody;
 		int* wireBins = reinterpret_cast<int*>( base + s->inBins );
+		const bool resident = s->resident;
+		const int known = s->cacheUsable ? s->shadowBodyCount : 0;
+		b2gStreamChunk dirty = { &s->dirtyCursor, s->dirtyCapacity, 0, 0, &s->streamOverflow };
 		int i = begin;
 		int bodyEnd = end < bodyCount ? end : bodyCount;
 		int w = i < bodyEnd ? b2gFindSegment( s->bodyStart, i ) : 0;
@@ -106,14 +142,41 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 					label = label >= 0 && label < seg.islandCount ? label : 0;
 					_mm_stream_si32( wireBins + i, s->islandBin[seg.islandBase + label] );
 				}
-				b2gStreamCopy( wireStates + 2 * (size_t)i, seg.states + (size_t)local * B2L_STATE_SIZE, 2 );
+				const uint8_t* state = seg.states + (size_t)local * B2L_STATE_SIZE;
 				const uint8_t* sim = seg.sims + (size_t)local * B2L_SIM_SIZE;
-				b2gStream4( wireBody + 2 * (size_t)i + 0, b2gRdF( sim, B2L_SIM_INV_MASS ), b2gRdF( sim, B2L_SIM_INV_INERTIA ),
-							b2gRdF( sim, B2L_SIM_FORCE ), b2gRdF( sim, B2L_SIM_FORCE + 4 ) );
-				b2gStream4( wireBody + 2 * (size_t)i + 1, b2gRdF( sim, B2L_SIM_TORQUE ), b2gRdF( sim, B2L_SIM_LINEAR_DAMPING ),
-							b2gRdF( sim, B2L_SIM_ANGULAR_DAMPING ), b2gRdF( sim, B2L_SIM_GRAVITY_SCALE ) );
+				alignas( 16 ) float constants[8] = { b2gRdF( sim, B2L_SIM_INV_MASS ),		 b2gRdF( sim, B2L_SIM_INV_INERTIA ),
+													 b2gRdF( sim, B2L_SIM_FORCE ),			 b2gRdF( sim, B2L_SIM_FORCE + 4 ),
+													 b2gRdF( sim, B2L_SIM_TORQUE ),			 b2gRdF( sim, B2L_SIM_LINEAR_DAMPING ),
+													 b2gRdF( sim, B2L_SIM_ANGULAR_DAMPING ), b2gRdF( sim, B2L_SIM_GRAVITY_SCALE ) };
+				if ( !resident )
+				{
+					b2gStreamCopy( wireStates + 2 * (size_t)i, state, 2 );
+					b2gStreamCopy( wireBody + 2 * (size_t)i, reinterpret_cast<const uint8_t*>( constants ), 2 );
+					continue;
+				}
+				float4* shadowState = s->shadowStates.data() + 2 * (size_t)i;
+				float4* shadowBody = s->shadowBody.data() + 2 * (size_t)i;
+				if ( i < known && memcmp( shadowState, state, B2L_STATE_SIZE ) == 0 && memcmp( shadowBody, constants, 32 ) == 0 )
+				{
+					continue; // the device has exactly this
+				}
+				memcpy( shadowBody, constants, 32 );
+				float4* record = s->hDirty.ptr + (size_t)b2gStreamTake( dirty ) * b2g::kDirtyBodyQuads;
+				b2gStream4( record, b2gIntBits( i ), 0.0f, 0.0f, 0.0f );
+				b2gStreamCopy( record + 1, state, 2 );
+				b2gStreamCopy( record + 3, reinterpret_cast<const uint8_t*>( constants ), 2 );
 			}
 			w += 1;
+		}
+		if ( dirty.taken > 0 )
+		{
+			s->dirtyCount.fetch_add( dirty.taken, std::memory_order_relaxed );
+		}
+		// the unused tail of the last chunk: records the apply pass skips
+		while ( dirty.next < dirty.end )
+		{
+			b2gStream4( s->hDirty.ptr + (size_t)dirty.next * b2g::kDirtyBodyQuads, b2gIntBits( -1 ), 0.0f, 0.0f, 0.0f );
+			dirty.next += 1;
 		}
 	}
 
@@ -121,6 +184,9 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 	{
 		float4* wire = base + s->inWire;
 		float4* wireMass = base + s->inMass;
+		const bool resident = s->resident;
+		const bool usable = s->cacheUsable;
+		b2gStreamChunk full = { &s->fullCursor, s->fullCapacity, 0, 0, &s->streamOverflow };
 		bool massDiffers = false;
 		int flat = ( begin > bodyCount ? begin : bodyCount ) - bodyCount;
 		int flatEnd = ( end - bodyCount < s->contactTotal ? end - bodyCount : s->contactTotal );
@@ -133,6 +199,12 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 			int localEnd = ( flatEnd < s->contactStart[k + 1] ? flatEnd : s->contactStart[k + 1] ) - segFlat;
 			int bodyBase = s->bodySegs[seg.world].base;
 			const uint8_t* worldSims = s->bodySegs[seg.world].sims;
+			int groupOf = -1, groupBits = 0;
+			// resident mode: the segment's homes, how many of them were occupied in the previous step and where they were then
+			const int homeKey = resident ? s->segHome[k] : 0;
+			const int homeBase = resident ? s->homeBase[homeKey] : 0;
+			const int homeCount = resident && usable ? s->homeCount[homeKey] : 0;
+			const int homeSlot = resident ? s->homeSlot[homeKey] : 0;
 			for ( int i = local; i < localEnd; ++i )
 			{
 				const uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
@@ -142,6 +214,21 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 				int pointCount = b2gRdI( m, B2L_MANIFOLD_POINT_COUNT );
 				int hitEnable = ( (uint32_t)b2gRdI( sim, B2L_CONTACT_SIM_FLAGS ) & B2L_SIM_ENABLE_HIT_EVENT ) != 0 ? b2g::kMetaHitEnable : 0;
 				int meta = ( seg.colorIndex << b2g::kMetaColorShift ) | hitEnable | ( pointCount & b2g::kMetaPointMask );
+				if ( seg.wide && ( i >> 2 ) != groupOf )
+				{
+					// The reference skips rolling resistance / restitution for a whole SIMD register when all its lanes have none
+					// (src/contact_solver.c:2021, :2131; 4 lanes in the default build): the test is over the aligned group of 4
+					// contacts of the colour's array this one belongs to.  x == 0 is false for NaN, like _mm_cmpeq_ps.
+					groupOf = i >> 2;
+					groupBits = 0;
+					int groupEnd = 4 * groupOf + 4 < seg.count ? 4 * groupOf + 4 : seg.count;
+					for ( int j = 4 * groupOf; j < groupEnd; ++j )
+					{
+						const uint8_t* other = seg.sims + (size_t)j * B2L_CONTACT_SIZE;
+						groupBits |= !( b2gRdF( other, B2L_CONTACT_ROLLING_RESISTANCE ) == 0.0f ) ? b2g::kMetaGroupRolling : 0;
+						groupBits |= !( b2gRdF( other, B2L_CONTACT_RESTITUTION ) == 0.0f ) ? b2g::kMetaGroupRestitution : 0;
+					}
+				}
 				int indexA = b2gRdI( sim, B2L_CONTACT_INDEX_A ), indexB = b2gRdI( sim, B2L_CONTACT_INDEX_B );
 				if ( s->checkMasses )
 				{
@@ -155,33 +242,79 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 				}
 				indexA = indexA >= 0 ? indexA + bodyBase : indexA;
 				indexB = indexB >= 0 ? indexB + bodyBase : indexB;
-				float4* w = wire + (size_t)( seg.slotStart + i ) * b2g::WR_COUNT;
-				b2gStream4( w + b2g::WR_HEAD, b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta ),
-							b2gRdF( m, B2L_MANIFOLD_ROLLING_IMPULSE ) );
-				b2gStream4( wireMass + ( seg.slotStart + i ), b2gRdF( sim, B2L_CONTACT_INV_MASS_A ), b2gRdF( sim, B2L_CONTACT_INV_I_A ),
+				const int slot = seg.slotStart + i;
+				b2gStream4( wireMass + slot, b2gRdF( sim, B2L_CONTACT_INV_MASS_A ), b2gRdF( sim, B2L_CONTACT_INV_I_A ),
 							b2gRdF( sim, B2L_CONTACT_INV_MASS_B ), b2gRdF( sim, B2L_CONTACT_INV_I_B ) );
-				b2gStream4( w + b2g::WR_NORMAL, b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ),
-							b2gRdF( sim, B2L_CONTACT_FRICTION ), b2gRdF( sim, B2L_CONTACT_TANGENT_SPEED ) );
-				b2gStream4( w + b2g::WR_MATERIAL, b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ), b2gRdF( sim, B2L_CONTACT_RESTITUTION ),
-							b2gRdF( p0, B2L_MP_SEPARATION ), b2gRdF( p1, B2L_MP_SEPARATION ) );
-				b2gStream4( w + b2g::WR_ANCHOR1, b2gRdF( p0, B2L_MP_ANCHOR_A ), b2gRdF( p0, B2L_MP_ANCHOR_A + 4 ),
-							b2gRdF( p0, B2L_MP_ANCHOR_B ), b2gRdF( p0, B2L_MP_ANCHOR_B + 4 ) );
-				b2gStream4( w + b2g::WR_ANCHOR2, b2gRdF( p1, B2L_MP_ANCHOR_A ), b2gRdF( p1, B2L_MP_ANCHOR_A + 4 ),
-							b2gRdF( p1, B2L_MP_ANCHOR_B ), b2gRdF( p1, B2L_MP_ANCHOR_B + 4 ) );
-				b2gStream4( w + b2g::WR_IMPULSE, b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ),
-							b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ) );
+				const float separation0 = b2gRdF( p0, B2L_MP_SEPARATION ), separation1 = b2gRdF( p1, B2L_MP_SEPARATION );
+				const float rollingImpulse = b2gRdF( m, B2L_MANIFOLD_ROLLING_IMPULSE );
+				if ( !resident )
+				{
+					float4* w = wire + (size_t)slot * b2g::WR_COUNT;
+					b2gStream4( w + b2g::WR_HEAD, b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta | groupBits ), rollingImpulse );
+					b2gStream4( w + b2g::WR_NORMAL, b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ),
+								b2gRdF( sim, B2L_CONTACT_FRICTION ), b2gRdF( sim, B2L_CONTACT_TANGENT_SPEED ) );
+					b2gStream4( w + b2g::WR_MATERIAL, b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ), b2gRdF( sim, B2L_CONTACT_RESTITUTION ),
+								separation0, separation1 );
+					b2gStream4( w + b2g::WR_ANCHOR1, b2gRdF( p0, B2L_MP_ANCHOR_A ), b2gRdF( p0, B2L_MP_ANCHOR_A + 4 ),
+								b2gRdF( p0, B2L_MP_ANCHOR_B ), b2gRdF( p0, B2L_MP_ANCHOR_B + 4 ) );
+					b2gStream4( w + b2g::WR_ANCHOR2, b2gRdF( p1, B2L_MP_ANCHOR_A ), b2gRdF( p1, B2L_MP_ANCHOR_A + 4 ),
+								b2gRdF( p1, B2L_MP_ANCHOR_B ), b2gRdF( p1, B2L_MP_ANCHOR_B + 4 ) );
+					b2gStream4( w + b2g::WR_IMPULSE, b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ),
+								b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ) );
+					continue;
+				}
+				// resident mode: the record the device would need, against the record it has
+				alignas( 16 ) float rows[b2g::kTableRows * 4] = {
+					b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta ), 0.0f,
+					b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ), b2gRdF( sim, B2L_CONTACT_FRICTION ), b2gRdF( sim, B2L_CONTACT_TANGENT_SPEED ),
+					b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ), b2gRdF( sim, B2L_CONTACT_RESTITUTION ), 0.0f, 0.0f,
+					b2gRdF( p0, B2L_MP_ANCHOR_A ), b2gRdF( p0, B2L_MP_ANCHOR_A + 4 ), b2gRdF( p0, B2L_MP_ANCHOR_B ), b2gRdF( p0, B2L_MP_ANCHOR_B + 4 ),
+					b2gRdF( p1, B2L_MP_ANCHOR_A ), b2gRdF( p1, B2L_MP_ANCHOR_A + 4 ), b2gRdF( p1, B2L_MP_ANCHOR_B ), b2gRdF( p1, B2L_MP_ANCHOR_B + 4 ) };
+				alignas( 16 ) float impulses[4] = { b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ),
+													b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ) };
+				const int id = b2gRdI( sim, B2L_CONTACT_ID );
+				const int home = homeBase + i;
+				b2gShadowContact& shadow = s->shadowContacts[(size_t)home];
+				const bool clean = i < homeCount && shadow.contactId == id && memcmp( shadow.rows, rows, sizeof( rows ) ) == 0 &&
+								   memcmp( shadow.impulses, impulses, sizeof( impulses ) ) == 0 &&
+								   memcmp( &shadow.rollingImpulse, &rollingImpulse, 4 ) == 0;
+				int ref = homeSlot + i; // its record among the previous step's outputs
+				if ( !clean )
+				{
+					int entry = b2gStreamTake( full );
+					ref = ~entry;
+					float4* w = s->hFull.ptr + (size_t)entry * b2g::WR_COUNT;
+					b2gStream4( w + b2g::WR_HEAD, rows[0], rows[1], rows[2], rollingImpulse );
+					b2gStream4( w + b2g::WR_NORMAL, rows[4], rows[5], rows[6], rows[7] );
+					b2gStream4( w + b2g::WR_MATERIAL, rows[8], rows[9], separation0, separation1 );
+					b2gStream4( w + b2g::WR_ANCHOR1, rows[12], rows[13], rows[14], rows[15] );
+					b2gStream4( w + b2g::WR_ANCHOR2, rows[16], rows[17], rows[18], rows[19] );
+					b2gStream4( w + b2g::WR_IMPULSE, impulses[0], impulses[1], impulses[2], impulses[3] );
+					memcpy( shadow.rows, rows, sizeof( rows ) );
+					memcpy( shadow.impulses, impulses, sizeof( impulses ) );
+					memcpy( &shadow.rollingImpulse, &rollingImpulse, 4 );
+					shadow.contactId = id;
+				}
+				b2gStream4( wire + slot, b2gIntBits( home | ( ( groupBits >> 3 ) << b2g::kLightGroupShift ) ), separation0, separation1, b2gIntBits( ref ) );
 			}
 			if ( localEnd == seg.count )
 			{
 				// dead slots between this segment and the next (segments start on multiples of 4 slots): a zero head
-				// (pointCount 0) is all the kernels look at
+				// (pointCount 0) -- resident mode: a negative key -- is all the kernels look at
 				int segEnd = seg.slotStart + seg.count;
 				int next = (size_t)k + 1 < s->contactSegs.size() ? s->contactSegs[(size_t)k + 1].slotStart : segEnd;
 				int limit = ( segEnd + 3 ) & ~3;
 				next = next < limit ? next : limit;
 				for ( int dead = segEnd; dead < next; ++dead )
 				{
-					_mm_stream_ps( reinterpret_cast<float*>( wire + (size_t)dead * b2g::WR_COUNT + b2g::WR_HEAD ), _mm_setzero_ps() );
+					if ( resident )
+					{
+						b2gStream4( wire + dead, b2gIntBits( -1 ), 0.0f, 0.0f, 0.0f );
+					}
+					else
+					{
+						_mm_stream_ps( reinterpret_cast<float*>( wire + (size_t)dead * b2g::WR_COUNT + b2g::WR_HEAD ), _mm_setzero_ps() );
+					}
 				}
 			}
 			flat = s->contactStart[k + 1];
@@ -190,6 +323,10 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		if ( massDiffers )
 		{
 			s->massMismatch.store( 1, std::memory_order_release );
+		}
+		if ( full.taken > 0 )
+		{
+			s->fullCount.fetch_add( full.taken, std::memory_order_relaxed );
 		}
 	}
 
@@ -269,7 +406,7 @@ static size_t b2gPackedPrefix( const b2GpuSolver* s, int blocksDone )
 	{
 		int k = b2gFindSegment( s->contactStart, flat );
 		int slot = s->contactSegs[k].slotStart + ( flat - s->contactStart[k] );
-		return s->inWire + (size_t)slot * b2g::WR_COUNT;
+		return s->inWire + (size_t)slot * s->wireQuads;
 	}
 	return s->inJoints + (size_t)( flat - s->contactTotal ) * ( b2g::kJointStride / 16 );
 }
@@ -294,6 +431,33 @@ static int b2gSendRange( b2GpuSolver* s, size_t fromQuads, size_t uptoQuads )
 	return 0;
 }
 
+// resident mode: the two variable-length streams, once the packing is done (dense prefixes of their staging buffers)
+static int b2gSendStreams( b2GpuSolver* s )
+{
+	if ( !s->resident )
+	{
+		return 0;
+	}
+	if ( s->streamOverflow.load( std::memory_order_relaxed ) != 0 )
+	{
+		return b2gFailMsg( "b2GpuSolverPackRange: packed in ranges too small for the planned streams" );
+	}
+	int full = s->fullCursor.load( std::memory_order_acquire ), dirty = s->dirtyCursor.load( std::memory_order_acquire );
+	full = full < s->fullCapacity ? full : s->fullCapacity;
+	dirty = dirty < s->dirtyCapacity ? dirty : s->dirtyCapacity;
+	if ( full > 0 )
+	{
+		B2G_CUDA( cudaMemcpyAsync( s->fullStream.ptr, s->hFull.ptr, (size_t)full * b2g::WR_COUNT * sizeof( float4 ), cudaMemcpyHostToDevice, s->stream ) );
+	}
+	if ( dirty > 0 )
+	{
+		B2G_CUDA( cudaMemcpyAsync( s->dirtyStream.ptr, s->hDirty.ptr, (size_t)dirty * b2g::kDirtyBodyQuads * sizeof( float4 ), cudaMemcpyHostToDevice, s->stream ) );
+	}
+	s->fullSent = full;
+	s->dirtySent = dirty;
+	return 0;
+}
+
 // the whole input arena in one piece (callers that packed it with b2GpuSolverPackRange)
 int b2gSendArena( b2GpuSolver* s, size_t uptoQuads )
 {
@@ -303,7 +467,7 @@ int b2gSendArena( b2GpuSolver* s, size_t uptoQuads )
 	}
 	s->arenaSent = true;
 	(void)uptoQuads;
-	if ( b2gSendRange( s, 0, s->inMass ) != 0 )
+	if ( b2gSendRange( s, 0, s->inMass ) != 0 || b2gSendStreams( s ) != 0 )
 	{
 		return 1;
 	}
@@ -384,6 +548,21 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 			if ( i < segEnd )
 			{
 				memcpy( seg.states + (size_t)( i - seg.base ) * B2L_STATE_SIZE, outStates + 2 * (size_t)i, (size_t)( segEnd - i ) * B2L_STATE_SIZE );
+				if ( s->resident )
+				{
+					// what the device starts the next step from (storeBody, b2g_stages.cuh): this step's velocity and flags
+					// with the transient flags cleared and the deltas reset, like the host's state after b2FinalizeBodiesTask
+					for ( int j = i; j < segEnd; ++j )
+					{
+						float4 velocity = outStates[2 * (size_t)j];
+						uint32_t flags;
+						memcpy( &flags, &velocity.w, 4 );
+						flags &= ~B2L_FLAG_TRANSIENT;
+						memcpy( &velocity.w, &flags, 4 );
+						s->shadowStates[2 * (size_t)j] = velocity;
+						s->shadowStates[2 * (size_t)j + 1] = make_float4( 0.0f, 0.0f, 1.0f, 0.0f );
+					}
+				}
 				b2gFlushLines( outStates + 2 * (size_t)i, (size_t)( segEnd - i ) * B2L_STATE_SIZE );
 				i = segEnd;
 			}
@@ -417,6 +596,16 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 					uint8_t* mp = manifold + B2L_MANIFOLD_POINTS + j * B2L_MP_SIZE;
 					// normalImpulse, tangentImpulse, totalNormalImpulse, normalVelocity are contiguous (collision.h:549-561)
 					memcpy( mp + B2L_MP_NORMAL_IMPULSE, rec + 1 + 4 * j, 16 );
+				}
+				if ( s->resident )
+				{
+					// the manifold now holds what the device holds: remember it for the next pack pass
+					b2gShadowContact& shadow = s->shadowContacts[(size_t)( s->homeBase[s->segHome[k]] + i )];
+					memcpy( &shadow.rollingImpulse, rec + 0, 4 );
+					for ( int j = 0; j < pointCount && j < 2; ++j )
+					{
+						memcpy( shadow.impulses + 2 * j, rec + 1 + 4 * j, 8 );
+					}
 				}
 				if ( rec[9] != 0.0f && result != nullptr )
 				{
@@ -533,7 +722,11 @@ static int b2gPumpUploads( b2GpuSolver* s, bool everything )
 	{
 		s->arenaSent = true;
 		// the masses' region only when some contact's differ from its bodies' (b2g::WireRow)
-		return b2gSendRange( s, s->inStates, s->massMismatch.load( std::memory_order_acquire ) != 0 ? s->inTotal : s->inMass );
+		if ( b2gSendRange( s, s->inStates, s->massMismatch.load( std::memory_order_acquire ) != 0 ? s->inTotal : s->inMass ) != 0 )
+		{
+			return 1;
+		}
+		return b2gSendStreams( s );
 	}
 	return 0;
 }

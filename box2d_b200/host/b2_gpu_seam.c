@@ -8,9 +8,13 @@
 #include "b2_gpu_seam.h"
 
 /* reference internals (include path: <reference>/src and <reference>/include) */
+#include "atomic.h"
 #include "bitset.h"
+#include "body.h"
+#include "constraint_graph.h"
 #include "core.h"
 #include "id_pool.h"
+#include "island.h"
 #include "parallel_for.h"
 #include "physics_world.h"
 #include "solver.h"
@@ -35,6 +39,8 @@ typedef struct b2SeamSlot
 	b2GpuSeamTotals totals;
 	b2GpuStepResult lastResult;
 	b2GpuStepDesc lastDesc;
+	bool islandsCaptured; /* b2GpuSeam_BeforeIslandSplit filled the hint of the step in flight */
+	int capturedIslandCount;
 } b2SeamSlot;
 
 static b2SeamSlot s_slots[B2_MAX_WORLDS];
@@ -128,44 +134,141 @@ void b2GpuSeam_InstallPinnedAllocator( void )
 	b2SetAllocator( b2GpuHostAlloc, b2GpuHostFree );
 }
 
-/* The two memory-bound host passes run on the world's own workers: workerCount - 1 tasks go through the world's task
- * callbacks (the same ones b2ParallelFor uses, src/parallel_for.c:108-132) and claim blocks of items from the device
- * library; the calling thread works along and pumps the PCIe transfers (b2GpuSolverPackWork / UnpackWork, pump = 1). */
-static void b2SeamPackWorker( void* taskContext )
+/* ---- the team: the world's workers are woken ONCE per step ------------------------------------------------------
+ * The host side of a step has three parallel passes -- island labels, packing, unpacking -- with a few microseconds of
+ * serial work between them (descriptor + layout, launches).  Waking the workers costs more than that (a semaphore post per
+ * task, src/scheduler.c:158-176, and tens of microseconds until a parked thread runs), so workerCount - 1 helper tasks go
+ * through the world's task callbacks once (the same ones b2ParallelFor uses, src/parallel_for.c:108-132) and walk the
+ * passes together with the calling thread, spinning across the short gaps like the reference's own solver workers spin
+ * for their next stage (src/solver.c:921-1008).  Work is claimed in blocks, so a helper that starts late -- or never -- only
+ * means fewer hands.  The calling thread pumps the PCIe transfers (b2GpuSolverPackWork / UnpackWork, pump = 1). */
+enum
 {
-	b2GpuSolverPackWork( taskContext, 0 );
-}
+	b2_seamLabels = 0,	   /* claiming blocks of island labels */
+	b2_seamPackOpen = 1,   /* the step has begun: b2GpuSolverPackWork */
+	b2_seamPackClosed = 2, /* everything is packed and on its way; the calling thread submits */
+	b2_seamUnpackOpen = 3, /* submitted: b2GpuSolverUnpackWork */
+	b2_seamDone = 4,
+};
 
-static void b2SeamUnpackWorker( void* taskContext )
+typedef struct b2SeamTeam
 {
-	b2GpuSolverUnpackWork( taskContext, 0 );
-}
+	b2World* world;
+	b2GpuSolver* solver;
+	const b2BodySim* sims;
+	int* labels;
+	int labelCount, labelBlocks;
+	b2AtomicInt labelNext, labelDone;
+	b2AtomicInt phase;
+	b2AtomicInt inPack, inUnpack;
+	b2AtomicInt failed;
+} b2SeamTeam;
 
-static void b2SeamWorkOnItems( b2World* world, b2GpuSolver* solver, int itemCount, b2TaskCallback* worker,
-							   int ( *work )( b2GpuSolver*, int ), const char* what )
+#define B2_SEAM_LABEL_BLOCK 512
+
+static inline void b2SeamRelax( int* spins )
 {
-	void* handles[B2_MAX_WORKERS];
-	int helperCount = world->workerCount - 1;
-	int useful = itemCount / 2048; /* a helper that wakes up for less than that only costs */
-	helperCount = helperCount < useful ? helperCount : useful;
-	int enqueued = 0;
-	for ( int i = 0; i < helperCount && world->taskCount < B2_MAX_TASKS; ++i )
+#if defined( B2_CPU_X86_X64 ) || defined( __x86_64__ )
+	__builtin_ia32_pause();
+#endif
+	*spins += 1;
+	if ( *spins > 4096 )
 	{
-		handles[enqueued++] = world->enqueueTaskFcn( worker, solver, world->userTaskContext );
-		world->taskCount += 1;
+		/* somebody this thread waits for is not running: give it the core */
+		b2Yield();
+		*spins = 0;
 	}
-	int rc = work( solver, 1 );
-	for ( int i = 0; i < enqueued; ++i )
+}
+
+static void b2SeamTeamLabels( b2SeamTeam* team )
+{
+	const b2Body* bodies = team->world->bodies.data;
+	const b2Island* islands = team->world->islands.data;
+	for ( ;; )
 	{
-		if ( handles[i] != NULL )
+		int block = b2AtomicFetchAddInt( &team->labelNext, 1 );
+		if ( block >= team->labelBlocks )
 		{
-			world->finishTaskFcn( handles[i], world->userTaskContext );
+			break;
 		}
+		int begin = block * B2_SEAM_LABEL_BLOCK;
+		int end = begin + B2_SEAM_LABEL_BLOCK < team->labelCount ? begin + B2_SEAM_LABEL_BLOCK : team->labelCount;
+		// label = index of the body's island among the awake islands (b2Island::localIndex, src/island.h:49-74)
+		for ( int i = begin; i < end; ++i )
+		{
+			int islandId = bodies[team->sims[i].bodyId].islandId;
+			team->labels[i] = islandId == B2_NULL_INDEX ? -1 : islands[islandId].localIndex;
+		}
+		b2AtomicFetchAddInt( &team->labelDone, 1 );
 	}
-	if ( rc != 0 )
+}
+
+static void b2SeamTeamHelper( void* taskContext )
+{
+	b2SeamTeam* team = taskContext;
+	int spins = 0;
+	b2SeamTeamLabels( team );
+	while ( b2AtomicLoadInt( &team->phase ) < b2_seamPackOpen )
 	{
-		b2SeamFatal( what );
+		b2SeamRelax( &spins );
 	}
+	b2AtomicFetchAddInt( &team->inPack, 1 );
+	if ( b2AtomicLoadInt( &team->phase ) == b2_seamPackOpen && b2GpuSolverPackWork( team->solver, 0 ) != 0 )
+	{
+		b2AtomicStoreInt( &team->failed, 1 );
+	}
+	b2AtomicFetchAddInt( &team->inPack, -1 );
+	while ( b2AtomicLoadInt( &team->phase ) < b2_seamUnpackOpen )
+	{
+		b2SeamRelax( &spins );
+	}
+	b2AtomicFetchAddInt( &team->inUnpack, 1 );
+	if ( b2AtomicLoadInt( &team->phase ) == b2_seamUnpackOpen && b2GpuSolverUnpackWork( team->solver, 0 ) != 0 )
+	{
+		b2AtomicStoreInt( &team->failed, 1 );
+	}
+	b2AtomicFetchAddInt( &team->inUnpack, -1 );
+}
+
+/* ---- island capture ahead of a split ---------------------------------------------------------------------- */
+
+static void b2SeamReserveIslands( b2SeamSlot* slot, b2World* world )
+{
+	b2SolverSet* awakeSet = world->solverSets.data + b2_awakeSet;
+	int bodyCount = awakeSet->bodySims.count, islandCount = awakeSet->islandSims.count;
+	if ( slot->islandLabelCapacity < bodyCount )
+	{
+		free( slot->islandLabels );
+		slot->islandLabelCapacity = bodyCount + bodyCount / 2 + 64;
+		slot->islandLabels = malloc( (size_t)slot->islandLabelCapacity * sizeof( int ) );
+	}
+	if ( slot->islandSizeCapacity < islandCount )
+	{
+		free( slot->islandSizes );
+		slot->islandSizeCapacity = islandCount + islandCount / 2 + 64;
+		slot->islandSizes = malloc( (size_t)slot->islandSizeCapacity * sizeof( b2GpuIslandSize ) );
+	}
+}
+
+/* Called by the generated solver.c right before b2Solve may enqueue b2SplitIslandTask (src/solver.c:1476-1495).  That task
+ * runs concurrently with the constraint solve and rewrites world->islands, the awake set's island sims and the bodies'
+ * island ids (src/island.c, b2SplitIsland) -- everything the island hint is read from.  The reference's own solver never
+ * looks at islands, the seam does: so when a split is pending the hint is taken HERE, before the task exists.  The labels
+ * of the unsplit island are still a valid partition (a superset of what the split will produce). */
+void b2GpuSeam_BeforeIslandSplit( b2World* world, b2StepContext* context )
+{
+	(void)context;
+	b2SeamSlot* slot = b2SeamGetSlot( world );
+	slot->islandsCaptured = false;
+	if ( world->splitIslandId == B2_NULL_INDEX )
+	{
+		return;
+	}
+	b2SeamReserveIslands( slot, world );
+	b2GpuStepDesc scratch;
+	b2GpuSeam_FillIslands( world, &scratch, slot->islandLabels, slot->islandSizes, true );
+	slot->capturedIslandCount = scratch.islandCount;
+	slot->islandsCaptured = true;
 }
 
 /* ---- the seam ------------------------------------------------------------------------------------------- */
@@ -173,6 +276,7 @@ static void b2SeamWorkOnItems( b2World* world, b2GpuSolver* solver, int itemCoun
 void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 {
 	b2SeamSlot* slot = b2SeamGetSlot( world );
+	uint64_t seamTicks = b2GetTicks();
 
 	// Same per-worker reset the reference does before fanning out (src/solver.c:1563-1570).
 	int jointIdCapacity = b2GetIdCapacity( &world->jointIdPool );
@@ -189,24 +293,67 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 	// host-only structures, so it stays on the host.
 	b2GpuSeam_PrepareJoints( world, context );
 
-	b2GpuStepDesc* desc = &slot->lastDesc;
-	b2GpuSeam_BuildDesc( world, context, desc );
+	b2SolverSet* awakeSet = world->solverSets.data + b2_awakeSet;
+	const bool captured = slot->islandsCaptured;
+	slot->islandsCaptured = false;
+	if ( !captured )
+	{
+		b2SeamReserveIslands( slot, world );
+	}
+
+	// the team (see above): helpers for as much work as is worth a wake-up
+	b2SeamTeam team;
+	team.world = world;
+	team.solver = slot->solver;
+	team.sims = awakeSet->bodySims.data;
+	team.labels = slot->islandLabels;
+	team.labelCount = captured ? 0 : awakeSet->bodySims.count;
+	team.labelBlocks = ( team.labelCount + B2_SEAM_LABEL_BLOCK - 1 ) / B2_SEAM_LABEL_BLOCK;
+	b2AtomicStoreInt( &team.labelNext, 0 );
+	b2AtomicStoreInt( &team.labelDone, 0 );
+	b2AtomicStoreInt( &team.phase, b2_seamLabels );
+	b2AtomicStoreInt( &team.inPack, 0 );
+	b2AtomicStoreInt( &team.inUnpack, 0 );
+	b2AtomicStoreInt( &team.failed, 0 );
+
+	int itemEstimate = awakeSet->bodySims.count;
+	for ( int i = 0; i < B2_GRAPH_COLOR_COUNT; ++i )
+	{
+		itemEstimate += world->constraintGraph.colors[i].contactSims.count + world->constraintGraph.colors[i].jointSims.count;
+	}
+	void* handles[B2_MAX_WORKERS];
+	int helperCount = world->workerCount - 1;
+	int useful = itemEstimate / 2048; /* a helper that wakes up for less than that only costs */
+	helperCount = helperCount < useful ? helperCount : useful;
+	int enqueued = 0;
+	for ( int i = 0; i < helperCount && world->taskCount < B2_MAX_TASKS; ++i )
+	{
+		handles[enqueued++] = world->enqueueTaskFcn( b2SeamTeamHelper, &team, world->userTaskContext );
+		world->taskCount += 1;
+	}
 
 	// island hint: lets the device solve islands independently in shared memory (no grid barriers)
-	if ( slot->islandLabelCapacity < desc->awakeBodyCount )
+	int spins = 0;
+	b2SeamTeamLabels( &team );
+	while ( b2AtomicLoadInt( &team.labelDone ) < team.labelBlocks )
 	{
-		free( slot->islandLabels );
-		slot->islandLabelCapacity = desc->awakeBodyCount + desc->awakeBodyCount / 2 + 64;
-		slot->islandLabels = malloc( (size_t)slot->islandLabelCapacity * sizeof( int ) );
+		b2SeamRelax( &spins );
 	}
-	b2SolverSet* awakeSet = world->solverSets.data + b2_awakeSet;
-	if ( slot->islandSizeCapacity < awakeSet->islandSims.count )
+
+	b2GpuStepDesc* desc = &slot->lastDesc;
+	b2GpuSeam_BuildDesc( world, context, desc );
+	if ( captured )
 	{
-		free( slot->islandSizes );
-		slot->islandSizeCapacity = awakeSet->islandSims.count + awakeSet->islandSims.count / 2 + 64;
-		slot->islandSizes = malloc( (size_t)slot->islandSizeCapacity * sizeof( b2GpuIslandSize ) );
+		desc->bodyIsland = slot->islandLabels;
+		desc->islandSizes = slot->islandSizes;
+		desc->islandCount = slot->capturedIslandCount;
 	}
-	b2GpuSeam_FillIslands( world, desc, slot->islandLabels, slot->islandSizes, true );
+	else
+	{
+		// sizes here, labels by the team above
+		b2GpuSeam_FillIslands( world, desc, NULL, slot->islandSizes, false );
+		desc->bodyIsland = slot->islandLabels;
+	}
 
 	b2GpuStepResult* result = &slot->lastResult;
 	memset( result, 0, sizeof( *result ) );
@@ -214,23 +361,67 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 	result->hitEventBits = taskContext0->hitEventBitSet.bits;
 	result->jointEventBits = taskContext0->jointStateBitSet.bits;
 
+	const char* failure = NULL;
 	if ( b2GpuSolverBeginStep( slot->solver, desc, result ) != 0 )
 	{
-		b2SeamFatal( "b2GpuSolverBeginStep failed" );
+		failure = "b2GpuSolverBeginStep failed";
 	}
-	int itemCount = b2GpuSolverGetPackItemCount( slot->solver );
-	b2SeamWorkOnItems( world, slot->solver, itemCount, b2SeamPackWorker, b2GpuSolverPackWork, "packing / upload failed" );
-	if ( b2GpuSolverSubmit( slot->solver ) != 0 )
+	if ( failure == NULL )
 	{
-		b2SeamFatal( "device solve failed" );
+		b2AtomicStoreInt( &team.phase, b2_seamPackOpen );
+		if ( b2GpuSolverPackWork( slot->solver, 1 ) != 0 )
+		{
+			failure = "packing / upload failed";
+		}
 	}
-	// the helpers are woken while the kernels run and unpack behind the download
-	b2SeamWorkOnItems( world, slot->solver, itemCount, b2SeamUnpackWorker, b2GpuSolverUnpackWork, "device solve / download failed" );
-	if ( b2GpuSolverEndStep( slot->solver, result ) != 0 )
+	// nobody may still be inside PackWork when Submit re-arms the block counter for the unpack pass
+	b2AtomicStoreInt( &team.phase, b2_seamPackClosed );
+	while ( b2AtomicLoadInt( &team.inPack ) != 0 )
 	{
-		b2SeamFatal( "b2GpuSolverEndStep failed" );
+		b2SeamRelax( &spins );
+	}
+	if ( failure == NULL && b2GpuSolverSubmit( slot->solver ) != 0 )
+	{
+		failure = "device solve failed";
+	}
+	if ( failure == NULL )
+	{
+		// the helpers unpack behind the download
+		b2AtomicStoreInt( &team.phase, b2_seamUnpackOpen );
+		if ( b2GpuSolverUnpackWork( slot->solver, 1 ) != 0 )
+		{
+			failure = "device solve / download failed";
+		}
+	}
+	b2AtomicStoreInt( &team.phase, b2_seamDone );
+	while ( b2AtomicLoadInt( &team.inUnpack ) != 0 )
+	{
+		b2SeamRelax( &spins );
+	}
+	for ( int i = 0; i < enqueued; ++i )
+	{
+		if ( handles[i] != NULL )
+		{
+			world->finishTaskFcn( handles[i], world->userTaskContext );
+		}
+	}
+	if ( failure == NULL && b2AtomicLoadInt( &team.failed ) != 0 )
+	{
+		failure = "a worker failed in packing / unpacking";
+	}
+	if ( failure == NULL && b2GpuSolverEndStep( slot->solver, result ) != 0 )
+	{
+		failure = "b2GpuSolverEndStep failed";
+	}
+	if ( failure != NULL )
+	{
+		b2SeamFatal( failure );
 	}
 
+	slot->totals.seamMs += b2GetMilliseconds( seamTicks );
+	slot->totals.packMs += result->uploadMs;
+	slot->totals.waitMs += result->waitMs;
+	slot->totals.unpackMs += result->scatterMs;
 	slot->totals.steps += 1;
 	slot->totals.kernelMs += result->kernelMs;
 	slot->totals.abiMs += result->totalMs;

@@ -38,6 +38,9 @@ void b2GpuSeam_PrepareJoints( b2World* world, b2StepContext* stepContext );
  * if the device solver fails: there is no CPU fallback. */
 void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* stepContext );
 
+/* Called right before b2Solve may start its island-split task: takes the island hint while nobody is rewriting the islands. */
+void b2GpuSeam_BeforeIslandSplit( b2World* world, b2StepContext* stepContext );
+
 /* Route the reference's allocations through page-locked memory (b2SetAllocator, include/box2d/base.h:86).
  * Call before creating any world. */
 void b2GpuSeam_InstallPinnedAllocator( void );
@@ -50,6 +53,8 @@ typedef struct b2GpuSeamTotals
 	double h2dBytes, d2hBytes;
 	double stageMs[b2GpuStage_count];
 	long long steps, launches, gridBarriers;
+	double seamMs;	 /* host wall time of the whole seam call (what b2Profile.constraints reports) */
+	double packMs, waitMs, unpackMs; /* Begin..Submit, Submit..first output seen, ..EndStep of the phased C-ABI calls */
 } b2GpuSeamTotals;
 void b2GpuSeam_GetTotals( int worldIndex, b2GpuSeamTotals* totals, int reset );
 

@@ -73,6 +73,7 @@ _Static_assert( b2_simEnableHitEvent == B2L_SIM_ENABLE_HIT_EVENT, "sim flags" );
 _Static_assert( b2_lockLinearX == B2L_FLAG_LOCK_LINEAR_X && b2_lockLinearY == B2L_FLAG_LOCK_LINEAR_Y, "body flags" );
 _Static_assert( b2_lockAngularZ == B2L_FLAG_LOCK_ANGULAR_Z && b2_isSpeedCapped == B2L_FLAG_IS_SPEED_CAPPED, "body flags" );
 _Static_assert( b2_allowFastRotation == B2L_FLAG_ALLOW_FAST_ROTATION && b2_dynamicFlag == B2L_FLAG_DYNAMIC, "body flags" );
+_Static_assert( (unsigned)b2_bodyTransientFlags == B2L_FLAG_TRANSIENT, "body flags" );
 _Static_assert( B2_GRAPH_COLOR_COUNT == B2GPU_GRAPH_COLOR_COUNT, "colour count" );
 _Static_assert( sizeof( b2Softness ) == sizeof( b2GpuSoftness ), "b2Softness" );
 
@@ -325,6 +326,11 @@ void b2GpuSeam_FillIslands( b2World* world, b2GpuStepDesc* desc, int* labels, b2
 		}
 	}
 	desc->islandSizes = sizes;
+	desc->islandCount = awakeSet->islandSims.count;
+	if ( labels == NULL )
+	{
+		return; // the caller fills the labels itself (the seam's team)
+	}
 	b2SeamIslandTask task = { world, awakeSet->bodySims.data, labels };
 	int count = awakeSet->bodySims.count;
 	if ( parallel )

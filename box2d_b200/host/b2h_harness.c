@@ -1,5 +1,6 @@
 /*
- * b2h_harness.c -- scene + stepping harness over the reference's PUBLIC API (test infrastructure).
+ * b2h_harness.c -- scene + stepping harness over the reference's PUBLIC API (scene driver for the tests and bench.py;
+ * it only calls include/box2d/box2d.h, so it behaves the same in front of the CPU solver and in front of the seam).
  *
  * The same file is linked into
  *    oracle/_ref/libbox2d_ref.so      the untouched reference (CPU solver)           -> the parity oracle
@@ -659,6 +660,12 @@ B2H_API void b2h_counters( int h, int* out )
 	{
 		out[6 + i] = c.colorCounts[i];
 	}
+}
+
+/* Contacts of the last step whose manifold the narrow phase recycled (src/physics_world.c:508-560). */
+B2H_API int b2h_recycled( int h )
+{
+	return b2World_GetCounters( s_worlds[h].worldId ).recycledContactCount;
 }
 
 /* Event counts of the last step: move, begin-touch, end-touch, hit, joint events. */

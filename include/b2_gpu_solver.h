@@ -241,6 +241,12 @@ B2GPU_API uint64_t b2GpuSolverGetLaunchCount( const b2GpuSolver* solver );
 /* How the last step was laid out for the island-local kernels: number of bins (0 = the step was planned for the
  * grid-barrier kernel) and thread blocks per bin (1, or the cluster size 2..16).  Returns binCount. */
 B2GPU_API int b2GpuSolverGetIslandPlan( const b2GpuSolver* solver, int* binCount, int* blocksPerBin );
+/* Resident mode (single worlds): the device keeps the contacts' static data, their impulses and the bodies across steps, and
+ * the pack pass only uploads what differs from that -- a 16-byte record per contact whose manifold the narrow phase recycled
+ * (src/physics_world.c:508-560), the full 96 bytes otherwise.  Returns 1 when the last step ran in resident mode and fills
+ * how many contacts travelled as full records and how many bodies were re-uploaded; 0 (counts untouched) otherwise.  The
+ * results do not depend on the mode (bit-identical); B2GPU_RESIDENT=0 turns it off. */
+B2GPU_API int b2GpuSolverGetResidentStats( const b2GpuSolver* solver, int* fullContacts, int* dirtyBodies );
 /* Host utility for callers that have island labels but no island bookkeeping: fill sizes[desc->islandCount] from
  * desc->bodyIsland and the constraint arrays (one pass over the constraints).  Returns 0 on success. */
 B2GPU_API int b2GpuCountIslandSizes( const b2GpuStepDesc* desc, b2GpuIslandSize* sizes );

@@ -32,6 +32,8 @@ extern "C"
 #define B2L_FLAG_IS_SPEED_CAPPED 0x00000020u
 #define B2L_FLAG_ALLOW_FAST_ROTATION 0x00000080u
 #define B2L_FLAG_DYNAMIC 0x00000200u
+/* b2_bodyTransientFlags = b2_isFast | b2_isSpeedCapped | b2_hadTimeOfImpact (src/body.h:64), cleared by b2FinalizeBodiesTask */
+#define B2L_FLAG_TRANSIENT 0x00000068u
 
 /* ---- b2BodySim (96 B) ------------------------------------------------------------------------------ */
 #define B2L_SIM_SIZE 96

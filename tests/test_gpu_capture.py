@@ -117,7 +117,7 @@ def test_island_failure_reruns_on_grid_kernel(capture_files, monkeypatch):
 			_check(cap, bufs, result)
 			if solver.island_plan()[0] > 0 and result.gridBarriers > 0:
 				reruns += 1
-				assert result.kernelLaunches == 3
+				assert result.kernelLaunches >= 3
 			# and through the split-phase API (fresh buffers: the step above wrote its results into the inputs)
 			desc, result, bufs = cap.make_call(islands=True)
 			solver.upload(desc)

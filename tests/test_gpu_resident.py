@@ -1,0 +1,238 @@
+"""Resident mode (include/b2_gpu_solver.h, b2GpuSolverGetResidentStats): the device keeps contacts, impulses and bodies
+across steps and the pack pass uploads only what differs from that.  These tests drive SEQUENCES of steps through one
+solver -- each step's outputs become the next step's inputs, the way b2World_Step chains them -- with the host touching
+things in between the way the reference does (recycled manifolds: only the separations move, src/physics_world.c:545-550;
+re-evaluated manifolds; swap-removes in the colour arrays, src/constraint_graph.c:198-211; bodies whose velocity the user
+set).  Every step is compared bit for bit with the CPU oracle on the very same inputs, and the statistics must show that
+the light path was really taken.  (A contact keeps its resident record as long as it keeps its place in its colour's
+array: the two contacts a swap-remove moves travel in full once.)"""
+import ctypes
+
+import numpy as np
+import pytest
+
+import box2d_b200 as b2
+
+pytestmark = pytest.mark.gpu
+
+MAN = 68  # b2ContactSim::manifold
+POINT = (MAN + 12, MAN + 12 + 44)
+
+
+@pytest.fixture(scope="module")
+def oracle():
+	lib = ctypes.CDLL(str(b2.ROOT / "oracle" / "liboracle.so"))
+	lib.b2OracleSolverStep.restype = ctypes.c_int
+	lib.b2OracleSolverStep.argtypes = [ctypes.POINTER(b2.StepDesc), ctypes.POINTER(b2.StepResult)]
+	return lib
+
+
+def _finalize(cap: b2.Capture, bufs) -> None:
+	"""What the host does to the solver's outputs before the next step (b2FinalizeBodiesTask, src/solver.c:611-612, :632):
+	the outputs become the capture's inputs, deltas reset, transient flags cleared."""
+	n = cap.body_count
+	st = bufs["states"].copy()
+	if n:
+		f = st.view(np.float32).reshape(n, 8)
+		f[:, 4:8] = np.array([0.0, 0.0, 1.0, 0.0], dtype=np.float32)
+		st.view(np.uint32).reshape(n, 8)[:, 3] &= np.uint32(~0x68 & 0xFFFFFFFF)
+	cap.states_in = st
+	cap.contacts_in = [a.copy() for a in bufs["contacts"]]
+	cap.joints_in = [a.copy() for a in bufs["joints"]]
+
+
+def _step_both(oracle, solver, cap, tag, **kw):
+	d0, r0, want = cap.make_call(**kw)
+	assert oracle.b2OracleSolverStep(ctypes.byref(d0), ctypes.byref(r0)) == 0
+	d, r, got = cap.make_call(**kw)
+	solver.step(d, r)
+	assert np.array_equal(got["states"], want["states"]), tag + ": states"
+	for a, b in zip(got["contacts"], want["contacts"]):
+		assert np.array_equal(a, b), tag + ": contact sims"
+	for a, b in zip(got["joints"], want["joints"]):
+		assert np.array_equal(a, b), tag + ": joint sims"
+	assert np.array_equal(got["hit"], want["hit"]), tag + ": hit bits"
+	assert np.array_equal(got["joint"], want["joint"]), tag + ": joint bits"
+	assert bool(r.hasHitEvents) == bool(r0.hasHitEvents), tag
+	return got
+
+
+def _contacts(arr):
+	return arr.reshape(-1, b2.CONTACT_SIZE)
+
+
+def _mutate(cap: b2.Capture, rng, kind: str) -> int:
+	"""Touch the inputs the way the host does between two steps; returns how many contacts MUST travel as full records."""
+	touched = 0
+	if kind == "recycle":
+		# recycled manifolds: new separations, nothing else (src/physics_world.c:545-550)
+		for arr in cap.contacts_in:
+			if arr.size:
+				c = _contacts(arr)
+				for p in POINT:
+					sep = c[:, p + 16:p + 20].view(np.float32)
+					sep += rng.normal(0.0, 0.002, size=sep.shape).astype(np.float32)
+	elif kind == "manifold":
+		# re-evaluated manifolds on every third contact: anchors and normal move, impulses are matched and kept
+		for arr in cap.contacts_in:
+			if arr.size:
+				c = _contacts(arr)[::3]
+				for p in POINT:
+					anchors = c[:, p:p + 16].view(np.float32)
+					anchors += rng.normal(0.0, 0.01, size=anchors.shape).astype(np.float32)
+				touched += c.shape[0]
+	elif kind == "impulses":
+		# a manifold whose point ids changed: the cached impulses are dropped (src/contact.c, b2UpdateContact)
+		for arr in cap.contacts_in:
+			if arr.size:
+				c = _contacts(arr)[1::4]
+				for p in POINT:
+					c[:, p + 24:p + 32] = 0
+				touched += c.shape[0]
+	elif kind == "material":
+		for arr in cap.contacts_in:
+			if arr.size:
+				c = _contacts(arr)[::5]
+				c[:, 172:176].view(np.float32)[:] = rng.uniform(0.1, 0.9, size=(c.shape[0], 1)).astype(np.float32)
+				touched += c.shape[0]
+	elif kind == "swap":
+		# swap-remove churn: the first and the last contact of every colour trade places (same ids, new slots)
+		for arr in cap.contacts_in:
+			c = _contacts(arr) if arr.size else None
+			if c is not None and c.shape[0] >= 2:
+				first = c[0].copy()
+				c[0] = c[-1]
+				c[-1] = first
+				touched += 2  # new at their homes
+	elif kind == "velocity":
+		n = cap.body_count
+		if n:
+			st = cap.states_in.view(np.float32).reshape(n, 8)
+			st[::4, 0:3] += rng.normal(0.0, 0.3, size=st[::4, 0:3].shape).astype(np.float32)
+	elif kind == "force":
+		n = cap.body_count
+		if n:
+			sims = cap.sims.reshape(n, b2.SIM_SIZE)
+			sims[::6, 48:56].view(np.float32)[:] += rng.normal(0.0, 2.0, size=(sims[::6].shape[0], 2)).astype(np.float32)
+	elif kind == "deltas":
+		# not something the reference does (finalize resets them), but the C-ABI takes any state
+		n = cap.body_count
+		if n:
+			st = cap.states_in.view(np.float32).reshape(n, 8)
+			st[::7, 4:6] += np.float32(0.001)
+	elif kind != "none":
+		raise ValueError(kind)
+	return touched
+
+
+SEQUENCE = ["none", "recycle", "none", "manifold", "recycle", "swap", "velocity", "impulses", "material", "force", "deltas", "recycle", "none"]
+
+
+@pytest.mark.parametrize("islands", [True, False], ids=["island-kernels", "grid-kernel"])
+def test_chained_steps_match_the_oracle(oracle, capture_files, islands):
+	rng = np.random.default_rng(7)
+	light_steps = 0
+	for path in capture_files:
+		cap = b2.Capture(path)
+		if cap.contact_count == 0:
+			continue
+		with b2.GpuSolver() as solver:
+			for step, kind in enumerate(SEQUENCE):
+				must_full = _mutate(cap, rng, kind)
+				tag = f"{path.name} step {step} after {kind!r}"
+				got = _step_both(oracle, solver, cap, tag, islands=islands)
+				stats = solver.resident_stats()
+				assert stats is not None, tag + ": not a resident step"
+				full, dirty = stats
+				if step == 0:
+					assert full == cap.contact_count and dirty == cap.body_count, tag + ": a cold step sends everything"
+				else:
+					if kind == "impulses":
+						assert full <= must_full, tag  # (impulses that were zero already do not make a contact dirty)
+					else:
+						assert full == must_full, tag + f": {full} contacts travelled in full, {must_full} were touched"
+					light_steps += 1 if full == 0 else 0
+					if kind in ("none", "recycle", "swap", "manifold", "impulses", "material"):
+						assert dirty == 0, tag + f": {dirty} bodies re-uploaded although the host did not touch any"
+					if kind in ("velocity", "force", "deltas"):
+						assert 0 < dirty < max(2, cap.body_count), tag
+				_finalize(cap, got)
+	assert light_steps > 0
+
+
+def test_contacts_leaving_and_returning(oracle, capture_files):
+	"""A contact that sits out a step (stopped touching, came back) must not pick up stale impulses: its previous output
+	record is two steps old."""
+	rng = np.random.default_rng(11)
+	path = [f for f in capture_files if "small_pyramid_030" in f.name][0]
+	cap = b2.Capture(path)
+	with b2.GpuSolver() as solver:
+		got = _step_both(oracle, solver, cap, "warm-up")
+		_finalize(cap, got)
+		keep = [a.copy() for a in cap.contacts_in]
+		counts = list(cap.color_counts)
+		# drop the last contact of every colour for one step ...
+		dropped = 0
+		for i, arr in enumerate(cap.contacts_in):
+			cc, jc = cap.color_counts[i]
+			if cc >= 2:
+				cap.contacts_in[i] = arr[: (cc - 1) * b2.CONTACT_SIZE].copy()
+				cap.color_counts[i] = (cc - 1, jc)
+				cd = cap.desc.colors[i] if i < cap.desc.activeColorCount else cap.desc.overflow
+				cd.contactCount = cc - 1
+				dropped += 1
+		assert dropped > 0
+		got = _step_both(oracle, solver, cap, "without them")
+		assert solver.resident_stats()[0] == 0
+		_finalize(cap, got)
+		# ... and bring them back exactly as they were two steps ago
+		for i, arr in enumerate(keep):
+			cc, jc = counts[i]
+			if cc >= 2:
+				cap.contacts_in[i] = np.concatenate([cap.contacts_in[i], arr[(cc - 1) * b2.CONTACT_SIZE:]])
+				cap.color_counts[i] = (cc, jc)
+				cd = cap.desc.colors[i] if i < cap.desc.activeColorCount else cap.desc.overflow
+				cd.contactCount = cc
+		_mutate(cap, rng, "recycle")
+		got = _step_both(oracle, solver, cap, "back again")
+		assert solver.resident_stats()[0] == dropped, "exactly the returning contacts travel in full"
+
+
+def test_resident_and_plain_steps_interleave(oracle, capture_files):
+	"""A batch step (plain wire) in between invalidates the resident copies: the next single-world step sends everything."""
+	cap = b2.Capture([f for f in capture_files if "falling_hinges_120" in f.name][0])
+	other = b2.Capture([f for f in capture_files if "small_pyramid_030" in f.name][0])
+	with b2.GpuSolver() as solver:
+		got = _step_both(oracle, solver, cap, "first")
+		_finalize(cap, got)
+		got = _step_both(oracle, solver, cap, "second")
+		assert solver.resident_stats()[0] == 0
+		_finalize(cap, got)
+		descs, results, keep = b2.make_batch([other, other])
+		solver.step_batch(descs, results)
+		assert solver.resident_stats() is None
+		got = _step_both(oracle, solver, cap, "after the batch")
+		assert solver.resident_stats() == (cap.contact_count, cap.body_count)
+		_finalize(cap, got)
+		# the split-phase entry points keep the copies in step too
+		d, r, bufs = cap.make_call()
+		d0, r0, want = cap.make_call()
+		assert oracle.b2OracleSolverStep(ctypes.byref(d0), ctypes.byref(r0)) == 0
+		solver.upload(d)
+		solver.run(r)
+		solver.run(r)
+		solver.download(d, r)
+		assert solver.resident_stats()[0] == 0
+		assert np.array_equal(bufs["states"], want["states"])
+		for a, b in zip(bufs["contacts"], want["contacts"]):
+			assert np.array_equal(a, b)
+
+
+def test_resident_off_matches(oracle, capture_files, monkeypatch):
+	monkeypatch.setenv("B2GPU_RESIDENT", "0")
+	cap = b2.Capture([f for f in capture_files if "contact_zoo_130" in f.name][0])
+	with b2.GpuSolver() as solver:
+		for step in range(3):
+			got = _step_both(oracle, solver, cap, f"plain step {step}")
+			assert solver.resident_stats() is None
+			_finalize(cap, got)

@@ -129,7 +129,7 @@ def build_reference_libs(verbose: bool = False) -> dict[str, Path]:
 	if not reference_available():
 		raise RuntimeError(f"reference sources not found at {REFERENCE}")
 	objs = compile_reference_objects()
-	harness = compile_own_c(ROOT / "oracle" / "harness" / "b2h_harness.c")
+	harness = compile_own_c(PKG_DIR / "host" / "b2h_harness.c")
 	pure = compile_solver_variant("pure")
 	hook = compile_solver_variant("hook")
 	capture = compile_own_c(ROOT / "oracle" / "harness" / "b2h_capture.c")
@@ -167,7 +167,7 @@ def build_host_lib(verbose: bool = False) -> Path:
 	cuda_lib = build_cuda_lib(verbose)
 	objs = compile_reference_objects()
 	gpu = compile_solver_variant("gpu")
-	harness = compile_own_c(ROOT / "oracle" / "harness" / "b2h_harness.c")
+	harness = compile_own_c(PKG_DIR / "host" / "b2h_harness.c")
 	seam = compile_own_c(PKG_DIR / "host" / "b2_gpu_seam.c")
 	seam_desc = compile_own_c(PKG_DIR / "host" / "b2_gpu_seam_desc.c")
 	target = PKG_DIR / "libbox2d_b200.so"
@@ -189,7 +189,7 @@ def build_reference_avx2(verbose: bool = False) -> Path:
 	flags = [*REF_CFLAGS, "-DBOX2D_AVX2", "-mavx2"]
 	jobs = [(src, out / f"src_{src.stem}.o") for src in sorted((REFERENCE / "src").glob("*.c"))]
 	jobs += [(src, out / f"shared_{src.stem}.o") for src in sorted((REFERENCE / "shared").glob("*.c"))]
-	harness = ROOT / "oracle" / "harness" / "b2h_harness.c"
+	harness = PKG_DIR / "host" / "b2h_harness.c"
 	jobs.append((harness, out / "own_b2h_harness.o"))
 
 	def one(job):

@@ -1,6 +1,6 @@
 """Step a benchmark scene through the product library and print, every 10 steps, what the seam handed to the device and
 how the device solved it (island plan, launches, grid barriers, kernel and ABI time, stage split).
-   python tools/scene_trace.py <scene> [blocks of 10 steps]      (needs a GPU; scenes: oracle/harness/b2h_harness.c)"""
+   python tools/scene_trace.py <scene> [blocks of 10 steps]      (needs a GPU; scenes: box2d_b200/host/b2h_harness.c)"""
 import ctypes, numpy as np, sys
 sys.path.insert(0,'.')
 import box2d_b200 as b2
