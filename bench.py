@@ -155,63 +155,116 @@ def load_reference_avx2():
 	return b2._bind_harness(ctypes.CDLL(str(path)))
 
 
-def cpu_solver_run(scene: str, workers: int, warmup: int, steps: int, lib=None) -> dict:
-	"""Time the reference's CPU solver: sum of b2Profile.constraints over `steps` world steps after `warmup`."""
+def scene_config(scene: str, bodies: int, contacts: int, joints: int, substeps: int = 4) -> dict:
+	"""The workload as both arms name it (identical keys and values, so that the two lines can be compared field by field)."""
+	return {"workload": scene, "settle_steps": SETTLE_STEPS.get(scene, 0), "bodies": bodies, "contacts": contacts, "joints": joints,
+			"substeps": substeps, "dt": 1.0 / 60.0}
+
+
+def cpu_solver_run(scene: str, workers: int, warmup: int, steps: int, lib=None, replicas: int = 1) -> dict:
+	"""Time the reference's CPU solver: sum of b2Profile.constraints over `steps` world steps after `warmup`.  replicas > 1:
+	that many independent copies of the scene stepped concurrently, one host thread each driving `workers` workers (the
+	multi-GPU arm steps one world per GPU); the times are the slowest replica's."""
 	lib = lib or load_reference()
-	with b2.World(lib, scene, workers) as w:
-		w.step(SETTLE_STEPS.get(scene, 0) + warmup)
-		bodies = w.counters()["awakeBodyCount"]
-		r = w.bench(steps)
-		c = w.counters()
-	r.update(bodies=bodies, contacts=sum(c["colorCounts"]) - c["jointCount"], joints=c["jointCount"], workers=workers)
+	worlds = [b2.World(lib, scene, workers) for _ in range(replicas)]
+	try:
+		def warm(w):
+			w.step(SETTLE_STEPS.get(scene, 0) + warmup)
+
+		def timed(w):
+			return w.bench(steps)
+
+		with ThreadPoolExecutor(max_workers=replicas) as pool:
+			list(pool.map(warm, worlds))
+			bodies = worlds[0].counters()["awakeBodyCount"]
+			results = list(pool.map(timed, worlds))
+		c = worlds[0].counters()
+	finally:
+		for w in worlds:
+			w.destroy()
+	r = max(results, key=lambda x: x["constraints_ms"])
+	r.update(bodies=bodies, contacts=sum(c["colorCounts"]) - c["jointCount"], joints=c["jointCount"], workers=workers, replicas=replicas)
 	return r
 
 
-def best_cpu_baseline(scene: str, warmup: int, steps: int) -> dict:
+def best_cpu_baseline(scene: str, warmup: int, steps: int, replicas: int = 1) -> dict:
 	cores = os.cpu_count() or 1
-	candidates = sorted({w for w in (1, 4, 8, 16, 24, 32, min(cores, 32)) if w <= min(cores, 32)})
+	share = max(1, min(cores // replicas, 32))
+	candidates = sorted({w for w in (1, 4, 8, 16, 24, 32, share) if w <= share})
 	best = None
 	tried = {}
 	for workers in candidates:
-		r = cpu_solver_run(scene, workers, warmup, steps)
+		r = cpu_solver_run(scene, workers, warmup, steps, replicas=replicas)
 		tried[workers] = r["constraints_ms"] / steps
 		if best is None or r["constraints_ms"] < best["constraints_ms"]:
 			best = r
 	best["tried_ms_per_step"] = tried
 	best["host_cores"] = cores
-	# second data point: the reference's optional AVX2 build at the best worker count (the default build is SSE2)
+	best["build"] = "default (SSE2, 4 lanes)"
+	best["sse2_ms_per_step"] = best["constraints_ms"] / steps
+	# the reference's optional AVX2 build (8 lanes) at the best worker count: the number to beat is the best CPU configuration
+	# (BASELINE.md section 3), so when it is faster it becomes the baseline
 	avx2 = load_reference_avx2()
-	best["avx2_ms_per_step"] = cpu_solver_run(scene, best["workers"], warmup, steps, avx2)["constraints_ms"] / steps if avx2 else None
+	best["avx2_ms_per_step"] = None
+	if avx2:
+		r = cpu_solver_run(scene, best["workers"], warmup, steps, avx2, replicas=replicas)
+		best["avx2_ms_per_step"] = r["constraints_ms"] / steps
+		if r["constraints_ms"] < best["constraints_ms"]:
+			keep = {k: best[k] for k in ("tried_ms_per_step", "host_cores", "sse2_ms_per_step", "avx2_ms_per_step")}
+			best = dict(r, **keep)
+			best["build"] = "BOX2D_AVX2 (8 lanes)"
 	return best
 
 
 def cpu_batch_baseline(worlds: int, warmup: int, steps: int) -> dict:
-	"""The batch on the host: independent worlds stepped concurrently by a thread pool, one worker each (worlds are
-	independent, include/box2d/box2d.h:31-32).  A bounded sample of 96 worlds; the solver time per world-step is
-	sum(b2Profile.constraints) / threads, i.e. the solver-only share of a perfectly parallel host loop."""
+	"""The batch on the host: ALL `worlds` independent worlds, stepped concurrently by a thread pool with one worker per world
+	(worlds are independent, include/box2d/box2d.h:31-32) in chunks that fit B2_MAX_WORLDS = 128
+	(include/box2d/constants.h:38-40).  Solver time of a batch step = sum(b2Profile.constraints) / threads, i.e. the
+	solver-only share of a perfectly parallel host loop; the wall clock of the whole loop is reported beside it."""
 	lib = load_reference()
 	threads = min(os.cpu_count() or 1, 32)
-	sample = 96  # B2_MAX_WORLDS is 128 (include/box2d/constants.h:38-40)
-	ws = [b2.World(lib, "small_pyramid", 1) for _ in range(sample)]
-	for w in ws:
-		w.step(warmup)
-	bodies = ws[0].counters()["awakeBodyCount"]
-
-	def run(group):
-		return sum(w.bench(steps)["constraints_ms"] for w in group)
-
-	groups = [ws[i::threads] for i in range(threads)]
-	t0 = time.perf_counter()
+	chunk = max(threads, (112 // threads) * threads)
+	constraints_ms = 0.0
+	step_ms = 0.0
+	wall = 0.0
+	bodies = 0
+	done = 0
 	with ThreadPoolExecutor(max_workers=threads) as pool:
-		constraints_ms = sum(pool.map(run, groups))
-	wall = time.perf_counter() - t0
-	for w in ws:
-		w.destroy()
+		while done < worlds:
+			n = min(chunk, worlds - done)
+			ws = [b2.World(lib, "small_pyramid", 1) for _ in range(n)]
+			groups = [ws[i::threads] for i in range(threads)]
+
+			def warm(group):
+				for w in group:
+					w.step(warmup)
+
+			def run(group):
+				c = s = 0.0
+				for w in group:
+					r = w.bench(steps)
+					c += r["constraints_ms"]
+					s += r["step_ms"]
+				return c, s
+
+			list(pool.map(warm, groups))
+			bodies = ws[0].counters()["awakeBodyCount"]
+			t0 = time.perf_counter()
+			for c, s in pool.map(run, groups):
+				constraints_ms += c
+				step_ms += s
+			wall += time.perf_counter() - t0
+			for w in ws:
+				w.destroy()
+			done += n
 	solver_s = constraints_ms * 1e-3 / threads
-	return {"value": sample * steps * bodies / solver_s, "unit": UNIT, "cores": threads, "kind": "reference",
-			"us_per_world_step": constraints_ms * 1e3 / (sample * steps),
-			"sample": f"{sample} of the {worlds} base-10 pyramid worlds x {steps} steps, one worker per world, {threads} host "
-					  f"threads; sum of b2Profile.constraints / threads (whole loop wall {wall * 1e3:.1f} ms)"}
+	return {"value": worlds * steps * bodies / solver_s, "unit": UNIT, "cores": os.cpu_count() or 1, "threads": threads, "kind": "reference",
+			"us_per_world_step": constraints_ms * 1e3 / (worlds * steps),
+			"solver_ms_per_batch_step": solver_s * 1e3 / steps,
+			"whole_step_ms_per_batch_step": step_ms / threads / steps,
+			"wall_ms_per_batch_step": wall * 1e3 / steps,
+			"sample": f"all {worlds} base-10 pyramid worlds x {steps} steps after {warmup} warm-up steps, in chunks of {chunk} "
+					  f"(B2_MAX_WORLDS), one worker per world, {threads} host threads; sum of b2Profile.constraints / threads"}
 
 
 def run_reference_arm(args) -> int:
@@ -228,23 +281,31 @@ def run_reference_arm(args) -> int:
 				"gpu_launches": 0}
 		print(json.dumps(line))
 		return 0
-	best = best_cpu_baseline(args.workload, args.warmup, args.steps)
+	# the GPU arm at N GPUs steps N independent copies of the world (weak scaling): so does this arm, on the host's cores
+	replicas = max(1, args.gpus)
+	best = best_cpu_baseline(args.workload, args.warmup, args.steps, replicas)
 	ms = best["constraints_ms"] / args.steps
-	value = best["bodies"] * args.steps / (best["constraints_ms"] * 1e-3)
+	value = replicas * best["bodies"] * args.steps / (best["constraints_ms"] * 1e-3)
 	line = {
 		"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
 		"warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
 		"dtype": "f32", "data": "synthetic",
-		"config": {"workload": args.workload, "settle_steps": SETTLE_STEPS.get(args.workload, 0), "bodies": best["bodies"], "contacts": best["contacts"], "joints": best["joints"],
-				   "substeps": 4, "dt": 1.0 / 60.0, "timed": "sum of b2Profile.constraints (reference src/solver.c:1561,1615)"},
-		"cpu_baseline": {"value": value, "unit": UNIT, "cores": best["workers"], "kind": "reference",
-						 "sample": f"{args.steps} steps of {args.workload} after {args.warmup} warm-up steps; best of worker counts "
-								   f"{sorted(best['tried_ms_per_step'])} on {best['host_cores']} host cores",
+		"config": scene_config(args.workload, best["bodies"], best["contacts"], best["joints"]),
+		"details": {"timed": "sum of b2Profile.constraints (reference src/solver.c:1561,1615), slowest of the concurrently stepped worlds",
+					"worlds": replicas, "workers_per_world": best["workers"], "build": best["build"],
+					"whole_step_ms": best["step_ms"] / args.steps},
+		"cpu_baseline": {"value": value, "unit": UNIT, "cores": best["host_cores"], "best_workers": best["workers"], "kind": "reference",
+						 "build": best["build"],
+						 "sample": f"{args.steps} steps of {replicas} x {args.workload} after {args.warmup} warm-up steps; best of worker counts "
+								   f"{sorted(best['tried_ms_per_step'])} per world and of the default / AVX2 builds on {best['host_cores']} host cores",
 						 "ms_per_step_by_workers": best["tried_ms_per_step"],
+						 "sse2_build_ms_per_step": best["sse2_ms_per_step"],
 						 "avx2_build_ms_per_step": best["avx2_ms_per_step"]},
 		"e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
 		"gpu_launches": 0,
 	}
+	if args.batch:
+		line["batch"] = cpu_batch_baseline(BATCH_WORLDS, 30, min(args.steps, 10))
 	print(json.dumps(line))
 	return 0
 
@@ -261,6 +322,8 @@ def _setup_distributed():
 		raise RuntimeError("bench.py needs a CUDA device: the solver has no CPU fallback")
 	torch.cuda.set_device(local_rank)
 	os.environ["B2GPU_DEVICE"] = str(local_rank)
+	# the library's own host threads (one-call entry points): the ranks of one box share its cores
+	os.environ.setdefault("B2GPU_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world_size))))
 	if world_size > 1:
 		dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 	return world_size, rank, local_rank
@@ -383,23 +446,25 @@ def run_scene(args) -> int:
 		if args.cpu_baseline and not distributed:
 			sample_steps = min(args.steps, 60)
 			b = best_cpu_baseline(scene, args.warmup, sample_steps)
-			cpu = {"value": b["bodies"] * sample_steps / (b["constraints_ms"] * 1e-3), "unit": UNIT, "cores": b["workers"],
-				   "kind": "reference", "ms_per_step": b["constraints_ms"] / sample_steps,
+			cpu = {"value": b["bodies"] * sample_steps / (b["constraints_ms"] * 1e-3), "unit": UNIT, "cores": b["host_cores"],
+				   "best_workers": b["workers"], "build": b["build"],
+				   "kind": "reference", "ms_per_step": b["constraints_ms"] / sample_steps, "whole_step_ms": b["step_ms"] / sample_steps,
 				   "sample": f"{sample_steps} steps of {scene} after {args.warmup} warm-up steps, sum of "
-							 f"b2Profile.constraints; best of worker counts {sorted(b['tried_ms_per_step'])} on "
-							 f"{b['host_cores']} host cores (oracle/_ref = untouched reference, gcc -O3 SSE2)",
+							 f"b2Profile.constraints; best of worker counts {sorted(b['tried_ms_per_step'])} and of the default / AVX2 "
+							 f"builds on {b['host_cores']} host cores (oracle/_ref = untouched reference, gcc -O3)",
 				   "ms_per_step_by_workers": b["tried_ms_per_step"],
+				   "sse2_build_ms_per_step": b["sse2_ms_per_step"],
 				   "avx2_build_ms_per_step": b["avx2_ms_per_step"]}
 		line = {
 			"metric": METRIC, "value": total_work / kernel_s, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
 			"warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
 			"vs_baseline": None, "dtype": "f32", "data": "synthetic",
-			"config": {"workload": scene, "settle_steps": SETTLE_STEPS.get(scene, 0), "bodies": bodies, "contacts": contacts, "joints": joints, "substeps": substeps,
-					   "dt": 1.0 / 60.0, "colors": sum(1 for c in counters["colorCounts"][:23] if c > 0),
-					   "parallelism": f"{world_size} independent world(s), one per GPU", "host_workers_per_world": workers,
-					   "l2": "flushed (256 MiB write) between timed iterations" if resident else
-							 "not flushed: kernels timed inside the real steps (awake set changes every step)",
-					   "timed": "CUDA events on the solver stream around the step's kernels, inputs resident"},
+			"config": scene_config(scene, bodies, contacts, joints, substeps),
+			"details": {"colors": sum(1 for c in counters["colorCounts"][:23] if c > 0),
+						"parallelism": f"{world_size} independent world(s), one per GPU", "host_workers_per_world": workers,
+						"l2": "flushed (256 MiB write) between timed iterations" if resident else
+							  "not flushed: kernels timed inside the real steps (awake set changes every step)",
+						"timed": "CUDA events on the solver stream around the step's kernels, inputs resident"},
 			"e2e": {"value": total_work / e2e_s, "unit": UNIT, "ms_per_step": e2e_s * 1e3 / args.steps,
 					"h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
 					"timed": "sum of b2Profile.constraints over K b2World_Step calls of libbox2d_b200.so",
@@ -417,6 +482,11 @@ def run_scene(args) -> int:
 		}
 		if cpu is not None:
 			line["cpu_baseline"] = cpu
+	# north_star's multi-GPU configuration rides along in the same line: the 8192-world batch sharded over the N ranks
+	batch = measure_batch(args, world_size, rank, local_rank, args.cpu_baseline and not distributed) if args.batch else None
+	if rank == 0:
+		if batch is not None:
+			line["batch"] = batch
 		print(json.dumps(line))
 	if distributed:
 		dist.destroy_process_group()
@@ -462,14 +532,14 @@ def build_batch(host, worlds: int, warmup: int):
 	return descs, results, keep, pristine, n, contacts, int(template.subStepCount)
 
 
-def run_batch(args) -> int:
+def measure_batch(args, world_size: int, rank: int, local_rank: int, cpu_baseline: bool):
+	"""BASELINE.json configs[4]: 8192 independent base-10 pyramid worlds sharded over the ranks (contiguous blocks, no
+	exchange), solved by b2GpuSolverStepBatch.  Returns the record on rank 0, None elsewhere."""
 	import torch
 	import torch.distributed as dist
 
-	world_size, rank, local_rank = _setup_distributed()
 	distributed = world_size > 1
 	# the library packs / unpacks a batch on its own threads: the ranks of one box share its cores
-	os.environ.setdefault("B2GPU_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world_size))))
 	host = b2.host_lib()
 	begin, end = shard_range(BATCH_WORLDS, rank, world_size)
 	worlds = end - begin
@@ -488,6 +558,7 @@ def run_batch(args) -> int:
 			for a, p in zip(cs, pristine[1]):
 				a[:] = p
 
+	steps = min(args.steps, 50)
 	sampler = ClockSampler(local_rank)
 	with b2.GpuSolver(device=local_rank) as solver:
 		# value: inputs resident, K x RunBatch
@@ -499,17 +570,17 @@ def run_batch(args) -> int:
 		sampler.start()
 		kernel_ms = []
 		torch.cuda.profiler.start()  # lets `ncu --profile-from-start off` skip the thousands of one-world warm-up launches
-		for _ in range(args.steps):
+		for _ in range(steps):
 			flush.zero_()
 			torch.cuda.synchronize()
 			solver.run_batch(r)
 			kernel_ms.append(float(r.kernelMs))
 		torch.cuda.profiler.stop()
-		launches = int(r.kernelLaunches) * args.steps
+		launches = int(r.kernelLaunches) * steps
 		grid_barriers = int(r.gridBarriers)
 		island_plan = list(solver.island_plan())
 		# e2e: the whole b2GpuSolverStepBatch from host arrays, inputs restored untimed
-		e2e_steps = max(3, min(args.steps, 10))
+		e2e_steps = max(3, min(steps, 10))
 		e2e_s = 0.0
 		for _ in range(e2e_steps):
 			restore()
@@ -525,36 +596,46 @@ def run_batch(args) -> int:
 	clocks = sampler.stop()
 
 	kernel_s = sum(kernel_ms) * 1e-3
-	(kernel_s, e2e_per_step), total_work = reduce_over_ranks([kernel_s, e2e_s / e2e_steps], float(worlds * bodies * args.steps), "cuda")
+	(kernel_s, e2e_per_step), total_work = reduce_over_ranks([kernel_s, e2e_s / e2e_steps], float(worlds * bodies * steps), "cuda")
 	total_worlds = BATCH_WORLDS
-	if rank == 0:
-		ms_per_step = kernel_s * 1e3 / args.steps
-		peak, peak_source = measured_peaks()
-		alg = algorithmic_bytes(bodies, contacts, 0, substeps) * worlds
-		achieved = alg / (ms_per_step * 1e-3) / 1e9
-		line = {
-			"metric": METRIC, "value": total_work / kernel_s, "unit": UNIT, "n_gpus": world_size, "steps": args.steps,
-			"warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
-			"vs_baseline": None, "dtype": "f32", "data": "synthetic",
-			"config": {"workload": f"batch of {total_worlds} small_pyramid worlds", "worlds": total_worlds, "worlds_per_gpu": worlds,
-					   "bodies_per_world": bodies, "contacts_per_world": contacts, "substeps": substeps,
-					   "world_steps_per_sec": total_worlds * args.steps / kernel_s,
-					   "parallelism": f"worlds sharded over {world_size} GPU(s), no exchange",
-					   "l2": "flushed (256 MiB write) between timed iterations"},
-			"e2e": {"value": total_worlds * bodies / e2e_per_step, "unit": UNIT, "ms_per_step": e2e_per_step * 1e3,
-					"h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "last_step_split": split,
-					"timed": "b2GpuSolverStepBatch wall clock: host packing (library threads) + H2D + kernels + D2H + write-back"},
-			"gpu_launches": launches,
-			"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-						 "traffic": measured_traffic("batch") if world_size == 1 else None,
-						 "algorithmic_bytes_per_launch": alg, "peak_source": peak_source, "grid_barriers_per_step": grid_barriers,
-						 "island_bins_blocks_per_bin": island_plan},
-			"clocks": clocks,
-		}
-		if args.cpu_baseline and not distributed:
-			line["cpu_baseline"] = cpu_batch_baseline(total_worlds, 30, min(args.steps, 40))
-		print(json.dumps(line))
-	if distributed:
+	if rank != 0:
+		return None
+	ms_per_step = kernel_s * 1e3 / steps
+	peak, peak_source = measured_peaks()
+	alg = algorithmic_bytes(bodies, contacts, 0, substeps) * worlds
+	achieved = alg / (ms_per_step * 1e-3) / 1e9
+	record = {
+		"metric": METRIC, "value": total_work / kernel_s, "unit": UNIT, "n_gpus": world_size, "steps": steps,
+		"warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+		"vs_baseline": None, "dtype": "f32", "data": "synthetic",
+		"config": {"workload": f"batch of {total_worlds} small_pyramid worlds", "worlds": total_worlds, "worlds_per_gpu": worlds,
+				   "bodies_per_world": bodies, "contacts_per_world": contacts, "substeps": substeps,
+				   "world_steps_per_sec": total_worlds * steps / kernel_s,
+				   "parallelism": f"worlds sharded over {world_size} GPU(s), no exchange",
+				   "l2": "flushed (256 MiB write) between timed iterations"},
+		"e2e": {"value": total_worlds * bodies / e2e_per_step, "unit": UNIT, "ms_per_step": e2e_per_step * 1e3,
+				"h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "last_step_split": split,
+				"timed": "b2GpuSolverStepBatch wall clock: host packing (library threads) + H2D + kernels + D2H + write-back"},
+		"gpu_launches": launches,
+		"roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+					 "traffic": measured_traffic("batch") if world_size == 1 else None,
+					 "algorithmic_bytes_per_launch": alg, "peak_source": peak_source, "grid_barriers_per_step": grid_barriers,
+					 "island_bins_blocks_per_bin": island_plan},
+		"clocks": clocks,
+	}
+	if cpu_baseline:
+		record["cpu_baseline"] = cpu_batch_baseline(total_worlds, 30, min(steps, 10))
+	return record
+
+
+def run_batch(args) -> int:
+	import torch.distributed as dist
+
+	world_size, rank, local_rank = _setup_distributed()
+	record = measure_batch(args, world_size, rank, local_rank, args.cpu_baseline and world_size == 1)
+	if record is not None:
+		print(json.dumps(record))
+	if world_size > 1:
 		dist.destroy_process_group()
 	return 0
 
@@ -567,6 +648,8 @@ def main() -> int:
 	ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
 	ap.add_argument("--workload", "--scene", dest="workload", default="many_pyramids", choices=SCENES + ("batch",))
 	ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+	ap.add_argument("--no-batch", dest="batch", action="store_false",
+					help="scene workloads: skip the 8192-world batch sub-record (north_star's multi-GPU configuration)")
 	args = ap.parse_args()
 	args.warmup = max(3, args.warmup)
 	if args.impl == "reference":

@@ -162,11 +162,15 @@ struct b2gJointSeg
 // bit, separations aside.  Homes follow the colour arrays, so both host passes walk the shadows front to back.
 struct b2gShadowContact
 {
-	uint32_t rows[b2g::kTableRows * 4]; // WR_HEAD .. WR_ANCHOR2 with the rolling impulse and the separations zeroed
-	uint32_t impulses[4];				// normalImpulse1, tangentImpulse1, normalImpulse2, tangentImpulse2
-	uint32_t rollingImpulse;
 	int contactId;
-	uint32_t reserved[2];
+	uint32_t rows[17]; // WR_HEAD.xyz, WR_NORMAL, WR_MATERIAL.xy, WR_ANCHOR1, WR_ANCHOR2
+};
+
+// ... and, in an array of their own (the unpack pass touches nothing else of the shadows): normalImpulse1, tangentImpulse1,
+// normalImpulse2, tangentImpulse2, rollingImpulse
+struct b2gShadowImpulses
+{
+	uint32_t values[5];
 };
 
 constexpr int kHomeColors = B2GPU_GRAPH_COLOR_COUNT;
@@ -241,6 +245,7 @@ struct b2GpuSolver
 	bool cacheUsable = false;	 // ... and this step's pack pass may rely on them
 	int parity = 0;				 // which of the double-buffered arrays this step WRITES (outAll, residentStates)
 	std::vector<b2gShadowContact> shadowContacts; // by home
+	std::vector<b2gShadowImpulses> shadowImpulses; // by home
 	int homeBase[kHomeColors + 1] = { 0 };		   // first home of every graph colour (persistent layout with spare room)
 	int homeCount[kHomeColors] = { 0 };			   // contacts the colour had in the previous resident step
 	int homeSlot[kHomeColors] = { 0 };			   // ... and the slot its array started at

@@ -144,6 +144,10 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 			// the list of the constraint: its bin, or -- owner lists -- the block that owns its first body (the overflow
 			// colour is solved by the cluster's first block)
 			bin = ownerLists ? ( isOverflow ? 0 : (int)__umulhi( (unsigned)first, P.clusterMagic ) ) : P.bodyBin[first];
+			if ( indexA >= 0 && indexB >= 0 && P.bodyBin[indexA] != P.bodyBin[indexB] )
+			{
+				*P.binFail = 1; // wrong island hint: the two bodies of a constraint must share an island (and so a bin)
+			}
 			key = bin * kColorSlots + c;
 		}
 		int rank = aggregatedAdd( P.binColorStart, key, active );
@@ -164,6 +168,13 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 				c += 1;
 			}
 			int body = jointBodyForBin( P.rawJoints + (size_t)j * kJointStride );
+			{
+				const int* pair = jointIndexPair( reinterpret_cast<b2lJointSim*>( const_cast<uint8_t*>( P.rawJoints + (size_t)j * kJointStride ) ) );
+				if ( pair != nullptr && pair[0] >= 0 && pair[1] >= 0 && P.bodyBin[pair[0]] != P.bodyBin[pair[1]] )
+				{
+					*P.binFail = 1;
+				}
+			}
 			// a filter joint has no solver data: park it in bin 0, it is a no-op in every stage
 			bin = body < 0 ? 0 : ownerLists ? ( c == P.colorCount ? 0 : (int)__umulhi( (unsigned)body, P.clusterMagic ) ) : P.bodyBin[body];
 			key = bin * kColorSlots + c;
@@ -339,6 +350,12 @@ __global__ void __launch_bounds__( 256 ) b2gScatterKernel( const __grid_constant
 		int bits = isOverflow ? 0 : __float_as_int( head.z ) & kMetaGroupMask;
 		int indexA = __float_as_int( head.x ), indexB = __float_as_int( head.y );
 		int bin = active ? P.bodyBin[indexA >= 0 ? indexA : indexB] : -1;
+		if ( active && indexA >= 0 && indexB >= 0 && P.bodyBin[indexB] != bin )
+		{
+			// the island hint is wrong (two bodies of one constraint in different islands): no partition, the grid-barrier
+			// kernel solves the step
+			*P.binFail = 1;
+		}
 		int position = aggregatedAdd( P.binColorStart, bin * kColorSlots, active );
 		if ( active )
 		{
@@ -371,6 +388,10 @@ __global__ void __launch_bounds__( 256 ) b2gScatterKernel( const __grid_constant
 			int body = bodies.x >= 0 ? bodies.x : bodies.y;
 			// a filter joint has no solver data: park it in bin 0, it is a no-op in every stage
 			bin = body < 0 ? 0 : P.bodyBin[body];
+			if ( bodies.x >= 0 && bodies.y >= 0 && P.bodyBin[bodies.y] != bin )
+			{
+				*P.binFail = 1; // wrong island hint, see the contacts above
+			}
 		}
 		int position = aggregatedAdd( P.binJointStart, bin * kColorSlots, active );
 		if ( active )

@@ -34,17 +34,29 @@
 // Host side
 // =================================================================================================================
 
+// The text of the last failure: of the calling thread if it had one, else of whichever thread failed last (the host passes
+// run on the caller's worker threads, the thread that asks is usually not the one that hit the error).
 static thread_local std::string t_lastError;
+static std::mutex g_errorMutex;
+static std::string g_lastError;
+static thread_local std::string t_errorReply;
+
+static void b2gRemember( const std::string& text )
+{
+	t_lastError = text;
+	std::lock_guard<std::mutex> lock( g_errorMutex );
+	g_lastError = text;
+}
 
 int b2gFail( const char* what, cudaError_t err )
 {
-	t_lastError = std::string( what ) + ": " + cudaGetErrorString( err );
+	b2gRemember( std::string( what ) + ": " + cudaGetErrorString( err ) );
 	return 1;
 }
 
 int b2gFailMsg( const char* what )
 {
-	t_lastError = what;
+	b2gRemember( what );
 	return 1;
 }
 
@@ -55,7 +67,13 @@ extern "C" int b2GpuGetVersion( void )
 
 extern "C" const char* b2GpuGetLastError( void )
 {
-	return t_lastError.c_str();
+	if ( !t_lastError.empty() )
+	{
+		return t_lastError.c_str();
+	}
+	std::lock_guard<std::mutex> lock( g_errorMutex );
+	t_errorReply = g_lastError;
+	return t_errorReply.c_str();
 }
 
 extern "C" int b2GpuGetDeviceCount( void )
@@ -1082,6 +1100,7 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 		if ( s->shadowContacts.size() < (size_t)s->homeTotal + 1 )
 		{
 			s->shadowContacts.resize( (size_t)s->homeTotal + 1, b2gShadowContact{} );
+			s->shadowImpulses.resize( (size_t)s->homeTotal + 1, b2gShadowImpulses{} );
 		}
 		if ( s->shadowStates.size() < 2 * nb + 2 )
 		{

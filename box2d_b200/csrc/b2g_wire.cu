@@ -264,20 +264,20 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 					continue;
 				}
 				// resident mode: the record the device would need, against the record it has
-				alignas( 16 ) float rows[b2g::kTableRows * 4] = {
-					b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta ), 0.0f,
+				alignas( 16 ) float rows[17] = {
+					b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta ),
 					b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ), b2gRdF( sim, B2L_CONTACT_FRICTION ), b2gRdF( sim, B2L_CONTACT_TANGENT_SPEED ),
-					b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ), b2gRdF( sim, B2L_CONTACT_RESTITUTION ), 0.0f, 0.0f,
+					b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ), b2gRdF( sim, B2L_CONTACT_RESTITUTION ),
 					b2gRdF( p0, B2L_MP_ANCHOR_A ), b2gRdF( p0, B2L_MP_ANCHOR_A + 4 ), b2gRdF( p0, B2L_MP_ANCHOR_B ), b2gRdF( p0, B2L_MP_ANCHOR_B + 4 ),
 					b2gRdF( p1, B2L_MP_ANCHOR_A ), b2gRdF( p1, B2L_MP_ANCHOR_A + 4 ), b2gRdF( p1, B2L_MP_ANCHOR_B ), b2gRdF( p1, B2L_MP_ANCHOR_B + 4 ) };
-				alignas( 16 ) float impulses[4] = { b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ),
-													b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ) };
+				float impulses[5] = { b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ), b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ),
+									  b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ), rollingImpulse };
 				const int id = b2gRdI( sim, B2L_CONTACT_ID );
 				const int home = homeBase + i;
 				b2gShadowContact& shadow = s->shadowContacts[(size_t)home];
+				b2gShadowImpulses& shadowImpulses = s->shadowImpulses[(size_t)home];
 				const bool clean = i < homeCount && shadow.contactId == id && memcmp( shadow.rows, rows, sizeof( rows ) ) == 0 &&
-								   memcmp( shadow.impulses, impulses, sizeof( impulses ) ) == 0 &&
-								   memcmp( &shadow.rollingImpulse, &rollingImpulse, 4 ) == 0;
+								   memcmp( shadowImpulses.values, impulses, sizeof( impulses ) ) == 0;
 				int ref = homeSlot + i; // its record among the previous step's outputs
 				if ( !clean )
 				{
@@ -285,14 +285,13 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 					ref = ~entry;
 					float4* w = s->hFull.ptr + (size_t)entry * b2g::WR_COUNT;
 					b2gStream4( w + b2g::WR_HEAD, rows[0], rows[1], rows[2], rollingImpulse );
-					b2gStream4( w + b2g::WR_NORMAL, rows[4], rows[5], rows[6], rows[7] );
-					b2gStream4( w + b2g::WR_MATERIAL, rows[8], rows[9], separation0, separation1 );
-					b2gStream4( w + b2g::WR_ANCHOR1, rows[12], rows[13], rows[14], rows[15] );
-					b2gStream4( w + b2g::WR_ANCHOR2, rows[16], rows[17], rows[18], rows[19] );
+					b2gStream4( w + b2g::WR_NORMAL, rows[3], rows[4], rows[5], rows[6] );
+					b2gStream4( w + b2g::WR_MATERIAL, rows[7], rows[8], separation0, separation1 );
+					b2gStream4( w + b2g::WR_ANCHOR1, rows[9], rows[10], rows[11], rows[12] );
+					b2gStream4( w + b2g::WR_ANCHOR2, rows[13], rows[14], rows[15], rows[16] );
 					b2gStream4( w + b2g::WR_IMPULSE, impulses[0], impulses[1], impulses[2], impulses[3] );
 					memcpy( shadow.rows, rows, sizeof( rows ) );
-					memcpy( shadow.impulses, impulses, sizeof( impulses ) );
-					memcpy( &shadow.rollingImpulse, &rollingImpulse, 4 );
+					memcpy( shadowImpulses.values, impulses, sizeof( impulses ) );
 					shadow.contactId = id;
 				}
 				b2gStream4( wire + slot, b2gIntBits( home | ( ( groupBits >> 3 ) << b2g::kLightGroupShift ) ), separation0, separation1, b2gIntBits( ref ) );
@@ -600,11 +599,11 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 				if ( s->resident )
 				{
 					// the manifold now holds what the device holds: remember it for the next pack pass
-					b2gShadowContact& shadow = s->shadowContacts[(size_t)( s->homeBase[s->segHome[k]] + i )];
-					memcpy( &shadow.rollingImpulse, rec + 0, 4 );
+					b2gShadowImpulses& shadow = s->shadowImpulses[(size_t)( s->homeBase[s->segHome[k]] + i )];
+					memcpy( shadow.values + 4, rec + 0, 4 );
 					for ( int j = 0; j < pointCount && j < 2; ++j )
 					{
-						memcpy( shadow.impulses + 2 * j, rec + 1 + 4 * j, 8 );
+						memcpy( shadow.values + 2 * j, rec + 1 + 4 * j, 8 );
 					}
 				}
 				if ( rec[9] != 0.0f && result != nullptr )

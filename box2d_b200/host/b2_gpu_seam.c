@@ -39,6 +39,7 @@ typedef struct b2SeamSlot
 	b2GpuSeamTotals totals;
 	b2GpuStepResult lastResult;
 	b2GpuStepDesc lastDesc;
+	uint16_t generation;  /* of the world the solver was created for (b2World::generation, bumped by b2DestroyWorld) */
 	bool islandsCaptured; /* b2GpuSeam_BeforeIslandSplit filled the hint of the step in flight */
 	int capturedIslandCount;
 } b2SeamSlot;
@@ -59,11 +60,29 @@ static void b2SeamFatal( const char* what )
 	abort();
 }
 
+static void b2SeamReleaseSlot( b2SeamSlot* slot )
+{
+	if ( slot->solver != NULL )
+	{
+		b2GpuSolverDestroy( slot->solver );
+	}
+	free( slot->islandLabels );
+	free( slot->islandSizes );
+	memset( slot, 0, sizeof( *slot ) );
+}
+
 static b2SeamSlot* b2SeamGetSlot( b2World* world )
 {
 	b2SeamSlot* slot = s_slots + world->worldId;
+	if ( slot->solver != NULL && slot->generation != world->generation )
+	{
+		// the slot's previous world was destroyed (src/physics_world.c, b2DestroyWorld bumps the generation): its device
+		// buffers, resident copies and planner state must not leak into the world that reuses the id
+		b2SeamReleaseSlot( slot );
+	}
 	if ( slot->solver == NULL )
 	{
+		slot->generation = world->generation;
 		int device = b2SeamEnvInt( "B2GPU_DEVICE", 0 );
 		slot->solver = b2GpuSolverCreate( device );
 		if ( slot->solver == NULL )
@@ -93,18 +112,21 @@ void b2GpuSeam_Shutdown( void )
 {
 	for ( int i = 0; i < B2_MAX_WORLDS; ++i )
 	{
-		if ( s_slots[i].solver != NULL )
-		{
-			b2GpuSolverDestroy( s_slots[i].solver );
-			s_slots[i].solver = NULL;
-			free( s_slots[i].islandLabels );
-			s_slots[i].islandLabels = NULL;
-			s_slots[i].islandLabelCapacity = 0;
-			free( s_slots[i].islandSizes );
-			s_slots[i].islandSizes = NULL;
-			s_slots[i].islandSizeCapacity = 0;
-		}
+		b2SeamReleaseSlot( s_slots + i );
 	}
+}
+
+void b2GpuSeam_ReleaseWorld( int worldIndex )
+{
+	if ( 0 <= worldIndex && worldIndex < B2_MAX_WORLDS )
+	{
+		b2SeamReleaseSlot( s_slots + worldIndex );
+	}
+}
+
+int b2GpuSeam_HasSolver( int worldIndex )
+{
+	return 0 <= worldIndex && worldIndex < B2_MAX_WORLDS && s_slots[worldIndex].solver != NULL ? 1 + (int)s_slots[worldIndex].generation : 0;
 }
 
 const b2GpuStepResult* b2GpuSeam_GetLastResult( int worldIndex )

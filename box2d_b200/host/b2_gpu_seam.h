@@ -68,6 +68,11 @@ void b2GpuSeam_SetMode( int mode );
 
 /* Destroy all device solvers created by the seam. */
 void b2GpuSeam_Shutdown( void );
+/* Device solvers are created lazily per world id and follow the world's generation: a world that reuses a destroyed world's id
+ * gets a fresh solver at its first step.  ReleaseWorld frees a destroyed world's device memory right away (optional).
+ * HasSolver: 0 = the slot has no solver, else 1 + the generation it belongs to (tests). */
+void b2GpuSeam_ReleaseWorld( int worldIndex );
+int b2GpuSeam_HasSolver( int worldIndex );
 
 #ifdef __cplusplus
 }

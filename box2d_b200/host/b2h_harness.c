@@ -41,6 +41,11 @@ typedef struct b2hWorld
 	int hasHinges;
 	b2BodyId kinematicId; // moved every step in contact_zoo
 	int hasKinematic;
+	// the "mutator" scene: handles the per-step callback pokes through the public API
+	b2BodyId mutBodies[64];
+	b2ShapeId mutShapes[64];
+	b2JointId mutJoints[8];
+	int mutBodyCount, mutJointCount;
 } b2hWorld;
 
 static b2hWorld s_worlds[B2H_MAX_WORLDS];
@@ -457,7 +462,173 @@ static void b2hCreateOverflow( b2WorldId worldId )
 	}
 }
 
+/* A base-9 pyramid next to a chain of boxes on revolute joints, and a per-step callback that changes the world BETWEEN steps
+ * through the public API the way an application does: gravity, velocities, impulses and forces, masses, friction and
+ * restitution, joint motors and springs, contact and joint tuning, warm starting, teleports, body types, disabling, destroying
+ * and creating bodies, the sub-step count.  Whatever a solver keeps from one step to the next must notice every one of these. */
+static void b2hCreateMutator( b2WorldId worldId, b2hWorld* w )
+{
+	b2World_EnableSleeping( worldId, false );
+	b2hGround( worldId, 40.0f );
+	b2ShapeDef shapeDef = b2DefaultShapeDef();
+	shapeDef.enableHitEvents = true;
+	b2Polygon box = b2MakeSquare( 0.5f );
+	int n = 0;
+	for ( int i = 0; i < 9; ++i )
+	{
+		for ( int j = i; j < 9; ++j )
+		{
+			b2BodyDef bodyDef = b2DefaultBodyDef();
+			bodyDef.type = b2_dynamicBody;
+			bodyDef.position = (b2Pos){ -12.0f + ( i + 1.0f ) * 0.5f + ( j - i ) * 1.0f, ( 2.0f * i + 1.0f ) * 0.5f };
+			b2BodyId bodyId = b2CreateBody( worldId, &bodyDef );
+			b2ShapeId shapeId = b2CreatePolygonShape( bodyId, &shapeDef, &box );
+			if ( n < 48 )
+			{
+				w->mutBodies[n] = bodyId;
+				w->mutShapes[n] = shapeId;
+				n += 1;
+			}
+		}
+	}
+	// a chain hanging from a static anchor, dragging over the ground
+	b2BodyDef anchorDef = b2DefaultBodyDef();
+	anchorDef.position = (b2Pos){ 6.0f, 6.0f };
+	b2BodyId previous = b2CreateBody( worldId, &anchorDef );
+	for ( int i = 0; i < 8; ++i )
+	{
+		b2BodyId link = b2hBox( worldId, b2_dynamicBody, 6.5f + 1.0f * i, 6.0f, 0.5f, 0.125f, 0.0f );
+		b2RevoluteJointDef rev = b2DefaultRevoluteJointDef();
+		rev.base.bodyIdA = previous;
+		rev.base.bodyIdB = link;
+		rev.base.localFrameA.p = i == 0 ? (b2Vec2){ 0.0f, 0.0f } : (b2Vec2){ 0.5f, 0.0f };
+		rev.base.localFrameB.p = (b2Vec2){ -0.5f, 0.0f };
+		rev.maxMotorTorque = 20.0f;
+		w->mutJoints[i] = b2CreateRevoluteJoint( worldId, &rev );
+		w->mutBodies[n] = link;
+		w->mutShapes[n] = (b2ShapeId){ 0 };
+		n += 1;
+		previous = link;
+	}
+	w->mutBodyCount = n;
+	w->mutJointCount = 8;
+}
+
+static b2hWorld* b2hFind( b2WorldId worldId );
+
+static float b2hStepMutator( b2WorldId worldId, int stepIndex )
+{
+	b2hWorld* w = b2hFind( worldId );
+	if ( w == NULL )
+	{
+		return 0.0f;
+	}
+	b2BodyId* body = w->mutBodies;
+	switch ( stepIndex )
+	{
+		case 8:
+			b2World_SetGravity( worldId, (b2Vec2){ 1.5f, -6.0f } );
+			break;
+		case 14:
+			b2Body_SetLinearVelocity( body[40], (b2Vec2){ 3.0f, 4.0f } );
+			b2Body_ApplyAngularImpulse( body[20], 1.5f, true );
+			b2Body_ApplyLinearImpulseToCenter( body[3], (b2Vec2){ -2.0f, 0.5f }, true );
+			break;
+		case 20:
+		{
+			// a body under persisting contacts gets three times its mass: the contacts remember the old one
+			b2MassData massData = b2Body_GetMassData( body[10] );
+			massData.mass *= 3.0f;
+			massData.rotationalInertia *= 3.0f;
+			b2Body_SetMassData( body[10], massData );
+			b2Body_SetGravityScale( body[11], 0.25f );
+			b2Body_SetLinearDamping( body[12], 0.8f );
+			break;
+		}
+		case 26:
+			for ( int i = 0; i < 12; ++i )
+			{
+				b2Shape_SetFriction( w->mutShapes[2 * i], 0.05f + 0.07f * i );
+				b2Shape_SetRestitution( w->mutShapes[2 * i + 1], 0.1f * ( i % 5 ) );
+			}
+			break;
+		case 32:
+			b2RevoluteJoint_EnableMotor( w->mutJoints[0], true );
+			b2RevoluteJoint_SetMotorSpeed( w->mutJoints[0], 1.5f );
+			b2RevoluteJoint_EnableSpring( w->mutJoints[3], true );
+			b2RevoluteJoint_SetSpringHertz( w->mutJoints[3], 3.0f );
+			b2Joint_SetConstraintTuning( w->mutJoints[5], 30.0f, 1.0f );
+			break;
+		case 38:
+			b2World_SetContactTuning( worldId, 20.0f, 5.0f, 2.0f );
+			break;
+		case 44:
+			b2World_EnableWarmStarting( worldId, false );
+			break;
+		case 48:
+			b2World_EnableWarmStarting( worldId, true );
+			b2World_SetGravity( worldId, (b2Vec2){ 0.0f, -10.0f } );
+			break;
+		case 54:
+			b2Body_SetTransform( body[44], (b2Pos){ -3.0f, 9.0f }, b2MakeRot( 0.4f ) );
+			b2RevoluteJoint_SetMotorSpeed( w->mutJoints[0], -2.0f );
+			break;
+		case 60:
+			b2Body_SetType( body[30], b2_kinematicBody );
+			b2Body_SetLinearVelocity( body[30], (b2Vec2){ 0.5f, 0.0f } );
+			b2Body_Disable( body[5] );
+			break;
+		case 66:
+			b2Body_SetType( body[30], b2_dynamicBody );
+			b2Body_Enable( body[5] );
+			break;
+		case 72:
+			// swap-removes in the solver arrays and the colour arrays, ids handed out again
+			b2DestroyBody( body[7] );
+			body[7] = b2hBox( worldId, b2_dynamicBody, -5.0f, 12.0f, 0.5f, 0.5f, 0.2f );
+			b2DestroyBody( body[22] );
+			body[22] = b2hBox( worldId, b2_dynamicBody, -7.0f, 14.0f, 0.4f, 0.6f, -0.3f );
+			break;
+		case 78:
+			b2World_SetMaximumLinearSpeed( worldId, 3.0f ); /* speed caps: the flag travels in the body state */
+			b2Body_SetLinearVelocity( body[41], (b2Vec2){ 30.0f, 10.0f } );
+			break;
+		case 82:
+			b2World_SetMaximumLinearSpeed( worldId, 400.0f );
+			b2World_SetRestitutionThreshold( worldId, 0.2f );
+			b2World_SetHitEventThreshold( worldId, 0.1f );
+			break;
+		case 88:
+			w->subStepCount = 6;
+			break;
+		case 94:
+			w->subStepCount = 4;
+			b2World_EnableSleeping( worldId, true );
+			break;
+		default:
+			break;
+	}
+	if ( 100 <= stepIndex && stepIndex < 110 )
+	{
+		b2Body_ApplyForceToCenter( body[1], (b2Vec2){ 40.0f, 0.0f }, true );
+		b2Body_ApplyTorque( body[2], 15.0f, true );
+	}
+	return 0.0f;
+}
+
 /* ---- API ----------------------------------------------------------------------------------------------------- */
+
+static b2hWorld* b2hFind( b2WorldId worldId )
+{
+	for ( int i = 0; i < B2H_MAX_WORLDS; ++i )
+	{
+		if ( s_worlds[i].inUse && s_worlds[i].worldId.index1 == worldId.index1 && s_worlds[i].worldId.generation == worldId.generation )
+		{
+			return s_worlds + i;
+		}
+	}
+	return NULL;
+}
 
 B2H_API int b2h_create( const char* scene, int workerCount )
 {
@@ -558,6 +729,11 @@ B2H_API int b2h_create( const char* scene, int workerCount )
 	else if ( strcmp( scene, "overflow" ) == 0 )
 	{
 		b2hCreateOverflow( w->worldId );
+	}
+	else if ( strcmp( scene, "mutator" ) == 0 )
+	{
+		b2hCreateMutator( w->worldId, w );
+		w->stepFcn = b2hStepMutator;
 	}
 	else
 	{

@@ -99,3 +99,26 @@ def test_island_sizes_from_labels(capture_files):
 		if valid.all():
 			assert sizes[:, 1].sum() == cap.contact_count
 		assert (sizes[:, 3] == 0).all()
+
+
+def test_no_device_means_a_loud_abort_not_a_cpu_fallback():
+	"""north_star: no CPU fallback.  Without a CUDA device the first b2World_Step of the product library aborts with a message
+	(box2d_b200/host/b2_gpu_seam.c, b2SeamFatal) instead of solving on the host."""
+	import os
+	import subprocess
+	import sys
+
+	if not (b2.PKG_DIR / "libbox2d_b200.so").is_file():
+		pytest.skip("host library not built")
+	code = (
+		"import box2d_b200 as b2\n"
+		"lib = b2.host_lib()\n"
+		"w = b2.World(lib, 'small_pyramid', 1)\n"
+		"w.step(3)\n"
+		"print('stepped without a device')\n"
+	)
+	env = dict(os.environ, CUDA_VISIBLE_DEVICES="", PYTHONPATH=str(b2.ROOT))
+	proc = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+	assert proc.returncode != 0, proc.stdout
+	assert "stepped without a device" not in proc.stdout
+	assert "cannot create the device solver" in proc.stderr and "no CPU fallback" in proc.stderr, proc.stderr

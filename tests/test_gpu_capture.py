@@ -184,3 +184,23 @@ def test_wrong_island_sizes_only_cost_time(solver, capture_files, distortion):
 		assert desc.islandSizes == ctypes.addressof(bufs["sizes"])
 		solver.step(desc, result)
 		_check(cap, bufs, result)
+
+
+def test_wrong_island_labels_never_change_the_result(solver, capture_files):
+	"""b2GpuStepDesc::bodyIsland is a hint: labels that put the two bodies of a constraint into different islands (with or
+	without sizes) are noticed on the device and the step is solved by the grid-barrier kernel instead -- same bits."""
+	solver.set_mode(0)
+	rng = np.random.default_rng(5)
+	fallbacks = 0
+	for path in capture_files:
+		cap = b2.Capture(path)
+		if cap.desc.islandCount < 2 or cap.contact_count + cap.joint_count == 0:
+			continue
+		for sizes in (False, True):
+			desc, result, bufs = cap.make_call(sizes=sizes)
+			labels = bufs["islands"]
+			labels[:] = rng.integers(0, cap.desc.islandCount, size=labels.size, dtype=np.int32)
+			solver.step(desc, result)
+			_check(cap, bufs, result)
+			fallbacks += 1 if result.gridBarriers > 0 else 0
+	assert fallbacks > 0, "scrambled labels never reached the device check"

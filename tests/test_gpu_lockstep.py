@@ -2,6 +2,8 @@
 lockstep; b2World_GetStateHash (include/box2d/box2d.h:235) must agree EVERY step -- the idiom of the reference's
 test/test_snapshot.c:258-283.  The hash covers transforms, velocities, contact impulses, joint impulses and the
 graph layout, so agreement means the whole hot path is bit-exact, including its side outputs feeding events/sleep."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -28,6 +30,18 @@ SCENES = [
 	("smash", 60, 5),
 	("compounds", 40, 5),
 	("washer", 40, 5),
+	# the host changes the world between steps through the public API (box2d_b200/host/b2h_harness.c, b2hStepMutator): gravity,
+	# velocities, masses, friction, motors, tuning, warm starting, teleports, body types, destroy / create, sub-step count
+	("mutator", 130, 1),
+]
+
+# BASELINE.json's configurations at the step counts of the reference's benchmark (benchmark/main.c:149-160), compared EVERY step
+FULL_SCALE = [
+	("large_pyramid", 500),
+	("many_pyramids", 200),
+	("joint_grid", 500),
+	("rain", 1000),
+	("tumbler", 750),
 ]
 
 
@@ -61,6 +75,32 @@ def test_lockstep_state_hash(ref_lib, gpu_host_lib, golden_hashes, scene, steps,
 		assert result.kernelLaunches >= 1
 
 
+@pytest.mark.parametrize("scene,steps", FULL_SCALE, ids=[s[0] for s in FULL_SCALE])
+def test_lockstep_at_benchmark_scale(ref_lib, gpu_host_lib, scene, steps):
+	"""The five benchmark scenes for as many steps as benchmark/main.c runs them, the state hash compared after every single
+	step (rain: spawn / destroy / sleep churn to the end; tumbler: the overflow colour all the way)."""
+	workers = 8
+	with b2.World(ref_lib, scene, workers) as ref, b2.World(gpu_host_lib, scene, workers) as gpu:
+		for step in range(1, steps + 1):
+			ref.step()
+			gpu.step()
+			assert gpu.hash() == ref.hash(), f"{scene}: state hash diverged at step {step}: {_diagnose(ref, gpu)}"
+		assert gpu.events() == ref.events()
+		assert gpu.counters() == ref.counters()
+
+
+def test_profile_stage_fields_come_from_the_device(gpu_host_lib):
+	"""b2Profile's solver stage split (include/box2d/types.h:526-551) keeps being filled on the GPU path: device time per stage
+	group, all of it inside b2Profile.constraints."""
+	with b2.World(gpu_host_lib, "many_pyramids", 4) as gpu:
+		gpu.step(5)
+		p = gpu.profile()
+		stages = [p[n] for n in b2.STAGE_NAMES if n != "applyRestitution"]
+		assert all(v > 0.0 for v in stages), p
+		assert sum(p[n] for n in b2.STAGE_NAMES) <= p["constraints"], p
+		assert p["constraints"] <= p["solve"] <= p["step"]
+
+
 def test_multi_launch_mode_matches(ref_lib, gpu_host_lib):
 	gpu_host_lib.b2GpuSeam_SetMode(1)
 	try:
@@ -71,3 +111,20 @@ def test_multi_launch_mode_matches(ref_lib, gpu_host_lib):
 				assert gpu.hash() == ref.hash()
 	finally:
 		gpu_host_lib.b2GpuSeam_SetMode(0)
+
+
+def test_world_ids_are_reused_with_a_fresh_solver(ref_lib, gpu_host_lib):
+	"""Device solvers follow the world's generation (box2d_b200/host/b2_gpu_seam.c): a world created in a destroyed world's
+	slot starts from a fresh solver -- no buffers, resident copies or planner state of its predecessor."""
+	gpu_host_lib.b2GpuSeam_HasSolver.restype = ctypes.c_int
+	gpu_host_lib.b2GpuSeam_HasSolver.argtypes = [ctypes.c_int]
+	seen = []
+	for scene in ("small_pyramid", "joint_zoo", "small_pyramid"):
+		with b2.World(ref_lib, scene, 2) as ref, b2.World(gpu_host_lib, scene, 2) as gpu:
+			for _ in range(25):
+				ref.step()
+				gpu.step()
+				assert gpu.hash() == ref.hash(), scene
+			seen.append((gpu.world_index(), gpu_host_lib.b2GpuSeam_HasSolver(gpu.world_index())))
+	assert seen[0][0] == seen[1][0] == seen[2][0], "the world id was not reused"
+	assert len({tag for _, tag in seen}) == 3 and all(tag > 0 for _, tag in seen), seen
