@@ -64,7 +64,13 @@ class StepDesc(ctypes.Structure):
 		("contactIdCapacity", ctypes.c_int), ("jointIdCapacity", ctypes.c_int),
 		("bodyIsland", ctypes.c_void_p), ("islandCount", ctypes.c_int), ("reserved0", ctypes.c_int),
 		("islandSizes", ctypes.c_void_p),
+		("recycled", ctypes.c_void_p), ("recycledStamp", ctypes.c_uint32),
+		("recycledStart", ctypes.c_int * (MAX_ACTIVE_COLORS + 1)), ("recycledCount", ctypes.c_int * (MAX_ACTIVE_COLORS + 1)),
 	]
+
+
+class RecycledContact(ctypes.Structure):
+	_fields_ = [("stamp", ctypes.c_uint32), ("contactId", ctypes.c_int), ("separation", ctypes.c_float * 2)]
 
 
 class IslandSize(ctypes.Structure):
@@ -173,7 +179,7 @@ def solver_lib() -> ctypes.CDLL:
 	lib.b2GpuCountIslandSizes.restype = ctypes.c_int
 	lib.b2GpuCountIslandSizes.argtypes = [P(StepDesc), P(IslandSize)]
 	lib.b2GpuSolverGetResidentStats.restype = ctypes.c_int
-	lib.b2GpuSolverGetResidentStats.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+	lib.b2GpuSolverGetResidentStats.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int)] * 3
 	lib.b2GpuSolverGetIslandPlan.restype = ctypes.c_int
 	lib.b2GpuSolverGetIslandPlan.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
 	_solver_lib = lib
@@ -222,6 +228,8 @@ def host_lib() -> ctypes.CDLL:
 	lib.b2GpuSeam_GetLastDesc.argtypes = [ctypes.c_int]
 	lib.b2GpuSeam_GetTotals.restype = None
 	lib.b2GpuSeam_GetTotals.argtypes = [ctypes.c_int, ctypes.POINTER(SeamTotals), ctypes.c_int]
+	lib.b2GpuSeam_GetResidentStats.restype = ctypes.c_int
+	lib.b2GpuSeam_GetResidentStats.argtypes = [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3
 	lib.b2GpuSeam_InstallPinnedAllocator.restype = None
 	lib.b2GpuSeam_Shutdown.restype = None
 	_host_lib = lib
@@ -523,9 +531,15 @@ class GpuSolver:
 	def resident_stats(self):
 		"""(full contact records, dirty bodies) of the last step, or None when it did not run in resident mode."""
 		full, dirty = ctypes.c_int(0), ctypes.c_int(0)
-		if self.lib.b2GpuSolverGetResidentStats(self.handle, ctypes.byref(full), ctypes.byref(dirty)) == 0:
+		if self.lib.b2GpuSolverGetResidentStats(self.handle, ctypes.byref(full), ctypes.byref(dirty), None) == 0:
 			return None
 		return full.value, dirty.value
+
+	def vouched_contacts(self) -> int:
+		"""Contacts of the last step the pack pass took on the caller's word (b2GpuStepDesc::recycled)."""
+		n = ctypes.c_int(0)
+		self.lib.b2GpuSolverGetResidentStats(self.handle, None, None, ctypes.byref(n))
+		return n.value
 
 	def close(self) -> None:
 		if self.handle:

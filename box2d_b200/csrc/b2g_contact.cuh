@@ -175,6 +175,7 @@ B2G_DEV void prepareContact( const StepParams& P, const SolveView& V, int wireSl
 							 float4 sB, bool wide, int groupBits )
 {
 	float4 head, nrm, mat, imp, anchor1, anchor2;
+	bool massFromBodies = P.massFromBodies != 0;
 	if ( P.light == nullptr )
 	{
 		const float4* w = P.wire + (size_t)wireSlot * WR_COUNT;
@@ -190,6 +191,7 @@ B2G_DEV void prepareContact( const StepParams& P, const SolveView& V, int wireSl
 		float4 L = P.light[wireSlot];
 		int key = __float_as_int( L.x ), ref = __float_as_int( L.w );
 		const float4* w = ref < 0 ? P.full + (size_t)( ~ref ) * WR_COUNT : P.table + (size_t)( key & kLightIdMask ) * kTableRows;
+		massFromBodies = massFromBodies || ( key & kLightBodyMass ) != 0;
 		head = w[WR_HEAD];
 		nrm = w[WR_NORMAL];
 		mat = w[WR_MATERIAL];
@@ -211,7 +213,7 @@ B2G_DEV void prepareContact( const StepParams& P, const SolveView& V, int wireSl
 		}
 	}
 	float4 mass;
-	if ( P.massFromBodies != 0 )
+	if ( massFromBodies )
 	{
 		// the contact's masses are its bodies' (the pack pass compared them bit for bit); a static body has none
 		int indexA = __float_as_int( head.x ), indexB = __float_as_int( head.y );

@@ -145,6 +145,9 @@ struct b2gContactSeg
 	int world;
 	bool wide; // false for the overflow colour
 	int colorIndex;
+	const b2GpuRecycledContact* hints; // optional (b2GpuStepDesc::recycled), entry i describes contact i
+	int hintCount;
+	uint32_t hintStamp;
 };
 
 struct b2gJointSeg
@@ -162,8 +165,17 @@ struct b2gJointSeg
 // bit, separations aside.  Homes follow the colour arrays, so both host passes walk the shadows front to back.
 struct b2gShadowContact
 {
-	int contactId;
 	uint32_t rows[17]; // WR_HEAD.xyz, WR_NORMAL, WR_MATERIAL.xy, WR_ANCHOR1, WR_ANCHOR2
+};
+
+// ... what the pack pass needs of a contact that comes with a valid b2GpuRecycledContact (nothing else is read then): who
+// lives at the home, its bodies (they may move in the awake set while the manifold is recycled) and whether it has rolling
+// resistance / restitution (kMetaGroup* bits of its own, OR-ed over its SIMD group)
+struct b2gShadowHead
+{
+	int contactId;
+	int indexA, indexB;
+	int ownBits;
 };
 
 // ... and, in an array of their own (the unpack pass touches nothing else of the shadows): normalImpulse1, tangentImpulse1,
@@ -246,6 +258,7 @@ struct b2GpuSolver
 	int parity = 0;				 // which of the double-buffered arrays this step WRITES (outAll, residentStates)
 	std::vector<b2gShadowContact> shadowContacts; // by home
 	std::vector<b2gShadowImpulses> shadowImpulses; // by home
+	std::vector<b2gShadowHead> shadowHeads;		   // by home
 	int homeBase[kHomeColors + 1] = { 0 };		   // first home of every graph colour (persistent layout with spare room)
 	int homeCount[kHomeColors] = { 0 };			   // contacts the colour had in the previous resident step
 	int homeSlot[kHomeColors] = { 0 };			   // ... and the slot its array started at
@@ -261,7 +274,7 @@ struct b2GpuSolver
 	int wireQuads = b2g::WR_COUNT; // quads per contact slot in the input arena: WR_COUNT, or 1 (light records)
 	int fullSent = 0, dirtySent = 0;
 	std::atomic<int> streamOverflow{ 0 };
-	std::atomic<int> fullCount{ 0 }, dirtyCount{ 0 }; // records actually written (statistics)
+	std::atomic<int> fullCount{ 0 }, dirtyCount{ 0 }, vouchedCount{ 0 }; // records actually written / contacts taken on the caller's word (statistics)
 
 	// page-locked staging owned by the library.  The input staging is written with non-temporal stores: on the
 	// target hosts a DMA read of lines that sit dirty in several cores' caches runs at ~6 GB/s instead of ~53 GB/s

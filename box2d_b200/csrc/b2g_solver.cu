@@ -342,7 +342,7 @@ extern "C" int b2GpuSolverGetIslandPlan( const b2GpuSolver* s, int* binCount, in
 	return bins;
 }
 
-extern "C" int b2GpuSolverGetResidentStats( const b2GpuSolver* s, int* fullContacts, int* dirtyBodies )
+extern "C" int b2GpuSolverGetResidentStats( const b2GpuSolver* s, int* fullContacts, int* dirtyBodies, int* vouchedContacts )
 {
 	if ( s == nullptr || !s->resident )
 	{
@@ -355,6 +355,10 @@ extern "C" int b2GpuSolverGetResidentStats( const b2GpuSolver* s, int* fullConta
 	if ( dirtyBodies != nullptr )
 	{
 		*dirtyBodies = s->dirtyCount.load( std::memory_order_relaxed );
+	}
+	if ( vouchedContacts != nullptr )
+	{
+		*vouchedContacts = s->vouchedCount.load( std::memory_order_relaxed );
 	}
 	return 1;
 }
@@ -908,6 +912,9 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 					seg.world = w;
 					seg.wide = !isOverflow;
 					seg.colorIndex = color.colorIndex;
+					seg.hints = dw.recycled != nullptr && dw.recycledCount[c] > 0 ? dw.recycled + dw.recycledStart[c] : nullptr;
+					seg.hintCount = seg.hints != nullptr ? dw.recycledCount[c] : 0;
+					seg.hintStamp = dw.recycledStamp;
 				}
 				if ( color.jointCount > 0 )
 				{
@@ -1097,10 +1104,12 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 		s->streamOverflow.store( 0, std::memory_order_relaxed );
 		s->fullCount.store( 0, std::memory_order_relaxed );
 		s->dirtyCount.store( 0, std::memory_order_relaxed );
+		s->vouchedCount.store( 0, std::memory_order_relaxed );
 		if ( s->shadowContacts.size() < (size_t)s->homeTotal + 1 )
 		{
 			s->shadowContacts.resize( (size_t)s->homeTotal + 1, b2gShadowContact{} );
 			s->shadowImpulses.resize( (size_t)s->homeTotal + 1, b2gShadowImpulses{} );
+			s->shadowHeads.resize( (size_t)s->homeTotal + 1, b2gShadowHead{ -1, -1, -1, 0 } );
 		}
 		if ( s->shadowStates.size() < 2 * nb + 2 )
 		{

@@ -77,8 +77,10 @@ constexpr int kMetaColorShift = 8;
 // records (ref = its slot in that step); anything else -- a re-evaluated manifold, a contact that is new at its home
 // after a swap-remove (src/constraint_graph.c:198-211) -- travels as a FULL record (ref = ~index into the step's full
 // stream) and is copied into the table after the solve.
-//   key  bits 0..27 home, bit 28/29 the SIMD-group bits (kMetaGroup*), negative = dead slot
+//   key  bits 0..27 home, bit 28/29 the SIMD-group bits (kMetaGroup*), bit 30: the contact's inverse masses are its
+//        bodies' (nothing was written to the mass region for it), negative = dead slot
 constexpr int kLightIdMask = ( 1 << 28 ) - 1;
+constexpr int kLightBodyMass = 1 << 30;
 constexpr int kLightGroupShift = 28; // key >> 28 & 3 -> kMetaGroupRolling | kMetaGroupRestitution after << 3
 constexpr int kTableRows = 5;		 // WR_HEAD .. WR_ANCHOR2 of a contact, by home
 constexpr int kDirtyBodyQuads = 5;	 // { body index, -, -, - }, the b2BodyState (2 quads), the packed constants (2 quads)

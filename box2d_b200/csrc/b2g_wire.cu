@@ -188,6 +188,7 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		const bool usable = s->cacheUsable;
 		b2gStreamChunk full = { &s->fullCursor, s->fullCapacity, 0, 0, &s->streamOverflow };
 		bool massDiffers = false;
+		int vouchedTotal = 0;
 		int flat = ( begin > bodyCount ? begin : bodyCount ) - bodyCount;
 		int flatEnd = ( end - bodyCount < s->contactTotal ? end - bodyCount : s->contactTotal );
 		int k = flat < flatEnd ? b2gFindSegment( s->contactStart, flat ) : 0;
@@ -199,102 +200,137 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 			int localEnd = ( flatEnd < s->contactStart[k + 1] ? flatEnd : s->contactStart[k + 1] ) - segFlat;
 			int bodyBase = s->bodySegs[seg.world].base;
 			const uint8_t* worldSims = s->bodySegs[seg.world].sims;
-			int groupOf = -1, groupBits = 0;
 			// resident mode: the segment's homes, how many of them were occupied in the previous step and where they were then
 			const int homeKey = resident ? s->segHome[k] : 0;
 			const int homeBase = resident ? s->homeBase[homeKey] : 0;
 			const int homeCount = resident && usable ? s->homeCount[homeKey] : 0;
 			const int homeSlot = resident ? s->homeSlot[homeKey] : 0;
-			for ( int i = local; i < localEnd; ++i )
+			const int hintCount = resident && usable && seg.hints != nullptr ? ( seg.hintCount < homeCount ? seg.hintCount : homeCount ) : 0;
+			// The contacts are walked in the reference's SIMD groups: aligned groups of 4 contacts of the colour's array.  The
+			// reference skips rolling resistance / restitution for a whole register when all its lanes have none
+			// (src/contact_solver.c:2021, :2131; 4 lanes in the default build), so every contact needs to know whether ANY
+			// member of its group has some (x == 0 is false for NaN, like _mm_cmpeq_ps).  Members outside [local, localEnd)
+			// belong to another pack block: they are only looked at.
+			for ( int group = local & ~3; group < localEnd; group += 4 )
 			{
-				const uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
-				const uint8_t* m = sim + B2L_CONTACT_MANIFOLD;
-				const uint8_t* p0 = m + B2L_MANIFOLD_POINTS;
-				const uint8_t* p1 = p0 + B2L_MP_SIZE;
-				int pointCount = b2gRdI( m, B2L_MANIFOLD_POINT_COUNT );
-				int hitEnable = ( (uint32_t)b2gRdI( sim, B2L_CONTACT_SIM_FLAGS ) & B2L_SIM_ENABLE_HIT_EVENT ) != 0 ? b2g::kMetaHitEnable : 0;
-				int meta = ( seg.colorIndex << b2g::kMetaColorShift ) | hitEnable | ( pointCount & b2g::kMetaPointMask );
-				if ( seg.wide && ( i >> 2 ) != groupOf )
+				const int groupEnd = group + 4 < seg.count ? group + 4 : seg.count;
+				bool vouched[4] = { false, false, false, false };
+				int groupBits = 0;
+				for ( int j = group; j < groupEnd; ++j )
 				{
-					// The reference skips rolling resistance / restitution for a whole SIMD register when all its lanes have none
-					// (src/contact_solver.c:2021, :2131; 4 lanes in the default build): the test is over the aligned group of 4
-					// contacts of the colour's array this one belongs to.  x == 0 is false for NaN, like _mm_cmpeq_ps.
-					groupOf = i >> 2;
-					groupBits = 0;
-					int groupEnd = 4 * groupOf + 4 < seg.count ? 4 * groupOf + 4 : seg.count;
-					for ( int j = 4 * groupOf; j < groupEnd; ++j )
+					const uint8_t* sim = seg.sims + (size_t)j * B2L_CONTACT_SIZE;
+					int ownBits = -1;
+					if ( j < hintCount )
 					{
-						const uint8_t* other = seg.sims + (size_t)j * B2L_CONTACT_SIZE;
-						groupBits |= !( b2gRdF( other, B2L_CONTACT_ROLLING_RESISTANCE ) == 0.0f ) ? b2g::kMetaGroupRolling : 0;
-						groupBits |= !( b2gRdF( other, B2L_CONTACT_RESTITUTION ) == 0.0f ) ? b2g::kMetaGroupRestitution : 0;
+						// A contact the narrow phase recycled (b2GpuStepDesc::recycled): if it still is where it was in the
+						// previous step, with the same bodies, the device has everything but the separations -- nothing of
+						// its record is read beyond the first cache line.
+						const b2GpuRecycledContact& hint = seg.hints[j];
+						const b2gShadowHead& head = s->shadowHeads[(size_t)( homeBase + j )];
+						const int id = b2gRdI( sim, B2L_CONTACT_ID );
+						if ( hint.stamp == seg.hintStamp && hint.contactId == id && head.contactId == id &&
+							 head.indexA == b2gRdI( sim, B2L_CONTACT_INDEX_A ) && head.indexB == b2gRdI( sim, B2L_CONTACT_INDEX_B ) )
+						{
+							vouched[j - group] = true;
+							ownBits = head.ownBits;
+						}
 					}
+					if ( ownBits < 0 )
+					{
+						ownBits = ( !( b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ) == 0.0f ) ? b2g::kMetaGroupRolling : 0 ) |
+								  ( !( b2gRdF( sim, B2L_CONTACT_RESTITUTION ) == 0.0f ) ? b2g::kMetaGroupRestitution : 0 );
+					}
+					groupBits |= seg.wide ? ownBits : 0;
 				}
-				int indexA = b2gRdI( sim, B2L_CONTACT_INDEX_A ), indexB = b2gRdI( sim, B2L_CONTACT_INDEX_B );
-				if ( s->checkMasses )
+				for ( int i = group > local ? group : local; i < groupEnd && i < localEnd; ++i )
 				{
-					// invMass, invInertia of the two bodies as the contact remembers them vs. as the bodies have them now
-					// (adjacent floats in both structures; bitwise, so that "equal" means the device may use either)
-					static const uint8_t zero[8] = { 0 };
-					const uint8_t* bodyA = indexA >= 0 ? worldSims + (size_t)indexA * B2L_SIM_SIZE + B2L_SIM_INV_MASS : zero;
-					const uint8_t* bodyB = indexB >= 0 ? worldSims + (size_t)indexB * B2L_SIM_SIZE + B2L_SIM_INV_MASS : zero;
-					massDiffers = massDiffers || memcmp( sim + B2L_CONTACT_INV_MASS_A, bodyA, 8 ) != 0 ||
-								  memcmp( sim + B2L_CONTACT_INV_MASS_B, bodyB, 8 ) != 0;
+					const int slot = seg.slotStart + i;
+					if ( vouched[i - group] )
+					{
+						const b2GpuRecycledContact& hint = seg.hints[i];
+						b2gStream4( wire + slot, b2gIntBits( ( homeBase + i ) | ( ( groupBits >> 3 ) << b2g::kLightGroupShift ) | b2g::kLightBodyMass ),
+									hint.separation[0], hint.separation[1], b2gIntBits( homeSlot + i ) );
+						vouchedTotal += 1;
+						continue;
+					}
+					const uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
+					const uint8_t* m = sim + B2L_CONTACT_MANIFOLD;
+					const uint8_t* p0 = m + B2L_MANIFOLD_POINTS;
+					const uint8_t* p1 = p0 + B2L_MP_SIZE;
+					int pointCount = b2gRdI( m, B2L_MANIFOLD_POINT_COUNT );
+					int hitEnable = ( (uint32_t)b2gRdI( sim, B2L_CONTACT_SIM_FLAGS ) & B2L_SIM_ENABLE_HIT_EVENT ) != 0 ? b2g::kMetaHitEnable : 0;
+					int meta = ( seg.colorIndex << b2g::kMetaColorShift ) | hitEnable | ( pointCount & b2g::kMetaPointMask );
+					int indexA = b2gRdI( sim, B2L_CONTACT_INDEX_A ), indexB = b2gRdI( sim, B2L_CONTACT_INDEX_B );
+					if ( s->checkMasses )
+					{
+						// invMass, invInertia of the two bodies as the contact remembers them vs. as the bodies have them now
+						// (adjacent floats in both structures; bitwise, so that "equal" means the device may use either)
+						static const uint8_t zero[8] = { 0 };
+						const uint8_t* bodyA = indexA >= 0 ? worldSims + (size_t)indexA * B2L_SIM_SIZE + B2L_SIM_INV_MASS : zero;
+						const uint8_t* bodyB = indexB >= 0 ? worldSims + (size_t)indexB * B2L_SIM_SIZE + B2L_SIM_INV_MASS : zero;
+						massDiffers = massDiffers || memcmp( sim + B2L_CONTACT_INV_MASS_A, bodyA, 8 ) != 0 ||
+									  memcmp( sim + B2L_CONTACT_INV_MASS_B, bodyB, 8 ) != 0;
+					}
+					const int rawIndexA = indexA, rawIndexB = indexB;
+					indexA = indexA >= 0 ? indexA + bodyBase : indexA;
+					indexB = indexB >= 0 ? indexB + bodyBase : indexB;
+					b2gStream4( wireMass + slot, b2gRdF( sim, B2L_CONTACT_INV_MASS_A ), b2gRdF( sim, B2L_CONTACT_INV_I_A ),
+								b2gRdF( sim, B2L_CONTACT_INV_MASS_B ), b2gRdF( sim, B2L_CONTACT_INV_I_B ) );
+					const float separation0 = b2gRdF( p0, B2L_MP_SEPARATION ), separation1 = b2gRdF( p1, B2L_MP_SEPARATION );
+					const float rollingImpulse = b2gRdF( m, B2L_MANIFOLD_ROLLING_IMPULSE );
+					if ( !resident )
+					{
+						float4* w = wire + (size_t)slot * b2g::WR_COUNT;
+						b2gStream4( w + b2g::WR_HEAD, b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta | groupBits ), rollingImpulse );
+						b2gStream4( w + b2g::WR_NORMAL, b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ),
+									b2gRdF( sim, B2L_CONTACT_FRICTION ), b2gRdF( sim, B2L_CONTACT_TANGENT_SPEED ) );
+						b2gStream4( w + b2g::WR_MATERIAL, b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ), b2gRdF( sim, B2L_CONTACT_RESTITUTION ),
+									separation0, separation1 );
+						b2gStream4( w + b2g::WR_ANCHOR1, b2gRdF( p0, B2L_MP_ANCHOR_A ), b2gRdF( p0, B2L_MP_ANCHOR_A + 4 ),
+									b2gRdF( p0, B2L_MP_ANCHOR_B ), b2gRdF( p0, B2L_MP_ANCHOR_B + 4 ) );
+						b2gStream4( w + b2g::WR_ANCHOR2, b2gRdF( p1, B2L_MP_ANCHOR_A ), b2gRdF( p1, B2L_MP_ANCHOR_A + 4 ),
+									b2gRdF( p1, B2L_MP_ANCHOR_B ), b2gRdF( p1, B2L_MP_ANCHOR_B + 4 ) );
+						b2gStream4( w + b2g::WR_IMPULSE, b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ),
+									b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ) );
+						continue;
+					}
+					// resident mode: the record the device would need, against the record it has
+					alignas( 16 ) float rows[17] = {
+						b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta ),
+						b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ), b2gRdF( sim, B2L_CONTACT_FRICTION ), b2gRdF( sim, B2L_CONTACT_TANGENT_SPEED ),
+						b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ), b2gRdF( sim, B2L_CONTACT_RESTITUTION ),
+						b2gRdF( p0, B2L_MP_ANCHOR_A ), b2gRdF( p0, B2L_MP_ANCHOR_A + 4 ), b2gRdF( p0, B2L_MP_ANCHOR_B ), b2gRdF( p0, B2L_MP_ANCHOR_B + 4 ),
+						b2gRdF( p1, B2L_MP_ANCHOR_A ), b2gRdF( p1, B2L_MP_ANCHOR_A + 4 ), b2gRdF( p1, B2L_MP_ANCHOR_B ), b2gRdF( p1, B2L_MP_ANCHOR_B + 4 ) };
+					float impulses[5] = { b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ), b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ),
+										  b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ), rollingImpulse };
+					const int id = b2gRdI( sim, B2L_CONTACT_ID );
+					const int home = homeBase + i;
+					b2gShadowContact& shadow = s->shadowContacts[(size_t)home];
+					b2gShadowImpulses& shadowImpulses = s->shadowImpulses[(size_t)home];
+					b2gShadowHead& head = s->shadowHeads[(size_t)home];
+					const bool clean = i < homeCount && head.contactId == id && memcmp( shadow.rows, rows, sizeof( rows ) ) == 0 &&
+									   memcmp( shadowImpulses.values, impulses, sizeof( impulses ) ) == 0;
+					int ref = homeSlot + i; // its record among the previous step's outputs
+					if ( !clean )
+					{
+						int entry = b2gStreamTake( full );
+						ref = ~entry;
+						float4* w = s->hFull.ptr + (size_t)entry * b2g::WR_COUNT;
+						b2gStream4( w + b2g::WR_HEAD, rows[0], rows[1], rows[2], rollingImpulse );
+						b2gStream4( w + b2g::WR_NORMAL, rows[3], rows[4], rows[5], rows[6] );
+						b2gStream4( w + b2g::WR_MATERIAL, rows[7], rows[8], separation0, separation1 );
+						b2gStream4( w + b2g::WR_ANCHOR1, rows[9], rows[10], rows[11], rows[12] );
+						b2gStream4( w + b2g::WR_ANCHOR2, rows[13], rows[14], rows[15], rows[16] );
+						b2gStream4( w + b2g::WR_IMPULSE, impulses[0], impulses[1], impulses[2], impulses[3] );
+						memcpy( shadow.rows, rows, sizeof( rows ) );
+						memcpy( shadowImpulses.values, impulses, sizeof( impulses ) );
+						head.contactId = id;
+						head.indexA = rawIndexA;
+						head.indexB = rawIndexB;
+						head.ownBits = ( !( rows[7] == 0.0f ) ? b2g::kMetaGroupRolling : 0 ) | ( !( rows[8] == 0.0f ) ? b2g::kMetaGroupRestitution : 0 );
+					}
+					b2gStream4( wire + slot, b2gIntBits( home | ( ( groupBits >> 3 ) << b2g::kLightGroupShift ) ), separation0, separation1, b2gIntBits( ref ) );
 				}
-				indexA = indexA >= 0 ? indexA + bodyBase : indexA;
-				indexB = indexB >= 0 ? indexB + bodyBase : indexB;
-				const int slot = seg.slotStart + i;
-				b2gStream4( wireMass + slot, b2gRdF( sim, B2L_CONTACT_INV_MASS_A ), b2gRdF( sim, B2L_CONTACT_INV_I_A ),
-							b2gRdF( sim, B2L_CONTACT_INV_MASS_B ), b2gRdF( sim, B2L_CONTACT_INV_I_B ) );
-				const float separation0 = b2gRdF( p0, B2L_MP_SEPARATION ), separation1 = b2gRdF( p1, B2L_MP_SEPARATION );
-				const float rollingImpulse = b2gRdF( m, B2L_MANIFOLD_ROLLING_IMPULSE );
-				if ( !resident )
-				{
-					float4* w = wire + (size_t)slot * b2g::WR_COUNT;
-					b2gStream4( w + b2g::WR_HEAD, b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta | groupBits ), rollingImpulse );
-					b2gStream4( w + b2g::WR_NORMAL, b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ),
-								b2gRdF( sim, B2L_CONTACT_FRICTION ), b2gRdF( sim, B2L_CONTACT_TANGENT_SPEED ) );
-					b2gStream4( w + b2g::WR_MATERIAL, b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ), b2gRdF( sim, B2L_CONTACT_RESTITUTION ),
-								separation0, separation1 );
-					b2gStream4( w + b2g::WR_ANCHOR1, b2gRdF( p0, B2L_MP_ANCHOR_A ), b2gRdF( p0, B2L_MP_ANCHOR_A + 4 ),
-								b2gRdF( p0, B2L_MP_ANCHOR_B ), b2gRdF( p0, B2L_MP_ANCHOR_B + 4 ) );
-					b2gStream4( w + b2g::WR_ANCHOR2, b2gRdF( p1, B2L_MP_ANCHOR_A ), b2gRdF( p1, B2L_MP_ANCHOR_A + 4 ),
-								b2gRdF( p1, B2L_MP_ANCHOR_B ), b2gRdF( p1, B2L_MP_ANCHOR_B + 4 ) );
-					b2gStream4( w + b2g::WR_IMPULSE, b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ),
-								b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ) );
-					continue;
-				}
-				// resident mode: the record the device would need, against the record it has
-				alignas( 16 ) float rows[17] = {
-					b2gIntBits( indexA ), b2gIntBits( indexB ), b2gIntBits( meta ),
-					b2gRdF( m, B2L_MANIFOLD_NORMAL ), b2gRdF( m, B2L_MANIFOLD_NORMAL + 4 ), b2gRdF( sim, B2L_CONTACT_FRICTION ), b2gRdF( sim, B2L_CONTACT_TANGENT_SPEED ),
-					b2gRdF( sim, B2L_CONTACT_ROLLING_RESISTANCE ), b2gRdF( sim, B2L_CONTACT_RESTITUTION ),
-					b2gRdF( p0, B2L_MP_ANCHOR_A ), b2gRdF( p0, B2L_MP_ANCHOR_A + 4 ), b2gRdF( p0, B2L_MP_ANCHOR_B ), b2gRdF( p0, B2L_MP_ANCHOR_B + 4 ),
-					b2gRdF( p1, B2L_MP_ANCHOR_A ), b2gRdF( p1, B2L_MP_ANCHOR_A + 4 ), b2gRdF( p1, B2L_MP_ANCHOR_B ), b2gRdF( p1, B2L_MP_ANCHOR_B + 4 ) };
-				float impulses[5] = { b2gRdF( p0, B2L_MP_NORMAL_IMPULSE ), b2gRdF( p0, B2L_MP_TANGENT_IMPULSE ), b2gRdF( p1, B2L_MP_NORMAL_IMPULSE ),
-									  b2gRdF( p1, B2L_MP_TANGENT_IMPULSE ), rollingImpulse };
-				const int id = b2gRdI( sim, B2L_CONTACT_ID );
-				const int home = homeBase + i;
-				b2gShadowContact& shadow = s->shadowContacts[(size_t)home];
-				b2gShadowImpulses& shadowImpulses = s->shadowImpulses[(size_t)home];
-				const bool clean = i < homeCount && shadow.contactId == id && memcmp( shadow.rows, rows, sizeof( rows ) ) == 0 &&
-								   memcmp( shadowImpulses.values, impulses, sizeof( impulses ) ) == 0;
-				int ref = homeSlot + i; // its record among the previous step's outputs
-				if ( !clean )
-				{
-					int entry = b2gStreamTake( full );
-					ref = ~entry;
-					float4* w = s->hFull.ptr + (size_t)entry * b2g::WR_COUNT;
-					b2gStream4( w + b2g::WR_HEAD, rows[0], rows[1], rows[2], rollingImpulse );
-					b2gStream4( w + b2g::WR_NORMAL, rows[3], rows[4], rows[5], rows[6] );
-					b2gStream4( w + b2g::WR_MATERIAL, rows[7], rows[8], separation0, separation1 );
-					b2gStream4( w + b2g::WR_ANCHOR1, rows[9], rows[10], rows[11], rows[12] );
-					b2gStream4( w + b2g::WR_ANCHOR2, rows[13], rows[14], rows[15], rows[16] );
-					b2gStream4( w + b2g::WR_IMPULSE, impulses[0], impulses[1], impulses[2], impulses[3] );
-					memcpy( shadow.rows, rows, sizeof( rows ) );
-					memcpy( shadowImpulses.values, impulses, sizeof( impulses ) );
-					shadow.contactId = id;
-				}
-				b2gStream4( wire + slot, b2gIntBits( home | ( ( groupBits >> 3 ) << b2g::kLightGroupShift ) ), separation0, separation1, b2gIntBits( ref ) );
 			}
 			if ( localEnd == seg.count )
 			{
@@ -326,6 +362,10 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		if ( full.taken > 0 )
 		{
 			s->fullCount.fetch_add( full.taken, std::memory_order_relaxed );
+		}
+		if ( vouchedTotal > 0 )
+		{
+			s->vouchedCount.fetch_add( vouchedTotal, std::memory_order_relaxed );
 		}
 	}
 

@@ -11,6 +11,7 @@
 #include "atomic.h"
 #include "bitset.h"
 #include "body.h"
+#include "contact.h"
 #include "constraint_graph.h"
 #include "core.h"
 #include "id_pool.h"
@@ -40,6 +41,12 @@ typedef struct b2SeamSlot
 	b2GpuStepResult lastResult;
 	b2GpuStepDesc lastDesc;
 	uint16_t generation;  /* of the world the solver was created for (b2World::generation, bumped by b2DestroyWorld) */
+	/* what the narrow phase recycled this step (b2GpuSeam_BeginCollide / b2GpuSeam_ContactRecycled) */
+	b2GpuRecycledContact* recycled;
+	int recycledCapacity;
+	uint32_t recycledStamp;
+	int collideStart[B2_GRAPH_COLOR_COUNT], collideCount[B2_GRAPH_COLOR_COUNT];
+	int collidesSinceSolve;
 	bool islandsCaptured; /* b2GpuSeam_BeforeIslandSplit filled the hint of the step in flight */
 	int capturedIslandCount;
 } b2SeamSlot;
@@ -68,6 +75,7 @@ static void b2SeamReleaseSlot( b2SeamSlot* slot )
 	}
 	free( slot->islandLabels );
 	free( slot->islandSizes );
+	free( slot->recycled );
 	memset( slot, 0, sizeof( *slot ) );
 }
 
@@ -144,6 +152,15 @@ void b2GpuSeam_GetTotals( int worldIndex, b2GpuSeamTotals* totals, int reset )
 			memset( &s_slots[worldIndex].totals, 0, sizeof( b2GpuSeamTotals ) );
 		}
 	}
+}
+
+int b2GpuSeam_GetResidentStats( int worldIndex, int* fullContacts, int* dirtyBodies, int* vouchedContacts )
+{
+	if ( worldIndex < 0 || worldIndex >= B2_MAX_WORLDS || s_slots[worldIndex].solver == NULL )
+	{
+		return 0;
+	}
+	return b2GpuSolverGetResidentStats( s_slots[worldIndex].solver, fullContacts, dirtyBodies, vouchedContacts );
 }
 
 const b2GpuStepDesc* b2GpuSeam_GetLastDesc( int worldIndex )
@@ -250,6 +267,50 @@ static void b2SeamTeamHelper( void* taskContext )
 		b2AtomicStoreInt( &team->failed, 1 );
 	}
 	b2AtomicFetchAddInt( &team->inUnpack, -1 );
+}
+
+/* ---- recycled manifolds: the narrow phase tells, the pack pass need not rediscover ------------------------------------
+ * Called by the generated physics_world.c (tools/patch_collide.py).  The reference's contact recycling
+ * (src/physics_world.c:508-560) leaves a b2ContactSim exactly as the previous step's solver left it, except for the two
+ * separations it recomputes and the body indices / masses it refreshes -- which is what b2GpuStepDesc::recycled says. */
+void b2GpuSeam_BeginCollide( b2World* world, b2StepContext* context, int contactCount )
+{
+	(void)context;
+	b2SeamSlot* slot = b2SeamGetSlot( world );
+	if ( slot->recycledCapacity < contactCount )
+	{
+		free( slot->recycled );
+		slot->recycledCapacity = contactCount + contactCount / 2 + 256;
+		slot->recycled = calloc( (size_t)slot->recycledCapacity, sizeof( b2GpuRecycledContact ) );
+		slot->recycledStamp = 0;
+	}
+	slot->recycledStamp += 1;
+	if ( slot->recycledStamp == 0 )
+	{
+		// wrapped: no entry of the past may look current
+		memset( slot->recycled, 0, (size_t)slot->recycledCapacity * sizeof( b2GpuRecycledContact ) );
+		slot->recycledStamp = 1;
+	}
+	// b2Collide lays the colours' arrays end to end, in colour order (src/physics_world.c:665-677): contact j of colour i is
+	// contactIndex collideStart[i] + j of b2CollideTask
+	int start = 0;
+	for ( int i = 0; i < B2_GRAPH_COLOR_COUNT; ++i )
+	{
+		slot->collideStart[i] = start;
+		slot->collideCount[i] = world->constraintGraph.colors[i].contactSims.count;
+		start += slot->collideCount[i];
+	}
+	slot->collidesSinceSolve += 1;
+}
+
+void b2GpuSeam_ContactRecycled( b2World* world, int contactIndex, const b2ContactSim* contactSim )
+{
+	b2SeamSlot* slot = s_slots + world->worldId;
+	b2GpuRecycledContact* entry = slot->recycled + contactIndex;
+	entry->contactId = contactSim->contactId;
+	entry->separation[0] = contactSim->manifold.points[0].separation;
+	entry->separation[1] = contactSim->manifold.points[1].separation;
+	entry->stamp = slot->recycledStamp;
 }
 
 /* ---- island capture ahead of a split ---------------------------------------------------------------------- */
@@ -376,6 +437,23 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 		b2GpuSeam_FillIslands( world, desc, NULL, slot->islandSizes, false );
 		desc->bodyIsland = slot->islandLabels;
 	}
+
+	// The narrow phase's word on the manifolds it recycled.  It only holds when exactly one narrow phase ran since this
+	// world's previous solve: a step with dt == 0 runs the narrow phase but not the solver (src/physics_world.c:912-950),
+	// and what it re-evaluated the device has never seen.
+	if ( slot->collidesSinceSolve == 1 && slot->recycled != NULL )
+	{
+		desc->recycled = slot->recycled;
+		desc->recycledStamp = slot->recycledStamp;
+		for ( int c = 0; c <= desc->activeColorCount; ++c )
+		{
+			const b2GpuColorDesc* color = c < desc->activeColorCount ? desc->colors + c : &desc->overflow;
+			int i = color->colorIndex;
+			desc->recycledStart[c] = slot->collideStart[i];
+			desc->recycledCount[c] = slot->collideCount[i] < color->contactCount ? slot->collideCount[i] : color->contactCount;
+		}
+	}
+	slot->collidesSinceSolve = 0;
 
 	b2GpuStepResult* result = &slot->lastResult;
 	memset( result, 0, sizeof( *result ) );

@@ -41,6 +41,11 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* stepContext );
 /* Called right before b2Solve may start its island-split task: takes the island hint while nobody is rewriting the islands. */
 void b2GpuSeam_BeforeIslandSplit( b2World* world, b2StepContext* stepContext );
 
+/* Called by the generated physics_world.c (tools/patch_collide.py): the narrow phase begins / has recycled a manifold. */
+typedef struct b2ContactSim b2ContactSim;
+void b2GpuSeam_BeginCollide( b2World* world, b2StepContext* stepContext, int contactCount );
+void b2GpuSeam_ContactRecycled( b2World* world, int contactIndex, const b2ContactSim* contactSim );
+
 /* Route the reference's allocations through page-locked memory (b2SetAllocator, include/box2d/base.h:86).
  * Call before creating any world. */
 void b2GpuSeam_InstallPinnedAllocator( void );
@@ -61,6 +66,8 @@ void b2GpuSeam_GetTotals( int worldIndex, b2GpuSeamTotals* totals, int reset );
 /* Last step's device-side result for a world id slot (for benchmarks / tests). */
 const b2GpuStepResult* b2GpuSeam_GetLastResult( int worldIndex );
 const b2GpuStepDesc* b2GpuSeam_GetLastDesc( int worldIndex );
+/* b2GpuSolverGetResidentStats of the world's solver for its last step (0 = no solver or not a resident step). */
+int b2GpuSeam_GetResidentStats( int worldIndex, int* fullContacts, int* dirtyBodies, int* vouchedContacts );
 
 /* 0 = persistent cooperative kernel, 1 = one launch per stage.  Applies to solvers created afterwards and
  * to existing ones. */

@@ -72,6 +72,16 @@ typedef struct b2GpuIslandSize
 	int reserved;
 } b2GpuIslandSize;
 
+/* What the narrow phase knows about a contact it RECYCLED this step (src/physics_world.c:508-560): the b2ContactSim is what
+ * the previous step left behind -- the solver's own impulse outputs included -- except for the two separations, which are
+ * recomputed, and the body indices / inverse masses, which are refreshed from the bodies.  See b2GpuStepDesc::recycled. */
+typedef struct b2GpuRecycledContact
+{
+	uint32_t stamp; /* == b2GpuStepDesc::recycledStamp when the entry was written for this step */
+	int contactId;	/* b2ContactSim::contactId of the contact the entry was written for */
+	float separation[2]; /* b2ManifoldPoint::separation of the two points */
+} b2GpuRecycledContact;
+
 /* Everything b2SolverTask reads from b2StepContext (src/solver.h:155-237) and b2World
  * (src/physics_world.h:162-216). */
 typedef struct b2GpuStepDesc
@@ -126,6 +136,19 @@ typedef struct b2GpuStepDesc
 	 * counted on the step's critical path.  Counts may be slightly off (they are only used for sizing; the device checks).
 	 * NULL = the library counts the bodies per island itself and estimates the rest. */
 	const struct b2GpuIslandSize* islandSizes;
+
+	/* Optional (resident mode): recycled[recycledStart[c] + i] describes contact i of colors[c] (c == activeColorCount: the
+	 * overflow colour) for i < recycledCount[c].  An entry counts only when its stamp equals recycledStamp AND its contactId
+	 * is that contact's; the caller then vouches that, since the previous b2GpuSolverStep of this solver, nothing the solver
+	 * reads from the contact's b2ContactSim has changed but the separations given in the entry, the body indices (re-read
+	 * by the library) and the inverse masses, which equal the bodies'.  The pack pass then skips re-reading and comparing the
+	 * record.  Any other entry (stale stamp, another contact's id: the contact moved in its array after the narrow phase
+	 * ran) is ignored and the contact is examined as usual.  NULL = no hint.  Results do not depend on the hint as long as
+	 * the caller's claim is true. */
+	const b2GpuRecycledContact* recycled;
+	uint32_t recycledStamp;
+	int recycledStart[B2GPU_MAX_ACTIVE_COLORS + 1];
+	int recycledCount[B2GPU_MAX_ACTIVE_COLORS + 1];
 } b2GpuStepDesc;
 
 /* Index of each per-stage timer, same split as b2Profile (include/box2d/types.h:526-551) filled by the
@@ -244,9 +267,10 @@ B2GPU_API int b2GpuSolverGetIslandPlan( const b2GpuSolver* solver, int* binCount
 /* Resident mode (single worlds): the device keeps the contacts' static data, their impulses and the bodies across steps, and
  * the pack pass only uploads what differs from that -- a 16-byte record per contact whose manifold the narrow phase recycled
  * (src/physics_world.c:508-560), the full 96 bytes otherwise.  Returns 1 when the last step ran in resident mode and fills
- * how many contacts travelled as full records and how many bodies were re-uploaded; 0 (counts untouched) otherwise.  The
- * results do not depend on the mode (bit-identical); B2GPU_RESIDENT=0 turns it off. */
-B2GPU_API int b2GpuSolverGetResidentStats( const b2GpuSolver* solver, int* fullContacts, int* dirtyBodies );
+ * how many contacts travelled as full records, how many bodies were re-uploaded and how many contacts were taken on the
+ * caller's word (b2GpuStepDesc::recycled) without their record being read; 0 (counts untouched) otherwise.  The results do
+ * not depend on the mode (bit-identical); B2GPU_RESIDENT=0 turns it off. */
+B2GPU_API int b2GpuSolverGetResidentStats( const b2GpuSolver* solver, int* fullContacts, int* dirtyBodies, int* vouchedContacts );
 /* Host utility for callers that have island labels but no island bookkeeping: fill sizes[desc->islandCount] from
  * desc->bodyIsland and the constraint arrays (one pass over the constraints).  Returns 0 on success. */
 B2GPU_API int b2GpuCountIslandSizes( const b2GpuStepDesc* desc, b2GpuIslandSize* sizes );

@@ -108,6 +108,21 @@ def compile_solver_variant(mode: str) -> Path:
 	return obj
 
 
+def compile_collide_gpu() -> Path:
+	"""The product's physics_world.c: the reference's, with the two recycle hooks of tools/patch_collide.py."""
+	OBJ_DIR.mkdir(parents=True, exist_ok=True)
+	GEN_DIR.mkdir(parents=True, exist_ok=True)
+	src = REFERENCE / "src" / "physics_world.c"
+	gen = GEN_DIR / "physics_world_gpu.c"
+	obj = OBJ_DIR / "physics_world_gpu.o"
+	patcher = ROOT / "tools" / "patch_collide.py"
+	if _stale(gen, [src, patcher]):
+		_run([sys.executable, str(patcher), "--src", str(src), "--out", str(gen)])
+	if _stale(obj, [gen]):
+		_run([CC, *REF_CFLAGS, *ref_includes(), "-c", str(gen), "-o", str(obj)])
+	return obj
+
+
 def compile_own_c(src: Path, tag: str = "") -> Path:
 	OBJ_DIR.mkdir(parents=True, exist_ok=True)
 	obj = OBJ_DIR / f"own_{src.stem}{tag}.o"
@@ -165,7 +180,7 @@ def build_host_lib(verbose: bool = False) -> Path:
 	if not reference_available():
 		raise RuntimeError(f"reference sources not found at {REFERENCE}")
 	cuda_lib = build_cuda_lib(verbose)
-	objs = compile_reference_objects()
+	objs = [o for o in compile_reference_objects() if o.name != "src_physics_world.o"] + [compile_collide_gpu()]
 	gpu = compile_solver_variant("gpu")
 	harness = compile_own_c(PKG_DIR / "host" / "b2h_harness.c")
 	seam = compile_own_c(PKG_DIR / "host" / "b2_gpu_seam.c")
