@@ -179,7 +179,7 @@ def solver_lib() -> ctypes.CDLL:
 	lib.b2GpuCountIslandSizes.restype = ctypes.c_int
 	lib.b2GpuCountIslandSizes.argtypes = [P(StepDesc), P(IslandSize)]
 	lib.b2GpuSolverGetResidentStats.restype = ctypes.c_int
-	lib.b2GpuSolverGetResidentStats.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int)] * 3
+	lib.b2GpuSolverGetResidentStats.argtypes = [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int)] * 4
 	lib.b2GpuSolverGetIslandPlan.restype = ctypes.c_int
 	lib.b2GpuSolverGetIslandPlan.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
 	_solver_lib = lib
@@ -531,14 +531,20 @@ class GpuSolver:
 	def resident_stats(self):
 		"""(full contact records, dirty bodies) of the last step, or None when it did not run in resident mode."""
 		full, dirty = ctypes.c_int(0), ctypes.c_int(0)
-		if self.lib.b2GpuSolverGetResidentStats(self.handle, ctypes.byref(full), ctypes.byref(dirty), None) == 0:
+		if self.lib.b2GpuSolverGetResidentStats(self.handle, ctypes.byref(full), ctypes.byref(dirty), None, None) == 0:
 			return None
 		return full.value, dirty.value
 
 	def vouched_contacts(self) -> int:
 		"""Contacts of the last step the pack pass took on the caller's word (b2GpuStepDesc::recycled)."""
 		n = ctypes.c_int(0)
-		self.lib.b2GpuSolverGetResidentStats(self.handle, None, None, ctypes.byref(n))
+		self.lib.b2GpuSolverGetResidentStats(self.handle, None, None, ctypes.byref(n), None)
+		return n.value
+
+	def full_joints(self) -> int:
+		"""Joints of the last step that travelled as complete 256-byte records (resident mode)."""
+		n = ctypes.c_int(0)
+		self.lib.b2GpuSolverGetResidentStats(self.handle, None, None, None, ctypes.byref(n))
 		return n.value
 
 	def close(self) -> None:

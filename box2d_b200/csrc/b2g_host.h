@@ -156,6 +156,8 @@ struct b2gJointSeg
 	int count;
 	int jointStart;
 	int world;
+	int colorIndex;
+	bool overflow;
 };
 
 // ---- resident mode: host-side shadows of what the device holds (b2g_types.cuh, b2g_resident.cuh) -----------------------
@@ -271,6 +273,18 @@ struct b2GpuSolver
 	int fullCapacity = 0, dirtyCapacity = 0;
 	size_t prevOutImpulses = 0; // where the previous step's impulse records start in ITS output arena (quads)
 	int homeTotal = 0;
+	// the same for joints: homes by (graph colour, index in the colour's joint array), shadows = the complete 256-byte record
+	// the device's table holds (the solver's outputs written in by the unpack pass)
+	std::vector<uint8_t> shadowJoints; // [joint homes * kJointStride]
+	int jointHomeBase[kHomeColors + 1] = { 0 }, jointHomeCount[kHomeColors] = { 0 }, jointHomeSlot[kHomeColors] = { 0 }, jointSegHome[kHomeColors] = { 0 };
+	int jointHomeTotal = 0;
+	DeviceBuffer<float4> jointTable, jointAssembled, fullJointStream;
+	PinnedBuffer<float4> hFullJoints;
+	std::atomic<int> fullJointCursor{ 0 };
+	int fullJointCapacity = 0, fullJointSent = 0;
+	std::atomic<int> fullJointCount{ 0 };
+	size_t prevOutJoints = 0; // where the previous step's joint records start in ITS output arena (quads)
+	int jointWireQuads = b2g::kJointStride / 16; // quads per joint in the input arena: 16, or kLightJointQuads
 	int wireQuads = b2g::WR_COUNT; // quads per contact slot in the input arena: WR_COUNT, or 1 (light records)
 	int fullSent = 0, dirtySent = 0;
 	std::atomic<int> streamOverflow{ 0 };

@@ -13,6 +13,8 @@
 
 #include "b2g_contact.cuh"
 
+#include <cstddef>
+
 namespace b2g
 {
 
@@ -55,6 +57,81 @@ __global__ void __launch_bounds__( 256 ) b2gCommitKernel( const __grid_constant_
 				}
 				P.table[(size_t)( key & kLightIdMask ) * kTableRows + row] = value;
 			}
+		}
+	}
+}
+
+// Joints in resident mode.  A prepared b2JointSim changes from step to step only in the run of fields b2PrepareJoint
+// rewrites from the bodies' poses (b2lJointPreparedRun, include/b2gpu_layout.h: body indices, anchor frames, deltaCenter,
+// the effective masses that depend on them) and in the accumulated impulses the device itself wrote.  So a joint that is
+// otherwise unchanged travels as 96 bytes instead of 256: its home, where its previous output record is, and the run.
+// This kernel rebuilds the complete records the stage code reads (P.rawJoints) and keeps the table up to date:
+//     full record (ref < 0):   the record as uploaded
+//     light record:            the table's record + the solver's own outputs of the previous step (the fields
+//                              b2lJointMutableRuns lists) + the fresh prepared run, in that order -- the motor joint's
+//                              linearMass is both an output and re-prepared, and the host's value is the prepared one
+// Idempotent (the table ends up holding what was assembled), one thread per joint.
+__global__ void __launch_bounds__( 128 ) b2gAssembleJointsKernel( const __grid_constant__ StepParams P )
+{
+	constexpr int quads = kJointStride / 16;
+	for ( int j = (int)( blockIdx.x * blockDim.x + threadIdx.x ); j < P.jointCount; j += (int)( gridDim.x * blockDim.x ) )
+	{
+		const float4* light = P.lightJoints + (size_t)j * kLightJointQuads;
+		float4 head = light[0];
+		int home = __float_as_int( head.x ), ref = __float_as_int( head.y );
+		float4* out = P.jointAssembled + (size_t)j * quads;
+		float4* keep = P.jointTable + (size_t)home * quads;
+		if ( ref < 0 )
+		{
+			const float4* full = P.fullJoints + (size_t)( ~ref ) * quads;
+#pragma unroll
+			for ( int q = 0; q < quads; ++q )
+			{
+				float4 value = full[q];
+				out[q] = value;
+				keep[q] = value;
+			}
+			continue;
+		}
+		float record[kJointStride / 4];
+#pragma unroll
+		for ( int q = 0; q < quads; ++q )
+		{
+			float4 value = keep[q];
+			record[4 * q + 0] = value.x;
+			record[4 * q + 1] = value.y;
+			record[4 * q + 2] = value.z;
+			record[4 * q + 3] = value.w;
+		}
+		const int type = __float_as_int( record[offsetof( b2lJointSim, type ) / 4] );
+		{
+			int offsets[2], floats[2];
+			int runs = b2lJointMutableRuns( type, offsets, floats );
+			const float* previous = P.prevOutJoints + (size_t)ref * B2L_JOINT_OUT_FLOATS;
+			for ( int r = 0; r < runs; ++r )
+			{
+				for ( int k = 0; k < floats[r]; ++k )
+				{
+					record[offsets[r] / 4 + k] = previous[k];
+				}
+				previous += floats[r];
+			}
+		}
+		{
+			int offset = 0;
+			int bytes = b2lJointPreparedRun( type, &offset );
+			const float* run = reinterpret_cast<const float*>( light + 1 );
+			for ( int k = 0; k < bytes / 4; ++k )
+			{
+				record[offset / 4 + k] = run[k];
+			}
+		}
+#pragma unroll
+		for ( int q = 0; q < quads; ++q )
+		{
+			float4 value = make_float4( record[4 * q + 0], record[4 * q + 1], record[4 * q + 2], record[4 * q + 3] );
+			out[q] = value;
+			keep[q] = value;
 		}
 	}
 }

@@ -276,6 +276,10 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	s->dirtyStream.release();
 	s->hFull.release();
 	s->hDirty.release();
+	s->jointTable.release();
+	s->jointAssembled.release();
+	s->fullJointStream.release();
+	s->hFullJoints.release();
 	s->binCounters.release();
 	s->bodyLocal.release();
 	s->binBodyList.release();
@@ -342,7 +346,7 @@ extern "C" int b2GpuSolverGetIslandPlan( const b2GpuSolver* s, int* binCount, in
 	return bins;
 }
 
-extern "C" int b2GpuSolverGetResidentStats( const b2GpuSolver* s, int* fullContacts, int* dirtyBodies, int* vouchedContacts )
+extern "C" int b2GpuSolverGetResidentStats( const b2GpuSolver* s, int* fullContacts, int* dirtyBodies, int* vouchedContacts, int* fullJoints )
 {
 	if ( s == nullptr || !s->resident )
 	{
@@ -359,6 +363,10 @@ extern "C" int b2GpuSolverGetResidentStats( const b2GpuSolver* s, int* fullConta
 	if ( vouchedContacts != nullptr )
 	{
 		*vouchedContacts = s->vouchedCount.load( std::memory_order_relaxed );
+	}
+	if ( fullJoints != nullptr )
+	{
+		*fullJoints = s->fullJointCount.load( std::memory_order_relaxed );
 	}
 	return 1;
 }
@@ -923,6 +931,8 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 					seg.count = color.jointCount;
 					seg.jointStart = 0;
 					seg.world = w;
+					seg.colorIndex = color.colorIndex;
+					seg.overflow = isOverflow;
 				}
 			}
 		}
@@ -984,6 +994,7 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 		s->cacheValid = false; // a plain step reuses the arenas the resident copies live in
 	}
 	s->wireQuads = s->resident ? 1 : b2g::WR_COUNT;
+	s->jointWireQuads = s->resident ? b2g::kLightJointQuads : (int)jointQuads;
 	const size_t bodyQuads = s->resident ? 0 : 2;
 	// input arena: [contacts 6/slot or 1/slot][joints 16/joint][states 2/body][packed sims 2/body][bins 1/4 body].  The
 	// pipelined pack pass (b2GpuSolverPackWork) works through it in address order -- constraints first, the three body
@@ -991,7 +1002,7 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	// first megabyte of contacts.
 	s->inWire = 0;
 	s->inJoints = s->inWire + (size_t)s->wireQuads * slot;
-	s->inStates = s->inJoints + jointQuads * joint;
+	s->inStates = s->inJoints + (size_t)s->jointWireQuads * joint;
 	s->inBody = s->inStates + bodyQuads * nb;
 	s->inBins = s->inBody + bodyQuads * nb;
 	s->inMass = s->inBins + ( nb + 3 ) / 4; // optional tail: one quad per contact slot, see b2g::WireRow
@@ -1085,6 +1096,52 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 			s->homeTotal = s->homeBase[kHomeColors];
 		}
 		B2G_CUDA( persistent( s->table, (size_t)( s->homeTotal + 1 ) * b2g::kTableRows ) );
+		// joints: the same layout of homes
+		{
+			bool ordered = true;
+			int last = -1;
+			for ( const b2gJointSeg& seg : s->jointSegs )
+			{
+				int index = seg.colorIndex;
+				ordered = ordered && ( !seg.overflow ? index > last && index < kHomeColors - 1 : index == kHomeColors - 1 );
+				last = !seg.overflow ? index : last;
+			}
+			bool fits = true;
+			int ordinal = 0;
+			for ( size_t k = 0; k < s->jointSegs.size(); ++k )
+			{
+				const b2gJointSeg& seg = s->jointSegs[k];
+				int key = seg.overflow ? kHomeColors - 1 : ordered ? seg.colorIndex : ordinal++;
+				s->jointSegHome[k] = key;
+				fits = fits && seg.count <= s->jointHomeBase[key + 1] - s->jointHomeBase[key];
+			}
+			if ( !fits )
+			{
+				int need[kHomeColors] = { 0 };
+				for ( size_t k = 0; k < s->jointSegs.size(); ++k )
+				{
+					need[s->jointSegHome[k]] = s->jointSegs[k].count;
+				}
+				for ( int key = 0; key < kHomeColors; ++key )
+				{
+					int have = s->jointHomeBase[key + 1] - s->jointHomeBase[key];
+					need[key] = need[key] > have ? need[key] + need[key] / 2 + 32 : have;
+				}
+				int base = 0;
+				for ( int key = 0; key < kHomeColors; ++key )
+				{
+					s->jointHomeBase[key] = base;
+					base += need[key];
+					s->jointHomeCount[key] = 0;
+				}
+				s->jointHomeBase[kHomeColors] = base;
+				s->cacheValid = false;
+			}
+			s->jointHomeTotal = s->jointHomeBase[kHomeColors];
+		}
+		B2G_CUDA( persistent( s->jointTable, (size_t)( s->jointHomeTotal + 1 ) * jointQuads ) );
+		B2G_CUDA( s->jointAssembled.reserve( jointQuads * joint + 1 ) );
+		s->fullJointCapacity = ( joint + kStreamChunk ) & ~( kStreamChunk - 1 );
 		B2G_CUDA( persistent( s->residentStates[0], 2 * nb + 2 ) );
 		B2G_CUDA( persistent( s->residentStates[1], 2 * nb + 2 ) );
 		B2G_CUDA( persistent( s->residentBody, 2 * nb + 2 ) );
@@ -1094,6 +1151,16 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 		int packBlocks = ( bodies + s->contactTotal + s->jointTotal ) / 128 + 2;
 		s->fullCapacity += packBlocks * kStreamChunk;
 		s->dirtyCapacity += packBlocks * kStreamChunk;
+		s->fullJointCapacity += packBlocks * kStreamChunk;
+		B2G_CUDA( s->fullJointStream.reserve( (size_t)s->fullJointCapacity * jointQuads ) );
+		B2G_CUDA( s->hFullJoints.reserve( (size_t)s->fullJointCapacity * jointQuads ) );
+		s->fullJointCursor.store( 0, std::memory_order_relaxed );
+		s->fullJointCount.store( 0, std::memory_order_relaxed );
+		s->fullJointSent = 0;
+		if ( s->shadowJoints.size() < (size_t)( s->jointHomeTotal + 1 ) * b2g::kJointStride )
+		{
+			s->shadowJoints.resize( (size_t)( s->jointHomeTotal + 1 ) * b2g::kJointStride, 0 );
+		}
 		B2G_CUDA( s->fullStream.reserve( (size_t)s->fullCapacity * b2g::WR_COUNT ) );
 		B2G_CUDA( s->hFull.reserve( (size_t)s->fullCapacity * b2g::WR_COUNT ) );
 		B2G_CUDA( s->dirtyStream.reserve( (size_t)s->dirtyCapacity * b2g::kDirtyBodyQuads ) );
@@ -1139,7 +1206,12 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	P.residentBody = s->residentBody.ptr;
 	P.dirtyBodies = s->dirtyStream.ptr;
 	P.dirtyBodyCapacity = 0; // decided when the packing is done
-	P.rawJoints = reinterpret_cast<const uint8_t*>( s->wireAll.ptr + s->inJoints );
+	P.rawJoints = reinterpret_cast<const uint8_t*>( s->resident ? s->jointAssembled.ptr : s->wireAll.ptr + s->inJoints );
+	P.lightJoints = s->resident ? s->wireAll.ptr + s->inJoints : nullptr;
+	P.jointTable = s->jointTable.ptr;
+	P.fullJoints = s->fullJointStream.ptr;
+	P.prevOutJoints = s->outOther.ptr != nullptr ? reinterpret_cast<const float*>( s->outOther.ptr + s->prevOutJoints ) : nullptr;
+	P.jointAssembled = s->jointAssembled.ptr;
 	P.g.vel = s->vel.ptr;
 	P.g.pos = s->pos.ptr;
 	P.g.bodyK = s->bodyK.ptr;
@@ -1214,7 +1286,8 @@ static int b2gEnqueueUpload( b2GpuSolver* s )
 	if ( s->resident )
 	{
 		s->params.dirtyBodyCapacity = s->dirtySent;
-		s->lastH2D += ( (size_t)s->fullSent * b2g::WR_COUNT + (size_t)s->dirtySent * b2g::kDirtyBodyQuads ) * sizeof( float4 );
+		s->lastH2D += ( (size_t)s->fullSent * b2g::WR_COUNT + (size_t)s->dirtySent * b2g::kDirtyBodyQuads +
+						(size_t)s->fullJointSent * ( b2g::kJointStride / 16 ) ) * sizeof( float4 );
 	}
 	s->uploaded = true;
 	return 0;
@@ -1393,6 +1466,18 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 		if ( applyErr != cudaSuccess )
 		{
 			return b2gFail( "b2gApplyBodiesKernel launch", applyErr );
+		}
+		s->lastLaunches += 1;
+	}
+	if ( s->resident && s->params.jointCount > 0 )
+	{
+		// joints: the complete records of this step from the table, the previous outputs and the uploaded runs
+		int blocks = ( s->params.jointCount + 127 ) / 128;
+		b2g::b2gAssembleJointsKernel<<<blocks, 128, 0, s->stream>>>( s->params );
+		cudaError_t assembleErr = cudaGetLastError();
+		if ( assembleErr != cudaSuccess )
+		{
+			return b2gFail( "b2gAssembleJointsKernel launch", assembleErr );
 		}
 		s->lastLaunches += 1;
 	}
@@ -1659,6 +1744,16 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 		std::swap( s->outAll, s->outOther );
 		std::swap( s->residentStates[0], s->residentStates[1] );
 		s->prevOutImpulses = s->outImpulses;
+		s->prevOutJoints = s->outJoints;
+		for ( int key = 0; key < kHomeColors; ++key )
+		{
+			s->jointHomeCount[key] = 0;
+		}
+		for ( size_t k = 0; k < s->jointSegs.size(); ++k )
+		{
+			s->jointHomeCount[s->jointSegHome[k]] = s->jointSegs[k].count;
+			s->jointHomeSlot[s->jointSegHome[k]] = s->jointSegs[k].jointStart;
+		}
 		s->shadowBodyCount = s->params.bodyCount;
 		for ( int key = 0; key < kHomeColors; ++key )
 		{

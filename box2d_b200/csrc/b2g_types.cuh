@@ -83,6 +83,7 @@ constexpr int kLightIdMask = ( 1 << 28 ) - 1;
 constexpr int kLightBodyMass = 1 << 30;
 constexpr int kLightGroupShift = 28; // key >> 28 & 3 -> kMetaGroupRolling | kMetaGroupRestitution after << 3
 constexpr int kTableRows = 5;		 // WR_HEAD .. WR_ANCHOR2 of a contact, by home
+constexpr int kLightJointQuads = 6;	 // { home, ref, -, - } + B2L_JOINT_RUN_MAX bytes of prepared run
 constexpr int kDirtyBodyQuads = 5;	 // { body index, -, -, - }, the b2BodyState (2 quads), the packed constants (2 quads)
 
 struct ColorRange
@@ -169,6 +170,12 @@ struct StepParams
 	float4* residentBody;
 	const float4* dirtyBodies;	// [dirtyBodyCapacity * kDirtyBodyQuads] bodies whose state or constants the host changed
 	int dirtyBodyCapacity;
+	// joints in resident mode (lightJoints != nullptr): b2gAssembleJointsKernel builds rawJoints from these before the step
+	const float4* lightJoints;	// [jointCount * kLightJointQuads] { home, ref, -, - } + the joint's prepared run (b2lJointPreparedRun)
+	float4* jointTable;			// [joint homes * kJointStride / 16] the records as assembled for the last step, by home
+	const float4* fullJoints;	// the step's full joint records (kJointStride bytes each)
+	const float* prevOutJoints; // the previous step's joint impulse records (B2L_JOINT_OUT_FLOATS per joint of THAT step)
+	float4* jointAssembled;		// writable alias of rawJoints
 
 	// solver state in global memory (the grid-barrier kernel's view)
 	SolveView g;

@@ -370,9 +370,13 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 	}
 
 	// ---- joints: the prepared b2JointSim padded to 256 bytes; bodies renumbered to the batch, and the world's base in
-	// the joint-event bit set stored in the padding (read by jointEventTest)
+	// the joint-event bit set stored in the padding (read by jointEventTest).  Resident mode: a joint whose record equals
+	// what the device holds at its home -- outside the run of fields b2PrepareJoint rewrites every step -- travels as its
+	// home, the place of its previous output record and that run (b2gAssembleJointsKernel, b2g_resident.cuh).
 	{
 		float4* wireJoints = base + s->inJoints;
+		const bool resident = s->resident;
+		b2gStreamChunk full = { &s->fullJointCursor, s->fullJointCapacity, 0, 0, &s->streamOverflow };
 		int first = bodyCount + s->contactTotal;
 		int flat = ( begin > first ? begin : first ) - first;
 		int flatEnd = end - first;
@@ -383,6 +387,10 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 			int local = flat - s->jointStart[k];
 			int localEnd = ( flatEnd < s->jointStart[k + 1] ? flatEnd : s->jointStart[k + 1] ) - s->jointStart[k];
 			const b2gBodySeg& world = s->bodySegs[seg.world];
+			const int homeKey = resident ? s->jointSegHome[k] : 0;
+			const int homeBase = resident ? s->jointHomeBase[homeKey] : 0;
+			const int homeCount = resident && s->cacheUsable ? s->jointHomeCount[homeKey] : 0;
+			const int homeSlot = resident ? s->jointHomeSlot[homeKey] : 0;
 			for ( int i = local; i < localEnd; ++i )
 			{
 				alignas( 16 ) uint8_t padded[b2g::kJointStride] = { 0 };
@@ -397,10 +405,40 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 					}
 				}
 				memcpy( padded + B2L_JOINT_SIZE, &world.jointBitBase, 4 );
-				b2gStreamCopy( wireJoints + (size_t)( seg.jointStart + i ) * ( b2g::kJointStride / 16 ), padded, b2g::kJointStride / 16 );
+				if ( !resident )
+				{
+					b2gStreamCopy( wireJoints + (size_t)( seg.jointStart + i ) * ( b2g::kJointStride / 16 ), padded, b2g::kJointStride / 16 );
+					continue;
+				}
+				const int home = homeBase + i;
+				uint8_t* shadow = s->shadowJoints.data() + (size_t)home * b2g::kJointStride;
+				int runOffset = 0;
+				const int runBytes = b2lJointPreparedRun( reinterpret_cast<const b2lJointSim*>( padded )->type, &runOffset );
+				const bool clean = i < homeCount && memcmp( shadow, padded, (size_t)runOffset ) == 0 &&
+								   memcmp( shadow + runOffset + runBytes, padded + runOffset + runBytes, (size_t)( b2g::kJointStride - runOffset - runBytes ) ) == 0;
+				float4* light = wireJoints + (size_t)( seg.jointStart + i ) * b2g::kLightJointQuads;
+				int ref = homeSlot + i; // its record among the previous step's outputs
+				if ( clean )
+				{
+					alignas( 16 ) uint8_t run[B2L_JOINT_RUN_MAX] = { 0 };
+					memcpy( run, padded + runOffset, (size_t)runBytes );
+					b2gStreamCopy( light + 1, run, B2L_JOINT_RUN_MAX / 16 );
+				}
+				else
+				{
+					int entry = b2gStreamTake( full );
+					ref = ~entry;
+					b2gStreamCopy( s->hFullJoints.ptr + (size_t)entry * ( b2g::kJointStride / 16 ), padded, b2g::kJointStride / 16 );
+					memcpy( shadow, padded, b2g::kJointStride );
+				}
+				b2gStream4( light, b2gIntBits( home ), b2gIntBits( ref ), 0.0f, 0.0f );
 			}
 			flat = s->jointStart[k + 1];
 			k += 1;
+		}
+		if ( full.taken > 0 )
+		{
+			s->fullJointCount.fetch_add( full.taken, std::memory_order_relaxed );
 		}
 	}
 	_mm_sfence();
@@ -447,7 +485,7 @@ static size_t b2gPackedPrefix( const b2GpuSolver* s, int blocksDone )
 		int slot = s->contactSegs[k].slotStart + ( flat - s->contactStart[k] );
 		return s->inWire + (size_t)slot * s->wireQuads;
 	}
-	return s->inJoints + (size_t)( flat - s->contactTotal ) * ( b2g::kJointStride / 16 );
+	return s->inJoints + (size_t)( flat - s->contactTotal ) * s->jointWireQuads;
 }
 
 // enqueue the upload of quads [fromQuads, uptoQuads) of the input arena
@@ -492,8 +530,15 @@ static int b2gSendStreams( b2GpuSolver* s )
 	{
 		B2G_CUDA( cudaMemcpyAsync( s->dirtyStream.ptr, s->hDirty.ptr, (size_t)dirty * b2g::kDirtyBodyQuads * sizeof( float4 ), cudaMemcpyHostToDevice, s->stream ) );
 	}
+	int fullJoints = s->fullJointCursor.load( std::memory_order_acquire );
+	fullJoints = fullJoints < s->fullJointCapacity ? fullJoints : s->fullJointCapacity;
+	if ( fullJoints > 0 )
+	{
+		B2G_CUDA( cudaMemcpyAsync( s->fullJointStream.ptr, s->hFullJoints.ptr, (size_t)fullJoints * b2g::kJointStride, cudaMemcpyHostToDevice, s->stream ) );
+	}
 	s->fullSent = full;
 	s->dirtySent = dirty;
+	s->fullJointSent = fullJoints;
 	return 0;
 }
 
@@ -683,9 +728,15 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 				const float* record = outJoints + (size_t)( seg.jointStart + i ) * B2L_JOINT_OUT_FLOATS;
 				int offsets[2], floats[2];
 				int runs = b2lJointMutableRuns( b2gRdI( sim, offsetof( b2lJointSim, type ) ), offsets, floats );
+				uint8_t* shadow = s->resident ? s->shadowJoints.data() + (size_t)( s->jointHomeBase[s->jointSegHome[k]] + i ) * b2g::kJointStride : nullptr;
 				for ( int r = 0; r < runs; ++r )
 				{
 					memcpy( sim + offsets[r], record, (size_t)floats[r] * sizeof( float ) );
+					if ( shadow != nullptr )
+					{
+						// the device's table holds the same (b2gAssembleJointsKernel takes them from the output records)
+						memcpy( shadow + offsets[r], record, (size_t)floats[r] * sizeof( float ) );
+					}
 					record += floats[r];
 				}
 			}

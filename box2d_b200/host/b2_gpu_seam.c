@@ -16,6 +16,7 @@
 #include "core.h"
 #include "id_pool.h"
 #include "island.h"
+#include "joint.h"
 #include "parallel_for.h"
 #include "physics_world.h"
 #include "solver.h"
@@ -160,7 +161,7 @@ int b2GpuSeam_GetResidentStats( int worldIndex, int* fullContacts, int* dirtyBod
 	{
 		return 0;
 	}
-	return b2GpuSolverGetResidentStats( s_slots[worldIndex].solver, fullContacts, dirtyBodies, vouchedContacts );
+	return b2GpuSolverGetResidentStats( s_slots[worldIndex].solver, fullContacts, dirtyBodies, vouchedContacts, NULL );
 }
 
 const b2GpuStepDesc* b2GpuSeam_GetLastDesc( int worldIndex )
@@ -198,12 +199,19 @@ typedef struct b2SeamTeam
 	int* labels;
 	int labelCount, labelBlocks;
 	b2AtomicInt labelNext, labelDone;
+	// host joint prepare (b2PrepareJoint, src/joint.c:1406): the colours' joint arrays laid end to end, overflow colour last
+	b2StepContext* context;
+	b2JointSim* jointArrays[B2_GRAPH_COLOR_COUNT];
+	int jointStarts[B2_GRAPH_COLOR_COUNT + 1];
+	int jointArrayCount, jointBlocks;
+	b2AtomicInt jointNext, jointDone;
 	b2AtomicInt phase;
 	b2AtomicInt inPack, inUnpack;
 	b2AtomicInt failed;
 } b2SeamTeam;
 
 #define B2_SEAM_LABEL_BLOCK 512
+#define B2_SEAM_JOINT_BLOCK 32
 
 static inline void b2SeamRelax( int* spins )
 {
@@ -242,10 +250,39 @@ static void b2SeamTeamLabels( b2SeamTeam* team )
 	}
 }
 
+// Joint preparation chases world->bodies -> solverSets -> bodySims (e.g. src/revolute_joint.c:221-266): host-only structures,
+// so it stays on the host -- the reference's own b2PrepareJoint, joint by joint, in blocks the
+// team claims (the reference runs it as its first solver stage, src/solver.c:1060-1077).
+static void b2SeamTeamJoints( b2SeamTeam* team )
+{
+	for ( ;; )
+	{
+		int block = b2AtomicFetchAddInt( &team->jointNext, 1 );
+		if ( block >= team->jointBlocks )
+		{
+			break;
+		}
+		int begin = block * B2_SEAM_JOINT_BLOCK;
+		int total = team->jointStarts[team->jointArrayCount];
+		int end = begin + B2_SEAM_JOINT_BLOCK < total ? begin + B2_SEAM_JOINT_BLOCK : total;
+		int array = 0;
+		for ( int i = begin; i < end; ++i )
+		{
+			while ( team->jointStarts[array + 1] <= i )
+			{
+				array += 1;
+			}
+			b2PrepareJoint( team->jointArrays[array] + ( i - team->jointStarts[array] ), team->context );
+		}
+		b2AtomicFetchAddInt( &team->jointDone, 1 );
+	}
+}
+
 static void b2SeamTeamHelper( void* taskContext )
 {
 	b2SeamTeam* team = taskContext;
 	int spins = 0;
+	b2SeamTeamJoints( team );
 	b2SeamTeamLabels( team );
 	while ( b2AtomicLoadInt( &team->phase ) < b2_seamPackOpen )
 	{
@@ -372,10 +409,6 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 		taskContext->hasHitEvents = false;
 	}
 
-	// Joint preparation chases world->bodies -> solverSets -> bodySims (e.g. src/revolute_joint.c:221-266):
-	// host-only structures, so it stays on the host.
-	b2GpuSeam_PrepareJoints( world, context );
-
 	b2SolverSet* awakeSet = world->solverSets.data + b2_awakeSet;
 	const bool captured = slot->islandsCaptured;
 	slot->islandsCaptured = false;
@@ -394,6 +427,22 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 	team.labelBlocks = ( team.labelCount + B2_SEAM_LABEL_BLOCK - 1 ) / B2_SEAM_LABEL_BLOCK;
 	b2AtomicStoreInt( &team.labelNext, 0 );
 	b2AtomicStoreInt( &team.labelDone, 0 );
+	team.context = context;
+	team.jointArrayCount = 0;
+	team.jointStarts[0] = 0;
+	for ( int i = 0; i < B2_GRAPH_COLOR_COUNT; ++i ) // the overflow colour is the last one (B2_OVERFLOW_INDEX)
+	{
+		b2GraphColor* color = world->constraintGraph.colors + i;
+		if ( color->jointSims.count > 0 )
+		{
+			team.jointArrays[team.jointArrayCount] = color->jointSims.data;
+			team.jointStarts[team.jointArrayCount + 1] = team.jointStarts[team.jointArrayCount] + color->jointSims.count;
+			team.jointArrayCount += 1;
+		}
+	}
+	team.jointBlocks = ( team.jointStarts[team.jointArrayCount] + B2_SEAM_JOINT_BLOCK - 1 ) / B2_SEAM_JOINT_BLOCK;
+	b2AtomicStoreInt( &team.jointNext, 0 );
+	b2AtomicStoreInt( &team.jointDone, 0 );
 	b2AtomicStoreInt( &team.phase, b2_seamLabels );
 	b2AtomicStoreInt( &team.inPack, 0 );
 	b2AtomicStoreInt( &team.inUnpack, 0 );
@@ -417,8 +466,9 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 
 	// island hint: lets the device solve islands independently in shared memory (no grid barriers)
 	int spins = 0;
+	b2SeamTeamJoints( &team );
 	b2SeamTeamLabels( &team );
-	while ( b2AtomicLoadInt( &team.labelDone ) < team.labelBlocks )
+	while ( b2AtomicLoadInt( &team.labelDone ) < team.labelBlocks || b2AtomicLoadInt( &team.jointDone ) < team.jointBlocks )
 	{
 		b2SeamRelax( &spins );
 	}

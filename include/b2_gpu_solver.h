@@ -268,9 +268,11 @@ B2GPU_API int b2GpuSolverGetIslandPlan( const b2GpuSolver* solver, int* binCount
  * the pack pass only uploads what differs from that -- a 16-byte record per contact whose manifold the narrow phase recycled
  * (src/physics_world.c:508-560), the full 96 bytes otherwise.  Returns 1 when the last step ran in resident mode and fills
  * how many contacts travelled as full records, how many bodies were re-uploaded and how many contacts were taken on the
- * caller's word (b2GpuStepDesc::recycled) without their record being read; 0 (counts untouched) otherwise.  The results do
- * not depend on the mode (bit-identical); B2GPU_RESIDENT=0 turns it off. */
-B2GPU_API int b2GpuSolverGetResidentStats( const b2GpuSolver* solver, int* fullContacts, int* dirtyBodies, int* vouchedContacts );
+ * caller's word (b2GpuStepDesc::recycled) without their record being read, and how many joints travelled as full 256-byte
+ * records (the others as 96 bytes: the fields b2PrepareJoint rewrites every step); 0 (counts untouched) otherwise.  The
+ * results do not depend on the mode (bit-identical); B2GPU_RESIDENT=0 turns it off.  Any of the pointers may be NULL. */
+B2GPU_API int b2GpuSolverGetResidentStats( const b2GpuSolver* solver, int* fullContacts, int* dirtyBodies, int* vouchedContacts,
+										  int* fullJoints );
 /* Host utility for callers that have island labels but no island bookkeeping: fill sizes[desc->islandCount] from
  * desc->bodyIsland and the constraint arrays (one pass over the constraints).  Returns 0 on success. */
 B2GPU_API int b2GpuCountIslandSizes( const b2GpuStepDesc* desc, b2GpuIslandSize* sizes );

@@ -300,6 +300,46 @@ static inline B2L_HD int b2lJointMutableRuns( int type, int offsets[2], int floa
 	}
 }
 
+/* What b2PrepareJoint (src/joint.c:1406 + the per-type prepare functions) REWRITES every step from the bodies' poses: the
+ * body indices, the anchor frames / anchors in world orientation, deltaCenter and the effective masses that depend on them.
+ * In every joint type these fields are one run of consecutive bytes that starts at indexA.  Everything outside this run and
+ * outside the mutable runs above only changes when the application changes the joint (or the step parameters).  Returns the
+ * length of the run in bytes (at most B2L_JOINT_RUN_MAX) and its offset from the start of b2JointSim; 0 for a filter joint. */
+#define B2L_JOINT_RUN_MAX 80
+static inline B2L_HD int b2lJointPreparedRun( int type, int* offset )
+{
+	switch ( type )
+	{
+		case b2l_distanceJoint: /* indexA .. axialMass (anchors, deltaCenter, distanceSoftness, axialMass) */
+			*offset = (int)offsetof( b2lJointSim, u.distance.indexA );
+			return (int)( offsetof( b2lJointSim, u.distance.axialMass ) + 4 - offsetof( b2lJointSim, u.distance.indexA ) );
+		case b2l_motorJoint: /* indexA .. angularMass */
+			*offset = (int)offsetof( b2lJointSim, u.motor.indexA );
+			return (int)( offsetof( b2lJointSim, u.motor.angularMass ) + 4 - offsetof( b2lJointSim, u.motor.indexA ) );
+		case b2l_moverJoint: /* indexA .. linearMass */
+			*offset = (int)offsetof( b2lJointSim, u.mover.indexA );
+			return (int)( offsetof( b2lJointSim, u.mover.linearMass ) + 4 - offsetof( b2lJointSim, u.mover.indexA ) );
+		case b2l_pogoJoint: /* indexA .. linearMass (velocity behind it is the solver's own) */
+			*offset = (int)offsetof( b2lJointSim, u.pogo.indexA );
+			return (int)( offsetof( b2lJointSim, u.pogo.linearMass ) + 4 - offsetof( b2lJointSim, u.pogo.indexA ) );
+		case b2l_prismaticJoint: /* indexA .. deltaCenter */
+			*offset = (int)offsetof( b2lJointSim, u.prismatic.indexA );
+			return (int)( offsetof( b2lJointSim, u.prismatic.deltaCenter ) + 8 - offsetof( b2lJointSim, u.prismatic.indexA ) );
+		case b2l_revoluteJoint: /* indexA .. axialMass */
+			*offset = (int)offsetof( b2lJointSim, u.revolute.indexA );
+			return (int)( offsetof( b2lJointSim, u.revolute.axialMass ) + 4 - offsetof( b2lJointSim, u.revolute.indexA ) );
+		case b2l_weldJoint: /* indexA .. axialMass */
+			*offset = (int)offsetof( b2lJointSim, u.weld.indexA );
+			return (int)( offsetof( b2lJointSim, u.weld.axialMass ) + 4 - offsetof( b2lJointSim, u.weld.indexA ) );
+		case b2l_wheelJoint: /* indexA .. axialMass (perpMass, motorMass, axialMass) */
+			*offset = (int)offsetof( b2lJointSim, u.wheel.indexA );
+			return (int)( offsetof( b2lJointSim, u.wheel.axialMass ) + 4 - offsetof( b2lJointSim, u.wheel.indexA ) );
+		default:
+			*offset = 0;
+			return 0;
+	}
+}
+
 #if defined( __cplusplus )
 static_assert( sizeof( b2lJointSim ) == B2L_JOINT_SIZE, "b2JointSim mirror size" );
 static_assert( sizeof( b2lRevolute ) == 120 && sizeof( b2lWeld ) == 104 && sizeof( b2lPrismatic ) == 116, "joint mirrors" );
