@@ -40,7 +40,7 @@ def launch_summary(rnd: str) -> None:
 	steps = max(len(v) for v in ours.values()) if ours else 1
 	total = sum(sum(v) for v in ours.values()) / steps
 	with open(PROF / f"{rnd}_launch_summary.txt", "w") as f:
-		f.write(f"ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 3 --warmup 3 (many_pyramids)\n")
+		f.write(f"ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 3 --warmup 3 --no-batch --no-cpu-baseline (many_pyramids)\n")
 		f.write("per-launch times under ncu are serialised and cold-cache: the SHARE of the step is what must agree with bench.py\n\n")
 		f.write(f"{'kernel':42s} {'launches':>8s} {'mean us':>9s} {'min us':>9s} {'share of step':>14s}\n")
 		for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
@@ -111,6 +111,7 @@ def main() -> None:
 					   ("partition", "large_pyramid, two-phase partition for a cluster with owner lists"),
 					   ("cluster", "large_pyramid, one 16-block cluster for the single island"),
 					   ("grid", "joint_grid, grid-barrier kernel: the island does not fit any cluster"),
+					   ("assemble", "joint_grid, resident mode: the step's joint records from the table, the previous outputs and the uploaded runs"),
 					   ("island_batch", "batch of 8192 small_pyramid worlds")):
 		kernel_summary(rnd, name, note)
 	for f in list(OUT.glob(f"{rnd}_bench_*.json")) + list(OUT.glob(f"{rnd}_e2e_trace.txt")):
