@@ -357,7 +357,10 @@ def run_scene(args) -> int:
 
 	sampler = ClockSampler(local_rank)
 	# host phases of the GPU arm (collide, pack/unpack, finalize): the ranks of one box share its cores
-	workers = max(1, min((os.cpu_count() or 1) // max(1, world_size), 16))
+	# (with several ranks one core per rank is left to the process's other threads: the helpers spin across the short gaps
+	# between the host passes, an oversubscribed box would make them wait for each other's time slices)
+	cores = os.cpu_count() or 1
+	workers = max(1, min(cores, 16)) if world_size == 1 else max(1, min(cores // world_size - 1, 16))
 	scene = args.workload
 	with b2.World(host, scene, workers) as world:
 		world.step(SETTLE_STEPS.get(scene, 0) + args.warmup)

@@ -71,68 +71,61 @@ __global__ void __launch_bounds__( 256 ) b2gCommitKernel( const __grid_constant_
 //                              b2lJointMutableRuns lists) + the fresh prepared run, in that order -- the motor joint's
 //                              linearMass is both an output and re-prepared, and the host's value is the prepared one
 // Idempotent (the table ends up holding what was assembled), one thread per joint.
-__global__ void __launch_bounds__( 128 ) b2gAssembleJointsKernel( const __grid_constant__ StepParams P )
+__global__ void __launch_bounds__( 256 ) b2gAssembleJointsKernel( const __grid_constant__ StepParams P )
 {
+	// 16 threads per joint, one per 16-byte quad of the record: coalesced on every side, no per-thread record
 	constexpr int quads = kJointStride / 16;
-	for ( int j = (int)( blockIdx.x * blockDim.x + threadIdx.x ); j < P.jointCount; j += (int)( gridDim.x * blockDim.x ) )
+	const int total = P.jointCount * quads;
+	for ( int t = (int)( blockIdx.x * blockDim.x + threadIdx.x ); t < total; t += (int)( gridDim.x * blockDim.x ) )
 	{
+		const int j = t / quads, q = t - j * quads;
 		const float4* light = P.lightJoints + (size_t)j * kLightJointQuads;
-		float4 head = light[0];
-		int home = __float_as_int( head.x ), ref = __float_as_int( head.y );
+		const float4 head = light[0];
+		const int home = __float_as_int( head.x ), ref = __float_as_int( head.y );
 		float4* out = P.jointAssembled + (size_t)j * quads;
 		float4* keep = P.jointTable + (size_t)home * quads;
 		if ( ref < 0 )
 		{
-			const float4* full = P.fullJoints + (size_t)( ~ref ) * quads;
-#pragma unroll
-			for ( int q = 0; q < quads; ++q )
-			{
-				float4 value = full[q];
-				out[q] = value;
-				keep[q] = value;
-			}
-			continue;
-		}
-		float record[kJointStride / 4];
-#pragma unroll
-		for ( int q = 0; q < quads; ++q )
-		{
-			float4 value = keep[q];
-			record[4 * q + 0] = value.x;
-			record[4 * q + 1] = value.y;
-			record[4 * q + 2] = value.z;
-			record[4 * q + 3] = value.w;
-		}
-		const int type = __float_as_int( record[offsetof( b2lJointSim, type ) / 4] );
-		{
-			int offsets[2], floats[2];
-			int runs = b2lJointMutableRuns( type, offsets, floats );
-			const float* previous = P.prevOutJoints + (size_t)ref * B2L_JOINT_OUT_FLOATS;
-			for ( int r = 0; r < runs; ++r )
-			{
-				for ( int k = 0; k < floats[r]; ++k )
-				{
-					record[offsets[r] / 4 + k] = previous[k];
-				}
-				previous += floats[r];
-			}
-		}
-		{
-			int offset = 0;
-			int bytes = b2lJointPreparedRun( type, &offset );
-			const float* run = reinterpret_cast<const float*>( light + 1 );
-			for ( int k = 0; k < bytes / 4; ++k )
-			{
-				record[offset / 4 + k] = run[k];
-			}
-		}
-#pragma unroll
-		for ( int q = 0; q < quads; ++q )
-		{
-			float4 value = make_float4( record[4 * q + 0], record[4 * q + 1], record[4 * q + 2], record[4 * q + 3] );
+			float4 value = P.fullJoints[(size_t)( ~ref ) * quads + q];
 			out[q] = value;
 			keep[q] = value;
+			continue;
 		}
+		float4 value = keep[q];
+		const int type = __float_as_int( keep[0].w ); // b2JointSim::type, the fourth word of the record
+		static_assert( offsetof( b2lJointSim, type ) == 12, "type is expected in the first quad" );
+		float words[4] = { value.x, value.y, value.z, value.w };
+		int offsets[2], floats[2];
+		const int runs = b2lJointMutableRuns( type, offsets, floats );
+		int runOffset = 0;
+		const int runBytes = b2lJointPreparedRun( type, &runOffset );
+		const float* previous = P.prevOutJoints + (size_t)ref * B2L_JOINT_OUT_FLOATS;
+		const float* run = reinterpret_cast<const float*>( light + 1 );
+#pragma unroll
+		for ( int i = 0; i < 4; ++i )
+		{
+			const int word = 4 * q + i; // index of the float in the record
+			// the solver's own outputs of the previous step first ...
+			int before = 0;
+			for ( int r = 0; r < runs; ++r )
+			{
+				int first = offsets[r] / 4;
+				if ( word >= first && word < first + floats[r] )
+				{
+					words[i] = previous[before + word - first];
+				}
+				before += floats[r];
+			}
+			// ... then what b2PrepareJoint wrote this step (it wins where the two overlap: the motor joint's linearMass)
+			int first = runOffset / 4;
+			if ( word >= first && word < first + runBytes / 4 )
+			{
+				words[i] = run[word - first];
+			}
+		}
+		value = make_float4( words[0], words[1], words[2], words[3] );
+		out[q] = value;
+		keep[q] = value;
 	}
 }
 

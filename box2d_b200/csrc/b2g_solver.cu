@@ -1472,8 +1472,9 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 	if ( s->resident && s->params.jointCount > 0 )
 	{
 		// joints: the complete records of this step from the table, the previous outputs and the uploaded runs
-		int blocks = ( s->params.jointCount + 127 ) / 128;
-		b2g::b2gAssembleJointsKernel<<<blocks, 128, 0, s->stream>>>( s->params );
+		int blocks = ( s->params.jointCount * ( b2g::kJointStride / 16 ) + 255 ) / 256;
+		blocks = blocks > s->smCount * 8 ? s->smCount * 8 : blocks;
+		b2g::b2gAssembleJointsKernel<<<blocks, 256, 0, s->stream>>>( s->params );
 		cudaError_t assembleErr = cudaGetLastError();
 		if ( assembleErr != cudaSuccess )
 		{
