@@ -190,6 +190,10 @@ def _bind_harness(lib: ctypes.CDLL) -> ctypes.CDLL:
 	"""Prototypes of box2d_b200/host/b2h_harness.c (linked into every host library variant)."""
 	lib.b2h_create.restype = ctypes.c_int
 	lib.b2h_create.argtypes = [ctypes.c_char_p, ctypes.c_int]
+	lib.b2h_create_variant.restype = ctypes.c_int
+	lib.b2h_create_variant.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_int]
+	lib.b2h_step_many.restype = ctypes.c_int
+	lib.b2h_step_many.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int, ctypes.c_int]
 	lib.b2h_destroy.argtypes = [ctypes.c_int]
 	lib.b2h_step.argtypes = [ctypes.c_int, ctypes.c_int]
 	lib.b2h_set_substeps.argtypes = [ctypes.c_int, ctypes.c_int]
@@ -228,6 +232,10 @@ def host_lib() -> ctypes.CDLL:
 	lib.b2GpuSeam_GetLastDesc.argtypes = [ctypes.c_int]
 	lib.b2GpuSeam_GetTotals.restype = None
 	lib.b2GpuSeam_GetTotals.argtypes = [ctypes.c_int, ctypes.POINTER(SeamTotals), ctypes.c_int]
+	lib.b2GpuSeam_CreateGroup.restype = ctypes.c_int
+	lib.b2GpuSeam_CreateGroup.argtypes = [ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+	lib.b2GpuSeam_DestroyGroup.restype = None
+	lib.b2GpuSeam_DestroyGroup.argtypes = [ctypes.c_int]
 	lib.b2GpuSeam_GetResidentStats.restype = ctypes.c_int
 	lib.b2GpuSeam_GetResidentStats.argtypes = [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3
 	lib.b2GpuSeam_InstallPinnedAllocator.restype = None
@@ -236,12 +244,45 @@ def host_lib() -> ctypes.CDLL:
 	return lib
 
 
+def step_many(lib: ctypes.CDLL, worlds, steps: int) -> None:
+	"""Step the worlds concurrently, one native thread per world (b2h_step_many)."""
+	handles = (ctypes.c_int * len(worlds))(*[w.handle for w in worlds])
+	if lib.b2h_step_many(handles, len(worlds), steps) != 0:
+		raise RuntimeError("b2h_step_many: could not start a thread per world")
+
+
+class WorldGroup:
+	"""Worlds of the GPU host library that are stepped as ONE batch per step (b2GpuSeam_CreateGroup)."""
+
+	def __init__(self, lib: ctypes.CDLL, worlds):
+		self.lib = lib
+		self.worlds = list(worlds)
+		indices = (ctypes.c_int * len(self.worlds))(*[w.world_index() for w in self.worlds])
+		self.group = lib.b2GpuSeam_CreateGroup(indices, len(self.worlds))
+		if self.group < 0:
+			raise RuntimeError("b2GpuSeam_CreateGroup failed")
+
+	def step(self, steps: int = 1) -> None:
+		step_many(self.lib, self.worlds, steps)
+
+	def close(self) -> None:
+		if self.group >= 0:
+			self.lib.b2GpuSeam_DestroyGroup(self.group)
+			self.group = -1
+
+	def __enter__(self):
+		return self
+
+	def __exit__(self, *exc):
+		self.close()
+
+
 class World:
 	"""A scene in one of the host libraries (reference or GPU), driven through the b2h_* harness."""
 
-	def __init__(self, lib: ctypes.CDLL, scene: str, workers: int = 1):
+	def __init__(self, lib: ctypes.CDLL, scene: str, workers: int = 1, variant: int = 0):
 		self.lib = lib
-		self.handle = lib.b2h_create(scene.encode(), workers)
+		self.handle = lib.b2h_create_variant(scene.encode(), workers, variant) if variant else lib.b2h_create(scene.encode(), workers)
 		if self.handle < 0:
 			raise ValueError(f"unknown scene {scene!r} or no free world slot ({self.handle})")
 

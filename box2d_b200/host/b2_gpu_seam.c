@@ -25,14 +25,19 @@
 #include "box2d/base.h"
 #include "box2d/constants.h"
 
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 /* ---- per world-slot device solvers ---------------------------------------------------------------------- */
 
+struct b2SeamGroup;
+
 typedef struct b2SeamSlot
 {
+	struct b2SeamGroup* group; /* the world is stepped as a member of a group (b2GpuSeam_CreateGroup) */
+	int groupMember;
 	b2GpuSolver* solver;
 	int* islandLabels;
 	int islandLabelCapacity;
@@ -55,6 +60,25 @@ typedef struct b2SeamSlot
 static b2SeamSlot s_slots[B2_MAX_WORLDS];
 static int s_mode = -1;
 
+/* A group of worlds that meet at the seam (see b2_gpu_seam.h) */
+typedef struct b2SeamGroup
+{
+	b2GpuSolver* solver; /* one solver for the whole group */
+	int count;
+	int* worldIndices;
+	b2GpuStepDesc* descs;
+	b2GpuStepResult* results;
+	pthread_mutex_t mutex;
+	pthread_cond_t arrivedAll;
+	int arrived;
+	unsigned round;
+	int failed;
+	int inUse;
+} b2SeamGroup;
+
+#define B2_SEAM_MAX_GROUPS 16
+static b2SeamGroup s_groups[B2_SEAM_MAX_GROUPS];
+
 static int b2SeamEnvInt( const char* name, int fallback )
 {
 	const char* v = getenv( name );
@@ -70,6 +94,10 @@ static void b2SeamFatal( const char* what )
 
 static void b2SeamReleaseSlot( b2SeamSlot* slot )
 {
+	if ( slot->group != NULL )
+	{
+		return; /* a member of a live group: released with the group */
+	}
 	if ( slot->solver != NULL )
 	{
 		b2GpuSolverDestroy( slot->solver );
@@ -83,6 +111,10 @@ static void b2SeamReleaseSlot( b2SeamSlot* slot )
 static b2SeamSlot* b2SeamGetSlot( b2World* world )
 {
 	b2SeamSlot* slot = s_slots + world->worldId;
+	if ( slot->group != NULL )
+	{
+		return slot; /* the group owns the device solver */
+	}
 	if ( slot->solver != NULL && slot->generation != world->generation )
 	{
 		// the slot's previous world was destroyed (src/physics_world.c, b2DestroyWorld bumps the generation): its device
@@ -391,6 +423,155 @@ void b2GpuSeam_BeforeIslandSplit( b2World* world, b2StepContext* context )
 	slot->islandsCaptured = true;
 }
 
+/* ---- world-level batched step: groups ------------------------------------------------------------------------ */
+
+int b2GpuSeam_CreateGroup( const int* worldIndices, int worldCount )
+{
+	if ( worldIndices == NULL || worldCount <= 0 )
+	{
+		return -1;
+	}
+	for ( int g = 0; g < B2_SEAM_MAX_GROUPS; ++g )
+	{
+		b2SeamGroup* group = s_groups + g;
+		if ( group->inUse )
+		{
+			continue;
+		}
+		for ( int i = 0; i < worldCount; ++i )
+		{
+			int w = worldIndices[i];
+			if ( w < 0 || w >= B2_MAX_WORLDS || s_slots[w].group != NULL )
+			{
+				return -1;
+			}
+		}
+		memset( group, 0, sizeof( *group ) );
+		group->solver = b2GpuSolverCreate( b2SeamEnvInt( "B2GPU_DEVICE", 0 ) );
+		if ( group->solver == NULL )
+		{
+			b2SeamFatal( "cannot create the device solver of a group" );
+		}
+		group->count = worldCount;
+		group->worldIndices = malloc( (size_t)worldCount * sizeof( int ) );
+		group->descs = calloc( (size_t)worldCount, sizeof( b2GpuStepDesc ) );
+		group->results = calloc( (size_t)worldCount, sizeof( b2GpuStepResult ) );
+		pthread_mutex_init( &group->mutex, NULL );
+		pthread_cond_init( &group->arrivedAll, NULL );
+		group->inUse = 1;
+		for ( int i = 0; i < worldCount; ++i )
+		{
+			int w = worldIndices[i];
+			group->worldIndices[i] = w;
+			b2SeamReleaseSlot( s_slots + w ); /* a solver the world had on its own */
+			s_slots[w].group = group;
+			s_slots[w].groupMember = i;
+		}
+		return g;
+	}
+	return -1;
+}
+
+void b2GpuSeam_DestroyGroup( int g )
+{
+	if ( g < 0 || g >= B2_SEAM_MAX_GROUPS || s_groups[g].inUse == 0 )
+	{
+		return;
+	}
+	b2SeamGroup* group = s_groups + g;
+	for ( int i = 0; i < group->count; ++i )
+	{
+		b2SeamSlot* slot = s_slots + group->worldIndices[i];
+		slot->group = NULL;
+		b2SeamReleaseSlot( slot );
+	}
+	b2GpuSolverDestroy( group->solver );
+	free( group->worldIndices );
+	free( group->descs );
+	free( group->results );
+	pthread_mutex_destroy( &group->mutex );
+	pthread_cond_destroy( &group->arrivedAll );
+	memset( group, 0, sizeof( *group ) );
+}
+
+/* The seam of a world that is a member of a group: prepare on this world's thread, meet the others, let the last one solve. */
+static void b2SeamSolveInGroup( b2World* world, b2StepContext* context, b2SeamSlot* slot )
+{
+	b2SeamGroup* group = slot->group;
+	const int member = slot->groupMember;
+	uint64_t seamTicks = b2GetTicks();
+
+	b2GpuSeam_PrepareJoints( world, context );
+	b2SeamReserveIslands( slot, world );
+	b2GpuStepDesc* desc = group->descs + member;
+	b2GpuSeam_BuildDesc( world, context, desc );
+	if ( slot->islandsCaptured )
+	{
+		desc->bodyIsland = slot->islandLabels;
+		desc->islandSizes = slot->islandSizes;
+		desc->islandCount = slot->capturedIslandCount;
+	}
+	else
+	{
+		b2GpuSeam_FillIslands( world, desc, slot->islandLabels, slot->islandSizes, false );
+	}
+	slot->islandsCaptured = false;
+	slot->collidesSinceSolve = 0; /* the batch runs in plain mode: no recycle hints */
+
+	b2GpuStepResult* result = group->results + member;
+	memset( result, 0, sizeof( *result ) );
+	b2TaskContext* taskContext0 = world->taskContexts.data + 0;
+	result->hitEventBits = taskContext0->hitEventBitSet.bits;
+	result->jointEventBits = taskContext0->jointStateBitSet.bits;
+
+	pthread_mutex_lock( &group->mutex );
+	group->arrived += 1;
+	if ( group->arrived == group->count )
+	{
+		// the last world to arrive solves the whole group; the library packs / unpacks on its own host threads while the
+		// other worlds' threads sleep
+		int rc = b2GpuSolverStepBatch( group->solver, group->descs, group->count, group->results );
+		group->failed = rc != 0;
+		group->arrived = 0;
+		group->round += 1;
+		pthread_cond_broadcast( &group->arrivedAll );
+	}
+	else
+	{
+		unsigned round = group->round;
+		while ( group->round == round )
+		{
+			pthread_cond_wait( &group->arrivedAll, &group->mutex );
+		}
+	}
+	int failed = group->failed;
+	pthread_mutex_unlock( &group->mutex );
+	if ( failed )
+	{
+		b2SeamFatal( "b2GpuSolverStepBatch failed" );
+	}
+
+	slot->lastResult = *result;
+	slot->lastDesc = *desc;
+	slot->totals.steps += 1;
+	slot->totals.kernelMs += result->kernelMs;
+	slot->totals.abiMs += result->totalMs;
+	slot->totals.h2dBytes += (double)result->h2dBytes;
+	slot->totals.d2hBytes += (double)result->d2hBytes;
+	slot->totals.launches += result->kernelLaunches;
+	slot->totals.seamMs += b2GetMilliseconds( seamTicks );
+	taskContext0->hasHitEvents = result->hasHitEvents != 0;
+	b2Profile* profile = &world->profile;
+	profile->prepareConstraints += result->stageMs[b2GpuStage_prepareConstraints];
+	profile->integrateVelocities += result->stageMs[b2GpuStage_integrateVelocities];
+	profile->warmStart += result->stageMs[b2GpuStage_warmStart];
+	profile->solveImpulses += result->stageMs[b2GpuStage_solveImpulses];
+	profile->integratePositions += result->stageMs[b2GpuStage_integratePositions];
+	profile->relaxImpulses += result->stageMs[b2GpuStage_relaxImpulses];
+	profile->applyRestitution += result->stageMs[b2GpuStage_applyRestitution];
+	profile->storeImpulses += result->stageMs[b2GpuStage_storeImpulses];
+}
+
 /* ---- the seam ------------------------------------------------------------------------------------------- */
 
 void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
@@ -407,6 +588,12 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 		b2SetBitCountAndClear( &taskContext->jointStateBitSet, jointIdCapacity );
 		b2SetBitCountAndClear( &taskContext->hitEventBitSet, contactIdCapacity );
 		taskContext->hasHitEvents = false;
+	}
+
+	if ( slot->group != NULL )
+	{
+		b2SeamSolveInGroup( world, context, slot );
+		return;
 	}
 
 	b2SolverSet* awakeSet = world->solverSets.data + b2_awakeSet;

@@ -50,6 +50,17 @@ void b2GpuSeam_ContactRecycled( b2World* world, int contactIndex, const b2Contac
  * Call before creating any world. */
 void b2GpuSeam_InstallPinnedAllocator( void );
 
+/* World-level batched step (the RL-style workload).  A GROUP is a set of independent worlds that
+ * the application steps concurrently -- one thread per world, every world with the same time step and sub-step count
+ * (include/box2d/box2d.h:31-32: different worlds may be stepped from different threads).  Inside b2World_Step each world
+ * runs its own broad phase, narrow phase and solver setup as always; at the seam the worlds of a group meet, and the last
+ * one to arrive solves ALL of them with one b2GpuSolverStepBatch (one launch sequence, one pair of transfers) while the
+ * others wait; then every world finalizes on its own thread.  Results are those of stepping each world alone (bit for
+ * bit).  Every world of a group must be stepped in every round, or the others wait for it.  Worlds of a group should be
+ * created with workerCount = 1 (their parallelism is the group).  Returns a group id >= 0, or -1. */
+int b2GpuSeam_CreateGroup( const int* worldIndices, int worldCount );
+void b2GpuSeam_DestroyGroup( int group );
+
 /* Sums over the steps of a world slot since the last reset (for benchmarks). */
 typedef struct b2GpuSeamTotals
 {

@@ -21,6 +21,7 @@
 #include "benchmarks.h"
 #include "determinism.h"
 
+#include <pthread.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -49,6 +50,10 @@ typedef struct b2hWorld
 } b2hWorld;
 
 static b2hWorld s_worlds[B2H_MAX_WORLDS];
+
+/* Variant of the scene being created (b2h_create_variant): worlds of a batch differ by an offset derived from their index,
+ * never from an RNG.  0 = the scene as the reference's benchmarks build it. */
+static int s_variant = 0;
 
 /* ---- small scenes ------------------------------------------------------------------------------------------ */
 
@@ -79,6 +84,12 @@ static void b2hCreatePyramid( b2WorldId worldId, int baseCount, float extent )
 		for ( int j = i; j < baseCount; ++j )
 		{
 			float x = ( i + 1.0f ) * extent + 2.0f * ( j - i ) * extent + centerX - 0.5f;
+			if ( s_variant != 0 )
+			{
+				// every world of a batch gets its own, slightly different pile
+				x += 0.004f * (float)( ( s_variant * 7 + i * 3 + j * 5 ) % 11 - 5 ) + 0.0002f * (float)( s_variant % 97 );
+				bodyDef.linearVelocity = (b2Vec2){ 0.05f * (float)( ( s_variant + i + 2 * j ) % 5 - 2 ), 0.0f };
+			}
 			bodyDef.position = (b2Pos){ x, y };
 			b2BodyId bodyId = b2CreateBody( worldId, &bodyDef );
 			b2CreatePolygonShape( bodyId, &shapeDef, &box );
@@ -744,6 +755,14 @@ B2H_API int b2h_create( const char* scene, int workerCount )
 	return h;
 }
 
+B2H_API int b2h_create_variant( const char* scene, int workerCount, int variant )
+{
+	s_variant = variant;
+	int h = b2h_create( scene, workerCount );
+	s_variant = 0;
+	return h;
+}
+
 B2H_API void b2h_destroy( int h )
 {
 	b2hWorld* w = s_worlds + h;
@@ -785,6 +804,50 @@ B2H_API void b2h_step( int h, int n )
 		}
 		w->stepIndex += 1;
 	}
+}
+
+/* Step many worlds concurrently, one thread per world, `n` steps each (include/box2d/box2d.h:31-32).  In front of the seam
+ * with the worlds in a group (b2GpuSeam_CreateGroup) every round of steps is one batched solve; in front of the CPU solver
+ * the worlds simply run side by side. */
+typedef struct b2hStepJob
+{
+	int handle;
+	int steps;
+} b2hStepJob;
+
+static void* b2hStepThread( void* arg )
+{
+	b2hStepJob* job = arg;
+	b2h_step( job->handle, job->steps );
+	return NULL;
+}
+
+B2H_API int b2h_step_many( const int* handles, int count, int steps )
+{
+	pthread_t* threads = malloc( (size_t)count * sizeof( pthread_t ) );
+	b2hStepJob* jobs = malloc( (size_t)count * sizeof( b2hStepJob ) );
+	pthread_attr_t attr;
+	pthread_attr_init( &attr );
+	pthread_attr_setstacksize( &attr, 1 << 20 );
+	int started = 0;
+	for ( int i = 0; i < count; ++i )
+	{
+		jobs[i].handle = handles[i];
+		jobs[i].steps = steps;
+		if ( pthread_create( threads + i, &attr, b2hStepThread, jobs + i ) != 0 )
+		{
+			break;
+		}
+		started += 1;
+	}
+	for ( int i = 0; i < started; ++i )
+	{
+		pthread_join( threads[i], NULL );
+	}
+	pthread_attr_destroy( &attr );
+	free( threads );
+	free( jobs );
+	return started == count ? 0 : 1;
 }
 
 B2H_API uint64_t b2h_hash( int h )

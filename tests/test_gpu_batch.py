@@ -93,3 +93,32 @@ def test_batch_on_clusters(blocks, monkeypatch):
 		assert bins > 1 and per_bin >= blocks
 	for cap, buf, res in zip(caps, bufs, results):
 		_check(cap, buf, res)
+
+
+def test_group_of_live_worlds_steps_as_one_batch(ref_lib, gpu_host_lib):
+	"""World-level batched step (b2GpuSeam_CreateGroup): 96 live worlds, each its own slightly different pile (the offset
+	is derived from the world's index), stepped concurrently -- broad phase, narrow phase and finalize per world on the host,
+	ONE b2GpuSolverStepBatch per round of steps.  Every world is compared with the reference stepping the same world."""
+	count, rounds, per_round = 96, 12, 10
+	refs = [b2.World(ref_lib, "small_pyramid", 1, variant=1 + i) for i in range(count)]
+	gpus = [b2.World(gpu_host_lib, "small_pyramid", 1, variant=1 + i) for i in range(count)]
+	try:
+		assert len({w.world_index() for w in gpus}) == count
+		with b2.WorldGroup(gpu_host_lib, gpus) as group:
+			for r in range(rounds):
+				b2.step_many(ref_lib, refs, per_round)
+				group.step(per_round)
+				want = [w.hash() for w in refs]
+				got = [w.hash() for w in gpus]
+				assert got == want, f"round {r}: worlds {[i for i in range(count) if got[i] != want[i]][:8]} diverged"
+			assert len(set(want)) > count // 2, "the worlds of the batch are supposed to differ"
+			last = gpu_host_lib.b2GpuSeam_GetLastResult(gpus[0].world_index()).contents
+			assert last.kernelLaunches >= 1 and last.gridBarriers == 0
+		# out of the group again: every world back on a solver of its own
+		for w, g in zip(refs[:4], gpus[:4]):
+			w.step(5)
+			g.step(5)
+			assert g.hash() == w.hash()
+	finally:
+		for w in refs + gpus:
+			w.destroy()
