@@ -628,7 +628,40 @@ def measure_batch(args, world_size: int, rank: int, local_rank: int, cpu_baselin
 	}
 	if cpu_baseline:
 		record["cpu_baseline"] = cpu_batch_baseline(total_worlds, 30, min(steps, 10))
+		record["live_worlds"] = live_group_run(host, min(worlds, 1024), 100)
 	return record
+
+
+def live_group_run(host, count: int, steps: int) -> dict:
+	"""World-level batched step (b2GpuSeam_CreateGroup): `count` LIVE worlds -- every world its own slightly different pile,
+	offset derived from its index -- stepped concurrently through b2World_Step for `steps` steps: broad phase, narrow phase
+	and finalize per world on the host, one b2GpuSolverStepBatch per round.  A sample of the worlds is stepped by the
+	reference as well and compared (state hash).  The wall clock covers the WHOLE step of every world."""
+	ref = load_reference()
+	sample = min(count, 32)
+	worlds = [b2.World(host, "small_pyramid", 1, variant=1 + i) for i in range(count)]
+	refs = [b2.World(ref, "small_pyramid", 1, variant=1 + i) for i in range(sample)]
+	try:
+		with b2.WorldGroup(host, worlds) as group:
+			group.step(10)
+			t0 = time.perf_counter()
+			group.step(steps)
+			wall = time.perf_counter() - t0
+			last = host.b2GpuSeam_GetLastResult(worlds[0].world_index()).contents
+			split = {"pack_ms": float(last.uploadMs), "h2d_kernels_d2h_ms": float(last.waitMs), "unpack_ms": float(last.scatterMs),
+					 "kernel_ms": float(last.kernelMs)}
+		b2.step_many(ref, refs, 10 + steps)
+		same = all(worlds[i].hash() == refs[i].hash() for i in range(sample))
+		bodies = worlds[0].counters()["awakeBodyCount"]
+	finally:
+		for w in worlds + refs:
+			w.destroy()
+	return {"worlds": count, "steps": steps, "wall_ms_per_batch_step": wall * 1e3 / steps,
+			"whole_step_body_steps_per_sec": count * bodies * steps / wall, "last_batch_split": split,
+			"parity": f"state hash of the first {sample} worlds equals the reference's after {10 + steps} steps: {same}",
+			"parity_ok": bool(same),
+			"note": "one OS thread per world meets the others at the seam; the wall clock includes every world's broad phase, narrow "
+					"phase and finalize on the host"}
 
 
 def run_batch(args) -> int:

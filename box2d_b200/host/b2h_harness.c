@@ -28,7 +28,7 @@
 #include <string.h>
 
 #define B2H_API __attribute__( ( visibility( "default" ) ) )
-#define B2H_MAX_WORLDS 120
+#define B2H_MAX_WORLDS 8192 /* the library's own limit (B2_MAX_WORLDS) decides how many can really be created */
 
 typedef struct b2hWorld
 {
@@ -668,6 +668,10 @@ B2H_API int b2h_create( const char* scene, int workerCount )
 	}
 
 	w->worldId = b2CreateWorld( &worldDef );
+	if ( b2World_IsValid( w->worldId ) == false )
+	{
+		return -1; /* the library's world array is full (B2_MAX_WORLDS) */
+	}
 	w->inUse = 1;
 	w->timeStep = 1.0f / 60.0f;
 	w->subStepCount = 4;

@@ -28,6 +28,10 @@ CC = os.environ.get("CC", "gcc")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 REF_CFLAGS = ["-O3", "-DNDEBUG", "-std=gnu17", "-ffp-contract=off", "-fPIC", "-w"]
+# The product library can hold a whole batch of live worlds (b2GpuSeam_CreateGroup): B2_MAX_WORLDS is a documented knob of the
+# reference (include/box2d/constants.h:38-40, "must stay < 65535"); it only sizes the static world array of
+# src/physics_world.c and the seam's slot table.  The reference builds under oracle/_ref keep the default (128).
+PRODUCT_DEFINES = ["-DB2_MAX_WORLDS=8192"]
 OWN_CFLAGS = ["-O2", "-DNDEBUG", "-std=gnu17", "-ffp-contract=off", "-fPIC", "-Wall", "-Wextra"]
 
 NVCC_FLAGS = [
@@ -118,17 +122,17 @@ def compile_collide_gpu() -> Path:
 	patcher = ROOT / "tools" / "patch_collide.py"
 	if _stale(gen, [src, patcher]):
 		_run([sys.executable, str(patcher), "--src", str(src), "--out", str(gen)])
-	if _stale(obj, [gen]):
-		_run([CC, *REF_CFLAGS, *ref_includes(), "-c", str(gen), "-o", str(obj)])
+	if _stale(obj, [gen, Path(__file__)]):
+		_run([CC, *REF_CFLAGS, *PRODUCT_DEFINES, *ref_includes(), "-c", str(gen), "-o", str(obj)])
 	return obj
 
 
-def compile_own_c(src: Path, tag: str = "") -> Path:
+def compile_own_c(src: Path, tag: str = "", defines: list[str] | None = None) -> Path:
 	OBJ_DIR.mkdir(parents=True, exist_ok=True)
 	obj = OBJ_DIR / f"own_{src.stem}{tag}.o"
 	headers = list((ROOT / "include").glob("*.h")) + list((PKG_DIR / "host").glob("*.h"))
-	if _stale(obj, [src, *headers]):
-		_run([CC, *OWN_CFLAGS, *own_includes(), *ref_includes(), "-c", str(src), "-o", str(obj)])
+	if _stale(obj, [src, *headers, Path(__file__)]):
+		_run([CC, *OWN_CFLAGS, *(defines or []), *own_includes(), *ref_includes(), "-c", str(src), "-o", str(obj)])
 	return obj
 
 
@@ -183,8 +187,8 @@ def build_host_lib(verbose: bool = False) -> Path:
 	objs = [o for o in compile_reference_objects() if o.name != "src_physics_world.o"] + [compile_collide_gpu()]
 	gpu = compile_solver_variant("gpu")
 	harness = compile_own_c(PKG_DIR / "host" / "b2h_harness.c")
-	seam = compile_own_c(PKG_DIR / "host" / "b2_gpu_seam.c")
-	seam_desc = compile_own_c(PKG_DIR / "host" / "b2_gpu_seam_desc.c")
+	seam = compile_own_c(PKG_DIR / "host" / "b2_gpu_seam.c", "_product", PRODUCT_DEFINES)
+	seam_desc = compile_own_c(PKG_DIR / "host" / "b2_gpu_seam_desc.c", "_product", PRODUCT_DEFINES)
 	target = PKG_DIR / "libbox2d_b200.so"
 	link_shared(target, [*objs, gpu, harness, seam, seam_desc, cuda_lib],
 				[f"-L{PKG_DIR}", "-lb2gpusolver", "-Wl,-rpath,$ORIGIN"])
