@@ -616,6 +616,12 @@ static float b2hStepMutator( b2WorldId worldId, int stepIndex )
 			w->subStepCount = 4;
 			b2World_EnableSleeping( worldId, true );
 			break;
+		case 97:
+			// a step that does not advance time: the narrow phase runs (and may re-evaluate manifolds), the solver does not
+			// (src/physics_world.c:912-950) -- whatever the next solve is told about recycled manifolds must not skip this
+			b2Body_SetTransform( body[43], (b2Pos){ -2.0f, 7.0f }, b2MakeRot( -0.2f ) );
+			b2World_Step( worldId, 0.0f, 4 );
+			break;
 		default:
 			break;
 	}

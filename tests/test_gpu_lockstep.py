@@ -101,6 +101,17 @@ def test_profile_stage_fields_come_from_the_device(gpu_host_lib):
 		assert p["constraints"] <= p["solve"] <= p["step"]
 
 
+@pytest.mark.parametrize("workers", [1, 3, 16])
+def test_lockstep_with_other_worker_counts(ref_lib, gpu_host_lib, workers):
+	"""The seam's team (box2d_b200/host/b2_gpu_seam.c): no helpers at all, an odd number, more workers than there is work for."""
+	for scene, steps in (("mutator", 110), ("falling_hinges", 60), ("rain", 80)):
+		with b2.World(ref_lib, scene, workers) as ref, b2.World(gpu_host_lib, scene, workers) as gpu:
+			for step in range(steps):
+				ref.step()
+				gpu.step()
+				assert gpu.hash() == ref.hash(), f"{scene} with {workers} workers: diverged at step {step + 1}"
+
+
 def test_multi_launch_mode_matches(ref_lib, gpu_host_lib):
 	gpu_host_lib.b2GpuSeam_SetMode(1)
 	try:
