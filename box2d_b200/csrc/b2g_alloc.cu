@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -26,6 +27,11 @@ struct PinnedPool
 	std::mutex mutex;
 	std::vector<void*> freeLists[kMaxShift + 1];
 	std::vector<std::pair<char*, size_t>> slabs;
+	// blocks of kSlabBytes / 4 and more are registrations of their own, sized to whole 2 MiB pages (not to a power of two: a
+	// 33 MB array would page-lock 64 MB) and given back when they are released -- Box2D's arrays grow geometrically, every
+	// outgrown capacity would otherwise stay page-locked for good
+	std::unordered_map<void*, std::pair<size_t, bool>> bigBlocks; // -> { bytes, pinned }
+	bool warned = false;
 	char* cursor = nullptr;
 	size_t remaining = 0;
 	bool pinned = true;
@@ -50,6 +56,12 @@ struct PinnedPool
 				cudaGetLastError();
 				pinned = false; // no driver: plain memory keeps the host library usable for CPU-only tests
 				mem = nullptr;
+				if ( !warned )
+				{
+					warned = true;
+					fprintf( stderr, "box2d_b200: page-locked host memory is not available (%zu bytes asked); the reference's arrays "
+									 "stay in pageable memory from here on (uploads still go through the library's own staging)\n", bytes );
+				}
 			}
 		}
 		if ( mem == nullptr )
@@ -63,21 +75,44 @@ struct PinnedPool
 		return static_cast<char*>( mem );
 	}
 
+	void* allocateBig( size_t size )
+	{
+		const size_t page = size_t( 2 ) << 20;
+		size_t bytes = ( size + page - 1 ) / page * page;
+		void* mem = nullptr;
+		bool locked = false;
+		if ( pinned && cudaHostAlloc( &mem, bytes, cudaHostAllocPortable ) == cudaSuccess )
+		{
+			locked = true;
+		}
+		else
+		{
+			cudaGetLastError();
+			mem = nullptr;
+			if ( posix_memalign( &mem, 4096, bytes ) != 0 )
+			{
+				return nullptr;
+			}
+		}
+		bigBlocks[mem] = { bytes, locked };
+		return mem;
+	}
+
 	void* allocate( size_t size )
 	{
 		int shift = classOf( size );
 		size_t bytes = size_t( 1 ) << shift;
 		std::lock_guard<std::mutex> lock( mutex );
+		if ( size >= kSlabBytes / 4 )
+		{
+			return allocateBig( size );
+		}
 		std::vector<void*>& list = freeLists[shift];
 		if ( !list.empty() )
 		{
 			void* mem = list.back();
 			list.pop_back();
 			return mem;
-		}
-		if ( bytes >= kSlabBytes / 4 )
-		{
-			return newSlab( bytes ); // big blocks get their own registration
 		}
 		if ( remaining < bytes )
 		{
@@ -123,6 +158,20 @@ struct PinnedPool
 		}
 		int shift = classOf( size );
 		std::lock_guard<std::mutex> lock( mutex );
+		auto big = bigBlocks.find( mem );
+		if ( big != bigBlocks.end() )
+		{
+			if ( big->second.second )
+			{
+				cudaFreeHost( mem );
+			}
+			else
+			{
+				free( mem );
+			}
+			bigBlocks.erase( big );
+			return;
+		}
 		freeLists[shift].push_back( mem );
 	}
 };

@@ -53,6 +53,10 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	// bytes of body writes this block receives in a pass over colour c (16 per dynamic body of mine that a contact of
 	// the colour touches), counted by the writers during prepare
 	__shared__ int expectBytes[kColorSlots];
+	// ... counted here first, per owner block and colour, and sent to the owners in one remote atomic per (owner, colour):
+	// thousands of constraints adding 16 at a time to the same few remote counters serialised the prologue (joint_grid:
+	// 39 600 remote atomics on 96 addresses)
+	__shared__ int expectLocal[16][kColorSlots];
 	__shared__ __align__( 8 ) unsigned long long arrivalBar;
 	__shared__ int overflowOrder[kMaxBinOverflow];
 	__shared__ OverflowSchedule overflow; // of the bin's overflow colour (held by the cluster's first block)
@@ -83,7 +87,8 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	// distributed shared memory either way
 	const bool jointsSpilled = P.jointsSpilled != 0;
 	V.joints = jointsSpilled ? P.g.joints : cursor;
-	cursor += jointsSpilled ? 0 : (size_t)capJ * kJointStride;
+	V.jointLite = jointsSpilled ? 0 : P.liteJoints; // (the planner never combines the two)
+	cursor += jointsSpilled ? 0 : (size_t)capJ * jointBytesOf( V.jointLite != 0 );
 	V.cidx = reinterpret_cast<int2*>( cursor );
 	cursor += (size_t)capC * sizeof( int2 );
 	int* jointIndexOf = reinterpret_cast<int*>( cursor );
@@ -101,9 +106,8 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	const unsigned barAddr = (unsigned)__cvta_generic_to_shared( &arrivalBar );
 	VA.asyncBar = barAddr;
 	unsigned barPhase = 0;
-	auto jointRecord = [&]( int k ) -> b2lJointSim* {
-		return jointAt( V, jointsSpilled ? jointIndexOf[k] : k );
-	};
+	// slot of local joint k in the view's joint array (spilled: the global working copy, indexed by the step's joint index)
+	auto jointSlot = [&]( int k ) -> int { return jointsSpilled ? jointIndexOf[k] : k; };
 
 	// this block's run of the bin's bodies
 	const int binBodies = P.binBodyCount[bin];
@@ -168,6 +172,10 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	if ( threadIdx.x < kColorSlots )
 	{
 		expectBytes[threadIdx.x] = 0;
+	}
+	for ( int t = (int)threadIdx.x; t < 16 * kColorSlots; t += (int)blockDim.x )
+	{
+		( &expectLocal[0][0] )[t] = 0;
 	}
 	forEachLocal( bodyCount, [&]( int i ) { loadBody( P, V, bodyList[i], i + 1 ); } );
 	cluster.sync(); // every block of the cluster is running and its bodies are in place
@@ -239,11 +247,11 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 			// tell the owners of the two bodies what to expect from this contact in every pass over its colour
 			if ( ( __float_as_uint( sA.w ) & B2L_FLAG_DYNAMIC ) != 0 )
 			{
-				atomicAdd( cluster.map_shared_rank( expectBytes, clusterOwner( V, (unsigned)localA - 1u ) ) + c, (int)sizeof( float4 ) );
+				atomicAdd( &expectLocal[clusterOwner( V, (unsigned)localA - 1u )][c], (int)sizeof( float4 ) );
 			}
 			if ( ( __float_as_uint( sB.w ) & B2L_FLAG_DYNAMIC ) != 0 )
 			{
-				atomicAdd( cluster.map_shared_rank( expectBytes, clusterOwner( V, (unsigned)localB - 1u ) ) + c, (int)sizeof( float4 ) );
+				atomicAdd( &expectLocal[clusterOwner( V, (unsigned)localB - 1u )][c], (int)sizeof( float4 ) );
 			}
 		}
 		prepareContact( P, V, slot, k, localA, localB, sA, sB, wide, groupBits );
@@ -257,43 +265,54 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		jointIndexOf[k] = c < colorCount ? jointList[listBeginJ[c] + offset] : overflowOrder[offset];
 	} );
 	__syncthreads();
+	if ( V.jointLite != 0 )
+	{
+		forEachLocal( jointCount, [&]( int k ) { loadJointSlot( P, V, jointSlot( k ), jointIndexOf[k] ); } );
+	}
+	else
 	{
 		const int quads = kJointStride / 16;
 		for ( int t = (int)threadIdx.x; t < jointCount * quads; t += (int)blockDim.x )
 		{
 			int k = t / quads, q = t - k * quads;
 			const float4* src = reinterpret_cast<const float4*>( P.rawJoints + (size_t)jointIndexOf[k] * kJointStride );
-			reinterpret_cast<float4*>( jointRecord( k ) )[q] = src[q];
+			reinterpret_cast<float4*>( jointAt( V, jointSlot( k ) ) )[q] = src[q];
 		}
 	}
 	__syncthreads();
 	forEachLocal( jointCount, [&]( int k ) {
-		b2lJointSim* joint = jointRecord( k );
-		int* pair = jointIndexPair( joint );
-		if ( pair != nullptr )
+		int a, b;
+		if ( jointSlotBodies( V, jointSlot( k ), a, b ) )
 		{
-			int a = pair[0], b = pair[1];
 			a = a >= 0 ? P.bodyLocal[a] - 1 : -1;
 			b = b >= 0 ? P.bodyLocal[b] - 1 : -1;
-			pair[0] = a;
-			pair[1] = b;
+			setJointSlotBodies( V, jointSlot( k ), a, b );
 			// tell the owners of the two bodies what to expect from this joint in every pass over its colour: every joint
 			// type writes both bodies back once per pass, except a pogo joint without a spring (src/pogo_joint.c:165,203)
 			int c = colorOfLocal( localStartJ, slotCount, k );
-			bool writes = !( joint->type == b2l_pogoJoint && joint->u.pogo.hertz == 0.0f );
-			if ( c < colorCount && writes )
+			if ( c < colorCount && jointSlotWrites( V, jointSlot( k ) ) )
 			{
 				if ( a >= 0 && ( __float_as_uint( gatherVel( V, a + 1 ).w ) & B2L_FLAG_DYNAMIC ) != 0 )
 				{
-					atomicAdd( cluster.map_shared_rank( expectBytes, clusterOwner( V, (unsigned)a ) ) + c, (int)sizeof( float4 ) );
+					atomicAdd( &expectLocal[clusterOwner( V, (unsigned)a )][c], (int)sizeof( float4 ) );
 				}
 				if ( b >= 0 && ( __float_as_uint( gatherVel( V, b + 1 ).w ) & B2L_FLAG_DYNAMIC ) != 0 )
 				{
-					atomicAdd( cluster.map_shared_rank( expectBytes, clusterOwner( V, (unsigned)b ) ) + c, (int)sizeof( float4 ) );
+					atomicAdd( &expectLocal[clusterOwner( V, (unsigned)b )][c], (int)sizeof( float4 ) );
 				}
 			}
 		}
 	} );
+	__syncthreads();
+	for ( int t = (int)threadIdx.x; t < share * kColorSlots; t += (int)blockDim.x )
+	{
+		int owner = t / kColorSlots, c = t - owner * kColorSlots;
+		int bytes = expectLocal[owner][c];
+		if ( bytes != 0 )
+		{
+			atomicAdd( cluster.map_shared_rank( expectBytes, owner ) + c, bytes );
+		}
+	}
 	const int ovJoints = ovJe - ovJb;
 	if ( hasOverflow && rank == 0 )
 	{
@@ -301,9 +320,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		buildOverflowSchedule( overflow, ovJoints + ( ovCe - ovCb ), [&]( int i, int& a, int& b ) {
 			if ( i < ovJoints )
 			{
-				const int* pair = jointIndexPair( jointRecord( ovJb + i ) );
-				a = pair != nullptr ? pair[0] + 1 : 0; // bin-local, -1 = static
-				b = pair != nullptr ? pair[1] + 1 : 0;
+				jointSlotBodies( V, jointSlot( ovJb + i ), a, b ); // bin-local, -1 = static
+				a += 1;
+				b += 1;
 			}
 			else
 			{
@@ -520,20 +539,16 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		cluster.sync();
 		clk.lap( b2GpuStage_integrateVelocities );
 
-		overflowPass( std::integral_constant<int, OV_WARM>{}, [&]( int k ) { warmStartJoint( P, V, jointRecord( k ) ); },
+		overflowPass( std::integral_constant<int, OV_WARM>{}, [&]( int k ) { warmStartJointSlot( P, V, V, jointSlot( k ) ); },
 					  [&]( const SolveView& view, int k ) { warmStartContactOverflow( view, k ); } );
-		colorPass( [&]( const SolveView& view, int k ) { warmStartJoint( P, view, jointRecord( k ) ); },
+		colorPass( [&]( const SolveView& view, int k ) { warmStartJointSlot( P, view, V, jointSlot( k ) ); },
 				   [&]( const SolveView& view, int k ) { warmStartContact( view, k ); } );
 		clk.lap( b2GpuStage_warmStart );
 
-		overflowPass( std::integral_constant<int, OV_SOLVE>{}, [&]( int k ) { solveJoint( P, V, jointRecord( k ), true ); },
+		overflowPass( std::integral_constant<int, OV_SOLVE>{}, [&]( int k ) { solveJointSlot( P, V, V, jointSlot( k ), true, false ); },
 					  [&]( const SolveView& view, int k ) { solveContactOverflow( P, view, k, true ); } );
 		colorPass(
-			[&]( const SolveView& view, int k ) {
-				b2lJointSim* joint = jointRecord( k );
-				solveJoint( P, view, joint, true );
-				jointEventTest( P, joint );
-			},
+			[&]( const SolveView& view, int k ) { solveJointSlot( P, view, V, jointSlot( k ), true, true ); },
 			[&]( const SolveView& view, int k ) { solveContact( P, view, k, true ); } );
 		clk.lap( b2GpuStage_solveImpulses );
 
@@ -541,9 +556,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 		cluster.sync();
 		clk.lap( b2GpuStage_integratePositions );
 
-		overflowPass( std::integral_constant<int, OV_RELAX>{}, [&]( int k ) { solveJoint( P, V, jointRecord( k ), false ); },
+		overflowPass( std::integral_constant<int, OV_RELAX>{}, [&]( int k ) { solveJointSlot( P, V, V, jointSlot( k ), false, false ); },
 					  [&]( const SolveView& view, int k ) { solveContactOverflow( P, view, k, false ); } );
-		colorPass( [&]( const SolveView& view, int k ) { solveJoint( P, view, jointRecord( k ), false ); },
+		colorPass( [&]( const SolveView& view, int k ) { solveJointSlot( P, view, V, jointSlot( k ), false, false ); },
 				   [&]( const SolveView& view, int k ) { solveContact( P, view, k, false ); } );
 		clk.lap( b2GpuStage_relaxImpulses );
 	}
@@ -573,7 +588,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	// store: everything a block needs is in its own shared memory again
 	forEachLocal( contactCount, [&]( int k ) { storeContact( P, V, k, wireSlot[k], k < ovCb || k >= ovCe ); } );
 	forEachLocal( bodyCount, [&]( int i ) { storeBody( P, V, bodyList[i], i + 1 ); } );
-	forEachLocal( jointCount, [&]( int k ) { storeJointImpulses( P, jointIndexOf[k], jointRecord( k ) ); } );
+	forEachLocal( jointCount, [&]( int k ) { storeJointSlot( P, V, jointIndexOf[k], jointSlot( k ) ); } );
 	clk.lap( b2GpuStage_storeImpulses );
 
 	if ( clk.lead )

@@ -253,6 +253,10 @@ struct b2GpuSolver
 	int maxSharedOptin = 0;
 
 	// resident mode (single worlds): see b2gShadowContact
+	bool liteJointsEnabled = true; // B2GPU_LITE_JOINTS=0: joints always keep their 256-byte records
+	bool liteJointsSeen = false;  // every joint of the previous step was a plain revolute joint (pack pass)
+	bool planLiteJoints = false;  // this step's plan counts on that
+	std::atomic<int> heavyJoint{ 0 }; // pack pass: some joint of this step is not a plain revolute joint
 	bool residentEnabled = true; // B2GPU_RESIDENT=0: every step uploads everything (plain wire)
 	bool resident = false;		 // this step
 	bool cacheValid = false;	 // the shadows describe what the device holds (false: the next resident step sends everything)

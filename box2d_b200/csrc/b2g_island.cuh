@@ -169,7 +169,13 @@ __global__ void __launch_bounds__( kPartitionThreads, 1 ) b2gPartitionKernel( co
 			}
 			int body = jointBodyForBin( P.rawJoints + (size_t)j * kJointStride );
 			{
-				const int* pair = jointIndexPair( reinterpret_cast<b2lJointSim*>( const_cast<uint8_t*>( P.rawJoints + (size_t)j * kJointStride ) ) );
+				b2lJointSim* record = reinterpret_cast<b2lJointSim*>( const_cast<uint8_t*>( P.rawJoints + (size_t)j * kJointStride ) );
+				if ( P.liteJoints != 0 && !isLiteRevolute( record ) )
+				{
+					// the plan counted on plain revolute joints only (b2gPlanIslands): the grid-barrier kernel takes the step
+					*P.binFail = 1;
+				}
+				const int* pair = jointIndexPair( record );
 				if ( pair != nullptr && pair[0] >= 0 && pair[1] >= 0 && P.bodyBin[pair[0]] != P.bodyBin[pair[1]] )
 				{
 					*P.binFail = 1;
@@ -1305,13 +1311,13 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 
 // bytes of dynamic shared memory the island kernels need for the given per-block capacities; jointsResident = false:
 // the joint records themselves stay in global memory (cluster kernel with spilled joints)
-inline size_t islandSharedBytes( int capB, int capC, int capJ, bool jointsResident = true )
+inline size_t islandSharedBytes( int capB, int capC, int capJ, bool jointsResident = true, bool liteJoints = false )
 {
 	size_t bytes = 0;
 	bytes += 2 * (size_t)( capB + 1 ) * sizeof( float4 ); // vel, pos
 	bytes += (size_t)capB * sizeof( float4 );			  // bodyK
 	bytes += (size_t)CF_COUNT * capC * sizeof( float4 );  // contact fields
-	bytes += jointsResident ? (size_t)capJ * kJointStride : 0; // joints
+	bytes += jointsResident ? (size_t)capJ * ( liteJoints ? (size_t)kLiteJointWords * sizeof( float ) : (size_t)kJointStride ) : 0; // joints
 	bytes += (size_t)capC * sizeof( int2 );				  // cidx
 	bytes += (size_t)capJ * sizeof( int );				  // jointIndexOf
 	bytes += (size_t)capB * sizeof( float );			  // angDamp

@@ -1328,6 +1328,180 @@ B2G_DEV void storeJointImpulses( const StepParams& P, int jointIndex, const b2lJ
 	}
 }
 
+// ---- plain revolute joints, compact ------------------------------------------------------------------------------
+// A revolute joint without spring, motor and limit -- a hinge: chains, bridges, rag-doll-less rope, the joint_grid
+// benchmark -- only ever runs the point-to-point part of b2SolveRevoluteJoint (src/revolute_joint.c:443-487) and the warm
+// start (:283-315).  Of its 252-byte b2JointSim those two read 25 floats; when every joint of a step is such a hinge the
+// island / cluster kernels keep just those (27 words with the two constants below), so an island of 20 000 joints fits
+// the shared memory of one 16-block cluster instead of falling back to the grid-barrier kernel.  The arithmetic is the
+// full path's, operation for operation (the disabled sub-constraints contribute nothing but the constants).
+enum LiteRevolute
+{
+	LR_INV_MASS_A = 0,
+	LR_INV_MASS_B = 1,
+	LR_INV_I_A = 2,
+	LR_INV_I_B = 3,
+	LR_BIAS_RATE = 4, // constraintSoftness
+	LR_MASS_SCALE = 5,
+	LR_IMPULSE_SCALE = 6,
+	LR_JOINT_ID = 7, // int, with the world's bit base added
+	LR_IMPULSE_X = 8, // linearImpulse (mutable)
+	LR_IMPULSE_Y = 9,
+	LR_INDEX_A = 10, // int, the view's numbering, -1 = static
+	LR_INDEX_B = 11,
+	LR_FRAME_A = 12, // p.x p.y q.c q.s
+	LR_FRAME_B = 16,
+	LR_DELTA_CENTER = 20,
+	LR_FORCE_THRESHOLD = 22,
+	LR_TORQUE_THRESHOLD = 23,
+	// springImpulse + motorImpulse + lowerImpulse - upperImpulse: whatever the disabled sub-constraints accumulated while
+	// they were enabled still takes part in the warm start (src/revolute_joint.c:296), and nothing changes it during the step
+	LR_AXIAL_IMPULSE = 24,
+	LR_EVENT_ANGULAR = 25, // |motorImpulse + lowerImpulse - upperImpulse| of b2GetJointReaction (src/joint.c:1040-1046)
+	LR_RESERVED = 26
+};
+static_assert( LR_RESERVED + 1 == kLiteJointWords, "LiteRevolute layout" );
+
+B2G_DEV bool isLiteRevolute( const b2lJointSim* joint )
+{
+	return joint->type == b2l_revoluteJoint && joint->u.revolute.enableSpring == 0 && joint->u.revolute.enableMotor == 0 &&
+		   joint->u.revolute.enableLimit == 0;
+}
+
+B2G_DEV float* liteJointAt( const SolveView& V, int index )
+{
+	return reinterpret_cast<float*>( V.joints ) + (size_t)index * kLiteJointWords;
+}
+
+// the full record (global memory) -> the compact one; the body indices stay as they are (the caller renumbers them)
+B2G_DEV void loadLiteRevolute( float* lite, const b2lJointSim* joint )
+{
+	const b2lRevolute* j = &joint->u.revolute;
+	lite[LR_INV_MASS_A] = joint->invMassA;
+	lite[LR_INV_MASS_B] = joint->invMassB;
+	lite[LR_INV_I_A] = joint->invIA;
+	lite[LR_INV_I_B] = joint->invIB;
+	lite[LR_BIAS_RATE] = joint->constraintSoftness.biasRate;
+	lite[LR_MASS_SCALE] = joint->constraintSoftness.massScale;
+	lite[LR_IMPULSE_SCALE] = joint->constraintSoftness.impulseScale;
+	int bitBase = *reinterpret_cast<const int*>( reinterpret_cast<const uint8_t*>( joint ) + B2L_JOINT_SIZE );
+	lite[LR_JOINT_ID] = __int_as_float( joint->jointId + bitBase );
+	lite[LR_IMPULSE_X] = j->linearImpulse.x;
+	lite[LR_IMPULSE_Y] = j->linearImpulse.y;
+	lite[LR_INDEX_A] = __int_as_float( j->indexA );
+	lite[LR_INDEX_B] = __int_as_float( j->indexB );
+	lite[LR_FRAME_A + 0] = j->frameA.p.x;
+	lite[LR_FRAME_A + 1] = j->frameA.p.y;
+	lite[LR_FRAME_A + 2] = j->frameA.q.c;
+	lite[LR_FRAME_A + 3] = j->frameA.q.s;
+	lite[LR_FRAME_B + 0] = j->frameB.p.x;
+	lite[LR_FRAME_B + 1] = j->frameB.p.y;
+	lite[LR_FRAME_B + 2] = j->frameB.q.c;
+	lite[LR_FRAME_B + 3] = j->frameB.q.s;
+	lite[LR_DELTA_CENTER + 0] = j->deltaCenter.x;
+	lite[LR_DELTA_CENTER + 1] = j->deltaCenter.y;
+	lite[LR_FORCE_THRESHOLD] = joint->forceThreshold;
+	lite[LR_TORQUE_THRESHOLD] = joint->torqueThreshold;
+	lite[LR_AXIAL_IMPULSE] = j->springImpulse + j->motorImpulse + j->lowerImpulse - j->upperImpulse;
+	lite[LR_EVENT_ANGULAR] = absf_( j->motorImpulse + j->lowerImpulse - j->upperImpulse );
+	lite[LR_RESERVED] = 0.0f;
+}
+
+// b2WarmStartRevoluteJoint, src/revolute_joint.c:283-315
+B2G_DEV void warmStartRevoluteLite( const SolveView& V, const float* lite )
+{
+	JointBodies jb = gatherJointBodies( V, __float_as_int( lite[LR_INDEX_A] ), __float_as_int( lite[LR_INDEX_B] ) );
+	V2 rA = rotate( deltaRot( jb.pA ), v2( lite[LR_FRAME_A + 0], lite[LR_FRAME_A + 1] ) );
+	V2 rB = rotate( deltaRot( jb.pB ), v2( lite[LR_FRAME_B + 0], lite[LR_FRAME_B + 1] ) );
+	float axialImpulse = lite[LR_AXIAL_IMPULSE];
+	V2 L = v2( lite[LR_IMPULSE_X], lite[LR_IMPULSE_Y] );
+	applyWarmStart( V, jb, lite[LR_INV_MASS_A], lite[LR_INV_I_A], lite[LR_INV_MASS_B], lite[LR_INV_I_B], L, cross( rA, L ) + axialImpulse,
+					cross( rB, L ) + axialImpulse );
+}
+
+// b2SolveRevoluteJoint with spring, motor and limit disabled: the point-to-point constraint, src/revolute_joint.c:443-499
+B2G_DEV void solveRevoluteLite( const SolveView& V, float* lite, bool useBias )
+{
+	float mA = lite[LR_INV_MASS_A], mB = lite[LR_INV_MASS_B];
+	float iA = lite[LR_INV_I_A], iB = lite[LR_INV_I_B];
+	JointBodies jb = gatherJointBodies( V, __float_as_int( lite[LR_INDEX_A] ), __float_as_int( lite[LR_INDEX_B] ) );
+
+	V2 vA = v2( jb.vA.x, jb.vA.y );
+	float wA = jb.vA.z;
+	V2 vB = v2( jb.vB.x, jb.vB.y );
+	float wB = jb.vB.z;
+	Rot dqA = deltaRot( jb.pA ), dqB = deltaRot( jb.pB );
+
+	V2 rA = rotate( dqA, v2( lite[LR_FRAME_A + 0], lite[LR_FRAME_A + 1] ) );
+	V2 rB = rotate( dqB, v2( lite[LR_FRAME_B + 0], lite[LR_FRAME_B + 1] ) );
+
+	V2 Cdot = sub( add( vB, crossSV( wB, rB ) ), add( vA, crossSV( wA, rA ) ) );
+
+	V2 bias = v2( 0.0f, 0.0f );
+	float massScale = 1.0f;
+	float impulseScale = 0.0f;
+	if ( useBias )
+	{
+		V2 dcA = v2( jb.pA.x, jb.pA.y );
+		V2 dcB = v2( jb.pB.x, jb.pB.y );
+		V2 separation = add( add( sub( dcB, dcA ), sub( rB, rA ) ), v2( lite[LR_DELTA_CENTER + 0], lite[LR_DELTA_CENTER + 1] ) );
+		bias = mulSV( lite[LR_BIAS_RATE], separation );
+		massScale = lite[LR_MASS_SCALE];
+		impulseScale = lite[LR_IMPULSE_SCALE];
+	}
+
+	float k11 = mA + mB + rA.y * rA.y * iA + rB.y * rB.y * iB;
+	float k12 = -rA.y * rA.x * iA - rB.y * rB.x * iB;
+	float k21 = k12;
+	float k22 = mA + mB + rA.x * rA.x * iA + rB.x * rB.x * iB;
+	V2 b = solve22( k11, k12, k21, k22, add( Cdot, bias ) );
+
+	V2 impulse;
+	impulse.x = -massScale * b.x - impulseScale * lite[LR_IMPULSE_X];
+	impulse.y = -massScale * b.y - impulseScale * lite[LR_IMPULSE_Y];
+	lite[LR_IMPULSE_X] += impulse.x;
+	lite[LR_IMPULSE_Y] += impulse.y;
+
+	vA = mulSub( vA, mA, impulse );
+	wA -= iA * cross( rA, impulse );
+	vB = mulAdd( vB, mB, impulse );
+	wB += iB * cross( rB, impulse );
+
+	scatterJointBodies( V, jb, vA, wA, vB, wB );
+}
+
+// jointEventTest for a LiteRevolute record
+B2G_DEV void jointEventTestLite( const StepParams& P, const float* lite )
+{
+	float forceThreshold = lite[LR_FORCE_THRESHOLD], torqueThreshold = lite[LR_TORQUE_THRESHOLD];
+	if ( !( forceThreshold < kHugeFloatMax || torqueThreshold < kHugeFloatMax ) )
+	{
+		return;
+	}
+	float linearImpulse = length( v2( lite[LR_IMPULSE_X], lite[LR_IMPULSE_Y] ) );
+	float force = linearImpulse * P.inv_h;
+	float torque = lite[LR_EVENT_ANGULAR] * P.inv_h;
+	if ( force >= forceThreshold || torque >= torqueThreshold )
+	{
+		unsigned id = (unsigned)__float_as_int( lite[LR_JOINT_ID] );
+		atomicOr( P.jointBits + ( id >> 5 ), 1u << ( id & 31u ) );
+	}
+}
+
+// the output record of a LiteRevolute joint: its linearImpulse, and the four accumulated impulses of the disabled
+// sub-constraints exactly as they came in (`pristine` is the record as uploaded)
+B2G_DEV void storeJointImpulsesLite( const StepParams& P, int jointIndex, const float* lite, const b2lJointSim* pristine )
+{
+	float* out = P.outJoints + (size_t)jointIndex * B2L_JOINT_OUT_FLOATS;
+	const b2lRevolute* j = &pristine->u.revolute;
+	out[0] = lite[LR_IMPULSE_X];
+	out[1] = lite[LR_IMPULSE_Y];
+	out[2] = j->springImpulse;
+	out[3] = j->motorImpulse;
+	out[4] = j->lowerImpulse;
+	out[5] = j->upperImpulse;
+}
+
 // ---- dispatch (src/joint.c:1454-1540) ----------------------------------------------------------------------------
 B2G_DEV void warmStartJoint( const StepParams& P, const SolveView& V, b2lJointSim* joint )
 {

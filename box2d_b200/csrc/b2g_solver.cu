@@ -183,6 +183,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		// at ~192 us, the link is the limit, not snoops.)
 		const char* chunkEnv = getenv( "B2GPU_DOWNLOAD_KIB" );
 		s->downloadQuads = chunkEnv != nullptr && atoi( chunkEnv ) >= 16 ? (size_t)atoi( chunkEnv ) * 64 : kDownloadQuads;
+		const char* liteEnv = getenv( "B2GPU_LITE_JOINTS" );
+		s->liteJointsEnabled = liteEnv == nullptr || atoi( liteEnv ) != 0;
 		const char* residentEnv = getenv( "B2GPU_RESIDENT" );
 		s->residentEnabled = residentEnv == nullptr || atoi( residentEnv ) != 0;
 		const char* pdlEnv = getenv( "B2GPU_PDL" );
@@ -387,7 +389,8 @@ static bool b2gPlanBinsOnce( b2GpuSolver* s, int islandCount, int share, int bin
 	const int bodies = P.bodyCount;
 	size_t budget = s->islandSmemBudget;
 	const double bytesPerBody = 52.0, bytesPerContact = b2g::CF_COUNT * 16.0 + 8.0 + 8.0;
-	const double bytesPerJoint = ( spillJoints ? 0.0 : (double)b2g::kJointStride ) + 4.0;
+	const bool lite = s->planLiteJoints && !spillJoints && share > 1; // (the cluster kernel only: b2gIslandKernel keeps the full records)
+	const double bytesPerJoint = ( spillJoints ? 0.0 : lite ? (double)b2g::kLiteJointWords * 4.0 : (double)b2g::kJointStride ) + 4.0;
 	const bool exact = s->islandSizesExact;
 	// bytes of shared memory an island needs: from its real size, or -- no sizes given -- from its bodies and the step's
 	// average constraint density
@@ -489,7 +492,7 @@ static bool b2gPlanBinsOnce( b2GpuSolver* s, int islandCount, int share, int bin
 	double needJ = binJ + ( s->jointTotal > 0 ? slack : 0.0 ) + ( share > 1 ? (double)s->overflowJoints : 0.0 );
 	needC = needC < (double)s->contactTotal ? needC : (double)s->contactTotal;
 	needJ = needJ < (double)s->jointTotal ? needJ : (double)s->jointTotal;
-	size_t fixed = b2g::islandSharedBytes( capB, 0, 0, !spillJoints );
+	size_t fixed = b2g::islandSharedBytes( capB, 0, 0, !spillJoints, lite );
 	const double margin = exact ? 1.02 : 1.1;
 	if ( fixed + (size_t)( needC * margin * bytesPerContact + needJ * margin * bytesPerJoint ) + 4096 > budget )
 	{
@@ -510,14 +513,14 @@ static bool b2gPlanBinsOnce( b2GpuSolver* s, int islandCount, int share, int bin
 	capC = capC > ( ( s->contactTotal + 3 ) & ~3 ) ? ( ( s->contactTotal + 3 ) & ~3 ) : capC;
 	capJ = capJ > ( ( s->jointTotal + 3 ) & ~3 ) ? ( ( s->jointTotal + 3 ) & ~3 ) : capJ;
 	capC = capC < 4 ? 4 : capC;
-	for ( int guard = 0; guard < 64 && b2g::islandSharedBytes( capB, capC, capJ, !spillJoints ) > budget; ++guard )
+	for ( int guard = 0; guard < 64 && b2g::islandSharedBytes( capB, capC, capJ, !spillJoints, lite ) > budget; ++guard )
 	{
 		capC = ( capC - capC / 32 - 4 ) & ~3; // rounding slack: shave ~3 % until it fits
 		capJ = capJ > 0 ? ( capJ - capJ / 32 - 4 ) & ~3 : 0;
 		capC = capC < 4 ? 4 : capC;
 		capJ = capJ < 0 ? 0 : capJ;
 	}
-	if ( b2g::islandSharedBytes( capB, capC, capJ, !spillJoints ) > budget || capC < needC || capJ < needJ )
+	if ( b2g::islandSharedBytes( capB, capC, capJ, !spillJoints, lite ) > budget || capC < needC || capJ < needJ )
 	{
 		return false;
 	}
@@ -568,6 +571,11 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	b2g::StepParams& P = s->params;
 	s->islandMode = false;
 	P.binCount = 0;
+	P.liteJoints = 0;
+	// Plain revolute joints are kept as 27 words instead of 64 by the island / cluster kernels when EVERY joint of the step is
+	// one (b2g_joint.cuh).  Whether that holds is only known once the pack pass has looked at the joints, so the plan goes by
+	// what the previous step saw; the scatter / partition kernel checks, and a wrong guess costs a rerun on the grid kernel.
+	s->planLiteJoints = s->liteJointsEnabled && s->liteJointsSeen && s->jointTotal > 0;
 	int bodies = P.bodyCount;
 	if ( s->islandsEnabled == 0 || s->mode != 0 || bodies == 0 )
 	{
@@ -744,7 +752,9 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	P.jointBinRank = s->jointBinRank.ptr;
 	P.binJointList = s->binJointList.ptr;
 	P.binJointBodies = s->binJointBodies.ptr;
-	s->islandSmemBytes = b2g::islandSharedBytes( capB, capC, capJ, !plan.spillJoints );
+	const bool liteJoints = s->planLiteJoints && !plan.spillJoints && plan.share > 1;
+	s->islandSmemBytes = b2g::islandSharedBytes( capB, capC, capJ, !plan.spillJoints, liteJoints );
+	P.liteJoints = liteJoints ? 1 : 0;
 	s->islandMode = true;
 	return 0;
 }
@@ -801,6 +811,7 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	s->uploaded = false;
 	s->ran = false;
 	s->results = results;
+	s->heavyJoint.store( 0, std::memory_order_relaxed );
 	const b2GpuStepDesc* d = descs;
 
 	int maxColors = 0;
@@ -1739,6 +1750,7 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 	s->tracePump.clear();
 	s->traceArrivals.clear();
 	s->begun = false;
+	s->liteJointsSeen = s->jointTotal > 0 && s->heavyJoint.load( std::memory_order_relaxed ) == 0;
 	if ( s->resident && s->ran && s->workFailed.load() == 0 )
 	{
 		// this step's outputs are the next step's resident inputs

@@ -239,6 +239,121 @@ B2G_DEV b2lJointSim* jointAt( const SolveView& V, int index )
 	return reinterpret_cast<b2lJointSim*>( V.joints + (size_t)index * kJointStride );
 }
 
+// ---- a joint of a view by slot, whatever the view keeps: the full 256-byte record or a LiteRevolute ------------------------
+B2G_DEV size_t jointBytesOf( bool lite )
+{
+	return lite ? (size_t)kLiteJointWords * sizeof( float ) : (size_t)kJointStride;
+}
+
+// slot k of the view <- joint j of the step (P.rawJoints); the body indices are still the step's
+B2G_DEV void loadJointSlot( const StepParams& P, const SolveView& V, int k, int j )
+{
+	const b2lJointSim* record = reinterpret_cast<const b2lJointSim*>( P.rawJoints + (size_t)j * kJointStride );
+	if ( V.jointLite != 0 )
+	{
+		loadLiteRevolute( liteJointAt( V, k ), record );
+		return;
+	}
+	const float4* src = reinterpret_cast<const float4*>( record );
+	float4* dst = reinterpret_cast<float4*>( V.joints + (size_t)k * kJointStride );
+#pragma unroll
+	for ( int q = 0; q < kJointStride / 16; ++q )
+	{
+		dst[q] = src[q];
+	}
+}
+
+// the two bodies of the joint in slot k (-1 = static); false for a filter joint (no solver data)
+B2G_DEV bool jointSlotBodies( const SolveView& V, int k, int& a, int& b )
+{
+	if ( V.jointLite != 0 )
+	{
+		const float* lite = liteJointAt( V, k );
+		a = __float_as_int( lite[LR_INDEX_A] );
+		b = __float_as_int( lite[LR_INDEX_B] );
+		return true;
+	}
+	const int* pair = jointIndexPair( jointAt( V, k ) );
+	a = pair != nullptr ? pair[0] : -1;
+	b = pair != nullptr ? pair[1] : -1;
+	return pair != nullptr;
+}
+
+B2G_DEV void setJointSlotBodies( const SolveView& V, int k, int a, int b )
+{
+	if ( V.jointLite != 0 )
+	{
+		float* lite = liteJointAt( V, k );
+		lite[LR_INDEX_A] = __int_as_float( a );
+		lite[LR_INDEX_B] = __int_as_float( b );
+		return;
+	}
+	int* pair = jointIndexPair( jointAt( V, k ) );
+	if ( pair != nullptr )
+	{
+		pair[0] = a;
+		pair[1] = b;
+	}
+}
+
+// false for the one joint that writes no body in a pass: a pogo joint without a spring (src/pogo_joint.c:165,203)
+B2G_DEV bool jointSlotWrites( const SolveView& V, int k )
+{
+	if ( V.jointLite != 0 )
+	{
+		return true;
+	}
+	const b2lJointSim* joint = jointAt( V, k );
+	return !( joint->type == b2l_pogoJoint && joint->u.pogo.hertz == 0.0f );
+}
+
+B2G_DEV void warmStartJointSlot( const StepParams& P, const SolveView& V, const SolveView& geometry, int k )
+{
+	// (`geometry` names the records, `V` the body arrays the stage writes through: the cluster kernel's counted stores)
+	if ( geometry.jointLite != 0 )
+	{
+		warmStartRevoluteLite( V, liteJointAt( geometry, k ) );
+	}
+	else
+	{
+		warmStartJoint( P, V, jointAt( geometry, k ) );
+	}
+}
+
+B2G_DEV void solveJointSlot( const StepParams& P, const SolveView& V, const SolveView& geometry, int k, bool useBias, bool events )
+{
+	if ( geometry.jointLite != 0 )
+	{
+		float* lite = liteJointAt( geometry, k );
+		solveRevoluteLite( V, lite, useBias );
+		if ( events )
+		{
+			jointEventTestLite( P, lite );
+		}
+	}
+	else
+	{
+		b2lJointSim* joint = jointAt( geometry, k );
+		solveJoint( P, V, joint, useBias );
+		if ( events )
+		{
+			jointEventTest( P, joint );
+		}
+	}
+}
+
+B2G_DEV void storeJointSlot( const StepParams& P, const SolveView& V, int jointIndex, int k )
+{
+	if ( V.jointLite != 0 )
+	{
+		storeJointImpulsesLite( P, jointIndex, liteJointAt( V, k ), reinterpret_cast<const b2lJointSim*>( P.rawJoints + (size_t)jointIndex * kJointStride ) );
+	}
+	else
+	{
+		storeJointImpulses( P, jointIndex, jointAt( V, k ) );
+	}
+}
+
 // ---- joints of the grid-barrier kernel, cached by the block that solves them --------------------------------------------
 // forEachInColor gives joint t of a colour to chunk t / 32, i.e. to block (t / 32) % gridDim -- the same thread in every
 // stage of the step.  The persistent kernel therefore keeps the 256-byte records of ITS joints in shared memory for the

@@ -96,6 +96,10 @@ struct ColorRange
 
 constexpr int kMaxColors = 23;
 constexpr int kJointStride = 256; // b2JointSim (252 B) padded to 16-byte multiples on the wire and in the working copy
+// A plain revolute joint (no spring, motor or limit) as the island / cluster kernels keep it in shared memory when EVERY
+// joint of the step is one (b2g_joint.cuh, LiteRevolute): 27 floats instead of 64.  An odd number of words, so that a
+// warp's accesses to one field of 32 consecutive records hit 32 different banks.
+constexpr int kLiteJointWords = 27;
 constexpr int kStageTimerCount = 8;
 
 // Per-contact output record copied back to the host and scattered into b2Manifold
@@ -114,6 +118,7 @@ struct SolveView
 	int2* cidx;	   // indexA+1, indexB+1 (0 = static dummy) in the view's own body numbering
 	int* cmeta;	   // kMeta* bits
 	uint8_t* joints; // b2JointSim working copy (indexA/indexB in the view's numbering, 0-based, -1 = static)
+	int jointLite;	 // != 0: `joints` holds LiteRevolute records of kLiteJointWords floats instead (island / cluster kernels)
 	int* anyRestitution; // set by prepare when a contact of the view has restitution != 0
 	// Cluster mode (island kernel on a thread-block cluster): the body arrays are distributed over the blocks' shared
 	// memory in runs of clusterRun bodies; body index i (1-based, 0 = this block's own static dummy) lives in block
@@ -198,6 +203,7 @@ struct StepParams
 	int capBodies;	   // per-BLOCK capacities the shared memory carve-up was sized for (a bin holds clusterSize times that)
 	int capContacts;
 	int capJoints;
+	int liteJoints;	   // island / cluster kernels: every joint of the step is a plain revolute joint (checked by the scatter / partition kernel: binFail otherwise)
 	int jointsSpilled; // cluster kernel: the joint records stay in the global working copy instead of shared memory
 	int ownerLists;	   // one bin shared by a cluster: constraint lists per BLOCK, keyed by the owner of the first body
 	int listCount;	   // number of constraint lists: binCount, or clusterSize with owner lists

@@ -377,6 +377,7 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		float4* wireJoints = base + s->inJoints;
 		const bool resident = s->resident;
 		b2gStreamChunk full = { &s->fullJointCursor, s->fullJointCapacity, 0, 0, &s->streamOverflow };
+		bool heavy = false;
 		int first = bodyCount + s->contactTotal;
 		int flat = ( begin > first ? begin : first ) - first;
 		int flatEnd = end - first;
@@ -405,6 +406,12 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 					}
 				}
 				memcpy( padded + B2L_JOINT_SIZE, &world.jointBitBase, 4 );
+				{
+					// is every joint of the step a plain revolute joint?  (the next step's plan goes by it, b2gPlanIslands)
+					const b2lJointSim* joint = reinterpret_cast<const b2lJointSim*>( padded );
+					heavy = heavy || !( joint->type == b2l_revoluteJoint && joint->u.revolute.enableSpring == 0 &&
+										joint->u.revolute.enableMotor == 0 && joint->u.revolute.enableLimit == 0 );
+				}
 				if ( !resident )
 				{
 					b2gStreamCopy( wireJoints + (size_t)( seg.jointStart + i ) * ( b2g::kJointStride / 16 ), padded, b2g::kJointStride / 16 );
@@ -439,6 +446,10 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		if ( full.taken > 0 )
 		{
 			s->fullJointCount.fetch_add( full.taken, std::memory_order_relaxed );
+		}
+		if ( heavy )
+		{
+			s->heavyJoint.store( 1, std::memory_order_relaxed );
 		}
 	}
 	_mm_sfence();

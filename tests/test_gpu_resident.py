@@ -325,3 +325,46 @@ def test_the_seam_vouches_for_recycled_manifolds(gpu_host_lib):
 		assert gpu_host_lib.b2GpuSeam_GetResidentStats(gpu.world_index(), ctypes.byref(full), ctypes.byref(dirty), ctypes.byref(vouched)) == 1
 		contacts = sum(gpu.counters()["colorCounts"])
 		assert (full.value, dirty.value, vouched.value) == (0, 0, contacts), (full.value, dirty.value, vouched.value, contacts)
+
+
+def test_plain_revolute_joints_take_the_compact_records(oracle, capture_files):
+	"""When every joint of a step is a plain revolute joint (no spring, motor, limit) the cluster kernel keeps 27
+	words per joint instead of 64 (b2g_joint.cuh, LiteRevolute).  The plan goes by what the previous step's pack pass saw and
+	the device checks: same bits on the first step (full records), on the following ones (compact), on clusters, and when a
+	joint turns its motor on again (wrong guess: the step is rerun on the grid-barrier kernel)."""
+	path = [f for f in capture_files if "falling_hinges_120" in f.name][0]
+	for force_cluster in (None, "4"):
+		import os
+		if force_cluster:
+			os.environ["B2GPU_CLUSTER_FORCE"] = force_cluster
+		try:
+			cap = b2.Capture(path)
+			assert cap.joint_count > 0
+			for arr in cap.joints_in:
+				if arr.size:
+					j = arr.reshape(-1, b2.JOINT_SIZE)
+					assert (j[:, 12:16].view(np.int32) == 6).all(), "expected revolute joints only"
+					j[:, 208:211] = 0  # enableSpring, enableMotor, enableLimit (include/b2gpu_layout.h, b2lRevolute)
+			with b2.GpuSolver() as solver:
+				for step in range(4):
+					got = _step_both(oracle, solver, cap, f"plain revolutes, step {step}, cluster {force_cluster}")
+					d, r, _ = cap.make_call()
+					_finalize(cap, got)
+				# one joint turns its motor on: the plan still counts on compact records, the device notices
+				for arr in cap.joints_in:
+					if arr.size:
+						arr.reshape(-1, b2.JOINT_SIZE)[0, 209] = 1
+						break
+				d0, r0, want = cap.make_call()
+				assert oracle.b2OracleSolverStep(ctypes.byref(d0), ctypes.byref(r0)) == 0
+				d, r, got = cap.make_call()
+				solver.step(d, r)
+				if force_cluster:  # (compact records are a cluster-kernel matter: one block keeps the full ones)
+					assert r.gridBarriers > 0, "a joint that is not a plain revolute must send the step to the grid-barrier kernel"
+				assert np.array_equal(got["states"], want["states"])
+				for a, b in zip(got["joints"], want["joints"]):
+					assert np.array_equal(a, b)
+				_finalize(cap, got)
+				got = _step_both(oracle, solver, cap, "after the wrong guess")  # full records again, island kernels
+		finally:
+			os.environ.pop("B2GPU_CLUSTER_FORCE", None)
