@@ -187,6 +187,17 @@ struct b2gShadowImpulses
 	uint32_t values[5];
 };
 
+// ---- deferred contact impulses (b2GpuSolverSetDeferredImpulses) ----------------------------------------------------------
+// Where the record of a contact is among the outputs the host has not written into the manifolds yet: its wire slot in the
+// pending step (kDeferWide: a contact of a graph colour -- both points are stored, like b2StoreImpulsesTask does), -1 once the
+// record has been written into the manifold.  An entry counts when its stamp is the pending step's.
+struct b2gDeferEntry
+{
+	int slot;
+	uint32_t stamp;
+};
+constexpr int kDeferWide = 1 << 30;
+
 constexpr int kHomeColors = B2GPU_GRAPH_COLOR_COUNT;
 
 constexpr int kStreamChunk = 16; // records a pack block reserves at a time in the full / dirty-body streams
@@ -299,6 +310,25 @@ struct b2GpuSolver
 	// (tools/microbench/h2d_bench.cu, profiles/).
 	PinnedBuffer<float4> hWire;
 	PinnedBuffer<float4> hOut;
+
+	// Deferred contact impulses (resident mode, the phased entry points; see include/b2_gpu_solver.h).  The step's impulse
+	// records come back LAST and behind the caller's back: EndStep returns once the body states and the joints' outputs are
+	// unpacked, the records stay in the page-locked output arena (two arenas, swapped every step) and are written into a
+	// manifold only when somebody is going to read it (b2GpuSolverMaterializeContacts: the narrow phase before it
+	// re-evaluates a manifold, the pack pass before it reads a contact it has no word on, the caller's flush).
+	bool deferEnabled = false;
+	bool defer = false; // this step
+	PinnedBuffer<float4> hOutOther; // the previous step's output arena
+	bool deferPending = false;		// hOutOther holds records that some manifolds have not received
+	uint32_t deferStamp = 0;		// of the pending step's entries in deferMap
+	uint32_t deferNewStamp = 1;		// of the entries this step's pack pass writes
+	std::vector<b2gDeferEntry> deferMap; // by contact id
+	const float* pendingRecords = nullptr; // the pending step's impulse records, by wire slot
+	const float* prevRecords = nullptr;	   // the previous resident step's (what the device warm-starts clean contacts from)
+	cudaEvent_t evRecords = nullptr;	   // behind the last chunk of the download
+	std::atomic<int> recordsSynced{ 1 };
+	int deferWaitChunks = 0; // chunks of the download the unpack pass waits for (the rest holds the impulse records)
+	std::atomic<int> materialized{ 0 }; // statistics: records written into manifolds since the last step began
 	ControlBlock* hControl = nullptr;
 
 	// arena layouts, in float4 units
@@ -399,6 +429,7 @@ constexpr size_t kDownloadQuads = 32 * 1024; // 512 KiB: the unpack pass runs th
 int b2gSendArena( b2GpuSolver* s, size_t uptoQuads );
 void b2gFlushLines( const void* ptr, size_t bytes );
 // b2g_solver.cu
+int b2gDeferSync( b2GpuSolver* s );
 int b2gEnqueueDownload( b2GpuSolver* s );
 int b2gRerunIfIslandsFailed( b2GpuSolver* s, bool download );
 

@@ -235,6 +235,7 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 	ok = ok && cudaEventCreate( &s->evStop ) == cudaSuccess;
 	ok = ok && cudaEventCreate( &s->evUpload ) == cudaSuccess;
 	ok = ok && cudaEventCreateWithFlags( &s->evControl, cudaEventDisableTiming ) == cudaSuccess;
+	ok = ok && cudaEventCreateWithFlags( &s->evRecords, cudaEventDisableTiming ) == cudaSuccess;
 	ok = ok && cudaMalloc( &s->control, sizeof( ControlBlock ) ) == cudaSuccess;
 	ok = ok && cudaHostAlloc( &s->hControl, sizeof( ControlBlock ), cudaHostAllocDefault ) == cudaSuccess;
 	if ( !ok )
@@ -269,6 +270,7 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	s->cmeta.release();
 	s->hWire.release();
 	s->hOut.release();
+	s->hOutOther.release();
 	s->table.release();
 	s->residentStates[0].release();
 	s->residentStates[1].release();
@@ -301,7 +303,7 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	{
 		cudaFreeHost( s->hControl );
 	}
-	for ( cudaEvent_t ev : { s->evStart, s->evStop, s->evUpload, s->evControl } )
+	for ( cudaEvent_t ev : { s->evStart, s->evStop, s->evUpload, s->evControl, s->evRecords } )
 	{
 		if ( ev != nullptr )
 		{
@@ -1026,13 +1028,25 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	s->massMismatch.store( s->checkMasses ? 0 : 1, std::memory_order_relaxed );
 	s->uploadStarted = false;
 	s->arenaSent = false;
-	// output arena: [states 2/body][impulse records][joint impulse records 3/joint][joint event bits]
+	// output arena: [states 2/body][impulse records][joint impulse records 3/joint][joint event bits]; with deferred
+	// impulses the records come last: [states][joints][bits][impulse records], and the step ends without them
 	size_t impulseQuads = ( (size_t)slot * b2g::kImpulseFloats + 3 ) / 4;
+	s->defer = s->deferEnabled && s->resident;
 	s->outStates = 0;
-	s->outImpulses = s->outStates + 2 * nb;
-	s->outJoints = s->outImpulses + impulseQuads;
-	s->outBits = s->outJoints + (size_t)( B2L_JOINT_OUT_FLOATS / 4 ) * joint;
-	s->outTotal = s->outBits + ( (size_t)P.jointWords + 3 ) / 4;
+	if ( s->defer )
+	{
+		s->outJoints = s->outStates + 2 * nb;
+		s->outBits = s->outJoints + (size_t)( B2L_JOINT_OUT_FLOATS / 4 ) * joint;
+		s->outImpulses = s->outBits + ( (size_t)P.jointWords + 3 ) / 4;
+		s->outTotal = s->outImpulses + impulseQuads;
+	}
+	else
+	{
+		s->outImpulses = s->outStates + 2 * nb;
+		s->outJoints = s->outImpulses + impulseQuads;
+		s->outBits = s->outJoints + (size_t)( B2L_JOINT_OUT_FLOATS / 4 ) * joint;
+		s->outTotal = s->outBits + ( (size_t)P.jointWords + 3 ) / 4;
+	}
 
 	B2G_CUDA( s->wireAll.reserve( s->inTotal + 1 ) );
 	B2G_CUDA( s->hWire.reserve( s->inTotal + 1 ) );
@@ -1202,6 +1216,37 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	// the shadows are trusted by this step's pack pass only; they count again once the step has ended (b2gEnd)
 	s->cacheUsable = s->resident && s->cacheValid;
 	s->cacheValid = false;
+	if ( s->defer )
+	{
+		size_t ids = d->contactIdCapacity > 0 ? (size_t)d->contactIdCapacity : 0;
+		if ( s->deferMap.size() < ids + 1 )
+		{
+			s->deferMap.resize( ids + ids / 2 + 64, b2gDeferEntry{ -1, 0 } );
+		}
+		s->deferNewStamp += 1;
+		if ( s->deferNewStamp == 0 )
+		{
+			// wrapped: no entry of the past may look current (nothing can be pending with stamp 0)
+			if ( s->deferPending )
+			{
+				return b2gFailMsg( "b2GpuSolverBeginStep: deferred impulses pending across a stamp wrap-around" );
+			}
+			s->deferMap.assign( s->deferMap.size(), b2gDeferEntry{ -1, 0 } );
+			s->deferNewStamp = 1;
+		}
+		// the pack pass reads the previous step's records (a contact it has no word on: are its impulses still the device's?)
+		if ( b2gDeferSync( s ) != 0 )
+		{
+			return 1;
+		}
+		s->prevRecords = s->cacheUsable && s->hOutOther.ptr != nullptr ? reinterpret_cast<const float*>( s->hOutOther.ptr + s->prevOutImpulses ) : nullptr;
+		s->materialized.store( 0, std::memory_order_relaxed );
+	}
+	else if ( s->deferPending )
+	{
+		return b2gFailMsg( "b2GpuSolverBeginStep: the previous step's impulses are still deferred (b2GpuSolverMaterializeContacts, "
+						   "b2GpuSolverDeferredDone) and this step cannot take them over" );
+	}
 
 	P.rawStates = reinterpret_cast<const uint8_t*>( s->resident ? s->residentStates[0].ptr : s->wireAll.ptr + s->inStates );
 	P.wireBody = s->resident ? s->residentBody.ptr : s->wireAll.ptr + s->inBody;
@@ -1596,21 +1641,37 @@ int b2gEnqueueDownload( b2GpuSolver* s )
 	s->controlSeen = false;
 	size_t total = s->outTotal;
 	const size_t chunkQuads = s->downloadQuads;
-	int chunks = (int)( ( total + chunkQuads - 1 ) / chunkQuads );
-	while ( (int)s->chunkEvents.size() < chunks )
+	s->chunkEnd.clear();
+	// deferred impulses: the arena's tail holds the records nobody waits for (one piece, one event)
+	const size_t awaited = s->defer ? s->outImpulses : total;
+	s->deferWaitChunks = 0;
+	int made = 0;
+	for ( size_t begin = 0; begin < total; )
 	{
-		cudaEvent_t ev = nullptr;
-		B2G_CUDA( cudaEventCreateWithFlags( &ev, cudaEventDisableTiming ) );
-		s->chunkEvents.push_back( ev );
-	}
-	s->chunkEnd.resize( (size_t)chunks );
-	for ( int i = 0; i < chunks; ++i )
-	{
-		size_t begin = (size_t)i * chunkQuads;
 		size_t end = begin + chunkQuads < total ? begin + chunkQuads : total;
+		end = begin < awaited && end > awaited ? awaited : end;
+		end = begin >= awaited ? total : end;
 		B2G_CUDA( cudaMemcpyAsync( s->hOut.ptr + begin, s->outAll.ptr + begin, ( end - begin ) * sizeof( float4 ), cudaMemcpyDeviceToHost, st ) );
-		B2G_CUDA( cudaEventRecord( s->chunkEvents[(size_t)i], st ) );
-		s->chunkEnd[(size_t)i] = end;
+		if ( (int)s->chunkEvents.size() <= made )
+		{
+			cudaEvent_t ev = nullptr;
+			B2G_CUDA( cudaEventCreateWithFlags( &ev, cudaEventDisableTiming ) );
+			s->chunkEvents.push_back( ev );
+		}
+		B2G_CUDA( cudaEventRecord( s->chunkEvents[(size_t)made], st ) );
+		s->chunkEnd.push_back( end );
+		made += 1;
+		if ( end == awaited )
+		{
+			s->deferWaitChunks = made;
+		}
+		begin = end;
+	}
+	const int chunks = made;
+	s->deferWaitChunks = s->defer && awaited < total ? s->deferWaitChunks : chunks;
+	if ( s->defer )
+	{
+		B2G_CUDA( cudaEventRecord( s->evRecords, st ) );
 	}
 	s->chunkCount = chunks;
 	s->chunkNext = 0;
@@ -1632,8 +1693,66 @@ extern "C" int b2GpuSolverSubmit( b2GpuSolver* s )
 	{
 		return 1;
 	}
-	b2gResetWork( s, b2GpuSolverGetUnpackItemCount( s ), b2gBlocksFor( s, b2GpuSolverGetUnpackItemCount( s ) ) );
+	// deferred impulses: the unpack pass has the bodies and the joints to do (b2GpuSolverUnpackWork skips the contacts' items)
+	const int unpackItems = b2GpuSolverGetUnpackItemCount( s ) - ( s->defer ? s->contactTotal : 0 );
+	b2gResetWork( s, unpackItems, b2gBlocksFor( s, unpackItems ) );
 	return 0;
+}
+
+// ---- deferred contact impulses -------------------------------------------------------------------------------------------
+// the pending records have arrived (any thread; the first one waits for the tail of the previous step's download)
+int b2gDeferSync( b2GpuSolver* s )
+{
+	if ( s->recordsSynced.load( std::memory_order_acquire ) == 0 )
+	{
+		cudaError_t err = cudaEventSynchronize( s->evRecords );
+		if ( err != cudaSuccess )
+		{
+			return b2gFail( "download of the deferred impulse records", err );
+		}
+		s->recordsSynced.store( 1, std::memory_order_release );
+	}
+	return 0;
+}
+
+extern "C" int b2GpuSolverSetDeferredImpulses( b2GpuSolver* s, int enabled )
+{
+	if ( s == nullptr || s->begun )
+	{
+		return b2gFailMsg( "b2GpuSolverSetDeferredImpulses: no solver, or a step is in flight" );
+	}
+	if ( s->deferPending )
+	{
+		return b2gFailMsg( "b2GpuSolverSetDeferredImpulses: impulses are pending" );
+	}
+	if ( ( enabled != 0 ) != s->deferEnabled )
+	{
+		s->deferEnabled = enabled != 0;
+		s->cacheValid = false; // the two modes keep the previous step's impulses in different places
+	}
+	return 0;
+}
+
+extern "C" int b2GpuSolverDeferredPending( const b2GpuSolver* s )
+{
+	return s != nullptr && s->deferPending ? 1 : 0;
+}
+
+extern "C" int b2GpuSolverDeferredSync( b2GpuSolver* s )
+{
+	if ( s == nullptr )
+	{
+		return b2gFailMsg( "b2GpuSolverDeferredSync: null solver" );
+	}
+	return s->deferPending ? b2gDeferSync( s ) : 0;
+}
+
+extern "C" void b2GpuSolverDeferredDone( b2GpuSolver* s )
+{
+	if ( s != nullptr )
+	{
+		s->deferPending = false;
+	}
 }
 
 extern "C" int b2GpuSolverWait( b2GpuSolver* s )
@@ -1705,6 +1824,11 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 					r->jointEventBits[i] |= word;
 				}
 			}
+			if ( s->defer && s->hControl->hasHitEvents != 0 )
+			{
+				// nobody has looked at the records: the caller materializes them (that sets the bits) before it reads the events
+				r->hasHitEvents = 1;
+			}
 			r->kernelMs = s->lastKernelMs;
 			r->kernelLaunches = s->lastLaunches;
 			r->h2dBytes = s->lastH2D;
@@ -1754,6 +1878,15 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 	if ( s->resident && s->ran && s->workFailed.load() == 0 )
 	{
 		// this step's outputs are the next step's resident inputs
+		if ( s->defer )
+		{
+			// ... and its impulse records wait in the arena that was just filled (the tail may still be on its way)
+			std::swap( s->hOut, s->hOutOther );
+			s->pendingRecords = reinterpret_cast<const float*>( s->hOutOther.ptr + s->outImpulses );
+			s->deferPending = s->contactTotal > 0;
+			s->deferStamp = s->deferNewStamp;
+			s->recordsSynced.store( 0, std::memory_order_release );
+		}
 		std::swap( s->outAll, s->outOther );
 		std::swap( s->residentStates[0], s->residentStates[1] );
 		s->prevOutImpulses = s->outImpulses;

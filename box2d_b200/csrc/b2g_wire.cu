@@ -109,6 +109,78 @@ static inline int b2gStreamTake( b2gStreamChunk& chunk )
 	return chunk.next++;
 }
 
+void b2gFlushLines( const void* ptr, size_t bytes );
+
+// Deferred impulses: write the pending record `slot` into the manifold of `sim` -- what b2StoreImpulsesTask
+// (src/contact_solver.c:2293-2320: both points of a coloured contact) and b2StoreImpulses_Overflow (:526-542) would have
+// written at the end of the pending step.  Returns the record's hit-event flag.
+static inline bool b2gMaterializeRecord( const b2GpuSolver* s, uint8_t* sim, int slotAndWide )
+{
+	const float* rec = s->pendingRecords + (size_t)( slotAndWide & ~kDeferWide ) * b2g::kImpulseFloats;
+	uint8_t* manifold = sim + B2L_CONTACT_MANIFOLD;
+	int pointCount = ( slotAndWide & kDeferWide ) != 0 ? 2 : *reinterpret_cast<const int*>( manifold + B2L_MANIFOLD_POINT_COUNT );
+	memcpy( manifold + B2L_MANIFOLD_ROLLING_IMPULSE, rec + 0, 4 );
+	for ( int j = 0; j < pointCount; ++j )
+	{
+		// normalImpulse, tangentImpulse, totalNormalImpulse, normalVelocity are contiguous (collision.h:549-561)
+		memcpy( manifold + B2L_MANIFOLD_POINTS + j * B2L_MP_SIZE + B2L_MP_NORMAL_IMPULSE, rec + 1 + 4 * j, 16 );
+	}
+	bool hit = rec[9] != 0.0f;
+	b2gFlushLines( rec, b2g::kImpulseFloats * sizeof( float ) ); // (the arena is a DMA target again two steps from now)
+	return hit;
+}
+
+// the pending entry of contact `id`, or nullptr (none, consumed, or of an older step)
+static inline b2gDeferEntry* b2gPendingEntry( b2GpuSolver* s, int id )
+{
+	if ( !s->deferPending || id < 0 || (size_t)id >= s->deferMap.size() )
+	{
+		return nullptr;
+	}
+	b2gDeferEntry* entry = s->deferMap.data() + id;
+	return entry->stamp == s->deferStamp && entry->slot >= 0 ? entry : nullptr;
+}
+
+extern "C" int b2GpuSolverMaterializeContacts( b2GpuSolver* s, void* contactSims, int count, b2GpuStepResult* result )
+{
+	if ( s == nullptr || !s->deferPending || count <= 0 )
+	{
+		return 0;
+	}
+	if ( b2gDeferSync( s ) != 0 )
+	{
+		return -1;
+	}
+	uint8_t* sims = static_cast<uint8_t*>( contactSims );
+	int done = 0;
+	for ( int i = 0; i < count; ++i )
+	{
+		uint8_t* sim = sims + (size_t)i * B2L_CONTACT_SIZE;
+		const int id = *reinterpret_cast<const int*>( sim + B2L_CONTACT_ID );
+		b2gDeferEntry* entry = b2gPendingEntry( s, id );
+		if ( entry == nullptr )
+		{
+			continue;
+		}
+		bool hit = b2gMaterializeRecord( s, sim, entry->slot );
+		entry->slot = -1;
+		done += 1;
+		if ( hit && result != nullptr )
+		{
+			if ( result->hitEventBits != nullptr )
+			{
+				__atomic_fetch_or( result->hitEventBits + ( (uint32_t)id >> 6 ), (uint64_t)1 << ( (uint32_t)id & 63u ), __ATOMIC_RELAXED );
+			}
+			__atomic_store_n( &result->hasHitEvents, 1, __ATOMIC_RELAXED );
+		}
+	}
+	if ( done > 0 )
+	{
+		s->materialized.fetch_add( done, std::memory_order_relaxed );
+	}
+	return done;
+}
+
 extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 {
 	int bodyCount = s->params.bodyCount;
@@ -186,6 +258,11 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		float4* wireMass = base + s->inMass;
 		const bool resident = s->resident;
 		const bool usable = s->cacheUsable;
+		const bool defer = s->defer;
+		b2gDeferEntry* const deferMap = s->deferMap.data();
+		const size_t deferIds = s->deferMap.size();
+		const uint32_t deferNewStamp = s->deferNewStamp;
+		int materialized = 0;
 		b2gStreamChunk full = { &s->fullCursor, s->fullCapacity, 0, 0, &s->streamOverflow };
 		bool massDiffers = false;
 		int vouchedTotal = 0;
@@ -233,6 +310,12 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 						{
 							vouched[j - group] = true;
 							ownBits = head.ownBits;
+							if ( defer && j >= local && j < localEnd && (size_t)id < deferIds )
+							{
+								// its record of THIS step is the one a later reader of the manifold needs (the one of the
+								// previous step, if it is still pending, is superseded: the device has it)
+								deferMap[id] = b2gDeferEntry{ ( seg.slotStart + j ) | ( seg.wide ? kDeferWide : 0 ), deferNewStamp };
+							}
 						}
 					}
 					if ( ownBits < 0 )
@@ -254,6 +337,22 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 						continue;
 					}
 					const uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
+					if ( defer )
+					{
+						// a contact nobody vouches for is read in full below: if the previous step's impulses never reached
+						// its manifold (nothing has read it since), they do now; then its record of this step is entered
+						const int id = b2gRdI( sim, B2L_CONTACT_ID );
+						b2gDeferEntry* pending = b2gPendingEntry( s, id );
+						if ( pending != nullptr )
+						{
+							b2gMaterializeRecord( s, seg.sims + (size_t)i * B2L_CONTACT_SIZE, pending->slot );
+							materialized += 1;
+						}
+						if ( (size_t)id < deferIds )
+						{
+							deferMap[id] = b2gDeferEntry{ slot | ( seg.wide ? kDeferWide : 0 ), deferNewStamp };
+						}
+					}
 					const uint8_t* m = sim + B2L_CONTACT_MANIFOLD;
 					const uint8_t* p0 = m + B2L_MANIFOLD_POINTS;
 					const uint8_t* p1 = p0 + B2L_MP_SIZE;
@@ -308,9 +407,20 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 					b2gShadowContact& shadow = s->shadowContacts[(size_t)home];
 					b2gShadowImpulses& shadowImpulses = s->shadowImpulses[(size_t)home];
 					b2gShadowHead& head = s->shadowHeads[(size_t)home];
-					const bool clean = i < homeCount && head.contactId == id && memcmp( shadow.rows, rows, sizeof( rows ) ) == 0 &&
-									   memcmp( shadowImpulses.values, impulses, sizeof( impulses ) ) == 0;
 					int ref = homeSlot + i; // its record among the previous step's outputs
+					bool clean = i < homeCount && head.contactId == id && memcmp( shadow.rows, rows, sizeof( rows ) ) == 0;
+					if ( clean && defer )
+					{
+						// the impulses in the manifold against what the device computed last (rollingImpulse, normalImpulse1,
+						// tangentImpulse1, ..., normalImpulse2, tangentImpulse2: b2g::ImpulseRecord) -- the unpack pass keeps no shadow
+						const float* rec = s->prevRecords + (size_t)ref * b2g::kImpulseFloats;
+						clean = s->prevRecords != nullptr && memcmp( rec + 1, impulses + 0, 8 ) == 0 && memcmp( rec + 5, impulses + 2, 8 ) == 0 &&
+								memcmp( rec + 0, impulses + 4, 4 ) == 0;
+					}
+					else if ( clean )
+					{
+						clean = memcmp( shadowImpulses.values, impulses, sizeof( impulses ) ) == 0;
+					}
 					if ( !clean )
 					{
 						int entry = b2gStreamTake( full );
@@ -366,6 +476,10 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		if ( vouchedTotal > 0 )
 		{
 			s->vouchedCount.fetch_add( vouchedTotal, std::memory_order_relaxed );
+		}
+		if ( materialized > 0 )
+		{
+			s->materialized.fetch_add( materialized, std::memory_order_relaxed );
 		}
 	}
 
@@ -665,7 +779,8 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 		}
 	}
 
-	// ---- contact impulses
+	// ---- contact impulses (deferred impulses: not here -- b2GpuSolverMaterializeContacts, when somebody needs them)
+	if ( !s->defer )
 	{
 		const float* allRecords = reinterpret_cast<const float*>( base + s->outImpulses );
 		int flat = ( begin > bodyCount ? begin : bodyCount ) - bodyCount;
@@ -1007,7 +1122,23 @@ extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 		}
 		int begin = block * s->blockItems;
 		int end = begin + s->blockItems < s->workItems ? begin + s->blockItems : s->workItems;
-		size_t need = b2gOutPrefix( s, end );
+		int begin2 = 0, end2 = 0; // deferred impulses: the items are the bodies and the joints, a block may hold some of both
+		if ( s->defer )
+		{
+			const int bodyCount = s->params.bodyCount, skip = s->contactTotal;
+			if ( begin >= bodyCount )
+			{
+				begin += skip;
+				end += skip;
+			}
+			else if ( end > bodyCount )
+			{
+				begin2 = bodyCount + skip;
+				end2 = end + skip;
+				end = bodyCount;
+			}
+		}
+		size_t need = b2gOutPrefix( s, end2 > end ? end2 : end );
 		while ( s->arrivedQuads.load( std::memory_order_acquire ) < need )
 		{
 			if ( b2gTryPumpDownloads( s ) != 0 )
@@ -1022,6 +1153,7 @@ extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 			_mm_pause();
 		}
 		b2GpuSolverUnpackRange( s, begin, end );
+		b2GpuSolverUnpackRange( s, begin2, end2 );
 	}
 	if ( pump != 0 )
 	{
@@ -1032,7 +1164,7 @@ extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 			if ( s->pumpBusy.exchange( 1, std::memory_order_acquire ) == 0 )
 			{
 				int rc = b2gPumpDownloads( s );
-				bool done = s->controlSeen && s->chunkNext >= s->chunkCount;
+				bool done = s->controlSeen && s->chunkNext >= s->deferWaitChunks; // (all chunks, unless the impulse records are deferred)
 				s->pumpBusy.store( 0, std::memory_order_release );
 				if ( rc != 0 )
 				{

@@ -21,8 +21,10 @@
 #include "physics_world.h"
 #include "solver.h"
 #include "solver_set.h"
+#include "world_snapshot.h"
 
 #include "box2d/base.h"
+#include "box2d/box2d.h"
 #include "box2d/constants.h"
 
 #include <pthread.h>
@@ -55,6 +57,7 @@ typedef struct b2SeamSlot
 	int collidesSinceSolve;
 	bool islandsCaptured; /* b2GpuSeam_BeforeIslandSplit filled the hint of the step in flight */
 	int capturedIslandCount;
+	long long flushes; /* deferred impulses: times every pending manifold had to be materialized at once */
 } b2SeamSlot;
 
 static b2SeamSlot s_slots[B2_MAX_WORLDS];
@@ -133,6 +136,12 @@ static b2SeamSlot* b2SeamGetSlot( b2World* world )
 		}
 		int mode = s_mode >= 0 ? s_mode : b2SeamEnvInt( "B2GPU_MODE", 0 );
 		b2GpuSolverSetMode( slot->solver, mode );
+		// the impulse records stay on the library's side until a manifold is read ("deferred impulses" below); B2GPU_DEFER=0:
+		// every step writes them into the manifolds like b2StoreImpulsesTask does
+		if ( b2GpuSolverSetDeferredImpulses( slot->solver, b2SeamEnvInt( "B2GPU_DEFER", 1 ) ) != 0 )
+		{
+			b2SeamFatal( "b2GpuSolverSetDeferredImpulses" );
+		}
 	}
 	return slot;
 }
@@ -370,6 +379,12 @@ void b2GpuSeam_BeginCollide( b2World* world, b2StepContext* context, int contact
 		start += slot->collideCount[i];
 	}
 	slot->collidesSinceSolve += 1;
+	// the narrow phase's workers materialize what they re-evaluate (b2GpuSeam_ContactReevaluated): the tail of the previous
+	// step's download is waited for here, once
+	if ( slot->solver != NULL && b2GpuSolverDeferredSync( slot->solver ) != 0 )
+	{
+		b2SeamFatal( "download of the deferred impulses failed" );
+	}
 }
 
 void b2GpuSeam_ContactRecycled( b2World* world, int contactIndex, const b2ContactSim* contactSim )
@@ -380,6 +395,172 @@ void b2GpuSeam_ContactRecycled( b2World* world, int contactIndex, const b2Contac
 	entry->separation[0] = contactSim->manifold.points[0].separation;
 	entry->separation[1] = contactSim->manifold.points[1].separation;
 	entry->stamp = slot->recycledStamp;
+}
+
+/* ---- deferred impulses: a manifold receives the solver's impulses when somebody is going to read them -----------------
+ * The reference stores the impulses of every contact at the end of every step (b2StoreImpulsesTask,
+ * src/contact_solver.c:2293-2320) -- and then reads them back in few places: b2UpdateContact when it re-evaluates a manifold
+ * (src/contact.c:523: the old points' impulses are matched by feature id), the hit events of the step
+ * (src/solver.c:1759-1766), the contact-data API (src/body.c:482, src/shape.c:1765, src/contact.c:83), the debug draw
+ * (src/physics_world.c:1325), the snapshot / state hash (src/world_snapshot.c) and, implicitly, island sleep, which moves
+ * the b2ContactSims out of the solver's sight (src/solver_set.c:318).  A RECYCLED manifold (src/physics_world.c:508-560)
+ * is not read at all, and the device warm-starts it from its own previous output.  So the seam leaves the records in the
+ * library's page-locked output arena (b2GpuSolverSetDeferredImpulses) and calls b2GpuSolverMaterializeContacts from
+ * exactly those places: the generated physics_world.c before b2UpdateContact, and the functions below, which the build
+ * puts in front of the reference's (tools/buildlib.py renames the reference's definitions to b2Ref_*; the reference's
+ * sources are not touched).  The many_pyramids step loses its 3 MB download and the unpack pass over 58 000 manifolds from
+ * the critical path. */
+void b2GpuSeam_ContactReevaluated( b2World* world, b2ContactSim* contactSim )
+{
+	b2SeamSlot* slot = s_slots + world->worldId;
+	if ( slot->solver != NULL && b2GpuSolverMaterializeContacts( slot->solver, contactSim, 1, NULL ) < 0 )
+	{
+		b2SeamFatal( "b2GpuSolverMaterializeContacts" );
+	}
+}
+
+/* every contact of the constraint graph that still waits for its impulses receives them */
+static void b2SeamFlushImpulses( b2World* world, b2GpuStepResult* result )
+{
+	if ( world == NULL || world->worldId < 0 || world->worldId >= B2_MAX_WORLDS )
+	{
+		return;
+	}
+	b2SeamSlot* slot = s_slots + world->worldId;
+	if ( slot->solver == NULL || slot->generation != world->generation || b2GpuSolverDeferredPending( slot->solver ) == 0 )
+	{
+		return;
+	}
+	for ( int i = 0; i < B2_GRAPH_COLOR_COUNT; ++i )
+	{
+		b2GraphColor* color = world->constraintGraph.colors + i;
+		if ( color->contactSims.count > 0 &&
+			 b2GpuSolverMaterializeContacts( slot->solver, color->contactSims.data, color->contactSims.count, result ) < 0 )
+		{
+			b2SeamFatal( "b2GpuSolverMaterializeContacts" );
+		}
+	}
+	b2GpuSolverDeferredDone( slot->solver );
+	slot->flushes += 1;
+}
+
+void b2GpuSeam_FlushImpulses( int worldIndex )
+{
+	if ( 0 <= worldIndex && worldIndex < B2_MAX_WORLDS && s_slots[worldIndex].solver != NULL )
+	{
+		b2SeamFlushImpulses( b2GetWorld( worldIndex ), NULL );
+	}
+}
+
+int b2GpuSeam_GetDeferredStats( int worldIndex, int* pending, long long* flushes )
+{
+	if ( worldIndex < 0 || worldIndex >= B2_MAX_WORLDS || s_slots[worldIndex].solver == NULL )
+	{
+		return 0;
+	}
+	*pending = b2GpuSolverDeferredPending( s_slots[worldIndex].solver );
+	*flushes = s_slots[worldIndex].flushes;
+	return 1;
+}
+
+/* The reference's readers of manifold impulses outside the narrow phase and the solver, each behind a flush.  b2Ref_* are the
+ * reference's own definitions (renamed in the product's copies of its object files). */
+int b2Ref_Body_GetContactData( b2BodyId bodyId, b2ContactData* contactData, int capacity );
+int b2Ref_Shape_GetContactData( b2ShapeId shapeId, b2ContactData* contactData, int capacity );
+b2ContactData b2Ref_Contact_GetData( b2ContactId contactId );
+void b2Ref_World_Draw( b2WorldId worldId, b2DebugDraw* draw );
+uint64_t b2Ref_World_GetStateHash( b2WorldId worldId );
+int b2Ref_World_Snapshot( b2WorldId worldId, uint8_t* image, int capacity );
+bool b2Ref_World_Restore( b2WorldId worldId, const uint8_t* image, int size );
+void b2Ref_SerializeWorld( b2World* world, b2RecBuffer* buf );
+uint64_t b2Ref_HashWorldStateDeep( b2World* world );
+void b2Ref_TrySleepIsland( b2World* world, int islandId );
+
+static void b2SeamFlushIndex( int worldIndex )
+{
+	if ( 0 <= worldIndex && worldIndex < B2_MAX_WORLDS && s_slots[worldIndex].solver != NULL )
+	{
+		b2World* world = b2GetWorld( worldIndex );
+		if ( world->inUse && world->locked == false )
+		{
+			b2SeamFlushImpulses( world, NULL );
+		}
+	}
+}
+
+int b2Body_GetContactData( b2BodyId bodyId, b2ContactData* contactData, int capacity )
+{
+	b2SeamFlushIndex( bodyId.world0 );
+	return b2Ref_Body_GetContactData( bodyId, contactData, capacity );
+}
+
+int b2Shape_GetContactData( b2ShapeId shapeId, b2ContactData* contactData, int capacity )
+{
+	b2SeamFlushIndex( shapeId.world0 );
+	return b2Ref_Shape_GetContactData( shapeId, contactData, capacity );
+}
+
+b2ContactData b2Contact_GetData( b2ContactId contactId )
+{
+	b2SeamFlushIndex( contactId.world0 );
+	return b2Ref_Contact_GetData( contactId );
+}
+
+void b2World_Draw( b2WorldId worldId, b2DebugDraw* draw )
+{
+	b2SeamFlushIndex( (int)worldId.index1 - 1 );
+	b2Ref_World_Draw( worldId, draw );
+}
+
+uint64_t b2World_GetStateHash( b2WorldId worldId )
+{
+	b2SeamFlushIndex( (int)worldId.index1 - 1 );
+	return b2Ref_World_GetStateHash( worldId );
+}
+
+int b2World_Snapshot( b2WorldId worldId, uint8_t* image, int capacity )
+{
+	b2SeamFlushIndex( (int)worldId.index1 - 1 );
+	return b2Ref_World_Snapshot( worldId, image, capacity );
+}
+
+bool b2World_Restore( b2WorldId worldId, const uint8_t* image, int size )
+{
+	// the host's contacts are replaced wholesale: nothing of the previous step is owed to them any more, and the narrow
+	// phase's word on what it recycles does not hold for the step that follows (the device has never seen this state;
+	// the pack pass compares everything by value)
+	int worldIndex = (int)worldId.index1 - 1;
+	if ( 0 <= worldIndex && worldIndex < B2_MAX_WORLDS && s_slots[worldIndex].solver != NULL )
+	{
+		b2GpuSolverDeferredDone( s_slots[worldIndex].solver );
+		s_slots[worldIndex].collidesSinceSolve = 2;
+	}
+	return b2Ref_World_Restore( worldId, image, size );
+}
+
+void b2SerializeWorld( b2World* world, b2RecBuffer* buf )
+{
+	if ( world->locked == false )
+	{
+		b2SeamFlushImpulses( world, NULL );
+	}
+	b2Ref_SerializeWorld( world, buf );
+}
+
+uint64_t b2HashWorldStateDeep( b2World* world )
+{
+	if ( world->locked == false )
+	{
+		b2SeamFlushImpulses( world, NULL );
+	}
+	return b2Ref_HashWorldStateDeep( world );
+}
+
+void b2TrySleepIsland( b2World* world, int islandId )
+{
+	// (called on the stepping thread: the tail of b2Solve, src/solver.c:2073, and b2Body_SetAwake, src/body.c:1575)
+	b2SeamFlushImpulses( world, NULL );
+	b2Ref_TrySleepIsland( world, islandId );
 }
 
 /* ---- island capture ahead of a split ---------------------------------------------------------------------- */
@@ -753,6 +934,12 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 	if ( failure != NULL )
 	{
 		b2SeamFatal( failure );
+	}
+	if ( result->hasHitEvents != 0 && b2GpuSolverDeferredPending( slot->solver ) != 0 )
+	{
+		// deferred impulses: some contact of the step reports a hit event (the device's flag).  The events are built from the
+		// manifolds of the flagged contacts (src/solver.c:1745-1790), and the flags are in the records.
+		b2SeamFlushImpulses( world, result );
 	}
 
 	slot->totals.seamMs += b2GetMilliseconds( seamTicks );

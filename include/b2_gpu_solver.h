@@ -235,6 +235,30 @@ B2GPU_API int b2GpuSolverEndStep( b2GpuSolver* solver, b2GpuStepResult* result )
 B2GPU_API int b2GpuSolverPackWork( b2GpuSolver* solver, int pump );
 B2GPU_API int b2GpuSolverUnpackWork( b2GpuSolver* solver, int pump );
 
+/* Deferred contact impulses (resident mode of a single world, phased entry points).  What a step writes into the
+ * manifolds -- b2StoreImpulsesTask, src/contact_solver.c:2293-2320 -- is read back by the host far less often than it is
+ * written: a manifold the narrow phase RECYCLES (src/physics_world.c:508-560) is not looked at, and the device warm-starts
+ * such a contact from its own previous output.  When enabled, EndStep returns once the body states and the joints'
+ * outputs are in place; the impulse records follow behind the caller's back and stay in the library's page-locked output
+ * arena, and the CALLER promises to call b2GpuSolverMaterializeContacts on a contact before anything reads its manifold's
+ * impulses (normalImpulse, tangentImpulse, totalNormalImpulse, normalVelocity, rollingImpulse) or moves it out of the
+ * awake contact arrays for good: the narrow phase before it re-evaluates the manifold (src/contact.c:523), island sleep
+ * (src/solver_set.c:155), the contact-data and snapshot API, hit events (b2GpuStepResult::hasHitEvents is then set from
+ * the device's flag and the bits are set by the materialize call).  Contacts are identified by b2ContactSim::contactId, so
+ * they may have moved in their arrays in the meantime.  The pack pass of the next step materializes whatever it has to read
+ * in full itself.  Must be set before the first step (or between steps with nothing pending); off by default. */
+B2GPU_API int b2GpuSolverSetDeferredImpulses( b2GpuSolver* solver, int enabled );
+/* 1 while some manifolds may not have received the last step's impulses */
+B2GPU_API int b2GpuSolverDeferredPending( const b2GpuSolver* solver );
+/* Waits for the tail of the last step's download (otherwise the first materialize call does); 0 on success. */
+B2GPU_API int b2GpuSolverDeferredSync( b2GpuSolver* solver );
+/* Writes the pending impulses of `count` consecutive b2ContactSim into their manifolds (those that have some pending) and,
+ * with `result`, ORs their hit-event bits into result->hitEventBits.  May be called concurrently on different contacts.
+ * Returns the number of manifolds written, -1 on a device error. */
+B2GPU_API int b2GpuSolverMaterializeContacts( b2GpuSolver* solver, void* contactSims, int count, b2GpuStepResult* result );
+/* Every manifold that matters has been materialized (or the host's contacts were replaced wholesale): nothing is pending. */
+B2GPU_API void b2GpuSolverDeferredDone( b2GpuSolver* solver );
+
 /* Batch of independent worlds (the RL-style workload): one launch solves all of them, one thread block
  * per world with the world's bodies and constraints resident in shared memory for all sub-steps.  Each
  * desc is a complete, independent world step.  Worlds that do not fit the per-block budget are solved

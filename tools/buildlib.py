@@ -127,6 +127,41 @@ def compile_collide_gpu() -> Path:
 	return obj
 
 
+# Deferred impulses (box2d_b200/host/b2_gpu_seam.c): the reference's readers of manifold impulses outside the narrow phase and the
+# solver.  In the PRODUCT's copies of the reference's object files their definitions are renamed to b2Ref_* (objcopy; the sources
+# are not touched, the reference builds under oracle/_ref keep the originals) and the seam defines the public names: a flush of
+# the pending impulses, then the reference's function.
+INTERPOSED = {
+	"src_body.o": ["b2Body_GetContactData"],
+	"src_shape.o": ["b2Shape_GetContactData"],
+	"src_contact.o": ["b2Contact_GetData"],
+	"physics_world_gpu.o": ["b2World_Draw"],
+	"src_world_snapshot.o": ["b2World_GetStateHash", "b2World_Snapshot", "b2World_Restore", "b2SerializeWorld", "b2HashWorldStateDeep"],
+	"src_solver_set.o": ["b2TrySleepIsland"],
+}
+OBJCOPY = os.environ.get("OBJCOPY", "objcopy")
+
+
+def interpose(obj: Path) -> Path:
+	"""The product's copy of a reference object file, with the INTERPOSED definitions renamed to b2Ref_*."""
+	names = INTERPOSED.get(obj.name)
+	if not names:
+		return obj
+	out = obj.with_name(obj.stem + "_interposed.o")
+	if _stale(out, [obj, Path(__file__)]):
+		cmd = [OBJCOPY]
+		for name in names:
+			cmd += ["--redefine-sym", f"{name}=b2Ref_{name[2:]}"]
+		_run(cmd + [str(obj), str(out)])
+		# every name must have been defined there, or the seam's wrapper would call itself
+		syms = subprocess.run(["nm", "--defined-only", str(out)], stdout=subprocess.PIPE, text=True, check=True).stdout
+		for name in names:
+			if f" T b2Ref_{name[2:]}\n" not in syms:
+				out.unlink()
+				raise RuntimeError(f"interpose: {obj.name} does not define {name}")
+	return out
+
+
 def compile_own_c(src: Path, tag: str = "", defines: list[str] | None = None) -> Path:
 	OBJ_DIR.mkdir(parents=True, exist_ok=True)
 	obj = OBJ_DIR / f"own_{src.stem}{tag}.o"
@@ -184,7 +219,7 @@ def build_host_lib(verbose: bool = False) -> Path:
 	if not reference_available():
 		raise RuntimeError(f"reference sources not found at {REFERENCE}")
 	cuda_lib = build_cuda_lib(verbose)
-	objs = [o for o in compile_reference_objects() if o.name != "src_physics_world.o"] + [compile_collide_gpu()]
+	objs = [interpose(o) for o in compile_reference_objects() if o.name != "src_physics_world.o"] + [interpose(compile_collide_gpu())]
 	gpu = compile_solver_variant("gpu")
 	harness = compile_own_c(PKG_DIR / "host" / "b2h_harness.c")
 	seam = compile_own_c(PKG_DIR / "host" / "b2_gpu_seam.c", "_product", PRODUCT_DEFINES)
