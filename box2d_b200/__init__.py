@@ -163,6 +163,16 @@ def solver_lib() -> ctypes.CDLL:
 	lib.b2GpuSolverEndStep.argtypes = [ctypes.c_void_p, P(StepResult)]
 	lib.b2GpuSolverSetMode.restype = ctypes.c_int
 	lib.b2GpuSolverSetMode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+	lib.b2GpuSolverSetDeferredImpulses.restype = ctypes.c_int
+	lib.b2GpuSolverSetDeferredImpulses.argtypes = [ctypes.c_void_p, ctypes.c_int]
+	lib.b2GpuSolverDeferredPending.restype = ctypes.c_int
+	lib.b2GpuSolverDeferredPending.argtypes = [ctypes.c_void_p]
+	lib.b2GpuSolverDeferredSync.restype = ctypes.c_int
+	lib.b2GpuSolverDeferredSync.argtypes = [ctypes.c_void_p]
+	lib.b2GpuSolverMaterializeContacts.restype = ctypes.c_int
+	lib.b2GpuSolverMaterializeContacts.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, P(StepResult)]
+	lib.b2GpuSolverDeferredDone.restype = None
+	lib.b2GpuSolverDeferredDone.argtypes = [ctypes.c_void_p]
 	lib.b2GpuHostAlloc.restype = ctypes.c_void_p
 	lib.b2GpuHostAlloc.argtypes = [ctypes.c_size_t, ctypes.c_int]
 	lib.b2GpuHostFree.restype = None
@@ -215,6 +225,14 @@ def _bind_harness(lib: ctypes.CDLL) -> ctypes.CDLL:
 	lib.b2h_bench.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float),
 							  ctypes.POINTER(ctypes.c_float)]
 	lib.b2h_version.restype = ctypes.c_int
+	lib.b2h_contact_checksum.restype = ctypes.c_uint64
+	lib.b2h_contact_checksum.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+	lib.b2h_snapshot.restype = ctypes.c_int
+	lib.b2h_snapshot.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+	lib.b2h_restore.restype = ctypes.c_int
+	lib.b2h_restore.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
+	lib.b2h_step_index.restype = ctypes.c_int
+	lib.b2h_step_index.argtypes = [ctypes.c_int]
 	return lib
 
 
@@ -238,6 +256,10 @@ def host_lib() -> ctypes.CDLL:
 	lib.b2GpuSeam_DestroyGroup.argtypes = [ctypes.c_int]
 	lib.b2GpuSeam_GetResidentStats.restype = ctypes.c_int
 	lib.b2GpuSeam_GetResidentStats.argtypes = [ctypes.c_int] + [ctypes.POINTER(ctypes.c_int)] * 3
+	lib.b2GpuSeam_GetDeferredStats.restype = ctypes.c_int
+	lib.b2GpuSeam_GetDeferredStats.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_longlong)]
+	lib.b2GpuSeam_FlushImpulses.restype = None
+	lib.b2GpuSeam_FlushImpulses.argtypes = [ctypes.c_int]
 	lib.b2GpuSeam_InstallPinnedAllocator.restype = None
 	lib.b2GpuSeam_Shutdown.restype = None
 	_host_lib = lib
@@ -332,6 +354,31 @@ class World:
 		total = self.lib.b2h_bench(self.handle, steps, ctypes.byref(c), ctypes.byref(s), stages)
 		return {"wall_ms": float(total), "constraints_ms": float(c.value), "step_ms": float(s.value),
 				"stages_ms": dict(zip(STAGE_NAMES, stages))}
+
+	def contact_checksum(self):
+		"""(checksum, contact count) of what b2Shape_GetContactData reports for every shape (the impulses an application sees)."""
+		n = ctypes.c_int()
+		return int(self.lib.b2h_contact_checksum(self.handle, ctypes.byref(n))), n.value
+
+	def snapshot(self) -> tuple:
+		"""(image, step index): b2World_Snapshot."""
+		size = self.lib.b2h_snapshot(self.handle, None, 0)
+		buf = (ctypes.c_uint8 * size)()
+		got = self.lib.b2h_snapshot(self.handle, buf, size)
+		assert got == size, (got, size)
+		return bytes(buf), self.lib.b2h_step_index(self.handle)
+
+	def restore(self, snap: tuple) -> None:
+		image, step_index = snap
+		if self.lib.b2h_restore(self.handle, image, len(image), step_index) != 1:
+			raise RuntimeError("b2World_Restore failed")
+
+	def deferred_stats(self) -> tuple:
+		"""GPU host library only: (impulses pending?, number of whole-world flushes so far)."""
+		pending, flushes = ctypes.c_int(), ctypes.c_longlong()
+		if self.lib.b2GpuSeam_GetDeferredStats(self.world_index(), ctypes.byref(pending), ctypes.byref(flushes)) != 1:
+			raise RuntimeError("no device solver for this world yet")
+		return bool(pending.value), int(flushes.value)
 
 	def hinges_result(self):
 		sleep_step = ctypes.c_int()
@@ -495,6 +542,26 @@ class GpuSolver:
 
 	def step(self, desc: StepDesc, result: StepResult) -> None:
 		self._check(self.lib.b2GpuSolverStep(self.handle, ctypes.byref(desc), ctypes.byref(result)), "b2GpuSolverStep")
+
+	def set_deferred(self, enabled: bool) -> None:
+		self._check(self.lib.b2GpuSolverSetDeferredImpulses(self.handle, 1 if enabled else 0), "b2GpuSolverSetDeferredImpulses")
+
+	def deferred_pending(self) -> bool:
+		return bool(self.lib.b2GpuSolverDeferredPending(self.handle))
+
+	def materialize(self, contact_arrays, result: StepResult = None, done: bool = True) -> int:
+		"""b2GpuSolverMaterializeContacts over byte arrays of b2ContactSim; done = nothing is pending afterwards."""
+		total = 0
+		for arr in contact_arrays:
+			if arr.size:
+				n = self.lib.b2GpuSolverMaterializeContacts(self.handle, arr.ctypes.data, arr.size // CONTACT_SIZE,
+															ctypes.byref(result) if result is not None else None)
+				if n < 0:
+					raise RuntimeError("b2GpuSolverMaterializeContacts failed: " + self.lib.b2GpuGetLastError().decode())
+				total += n
+		if done:
+			self.lib.b2GpuSolverDeferredDone(self.handle)
+		return total
 
 	def upload(self, desc: StepDesc) -> None:
 		self._check(self.lib.b2GpuSolverUpload(self.handle, ctypes.byref(desc)), "b2GpuSolverUpload")

@@ -559,7 +559,12 @@ uint64_t b2HashWorldStateDeep( b2World* world )
 void b2TrySleepIsland( b2World* world, int islandId )
 {
 	// (called on the stepping thread: the tail of b2Solve, src/solver.c:2073, and b2Body_SetAwake, src/body.c:1575)
-	b2SeamFlushImpulses( world, NULL );
+	b2Island* island = world->islands.data + islandId;
+	if ( !( island->constraintRemoveCount > 0 && island->bodies.count > 1 ) )
+	{
+		// (otherwise the island stays awake: src/solver_set.c:160-164)
+		b2SeamFlushImpulses( world, NULL );
+	}
 	b2Ref_TrySleepIsland( world, islandId );
 }
 

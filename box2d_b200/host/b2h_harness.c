@@ -865,6 +865,72 @@ B2H_API uint64_t b2h_hash( int h )
 	return b2World_GetStateHash( s_worlds[h].worldId );
 }
 
+/* Checksum of what b2Shape_GetContactData (include/box2d/box2d.h:841) reports for every shape of the world: the manifolds'
+ * impulses as an application sees them.  Order independent (a sum of per-contact hashes). */
+typedef struct b2hContactSum
+{
+	uint64_t sum;
+	int contacts;
+} b2hContactSum;
+
+static bool b2hContactSumShape( b2ShapeId shapeId, void* context )
+{
+	b2hContactSum* acc = context;
+	b2ContactData data[64];
+	int count = b2Shape_GetContactData( shapeId, data, 64 );
+	for ( int i = 0; i < count; ++i )
+	{
+		const b2Manifold* m = &data[i].manifold;
+		uint64_t h = 1469598103934665603ull;
+		float values[10] = { m->rollingImpulse };
+		for ( int p = 0; p < m->pointCount && p < 2; ++p )
+		{
+			values[1 + 4 * p] = m->points[p].normalImpulse;
+			values[2 + 4 * p] = m->points[p].tangentImpulse;
+			values[3 + 4 * p] = m->points[p].totalNormalImpulse;
+			values[4 + 4 * p] = m->points[p].normalVelocity;
+		}
+		values[9] = (float)m->pointCount;
+		const uint8_t* bytes = (const uint8_t*)values;
+		for ( size_t k = 0; k < sizeof( values ); ++k )
+		{
+			h = ( h ^ bytes[k] ) * 1099511628211ull;
+		}
+		acc->sum += h;
+		acc->contacts += 1;
+	}
+	return true;
+}
+
+B2H_API uint64_t b2h_contact_checksum( int h, int* contacts )
+{
+	b2hContactSum acc = { 0, 0 };
+	b2AABB everything = { { -1.0e6f, -1.0e6f }, { 1.0e6f, 1.0e6f } };
+	b2World_OverlapAABB( s_worlds[h].worldId, (b2Pos){ 0.0f, 0.0f }, everything, b2DefaultQueryFilter(), b2hContactSumShape, &acc );
+	if ( contacts != NULL )
+	{
+		*contacts = acc.contacts;
+	}
+	return acc.sum;
+}
+
+/* b2World_Snapshot / b2World_Restore (include/box2d/box2d.h:316,329) */
+B2H_API int b2h_snapshot( int h, uint8_t* image, int capacity )
+{
+	return b2World_Snapshot( s_worlds[h].worldId, image, capacity );
+}
+
+B2H_API int b2h_restore( int h, const uint8_t* image, int size, int stepIndex )
+{
+	s_worlds[h].stepIndex = stepIndex;
+	return b2World_Restore( s_worlds[h].worldId, image, size ) ? 1 : 0;
+}
+
+B2H_API int b2h_step_index( int h )
+{
+	return s_worlds[h].stepIndex;
+}
+
 B2H_API int b2h_world_index( int h )
 {
 	return (int)s_worlds[h].worldId.index1 - 1;
