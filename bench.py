@@ -395,7 +395,8 @@ def run_scene(args) -> int:
 		resident = scene not in SLEEPING_SCENES
 		resident_stats = None
 		abi_split = {"seam_ms": totals.seamMs / max(1, totals.steps), "pack_ms": totals.packMs / max(1, totals.steps),
-					 "h2d_kernels_d2h_ms": totals.waitMs / max(1, totals.steps), "unpack_ms": totals.unpackMs / max(1, totals.steps)}
+					 "h2d_kernels_d2h_ms": totals.waitMs / max(1, totals.steps), "unpack_ms": totals.unpackMs / max(1, totals.steps),
+					 "before_begin_ms": totals.beforeMs / max(1, totals.steps)}
 		kernel_s = e2e_kernel_s
 		launches = 0
 		substeps = 4
@@ -403,6 +404,7 @@ def run_scene(args) -> int:
 			# The desc still points at the world's arrays.  After b2World_Step returned they hold what the NEXT step
 			# would start from (finalize reset the state deltas, src/solver.c:611-612; manifolds carry the stored
 			# impulses), i.e. a valid, representative solver input with the same constraint graph.
+			host.b2GpuSeam_FlushImpulses(widx)  # (deferred impulses: the manifolds receive what the last step computed)
 			desc = host.b2GpuSeam_GetLastDesc(widx).contents
 			substeps = int(desc.subStepCount)
 			with b2.GpuSolver(device=local_rank) as solver:

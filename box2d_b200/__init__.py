@@ -66,11 +66,13 @@ class StepDesc(ctypes.Structure):
 		("islandSizes", ctypes.c_void_p),
 		("recycled", ctypes.c_void_p), ("recycledStamp", ctypes.c_uint32),
 		("recycledStart", ctypes.c_int * (MAX_ACTIVE_COLORS + 1)), ("recycledCount", ctypes.c_int * (MAX_ACTIVE_COLORS + 1)),
+		("recycledInPlace", ctypes.c_int * (MAX_ACTIVE_COLORS + 1)),
 	]
 
 
 class RecycledContact(ctypes.Structure):
-	_fields_ = [("stamp", ctypes.c_uint32), ("contactId", ctypes.c_int), ("separation", ctypes.c_float * 2)]
+	_fields_ = [("stamp", ctypes.c_uint32), ("contactId", ctypes.c_int), ("separation", ctypes.c_float * 2),
+				("indexA", ctypes.c_int), ("indexB", ctypes.c_int)]
 
 
 class IslandSize(ctypes.Structure):
@@ -102,6 +104,7 @@ class SeamTotals(ctypes.Structure):
 		("stageMs", ctypes.c_double * 8),
 		("steps", ctypes.c_longlong), ("launches", ctypes.c_longlong), ("gridBarriers", ctypes.c_longlong),
 		("seamMs", ctypes.c_double), ("packMs", ctypes.c_double), ("waitMs", ctypes.c_double), ("unpackMs", ctypes.c_double),
+		("beforeMs", ctypes.c_double),
 	]
 
 

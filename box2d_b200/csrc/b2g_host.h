@@ -148,6 +148,7 @@ struct b2gContactSeg
 	const b2GpuRecycledContact* hints; // optional (b2GpuStepDesc::recycled), entry i describes contact i
 	int hintCount;
 	uint32_t hintStamp;
+	bool hintsInPlace; // b2GpuStepDesc::recycledInPlace: entry i is contact i, the contact need not be looked at
 };
 
 struct b2gJointSeg
@@ -329,6 +330,17 @@ struct b2GpuSolver
 	std::atomic<int> recordsSynced{ 1 };
 	int deferWaitChunks = 0; // chunks of the download the unpack pass waits for (the rest holds the impulse records)
 	std::atomic<int> materialized{ 0 }; // statistics: records written into manifolds since the last step began
+
+	// Direct outputs (with deferred impulses; B2GPU_DIRECT_OUT=0 turns them off): the kernels store the body states straight
+	// into the page-locked output arena (mapped into the device's address space: the stores travel over PCIe while other
+	// blocks are still solving) and the step's last kernel copies the control block the same way and raises a flag the host
+	// polls -- no copy-engine round trips between the end of the kernels and the host's finalize pass.
+	bool directEnabled = true;
+	bool direct = false; // this step
+	int* hFlag = nullptr; // page-locked, written by b2gSignalKernel
+	int flagSerial = 0;
+	unsigned flagPolls = 0;
+	size_t directEnd = 0; // quads at the front of the output arena that are there when the flag is (the body states)
 	ControlBlock* hControl = nullptr;
 
 	// arena layouts, in float4 units
@@ -429,6 +441,7 @@ constexpr size_t kDownloadQuads = 32 * 1024; // 512 KiB: the unpack pass runs th
 int b2gSendArena( b2GpuSolver* s, size_t uptoQuads );
 void b2gFlushLines( const void* ptr, size_t bytes );
 // b2g_solver.cu
+int b2gPollControl( b2GpuSolver* s, bool* seen );
 int b2gDeferSync( b2GpuSolver* s );
 int b2gEnqueueDownload( b2GpuSolver* s );
 int b2gRerunIfIslandsFailed( b2GpuSolver* s, bool download );

@@ -183,6 +183,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		// at ~192 us, the link is the limit, not snoops.)
 		const char* chunkEnv = getenv( "B2GPU_DOWNLOAD_KIB" );
 		s->downloadQuads = chunkEnv != nullptr && atoi( chunkEnv ) >= 16 ? (size_t)atoi( chunkEnv ) * 64 : kDownloadQuads;
+		const char* directEnv = getenv( "B2GPU_DIRECT_OUT" );
+		s->directEnabled = directEnv == nullptr || atoi( directEnv ) != 0;
 		const char* liteEnv = getenv( "B2GPU_LITE_JOINTS" );
 		s->liteJointsEnabled = liteEnv == nullptr || atoi( liteEnv ) != 0;
 		const char* residentEnv = getenv( "B2GPU_RESIDENT" );
@@ -238,6 +240,11 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 	ok = ok && cudaEventCreateWithFlags( &s->evRecords, cudaEventDisableTiming ) == cudaSuccess;
 	ok = ok && cudaMalloc( &s->control, sizeof( ControlBlock ) ) == cudaSuccess;
 	ok = ok && cudaHostAlloc( &s->hControl, sizeof( ControlBlock ), cudaHostAllocDefault ) == cudaSuccess;
+	ok = ok && cudaHostAlloc( &s->hFlag, 64, cudaHostAllocDefault ) == cudaSuccess;
+	if ( ok )
+	{
+		*s->hFlag = 0;
+	}
 	if ( !ok )
 	{
 		b2gFail( "b2GpuSolverCreate: resource allocation", cudaGetLastError() );
@@ -302,6 +309,10 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	if ( s->hControl != nullptr )
 	{
 		cudaFreeHost( s->hControl );
+	}
+	if ( s->hFlag != nullptr )
+	{
+		cudaFreeHost( s->hFlag );
 	}
 	for ( cudaEvent_t ev : { s->evStart, s->evStop, s->evUpload, s->evControl, s->evRecords } )
 	{
@@ -936,6 +947,7 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 					seg.hints = dw.recycled != nullptr && dw.recycledCount[c] > 0 ? dw.recycled + dw.recycledStart[c] : nullptr;
 					seg.hintCount = seg.hints != nullptr ? dw.recycledCount[c] : 0;
 					seg.hintStamp = dw.recycledStamp;
+					seg.hintsInPlace = seg.hints != nullptr && dw.recycledInPlace[c] != 0;
 				}
 				if ( color.jointCount > 0 )
 				{
@@ -1279,6 +1291,14 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	P.g.joints = reinterpret_cast<uint8_t*>( s->jointWork.ptr ); // working copy of the joint records (grid kernel, spilled joints)
 	P.outJoints = reinterpret_cast<float*>( s->outAll.ptr + s->outJoints );
 	P.outStates = reinterpret_cast<uint8_t*>( s->outAll.ptr + s->outStates );
+	s->direct = s->defer && s->directEnabled;
+	s->directEnd = 0;
+	if ( s->direct )
+	{
+		// (page-locked host memory has the same address on the device: unified addressing)
+		P.outStates = reinterpret_cast<uint8_t*>( s->hOut.ptr + s->outStates );
+		s->directEnd = s->outJoints; // the states are the arena's first region
+	}
 	P.outImpulses = reinterpret_cast<float*>( s->outAll.ptr + s->outImpulses );
 	P.jointBits = reinterpret_cast<uint32_t*>( s->outAll.ptr + s->outBits );
 	P.hasHitEvents = &s->control->hasHitEvents;
@@ -1631,12 +1651,79 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 	return 0;
 }
 
+// Direct outputs: the last kernel of a step.  The body states are in the host's arena already (the solve kernels stored them
+// there); the control block follows the same way, then the flag.  Stream order puts this kernel behind every store of the
+// solve kernels; the fences order its own stores before the flag for an observer on the host.
+__global__ void b2gSignalKernel( const int* control, int* hostControl, int words, volatile int* flag, int serial )
+{
+	for ( int i = (int)threadIdx.x; i < words; i += (int)blockDim.x )
+	{
+		hostControl[i] = control[i];
+	}
+	__threadfence_system();
+	__syncthreads();
+	if ( threadIdx.x == 0 )
+	{
+		__threadfence_system();
+		*flag = serial;
+	}
+}
+
+// has the control block of the step in flight come back?  (the host's poll, b2gPumpDownloads)
+int b2gPollControl( b2GpuSolver* s, bool* seen )
+{
+	*seen = false;
+	if ( s->direct )
+	{
+		if ( *const_cast<volatile int*>( s->hFlag ) == s->flagSerial )
+		{
+			std::atomic_thread_fence( std::memory_order_acquire );
+			*seen = true;
+			return 0;
+		}
+		// the flag never comes if a kernel faulted: look at the event behind the signal kernel now and then
+		s->flagPolls += 1;
+		if ( ( s->flagPolls & 1023 ) != 0 )
+		{
+			return 0;
+		}
+	}
+	cudaError_t err = cudaEventQuery( s->evControl );
+	if ( err == cudaErrorNotReady )
+	{
+		return 0;
+	}
+	if ( err != cudaSuccess )
+	{
+		return b2gFail( "device solve", err );
+	}
+	*seen = true;
+	return 0;
+}
+
 int b2gEnqueueDownload( b2GpuSolver* s )
 {
 	// the control block first (it says whether the island kernels gave up), then the output arena in chunks with an
 	// event each, so that unpacking can start behind the transfer
 	cudaStream_t st = s->stream;
-	B2G_CUDA( cudaMemcpyAsync( s->hControl, s->control, sizeof( ControlBlock ), cudaMemcpyDeviceToHost, st ) );
+	if ( s->direct )
+	{
+		s->flagSerial += 1;
+		s->flagPolls = 0;
+		b2gSignalKernel<<<1, 32, 0, st>>>( reinterpret_cast<const int*>( s->control ), reinterpret_cast<int*>( s->hControl ),
+										   (int)( sizeof( ControlBlock ) / sizeof( int ) ), s->hFlag, s->flagSerial );
+		cudaError_t err = cudaGetLastError();
+		if ( err != cudaSuccess )
+		{
+			return b2gFail( "b2gSignalKernel launch", err );
+		}
+		s->lastLaunches += 1;
+		s->launchCount += 1;
+	}
+	else
+	{
+		B2G_CUDA( cudaMemcpyAsync( s->hControl, s->control, sizeof( ControlBlock ), cudaMemcpyDeviceToHost, st ) );
+	}
 	B2G_CUDA( cudaEventRecord( s->evControl, st ) );
 	s->controlSeen = false;
 	size_t total = s->outTotal;
@@ -1646,7 +1733,7 @@ int b2gEnqueueDownload( b2GpuSolver* s )
 	const size_t awaited = s->defer ? s->outImpulses : total;
 	s->deferWaitChunks = 0;
 	int made = 0;
-	for ( size_t begin = 0; begin < total; )
+	for ( size_t begin = s->direct ? s->directEnd : 0; begin < total; )
 	{
 		size_t end = begin + chunkQuads < total ? begin + chunkQuads : total;
 		end = begin < awaited && end > awaited ? awaited : end;

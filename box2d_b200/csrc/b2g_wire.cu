@@ -14,6 +14,7 @@
 
 #include <cstddef>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 static int* b2gJointIndexPair( b2lJointSim* joint )
@@ -181,6 +182,11 @@ extern "C" int b2GpuSolverMaterializeContacts( b2GpuSolver* s, void* contactSims
 	return done;
 }
 
+static const int kPackPrefetch = []() {
+	const char* v = getenv( "B2GPU_PACK_PREFETCH" );
+	return v != nullptr ? atoi( v ) : 16;
+}();
+
 extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 {
 	int bodyCount = s->params.bodyCount;
@@ -293,6 +299,15 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 				const int groupEnd = group + 4 < seg.count ? group + 4 : seg.count;
 				bool vouched[4] = { false, false, false, false };
 				int groupBits = 0;
+				if ( kPackPrefetch > 0 && !seg.hintsInPlace && group + kPackPrefetch < seg.count )
+				{
+					// the first cache line of the contacts two groups ahead (a 200-byte stride of which one line is read: the
+					// hardware prefetcher does not follow it), their hints and shadow heads
+					for ( int j = 0; j < 4; ++j )
+					{
+						_mm_prefetch( reinterpret_cast<const char*>( seg.sims + (size_t)( group + kPackPrefetch + j ) * B2L_CONTACT_SIZE ), _MM_HINT_T0 );
+					}
+				}
 				for ( int j = group; j < groupEnd; ++j )
 				{
 					const uint8_t* sim = seg.sims + (size_t)j * B2L_CONTACT_SIZE;
@@ -304,9 +319,12 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 						// its record is read beyond the first cache line.
 						const b2GpuRecycledContact& hint = seg.hints[j];
 						const b2gShadowHead& head = s->shadowHeads[(size_t)( homeBase + j )];
-						const int id = b2gRdI( sim, B2L_CONTACT_ID );
-						if ( hint.stamp == seg.hintStamp && hint.contactId == id && head.contactId == id &&
-							 head.indexA == b2gRdI( sim, B2L_CONTACT_INDEX_A ) && head.indexB == b2gRdI( sim, B2L_CONTACT_INDEX_B ) )
+						// (entries written in place: the caller says entry j is contact j -- the contact itself is not touched)
+						const int id = seg.hintsInPlace ? hint.contactId : b2gRdI( sim, B2L_CONTACT_ID );
+						const int simIndexA = seg.hintsInPlace ? hint.indexA : b2gRdI( sim, B2L_CONTACT_INDEX_A );
+						const int simIndexB = seg.hintsInPlace ? hint.indexB : b2gRdI( sim, B2L_CONTACT_INDEX_B );
+						if ( hint.stamp == seg.hintStamp && hint.contactId == id && head.contactId == id && head.indexA == simIndexA &&
+							 head.indexB == simIndexB )
 						{
 							vouched[j - group] = true;
 							ownBits = head.ownBits;
@@ -1044,14 +1062,14 @@ static int b2gPumpDownloads( b2GpuSolver* s )
 	if ( !s->controlSeen )
 	{
 		// kernels done?  (the control block is the first thing that comes back)
-		cudaError_t err = cudaEventQuery( s->evControl );
-		if ( err == cudaErrorNotReady )
+		bool seen = false;
+		if ( b2gPollControl( s, &seen ) != 0 )
+		{
+			return 1;
+		}
+		if ( !seen )
 		{
 			return 0;
-		}
-		if ( err != cudaSuccess )
-		{
-			return b2gFail( "device solve", err );
 		}
 		if ( s->ran && s->islandMode && s->hControl->islandFailed != 0 )
 		{
@@ -1065,6 +1083,10 @@ static int b2gPumpDownloads( b2GpuSolver* s )
 			s->arrivedQuads.store( s->outTotal, std::memory_order_release );
 		}
 		s->controlSeen = true;
+		if ( s->direct && s->arrivedQuads.load( std::memory_order_relaxed ) < s->directEnd )
+		{
+			s->arrivedQuads.store( s->directEnd, std::memory_order_release ); // the kernels stored the body states themselves
+		}
 		s->tWaited = std::chrono::steady_clock::now();
 		s->traceControl = std::chrono::duration<float, std::micro>( s->tWaited - s->tBegin ).count();
 	}

@@ -54,6 +54,7 @@ typedef struct b2SeamSlot
 	int recycledCapacity;
 	uint32_t recycledStamp;
 	int collideStart[B2_GRAPH_COLOR_COUNT], collideCount[B2_GRAPH_COLOR_COUNT];
+	bool colorTouched[B2_GRAPH_COLOR_COUNT]; /* a contact was added to / removed from the colour since the narrow phase began */
 	int collidesSinceSolve;
 	bool islandsCaptured; /* b2GpuSeam_BeforeIslandSplit filled the hint of the step in flight */
 	int capturedIslandCount;
@@ -376,6 +377,7 @@ void b2GpuSeam_BeginCollide( b2World* world, b2StepContext* context, int contact
 	{
 		slot->collideStart[i] = start;
 		slot->collideCount[i] = world->constraintGraph.colors[i].contactSims.count;
+		slot->colorTouched[i] = false;
 		start += slot->collideCount[i];
 	}
 	slot->collidesSinceSolve += 1;
@@ -394,6 +396,8 @@ void b2GpuSeam_ContactRecycled( b2World* world, int contactIndex, const b2Contac
 	entry->contactId = contactSim->contactId;
 	entry->separation[0] = contactSim->manifold.points[0].separation;
 	entry->separation[1] = contactSim->manifold.points[1].separation;
+	entry->indexA = contactSim->bodySimIndexA;
+	entry->indexB = contactSim->bodySimIndexB;
 	entry->stamp = slot->recycledStamp;
 }
 
@@ -554,6 +558,30 @@ uint64_t b2HashWorldStateDeep( b2World* world )
 		b2SeamFlushImpulses( world, NULL );
 	}
 	return b2Ref_HashWorldStateDeep( world );
+}
+
+/* The two functions through which a contact enters or leaves a colour's array between the narrow phase and the solver
+ * (b2UpdateContacts, src/physics_world.c:802,828; b2DestroyContact, src/contact.c:472; b2WakeSolverSet, src/solver_set.c:114):
+ * a colour they have touched is no longer the array the narrow phase's entries were written against. */
+void b2Ref_AddContactToGraph( b2World* world, b2ContactSim* contactSim, b2Contact* contact );
+void b2Ref_RemoveContactFromGraph( b2World* world, int bodyIdA, int bodyIdB, int colorIndex, int localIndex );
+
+void b2AddContactToGraph( b2World* world, b2ContactSim* contactSim, b2Contact* contact )
+{
+	b2Ref_AddContactToGraph( world, contactSim, contact );
+	if ( 0 <= contact->colorIndex && contact->colorIndex < B2_GRAPH_COLOR_COUNT )
+	{
+		s_slots[world->worldId].colorTouched[contact->colorIndex] = true;
+	}
+}
+
+void b2RemoveContactFromGraph( b2World* world, int bodyIdA, int bodyIdB, int colorIndex, int localIndex )
+{
+	if ( 0 <= colorIndex && colorIndex < B2_GRAPH_COLOR_COUNT )
+	{
+		s_slots[world->worldId].colorTouched[colorIndex] = true;
+	}
+	b2Ref_RemoveContactFromGraph( world, bodyIdA, bodyIdB, colorIndex, localIndex );
 }
 
 void b2TrySleepIsland( b2World* world, int islandId )
@@ -874,6 +902,8 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 			int i = color->colorIndex;
 			desc->recycledStart[c] = slot->collideStart[i];
 			desc->recycledCount[c] = slot->collideCount[i] < color->contactCount ? slot->collideCount[i] : color->contactCount;
+			// the colour's array is what the narrow phase walked (nothing added, removed or moved since): entry j is contact j
+			desc->recycledInPlace[c] = slot->colorTouched[i] ? 0 : 1;
 		}
 	}
 	slot->collidesSinceSolve = 0;
@@ -884,6 +914,7 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 	result->hitEventBits = taskContext0->hitEventBitSet.bits;
 	result->jointEventBits = taskContext0->jointStateBitSet.bits;
 
+	slot->totals.beforeMs += b2GetMilliseconds( seamTicks );
 	const char* failure = NULL;
 	if ( b2GpuSolverBeginStep( slot->solver, desc, result ) != 0 )
 	{

@@ -77,6 +77,7 @@ typedef struct b2GpuSeamTotals
 	long long steps, launches, gridBarriers;
 	double seamMs;	 /* host wall time of the whole seam call (what b2Profile.constraints reports) */
 	double packMs, waitMs, unpackMs; /* Begin..Submit, Submit..first output seen, ..EndStep of the phased C-ABI calls */
+	double beforeMs; /* seam entry .. BeginStep: bit-set clears, host joint prepare, island labels and sizes, the descriptor */
 } b2GpuSeamTotals;
 void b2GpuSeam_GetTotals( int worldIndex, b2GpuSeamTotals* totals, int reset );
 

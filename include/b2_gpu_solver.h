@@ -80,6 +80,7 @@ typedef struct b2GpuRecycledContact
 	uint32_t stamp; /* == b2GpuStepDesc::recycledStamp when the entry was written for this step */
 	int contactId;	/* b2ContactSim::contactId of the contact the entry was written for */
 	float separation[2]; /* b2ManifoldPoint::separation of the two points */
+	int indexA, indexB;	 /* b2ContactSim::bodySimIndexA / B as the narrow phase refreshed them (src/physics_world.c:497-504) */
 } b2GpuRecycledContact;
 
 /* Everything b2SolverTask reads from b2StepContext (src/solver.h:155-237) and b2World
@@ -149,6 +150,11 @@ typedef struct b2GpuStepDesc
 	uint32_t recycledStamp;
 	int recycledStart[B2GPU_MAX_ACTIVE_COLORS + 1];
 	int recycledCount[B2GPU_MAX_ACTIVE_COLORS + 1];
+	/* Optional, with recycled: recycledInPlace[c] != 0 = the caller also vouches that the contact array of colors[c] has not
+	 * changed since the entries were written -- no contact added, removed or moved (src/constraint_graph.c:66-211) -- so entry
+	 * i IS contact i and its indexA / indexB are the contact's: the pack pass takes a current entry without looking at the
+	 * contact at all.  0 = it checks the contact's id and body indices itself (one cache line per contact). */
+	int recycledInPlace[B2GPU_MAX_ACTIVE_COLORS + 1];
 } b2GpuStepDesc;
 
 /* Index of each per-stage timer, same split as b2Profile (include/box2d/types.h:526-551) filled by the

@@ -253,11 +253,13 @@ def _hints(cap: b2.Capture, stamp: int):
 			hints[k].contactId = int(row[0:4].view(np.int32)[0])
 			hints[k].separation[0] = float(row[POINT[0] + 16:POINT[0] + 20].view(np.float32)[0])
 			hints[k].separation[1] = float(row[POINT[1] + 16:POINT[1] + 20].view(np.float32)[0])
+			hints[k].indexA = int(row[36:40].view(np.int32)[0])
+			hints[k].indexB = int(row[40:44].view(np.int32)[0])
 			k += 1
 	return hints, starts, counts
 
 
-def _step_with_hints(oracle, solver, cap, tag, stamp, desc_stamp=None, spoil=()):
+def _step_with_hints(oracle, solver, cap, tag, stamp, desc_stamp=None, spoil=(), in_place=False):
 	d0, r0, want = cap.make_call()
 	assert oracle.b2OracleSolverStep(ctypes.byref(d0), ctypes.byref(r0)) == 0
 	d, r, got = cap.make_call()
@@ -269,6 +271,7 @@ def _step_with_hints(oracle, solver, cap, tag, stamp, desc_stamp=None, spoil=())
 	for c, (a, n) in enumerate(zip(starts, counts)):
 		d.recycledStart[c] = a
 		d.recycledCount[c] = n
+		d.recycledInPlace[c] = 1 if in_place else 0
 	solver.step(d, r)
 	assert np.array_equal(got["states"], want["states"]), tag + ": states"
 	for a, b in zip(got["contacts"], want["contacts"]):
@@ -277,28 +280,31 @@ def _step_with_hints(oracle, solver, cap, tag, stamp, desc_stamp=None, spoil=())
 	return got
 
 
-def test_recycled_hint_skips_the_comparison(oracle, capture_files):
+@pytest.mark.parametrize("in_place", [False, True], ids=["by id", "in place"])
+def test_recycled_hint_skips_the_comparison(oracle, capture_files, in_place):
 	"""b2GpuStepDesc::recycled: contacts the narrow phase vouches for are taken without reading their record; entries with a
-	stale stamp or another contact's id are ignored; the results are the oracle's either way."""
+	stale stamp or another contact's id are ignored; the results are the oracle's either way.  In place (recycledInPlace):
+	the caller also says that the colour arrays are the ones the entries were written against, and the pack pass does not
+	look at the contacts at all -- their ids and body indices come from the entries."""
 	rng = np.random.default_rng(3)
 	for name in ("small_pyramid_030", "contact_zoo_130", "overflow_025", "falling_hinges_120"):
 		cap = b2.Capture([f for f in capture_files if name in f.name][0])
 		n = cap.contact_count
 		with b2.GpuSolver() as solver:
-			got = _step_with_hints(oracle, solver, cap, name + " cold", stamp=1)
+			got = _step_with_hints(oracle, solver, cap, name + " cold", stamp=1, in_place=in_place)
 			assert solver.vouched_contacts() == 0, "nothing can be vouched for before the device has seen it"
 			_finalize(cap, got)
 			_mutate(cap, rng, "recycle")
-			got = _step_with_hints(oracle, solver, cap, name + " vouched", stamp=2)
+			got = _step_with_hints(oracle, solver, cap, name + " vouched", stamp=2, in_place=in_place)
 			assert solver.vouched_contacts() == n and solver.resident_stats()[0] == 0
 			_finalize(cap, got)
 			_mutate(cap, rng, "recycle")
-			got = _step_with_hints(oracle, solver, cap, name + " stale stamp", stamp=2, desc_stamp=3)
+			got = _step_with_hints(oracle, solver, cap, name + " stale stamp", stamp=2, desc_stamp=3, in_place=in_place)
 			assert solver.vouched_contacts() == 0 and solver.resident_stats()[0] == 0
 			_finalize(cap, got)
 			_mutate(cap, rng, "recycle")
 			spoil = list(range(0, n, 3))
-			got = _step_with_hints(oracle, solver, cap, name + " foreign ids", stamp=4, spoil=spoil)
+			got = _step_with_hints(oracle, solver, cap, name + " foreign ids", stamp=4, spoil=spoil, in_place=in_place)
 			assert solver.vouched_contacts() == n - len(spoil) and solver.resident_stats()[0] == 0
 			_finalize(cap, got)
 			# bodies that moved in the awake set while the manifold was recycled (src/physics_world.c:497-504 refreshes the
@@ -312,7 +318,7 @@ def test_recycled_hint_skips_the_comparison(oracle, capture_files):
 					swap = (ia[:, 0] >= 0) & (ib[:, 0] >= 0) & (np.arange(c.shape[0]) % 4 == 0)
 					ia[swap, 0], ib[swap, 0] = ib[swap, 0].copy(), ia[swap, 0].copy()
 					moved += int(swap.sum())
-			got = _step_with_hints(oracle, solver, cap, name + " moved bodies", stamp=5)
+			got = _step_with_hints(oracle, solver, cap, name + " moved bodies", stamp=5, in_place=in_place)
 			assert solver.vouched_contacts() == n - moved and solver.resident_stats()[0] == moved
 
 

@@ -138,6 +138,8 @@ INTERPOSED = {
 	"physics_world_gpu.o": ["b2World_Draw"],
 	"src_world_snapshot.o": ["b2World_GetStateHash", "b2World_Snapshot", "b2World_Restore", "b2SerializeWorld", "b2HashWorldStateDeep"],
 	"src_solver_set.o": ["b2TrySleepIsland"],
+	# ... and the two functions that change a colour's contact array between the narrow phase and the solver (recycledInPlace)
+	"src_constraint_graph.o": ["b2AddContactToGraph", "b2RemoveContactFromGraph"],
 }
 OBJCOPY = os.environ.get("OBJCOPY", "objcopy")
 
