@@ -173,7 +173,9 @@ def solver_lib() -> ctypes.CDLL:
 	lib.b2GpuSolverDeferredSync.restype = ctypes.c_int
 	lib.b2GpuSolverDeferredSync.argtypes = [ctypes.c_void_p]
 	lib.b2GpuSolverMaterializeContacts.restype = ctypes.c_int
-	lib.b2GpuSolverMaterializeContacts.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, P(StepResult)]
+	lib.b2GpuSolverMaterializeContacts.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, P(StepResult)]
+	lib.b2GpuSolverDeferredForget.restype = None
+	lib.b2GpuSolverDeferredForget.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
 	lib.b2GpuSolverDeferredDone.restype = None
 	lib.b2GpuSolverDeferredDone.argtypes = [ctypes.c_void_p]
 	lib.b2GpuHostAlloc.restype = ctypes.c_void_p
@@ -552,12 +554,14 @@ class GpuSolver:
 	def deferred_pending(self) -> bool:
 		return bool(self.lib.b2GpuSolverDeferredPending(self.handle))
 
-	def materialize(self, contact_arrays, result: StepResult = None, done: bool = True) -> int:
-		"""b2GpuSolverMaterializeContacts over byte arrays of b2ContactSim; done = nothing is pending afterwards."""
+	def materialize(self, desc: StepDesc, contact_arrays, result: StepResult = None, done: bool = True) -> int:
+		"""b2GpuSolverMaterializeContacts over the colours' byte arrays of b2ContactSim (in the descriptor's order: the active
+		colours, then the overflow colour); done = nothing is pending afterwards."""
 		total = 0
-		for arr in contact_arrays:
+		for c, arr in enumerate(contact_arrays):
 			if arr.size:
-				n = self.lib.b2GpuSolverMaterializeContacts(self.handle, arr.ctypes.data, arr.size // CONTACT_SIZE,
+				color = desc.colors[c] if c < desc.activeColorCount else desc.overflow
+				n = self.lib.b2GpuSolverMaterializeContacts(self.handle, color.colorIndex, 0, arr.ctypes.data, arr.size // CONTACT_SIZE,
 															ctypes.byref(result) if result is not None else None)
 				if n < 0:
 					raise RuntimeError("b2GpuSolverMaterializeContacts failed: " + self.lib.b2GpuGetLastError().decode())

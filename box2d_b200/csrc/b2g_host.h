@@ -189,15 +189,11 @@ struct b2gShadowImpulses
 };
 
 // ---- deferred contact impulses (b2GpuSolverSetDeferredImpulses) ----------------------------------------------------------
-// Where the record of a contact is among the outputs the host has not written into the manifolds yet: its wire slot in the
-// pending step (kDeferWide: a contact of a graph colour -- both points are stored, like b2StoreImpulsesTask does), -1 once the
-// record has been written into the manifold.  An entry counts when its stamp is the pending step's.
-struct b2gDeferEntry
-{
-	int slot;
-	uint32_t stamp;
-};
-constexpr int kDeferWide = 1 << 30;
+// A contact's record among the outputs the host has not written into the manifolds yet is found by PLACE: the contact sat at
+// (graph colour, index in the colour's array) when the pending step was solved = at a home (see b2gShadowContact), the home's
+// shadow head says which contact that was, and the record is at the colour's first slot of that step + index.  The caller
+// materializes a contact before it moves it (include/b2_gpu_solver.h), so a pending contact is still where it was.
+// consumedStamp[home] == the pending step's stamp: that record has been written into its manifold (or must not be).
 
 constexpr int kHomeColors = B2GPU_GRAPH_COLOR_COUNT;
 
@@ -321,9 +317,10 @@ struct b2GpuSolver
 	bool defer = false; // this step
 	PinnedBuffer<float4> hOutOther; // the previous step's output arena
 	bool deferPending = false;		// hOutOther holds records that some manifolds have not received
-	uint32_t deferStamp = 0;		// of the pending step's entries in deferMap
-	uint32_t deferNewStamp = 1;		// of the entries this step's pack pass writes
-	std::vector<b2gDeferEntry> deferMap; // by contact id
+	uint32_t deferStamp = 0;		// of the pending step (0: never)
+	uint32_t deferNewStamp = 1;		// of the step in flight
+	std::vector<uint32_t> consumedStamp; // by home
+	bool homesOrdered = true;		// the homes' keys are the callers' graph colour indices (they came in ascending order)
 	const float* pendingRecords = nullptr; // the pending step's impulse records, by wire slot
 	const float* prevRecords = nullptr;	   // the previous resident step's (what the device warm-starts clean contacts from)
 	cudaEvent_t evRecords = nullptr;	   // behind the last chunk of the download
@@ -440,6 +437,8 @@ constexpr size_t kDownloadQuads = 32 * 1024; // 512 KiB: the unpack pass runs th
 // b2g_wire.cu
 int b2gSendArena( b2GpuSolver* s, size_t uptoQuads );
 void b2gFlushLines( const void* ptr, size_t bytes );
+// b2g_wire.cu
+int b2gMaterializePendingFromSegs( b2GpuSolver* s, b2GpuStepResult* results );
 // b2g_solver.cu
 int b2gPollControl( b2GpuSolver* s, bool* seen );
 int b2gDeferSync( b2GpuSolver* s );

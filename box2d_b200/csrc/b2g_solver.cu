@@ -1107,6 +1107,16 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 				s->segHome[k] = key;
 				fits = fits && seg.count <= s->homeBase[key + 1] - s->homeBase[key];
 			}
+			if ( s->deferPending && ( !fits || ordered != s->homesOrdered || !s->deferEnabled ) )
+			{
+				// the homes are about to move (or to mean something else): whatever is pending is found by home, so it
+				// goes into the manifolds now -- the step's own contact arrays say where every contact is
+				if ( b2gMaterializePendingFromSegs( s, nullptr ) != 0 )
+				{
+					return 1;
+				}
+			}
+			s->homesOrdered = ordered;
 			if ( !fits )
 			{
 				int need[kHomeColors] = { 0 };
@@ -1230,20 +1240,19 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	s->cacheValid = false;
 	if ( s->defer )
 	{
-		size_t ids = d->contactIdCapacity > 0 ? (size_t)d->contactIdCapacity : 0;
-		if ( s->deferMap.size() < ids + 1 )
+		if ( s->consumedStamp.size() < (size_t)s->homeTotal + 1 )
 		{
-			s->deferMap.resize( ids + ids / 2 + 64, b2gDeferEntry{ -1, 0 } );
+			s->consumedStamp.resize( (size_t)s->homeTotal + 1, 0 );
 		}
 		s->deferNewStamp += 1;
 		if ( s->deferNewStamp == 0 )
 		{
-			// wrapped: no entry of the past may look current (nothing can be pending with stamp 0)
-			if ( s->deferPending )
+			// wrapped: no mark of the past may look current (nothing is pending with stamp 0)
+			if ( s->deferPending && b2gMaterializePendingFromSegs( s, nullptr ) != 0 )
 			{
-				return b2gFailMsg( "b2GpuSolverBeginStep: deferred impulses pending across a stamp wrap-around" );
+				return 1;
 			}
-			s->deferMap.assign( s->deferMap.size(), b2gDeferEntry{ -1, 0 } );
+			s->consumedStamp.assign( s->consumedStamp.size(), 0 );
 			s->deferNewStamp = 1;
 		}
 		// the pack pass reads the previous step's records (a contact it has no word on: are its impulses still the device's?)
@@ -1256,8 +1265,17 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	}
 	else if ( s->deferPending )
 	{
-		return b2gFailMsg( "b2GpuSolverBeginStep: the previous step's impulses are still deferred (b2GpuSolverMaterializeContacts, "
-						   "b2GpuSolverDeferredDone) and this step cannot take them over" );
+		// a step that does not defer (a batch, a plain step) after one that did: the manifolds it is about to read receive what
+		// is owed to them, found by place in the step's own arrays (single worlds; a batch's arrays are other worlds')
+		if ( worldCount != 1 )
+		{
+			return b2gFailMsg( "b2GpuSolverStepBatch: the solver's previous single-world step left impulses deferred "
+							   "(b2GpuSolverMaterializeContacts, b2GpuSolverDeferredDone)" );
+		}
+		if ( b2gMaterializePendingFromSegs( s, nullptr ) != 0 )
+		{
+			return 1;
+		}
 	}
 
 	P.rawStates = reinterpret_cast<const uint8_t*>( s->resident ? s->residentStates[0].ptr : s->wireAll.ptr + s->inStates );
@@ -1962,6 +1980,7 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 	s->traceArrivals.clear();
 	s->begun = false;
 	s->liteJointsSeen = s->jointTotal > 0 && s->heavyJoint.load( std::memory_order_relaxed ) == 0;
+	bool deferredNow = false;
 	if ( s->resident && s->ran && s->workFailed.load() == 0 )
 	{
 		// this step's outputs are the next step's resident inputs
@@ -1973,6 +1992,7 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 			s->deferPending = s->contactTotal > 0;
 			s->deferStamp = s->deferNewStamp;
 			s->recordsSynced.store( 0, std::memory_order_release );
+			deferredNow = s->deferPending;
 		}
 		std::swap( s->outAll, s->outOther );
 		std::swap( s->residentStates[0], s->residentStates[1] );
@@ -1998,6 +2018,12 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 			s->homeSlot[s->segHome[k]] = s->contactSegs[k].slotStart;
 		}
 		s->cacheValid = true;
+	}
+	if ( deferredNow && !s->homesOrdered )
+	{
+		// pending records are found by (graph colour, place); a caller whose colours do not come with ascending indices has
+		// no such address: its manifolds are written now, like a step that does not defer
+		return b2gMaterializePendingFromSegs( s, s->results );
 	}
 	return 0;
 }

@@ -115,11 +115,11 @@ void b2gFlushLines( const void* ptr, size_t bytes );
 // Deferred impulses: write the pending record `slot` into the manifold of `sim` -- what b2StoreImpulsesTask
 // (src/contact_solver.c:2293-2320: both points of a coloured contact) and b2StoreImpulses_Overflow (:526-542) would have
 // written at the end of the pending step.  Returns the record's hit-event flag.
-static inline bool b2gMaterializeRecord( const b2GpuSolver* s, uint8_t* sim, int slotAndWide )
+static inline bool b2gMaterializeRecord( const b2GpuSolver* s, uint8_t* sim, int slot, bool wide )
 {
-	const float* rec = s->pendingRecords + (size_t)( slotAndWide & ~kDeferWide ) * b2g::kImpulseFloats;
+	const float* rec = s->pendingRecords + (size_t)slot * b2g::kImpulseFloats;
 	uint8_t* manifold = sim + B2L_CONTACT_MANIFOLD;
-	int pointCount = ( slotAndWide & kDeferWide ) != 0 ? 2 : *reinterpret_cast<const int*>( manifold + B2L_MANIFOLD_POINT_COUNT );
+	int pointCount = wide ? 2 : *reinterpret_cast<const int*>( manifold + B2L_MANIFOLD_POINT_COUNT );
 	memcpy( manifold + B2L_MANIFOLD_ROLLING_IMPULSE, rec + 0, 4 );
 	for ( int j = 0; j < pointCount; ++j )
 	{
@@ -131,20 +131,54 @@ static inline bool b2gMaterializeRecord( const b2GpuSolver* s, uint8_t* sim, int
 	return hit;
 }
 
-// the pending entry of contact `id`, or nullptr (none, consumed, or of an older step)
-static inline b2gDeferEntry* b2gPendingEntry( b2GpuSolver* s, int id )
+// The contact `sim` sits at place `index` of the colour with home key `key`: if that is where it was when the pending step was
+// solved and its record has not been used yet, the record goes into its manifold.  Returns 1 (materialized) or 0; *hit = the
+// record's hit-event flag.  Concurrent calls must be for different places.
+static inline int b2gMaterializeAt( b2GpuSolver* s, int key, int index, uint8_t* sim, bool* hit )
 {
-	if ( !s->deferPending || id < 0 || (size_t)id >= s->deferMap.size() )
+	if ( index >= s->homeCount[key] )
 	{
-		return nullptr;
+		return 0; // no such place in the pending step
 	}
-	b2gDeferEntry* entry = s->deferMap.data() + id;
-	return entry->stamp == s->deferStamp && entry->slot >= 0 ? entry : nullptr;
+	const int home = s->homeBase[key] + index;
+	if ( s->consumedStamp[(size_t)home] == s->deferStamp ||
+		 s->shadowHeads[(size_t)home].contactId != *reinterpret_cast<const int*>( sim + B2L_CONTACT_ID ) )
+	{
+		return 0; // used, or another contact's place
+	}
+	*hit = b2gMaterializeRecord( s, sim, s->homeSlot[key] + index, key != kHomeColors - 1 );
+	s->consumedStamp[(size_t)home] = s->deferStamp;
+	return 1;
 }
 
-extern "C" int b2GpuSolverMaterializeContacts( b2GpuSolver* s, void* contactSims, int count, b2GpuStepResult* result )
+static inline void b2gNoteHit( b2GpuStepResult* result, const uint8_t* sim )
 {
-	if ( s == nullptr || !s->deferPending || count <= 0 )
+	if ( result != nullptr )
+	{
+		if ( result->hitEventBits != nullptr )
+		{
+			uint32_t id = (uint32_t) * reinterpret_cast<const int*>( sim + B2L_CONTACT_ID );
+			__atomic_fetch_or( result->hitEventBits + ( id >> 6 ), (uint64_t)1 << ( id & 63u ), __ATOMIC_RELAXED );
+		}
+		__atomic_store_n( &result->hasHitEvents, 1, __ATOMIC_RELAXED );
+	}
+}
+
+// home key of a caller's graph colour index (b2GpuColorDesc::colorIndex), or -1
+static inline int b2gHomeKeyOf( const b2GpuSolver* s, int colorIndex )
+{
+	return s->homesOrdered && colorIndex >= 0 && colorIndex < kHomeColors ? colorIndex : -1;
+}
+
+extern "C" int b2GpuSolverMaterializeContacts( b2GpuSolver* s, int colorIndex, int firstIndex, void* contactSims, int count,
+											   b2GpuStepResult* result )
+{
+	if ( s == nullptr || !s->deferPending || count <= 0 || firstIndex < 0 )
+	{
+		return 0;
+	}
+	const int key = b2gHomeKeyOf( s, colorIndex );
+	if ( key < 0 )
 	{
 		return 0;
 	}
@@ -157,22 +191,14 @@ extern "C" int b2GpuSolverMaterializeContacts( b2GpuSolver* s, void* contactSims
 	for ( int i = 0; i < count; ++i )
 	{
 		uint8_t* sim = sims + (size_t)i * B2L_CONTACT_SIZE;
-		const int id = *reinterpret_cast<const int*>( sim + B2L_CONTACT_ID );
-		b2gDeferEntry* entry = b2gPendingEntry( s, id );
-		if ( entry == nullptr )
+		bool hit = false;
+		if ( b2gMaterializeAt( s, key, firstIndex + i, sim, &hit ) != 0 )
 		{
-			continue;
-		}
-		bool hit = b2gMaterializeRecord( s, sim, entry->slot );
-		entry->slot = -1;
-		done += 1;
-		if ( hit && result != nullptr )
-		{
-			if ( result->hitEventBits != nullptr )
+			done += 1;
+			if ( hit )
 			{
-				__atomic_fetch_or( result->hitEventBits + ( (uint32_t)id >> 6 ), (uint64_t)1 << ( (uint32_t)id & 63u ), __ATOMIC_RELAXED );
+				b2gNoteHit( result, sim );
 			}
-			__atomic_store_n( &result->hasHitEvents, 1, __ATOMIC_RELAXED );
 		}
 	}
 	if ( done > 0 )
@@ -180,6 +206,58 @@ extern "C" int b2GpuSolverMaterializeContacts( b2GpuSolver* s, void* contactSims
 		s->materialized.fetch_add( done, std::memory_order_relaxed );
 	}
 	return done;
+}
+
+extern "C" void b2GpuSolverDeferredForget( b2GpuSolver* s, int colorIndex, int index )
+{
+	if ( s == nullptr || !s->deferPending || index < 0 )
+	{
+		return;
+	}
+	const int key = b2gHomeKeyOf( s, colorIndex );
+	if ( key >= 0 && index < s->homeCount[key] )
+	{
+		s->consumedStamp[(size_t)( s->homeBase[key] + index )] = s->deferStamp;
+	}
+}
+
+// every pending record goes into its manifold, the contacts found in the arrays of the step that is being laid out (or has
+// just ended): s->contactSegs
+int b2gMaterializePendingFromSegs( b2GpuSolver* s, b2GpuStepResult* results )
+{
+	if ( !s->deferPending )
+	{
+		return 0;
+	}
+	if ( b2gDeferSync( s ) != 0 )
+	{
+		return 1;
+	}
+	int done = 0;
+	for ( const b2gContactSeg& seg : s->contactSegs )
+	{
+		const int key = seg.wide ? b2gHomeKeyOf( s, seg.colorIndex ) : kHomeColors - 1;
+		if ( key < 0 || ( seg.wide && key == kHomeColors - 1 ) )
+		{
+			continue;
+		}
+		for ( int i = 0; i < seg.count; ++i )
+		{
+			bool hit = false;
+			uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
+			if ( b2gMaterializeAt( s, key, i, sim, &hit ) != 0 )
+			{
+				done += 1;
+				if ( hit )
+				{
+					b2gNoteHit( results, sim );
+				}
+			}
+		}
+	}
+	s->materialized.fetch_add( done, std::memory_order_relaxed );
+	s->deferPending = false;
+	return 0;
 }
 
 static const int kPackPrefetch = []() {
@@ -264,10 +342,7 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		float4* wireMass = base + s->inMass;
 		const bool resident = s->resident;
 		const bool usable = s->cacheUsable;
-		const bool defer = s->defer;
-		b2gDeferEntry* const deferMap = s->deferMap.data();
-		const size_t deferIds = s->deferMap.size();
-		const uint32_t deferNewStamp = s->deferNewStamp;
+		const bool pending = s->defer && s->deferPending;
 		int materialized = 0;
 		b2gStreamChunk full = { &s->fullCursor, s->fullCapacity, 0, 0, &s->streamOverflow };
 		bool massDiffers = false;
@@ -328,12 +403,6 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 						{
 							vouched[j - group] = true;
 							ownBits = head.ownBits;
-							if ( defer && j >= local && j < localEnd && (size_t)id < deferIds )
-							{
-								// its record of THIS step is the one a later reader of the manifold needs (the one of the
-								// previous step, if it is still pending, is superseded: the device has it)
-								deferMap[id] = b2gDeferEntry{ ( seg.slotStart + j ) | ( seg.wide ? kDeferWide : 0 ), deferNewStamp };
-							}
 						}
 					}
 					if ( ownBits < 0 )
@@ -355,21 +424,12 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 						continue;
 					}
 					const uint8_t* sim = seg.sims + (size_t)i * B2L_CONTACT_SIZE;
-					if ( defer )
+					if ( pending )
 					{
 						// a contact nobody vouches for is read in full below: if the previous step's impulses never reached
-						// its manifold (nothing has read it since), they do now; then its record of this step is entered
-						const int id = b2gRdI( sim, B2L_CONTACT_ID );
-						b2gDeferEntry* pending = b2gPendingEntry( s, id );
-						if ( pending != nullptr )
-						{
-							b2gMaterializeRecord( s, seg.sims + (size_t)i * B2L_CONTACT_SIZE, pending->slot );
-							materialized += 1;
-						}
-						if ( (size_t)id < deferIds )
-						{
-							deferMap[id] = b2gDeferEntry{ slot | ( seg.wide ? kDeferWide : 0 ), deferNewStamp };
-						}
+						// its manifold (nothing has read it since), they do now
+						bool hit = false;
+						materialized += b2gMaterializeAt( s, homeKey, i, seg.sims + (size_t)i * B2L_CONTACT_SIZE, &hit );
 					}
 					const uint8_t* m = sim + B2L_CONTACT_MANIFOLD;
 					const uint8_t* p0 = m + B2L_MANIFOLD_POINTS;
@@ -427,7 +487,7 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 					b2gShadowHead& head = s->shadowHeads[(size_t)home];
 					int ref = homeSlot + i; // its record among the previous step's outputs
 					bool clean = i < homeCount && head.contactId == id && memcmp( shadow.rows, rows, sizeof( rows ) ) == 0;
-					if ( clean && defer )
+					if ( clean && s->defer )
 					{
 						// the impulses in the manifold against what the device computed last (rollingImpulse, normalImpulse1,
 						// tangentImpulse1, ..., normalImpulse2, tangentImpulse2: b2g::ImpulseRecord) -- the unpack pass keeps no shadow

@@ -414,12 +414,26 @@ void b2GpuSeam_ContactRecycled( b2World* world, int contactIndex, const b2Contac
  * puts in front of the reference's (tools/buildlib.py renames the reference's definitions to b2Ref_*; the reference's
  * sources are not touched).  The many_pyramids step loses its 3 MB download and the unpack pass over 58 000 manifolds from
  * the critical path. */
-void b2GpuSeam_ContactReevaluated( b2World* world, b2ContactSim* contactSim )
+void b2GpuSeam_ContactReevaluated( b2World* world, int contactIndex, b2ContactSim* contactSim )
 {
 	b2SeamSlot* slot = s_slots + world->worldId;
-	if ( slot->solver != NULL && b2GpuSolverMaterializeContacts( slot->solver, contactSim, 1, NULL ) < 0 )
+	if ( slot->solver == NULL || b2GpuSolverDeferredPending( slot->solver ) == 0 )
 	{
-		b2SeamFatal( "b2GpuSolverMaterializeContacts" );
+		return;
+	}
+	// contactIndex -> (graph colour, place): b2Collide laid the colours' arrays end to end (b2GpuSeam_BeginCollide); what
+	// follows them are the awake set's non-touching contacts, which no step has solved
+	for ( int i = 0; i < B2_GRAPH_COLOR_COUNT; ++i )
+	{
+		int j = contactIndex - slot->collideStart[i];
+		if ( 0 <= j && j < slot->collideCount[i] )
+		{
+			if ( b2GpuSolverMaterializeContacts( slot->solver, i, j, contactSim, 1, NULL ) < 0 )
+			{
+				b2SeamFatal( "b2GpuSolverMaterializeContacts" );
+			}
+			return;
+		}
 	}
 }
 
@@ -439,7 +453,7 @@ static void b2SeamFlushImpulses( b2World* world, b2GpuStepResult* result )
 	{
 		b2GraphColor* color = world->constraintGraph.colors + i;
 		if ( color->contactSims.count > 0 &&
-			 b2GpuSolverMaterializeContacts( slot->solver, color->contactSims.data, color->contactSims.count, result ) < 0 )
+			 b2GpuSolverMaterializeContacts( slot->solver, i, 0, color->contactSims.data, color->contactSims.count, result ) < 0 )
 		{
 			b2SeamFatal( "b2GpuSolverMaterializeContacts" );
 		}
@@ -579,7 +593,22 @@ void b2RemoveContactFromGraph( b2World* world, int bodyIdA, int bodyIdB, int col
 {
 	if ( 0 <= colorIndex && colorIndex < B2_GRAPH_COLOR_COUNT )
 	{
-		s_slots[world->worldId].colorTouched[colorIndex] = true;
+		b2SeamSlot* slot = s_slots + world->worldId;
+		slot->colorTouched[colorIndex] = true;
+		if ( slot->solver != NULL && slot->generation == world->generation && b2GpuSolverDeferredPending( slot->solver ) != 0 )
+		{
+			// deferred impulses are found by place: the colour's LAST contact is about to move into the place of the one that
+			// leaves (b2Array_RemoveSwap, src/constraint_graph.c:198-211) -- it receives its impulses first; the record of the
+			// one that leaves is void (it stopped touching, or is being destroyed)
+			b2GraphColor* color = world->constraintGraph.colors + colorIndex;
+			int last = color->contactSims.count - 1;
+			if ( last >= 0 && last != localIndex &&
+				 b2GpuSolverMaterializeContacts( slot->solver, colorIndex, last, color->contactSims.data + last, 1, NULL ) < 0 )
+			{
+				b2SeamFatal( "b2GpuSolverMaterializeContacts" );
+			}
+			b2GpuSolverDeferredForget( slot->solver, colorIndex, localIndex );
+		}
 	}
 	b2Ref_RemoveContactFromGraph( world, bodyIdA, bodyIdB, colorIndex, localIndex );
 }

@@ -250,18 +250,26 @@ B2GPU_API int b2GpuSolverUnpackWork( b2GpuSolver* solver, int pump );
  * impulses (normalImpulse, tangentImpulse, totalNormalImpulse, normalVelocity, rollingImpulse) or moves it out of the
  * awake contact arrays for good: the narrow phase before it re-evaluates the manifold (src/contact.c:523), island sleep
  * (src/solver_set.c:155), the contact-data and snapshot API, hit events (b2GpuStepResult::hasHitEvents is then set from
- * the device's flag and the bits are set by the materialize call).  Contacts are identified by b2ContactSim::contactId, so
- * they may have moved in their arrays in the meantime.  The pack pass of the next step materializes whatever it has to read
- * in full itself.  Must be set before the first step (or between steps with nothing pending); off by default. */
+ * the device's flag and the bits are set by the materialize call).  The pack pass of the next step materializes whatever it
+ * has to read in full itself.  Must be set before the first step (or between steps with nothing pending); off by default. */
 B2GPU_API int b2GpuSolverSetDeferredImpulses( b2GpuSolver* solver, int enabled );
 /* 1 while some manifolds may not have received the last step's impulses */
 B2GPU_API int b2GpuSolverDeferredPending( const b2GpuSolver* solver );
 /* Waits for the tail of the last step's download (otherwise the first materialize call does); 0 on success. */
 B2GPU_API int b2GpuSolverDeferredSync( b2GpuSolver* solver );
-/* Writes the pending impulses of `count` consecutive b2ContactSim into their manifolds (those that have some pending) and,
- * with `result`, ORs their hit-event bits into result->hitEventBits.  May be called concurrently on different contacts.
- * Returns the number of manifolds written, -1 on a device error. */
-B2GPU_API int b2GpuSolverMaterializeContacts( b2GpuSolver* solver, void* contactSims, int count, b2GpuStepResult* result );
+/* Writes the pending impulses of `count` consecutive b2ContactSim -- the contacts at places firstIndex .. of the colour whose
+ * b2GpuColorDesc::colorIndex was `colorIndex` (the overflow colour: B2GPU_GRAPH_COLOR_COUNT - 1) -- into their manifolds,
+ * those that have some pending, and with `result` ORs their hit-event bits into result->hitEventBits.  A pending record is
+ * found by PLACE: the contact must still be where it was when the step was solved (the library checks the contact id and
+ * skips a contact that is not), so the caller materializes a contact BEFORE it moves it in its colour's array (the last
+ * contact of a colour before a swap-remove, src/constraint_graph.c:198-211) and calls b2GpuSolverDeferredForget for a place
+ * whose contact leaves the array.  May be called concurrently for different places.  Needs the colours' indices to be
+ * ascending (what the reference produces); otherwise nothing is deferred.  Returns the number of manifolds written, -1 on a
+ * device error. */
+B2GPU_API int b2GpuSolverMaterializeContacts( b2GpuSolver* solver, int colorIndex, int firstIndex, void* contactSims, int count,
+											   b2GpuStepResult* result );
+/* The contact at this place is leaving its colour's array (it stopped touching, or is destroyed): its record is void. */
+B2GPU_API void b2GpuSolverDeferredForget( b2GpuSolver* solver, int colorIndex, int index );
 /* Every manifold that matters has been materialized (or the host's contacts were replaced wholesale): nothing is pending. */
 B2GPU_API void b2GpuSolverDeferredDone( b2GpuSolver* solver );
 

@@ -154,7 +154,7 @@ def test_c_abi_chain_of_steps_with_stale_manifolds(oracle, capture_files, name):
 				assert solver.deferred_pending()
 			if step == 3:
 				# somebody reads the manifolds in the middle of the run
-				solver.materialize(got["contacts"], r)
+				solver.materialize(d, got["contacts"], r)
 				for a, b in zip(got["contacts"], want["contacts"]):
 					assert np.array_equal(a, b), f"step {step}: contact sims after materialize"
 				assert np.array_equal(got["hit"], want["hit"])
@@ -171,6 +171,6 @@ def test_c_abi_chain_of_steps_with_stale_manifolds(oracle, capture_files, name):
 		d0, r0, want = cap_o.make_call()
 		d, r, got = cap_g.make_call()
 		# (make_call copied the inputs: materialize into the copies the last step's descriptor would have pointed at)
-		assert solver.materialize(got["contacts"]) == cap_g.contact_count
+		assert solver.materialize(d, got["contacts"]) == cap_g.contact_count
 		for a, b in zip(got["contacts"], want["contacts"]):
 			assert np.array_equal(a, b), "contact sims at the end of the chain"
