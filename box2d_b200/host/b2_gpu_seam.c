@@ -283,8 +283,15 @@ static void b2SeamTeamLabels( b2SeamTeam* team )
 		int begin = block * B2_SEAM_LABEL_BLOCK;
 		int end = begin + B2_SEAM_LABEL_BLOCK < team->labelCount ? begin + B2_SEAM_LABEL_BLOCK : team->labelCount;
 		// label = index of the body's island among the awake islands (b2Island::localIndex, src/island.h:49-74)
+		// (two dependent look-ups per body, the first one all over world->bodies: the body records of the bodies a few
+		// places ahead are asked for early)
+		const int ahead = 12;
 		for ( int i = begin; i < end; ++i )
 		{
+			if ( i + ahead < end )
+			{
+				__builtin_prefetch( &bodies[team->sims[i + ahead].bodyId].islandId, 0, 1 );
+			}
 			int islandId = bodies[team->sims[i].bodyId].islandId;
 			team->labels[i] = islandId == B2_NULL_INDEX ? -1 : islands[islandId].localIndex;
 		}
@@ -887,6 +894,14 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 	int helperCount = world->workerCount - 1;
 	int useful = itemEstimate / 2048; /* a helper that wakes up for less than that only costs */
 	helperCount = helperCount < useful ? helperCount : useful;
+	{
+		static int maxHelpers = -2;
+		if ( maxHelpers == -2 )
+		{
+			maxHelpers = b2SeamEnvInt( "B2GPU_SEAM_HELPERS", -1 );
+		}
+		helperCount = maxHelpers >= 0 && helperCount > maxHelpers ? maxHelpers : helperCount;
+	}
 	int enqueued = 0;
 	for ( int i = 0; i < helperCount && world->taskCount < B2_MAX_TASKS; ++i )
 	{
