@@ -18,11 +18,12 @@ timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gI
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gScatterKernel -c 1 -s 12 -o $O/${R}_scatter -f python bench.py --steps 3 --warmup 3 $Q > $O/${R}_ncu_scatter.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gPartitionKernel -c 1 -s 8 -o $O/${R}_partition -f python bench.py --workload large_pyramid --steps 3 --warmup 3 $Q > $O/${R}_ncu_partition.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gClusterIslandKernel -c 1 -s 8 -o $O/${R}_cluster -f python bench.py --workload large_pyramid --steps 3 --warmup 3 $Q > $O/${R}_ncu_cluster.log 2>&1
-timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gStepKernel -c 1 -s 8 -o $O/${R}_grid -f python bench.py --workload joint_grid --steps 3 --warmup 3 $Q > $O/${R}_ncu_grid.log 2>&1
+B2GPU_LITE_JOINTS=0 timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gStepKernel -c 1 -s 8 -o $O/${R}_grid -f python bench.py --workload joint_grid --steps 3 --warmup 3 $Q > $O/${R}_ncu_grid.log 2>&1
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gClusterIslandKernel -c 1 -s 8 -o $O/${R}_cluster_joints -f python bench.py --workload joint_grid --steps 3 --warmup 3 $Q > $O/${R}_ncu_cluster_joints.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none -k regex:b2gAssembleJointsKernel -c 1 -s 8 -o $O/${R}_assemble -f python bench.py --workload joint_grid --steps 3 --warmup 3 $Q > $O/${R}_ncu_assemble.log 2>&1
 timeout 300 ncu --set full --import-source on --clock-control none --profile-from-start off -k regex:b2gIslandKernel -c 1 -o $O/${R}_island_batch -f python bench.py --workload batch --steps 2 --warmup 3 > $O/${R}_ncu_island_batch.log 2>&1
 # gpurun brings back at most 64 MiB: keep the raw-metrics page of every capture, and only the island kernel's report itself
-for n in scatter partition cluster grid assemble island_batch island; do
+for n in scatter partition cluster cluster_joints grid assemble island_batch island; do
   [ -f $O/${R}_$n.ncu-rep ] && ncu -i $O/${R}_$n.ncu-rep --page raw --csv > $O/${R}_$n.rawpage.csv 2>/dev/null
   [ $n != island ] && rm -f $O/${R}_$n.ncu-rep
 done

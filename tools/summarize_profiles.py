@@ -110,7 +110,8 @@ def main() -> None:
 	for name, note in (("island", "many_pyramids, one block per bin"), ("scatter", "many_pyramids, single-pass partition for one block per bin"),
 					   ("partition", "large_pyramid, two-phase partition for a cluster with owner lists"),
 					   ("cluster", "large_pyramid, one 16-block cluster for the single island"),
-					   ("grid", "joint_grid, grid-barrier kernel: the island does not fit any cluster"),
+					   ("grid", "joint_grid with B2GPU_LITE_JOINTS=0, grid-barrier kernel: with 256-byte joint records the island fits no cluster"),
+					   ("cluster_joints", "joint_grid, one 16-block cluster: 19 800 plain revolute joints as 27-word records"),
 					   ("assemble", "joint_grid, resident mode: the step's joint records from the table, the previous outputs and the uploaded runs"),
 					   ("island_batch", "batch of 8192 small_pyramid worlds")):
 		kernel_summary(rnd, name, note)
