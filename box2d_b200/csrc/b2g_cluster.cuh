@@ -267,7 +267,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	__syncthreads();
 	if ( V.jointLite != 0 )
 	{
-		forEachLocal( jointCount, [&]( int k ) { loadJointSlot( P, V, jointSlot( k ), jointIndexOf[k] ); } );
+		loadLiteRevolutes( P, V, jointCount, jointSlot, [&]( int k ) { return jointIndexOf[k]; } );
 	}
 	else
 	{

@@ -1332,9 +1332,9 @@ B2G_DEV void storeJointImpulses( const StepParams& P, int jointIndex, const b2lJ
 // A revolute joint without spring, motor and limit -- a hinge: chains, bridges, rag-doll-less rope, the joint_grid
 // benchmark -- only ever runs the point-to-point part of b2SolveRevoluteJoint (src/revolute_joint.c:443-487) and the warm
 // start (:283-315).  Of its 252-byte b2JointSim those two read 25 floats; when every joint of a step is such a hinge the
-// island / cluster kernels keep just those (27 words with the two constants below), so an island of 20 000 joints fits
-// the shared memory of one 16-block cluster instead of falling back to the grid-barrier kernel.  The arithmetic is the
-// full path's, operation for operation (the disabled sub-constraints contribute nothing but the constants).
+// cluster kernel keeps just those (31 words with what the event test and the output record need), so an island of 20 000
+// joints fits the shared memory of one 16-block cluster instead of falling back to the grid-barrier kernel.  The
+// arithmetic is the full path's, operation for operation (the disabled sub-constraints contribute nothing but constants).
 enum LiteRevolute
 {
 	LR_INV_MASS_A = 0,
@@ -1344,7 +1344,7 @@ enum LiteRevolute
 	LR_BIAS_RATE = 4, // constraintSoftness
 	LR_MASS_SCALE = 5,
 	LR_IMPULSE_SCALE = 6,
-	LR_JOINT_ID = 7, // int, with the world's bit base added
+	LR_JOINT_ID = 7,  // int
 	LR_IMPULSE_X = 8, // linearImpulse (mutable)
 	LR_IMPULSE_Y = 9,
 	LR_INDEX_A = 10, // int, the view's numbering, -1 = static
@@ -1354,13 +1354,16 @@ enum LiteRevolute
 	LR_DELTA_CENTER = 20,
 	LR_FORCE_THRESHOLD = 22,
 	LR_TORQUE_THRESHOLD = 23,
-	// springImpulse + motorImpulse + lowerImpulse - upperImpulse: whatever the disabled sub-constraints accumulated while
-	// they were enabled still takes part in the warm start (src/revolute_joint.c:296), and nothing changes it during the step
-	LR_AXIAL_IMPULSE = 24,
-	LR_EVENT_ANGULAR = 25, // |motorImpulse + lowerImpulse - upperImpulse| of b2GetJointReaction (src/joint.c:1040-1046)
-	LR_RESERVED = 26
+	// whatever the disabled sub-constraints accumulated while they were enabled still takes part in the warm start
+	// (src/revolute_joint.c:296) and in the joint's reaction torque (src/joint.c:1040-1046); nothing changes it during the step
+	LR_SPRING_IMPULSE = 24,
+	LR_MOTOR_IMPULSE = 25,
+	LR_LOWER_IMPULSE = 26,
+	LR_UPPER_IMPULSE = 27,
+	LR_BIT_BASE = 28, // int: the world's first bit in the joint-event bit set (the record's padding word)
+	LR_RESERVED = 29  // .. 30: an odd number of words per record (b2g_types.cuh)
 };
-static_assert( LR_RESERVED + 1 == kLiteJointWords, "LiteRevolute layout" );
+static_assert( LR_RESERVED + 2 == kLiteJointWords, "LiteRevolute layout" );
 
 B2G_DEV bool isLiteRevolute( const b2lJointSim* joint )
 {
@@ -1373,38 +1376,76 @@ B2G_DEV float* liteJointAt( const SolveView& V, int index )
 	return reinterpret_cast<float*>( V.joints ) + (size_t)index * kLiteJointWords;
 }
 
-// the full record (global memory) -> the compact one; the body indices stay as they are (the caller renumbers them)
-B2G_DEV void loadLiteRevolute( float* lite, const b2lJointSim* joint )
+// word w of the 64-word joint record (kJointStride bytes) -> its place in a LiteRevolute, or -1
+struct LiteRevoluteMap
 {
-	const b2lRevolute* j = &joint->u.revolute;
-	lite[LR_INV_MASS_A] = joint->invMassA;
-	lite[LR_INV_MASS_B] = joint->invMassB;
-	lite[LR_INV_I_A] = joint->invIA;
-	lite[LR_INV_I_B] = joint->invIB;
-	lite[LR_BIAS_RATE] = joint->constraintSoftness.biasRate;
-	lite[LR_MASS_SCALE] = joint->constraintSoftness.massScale;
-	lite[LR_IMPULSE_SCALE] = joint->constraintSoftness.impulseScale;
-	int bitBase = *reinterpret_cast<const int*>( reinterpret_cast<const uint8_t*>( joint ) + B2L_JOINT_SIZE );
-	lite[LR_JOINT_ID] = __int_as_float( joint->jointId + bitBase );
-	lite[LR_IMPULSE_X] = j->linearImpulse.x;
-	lite[LR_IMPULSE_Y] = j->linearImpulse.y;
-	lite[LR_INDEX_A] = __int_as_float( j->indexA );
-	lite[LR_INDEX_B] = __int_as_float( j->indexB );
-	lite[LR_FRAME_A + 0] = j->frameA.p.x;
-	lite[LR_FRAME_A + 1] = j->frameA.p.y;
-	lite[LR_FRAME_A + 2] = j->frameA.q.c;
-	lite[LR_FRAME_A + 3] = j->frameA.q.s;
-	lite[LR_FRAME_B + 0] = j->frameB.p.x;
-	lite[LR_FRAME_B + 1] = j->frameB.p.y;
-	lite[LR_FRAME_B + 2] = j->frameB.q.c;
-	lite[LR_FRAME_B + 3] = j->frameB.q.s;
-	lite[LR_DELTA_CENTER + 0] = j->deltaCenter.x;
-	lite[LR_DELTA_CENTER + 1] = j->deltaCenter.y;
-	lite[LR_FORCE_THRESHOLD] = joint->forceThreshold;
-	lite[LR_TORQUE_THRESHOLD] = joint->torqueThreshold;
-	lite[LR_AXIAL_IMPULSE] = j->springImpulse + j->motorImpulse + j->lowerImpulse - j->upperImpulse;
-	lite[LR_EVENT_ANGULAR] = absf_( j->motorImpulse + j->lowerImpulse - j->upperImpulse );
-	lite[LR_RESERVED] = 0.0f;
+	signed char liteOf[kJointStride / 4];
+};
+
+__host__ __device__ constexpr LiteRevoluteMap makeLiteRevoluteMap()
+{
+	LiteRevoluteMap m{};
+	for ( int i = 0; i < kJointStride / 4; ++i )
+	{
+		m.liteOf[i] = -1;
+	}
+	m.liteOf[offsetof( b2lJointSim, invMassA ) / 4] = LR_INV_MASS_A;
+	m.liteOf[offsetof( b2lJointSim, invMassB ) / 4] = LR_INV_MASS_B;
+	m.liteOf[offsetof( b2lJointSim, invIA ) / 4] = LR_INV_I_A;
+	m.liteOf[offsetof( b2lJointSim, invIB ) / 4] = LR_INV_I_B;
+	m.liteOf[offsetof( b2lJointSim, constraintSoftness.biasRate ) / 4] = LR_BIAS_RATE;
+	m.liteOf[offsetof( b2lJointSim, constraintSoftness.massScale ) / 4] = LR_MASS_SCALE;
+	m.liteOf[offsetof( b2lJointSim, constraintSoftness.impulseScale ) / 4] = LR_IMPULSE_SCALE;
+	m.liteOf[offsetof( b2lJointSim, jointId ) / 4] = LR_JOINT_ID;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.linearImpulse.x ) / 4] = LR_IMPULSE_X;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.linearImpulse.y ) / 4] = LR_IMPULSE_Y;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.indexA ) / 4] = LR_INDEX_A;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.indexB ) / 4] = LR_INDEX_B;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.frameA.p.x ) / 4] = LR_FRAME_A + 0;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.frameA.p.y ) / 4] = LR_FRAME_A + 1;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.frameA.q.c ) / 4] = LR_FRAME_A + 2;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.frameA.q.s ) / 4] = LR_FRAME_A + 3;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.frameB.p.x ) / 4] = LR_FRAME_B + 0;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.frameB.p.y ) / 4] = LR_FRAME_B + 1;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.frameB.q.c ) / 4] = LR_FRAME_B + 2;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.frameB.q.s ) / 4] = LR_FRAME_B + 3;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.deltaCenter.x ) / 4] = LR_DELTA_CENTER + 0;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.deltaCenter.y ) / 4] = LR_DELTA_CENTER + 1;
+	m.liteOf[offsetof( b2lJointSim, forceThreshold ) / 4] = LR_FORCE_THRESHOLD;
+	m.liteOf[offsetof( b2lJointSim, torqueThreshold ) / 4] = LR_TORQUE_THRESHOLD;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.springImpulse ) / 4] = LR_SPRING_IMPULSE;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.motorImpulse ) / 4] = LR_MOTOR_IMPULSE;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.lowerImpulse ) / 4] = LR_LOWER_IMPULSE;
+	m.liteOf[offsetof( b2lJointSim, u.revolute.upperImpulse ) / 4] = LR_UPPER_IMPULSE;
+	m.liteOf[B2L_JOINT_SIZE / 4] = LR_BIT_BASE;
+	return m;
+}
+
+// The full records (global memory) -> the compact ones of a view, by 16 lanes per joint: lane q reads quad q of the 256-byte
+// record -- one coalesced 256-byte request per joint instead of 25 scattered 4-byte loads per thread (measured on joint_grid:
+// the scattered form took 41 of the step's 197 us) -- and puts the words of it that a LiteRevolute keeps in their places.
+// slotOf( k ) = the view's slot of local joint k, recordOf( k ) = its index among the step's joints.  The body indices stay
+// the step's (the caller renumbers them).
+template <typename SlotOf, typename RecordOf>
+B2G_DEV void loadLiteRevolutes( const StepParams& P, const SolveView& V, int jointCount, SlotOf slotOf, RecordOf recordOf )
+{
+	static constexpr LiteRevoluteMap map = makeLiteRevoluteMap();
+	const int quad = (int)threadIdx.x & 15;
+	for ( int k = (int)threadIdx.x >> 4; k < jointCount; k += (int)blockDim.x >> 4 )
+	{
+		const float4 q = reinterpret_cast<const float4*>( P.rawJoints + (size_t)recordOf( k ) * kJointStride )[quad];
+		float* lite = liteJointAt( V, slotOf( k ) );
+		const float words[4] = { q.x, q.y, q.z, q.w };
+#pragma unroll
+		for ( int c = 0; c < 4; ++c )
+		{
+			const int place = map.liteOf[4 * quad + c];
+			if ( place >= 0 )
+			{
+				lite[place] = words[c];
+			}
+		}
+	}
 }
 
 // b2WarmStartRevoluteJoint, src/revolute_joint.c:283-315
@@ -1413,7 +1454,7 @@ B2G_DEV void warmStartRevoluteLite( const SolveView& V, const float* lite )
 	JointBodies jb = gatherJointBodies( V, __float_as_int( lite[LR_INDEX_A] ), __float_as_int( lite[LR_INDEX_B] ) );
 	V2 rA = rotate( deltaRot( jb.pA ), v2( lite[LR_FRAME_A + 0], lite[LR_FRAME_A + 1] ) );
 	V2 rB = rotate( deltaRot( jb.pB ), v2( lite[LR_FRAME_B + 0], lite[LR_FRAME_B + 1] ) );
-	float axialImpulse = lite[LR_AXIAL_IMPULSE];
+	float axialImpulse = lite[LR_SPRING_IMPULSE] + lite[LR_MOTOR_IMPULSE] + lite[LR_LOWER_IMPULSE] - lite[LR_UPPER_IMPULSE];
 	V2 L = v2( lite[LR_IMPULSE_X], lite[LR_IMPULSE_Y] );
 	applyWarmStart( V, jb, lite[LR_INV_MASS_A], lite[LR_INV_I_A], lite[LR_INV_MASS_B], lite[LR_INV_I_B], L, cross( rA, L ) + axialImpulse,
 					cross( rB, L ) + axialImpulse );
@@ -1480,26 +1521,26 @@ B2G_DEV void jointEventTestLite( const StepParams& P, const float* lite )
 	}
 	float linearImpulse = length( v2( lite[LR_IMPULSE_X], lite[LR_IMPULSE_Y] ) );
 	float force = linearImpulse * P.inv_h;
-	float torque = lite[LR_EVENT_ANGULAR] * P.inv_h;
+	// b2GetJointReaction, src/joint.c:1040-1046
+	float torque = absf_( lite[LR_MOTOR_IMPULSE] + lite[LR_LOWER_IMPULSE] - lite[LR_UPPER_IMPULSE] ) * P.inv_h;
 	if ( force >= forceThreshold || torque >= torqueThreshold )
 	{
-		unsigned id = (unsigned)__float_as_int( lite[LR_JOINT_ID] );
+		unsigned id = (unsigned)( __float_as_int( lite[LR_JOINT_ID] ) + __float_as_int( lite[LR_BIT_BASE] ) );
 		atomicOr( P.jointBits + ( id >> 5 ), 1u << ( id & 31u ) );
 	}
 }
 
 // the output record of a LiteRevolute joint: its linearImpulse, and the four accumulated impulses of the disabled
-// sub-constraints exactly as they came in (`pristine` is the record as uploaded)
-B2G_DEV void storeJointImpulsesLite( const StepParams& P, int jointIndex, const float* lite, const b2lJointSim* pristine )
+// sub-constraints exactly as they came in
+B2G_DEV void storeJointImpulsesLite( const StepParams& P, int jointIndex, const float* lite )
 {
 	float* out = P.outJoints + (size_t)jointIndex * B2L_JOINT_OUT_FLOATS;
-	const b2lRevolute* j = &pristine->u.revolute;
 	out[0] = lite[LR_IMPULSE_X];
 	out[1] = lite[LR_IMPULSE_Y];
-	out[2] = j->springImpulse;
-	out[3] = j->motorImpulse;
-	out[4] = j->lowerImpulse;
-	out[5] = j->upperImpulse;
+	out[2] = lite[LR_SPRING_IMPULSE];
+	out[3] = lite[LR_MOTOR_IMPULSE];
+	out[4] = lite[LR_LOWER_IMPULSE];
+	out[5] = lite[LR_UPPER_IMPULSE];
 }
 
 // ---- dispatch (src/joint.c:1454-1540) ----------------------------------------------------------------------------

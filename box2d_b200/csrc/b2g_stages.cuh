@@ -245,24 +245,6 @@ B2G_DEV size_t jointBytesOf( bool lite )
 	return lite ? (size_t)kLiteJointWords * sizeof( float ) : (size_t)kJointStride;
 }
 
-// slot k of the view <- joint j of the step (P.rawJoints); the body indices are still the step's
-B2G_DEV void loadJointSlot( const StepParams& P, const SolveView& V, int k, int j )
-{
-	const b2lJointSim* record = reinterpret_cast<const b2lJointSim*>( P.rawJoints + (size_t)j * kJointStride );
-	if ( V.jointLite != 0 )
-	{
-		loadLiteRevolute( liteJointAt( V, k ), record );
-		return;
-	}
-	const float4* src = reinterpret_cast<const float4*>( record );
-	float4* dst = reinterpret_cast<float4*>( V.joints + (size_t)k * kJointStride );
-#pragma unroll
-	for ( int q = 0; q < kJointStride / 16; ++q )
-	{
-		dst[q] = src[q];
-	}
-}
-
 // the two bodies of the joint in slot k (-1 = static); false for a filter joint (no solver data)
 B2G_DEV bool jointSlotBodies( const SolveView& V, int k, int& a, int& b )
 {
@@ -346,7 +328,7 @@ B2G_DEV void storeJointSlot( const StepParams& P, const SolveView& V, int jointI
 {
 	if ( V.jointLite != 0 )
 	{
-		storeJointImpulsesLite( P, jointIndex, liteJointAt( V, k ), reinterpret_cast<const b2lJointSim*>( P.rawJoints + (size_t)jointIndex * kJointStride ) );
+		storeJointImpulsesLite( P, jointIndex, liteJointAt( V, k ) );
 	}
 	else
 	{

@@ -97,9 +97,9 @@ struct ColorRange
 constexpr int kMaxColors = 23;
 constexpr int kJointStride = 256; // b2JointSim (252 B) padded to 16-byte multiples on the wire and in the working copy
 // A plain revolute joint (no spring, motor or limit) as the island / cluster kernels keep it in shared memory when EVERY
-// joint of the step is one (b2g_joint.cuh, LiteRevolute): 27 floats instead of 64.  An odd number of words, so that a
+// joint of the step is one (b2g_joint.cuh, LiteRevolute): 31 floats instead of 64.  An odd number of words, so that a
 // warp's accesses to one field of 32 consecutive records hit 32 different banks.
-constexpr int kLiteJointWords = 27;
+constexpr int kLiteJointWords = 31;
 constexpr int kStageTimerCount = 8;
 
 // Per-contact output record copied back to the host and scattered into b2Manifold

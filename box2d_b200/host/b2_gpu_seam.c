@@ -55,6 +55,9 @@ typedef struct b2SeamSlot
 	uint32_t recycledStamp;
 	int collideStart[B2_GRAPH_COLOR_COUNT], collideCount[B2_GRAPH_COLOR_COUNT];
 	bool colorTouched[B2_GRAPH_COLOR_COUNT]; /* a contact was added to / removed from the colour since the narrow phase began */
+	int collideTotal;						 /* contacts of all colours (b2Collide's flat array goes on with the non-touching ones) */
+	bool impulsesPending;					 /* b2GpuSolverDeferredPending when the narrow phase began */
+	int collideCursor[B2_MAX_WORKERS][16];	 /* per narrow-phase worker (a cache line each): the colour of its previous contact */
 	int collidesSinceSolve;
 	bool islandsCaptured; /* b2GpuSeam_BeforeIslandSplit filled the hint of the step in flight */
 	int capturedIslandCount;
@@ -387,6 +390,9 @@ void b2GpuSeam_BeginCollide( b2World* world, b2StepContext* context, int contact
 		slot->colorTouched[i] = false;
 		start += slot->collideCount[i];
 	}
+	slot->collideTotal = start;
+	memset( slot->collideCursor, 0, sizeof( slot->collideCursor ) );
+	slot->impulsesPending = slot->solver != NULL && b2GpuSolverDeferredPending( slot->solver ) != 0;
 	slot->collidesSinceSolve += 1;
 	// the narrow phase's workers materialize what they re-evaluate (b2GpuSeam_ContactReevaluated): the tail of the previous
 	// step's download is waited for here, once
@@ -421,26 +427,34 @@ void b2GpuSeam_ContactRecycled( b2World* world, int contactIndex, const b2Contac
  * puts in front of the reference's (tools/buildlib.py renames the reference's definitions to b2Ref_*; the reference's
  * sources are not touched).  The many_pyramids step loses its 3 MB download and the unpack pass over 58 000 manifolds from
  * the critical path. */
-void b2GpuSeam_ContactReevaluated( b2World* world, int contactIndex, b2ContactSim* contactSim )
+void b2GpuSeam_ContactReevaluated( b2World* world, int workerIndex, int contactIndex, b2ContactSim* contactSim )
 {
 	b2SeamSlot* slot = s_slots + world->worldId;
-	if ( slot->solver == NULL || b2GpuSolverDeferredPending( slot->solver ) == 0 )
+	if ( slot->impulsesPending == false || contactIndex >= slot->collideTotal )
 	{
+		// (what follows the colours' arrays in b2Collide's flat array are the awake set's non-touching contacts: never solved)
 		return;
 	}
-	// contactIndex -> (graph colour, place): b2Collide laid the colours' arrays end to end (b2GpuSeam_BeginCollide); what
-	// follows them are the awake set's non-touching contacts, which no step has solved
-	for ( int i = 0; i < B2_GRAPH_COLOR_COUNT; ++i )
+	// contactIndex -> (graph colour, place): b2Collide laid the colours' arrays end to end (b2GpuSeam_BeginCollide) and a worker
+	// walks a range of that array front to back, so the colour of its previous contact is where to start looking
+	int* cursor = slot->collideCursor[workerIndex & ( B2_MAX_WORKERS - 1 )];
+	int i = *cursor;
+	if ( contactIndex < slot->collideStart[i] )
 	{
-		int j = contactIndex - slot->collideStart[i];
-		if ( 0 <= j && j < slot->collideCount[i] )
-		{
-			if ( b2GpuSolverMaterializeContacts( slot->solver, i, j, contactSim, 1, NULL ) < 0 )
-			{
-				b2SeamFatal( "b2GpuSolverMaterializeContacts" );
-			}
-			return;
-		}
+		i = 0;
+	}
+	while ( i < B2_GRAPH_COLOR_COUNT - 1 && contactIndex >= slot->collideStart[i] + slot->collideCount[i] )
+	{
+		i += 1;
+	}
+	if ( i != *cursor )
+	{
+		*cursor = i;
+	}
+	int j = contactIndex - slot->collideStart[i];
+	if ( 0 <= j && j < slot->collideCount[i] && b2GpuSolverMaterializeContacts( slot->solver, i, j, contactSim, 1, NULL ) < 0 )
+	{
+		b2SeamFatal( "b2GpuSolverMaterializeContacts" );
 	}
 }
 

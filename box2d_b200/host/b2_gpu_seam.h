@@ -47,7 +47,7 @@ void b2GpuSeam_BeginCollide( b2World* world, b2StepContext* stepContext, int con
 void b2GpuSeam_ContactRecycled( b2World* world, int contactIndex, const b2ContactSim* contactSim );
 
 /* Deferred impulses (b2_gpu_seam.c): called by the generated physics_world.c before b2UpdateContact re-evaluates a manifold. */
-void b2GpuSeam_ContactReevaluated( b2World* world, int contactIndex, b2ContactSim* contactSim );
+void b2GpuSeam_ContactReevaluated( b2World* world, int workerIndex, int contactIndex, b2ContactSim* contactSim );
 /* Writes every pending impulse record into its manifold now (what the interposed readers do); stats for tests. */
 void b2GpuSeam_FlushImpulses( int worldIndex );
 int b2GpuSeam_GetDeferredStats( int worldIndex, int* pending, long long* flushes );
