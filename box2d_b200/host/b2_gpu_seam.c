@@ -923,15 +923,10 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 		world->taskCount += 1;
 	}
 
-	// island hint: lets the device solve islands independently in shared memory (no grid barriers)
+	// While the helpers wake up and start on the joints and the island labels, the calling thread lays the step out: the
+	// descriptor and BeginStep read the arrays' addresses and counts and the islands' sizes, not the joints' contents or the labels
+	// (those are read by the pack pass, which opens when the team's first pass is done).
 	int spins = 0;
-	b2SeamTeamJoints( &team );
-	b2SeamTeamLabels( &team );
-	while ( b2AtomicLoadInt( &team.labelDone ) < team.labelBlocks || b2AtomicLoadInt( &team.jointDone ) < team.jointBlocks )
-	{
-		b2SeamRelax( &spins );
-	}
-
 	b2GpuStepDesc* desc = &slot->lastDesc;
 	b2GpuSeam_BuildDesc( world, context, desc );
 	if ( captured )
@@ -977,6 +972,13 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 	if ( b2GpuSolverBeginStep( slot->solver, desc, result ) != 0 )
 	{
 		failure = "b2GpuSolverBeginStep failed";
+	}
+	// island hint: lets the device solve islands independently in shared memory (no grid barriers)
+	b2SeamTeamJoints( &team );
+	b2SeamTeamLabels( &team );
+	while ( b2AtomicLoadInt( &team.labelDone ) < team.labelBlocks || b2AtomicLoadInt( &team.jointDone ) < team.jointBlocks )
+	{
+		b2SeamRelax( &spins );
 	}
 	if ( failure == NULL )
 	{
