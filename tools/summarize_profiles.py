@@ -36,7 +36,7 @@ def launch_summary(rnd: str) -> None:
 			v = float(d["Metric Value"].replace(",", ""))
 			v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(d["Metric Unit"], 1.0)
 			agg.setdefault(d["Kernel Name"].split("(")[0], []).append(v)
-	ours = {k: v for k, v in agg.items() if k.startswith("b2g::")}
+	ours = {k: v for k, v in agg.items() if k.startswith("b2g")}
 	steps = max(len(v) for v in ours.values()) if ours else 1
 	total = sum(sum(v) for v in ours.values()) / steps
 	with open(PROF / f"{rnd}_launch_summary.txt", "w") as f:
