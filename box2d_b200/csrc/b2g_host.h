@@ -215,6 +215,7 @@ struct b2GpuSolver
 	DeviceBuffer<int2> cidx;
 	DeviceBuffer<int> cmeta;
 	ControlBlock* control = nullptr;
+	bool controlClean = false; // zeroed behind the previous step's download: b2gEnqueueRun need not
 
 	// island mode scratch (b2g_island.cuh)
 	DeviceBuffer<int> binCounters; // [binBodyCount | binColorStart | binJointStart | binFail], zeroed every run

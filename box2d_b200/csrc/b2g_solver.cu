@@ -1550,7 +1550,11 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 	}
 	B2G_CUDA( cudaSetDevice( s->device ) );
 	s->lastLaunches = 0;
-	B2G_CUDA( cudaMemsetAsync( s->control, 0, sizeof( ControlBlock ), s->stream ) );
+	if ( !s->controlClean )
+	{
+		B2G_CUDA( cudaMemsetAsync( s->control, 0, sizeof( ControlBlock ), s->stream ) );
+	}
+	s->controlClean = false;
 	B2G_CUDA( cudaEventRecord( s->evStart, s->stream ) );
 	if ( s->resident && s->params.dirtyBodyCapacity > 0 )
 	{
@@ -1784,8 +1788,15 @@ int b2gEnqueueDownload( b2GpuSolver* s )
 	s->chunkNext = 0;
 	s->arrivedQuads.store( 0, std::memory_order_release );
 	s->lastD2H = total * sizeof( float4 ) + sizeof( ControlBlock );
-	// behind the download, off the host's critical path
-	return b2gEnqueueCommit( s );
+	// behind the download, off the host's critical path: the table's update, and the control block zeroed for the next
+	// step's kernels (one driver call less between the next Submit and its first launch)
+	if ( b2gEnqueueCommit( s ) != 0 )
+	{
+		return 1;
+	}
+	B2G_CUDA( cudaMemsetAsync( s->control, 0, sizeof( ControlBlock ), s->stream ) );
+	s->controlClean = true;
+	return 0;
 }
 
 extern "C" int b2GpuSolverSubmit( b2GpuSolver* s )

@@ -161,21 +161,26 @@ B2G_DEV void integratePositions( const StepParams& P, const SolveView& V, int i 
 	V.pos[i + 1] = make_float4( dp.x, dp.y, dq.c, dq.s );
 }
 
+// one 32-byte record in ONE store (sm_100: STG.256; the records are 32-byte aligned).  With direct outputs
+// the store is a PCIe write: a whole sector per instruction instead of two half-written ones.
+B2G_DEV void storeState( void* record, float4 a, float4 b )
+{
+	asm volatile( "st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"( record ), "f"( a.x ), "f"( a.y ), "f"( a.z ), "f"( a.w ),
+				  "f"( b.x ), "f"( b.y ), "f"( b.z ), "f"( b.w )
+				  : "memory" );
+}
+
 // view -> the reference's AoS b2BodyState for the download
 B2G_DEV void storeBody( const StepParams& P, const SolveView& V, int body, int local )
 {
-	float4* out = reinterpret_cast<float4*>( P.outStates + (size_t)body * B2L_STATE_SIZE );
 	float4 v = V.vel[local];
-	out[0] = v;
-	out[1] = V.pos[local];
+	storeState( P.outStates + (size_t)body * B2L_STATE_SIZE, v, V.pos[local] );
 	if ( P.residentOut != nullptr )
 	{
 		// what the host's state will be when the next step begins, unless somebody touches the body in between (the pack
 		// pass checks): b2FinalizeBodiesTask resets the deltas and clears the transient flags (src/solver.c:611-612, :632)
-		float4* next = reinterpret_cast<float4*>( P.residentOut + (size_t)body * B2L_STATE_SIZE );
 		v.w = __uint_as_float( __float_as_uint( v.w ) & ~B2L_FLAG_TRANSIENT );
-		next[0] = v;
-		next[1] = make_float4( 0.0f, 0.0f, 1.0f, 0.0f );
+		storeState( P.residentOut + (size_t)body * B2L_STATE_SIZE, v, make_float4( 0.0f, 0.0f, 1.0f, 0.0f ) );
 	}
 }
 
