@@ -166,6 +166,8 @@ def solver_lib() -> ctypes.CDLL:
 	lib.b2GpuSolverEndStep.argtypes = [ctypes.c_void_p, P(StepResult)]
 	lib.b2GpuSolverSetMode.restype = ctypes.c_int
 	lib.b2GpuSolverSetMode.argtypes = [ctypes.c_void_p, ctypes.c_int]
+	lib.b2GpuSolverGetListReuseCount.restype = ctypes.c_int
+	lib.b2GpuSolverGetListReuseCount.argtypes = [ctypes.c_void_p]
 	lib.b2GpuSolverSetDeferredImpulses.restype = ctypes.c_int
 	lib.b2GpuSolverSetDeferredImpulses.argtypes = [ctypes.c_void_p, ctypes.c_int]
 	lib.b2GpuSolverDeferredPending.restype = ctypes.c_int
@@ -547,6 +549,10 @@ class GpuSolver:
 
 	def step(self, desc: StepDesc, result: StepResult) -> None:
 		self._check(self.lib.b2GpuSolverStep(self.handle, ctypes.byref(desc), ctypes.byref(result)), "b2GpuSolverStep")
+
+	def list_reuse_count(self) -> int:
+		"""Steps that ran on the previous step's bin lists (b2GpuSolverGetListReuseCount)."""
+		return int(self.lib.b2GpuSolverGetListReuseCount(self.handle))
 
 	def set_deferred(self, enabled: bool) -> None:
 		self._check(self.lib.b2GpuSolverSetDeferredImpulses(self.handle, 1 if enabled else 0), "b2GpuSolverSetDeferredImpulses")

@@ -217,6 +217,26 @@ struct b2GpuSolver
 	ControlBlock* control = nullptr;
 	bool controlClean = false; // zeroed behind the previous step's download: b2gEnqueueRun need not
 
+	// The bins' lists from one step to the next (one block per bin, flat lists).  What b2gScatterKernel builds -- which bodies
+	// and contacts every bin holds -- only depends on the bodies' bins, the contacts' slots and their body indices.  In a
+	// steady scene none of that changes: no contact travels in full (each sits at the home, with the bodies, it had before),
+	// the layout and the plan are the same, every body is in the bin it was in.  The step then runs on the lists
+	// the previous step left in device memory: no scatter kernel (many_pyramids: 6 of 58 us).  B2GPU_KEEP_LISTS=0 turns it off.
+	bool keepListsEnabled = true;
+	bool listsValid = false; // the device's lists and counters are those of the step described by listsOf
+	struct ListsOf
+	{
+		int binCount, capBodies, capContacts, capJoints, bodyCount, contactSlots, colorCount, jointCount, jointWords;
+		b2g::ColorRange colors[b2g::kMaxColors];
+		b2g::ColorRange overflow;
+		const void* buffers[6];
+	} listsOf = {};
+	std::vector<int> prevBins;		   // bin of every awake body in the previous island-mode step
+	int prevBinCount = 0;
+	std::atomic<int> binsChanged{ 0 }; // pack pass: some body is in another bin than in the previous step
+	int listsReused = 0;			   // statistics: steps that ran without the scatter kernel
+
+
 	// island mode scratch (b2g_island.cuh)
 	DeviceBuffer<int> binCounters; // [binBodyCount | binColorStart | binJointStart | binFail], zeroed every run
 	DeviceBuffer<int> bodyLocal, binBodyList, slotGroupBits, binContactList, binJointList;

@@ -759,15 +759,19 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	}
 	forEachLocal( bodyCount, [&]( int i ) { loadBody( P, V, bodyList[i], i + 1 ); } );
 	__syncthreads();
-	// this block is the last reader of its bin's counters: leave them zeroed for the next step's partition kernel
-	if ( threadIdx.x < kColorSlots )
+	// this block is the last reader of its bin's counters: leave them zeroed for the next step's partition kernel -- unless
+	// the host may run the next step on these very lists (keepLists: a steady scene, see b2gEnqueueRun)
+	if ( P.keepLists == 0 )
 	{
-		P.binColorStart[(size_t)bin * kColorSlots + threadIdx.x] = 0;
-		P.binJointStart[(size_t)bin * kColorSlots + threadIdx.x] = 0;
-	}
-	if ( threadIdx.x == 0 )
-	{
-		P.binBodyCount[bin] = 0;
+		if ( threadIdx.x < kColorSlots )
+		{
+			P.binColorStart[(size_t)bin * kColorSlots + threadIdx.x] = 0;
+			P.binJointStart[(size_t)bin * kColorSlots + threadIdx.x] = 0;
+		}
+		if ( threadIdx.x == 0 )
+		{
+			P.binBodyCount[bin] = 0;
+		}
 	}
 
 	const int colorCount = P.colorCount;

@@ -183,6 +183,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		// at ~192 us, the link is the limit, not snoops.)
 		const char* chunkEnv = getenv( "B2GPU_DOWNLOAD_KIB" );
 		s->downloadQuads = chunkEnv != nullptr && atoi( chunkEnv ) >= 16 ? (size_t)atoi( chunkEnv ) * 64 : kDownloadQuads;
+		const char* keepEnv = getenv( "B2GPU_KEEP_LISTS" );
+		s->keepListsEnabled = keepEnv == nullptr || atoi( keepEnv ) != 0;
 		const char* directEnv = getenv( "B2GPU_DIRECT_OUT" );
 		s->directEnabled = directEnv == nullptr || atoi( directEnv ) != 0;
 		const char* liteEnv = getenv( "B2GPU_LITE_JOINTS" );
@@ -359,6 +361,12 @@ extern "C" int b2GpuSolverGetIslandPlan( const b2GpuSolver* s, int* binCount, in
 		*blocksPerBin = bins > 0 ? s->params.clusterSize : 0;
 	}
 	return bins;
+}
+
+// steps of this solver that ran on the previous step's bin lists (no scatter kernel)
+extern "C" int b2GpuSolverGetListReuseCount( const b2GpuSolver* s )
+{
+	return s != nullptr ? s->listsReused : 0;
 }
 
 extern "C" int b2GpuSolverGetResidentStats( const b2GpuSolver* s, int* fullContacts, int* dirtyBodies, int* vouchedContacts, int* fullJoints )
@@ -1339,6 +1347,26 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 		return 1;
 	}
 
+	// the bodies' bins of the previous step, for the pack pass to compare with (the bins' lists may serve again, b2gEnqueueRun)
+	s->binsChanged.store( 0, std::memory_order_relaxed );
+	if ( s->islandMode )
+	{
+		if ( s->prevBins.size() < (size_t)P.bodyCount + 1 )
+		{
+			s->prevBins.resize( (size_t)P.bodyCount + (size_t)P.bodyCount / 2 + 64, -1 );
+		}
+		if ( s->prevBinCount != P.bodyCount )
+		{
+			s->binsChanged.store( 1, std::memory_order_relaxed );
+			s->prevBinCount = P.bodyCount;
+		}
+	}
+	else
+	{
+		s->prevBinCount = 0;
+		s->listsValid = false;
+	}
+
 	// pack blocks: the constraints' blocks, then the bodies' blocks (b2gPackBlockRange)
 	{
 		// blocks of the host passes: ~128 per step so that a small step still spreads evenly over the host's workers and its
@@ -1506,6 +1534,7 @@ int b2gRerunIfIslandsFailed( b2GpuSolver* s, bool download )
 		return 0;
 	}
 	s->countersClean = false; // the island kernels returned before zeroing their counters
+	s->listsValid = false;
 	if ( s->params.ownerLists != 0 )
 	{
 		s->ownerListsOff = 512; // a block's share did not fit: deal the colours out evenly for a while
@@ -1590,12 +1619,43 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 		{
 			// partition -> island kernel; if a bin does not fit (binFail) the host reruns the step on the grid-barrier
 			// kernel once the flag has come back (b2gRerunIfIslandsFailed)
-			if ( !s->countersClean )
+			// A steady step (see b2GpuSolver::listsValid): no contact travelled in full -- every one of them sits at the home it
+			// had, with the bodies it had (on the narrow phase's word or by comparison) --, no joints, one block per bin with flat lists.  Such a step leaves its lists behind, and runs on the previous step's if that was
+			// one too and nothing the lists depend on has moved.
+			b2GpuSolver::ListsOf now = {};
+			{
+				const b2g::StepParams& P = s->params;
+				now.binCount = P.binCount, now.capBodies = P.capBodies, now.capContacts = P.capContacts, now.capJoints = P.capJoints;
+				now.bodyCount = P.bodyCount, now.contactSlots = P.contactSlots, now.colorCount = P.colorCount, now.jointCount = P.jointCount;
+				now.jointWords = P.jointWords;
+				memcpy( now.colors, P.colors, sizeof( now.colors ) );
+				now.overflow = P.overflow;
+				now.buffers[0] = P.binBodyCount, now.buffers[1] = P.binBodyList, now.buffers[2] = P.bodyLocal, now.buffers[3] = P.binContactInfo;
+				now.buffers[4] = P.binContactList, now.buffers[5] = P.bodyBin;
+			}
+			const bool steady = s->keepListsEnabled && s->resident && s->cacheUsable && s->params.flatLists != 0 && s->params.clusterSize == 1 &&
+								s->jointTotal == 0 && s->params.jointWords == 0 && s->contactTotal > 0 &&
+								s->fullCount.load( std::memory_order_relaxed ) == 0;
+			const bool reuse = steady && s->listsValid && s->binsChanged.load( std::memory_order_relaxed ) == 0 &&
+							   memcmp( &now, &s->listsOf, sizeof( now ) ) == 0;
+			s->params.keepLists = steady ? 1 : 0;
+			s->listsValid = steady; // (unless the step fails: b2gRerunIfIslandsFailed)
+			s->listsOf = now;
+			if ( reuse )
+			{
+				s->listsReused += 1;
+				err = cudaSuccess;
+			}
+			else if ( !s->countersClean )
 			{
 				B2G_CUDA( cudaMemsetAsync( s->binCounters.ptr, 0, s->binCounters.capacity * sizeof( int ), s->stream ) );
 			}
-			s->countersClean = true; // the island kernels zero the counters they have read
-			if ( s->params.flatLists != 0 )
+			s->countersClean = !steady; // the island kernels zero the counters they have read, unless they keep the lists
+			if ( reuse )
+			{
+				// nothing to partition
+			}
+			else if ( s->params.flatLists != 0 )
 			{
 				// one flat pass, one item per thread
 				const b2g::StepParams& P = s->params;
@@ -1648,14 +1708,15 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 				attribute.id = cudaLaunchAttributeProgrammaticStreamSerialization;
 				attribute.val.programmaticStreamSerializationAllowed = 1;
 				config.attrs = &attribute;
-				config.numAttrs = s->params.flatLists != 0 && s->dependentLaunch ? 1 : 0;
+				const bool noPrimary = reuse; // (no scatter kernel in front of it)
+				config.numAttrs = s->params.flatLists != 0 && s->dependentLaunch && !noPrimary ? 1 : 0;
 				err = cudaLaunchKernelEx( &config, b2g::b2gIslandKernel, s->params );
 			}
 			if ( err != cudaSuccess )
 			{
 				return b2gFail( "b2gIslandKernel launch", err );
 			}
-			s->lastLaunches += 2;
+			s->lastLaunches += reuse ? 1 : 2;
 		}
 		else if ( b2gLaunchGridKernel( s ) != 0 )
 		{

@@ -208,6 +208,7 @@ struct StepParams
 	int ownerLists;	   // one bin shared by a cluster: constraint lists per BLOCK, keyed by the owner of the first body
 	int listCount;	   // number of constraint lists: binCount, or clusterSize with owner lists
 	int leveliseContacts; // flat lists: jointless bins run their coloured contacts level by level (b2g_island.cuh)
+	int keepLists;	   // one block per bin, flat lists: the island kernel leaves the bins' counters as they are (the next step may run on the same lists, b2gEnqueueRun)
 	int flatLists;	   // one block per bin: b2gScatterKernel appends to flat per-bin lists, the island kernel sorts them by colour
 	int listCapContacts; // stride of the constraint lists (binCap*, or the per-block capacity with owner lists)
 	int listCapJoints;

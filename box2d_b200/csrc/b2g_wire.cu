@@ -282,6 +282,7 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		const bool resident = s->resident;
 		const int known = s->cacheUsable ? s->shadowBodyCount : 0;
 		b2gStreamChunk dirty = { &s->dirtyCursor, s->dirtyCapacity, 0, 0, &s->streamOverflow };
+		bool binMoved = false;
 		int i = begin;
 		int bodyEnd = end < bodyCount ? end : bodyCount;
 		int w = i < bodyEnd ? b2gFindSegment( s->bodyStart, i ) : 0;
@@ -298,7 +299,14 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 					// harmless for the result, and if it overfills a bin the device notices (binFail)
 					int label = seg.islandCount == 1 ? 0 : seg.islands[local];
 					label = label >= 0 && label < seg.islandCount ? label : 0;
-					_mm_stream_si32( wireBins + i, s->islandBin[seg.islandBase + label] );
+					const int bin = s->islandBin[seg.islandBase + label];
+					_mm_stream_si32( wireBins + i, bin );
+					if ( s->prevBins[(size_t)i] != bin )
+					{
+						// (the bins' lists of the previous step cannot serve this one, b2gEnqueueRun)
+						s->prevBins[(size_t)i] = bin;
+						binMoved = true;
+					}
 				}
 				const uint8_t* state = seg.states + (size_t)local * B2L_STATE_SIZE;
 				const uint8_t* sim = seg.sims + (size_t)local * B2L_SIM_SIZE;
@@ -329,6 +337,10 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		if ( dirty.taken > 0 )
 		{
 			s->dirtyCount.fetch_add( dirty.taken, std::memory_order_relaxed );
+		}
+		if ( binMoved )
+		{
+			s->binsChanged.store( 1, std::memory_order_relaxed );
 		}
 		// the unused tail of the last chunk: records the apply pass skips
 		while ( dirty.next < dirty.end )

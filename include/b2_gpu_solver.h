@@ -294,6 +294,9 @@ B2GPU_API void* b2GpuHostAlloc( size_t size, int alignment );
 B2GPU_API void b2GpuHostFree( void* mem, size_t size );
 
 /* Diagnostics */
+/* Steps of this solver that ran on the bin lists the previous step left on the device (a steady scene: no contact travelled
+ * in full, every body in the bin it was in, same layout and plan; the partition kernel is not launched). */
+B2GPU_API int b2GpuSolverGetListReuseCount( const b2GpuSolver* solver );
 B2GPU_API const char* b2GpuGetLastError( void );
 B2GPU_API int b2GpuGetDeviceCount( void );
 B2GPU_API int b2GpuGetVersion( void );
