@@ -179,8 +179,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gClusterIslandKernel( c
 	}
 	forEachLocal( bodyCount, [&]( int i ) { loadBody( P, V, bodyList[i], i + 1 ); } );
 	cluster.sync(); // every block of the cluster is running and its bodies are in place
-	// every block has read the bin's counters: leave them zeroed for the next step's partition kernel
-	if ( rank == 0 || ownerLists )
+	// every block has read the bin's counters: leave them zeroed for the next step's partition kernel -- unless the host may
+	// run the next step on these very lists (keepLists, see b2gEnqueueRun)
+	if ( P.keepLists == 0 && ( rank == 0 || ownerLists ) )
 	{
 		if ( threadIdx.x < kColorSlots )
 		{

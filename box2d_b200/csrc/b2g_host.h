@@ -217,7 +217,7 @@ struct b2GpuSolver
 	ControlBlock* control = nullptr;
 	bool controlClean = false; // zeroed behind the previous step's download: b2gEnqueueRun need not
 
-	// The bins' lists from one step to the next (one block per bin, flat lists).  What b2gScatterKernel builds -- which bodies
+	// The bins' lists from one step to the next (one block per bin with flat lists, or a cluster per bin).  What b2gScatterKernel builds -- which bodies
 	// and contacts every bin holds -- only depends on the bodies' bins, the contacts' slots and their body indices.  In a
 	// steady scene none of that changes: no contact travels in full (each sits at the home, with the bodies, it had before),
 	// the layout and the plan are the same, every body is in the bin it was in.  The step then runs on the lists
@@ -227,6 +227,7 @@ struct b2GpuSolver
 	struct ListsOf
 	{
 		int binCount, capBodies, capContacts, capJoints, bodyCount, contactSlots, colorCount, jointCount, jointWords;
+		int clusterSize, ownerLists, listCount, clusterRun, listCapContacts, flatLists;
 		b2g::ColorRange colors[b2g::kMaxColors];
 		b2g::ColorRange overflow;
 		const void* buffers[6];

@@ -1628,12 +1628,14 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 				now.binCount = P.binCount, now.capBodies = P.capBodies, now.capContacts = P.capContacts, now.capJoints = P.capJoints;
 				now.bodyCount = P.bodyCount, now.contactSlots = P.contactSlots, now.colorCount = P.colorCount, now.jointCount = P.jointCount;
 				now.jointWords = P.jointWords;
+				now.clusterSize = P.clusterSize, now.ownerLists = P.ownerLists, now.listCount = P.listCount, now.clusterRun = P.clusterRun;
+				now.listCapContacts = P.listCapContacts, now.flatLists = P.flatLists;
 				memcpy( now.colors, P.colors, sizeof( now.colors ) );
 				now.overflow = P.overflow;
 				now.buffers[0] = P.binBodyCount, now.buffers[1] = P.binBodyList, now.buffers[2] = P.bodyLocal, now.buffers[3] = P.binContactInfo;
 				now.buffers[4] = P.binContactList, now.buffers[5] = P.bodyBin;
 			}
-			const bool steady = s->keepListsEnabled && s->resident && s->cacheUsable && s->params.flatLists != 0 && s->params.clusterSize == 1 &&
+			const bool steady = s->keepListsEnabled && s->resident && s->cacheUsable && ( s->params.flatLists != 0 || s->params.clusterSize > 1 ) &&
 								s->jointTotal == 0 && s->params.jointWords == 0 && s->contactTotal > 0 &&
 								s->fullCount.load( std::memory_order_relaxed ) == 0;
 			const bool reuse = steady && s->listsValid && s->binsChanged.load( std::memory_order_relaxed ) == 0 &&
@@ -1694,7 +1696,7 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 				attribute[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
 				attribute[1].val.programmaticStreamSerializationAllowed = 1;
 				config.attrs = attribute;
-				config.numAttrs = s->dependentLaunch ? 2 : 1;
+				config.numAttrs = s->dependentLaunch && !reuse ? 2 : 1; // (reuse: no partition kernel in front of it)
 				err = cudaLaunchKernelEx( &config, b2g::b2gClusterIslandKernel, s->params );
 			}
 			else

@@ -166,6 +166,21 @@ def test_chained_steps_match_the_oracle(oracle, capture_files, islands):
 	assert light_steps > 0
 
 
+def test_clusters_run_on_the_previous_steps_lists_too(oracle, capture_files, monkeypatch):
+	"""The same chain of steps with every bin shared by a cluster of two blocks (b2gPartitionKernel + b2gClusterIslandKernel): the
+	steady steps of the chain skip the partition kernel, everything still matches the oracle bit for bit."""
+	monkeypatch.setenv("B2GPU_CLUSTER_FORCE", "2")
+	rng = np.random.default_rng(11)
+	cap = b2.Capture([f for f in capture_files if "small_pyramid_030" in f.name][0])
+	with b2.GpuSolver() as solver:
+		for step, kind in enumerate(SEQUENCE):
+			_mutate(cap, rng, kind)
+			got = _step_both(oracle, solver, cap, f"cluster of 2, step {step} after {kind!r}")
+			assert solver.island_plan()[1] == 2, "the step did not run on clusters of two blocks"
+			_finalize(cap, got)
+		assert solver.list_reuse_count() >= 2, solver.list_reuse_count()
+
+
 def test_contacts_leaving_and_returning(oracle, capture_files):
 	"""A contact that sits out a step (stopped touching, came back) must not pick up stale impulses: its previous output
 	record is two steps old."""
