@@ -219,7 +219,7 @@ struct b2GpuSolver
 
 	// The bins' lists from one step to the next (one block per bin with flat lists, or a cluster per bin).  What b2gScatterKernel builds -- which bodies
 	// and contacts every bin holds -- only depends on the bodies' bins, the contacts' slots and their body indices.  In a
-	// steady scene none of that changes: no contact travels in full (each sits at the home, with the bodies, it had before),
+	// steady scene none of that changes: no contact or joint travels in full (each sits at the home, with the bodies, it had before),
 	// the layout and the plan are the same, every body is in the bin it was in.  The step then runs on the lists
 	// the previous step left in device memory: no scatter kernel (many_pyramids: 6 of 58 us).  B2GPU_KEEP_LISTS=0 turns it off.
 	bool keepListsEnabled = true;
@@ -230,7 +230,7 @@ struct b2GpuSolver
 		int clusterSize, ownerLists, listCount, clusterRun, listCapContacts, flatLists;
 		b2g::ColorRange colors[b2g::kMaxColors];
 		b2g::ColorRange overflow;
-		const void* buffers[6];
+		const void* buffers[8];
 	} listsOf = {};
 	std::vector<int> prevBins;		   // bin of every awake body in the previous island-mode step
 	int prevBinCount = 0;

@@ -1633,20 +1633,28 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 				memcpy( now.colors, P.colors, sizeof( now.colors ) );
 				now.overflow = P.overflow;
 				now.buffers[0] = P.binBodyCount, now.buffers[1] = P.binBodyList, now.buffers[2] = P.bodyLocal, now.buffers[3] = P.binContactInfo;
-				now.buffers[4] = P.binContactList, now.buffers[5] = P.bodyBin;
+				now.buffers[4] = P.binContactList, now.buffers[5] = P.bodyBin, now.buffers[6] = P.binJointList, now.buffers[7] = P.binJointBodies;
 			}
 			const bool steady = s->keepListsEnabled && s->resident && s->cacheUsable && ( s->params.flatLists != 0 || s->params.clusterSize > 1 ) &&
-								s->jointTotal == 0 && s->params.jointWords == 0 && s->contactTotal > 0 &&
-								s->fullCount.load( std::memory_order_relaxed ) == 0;
+								s->contactTotal + s->jointTotal > 0 && s->fullCount.load( std::memory_order_relaxed ) == 0 &&
+								s->fullJointCount.load( std::memory_order_relaxed ) == 0;
 			const bool reuse = steady && s->listsValid && s->binsChanged.load( std::memory_order_relaxed ) == 0 &&
 							   memcmp( &now, &s->listsOf, sizeof( now ) ) == 0;
 			s->params.keepLists = steady ? 1 : 0;
 			s->listsValid = steady; // (unless the step fails: b2gRerunIfIslandsFailed)
 			s->listsOf = now;
+			// (the lists this run builds, or runs on, are those of the bins the pack pass has just seen: another run of the same
+			// upload -- b2GpuSolverRun can be repeated -- finds nothing changed)
+			s->binsChanged.store( 0, std::memory_order_relaxed );
 			if ( reuse )
 			{
 				s->listsReused += 1;
 				err = cudaSuccess;
+				if ( s->params.jointWords > 0 )
+				{
+					// (the partition kernels clear the joint-event bits on their way)
+					B2G_CUDA( cudaMemsetAsync( s->params.jointBits, 0, (size_t)s->params.jointWords * sizeof( uint32_t ), s->stream ) );
+				}
 			}
 			else if ( !s->countersClean )
 			{

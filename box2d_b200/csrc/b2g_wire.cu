@@ -584,6 +584,7 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		const bool resident = s->resident;
 		b2gStreamChunk full = { &s->fullJointCursor, s->fullJointCapacity, 0, 0, &s->streamOverflow };
 		bool heavy = false;
+		bool jointMoved = false;
 		int first = bodyCount + s->contactTotal;
 		int flat = ( begin > first ? begin : first ) - first;
 		int flatEnd = end - first;
@@ -633,6 +634,19 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 				int ref = homeSlot + i; // its record among the previous step's outputs
 				if ( clean )
 				{
+					// its bodies are part of the run that travels every step: the bins' lists of the previous step only serve
+					// this one (b2gEnqueueRun) if they are the bodies the joint had then
+					int* pair = b2gJointIndexPair( reinterpret_cast<b2lJointSim*>( padded ) );
+					if ( pair != nullptr )
+					{
+						int* known = reinterpret_cast<int*>( shadow + ( reinterpret_cast<uint8_t*>( pair ) - padded ) );
+						if ( known[0] != pair[0] || known[1] != pair[1] )
+						{
+							known[0] = pair[0];
+							known[1] = pair[1];
+							jointMoved = true;
+						}
+					}
 					alignas( 16 ) uint8_t run[B2L_JOINT_RUN_MAX] = { 0 };
 					memcpy( run, padded + runOffset, (size_t)runBytes );
 					b2gStreamCopy( light + 1, run, B2L_JOINT_RUN_MAX / 16 );
@@ -656,6 +670,10 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 		if ( heavy )
 		{
 			s->heavyJoint.store( 1, std::memory_order_relaxed );
+		}
+		if ( jointMoved )
+		{
+			s->binsChanged.store( 1, std::memory_order_relaxed );
 		}
 	}
 	_mm_sfence();
