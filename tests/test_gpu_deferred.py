@@ -174,3 +174,48 @@ def test_c_abi_chain_of_steps_with_stale_manifolds(oracle, capture_files, name):
 		assert solver.materialize(d, got["contacts"]) == cap_g.contact_count
 		for a, b in zip(got["contacts"], want["contacts"]):
 			assert np.array_equal(a, b), "contact sims at the end of the chain"
+
+
+@pytest.mark.parametrize("knob", ["B2GPU_DIRECT_OUT", "B2GPU_KEEP_LISTS", "B2GPU_RESIDENT", "B2GPU_PDL"])
+def test_each_shortcut_can_be_turned_off(ref_lib, gpu_host_lib, knob):
+	"""The shortcuts of the steady state -- body states stored straight into mapped host memory, steps that run on the previous
+	step's bin lists, the resident copies, the programmatic dependent launch -- are optimisations, not semantics: with any one of
+	them off (the knobs are read when a world's device solver is created) the results are the same bits."""
+	os.environ[knob] = "0"
+	try:
+		for scene, steps, every in (("many_pyramids", 24, 6), ("contact_zoo", 60, 5), ("falling_hinges", 40, 8)):
+			with b2.World(ref_lib, scene, 4) as ref, b2.World(gpu_host_lib, scene, 4) as gpu:
+				for _ in range(steps // every):
+					ref.step(every)
+					gpu.step(every)
+					assert gpu.hash() == ref.hash(), f"{scene} with {knob}=0"
+	finally:
+		os.environ.pop(knob, None)
+
+
+def test_two_worlds_side_by_side_keep_their_impulses_apart(ref_lib, gpu_host_lib):
+	"""Every world has its own device solver, output arenas and pending impulses; stepping two worlds alternately and reading
+	one of them must not disturb the other.  Destroying a world with impulses pending and creating another in its slot starts
+	from a clean slate."""
+	with b2.World(ref_lib, "small_pyramid", 2) as ref_a, b2.World(gpu_host_lib, "small_pyramid", 2) as gpu_a:
+		with b2.World(ref_lib, "contact_zoo", 2) as ref_b, b2.World(gpu_host_lib, "contact_zoo", 2) as gpu_b:
+			for round_ in range(12):
+				for w in (ref_a, gpu_a, ref_b, gpu_b):
+					w.step(5)
+				if round_ % 3 == 0:
+					assert gpu_b.hash() == ref_b.hash()
+					assert gpu_a.deferred_stats()[0], "reading world B must not flush world A"
+				if round_ % 4 == 3:
+					assert gpu_a.contact_checksum() == ref_a.contact_checksum()
+			assert gpu_a.hash() == ref_a.hash() and gpu_b.hash() == ref_b.hash()
+			index_b = gpu_b.world_index()
+		# world B is gone with impulses pending; its slot is taken by a new world
+		gpu_a.step(3)
+		ref_a.step(3)
+		with b2.World(ref_lib, "joint_zoo", 2) as ref_c, b2.World(gpu_host_lib, "joint_zoo", 2) as gpu_c:
+			assert gpu_c.world_index() == index_b
+			for _ in range(6):
+				ref_c.step(5)
+				gpu_c.step(5)
+				assert gpu_c.hash() == ref_c.hash()
+		assert gpu_a.hash() == ref_a.hash()
