@@ -230,7 +230,7 @@ struct b2GpuSolver
 		int clusterSize, ownerLists, listCount, clusterRun, listCapContacts, flatLists;
 		b2g::ColorRange colors[b2g::kMaxColors];
 		b2g::ColorRange overflow;
-		const void* buffers[8];
+		const void* buffers[11];
 	} listsOf = {};
 	std::vector<int> prevBins;		   // bin of every awake body in the previous island-mode step
 	int prevBinCount = 0;
@@ -257,6 +257,9 @@ struct b2GpuSolver
 	bool flatListsEnabled = true;  // B2GPU_FLAT_LISTS=0: two-phase partition kernel for one block per bin too
 	bool countersClean = false; // the bin counters are all zero (the island kernels zero what they have read)
 	DeviceBuffer<int2> contactBinRank, jointBinRank;
+	DeviceBuffer<int> planStart, planJoints; // the bins' plans (b2g::StepParams::planWrite)
+	DeviceBuffer<int4> planInfo;
+	bool planValid = false; // ... written by the step that built the lists the device holds
 	std::vector<int> islandBin;	 // host: bin of every awake island
 	std::vector<int> islandBodies; // host: bodies per island
 	std::vector<int> islandContacts, islandJoints; // host: with exact island sizes (b2GpuStepDesc::islandSizes)

@@ -707,8 +707,11 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	// sort in shared memory puts them colour-major -- pass 1 counts (while the bodies are on their way), one thread turns
 	// the counts into offsets, pass 2 hands out the slots.  The order inside a colour stays arbitrary (see the file
 	// header); the overflow colour is ranked by wire slot / joint index, i.e. back into array order.
-	const bool flat = P.flatLists != 0;
-	const int4* contactInfo = P.binContactInfo + (size_t)bin * capC;
+	// ... unless the step runs on the previous step's lists and that step wrote its order down (planRead): then the bin's
+	// constraints are read in their final order, like the colour-major lists of the two-phase partition kernel
+	const bool planned = P.planRead != 0;
+	const bool flat = P.flatLists != 0 && !planned;
+	const int4* contactInfo = planned ? P.planInfo + (size_t)bin * capC : P.binContactInfo + (size_t)bin * capC;
 	constexpr int kFlatJointMask = ( 1 << kFlatJointShift ) - 1;
 	int flatContacts = 0, flatJoints = 0;
 	if ( flat )
@@ -748,8 +751,9 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	}
 	else if ( threadIdx.x < kColorSlots )
 	{
-		colorStartC[threadIdx.x] = P.binColorOffset[(size_t)bin * kColorSlots + threadIdx.x];
-		colorStartJ[threadIdx.x] = P.binJointOffset[(size_t)bin * kColorSlots + threadIdx.x];
+		const int* planStart = P.planStart + (size_t)bin * 2 * kColorSlots;
+		colorStartC[threadIdx.x] = planned ? planStart[threadIdx.x] : P.binColorOffset[(size_t)bin * kColorSlots + threadIdx.x];
+		colorStartJ[threadIdx.x] = planned ? planStart[kColorSlots + threadIdx.x] : P.binJointOffset[(size_t)bin * kColorSlots + threadIdx.x];
 	}
 	if ( threadIdx.x == 0 )
 	{
@@ -1002,7 +1006,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		}
 		return rank;
 	};
-	if ( !flat && ovCe > ovCb )
+	if ( !flat && !planned && ovCe > ovCb )
 	{
 		for ( int k = ovCb + (int)threadIdx.x; k < ovCe; k += (int)blockDim.x )
 		{
@@ -1033,9 +1037,20 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 				localB = info.z >= 0 ? P.bodyLocal[info.z] : 0;
 			}
 			wireSlot[dest] = info.x;
+			if ( P.planWrite != 0 )
+			{
+				P.planInfo[(size_t)bin * capC + dest] = make_int4( info.x, localA, localB, info.w & ( kMetaGroupRolling | kMetaGroupRestitution ) );
+			}
 			prepareContact( P, V, info.x, dest, localA, localB, V.vel[localA], V.vel[localB], wide,
 							info.w & ( kMetaGroupRolling | kMetaGroupRestitution ) );
 		};
+		if ( P.planWrite != 0 && threadIdx.x < kColorSlots )
+		{
+			// (of the levels, if the bin was levelised: the table built last)
+			int* planStart = P.planStart + (size_t)bin * 2 * kColorSlots;
+			planStart[threadIdx.x] = colorStartC[threadIdx.x];
+			planStart[kColorSlots + threadIdx.x] = colorStartJ[threadIdx.x];
+		}
 		if ( levelise )
 		{
 			// (the levelisation's scratch lives in the field array: all of it was read before the barrier above)
@@ -1059,6 +1074,10 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 			int c = entry >> kFlatJointShift, j = entry & kFlatJointMask;
 			int dest = c != colorCount ? atomicAdd( &flatCursorJ[bucket >= 0 ? bucket : c], 1 ) : ovJb + rankAmong( overflowOrderJ, ovJe - ovJb, j );
 			jointIndexOf[dest] = j;
+			if ( P.planWrite != 0 )
+			{
+				P.planJoints[(size_t)bin * capJ + dest] = j;
+			}
 		};
 		if ( levelise )
 		{
@@ -1082,7 +1101,7 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 		forEachLocal( contactCount, [&]( int k ) {
 			bool wide = k < ovCb || k >= ovCe;
 			int slot, localA, localB, groupBits = 0;
-			if ( wide && P.resolveContacts != 0 )
+			if ( planned || ( wide && P.resolveContacts != 0 ) )
 			{
 				int4 info = contactInfo[k]; // resolved by the partition kernel
 				slot = info.x, localA = info.y, localB = info.z, groupBits = info.w;
@@ -1103,7 +1122,12 @@ __global__ void __launch_bounds__( kIslandThreads, 1 ) b2gIslandKernel( const __
 	}
 	__syncthreads();
 	// joints: copy the prepared record into shared memory, renumber its bodies to the bin
-	if ( !flat )
+	if ( planned )
+	{
+		forEachLocal( jointCount, [&]( int k ) { jointIndexOf[k] = P.planJoints[(size_t)bin * capJ + k]; } );
+		__syncthreads();
+	}
+	else if ( !flat )
 	{
 		if ( ovJe > ovJb )
 		{

@@ -299,6 +299,9 @@ extern "C" void b2GpuSolverDestroy( b2GpuSolver* s )
 	s->slotGroupBits.release();
 	s->binContactList.release();
 	s->binContactInfo.release();
+	s->planInfo.release();
+	s->planJoints.release();
+	s->planStart.release();
 	s->jointWork.release();
 	s->binJointList.release();
 	s->binJointBodies.release();
@@ -733,6 +736,12 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	B2G_CUDA( s->contactBinRank.reserve( slots + 1 ) );
 	B2G_CUDA( s->binContactList.reserve( (size_t)binCount * capC * share + 1 ) );
 	B2G_CUDA( s->binContactInfo.reserve( (size_t)binCount * capC * share + 1 ) );
+	if ( plan.share == 1 )
+	{
+		B2G_CUDA( s->planInfo.reserve( (size_t)binCount * capC + 1 ) );
+		B2G_CUDA( s->planJoints.reserve( (size_t)binCount * capJ + 1 ) );
+		B2G_CUDA( s->planStart.reserve( (size_t)binCount * 2 * b2g::kColorSlots + 1 ) );
+	}
 	B2G_CUDA( s->jointBinRank.reserve( (size_t)s->jointTotal + 1 ) );
 	B2G_CUDA( s->binJointList.reserve( (size_t)binCount * capJ * share + 1 ) );
 	B2G_CUDA( s->binJointBodies.reserve( (size_t)binCount * capJ * share + 1 ) );
@@ -770,6 +779,9 @@ static int b2gPlanIslands( b2GpuSolver* s )
 	P.slotGroupBits = s->slotGroupBits.ptr;
 	P.binContactList = s->binContactList.ptr;
 	P.binContactInfo = s->binContactInfo.ptr;
+	P.planInfo = s->planInfo.ptr;
+	P.planJoints = s->planJoints.ptr;
+	P.planStart = s->planStart.ptr;
 	P.jointBinRank = s->jointBinRank.ptr;
 	P.binJointList = s->binJointList.ptr;
 	P.binJointBodies = s->binJointBodies.ptr;
@@ -1535,6 +1547,7 @@ int b2gRerunIfIslandsFailed( b2GpuSolver* s, bool download )
 	}
 	s->countersClean = false; // the island kernels returned before zeroing their counters
 	s->listsValid = false;
+	s->planValid = false;
 	if ( s->params.ownerLists != 0 )
 	{
 		s->ownerListsOff = 512; // a block's share did not fit: deal the colours out evenly for a while
@@ -1634,12 +1647,18 @@ static int b2gEnqueueRun( b2GpuSolver* s )
 				now.overflow = P.overflow;
 				now.buffers[0] = P.binBodyCount, now.buffers[1] = P.binBodyList, now.buffers[2] = P.bodyLocal, now.buffers[3] = P.binContactInfo;
 				now.buffers[4] = P.binContactList, now.buffers[5] = P.bodyBin, now.buffers[6] = P.binJointList, now.buffers[7] = P.binJointBodies;
+				now.buffers[8] = P.planInfo, now.buffers[9] = P.planJoints, now.buffers[10] = P.planStart;
 			}
 			const bool steady = s->keepListsEnabled && s->resident && s->cacheUsable && ( s->params.flatLists != 0 || s->params.clusterSize > 1 ) &&
 								s->contactTotal + s->jointTotal > 0 && s->fullCount.load( std::memory_order_relaxed ) == 0 &&
 								s->fullJointCount.load( std::memory_order_relaxed ) == 0;
 			const bool reuse = steady && s->listsValid && s->binsChanged.load( std::memory_order_relaxed ) == 0 &&
 							   memcmp( &now, &s->listsOf, sizeof( now ) ) == 0;
+			// a steady step that builds its lists writes the bins' plans down; the steps that run on those lists read them
+			const bool planCapable = s->params.flatLists != 0 && s->params.clusterSize == 1 && s->params.leveliseContacts != 0;
+			s->params.planRead = reuse && s->planValid && planCapable ? 1 : 0;
+			s->params.planWrite = steady && !reuse && planCapable ? 1 : 0;
+			s->planValid = steady && ( reuse ? s->planValid : planCapable );
 			s->params.keepLists = steady ? 1 : 0;
 			s->listsValid = steady; // (unless the step fails: b2gRerunIfIslandsFailed)
 			s->listsOf = now;

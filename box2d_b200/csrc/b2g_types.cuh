@@ -208,6 +208,13 @@ struct StepParams
 	int ownerLists;	   // one bin shared by a cluster: constraint lists per BLOCK, keyed by the owner of the first body
 	int listCount;	   // number of constraint lists: binCount, or clusterSize with owner lists
 	int leveliseContacts; // flat lists: jointless bins run their coloured contacts level by level (b2g_island.cuh)
+	// The bins' plans (one block per bin, flat lists): a step that keeps its lists also writes down, per bin, the order it put its
+	// constraints in -- sorted by colour, levelised -- and the offsets of the levels; a step that runs on the previous step's
+	// lists reads that instead of sorting and levelising again (b2gIslandKernel).
+	int planWrite, planRead;
+	int* planStart;	   // [bins][2][kColorSlots] first contact / first joint of every level, totals in the last entry
+	int4* planInfo;	   // [bins][capContacts] { wire slot, bin-local body A, B, SIMD-group bits } in the bin's final order
+	int* planJoints;   // [bins][capJoints] joint index, final order
 	int keepLists;	   // one block per bin, flat lists: the island kernel leaves the bins' counters as they are (the next step may run on the same lists, b2gEnqueueRun)
 	int flatLists;	   // one block per bin: b2gScatterKernel appends to flat per-bin lists, the island kernel sorts them by colour
 	int listCapContacts; // stride of the constraint lists (binCap*, or the per-block capacity with owner lists)
