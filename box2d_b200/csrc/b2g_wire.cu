@@ -1011,10 +1011,20 @@ static int b2gPumpUploads( b2GpuSolver* s, bool everything )
 	{
 		s->tracePump.emplace_back( std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(), (size_t)s->pumpPrefix );
 	}
+	if ( complete && !everything )
+	{
+		// everything is packed: what is left goes out in ONE copy, from the caller that ends the pass (a copy costs 5 - 10 us
+		// of driver time on the calling thread, and the last ones are on the step's critical path)
+		return 0;
+	}
 	while ( s->sendScan < restBlocks && s->blockSent[(size_t)s->sendScan] != 0 )
 	{
 		s->sendScan += 1;
 	}
+	// the end of what follows the constraints in the arena (the body regions; the masses' region only when some contact's
+	// differ from its bodies', b2g::WireRow)
+	const size_t arenaEnd = complete && everything ? ( s->massMismatch.load( std::memory_order_acquire ) != 0 ? s->inTotal : s->inMass ) : 0;
+	bool tailSent = false;
 	for ( int i = s->sendScan; i < restBlocks; )
 	{
 		if ( s->blockSent[(size_t)i] != 0 || s->workDone[i].load( std::memory_order_acquire ) == 0 )
@@ -1028,6 +1038,11 @@ static int b2gPumpUploads( b2GpuSolver* s, bool everything )
 			j += 1;
 		}
 		size_t from = b2gPackedPrefix( s, i ), upto = b2gPackedPrefix( s, j );
+		if ( complete && everything && j == restBlocks )
+		{
+			upto = arenaEnd; // the last run of constraints and the body regions behind it: one piece
+			tailSent = true;
+		}
 		if ( upto - from >= s->sendThreshold || ( complete && everything ) )
 		{
 			if ( b2gSendRange( s, from, upto ) != 0 )
@@ -1047,8 +1062,7 @@ static int b2gPumpUploads( b2GpuSolver* s, bool everything )
 	if ( complete && everything )
 	{
 		s->arenaSent = true;
-		// the masses' region only when some contact's differ from its bodies' (b2g::WireRow)
-		if ( b2gSendRange( s, s->inStates, s->massMismatch.load( std::memory_order_acquire ) != 0 ? s->inTotal : s->inMass ) != 0 )
+		if ( !tailSent && b2gSendRange( s, s->inStates, arenaEnd ) != 0 )
 		{
 			return 1;
 		}
