@@ -262,6 +262,7 @@ int b2gMaterializePendingFromSegs( b2GpuSolver* s, b2GpuStepResult* results )
 	return 0;
 }
 
+static const bool kPollAll = getenv( "B2GPU_POLL_ALL" ) != nullptr; // (experiment)
 static const int kPackPrefetch = []() {
 	const char* v = getenv( "B2GPU_PACK_PREFETCH" );
 	return v != nullptr ? atoi( v ) : 16;
@@ -1267,9 +1268,14 @@ extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 			}
 		}
 		size_t need = b2gOutPrefix( s, end2 > end ? end2 : end );
+		unsigned spins = 0;
 		while ( s->arrivedQuads.load( std::memory_order_acquire ) < need )
 		{
-			if ( b2gTryPumpDownloads( s ) != 0 )
+			// Whoever waits looks after the downloads -- the pump = 1 caller all the time, the others now and then: a dozen
+			// threads exchanging on the try-lock's cache line (and reading the host-mapped flag the device is about to
+			// write) for the whole length of the kernels slows down the one poll that matters, and everything else on a
+			// host that several ranks share.
+			if ( ( pump != 0 || kPollAll || ( ++spins & 63u ) == 0u ) && b2gTryPumpDownloads( s ) != 0 )
 			{
 				s->workFailed.store( 1 );
 				return 1;
