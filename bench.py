@@ -331,12 +331,14 @@ def _setup_distributed():
 
 def measured_traffic(workload: str):
 	"""DRAM bytes per step of the workload's kernels from the committed ncu --set full captures (profiles/), or None."""
-	path = ROOT / "profiles" / "r01_traffic.json"
-	try:
-		entry = json.loads(path.read_text()).get(workload)
-	except (OSError, ValueError):
-		return None
-	return entry["bytes"] if entry else None
+	for name in ("r02_traffic.json", "r01_traffic.json"):
+		try:
+			entry = json.loads((ROOT / "profiles" / name).read_text()).get(workload)
+		except (OSError, ValueError):
+			continue
+		if entry:
+			return entry["bytes"]
+	return None
 
 
 def run_scene(args) -> int:
