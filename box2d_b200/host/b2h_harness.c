@@ -622,6 +622,37 @@ static float b2hStepMutator( b2WorldId worldId, int stepIndex )
 			b2Body_SetTransform( body[43], (b2Pos){ -2.0f, 7.0f }, b2MakeRot( -0.2f ) );
 			b2World_Step( worldId, 0.0f, 4 );
 			break;
+		case 112:
+			// the application puts an island to sleep itself (src/body.c:1575 -> b2TrySleepIsland) ...
+			b2Body_SetAwake( body[15], false );
+			break;
+		case 116:
+		{
+			// ... asks for contact data and joint reactions in the middle of the run ...
+			b2ContactData data[8];
+			(void)b2Body_GetContactData( body[2], data, 8 );
+			(void)b2Joint_GetConstraintForce( w->mutJoints[2] );
+			break;
+		}
+		case 119:
+			// ... wakes it again, sets off an explosion next to the pile
+			b2Body_SetAwake( body[15], true );
+			{
+				b2ExplosionDef explosion = b2DefaultExplosionDef();
+				explosion.position = (b2Pos){ 0.0f, 2.0f };
+				explosion.radius = 3.0f;
+				explosion.falloff = 1.0f;
+				explosion.impulsePerLength = 2.0f;
+				b2World_Explode( worldId, &explosion );
+			}
+			break;
+		case 124:
+			// ... and takes a joint away
+			if ( w->mutJointCount > 1 )
+			{
+				b2DestroyJoint( w->mutJoints[1] );
+			}
+			break;
 		default:
 			break;
 	}

@@ -48,7 +48,7 @@ def test_impulses_stay_in_the_arena_until_somebody_reads_a_manifold(ref_lib, gpu
 		assert gpu.deferred_stats() == (False, 2)
 
 
-@pytest.mark.parametrize("scene,steps", [("falling_hinges", 300), ("rain", 240), ("contact_zoo", 200), ("mutator", 130), ("tumbler", 120)])
+@pytest.mark.parametrize("scene,steps", [("falling_hinges", 300), ("rain", 240), ("contact_zoo", 200), ("mutator", 150), ("tumbler", 120)])
 def test_nobody_looks_until_the_end(ref_lib, gpu_host_lib, scene, steps):
 	"""The whole run without a single reader from outside: islands fall asleep and wake up (falling_hinges: the reference's
 	determinism golden, test/test_determinism.c:22-23), bodies are destroyed and created (rain, mutator), manifolds are

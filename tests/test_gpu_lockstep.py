@@ -32,7 +32,7 @@ SCENES = [
 	("washer", 40, 5),
 	# the host changes the world between steps through the public API (box2d_b200/host/b2h_harness.c, b2hStepMutator): gravity,
 	# velocities, masses, friction, motors, tuning, warm starting, teleports, body types, destroy / create, sub-step count
-	("mutator", 130, 1),
+	("mutator", 150, 1),
 ]
 
 # BASELINE.json's configurations at the step counts of the reference's benchmark (benchmark/main.c:149-160), compared EVERY step
@@ -104,7 +104,7 @@ def test_profile_stage_fields_come_from_the_device(gpu_host_lib):
 @pytest.mark.parametrize("workers", [1, 3, 16])
 def test_lockstep_with_other_worker_counts(ref_lib, gpu_host_lib, workers):
 	"""The seam's team (box2d_b200/host/b2_gpu_seam.c): no helpers at all, an odd number, more workers than there is work for."""
-	for scene, steps in (("mutator", 110), ("falling_hinges", 60), ("rain", 80)):
+	for scene, steps in (("mutator", 135), ("falling_hinges", 60), ("rain", 80)):
 		with b2.World(ref_lib, scene, workers) as ref, b2.World(gpu_host_lib, scene, workers) as gpu:
 			for step in range(steps):
 				ref.step()
