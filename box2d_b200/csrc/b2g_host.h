@@ -369,6 +369,12 @@ struct b2GpuSolver
 	size_t inStates = 0, inBody = 0, inWire = 0, inJoints = 0, inBins = 0, inMass = 0, inTotal = 0;
 	bool checkMasses = true; // this step's pack pass compares the contacts' masses with the bodies'
 	std::atomic<int> massMismatch{ 0 }; // pack pass: some contact's masses differ from its bodies' -> the mass region is uploaded
+	// the copies that end a step's upload (the last piece of the arena, the streams of full records) go out in ONE driver
+	// call (cudaMemcpyBatchAsync): each call costs 5 - 10 us on the calling thread and these are on the critical path
+	bool batching = false;
+	bool batchEnabled = true; // B2GPU_BATCH_COPIES=0
+	std::vector<void*> batchDst, batchSrc;
+	std::vector<size_t> batchBytes;
 	bool uploadStarted = false;		// evUpload recorded (first copy of the step)
 	bool arenaSent = false;			// the whole input arena has been enqueued for upload
 	std::vector<uint8_t> blockSent; // pack blocks whose part of the input arena has been enqueued for upload (b2gPumpUploads)

@@ -183,6 +183,8 @@ extern "C" b2GpuSolver* b2GpuSolverCreate( int device )
 		// at ~192 us, the link is the limit, not snoops.)
 		const char* chunkEnv = getenv( "B2GPU_DOWNLOAD_KIB" );
 		s->downloadQuads = chunkEnv != nullptr && atoi( chunkEnv ) >= 16 ? (size_t)atoi( chunkEnv ) * 64 : kDownloadQuads;
+		const char* batchEnv = getenv( "B2GPU_BATCH_COPIES" );
+		s->batchEnabled = batchEnv == nullptr || atoi( batchEnv ) != 0;
 		const char* keepEnv = getenv( "B2GPU_KEEP_LISTS" );
 		s->keepListsEnabled = keepEnv == nullptr || atoi( keepEnv ) != 0;
 		const char* directEnv = getenv( "B2GPU_DIRECT_OUT" );

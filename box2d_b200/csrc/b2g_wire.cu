@@ -724,6 +724,53 @@ static size_t b2gPackedPrefix( const b2GpuSolver* s, int blocksDone )
 	return s->inJoints + (size_t)( flat - s->contactTotal ) * s->jointWireQuads;
 }
 
+// one host -> device copy on the solver's stream, or -- while the step's last copies are being collected -- an entry of the batch
+static int b2gCopyUp( b2GpuSolver* s, void* dst, const void* src, size_t bytes )
+{
+	if ( s->batching )
+	{
+		s->batchDst.push_back( dst );
+		s->batchSrc.push_back( const_cast<void*>( src ) );
+		s->batchBytes.push_back( bytes );
+		return 0;
+	}
+	B2G_CUDA( cudaMemcpyAsync( dst, src, bytes, cudaMemcpyHostToDevice, s->stream ) );
+	return 0;
+}
+
+static int b2gFlushBatch( b2GpuSolver* s )
+{
+	s->batching = false;
+	const size_t count = s->batchDst.size();
+	int rc = 0;
+	if ( count > 1 )
+	{
+		cudaMemcpyAttributes attributes = {};
+		attributes.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+		size_t attributeIndex = 0, failed = 0;
+		cudaError_t err = cudaMemcpyBatchAsync( s->batchDst.data(), s->batchSrc.data(), s->batchBytes.data(), count, &attributes, &attributeIndex, 1,
+												&failed, s->stream );
+		if ( err != cudaSuccess )
+		{
+			// (a driver without the batch call: one copy each, from now on)
+			cudaGetLastError();
+			s->batchEnabled = false;
+			for ( size_t i = 0; i < count && rc == 0; ++i )
+			{
+				rc = b2gCopyUp( s, s->batchDst[i], s->batchSrc[i], s->batchBytes[i] );
+			}
+		}
+	}
+	else if ( count == 1 )
+	{
+		rc = b2gCopyUp( s, s->batchDst[0], s->batchSrc[0], s->batchBytes[0] );
+	}
+	s->batchDst.clear();
+	s->batchSrc.clear();
+	s->batchBytes.clear();
+	return rc;
+}
+
 // enqueue the upload of quads [fromQuads, uptoQuads) of the input arena
 static int b2gSendRange( b2GpuSolver* s, size_t fromQuads, size_t uptoQuads )
 {
@@ -738,8 +785,7 @@ static int b2gSendRange( b2GpuSolver* s, size_t fromQuads, size_t uptoQuads )
 		{
 			s->traceSends.emplace_back( std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count(), uptoQuads );
 		}
-		B2G_CUDA( cudaMemcpyAsync( s->wireAll.ptr + fromQuads, s->hWire.ptr + fromQuads, ( uptoQuads - fromQuads ) * sizeof( float4 ),
-								   cudaMemcpyHostToDevice, s->stream ) );
+		return b2gCopyUp( s, s->wireAll.ptr + fromQuads, s->hWire.ptr + fromQuads, ( uptoQuads - fromQuads ) * sizeof( float4 ) );
 	}
 	return 0;
 }
@@ -758,19 +804,19 @@ static int b2gSendStreams( b2GpuSolver* s )
 	int full = s->fullCursor.load( std::memory_order_acquire ), dirty = s->dirtyCursor.load( std::memory_order_acquire );
 	full = full < s->fullCapacity ? full : s->fullCapacity;
 	dirty = dirty < s->dirtyCapacity ? dirty : s->dirtyCapacity;
-	if ( full > 0 )
+	if ( full > 0 && b2gCopyUp( s, s->fullStream.ptr, s->hFull.ptr, (size_t)full * b2g::WR_COUNT * sizeof( float4 ) ) != 0 )
 	{
-		B2G_CUDA( cudaMemcpyAsync( s->fullStream.ptr, s->hFull.ptr, (size_t)full * b2g::WR_COUNT * sizeof( float4 ), cudaMemcpyHostToDevice, s->stream ) );
+		return 1;
 	}
-	if ( dirty > 0 )
+	if ( dirty > 0 && b2gCopyUp( s, s->dirtyStream.ptr, s->hDirty.ptr, (size_t)dirty * b2g::kDirtyBodyQuads * sizeof( float4 ) ) != 0 )
 	{
-		B2G_CUDA( cudaMemcpyAsync( s->dirtyStream.ptr, s->hDirty.ptr, (size_t)dirty * b2g::kDirtyBodyQuads * sizeof( float4 ), cudaMemcpyHostToDevice, s->stream ) );
+		return 1;
 	}
 	int fullJoints = s->fullJointCursor.load( std::memory_order_acquire );
 	fullJoints = fullJoints < s->fullJointCapacity ? fullJoints : s->fullJointCapacity;
-	if ( fullJoints > 0 )
+	if ( fullJoints > 0 && b2gCopyUp( s, s->fullJointStream.ptr, s->hFullJoints.ptr, (size_t)fullJoints * b2g::kJointStride ) != 0 )
 	{
-		B2G_CUDA( cudaMemcpyAsync( s->fullJointStream.ptr, s->hFullJoints.ptr, (size_t)fullJoints * b2g::kJointStride, cudaMemcpyHostToDevice, s->stream ) );
+		return 1;
 	}
 	s->fullSent = full;
 	s->dirtySent = dirty;
@@ -1026,6 +1072,7 @@ static int b2gPumpUploads( b2GpuSolver* s, bool everything )
 	// differ from its bodies', b2g::WireRow)
 	const size_t arenaEnd = complete && everything ? ( s->massMismatch.load( std::memory_order_acquire ) != 0 ? s->inTotal : s->inMass ) : 0;
 	bool tailSent = false;
+	s->batching = complete && everything && s->batchEnabled; // the step's last copies: one driver call (b2gFlushBatch)
 	for ( int i = s->sendScan; i < restBlocks; )
 	{
 		if ( s->blockSent[(size_t)i] != 0 || s->workDone[i].load( std::memory_order_acquire ) == 0 )
@@ -1063,11 +1110,12 @@ static int b2gPumpUploads( b2GpuSolver* s, bool everything )
 	if ( complete && everything )
 	{
 		s->arenaSent = true;
-		if ( !tailSent && b2gSendRange( s, s->inStates, arenaEnd ) != 0 )
+		if ( ( !tailSent && b2gSendRange( s, s->inStates, arenaEnd ) != 0 ) || b2gSendStreams( s ) != 0 )
 		{
+			s->batching = false;
 			return 1;
 		}
-		return b2gSendStreams( s );
+		return b2gFlushBatch( s );
 	}
 	return 0;
 }
