@@ -176,6 +176,10 @@ def solver_lib() -> ctypes.CDLL:
 	lib.b2GpuSolverDeferredSync.argtypes = [ctypes.c_void_p]
 	lib.b2GpuSolverMaterializeContacts.restype = ctypes.c_int
 	lib.b2GpuSolverMaterializeContacts.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int, P(StepResult)]
+	lib.b2GpuSolverMaterializeJoints.restype = ctypes.c_int
+	lib.b2GpuSolverMaterializeJoints.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+	lib.b2GpuSolverDeferredForgetJoint.restype = None
+	lib.b2GpuSolverDeferredForgetJoint.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
 	lib.b2GpuSolverDeferredForget.restype = None
 	lib.b2GpuSolverDeferredForget.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int]
 	lib.b2GpuSolverDeferredDone.restype = None
@@ -560,10 +564,16 @@ class GpuSolver:
 	def deferred_pending(self) -> bool:
 		return bool(self.lib.b2GpuSolverDeferredPending(self.handle))
 
-	def materialize(self, desc: StepDesc, contact_arrays, result: StepResult = None, done: bool = True) -> int:
-		"""b2GpuSolverMaterializeContacts over the colours' byte arrays of b2ContactSim (in the descriptor's order: the active
-		colours, then the overflow colour); done = nothing is pending afterwards."""
+	def materialize(self, desc: StepDesc, contact_arrays, result: StepResult = None, done: bool = True, joint_arrays=None) -> int:
+		"""b2GpuSolverMaterializeContacts (and, with joint_arrays, b2GpuSolverMaterializeJoints) over the colours' byte arrays
+		of b2ContactSim / b2JointSim (in the descriptor's order: the active colours, then the overflow colour); done = nothing
+		is pending afterwards.  Returns the number of manifolds written."""
 		total = 0
+		for c, arr in enumerate(joint_arrays or []):
+			if arr.size:
+				color = desc.colors[c] if c < desc.activeColorCount else desc.overflow
+				if self.lib.b2GpuSolverMaterializeJoints(self.handle, color.colorIndex, 0, arr.ctypes.data, arr.size // JOINT_SIZE) < 0:
+					raise RuntimeError("b2GpuSolverMaterializeJoints failed: " + self.lib.b2GpuGetLastError().decode())
 		for c, arr in enumerate(contact_arrays):
 			if arr.size:
 				color = desc.colors[c] if c < desc.activeColorCount else desc.overflow

@@ -345,6 +345,11 @@ struct b2GpuSolver
 	uint32_t deferStamp = 0;		// of the pending step (0: never)
 	uint32_t deferNewStamp = 1;		// of the step in flight
 	std::vector<uint32_t> consumedStamp; // by home
+	// ... and the joints' output records likewise: found by the joint's home, identified by the joint id in the home's shadow
+	std::vector<uint32_t> consumedJointStamp; // by joint home
+	bool deferJointsPending = false;
+	bool jointHomesOrdered = true;
+	const float* pendingJointRecords = nullptr; // B2L_JOINT_OUT_FLOATS per joint of the pending step, by its place among the step's joints
 	bool homesOrdered = true;		// the homes' keys are the callers' graph colour indices (they came in ascending order)
 	const float* pendingRecords = nullptr; // the pending step's impulse records, by wire slot
 	const float* prevRecords = nullptr;	   // the previous resident step's (what the device warm-starts clean contacts from)

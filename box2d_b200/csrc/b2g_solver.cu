@@ -1069,9 +1069,10 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	s->outStates = 0;
 	if ( s->defer )
 	{
-		s->outJoints = s->outStates + 2 * nb;
-		s->outBits = s->outJoints + (size_t)( B2L_JOINT_OUT_FLOATS / 4 ) * joint;
-		s->outImpulses = s->outBits + ( (size_t)P.jointWords + 3 ) / 4;
+		// (what the step waits for first: the states and the joint-event bits; then the records nobody waits for)
+		s->outBits = s->outStates + 2 * nb;
+		s->outJoints = s->outBits + ( (size_t)P.jointWords + 3 ) / 4;
+		s->outImpulses = s->outJoints + (size_t)( B2L_JOINT_OUT_FLOATS / 4 ) * joint;
 		s->outTotal = s->outImpulses + impulseQuads;
 	}
 	else
@@ -1184,6 +1185,15 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 				s->jointSegHome[k] = key;
 				fits = fits && seg.count <= s->jointHomeBase[key + 1] - s->jointHomeBase[key];
 			}
+			if ( s->deferJointsPending && ( !fits || ordered != s->jointHomesOrdered ) )
+			{
+				// (the joints' homes are about to move: see the contacts' homes above)
+				if ( b2gMaterializePendingFromSegs( s, nullptr ) != 0 )
+				{
+					return 1;
+				}
+			}
+			s->jointHomesOrdered = ordered;
 			if ( !fits )
 			{
 				int need[kHomeColors] = { 0 };
@@ -1266,6 +1276,10 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 		{
 			s->consumedStamp.resize( (size_t)s->homeTotal + 1, 0 );
 		}
+		if ( s->consumedJointStamp.size() < (size_t)s->jointHomeTotal + 1 )
+		{
+			s->consumedJointStamp.resize( (size_t)s->jointHomeTotal + 1, 0 );
+		}
 		s->deferNewStamp += 1;
 		if ( s->deferNewStamp == 0 )
 		{
@@ -1275,6 +1289,7 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 				return 1;
 			}
 			s->consumedStamp.assign( s->consumedStamp.size(), 0 );
+			s->consumedJointStamp.assign( s->consumedJointStamp.size(), 0 );
 			s->deferNewStamp = 1;
 		}
 		// the pack pass reads the previous step's records (a contact it has no word on: are its impulses still the device's?)
@@ -1331,15 +1346,15 @@ static int b2gBegin( b2GpuSolver* s, const b2GpuStepDesc* descs, int worldCount,
 	P.g.joints = reinterpret_cast<uint8_t*>( s->jointWork.ptr ); // working copy of the joint records (grid kernel, spilled joints)
 	P.outJoints = reinterpret_cast<float*>( s->outAll.ptr + s->outJoints );
 	P.outStates = reinterpret_cast<uint8_t*>( s->outAll.ptr + s->outStates );
-	// (a step with joints waits for their output records anyway -- they come by DMA, being the next step's device-side
-	// inputs as well -- so the stores over PCIe would only add to its kernels: measured on joint_grid, +9 us)
-	s->direct = s->defer && s->directEnabled && joint == 0;
+	// (the joint-event bits, set with atomics in device memory, follow by DMA; the joints' output records are deferred like
+	// the contacts')
+	s->direct = s->defer && s->directEnabled;
 	s->directEnd = 0;
 	if ( s->direct )
 	{
 		// (page-locked host memory has the same address on the device: unified addressing)
 		P.outStates = reinterpret_cast<uint8_t*>( s->hOut.ptr + s->outStates );
-		s->directEnd = s->outJoints; // the states are the arena's first region
+		s->directEnd = s->outBits; // the states are the arena's first region
 	}
 	P.outImpulses = reinterpret_cast<float*>( s->outAll.ptr + s->outImpulses );
 	P.jointBits = reinterpret_cast<uint32_t*>( s->outAll.ptr + s->outBits );
@@ -1846,7 +1861,7 @@ int b2gEnqueueDownload( b2GpuSolver* s )
 	const size_t chunkQuads = s->downloadQuads;
 	s->chunkEnd.clear();
 	// deferred impulses: the arena's tail holds the records nobody waits for (one piece, one event)
-	const size_t awaited = s->defer ? s->outImpulses : total;
+	const size_t awaited = s->defer ? s->outJoints : total; // (deferred: the states and the joint-event bits)
 	s->deferWaitChunks = 0;
 	int made = 0;
 	for ( size_t begin = s->direct ? s->directEnd : 0; begin < total; )
@@ -1904,7 +1919,7 @@ extern "C" int b2GpuSolverSubmit( b2GpuSolver* s )
 		return 1;
 	}
 	// deferred impulses: the unpack pass has the bodies and the joints to do (b2GpuSolverUnpackWork skips the contacts' items)
-	const int unpackItems = b2GpuSolverGetUnpackItemCount( s ) - ( s->defer ? s->contactTotal : 0 );
+	const int unpackItems = b2GpuSolverGetUnpackItemCount( s ) - ( s->defer ? s->contactTotal + s->jointTotal : 0 );
 	b2gResetWork( s, unpackItems, b2gBlocksFor( s, unpackItems ) );
 	return 0;
 }
@@ -1962,6 +1977,7 @@ extern "C" void b2GpuSolverDeferredDone( b2GpuSolver* s )
 	if ( s != nullptr )
 	{
 		s->deferPending = false;
+		s->deferJointsPending = false;
 	}
 }
 
@@ -2094,7 +2110,9 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 			// ... and its impulse records wait in the arena that was just filled (the tail may still be on its way)
 			std::swap( s->hOut, s->hOutOther );
 			s->pendingRecords = reinterpret_cast<const float*>( s->hOutOther.ptr + s->outImpulses );
-			s->deferPending = s->contactTotal > 0;
+			s->pendingJointRecords = reinterpret_cast<const float*>( s->hOutOther.ptr + s->outJoints );
+			s->deferJointsPending = s->jointTotal > 0;
+			s->deferPending = s->contactTotal > 0 || s->jointTotal > 0;
 			s->deferStamp = s->deferNewStamp;
 			s->recordsSynced.store( 0, std::memory_order_release );
 			deferredNow = s->deferPending;
@@ -2124,7 +2142,7 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 		}
 		s->cacheValid = true;
 	}
-	if ( deferredNow && !s->homesOrdered )
+	if ( deferredNow && ( !s->homesOrdered || ( s->jointTotal > 0 && !s->jointHomesOrdered ) ) )
 	{
 		// pending records are found by (graph colour, place); a caller whose colours do not come with ascending indices has
 		// no such address: its manifolds are written now, like a step that does not defer

@@ -223,6 +223,71 @@ extern "C" void b2GpuSolverDeferredForget( b2GpuSolver* s, int colorIndex, int i
 	}
 }
 
+// The joint `sim` sits at place `index` of the colour with home key `key`: if that is where it was when the pending step was
+// solved and its output record has not been used yet, the fields the stages wrote (b2lJointMutableRuns: the accumulated
+// impulses, ...) go into the b2JointSim -- and into the shadow of what the device's table holds, like the unpack pass does.
+static inline int b2gMaterializeJointAt( b2GpuSolver* s, int key, int index, uint8_t* sim )
+{
+	if ( index >= s->jointHomeCount[key] )
+	{
+		return 0;
+	}
+	const int home = s->jointHomeBase[key] + index;
+	uint8_t* shadow = s->shadowJoints.data() + (size_t)home * b2g::kJointStride;
+	if ( s->consumedJointStamp[(size_t)home] == s->deferStamp ||
+		 *reinterpret_cast<const int*>( shadow + offsetof( b2lJointSim, jointId ) ) != *reinterpret_cast<const int*>( sim + offsetof( b2lJointSim, jointId ) ) )
+	{
+		return 0; // used, or another joint's place
+	}
+	const float* record = s->pendingJointRecords + (size_t)( s->jointHomeSlot[key] + index ) * B2L_JOINT_OUT_FLOATS;
+	int offsets[2], floats[2];
+	int runs = b2lJointMutableRuns( *reinterpret_cast<const int*>( sim + offsetof( b2lJointSim, type ) ), offsets, floats );
+	for ( int r = 0; r < runs; ++r )
+	{
+		memcpy( sim + offsets[r], record, (size_t)floats[r] * sizeof( float ) );
+		memcpy( shadow + offsets[r], record, (size_t)floats[r] * sizeof( float ) );
+		record += floats[r];
+	}
+	s->consumedJointStamp[(size_t)home] = s->deferStamp;
+	return 1;
+}
+
+extern "C" int b2GpuSolverMaterializeJoints( b2GpuSolver* s, int colorIndex, int firstIndex, void* jointSims, int count )
+{
+	if ( s == nullptr || !s->deferJointsPending || count <= 0 || firstIndex < 0 )
+	{
+		return 0;
+	}
+	const int key = s->jointHomesOrdered && colorIndex >= 0 && colorIndex < kHomeColors ? colorIndex : -1;
+	if ( key < 0 )
+	{
+		return 0;
+	}
+	if ( b2gDeferSync( s ) != 0 )
+	{
+		return -1;
+	}
+	uint8_t* sims = static_cast<uint8_t*>( jointSims );
+	int done = 0;
+	for ( int i = 0; i < count; ++i )
+	{
+		done += b2gMaterializeJointAt( s, key, firstIndex + i, sims + (size_t)i * B2L_JOINT_SIZE );
+	}
+	return done;
+}
+
+extern "C" void b2GpuSolverDeferredForgetJoint( b2GpuSolver* s, int colorIndex, int index )
+{
+	if ( s == nullptr || !s->deferJointsPending || index < 0 || !s->jointHomesOrdered || colorIndex < 0 || colorIndex >= kHomeColors )
+	{
+		return;
+	}
+	if ( index < s->jointHomeCount[colorIndex] )
+	{
+		s->consumedJointStamp[(size_t)( s->jointHomeBase[colorIndex] + index )] = s->deferStamp;
+	}
+}
+
 // every pending record goes into its manifold, the contacts found in the arrays of the step that is being laid out (or has
 // just ended): s->contactSegs
 int b2gMaterializePendingFromSegs( b2GpuSolver* s, b2GpuStepResult* results )
@@ -236,6 +301,22 @@ int b2gMaterializePendingFromSegs( b2GpuSolver* s, b2GpuStepResult* results )
 		return 1;
 	}
 	int done = 0;
+	if ( s->deferJointsPending && s->jointHomesOrdered )
+	{
+		for ( const b2gJointSeg& seg : s->jointSegs )
+		{
+			const int key = seg.overflow ? kHomeColors - 1 : seg.colorIndex;
+			if ( key < 0 || key >= kHomeColors || ( !seg.overflow && key == kHomeColors - 1 ) )
+			{
+				continue;
+			}
+			for ( int i = 0; i < seg.count; ++i )
+			{
+				b2gMaterializeJointAt( s, key, i, seg.sims + (size_t)i * B2L_JOINT_SIZE );
+			}
+		}
+	}
+	s->deferJointsPending = false;
 	for ( const b2gContactSeg& seg : s->contactSegs )
 	{
 		const int key = seg.wide ? b2gHomeKeyOf( s, seg.colorIndex ) : kHomeColors - 1;
@@ -629,8 +710,28 @@ extern "C" void b2GpuSolverPackRange( b2GpuSolver* s, int begin, int end )
 				uint8_t* shadow = s->shadowJoints.data() + (size_t)home * b2g::kJointStride;
 				int runOffset = 0;
 				const int runBytes = b2lJointPreparedRun( reinterpret_cast<const b2lJointSim*>( padded )->type, &runOffset );
-				const bool clean = i < homeCount && memcmp( shadow, padded, (size_t)runOffset ) == 0 &&
-								   memcmp( shadow + runOffset + runBytes, padded + runOffset + runBytes, (size_t)( b2g::kJointStride - runOffset - runBytes ) ) == 0;
+				auto sameOutsideTheRun = [&]() {
+					return i < homeCount && memcmp( shadow, padded, (size_t)runOffset ) == 0 &&
+						   memcmp( shadow + runOffset + runBytes, padded + runOffset + runBytes, (size_t)( b2g::kJointStride - runOffset - runBytes ) ) == 0;
+				};
+				bool clean = sameOutsideTheRun();
+				if ( !clean && s->defer && s->deferJointsPending &&
+					 b2gMaterializeJointAt( s, homeKey, i, seg.sims + (size_t)i * B2L_JOINT_SIZE ) != 0 )
+				{
+					// the record travels in full: the previous step's outputs, which never reached this b2JointSim (nobody has read
+					// it since), do now -- and the record is built again from what it holds then
+					memcpy( padded, seg.sims + (size_t)i * B2L_JOINT_SIZE, B2L_JOINT_SIZE );
+					if ( world.base != 0 )
+					{
+						int* pair = b2gJointIndexPair( reinterpret_cast<b2lJointSim*>( padded ) );
+						if ( pair != nullptr )
+						{
+							pair[0] = pair[0] >= 0 ? pair[0] + world.base : pair[0];
+							pair[1] = pair[1] >= 0 ? pair[1] + world.base : pair[1];
+						}
+					}
+					clean = sameOutsideTheRun();
+				}
 				float4* light = wireJoints + (size_t)( seg.jointStart + i ) * b2g::kLightJointQuads;
 				int ref = homeSlot + i; // its record among the previous step's outputs
 				if ( clean )
@@ -994,6 +1095,8 @@ extern "C" void b2GpuSolverUnpackRange( b2GpuSolver* s, int begin, int end )
 	}
 
 	// ---- joints: the fields the stages wrote (b2lJointMutableRuns) go back into the reference's b2JointSim in place
+	// (deferred: not here -- b2GpuSolverMaterializeJoints, when somebody needs them)
+	if ( !s->defer )
 	{
 		const float* outJoints = reinterpret_cast<const float*>( base + s->outJoints );
 		int first = bodyCount + s->contactTotal;
@@ -1302,18 +1405,10 @@ extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 		int begin2 = 0, end2 = 0; // deferred impulses: the items are the bodies and the joints, a block may hold some of both
 		if ( s->defer )
 		{
-			const int bodyCount = s->params.bodyCount, skip = s->contactTotal;
-			if ( begin >= bodyCount )
-			{
-				begin += skip;
-				end += skip;
-			}
-			else if ( end > bodyCount )
-			{
-				begin2 = bodyCount + skip;
-				end2 = end + skip;
-				end = bodyCount;
-			}
+			// (the items are the bodies: the contacts' and the joints' records are deferred)
+			const int bodyCount = s->params.bodyCount;
+			begin = begin < bodyCount ? begin : bodyCount;
+			end = end < bodyCount ? end : bodyCount;
 		}
 		size_t need = b2gOutPrefix( s, end2 > end ? end2 : end );
 		unsigned spins = 0;

@@ -458,6 +458,53 @@ void b2GpuSeam_ContactReevaluated( b2World* world, int workerIndex, int contactI
 	}
 }
 
+/* A flush in the middle of a step (an island goes to sleep, hit events): the world's workers share it.  The colours' contact
+ * arrays, then their joint arrays, laid end to end; b2ParallelFor deals out ranges of that. */
+typedef struct b2SeamFlushJob
+{
+	b2World* world;
+	b2GpuSolver* solver;
+	b2GpuStepResult* result;
+	int starts[2 * B2_GRAPH_COLOR_COUNT + 1];
+	int failed;
+} b2SeamFlushJob;
+
+static void b2SeamFlushTask( int startIndex, int endIndex, int workerIndex, void* context )
+{
+	(void)workerIndex;
+	b2SeamFlushJob* job = context;
+	int segment = 0;
+	while ( job->starts[segment + 1] <= startIndex )
+	{
+		segment += 1;
+	}
+	for ( int at = startIndex; at < endIndex; )
+	{
+		while ( job->starts[segment + 1] <= at )
+		{
+			segment += 1;
+		}
+		int upto = endIndex < job->starts[segment + 1] ? endIndex : job->starts[segment + 1];
+		int first = at - job->starts[segment], count = upto - at;
+		int rc;
+		if ( segment < B2_GRAPH_COLOR_COUNT )
+		{
+			b2GraphColor* color = job->world->constraintGraph.colors + segment;
+			rc = b2GpuSolverMaterializeContacts( job->solver, segment, first, color->contactSims.data + first, count, job->result );
+		}
+		else
+		{
+			b2GraphColor* color = job->world->constraintGraph.colors + ( segment - B2_GRAPH_COLOR_COUNT );
+			rc = b2GpuSolverMaterializeJoints( job->solver, segment - B2_GRAPH_COLOR_COUNT, first, color->jointSims.data + first, count );
+		}
+		if ( rc < 0 )
+		{
+			job->failed = 1;
+		}
+		at = upto;
+	}
+}
+
 /* every contact of the constraint graph that still waits for its impulses receives them */
 static void b2SeamFlushImpulses( b2World* world, b2GpuStepResult* result )
 {
@@ -470,6 +517,31 @@ static void b2SeamFlushImpulses( b2World* world, b2GpuStepResult* result )
 	{
 		return;
 	}
+	if ( world->locked && world->workerCount > 1 )
+	{
+		// inside b2World_Step, on the stepping thread, between the reference's own parallel passes
+		b2SeamFlushJob job = { world, slot->solver, result, { 0 }, 0 };
+		for ( int i = 0; i < B2_GRAPH_COLOR_COUNT; ++i )
+		{
+			job.starts[i + 1] = job.starts[i] + world->constraintGraph.colors[i].contactSims.count;
+		}
+		for ( int i = 0; i < B2_GRAPH_COLOR_COUNT; ++i )
+		{
+			job.starts[B2_GRAPH_COLOR_COUNT + i + 1] = job.starts[B2_GRAPH_COLOR_COUNT + i] + world->constraintGraph.colors[i].jointSims.count;
+		}
+		int total = job.starts[2 * B2_GRAPH_COLOR_COUNT];
+		if ( total >= 4096 && b2GpuSolverDeferredSync( slot->solver ) == 0 )
+		{
+			b2ParallelFor( world, b2SeamFlushTask, total, 512, &job );
+			if ( job.failed )
+			{
+				b2SeamFatal( "b2GpuSolverMaterializeContacts" );
+			}
+			b2GpuSolverDeferredDone( slot->solver );
+			slot->flushes += 1;
+			return;
+		}
+	}
 	for ( int i = 0; i < B2_GRAPH_COLOR_COUNT; ++i )
 	{
 		b2GraphColor* color = world->constraintGraph.colors + i;
@@ -477,6 +549,10 @@ static void b2SeamFlushImpulses( b2World* world, b2GpuStepResult* result )
 			 b2GpuSolverMaterializeContacts( slot->solver, i, 0, color->contactSims.data, color->contactSims.count, result ) < 0 )
 		{
 			b2SeamFatal( "b2GpuSolverMaterializeContacts" );
+		}
+		if ( color->jointSims.count > 0 && b2GpuSolverMaterializeJoints( slot->solver, i, 0, color->jointSims.data, color->jointSims.count ) < 0 )
+		{
+			b2SeamFatal( "b2GpuSolverMaterializeJoints" );
 		}
 	}
 	b2GpuSolverDeferredDone( slot->solver );
@@ -632,6 +708,100 @@ void b2RemoveContactFromGraph( b2World* world, int bodyIdA, int bodyIdB, int col
 		}
 	}
 	b2Ref_RemoveContactFromGraph( world, bodyIdA, bodyIdB, colorIndex, localIndex );
+}
+
+/* The joints' accumulated impulses are deferred like the contacts' (b2GpuSolverMaterializeJoints).  Their readers and writers
+ * on the host all fetch the b2JointSim first: the per-type API through b2GetJointSimCheckType (src/joint.c:143; 124 call sites
+ * in src/*_joint.c), the generic reaction getters through b2GetJointSim inside src/joint.c.  A joint receives what is owed to
+ * it before it is handed out, before it moves in its colour's array, and before it leaves the awake set. */
+b2JointSim* b2Ref_GetJointSimCheckType( b2JointId jointId, b2JointType type );
+b2Vec2 b2Ref_Joint_GetConstraintForce( b2JointId jointId );
+float b2Ref_Joint_GetConstraintTorque( b2JointId jointId );
+void b2Ref_RemoveJointFromGraph( b2World* world, int bodyIdA, int bodyIdB, int colorIndex, int localIndex );
+void b2Ref_TransferJoint( b2World* world, b2SolverSet* targetSet, b2SolverSet* sourceSet, b2Joint* joint );
+
+static void b2SeamMaterializeJointAt( b2World* world, int colorIndex, int localIndex )
+{
+	b2SeamSlot* slot = s_slots + world->worldId;
+	if ( slot->solver == NULL || slot->generation != world->generation || b2GpuSolverDeferredPending( slot->solver ) == 0 )
+	{
+		return;
+	}
+	if ( colorIndex < 0 || colorIndex >= B2_GRAPH_COLOR_COUNT )
+	{
+		return;
+	}
+	b2GraphColor* color = world->constraintGraph.colors + colorIndex;
+	if ( 0 <= localIndex && localIndex < color->jointSims.count &&
+		 b2GpuSolverMaterializeJoints( slot->solver, colorIndex, localIndex, color->jointSims.data + localIndex, 1 ) < 0 )
+	{
+		b2SeamFatal( "b2GpuSolverMaterializeJoints" );
+	}
+}
+
+static void b2SeamMaterializeJointId( b2JointId jointId )
+{
+	int worldIndex = jointId.world0;
+	if ( worldIndex < 0 || worldIndex >= B2_MAX_WORLDS || s_slots[worldIndex].solver == NULL )
+	{
+		return;
+	}
+	b2World* world = b2GetWorld( worldIndex );
+	int id = jointId.index1 - 1;
+	if ( world->inUse == false || id < 0 || id >= world->joints.count )
+	{
+		return;
+	}
+	const b2Joint* joint = world->joints.data + id;
+	if ( joint->setIndex == b2_awakeSet && joint->generation == jointId.generation )
+	{
+		b2SeamMaterializeJointAt( world, joint->colorIndex, joint->localIndex );
+	}
+}
+
+b2JointSim* b2GetJointSimCheckType( b2JointId jointId, b2JointType type )
+{
+	b2SeamMaterializeJointId( jointId );
+	return b2Ref_GetJointSimCheckType( jointId, type );
+}
+
+b2Vec2 b2Joint_GetConstraintForce( b2JointId jointId )
+{
+	b2SeamMaterializeJointId( jointId );
+	return b2Ref_Joint_GetConstraintForce( jointId );
+}
+
+float b2Joint_GetConstraintTorque( b2JointId jointId )
+{
+	b2SeamMaterializeJointId( jointId );
+	return b2Ref_Joint_GetConstraintTorque( jointId );
+}
+
+void b2RemoveJointFromGraph( b2World* world, int bodyIdA, int bodyIdB, int colorIndex, int localIndex )
+{
+	if ( 0 <= colorIndex && colorIndex < B2_GRAPH_COLOR_COUNT )
+	{
+		// the joint that leaves keeps its b2JointSim elsewhere (another set) or is destroyed; the colour's last joint is about to
+		// move into its place (src/constraint_graph.c:312-324): both receive their impulses first, and the place is void
+		b2SeamMaterializeJointAt( world, colorIndex, localIndex );
+		b2SeamMaterializeJointAt( world, colorIndex, world->constraintGraph.colors[colorIndex].jointSims.count - 1 );
+		b2SeamSlot* slot = s_slots + world->worldId;
+		if ( slot->solver != NULL && slot->generation == world->generation )
+		{
+			b2GpuSolverDeferredForgetJoint( slot->solver, colorIndex, localIndex );
+		}
+	}
+	b2Ref_RemoveJointFromGraph( world, bodyIdA, bodyIdB, colorIndex, localIndex );
+}
+
+void b2TransferJoint( b2World* world, b2SolverSet* targetSet, b2SolverSet* sourceSet, b2Joint* joint )
+{
+	// (copies the b2JointSim to the target set BEFORE it takes it out of the graph, src/solver_set.c:573-591)
+	if ( sourceSet != targetSet && sourceSet->setIndex == b2_awakeSet )
+	{
+		b2SeamMaterializeJointAt( world, joint->colorIndex, joint->localIndex );
+	}
+	b2Ref_TransferJoint( world, targetSet, sourceSet, joint );
 }
 
 void b2TrySleepIsland( b2World* world, int islandId )
@@ -858,6 +1028,13 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 	{
 		b2SeamSolveInGroup( world, context, slot );
 		return;
+	}
+
+	if ( world->enableWarmStarting == false )
+	{
+		// b2Prepare*Joint is about to zero the joints' impulses on the host (e.g. src/revolute_joint.c:273-280): what the
+		// previous step computed must be in the b2JointSims before that, or it would be written over the zeroes later
+		b2SeamFlushImpulses( world, NULL );
 	}
 
 	b2SolverSet* awakeSet = world->solverSets.data + b2_awakeSet;

@@ -270,6 +270,14 @@ B2GPU_API int b2GpuSolverMaterializeContacts( b2GpuSolver* solver, int colorInde
 											   b2GpuStepResult* result );
 /* The contact at this place is leaving its colour's array (it stopped touching, or is destroyed): its record is void. */
 B2GPU_API void b2GpuSolverDeferredForget( b2GpuSolver* solver, int colorIndex, int index );
+/* The same for the joints: with deferred impulses the fields the stages write in a b2JointSim (the accumulated impulses,
+ * src/*_joint.c b2WarmStart* / b2Solve*) stay on the library's side too, and MaterializeJoints writes them into `count`
+ * consecutive b2JointSim -- the joints at places firstIndex .. of the colour `colorIndex` -- before anything reads or
+ * changes them (the per-type b2*Joint_Get* / Set* functions, b2Joint_GetConstraintForce / Torque), before a joint moves in
+ * its colour's array (src/constraint_graph.c:299-325) or leaves the awake set.  The caller must not defer across a step
+ * with warm starting disabled (b2Prepare*Joint then zeroes the impulses on the host, e.g. src/revolute_joint.c:273-280). */
+B2GPU_API int b2GpuSolverMaterializeJoints( b2GpuSolver* solver, int colorIndex, int firstIndex, void* jointSims, int count );
+B2GPU_API void b2GpuSolverDeferredForgetJoint( b2GpuSolver* solver, int colorIndex, int index );
 /* Every manifold that matters has been materialized (or the host's contacts were replaced wholesale): nothing is pending. */
 B2GPU_API void b2GpuSolverDeferredDone( b2GpuSolver* solver );
 

@@ -130,8 +130,8 @@ def _new_separations(cap: b2.Capture, rng) -> None:
 @pytest.mark.parametrize("name", ["small_pyramid_030", "overflow_025", "falling_hinges_120", "contact_zoo_040"])
 def test_c_abi_chain_of_steps_with_stale_manifolds(oracle, capture_files, name):
 	"""The C-ABI by itself.  A chain of steps through one solver with deferred impulses: the host's contact arrays are handed
-	back to the next step exactly as the previous step left them -- WITHOUT the impulses it computed -- the way the seam does
-	for contacts nobody has read.  The oracle runs the same chain with every impulse stored.  Bodies and joints agree after
+	and joint arrays are handed back to the next step exactly as the previous step left them -- WITHOUT the impulses it
+	computed -- the way the seam does for contacts and joints nobody has read.  The oracle runs the same chain with every impulse stored.  Bodies and joints agree after
 	every step (so the device warm-started from the right impulses); the manifolds agree once they are materialized, and
 	whatever the pack pass had to read in full it materialized by itself."""
 	path = [f for f in capture_files if name in f.name][0]
@@ -146,17 +146,17 @@ def test_c_abi_chain_of_steps_with_stale_manifolds(oracle, capture_files, name):
 			d, r, got = cap_g.make_call()
 			solver.step(d, r)
 			assert np.array_equal(got["states"], want["states"]), f"step {step}: states"
-			for a, b in zip(got["joints"], want["joints"]):
-				assert np.array_equal(a, b), f"step {step}: joint sims"
 			assert np.array_equal(got["joint"], want["joint"]), f"step {step}: joint bits"
 			assert bool(r.hasHitEvents) == bool(r0.hasHitEvents)
 			if cap_g.contact_count > 0:
 				assert solver.deferred_pending()
 			if step == 3:
 				# somebody reads the manifolds in the middle of the run
-				solver.materialize(d, got["contacts"], r)
+				solver.materialize(d, got["contacts"], r, joint_arrays=got["joints"])
 				for a, b in zip(got["contacts"], want["contacts"]):
 					assert np.array_equal(a, b), f"step {step}: contact sims after materialize"
+				for a, b in zip(got["joints"], want["joints"]):
+					assert np.array_equal(a, b), f"step {step}: joint sims after materialize"
 				assert np.array_equal(got["hit"], want["hit"])
 				assert not solver.deferred_pending()
 			# the next step's inputs: the oracle's chain has everything, the device's chain has stale manifolds
@@ -171,9 +171,11 @@ def test_c_abi_chain_of_steps_with_stale_manifolds(oracle, capture_files, name):
 		d0, r0, want = cap_o.make_call()
 		d, r, got = cap_g.make_call()
 		# (make_call copied the inputs: materialize into the copies the last step's descriptor would have pointed at)
-		assert solver.materialize(d, got["contacts"]) == cap_g.contact_count
+		assert solver.materialize(d, got["contacts"], joint_arrays=got["joints"]) == cap_g.contact_count
 		for a, b in zip(got["contacts"], want["contacts"]):
 			assert np.array_equal(a, b), "contact sims at the end of the chain"
+		for a, b in zip(got["joints"], want["joints"]):
+			assert np.array_equal(a, b), "joint sims at the end of the chain"
 
 
 @pytest.mark.parametrize("knob", ["B2GPU_DIRECT_OUT", "B2GPU_KEEP_LISTS", "B2GPU_RESIDENT", "B2GPU_PDL"])

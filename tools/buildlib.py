@@ -137,9 +137,10 @@ INTERPOSED = {
 	"src_contact.o": ["b2Contact_GetData"],
 	"physics_world_gpu.o": ["b2World_Draw"],
 	"src_world_snapshot.o": ["b2World_GetStateHash", "b2World_Snapshot", "b2World_Restore", "b2SerializeWorld", "b2HashWorldStateDeep"],
-	"src_solver_set.o": ["b2TrySleepIsland"],
+	"src_solver_set.o": ["b2TrySleepIsland", "b2TransferJoint"],
+	"src_joint.o": ["b2GetJointSimCheckType", "b2Joint_GetConstraintForce", "b2Joint_GetConstraintTorque"],
 	# ... and the two functions that change a colour's contact array between the narrow phase and the solver (recycledInPlace)
-	"src_constraint_graph.o": ["b2AddContactToGraph", "b2RemoveContactFromGraph"],
+	"src_constraint_graph.o": ["b2AddContactToGraph", "b2RemoveContactFromGraph", "b2RemoveJointFromGraph"],
 }
 OBJCOPY = os.environ.get("OBJCOPY", "objcopy")
 
