@@ -238,6 +238,8 @@ def _bind_harness(lib: ctypes.CDLL) -> ctypes.CDLL:
 	lib.b2h_version.restype = ctypes.c_int
 	lib.b2h_contact_checksum.restype = ctypes.c_uint64
 	lib.b2h_contact_checksum.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_int)]
+	lib.b2h_mut_joint_reactions.restype = ctypes.c_int
+	lib.b2h_mut_joint_reactions.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_float), ctypes.c_int]
 	lib.b2h_snapshot.restype = ctypes.c_int
 	lib.b2h_snapshot.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
 	lib.b2h_restore.restype = ctypes.c_int
@@ -370,6 +372,12 @@ class World:
 		"""(checksum, contact count) of what b2Shape_GetContactData reports for every shape (the impulses an application sees)."""
 		n = ctypes.c_int()
 		return int(self.lib.b2h_contact_checksum(self.handle, ctypes.byref(n))), n.value
+
+	def joint_reactions(self) -> np.ndarray:
+		"""The mutator scene's joints as the application sees them: constraint force and torque of each, motor torque of the first."""
+		buf = (ctypes.c_float * 64)()
+		n = self.lib.b2h_mut_joint_reactions(self.handle, buf, 64)
+		return np.array(buf[:n], dtype=np.float32)
 
 	def snapshot(self) -> tuple:
 		"""(image, step index): b2World_Snapshot."""

@@ -945,6 +945,30 @@ B2H_API uint64_t b2h_contact_checksum( int h, int* contacts )
 	return acc.sum;
 }
 
+/* Reactions of the mutator scene's joints as the application sees them: b2Joint_GetConstraintForce / Torque
+ * (include/box2d/box2d.h:964-967) of every joint, b2RevoluteJoint_GetMotorTorque of the first.  Returns the number of floats. */
+B2H_API int b2h_mut_joint_reactions( int h, float* out, int capacity )
+{
+	b2hWorld* w = s_worlds + h;
+	int n = 0;
+	for ( int i = 0; i < w->mutJointCount && n + 3 <= capacity; ++i )
+	{
+		if ( b2Joint_IsValid( w->mutJoints[i] ) == false )
+		{
+			continue;
+		}
+		b2Vec2 force = b2Joint_GetConstraintForce( w->mutJoints[i] );
+		out[n++] = force.x;
+		out[n++] = force.y;
+		out[n++] = b2Joint_GetConstraintTorque( w->mutJoints[i] );
+	}
+	if ( w->mutJointCount > 0 && n < capacity && b2Joint_IsValid( w->mutJoints[0] ) && b2Joint_GetType( w->mutJoints[0] ) == b2_revoluteJoint )
+	{
+		out[n++] = b2RevoluteJoint_GetMotorTorque( w->mutJoints[0] );
+	}
+	return n;
+}
+
 /* b2World_Snapshot / b2World_Restore (include/box2d/box2d.h:316,329) */
 B2H_API int b2h_snapshot( int h, uint8_t* image, int capacity )
 {

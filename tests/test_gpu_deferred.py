@@ -221,3 +221,19 @@ def test_two_worlds_side_by_side_keep_their_impulses_apart(ref_lib, gpu_host_lib
 				gpu_c.step(5)
 				assert gpu_c.hash() == ref_c.hash()
 		assert gpu_a.hash() == ref_a.hash()
+
+
+def test_joint_reactions_come_out_of_the_arena_joint_by_joint(ref_lib, gpu_host_lib):
+	"""The joints' accumulated impulses are deferred like the contacts': b2Joint_GetConstraintForce / Torque and the per-type
+	getters fetch ONE joint's record when they are asked (b2GetJointSimCheckType interposed), not the world's -- the values
+	are the reference's bits, and asking is not a flush."""
+	with b2.World(ref_lib, "mutator", 4) as ref, b2.World(gpu_host_lib, "mutator", 4) as gpu:
+		for steps in (30, 10, 25):  # (the scene turns motors and springs on at step 32)
+			ref.step(steps)
+			gpu.step(steps)
+			pending, flushes = gpu.deferred_stats()
+			assert pending
+			want, got = ref.joint_reactions(), gpu.joint_reactions()
+			assert want.size >= 12 and np.array_equal(want.view(np.uint32), got.view(np.uint32)), (want, got)
+			assert gpu.deferred_stats() == (True, flushes), "a joint getter flushed the whole world"
+		assert gpu.hash() == ref.hash()
