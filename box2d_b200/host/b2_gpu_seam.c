@@ -1083,7 +1083,13 @@ void b2GpuSeam_SolveConstraints( b2World* world, b2StepContext* context )
 	}
 	void* handles[B2_MAX_WORKERS];
 	int helperCount = world->workerCount - 1;
-	int useful = itemEstimate / 2048; /* a helper that wakes up for less than that only costs */
+	static int itemsPerHelper = 0;
+	if ( itemsPerHelper == 0 )
+	{
+		itemsPerHelper = b2SeamEnvInt( "B2GPU_SEAM_ITEMS_PER_HELPER", 1024 );
+		itemsPerHelper = itemsPerHelper < 1 ? 1 : itemsPerHelper;
+	}
+	int useful = itemEstimate / itemsPerHelper; /* a helper that wakes up for less than that only costs */
 	helperCount = helperCount < useful ? helperCount : useful;
 	{
 		static int maxHelpers = -2;
