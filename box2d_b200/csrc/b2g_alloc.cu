@@ -1,7 +1,9 @@
 // b2g_alloc.cu -- page-locked host allocator for b2SetAllocator (reference include/box2d/base.h:86).
 #include "b2_gpu_solver.h"
+#include "b2g_host.h"
 
 #include <cuda_runtime.h>
+#include <sys/mman.h>
 
 #include <cstdint>
 #include <cstdio>
@@ -15,6 +17,79 @@
 // =================================================================================================================
 // Page-locked host allocator for b2SetAllocator (include/box2d/base.h:86)
 // =================================================================================================================
+// Page-locked host memory on transparent huge pages, where the platform grants them (B2GPU_HUGE_PAGES, default on): 2 MB
+// aligned anonymous memory advised MADV_HUGEPAGE and then registered with the driver, instead of cudaHostAlloc (whose
+// pages are 4 KB ones).  The host passes over the reference's arrays and the staging arenas are streaming loops over
+// tens of megabytes; on a guest every TLB miss of theirs is a two-dimensional page walk.  The device address of such a
+// block must be its host address (the kernels store results through it, b2g_solver.cu "direct outputs"): where the
+// driver says otherwise, or refuses the registration, the block comes from cudaHostAlloc as before.
+namespace
+{
+std::mutex g_registeredMutex;
+std::unordered_map<void*, size_t> g_registered; // blocks of b2gPinnedAlloc that are registrations (the others are cudaHostAlloc's)
+
+} // namespace
+
+bool b2gHugePagesWanted()
+{
+	static const bool wanted = getenv( "B2GPU_HUGE_PAGES" ) == nullptr || atoi( getenv( "B2GPU_HUGE_PAGES" ) ) != 0;
+	return wanted;
+}
+
+void* b2gPinnedAlloc( size_t bytes, unsigned int flags )
+{
+	const size_t page = size_t( 2 ) << 20;
+	if ( b2gHugePagesWanted() && bytes >= page / 2 )
+	{
+		size_t size = ( bytes + page - 1 ) / page * page;
+		void* mem = aligned_alloc( page, size );
+		if ( mem != nullptr )
+		{
+			madvise( mem, size, MADV_HUGEPAGE );
+			void* device = nullptr;
+			if ( cudaHostRegister( mem, size, cudaHostRegisterPortable | cudaHostRegisterMapped ) == cudaSuccess )
+			{
+				if ( cudaHostGetDevicePointer( &device, mem, 0 ) == cudaSuccess && device == mem )
+				{
+					std::lock_guard<std::mutex> lock( g_registeredMutex );
+					g_registered[mem] = size;
+					return mem;
+				}
+				cudaHostUnregister( mem );
+			}
+			cudaGetLastError();
+			free( mem );
+		}
+	}
+	void* mem = nullptr;
+	if ( cudaHostAlloc( &mem, bytes, flags ) != cudaSuccess )
+	{
+		cudaGetLastError();
+		return nullptr;
+	}
+	return mem;
+}
+
+void b2gPinnedFree( void* mem )
+{
+	if ( mem == nullptr )
+	{
+		return;
+	}
+	{
+		std::lock_guard<std::mutex> lock( g_registeredMutex );
+		auto it = g_registered.find( mem );
+		if ( it != g_registered.end() )
+		{
+			g_registered.erase( it );
+			cudaHostUnregister( mem );
+			free( mem );
+			return;
+		}
+	}
+	cudaFreeHost( mem );
+}
+
 namespace
 {
 
@@ -51,9 +126,9 @@ struct PinnedPool
 		void* mem = nullptr;
 		if ( pinned )
 		{
-			if ( cudaHostAlloc( &mem, bytes, cudaHostAllocPortable ) != cudaSuccess )
+			mem = b2gPinnedAlloc( bytes, cudaHostAllocPortable );
+			if ( mem == nullptr )
 			{
-				cudaGetLastError();
 				pinned = false; // no driver: plain memory keeps the host library usable for CPU-only tests
 				mem = nullptr;
 				if ( !warned )
@@ -81,13 +156,12 @@ struct PinnedPool
 		size_t bytes = ( size + page - 1 ) / page * page;
 		void* mem = nullptr;
 		bool locked = false;
-		if ( pinned && cudaHostAlloc( &mem, bytes, cudaHostAllocPortable ) == cudaSuccess )
+		if ( pinned && ( mem = b2gPinnedAlloc( bytes, cudaHostAllocPortable ) ) != nullptr )
 		{
 			locked = true;
 		}
 		else
 		{
-			cudaGetLastError();
 			mem = nullptr;
 			if ( posix_memalign( &mem, 4096, bytes ) != 0 )
 			{
@@ -163,7 +237,7 @@ struct PinnedPool
 		{
 			if ( big->second.second )
 			{
-				cudaFreeHost( mem );
+				b2gPinnedFree( mem );
 			}
 			else
 			{

@@ -6,9 +6,13 @@
 
 #include <cuda_runtime.h>
 
+#include <sys/mman.h>
+
 #include <atomic>
 #include <chrono>
+#include <cstdlib>
 #include <memory>
+#include <new>
 #include <string>
 #include <utility>
 #include <vector>
@@ -70,6 +74,11 @@ template <typename T> struct DeviceBuffer
 	}
 };
 
+// page-locked host memory, on huge pages where possible (b2g_alloc.cu)
+bool b2gHugePagesWanted(); // B2GPU_HUGE_PAGES, default on
+void* b2gPinnedAlloc( size_t bytes, unsigned int flags );
+void b2gPinnedFree( void* mem );
+
 template <typename T> struct PinnedBuffer
 {
 	T* ptr = nullptr;
@@ -88,23 +97,24 @@ template <typename T> struct PinnedBuffer
 		}
 		if ( ptr != nullptr )
 		{
-			cudaFreeHost( ptr );
+			b2gPinnedFree( ptr );
 			ptr = nullptr;
 			capacity = 0;
 		}
-		cudaError_t err = cudaHostAlloc( &ptr, newCapacity * sizeof( T ), cudaHostAllocDefault );
-		if ( err == cudaSuccess )
+		ptr = static_cast<T*>( b2gPinnedAlloc( newCapacity * sizeof( T ), cudaHostAllocDefault ) );
+		if ( ptr == nullptr )
 		{
-			capacity = newCapacity;
+			return cudaErrorMemoryAllocation;
 		}
-		return err;
+		capacity = newCapacity;
+		return cudaSuccess;
 	}
 
 	void release()
 	{
 		if ( ptr != nullptr )
 		{
-			cudaFreeHost( ptr );
+			b2gPinnedFree( ptr );
 		}
 		ptr = nullptr;
 		capacity = 0;
@@ -199,6 +209,57 @@ constexpr int kHomeColors = B2GPU_GRAPH_COLOR_COUNT;
 
 constexpr int kStreamChunk = 16; // records a pack block reserves at a time in the full / dirty-body streams
 
+// The shadows are megabytes of host memory that the pack pass streams through on every step, next to the reference's
+// own arrays.  On 4 KB pages that is a few thousand TLB misses per step, each a two-dimensional page walk when the
+// host is a guest (every box this was measured on): with the address layout of the process as the dice, a third of the
+// runs of many_pyramids packed in 0.055 - 0.09 ms instead of 0.050.  Large shadow arrays are therefore 2 MB aligned and
+// advised to transparent huge pages (the default policy of the boxes is `madvise`); small ones stay plain malloc.
+template <class T> struct b2gHugeAllocator
+{
+	using value_type = T;
+	static constexpr size_t kHugePage = (size_t)2 << 20;
+	b2gHugeAllocator() = default;
+	template <class U> b2gHugeAllocator( const b2gHugeAllocator<U>& )
+	{
+	}
+	T* allocate( size_t n )
+	{
+		size_t bytes = n * sizeof( T );
+		void* mem = nullptr;
+		if ( bytes >= kHugePage / 4 && b2gHugePagesWanted() )
+		{
+			size_t size = ( bytes + kHugePage - 1 ) / kHugePage * kHugePage;
+			mem = aligned_alloc( kHugePage, size );
+			if ( mem != nullptr )
+			{
+				madvise( mem, size, MADV_HUGEPAGE ); // (advice: a refusal costs nothing but the TLB misses)
+			}
+		}
+		else
+		{
+			mem = malloc( bytes > 0 ? bytes : 1 );
+		}
+		if ( mem == nullptr )
+		{
+			throw std::bad_alloc();
+		}
+		return static_cast<T*>( mem );
+	}
+	void deallocate( T* mem, size_t )
+	{
+		free( mem );
+	}
+	template <class U> bool operator==( const b2gHugeAllocator<U>& ) const
+	{
+		return true;
+	}
+	template <class U> bool operator!=( const b2gHugeAllocator<U>& ) const
+	{
+		return false;
+	}
+};
+template <class T> using b2gHugeVector = std::vector<T, b2gHugeAllocator<T>>;
+
 struct b2GpuSolver
 {
 	int device = 0;
@@ -232,7 +293,7 @@ struct b2GpuSolver
 		b2g::ColorRange overflow;
 		const void* buffers[11];
 	} listsOf = {};
-	std::vector<int> prevBins;		   // bin of every awake body in the previous island-mode step
+	b2gHugeVector<int> prevBins;		   // bin of every awake body in the previous island-mode step
 	int prevBinCount = 0;
 	std::atomic<int> binsChanged{ 0 }; // pack pass: some body is in another bin than in the previous step
 	int listsReused = 0;			   // statistics: steps that ran without the scatter kernel
@@ -295,14 +356,14 @@ struct b2GpuSolver
 	bool cacheValid = false;	 // the shadows describe what the device holds (false: the next resident step sends everything)
 	bool cacheUsable = false;	 // ... and this step's pack pass may rely on them
 	int parity = 0;				 // which of the double-buffered arrays this step WRITES (outAll, residentStates)
-	std::vector<b2gShadowContact> shadowContacts; // by home
-	std::vector<b2gShadowImpulses> shadowImpulses; // by home
-	std::vector<b2gShadowHead> shadowHeads;		   // by home
+	b2gHugeVector<b2gShadowContact> shadowContacts; // by home
+	b2gHugeVector<b2gShadowImpulses> shadowImpulses; // by home
+	b2gHugeVector<b2gShadowHead> shadowHeads;		   // by home
 	int homeBase[kHomeColors + 1] = { 0 };		   // first home of every graph colour (persistent layout with spare room)
 	int homeCount[kHomeColors] = { 0 };			   // contacts the colour had in the previous resident step
 	int homeSlot[kHomeColors] = { 0 };			   // ... and the slot its array started at
 	int segHome[kHomeColors] = { 0 };			   // this step: home colour of every contact segment
-	std::vector<float4> shadowStates, shadowBody;  // by awake index: what residentStates[in] / residentBody hold
+	b2gHugeVector<float4> shadowStates, shadowBody;  // by awake index: what residentStates[in] / residentBody hold
 	int shadowBodyCount = 0;
 	DeviceBuffer<float4> table, residentStates[2], residentBody, outOther, fullStream, dirtyStream;
 	PinnedBuffer<float4> hFull, hDirty;
@@ -312,7 +373,7 @@ struct b2GpuSolver
 	int homeTotal = 0;
 	// the same for joints: homes by (graph colour, index in the colour's joint array), shadows = the complete 256-byte record
 	// the device's table holds (the solver's outputs written in by the unpack pass)
-	std::vector<uint8_t> shadowJoints; // [joint homes * kJointStride]
+	b2gHugeVector<uint8_t> shadowJoints; // [joint homes * kJointStride]
 	int jointHomeBase[kHomeColors + 1] = { 0 }, jointHomeCount[kHomeColors] = { 0 }, jointHomeSlot[kHomeColors] = { 0 }, jointSegHome[kHomeColors] = { 0 };
 	int jointHomeTotal = 0;
 	DeviceBuffer<float4> jointTable, jointAssembled, fullJointStream;
@@ -344,9 +405,9 @@ struct b2GpuSolver
 	bool deferPending = false;		// hOutOther holds records that some manifolds have not received
 	uint32_t deferStamp = 0;		// of the pending step (0: never)
 	uint32_t deferNewStamp = 1;		// of the step in flight
-	std::vector<uint32_t> consumedStamp; // by home
+	b2gHugeVector<uint32_t> consumedStamp; // by home
 	// ... and the joints' output records likewise: found by the joint's home, identified by the joint id in the home's shadow
-	std::vector<uint32_t> consumedJointStamp; // by joint home
+	b2gHugeVector<uint32_t> consumedJointStamp; // by joint home
 	bool deferJointsPending = false;
 	bool jointHomesOrdered = true;
 	const float* pendingJointRecords = nullptr; // B2L_JOINT_OUT_FLOATS per joint of the pending step, by its place among the step's joints
@@ -414,6 +475,8 @@ struct b2GpuSolver
 	// increasing order; one caller (the pump) moves the finished prefix over PCIe while the others keep packing, and
 	// publishes how much of the output arena has arrived while the others unpack behind it
 	std::atomic<int> workNext{ 0 };
+	// the CUDA-event time of the kernels is read by whoever runs out of unpack blocks first (b2GpuSolverUnpackWork)
+	std::atomic<int> kernelsSeen{ 0 }, timerClaim{ 0 }, timerDone{ 0 };
 	int workBlocks = 0;
 	int workItems = 0;
 	std::unique_ptr<std::atomic<unsigned char>[]> workDone;

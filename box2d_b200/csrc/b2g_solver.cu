@@ -817,6 +817,9 @@ static void b2gResetWork( b2GpuSolver* s, int itemCount, int blockCount )
 	s->sendThreshold = kTransferQuads;
 	s->blockSent.assign( (size_t)blockCount, 0 );
 	s->workFailed.store( 0, std::memory_order_relaxed );
+	s->kernelsSeen.store( 0, std::memory_order_relaxed );
+	s->timerClaim.store( 0, std::memory_order_relaxed );
+	s->timerDone.store( 0, std::memory_order_relaxed );
 	s->workNext.store( 0, std::memory_order_release );
 }
 
@@ -2034,7 +2037,12 @@ static int b2gEnd( b2GpuSolver* s, b2GpuStepResult* results )
 		const uint32_t* bits = reinterpret_cast<const uint32_t*>( s->hOut.ptr + s->outBits );
 		auto now = std::chrono::steady_clock::now();
 		float h2dMs = 0.0f;
-		cudaEventElapsedTime( &h2dMs, s->evUpload, s->evStart ); // one driver call, not one per world
+		static const bool eagerTimers = getenv( "B2GPU_EAGER_TIMERS" ) != nullptr && atoi( getenv( "B2GPU_EAGER_TIMERS" ) ) != 0; // (A/B)
+		if ( s->trace || eagerTimers )
+		{
+			// (a driver call of 4 - 5 us on the way out of every step, for a number only the trace shows)
+			cudaEventElapsedTime( &h2dMs, s->evUpload, s->evStart );
+		}
 		s->traceMarks[7] = std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count();
 		for ( size_t w = 0; w < s->bodySegs.size(); ++w )
 		{

@@ -1341,6 +1341,7 @@ static int b2gPumpDownloads( b2GpuSolver* s )
 			s->arrivedQuads.store( s->outTotal, std::memory_order_release );
 		}
 		s->controlSeen = true;
+		s->kernelsSeen.store( 1, std::memory_order_release );
 		if ( s->direct && s->arrivedQuads.load( std::memory_order_relaxed ) < s->directEnd )
 		{
 			s->arrivedQuads.store( s->directEnd, std::memory_order_release ); // the kernels stored the body states themselves
@@ -1432,6 +1433,23 @@ extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 		b2GpuSolverUnpackRange( s, begin, end );
 		b2GpuSolverUnpackRange( s, begin2, end2 );
 	}
+	// The CUDA-event time of the kernels (the stage split of b2Profile is scaled to it) is a driver call of 4 - 5 us: the
+	// first caller that runs out of blocks after the kernels were seen to be done reads it while the others still unpack;
+	// failing that, the pump = 1 caller reads it on its way out, as before.
+	auto readKernelTimer = [&]() -> int {
+		cudaError_t err = cudaEventElapsedTime( &s->lastKernelMs, s->evStart, s->evStop );
+		s->timerDone.store( 1, std::memory_order_release );
+		return err == cudaSuccess ? 0 : b2gFail( "kernel timer", err );
+	};
+	static const bool eagerTimers = getenv( "B2GPU_EAGER_TIMERS" ) != nullptr && atoi( getenv( "B2GPU_EAGER_TIMERS" ) ) != 0; // (A/B)
+	if ( pump == 0 && !eagerTimers && s->ran && s->kernelsSeen.load( std::memory_order_acquire ) != 0 && s->timerClaim.exchange( 1, std::memory_order_acq_rel ) == 0 )
+	{
+		if ( readKernelTimer() != 0 )
+		{
+			s->workFailed.store( 1 );
+			return 1;
+		}
+	}
 	if ( pump != 0 )
 	{
 		s->traceMarks[5] = std::chrono::duration<float, std::micro>( std::chrono::steady_clock::now() - s->tBegin ).count();
@@ -1461,7 +1479,20 @@ extern "C" int b2GpuSolverUnpackWork( b2GpuSolver* s, int pump )
 		}
 		if ( s->ran )
 		{
-			B2G_CUDA( cudaEventElapsedTime( &s->lastKernelMs, s->evStart, s->evStop ) );
+			if ( s->timerClaim.exchange( 1, std::memory_order_acq_rel ) == 0 )
+			{
+				if ( readKernelTimer() != 0 )
+				{
+					return 1;
+				}
+			}
+			else
+			{
+				while ( s->timerDone.load( std::memory_order_acquire ) == 0 && s->workFailed.load( std::memory_order_relaxed ) == 0 )
+				{
+					_mm_pause();
+				}
+			}
 		}
 	}
 	return 0;

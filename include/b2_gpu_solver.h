@@ -193,7 +193,7 @@ typedef struct b2GpuStepResult
 	float uploadMs;   /* descriptor -> params, buffer growth, enqueue of the H2D copies */
 	float waitMs;     /* launch + waiting for H2D, kernels and D2H to drain */
 	float scatterMs;  /* writing the impulses back into the reference's manifolds + event bits */
-	float h2dMs;      /* CUDA-event time of the H2D copies */
+	float h2dMs;      /* CUDA-event time of the H2D copies; only read when B2GPU_TRACE is set (a driver call per step), else 0 */
 } b2GpuStepResult;
 
 typedef struct b2GpuSolver b2GpuSolver;

@@ -205,7 +205,7 @@ def build_cuda_lib(verbose: bool = False) -> Path:
 	"""box2d_b200/libb2gpusolver.so: the CUDA kernels + the C-ABI of include/b2_gpu_solver.h (sm_100a only)."""
 	csrc = PKG_DIR / "csrc"
 	sources = sorted(csrc.glob("*.cu"))
-	headers = sorted(csrc.glob("*.cuh")) + sorted((ROOT / "include").glob("*.h"))
+	headers = sorted(csrc.glob("*.cuh")) + sorted(csrc.glob("*.h")) + sorted((ROOT / "include").glob("*.h"))
 	target = PKG_DIR / "libb2gpusolver.so"
 	if _stale(target, [*sources, *headers]):
 		cmd = [NVCC, *NVCC_FLAGS, f"-I{ROOT / 'include'}", f"-I{csrc}", "-shared", "-o", str(target),
