@@ -325,6 +325,13 @@ def _setup_distributed():
 	# the library's own host threads (one-call entry points): the ranks of one box share its cores
 	os.environ.setdefault("B2GPU_HOST_THREADS", str(max(1, (os.cpu_count() or 1) // max(1, world_size))))
 	if world_size > 1:
+		# The ranks of one box share its cores: every rank keeps to its own share of them (set before NCCL and the world's
+		# workers start their threads, which inherit it).  The workers spin across the short gaps between the host passes of
+		# a step; two ranks meeting on one core wait for each other's time slices.  BENCH_PIN_RANKS=0: leave it to the OS.
+		allowed = sorted(os.sched_getaffinity(0))
+		share = len(allowed) // world_size
+		if share >= 2 and os.environ.get("BENCH_PIN_RANKS", "1") != "0":
+			os.sched_setaffinity(0, allowed[local_rank * share:(local_rank + 1) * share])
 		dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 	return world_size, rank, local_rank
 
@@ -469,6 +476,7 @@ def run_scene(args) -> int:
 			"config": scene_config(scene, bodies, contacts, joints, substeps),
 			"details": {"colors": sum(1 for c in counters["colorCounts"][:23] if c > 0),
 						"parallelism": f"{world_size} independent world(s), one per GPU", "host_workers_per_world": workers,
+						"rank_cores": len(os.sched_getaffinity(0)),
 						"l2": "flushed (256 MiB write) between timed iterations" if resident else
 							  "not flushed: kernels timed inside the real steps (awake set changes every step)",
 						"timed": "CUDA events on the solver stream around the step's kernels, inputs resident"},

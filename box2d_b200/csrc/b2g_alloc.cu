@@ -30,16 +30,16 @@ std::unordered_map<void*, size_t> g_registered; // blocks of b2gPinnedAlloc that
 
 } // namespace
 
-bool b2gHugePagesWanted()
+int b2gHugePagesWanted()
 {
-	static const bool wanted = getenv( "B2GPU_HUGE_PAGES" ) == nullptr || atoi( getenv( "B2GPU_HUGE_PAGES" ) ) != 0;
+	static const int wanted = getenv( "B2GPU_HUGE_PAGES" ) == nullptr ? 2 : atoi( getenv( "B2GPU_HUGE_PAGES" ) );
 	return wanted;
 }
 
 void* b2gPinnedAlloc( size_t bytes, unsigned int flags )
 {
 	const size_t page = size_t( 2 ) << 20;
-	if ( b2gHugePagesWanted() && bytes >= page / 2 )
+	if ( b2gHugePagesWanted() >= 2 && bytes >= page / 2 )
 	{
 		size_t size = ( bytes + page - 1 ) / page * page;
 		void* mem = aligned_alloc( page, size );

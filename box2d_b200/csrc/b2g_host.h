@@ -75,7 +75,7 @@ template <typename T> struct DeviceBuffer
 };
 
 // page-locked host memory, on huge pages where possible (b2g_alloc.cu)
-bool b2gHugePagesWanted(); // B2GPU_HUGE_PAGES, default on
+int b2gHugePagesWanted(); // B2GPU_HUGE_PAGES: 0 none, 1 the library's own host arrays, 2 the page-locked blocks as well
 void* b2gPinnedAlloc( size_t bytes, unsigned int flags );
 void b2gPinnedFree( void* mem );
 
@@ -226,7 +226,7 @@ template <class T> struct b2gHugeAllocator
 	{
 		size_t bytes = n * sizeof( T );
 		void* mem = nullptr;
-		if ( bytes >= kHugePage / 4 && b2gHugePagesWanted() )
+		if ( bytes >= kHugePage / 4 && b2gHugePagesWanted() >= 1 )
 		{
 			size_t size = ( bytes + kHugePage - 1 ) / kHugePage * kHugePage;
 			mem = aligned_alloc( kHugePage, size );
