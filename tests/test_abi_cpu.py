@@ -66,10 +66,11 @@ def test_host_library_has_no_cpu_solver_entry():
 	assert "b2SolverTask" not in full, "the CPU solver driver must not be linked into the GPU host library"
 
 
-def test_pinned_allocator_round_trip():
+def _allocator_round_trip():
 	lib = b2.solver_lib()
 	blocks = []
-	for size in (1, 63, 64, 200, 4096, 100000, 5 << 20):
+	# (9 MB: a block of its own, registered and released on its own -- on a GPU box on huge pages, here plain memory)
+	for size in (1, 63, 64, 200, 4096, 100000, 5 << 20, 9 << 20):
 		p = lib.b2GpuHostAlloc(size, 32)
 		assert p and p % 64 == 0
 		ctypes.memset(p, 0xAB, size)
@@ -79,6 +80,20 @@ def test_pinned_allocator_round_trip():
 	again = lib.b2GpuHostAlloc(200, 32)
 	assert again in [p for p, _ in blocks]  # recycled from the free list
 	lib.b2GpuHostFree(again, 200)
+	big = lib.b2GpuHostAlloc(9 << 20, 32)  # (released above: a new registration)
+	assert big and big % 64 == 0
+	ctypes.memset(big, 0xCD, 9 << 20)
+	lib.b2GpuHostFree(big, 9 << 20)
+
+
+def test_pinned_allocator_round_trip():
+	_allocator_round_trip()
+
+
+@pytest.mark.gpu
+def test_pinned_allocator_round_trip_on_the_device_box():
+	"""The same through the page-locked path (b2gPinnedAlloc: registered huge pages, or cudaHostAlloc)."""
+	_allocator_round_trip()
 
 
 def test_island_sizes_from_labels(capture_files):
