@@ -195,6 +195,32 @@ def test_each_shortcut_can_be_turned_off(ref_lib, gpu_host_lib, knob):
 		os.environ.pop(knob, None)
 
 
+@pytest.mark.parametrize("env", [{"B2GPU_HUGE_PAGES": "0"}, {"B2GPU_HUGE_PAGES": "1"}, {"B2GPU_EAGER_TIMERS": "1"}])
+def test_process_wide_knobs_do_not_change_the_result(ref_lib, env):
+	"""Where the host arrays live (page-locked blocks from cudaHostAlloc instead of registered huge pages, B2GPU_HUGE_PAGES) and
+	who reads the kernels' CUDA-event time (B2GPU_EAGER_TIMERS) are read once per process: a fresh process per setting steps
+	two scenes in lockstep with the reference, with the pinned allocator installed as bench.py does."""
+	import subprocess
+	import sys
+
+	code = (
+		"import ctypes\n"
+		"import box2d_b200 as b2\n"
+		"ref = b2._bind_harness(ctypes.CDLL('oracle/_ref/libbox2d_ref.so'))\n"
+		"gpu = b2.host_lib(); gpu.b2GpuSeam_InstallPinnedAllocator()\n"
+		"for scene, steps, every in (('many_pyramids', 18, 6), ('joint_zoo', 40, 8)):\n"
+		"    with b2.World(ref, scene, 4) as r, b2.World(gpu, scene, 4) as g:\n"
+		"        for _ in range(steps // every):\n"
+		"            r.step(every); g.step(every)\n"
+		"            assert g.hash() == r.hash(), scene\n"
+		"        assert g.profile()['constraints'] > 0.0\n"
+		"print('lockstep ok')\n"
+	)
+	root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+	out = subprocess.run([sys.executable, "-c", code], cwd=root, env={**os.environ, **env}, capture_output=True, text=True, timeout=600)
+	assert out.returncode == 0 and "lockstep ok" in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
 def test_two_worlds_side_by_side_keep_their_impulses_apart(ref_lib, gpu_host_lib):
 	"""Every world has its own device solver, output arenas and pending impulses; stepping two worlds alternately and reading
 	one of them must not disturb the other.  Destroying a world with impulses pending and creating another in its slot starts
