@@ -17,7 +17,8 @@
 // =================================================================================================================
 // Page-locked host allocator for b2SetAllocator (include/box2d/base.h:86)
 // =================================================================================================================
-// Page-locked host memory on transparent huge pages, where the platform grants them (B2GPU_HUGE_PAGES, default on): 2 MB
+// Page-locked host memory on transparent huge pages, where the platform grants them (B2GPU_HUGE_PAGES: 2 = here and for
+// the library's own arrays, the default; 1 = only the latter, b2gHugeVector; 0 = neither): 2 MB
 // aligned anonymous memory advised MADV_HUGEPAGE and then registered with the driver, instead of cudaHostAlloc (whose
 // pages are 4 KB ones).  The host passes over the reference's arrays and the staging arenas are streaming loops over
 // tens of megabytes; on a guest every TLB miss of theirs is a two-dimensional page walk.  The device address of such a
